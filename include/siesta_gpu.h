@@ -1,0 +1,230 @@
+/*
+ * siesta_gpu.h — C-ABI of the B200-native SIESTA pattern-query hot path.
+ *
+ * This is the drop-in boundary a thin JNI class binds.
+ * The reference (siesta-tool/SequenceDetectionQueryExecutor) is pure Java and
+ * has no FFI of its own; every entry point below names the Java seam it
+ * replaces (paths relative to the reference's
+ * src/main/java/com/datalab/siesta/queryprocessor/, "S/" =
+ * src/main/java/edu/umass/cs/sase/).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, little-endian, no exceptions.
+ *   - Every int function returns 0 on success or a negative SIESTA_E_* code;
+ *     siesta_last_error() returns a thread-local message for the last failure.
+ *   - Inputs are borrowed for the duration of the call.  The library owns all
+ *     device memory and every result object it returns (free with the
+ *     matching *_free).
+ *   - Activity names and trace ids are mapped to dense integers by the
+ *     caller.  Names must be folded case-insensitively first because the
+ *     engine compares types with equalsIgnoreCase (S/query/State.java:135,
+ *     S/query/AdditionalState.java:45-52).
+ *   - There is no CPU fallback: every compute entry point fails with
+ *     SIESTA_E_CUDA when no sm_100 device is usable.
+ */
+#ifndef SIESTA_GPU_H
+#define SIESTA_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ errors */
+#define SIESTA_OK 0
+#define SIESTA_E_INVALID (-1)     /* bad argument / malformed NFA                */
+#define SIESTA_E_CUDA (-2)        /* CUDA runtime failure, or no device          */
+#define SIESTA_E_UNSUPPORTED (-3) /* NFA shape the GPU engine does not accept    */
+#define SIESTA_E_NOMEM (-4)
+#define SIESTA_E_REFERENCE_THROWS (-5) /* the Java engine would throw (see n_ref_errors) */
+
+const char* siesta_last_error(void);
+
+/* --------------------------------------------------------------------- NFA */
+/* State kinds: ComplexPattern.getStatesWithoutConstraints (model/Patterns/
+ * ComplexPattern.java:216-272): "_"->normal, "+"->kleeneClosure,
+ * "*"->kleeneClosure*, "!"->negative, "||"->or. */
+#define SIESTA_STATE_NORMAL 0
+#define SIESTA_STATE_KLEENE_PLUS 1
+#define SIESTA_STATE_KLEENE_STAR 2
+#define SIESTA_STATE_NEGATIVE 3
+#define SIESTA_STATE_OR 4
+
+#define SIESTA_ATTR_POSITION 0
+#define SIESTA_ATTR_TIMESTAMP 1
+#define SIESTA_OP_LE 0 /* "within"  -> attr <= $ref.attr + c (SIESTAPattern.java:136,142) */
+#define SIESTA_OP_GE 1 /* otherwise -> attr >= $ref.attr + c (SIESTAPattern.java:138,144) */
+
+#define SIESTA_MAX_STATES 8
+#define SIESTA_MAX_OR_TYPES 8
+#define SIESTA_MAX_PREDS 4
+
+/* One predicate " attr <=|>= $<ref_state+1>.attr + constant "
+ * (model/Patterns/SIESTAPattern.java:131-149).  SIESTA attaches the same list
+ * to the begin edge and, for both Kleene kinds, to the take edge; never to
+ * the proceed edge (ComplexPattern.java:200-208), so one list per state is
+ * the complete description. */
+typedef struct siesta_pred {
+    int32_t attr;      /* SIESTA_ATTR_*                         */
+    int32_t op;        /* SIESTA_OP_*                           */
+    int32_t ref_state; /* 0-based index of the referenced state */
+    int32_t reserved;
+    int64_t constant;  /* >= 0; seconds for timestamp           */
+} siesta_pred;
+
+typedef struct siesta_state {
+    int32_t kind;    /* SIESTA_STATE_*                                     */
+    int32_t n_types; /* 1, or >1 for an "or" state                         */
+    int32_t types[SIESTA_MAX_OR_TYPES]; /* dense activity ids              */
+    int32_t n_preds;
+    int32_t reserved;
+    siesta_pred preds[SIESTA_MAX_PREDS];
+} siesta_state;
+
+typedef struct siesta_nfa {
+    int32_t n_states;
+    int32_t reserved;
+    siesta_state states[SIESTA_MAX_STATES];
+} siesta_nfa;
+
+/* ------------------------------------------------------- pattern compiler */
+/* Replaces ComplexPattern.getNfa / getNfaWithoutConstraints
+ * (ComplexPattern.java:194-214, 274-283), SimplePattern.getNfa
+ * (SimplePattern.java:96-104) and SIESTAPattern.generatePredicates
+ * (SIESTAPattern.java:131-149).  Host only. */
+#define SIESTA_SYM_NORMAL 0 /* "_" (and "") */
+#define SIESTA_SYM_PLUS 1   /* "+"  */
+#define SIESTA_SYM_STAR 2   /* "*"  */
+#define SIESTA_SYM_NOT 3    /* "!"  */
+#define SIESTA_SYM_OR 4     /* "||" */
+
+typedef struct siesta_event_symbol {
+    int32_t activity; /* dense activity id                    */
+    int32_t position; /* EventSymbol.position in the pattern  */
+    int32_t symbol;   /* SIESTA_SYM_*                         */
+} siesta_event_symbol;
+
+#define SIESTA_CONSTRAINT_GAP 0
+#define SIESTA_CONSTRAINT_TIME 1
+#define SIESTA_METHOD_WITHIN 0
+#define SIESTA_METHOD_ATLEAST 1
+#define SIESTA_GRAN_SECONDS 0
+#define SIESTA_GRAN_MINUTES 1
+#define SIESTA_GRAN_HOURS 2
+
+typedef struct siesta_constraint {
+    int32_t pos_a, pos_b; /* state indices, pos_a < pos_b (Constraint.java:98-100) */
+    int32_t kind;         /* SIESTA_CONSTRAINT_*                                    */
+    int32_t method;       /* SIESTA_METHOD_*                                        */
+    int64_t value;
+    int32_t granularity;  /* SIESTA_GRAN_* (time constraints only)                  */
+    int32_t reserved;
+} siesta_constraint;
+
+int siesta_pattern_compile(const siesta_event_symbol* symbols, int32_t n_symbols,
+                           const siesta_constraint* constraints, int32_t n_constraints,
+                           int32_t only_appearances, siesta_nfa* out);
+
+/* ------------------------------------------------------------ ctx and log */
+typedef struct siesta_ctx siesta_ctx;
+typedef struct siesta_log siesta_log;
+
+/* One ctx per (process, device).  Multi-GPU = one ctx per GPU; the traces
+ * shard by contiguous trace range and the exchange step (match-list
+ * all-gather, count all-reduce) runs over NCCL one level up. */
+int siesta_init(int32_t device_id, siesta_ctx** out);
+void siesta_shutdown(siesta_ctx* ctx);
+
+/* CSR event log: trace_off[T+1] (int64), act[E] (int32 dense activity id),
+ * ts_ms[E] (int64 epoch milliseconds, sorted inside each trace).  Replaces the
+ * Map<String, List<Event>> the reference materialises per request
+ * (SaseConnection/SaseConnector.java:48-51, storage/repositories/
+ * SparkDatabaseRepository.java:94-107).  Copies host -> device. */
+int siesta_log_load(siesta_ctx* ctx, const int64_t* trace_off, const int32_t* act,
+                    const int64_t* ts_ms, int64_t n_traces, int64_t n_events,
+                    int32_t n_activities, siesta_log** out);
+/* Same, over device memory the caller owns and keeps alive (torch tensors). */
+int siesta_log_wrap_device(siesta_ctx* ctx, const int64_t* d_trace_off, const int32_t* d_act,
+                           const int64_t* d_ts_ms, int64_t n_traces, int64_t n_events,
+                           int32_t n_activities, int32_t max_trace_len, siesta_log** out);
+void siesta_log_free(siesta_log* log);
+int64_t siesta_log_n_traces(const siesta_log* log);
+int64_t siesta_log_n_events(const siesta_log* log);
+
+/* -------------------------------------------------------------- detection */
+/* flags */
+#define SIESTA_F_RETURN_ALL 1u       /* Occurrences.clearOccurrences(true) (model/Occurrences.java:58-89) */
+#define SIESTA_F_ONLY_APPEARANCES 2u /* ignore predicates (SaseConnector.java:156-158)                     */
+#define SIESTA_F_MODE_HEAD 4u        /* keep Engine.createNewRun's trailing block (S/engine/Engine.java:983-996);
+                                        default is the mode the reference's own tests pin      */
+#define SIESTA_F_EVT_POS 8u          /* events are EventPos: id = true position, timestamp = list index
+                                        (model/Utils/Utils.java:59-62); default EventTs/EventBoth:
+                                        id = list index, timestamp = (t - t0)/1000 s (Utils.java:51-58)    */
+#define SIESTA_F_NO_EVENT_COLUMNS 16u /* return only trace_idx/occ_off/ev_off/ev_pos                       */
+
+/* Result of SaseConnector.evaluate + Occurrences.clearOccurrences, CSR-shaped.
+ * Host memory owned by the library. */
+typedef struct siesta_matches {
+    int64_t n_traces;          /* traces with >= 1 match                             */
+    int64_t n_occurrences;     /* selected occurrences over all traces               */
+    int64_t n_events;          /* events over all selected occurrences               */
+    int64_t n_matches_emitted; /* engine matches before selection (Profiling.numberOfMatches) */
+    int64_t n_ref_errors;      /* traces on which the Java engine would throw        */
+    int64_t* trace_idx;        /* [n_traces] ascending                               */
+    int64_t* occ_off;          /* [n_traces+1] -> occurrence range of a trace        */
+    int64_t* ev_off;           /* [n_occurrences+1] -> event range of an occurrence  */
+    int32_t* ev_pos;           /* [n_events] index of the event inside its trace     */
+    int32_t* ev_rank;          /* [n_events] index in the list filtered to the pattern's types */
+    int32_t* ev_act;           /* [n_events] activity id                             */
+    int64_t* ev_ts_ms;         /* [n_events] SaseEvent.getEventBoth timestamp: rel_s*1000 + t0 (SaseEvent.java:94-106) */
+    int64_t* err_trace_idx;    /* [n_ref_errors] ascending                           */
+    double kernel_ms;          /* device time of the verification kernels            */
+} siesta_matches;
+
+/* Replaces SaseConnector.evaluate(pattern, events, onlyAppearances) followed by
+ * occurrences.forEach(clearOccurrences(returnAll))
+ * (SaseConnector.java:48-76; QueryPlanPatternDetection.java:121-122).
+ * cand = NULL verifies every trace of the log; otherwise cand[n_cand] are
+ * ascending trace indices (the output of siesta_intersect).
+ * Re-entrant: concurrent calls on one log from different threads are safe. */
+int siesta_detect(siesta_log* log, const siesta_nfa* nfa, const int64_t* cand, int64_t n_cand,
+                  uint32_t flags, siesta_matches** out);
+void siesta_matches_free(siesta_matches* m);
+
+/* Literal SaseConnector.evaluate signature: the caller hands the events of
+ * this request (host CSR); equals log_load + detect + log_free. */
+int siesta_evaluate_events(siesta_ctx* ctx, const int64_t* trace_off, const int32_t* act,
+                           const int64_t* ts_ms, int64_t n_traces, int64_t n_events,
+                           int32_t n_activities, const siesta_nfa* nfa, uint32_t flags,
+                           siesta_matches** out);
+
+/* Device-level variant used by the torch/NCCL layer: results stay in HBM.
+ * All pointers are device pointers owned by the library until
+ * siesta_dev_matches_free; `stream` is a cudaStream_t (NULL = the ctx stream). */
+typedef struct siesta_dev_matches {
+    int64_t n_traces, n_occurrences, n_events, n_matches_emitted, n_ref_errors;
+    int64_t* d_trace_idx;
+    int64_t* d_occ_off;
+    int64_t* d_ev_off;
+    int32_t* d_ev_pos;
+    int32_t* d_ev_rank;
+    int32_t* d_ev_act;
+    int64_t* d_ev_ts_ms;
+    int64_t* d_err_trace_idx;
+    double kernel_ms;
+    void* impl;
+} siesta_dev_matches;
+
+int siesta_detect_device(siesta_log* log, const siesta_nfa* nfa, const int64_t* d_cand,
+                         int64_t n_cand, uint32_t flags, void* stream, siesta_dev_matches* out);
+void siesta_dev_matches_free(siesta_dev_matches* m);
+
+/* Number of kernels this library has launched in this process (bench.py's
+ * gpu_launches). */
+int64_t siesta_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIESTA_GPU_H */

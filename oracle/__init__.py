@@ -1,0 +1,90 @@
+"""CPU ORACLE — test infrastructure, not the product.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this package.  It wraps oracle/_build/liboracle.so, a literal C++ restatement of the
+reference's verification engine (oracle/sase_oracle.cpp) and counting paths
+(oracle/counting_oracle.cpp).  Pinned against the reference's own known-answer tests by
+tests/test_oracle_kat.py.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from sequencedetectionqueryexecutor_b200 import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in ("sase_oracle.cpp", "counting_oracle.cpp", "Makefile")]
+    srcs.append(os.path.join(_HERE, "..", "include", "siesta_gpu.h"))
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        try:
+            build()
+        except Exception:
+            if not os.path.exists(_LIB_PATH):
+                raise
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.oracle_run_stream.restype = C.c_int
+        _lib.oracle_detect.restype = C.c_int
+        _lib.oracle_free.argtypes = [C.c_void_p]
+        _lib.oracle_matches_free.argtypes = [C.POINTER(_abi.Matches)]
+    return _lib
+
+
+def _p(a, ct):
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+def run_stream(nfa, types, ids, ts, flags=0):
+    """Engine-level: one explicit stream -> (status, [match event-id lists] in emission order)."""
+    L = lib()
+    types = np.ascontiguousarray(types, dtype=np.int32)
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    ts = np.ascontiguousarray(ts, dtype=np.int32)
+    status, n = C.c_int32(0), C.c_int64(0)
+    off, mid = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)()
+    rc = L.oracle_run_stream(C.byref(nfa), _p(types, C.c_int32), _p(ids, C.c_int32), _p(ts, C.c_int32),
+                             C.c_int32(len(types)), C.c_uint32(flags), C.byref(status), C.byref(n),
+                             C.byref(off), C.byref(mid))
+    assert rc == 0
+    offs = [off[i] for i in range(n.value + 1)]
+    matches = [[mid[j] for j in range(offs[i], offs[i + 1])] for i in range(n.value)]
+    L.oracle_free(off)
+    L.oracle_free(mid)
+    return status.value, matches
+
+
+def detect(trace_off, act, ts_ms, nfa, cand=None, flags=0, n_threads=1):
+    """SaseConnector.evaluate + clearOccurrences over a CSR log -> _abi.MatchResult."""
+    L = lib()
+    trace_off = np.ascontiguousarray(trace_off, dtype=np.int64)
+    act = np.ascontiguousarray(act, dtype=np.int32)
+    ts_ms = np.ascontiguousarray(ts_ms, dtype=np.int64)
+    T = len(trace_off) - 1
+    if cand is not None:
+        cand = np.ascontiguousarray(cand, dtype=np.int64)
+        cp, nc = _p(cand, C.c_int64), len(cand)
+    else:
+        cp, nc = None, 0
+    out = C.POINTER(_abi.Matches)()
+    rc = L.oracle_detect(_p(trace_off, C.c_int64), _p(act, C.c_int32), _p(ts_ms, C.c_int64), C.c_int64(T),
+                         C.byref(nfa), cp, C.c_int64(nc), C.c_uint32(flags), C.c_int32(n_threads), C.byref(out))
+    if rc != 0:
+        raise ValueError(f"oracle_detect failed: {rc}")
+    res = _abi.MatchResult.from_struct(out.contents)
+    L.oracle_matches_free(out)
+    return res

@@ -1,0 +1,143 @@
+"""ctypes mirror of include/siesta_gpu.h (struct layouts and constants only)."""
+import ctypes as C
+
+MAX_STATES = 8
+MAX_OR_TYPES = 8
+MAX_PREDS = 4
+
+STATE_NORMAL, STATE_KLEENE_PLUS, STATE_KLEENE_STAR, STATE_NEGATIVE, STATE_OR = range(5)
+ATTR_POSITION, ATTR_TIMESTAMP = 0, 1
+OP_LE, OP_GE = 0, 1
+
+SYM_NORMAL, SYM_PLUS, SYM_STAR, SYM_NOT, SYM_OR = range(5)
+CONSTRAINT_GAP, CONSTRAINT_TIME = 0, 1
+METHOD_WITHIN, METHOD_ATLEAST = 0, 1
+GRAN_SECONDS, GRAN_MINUTES, GRAN_HOURS = 0, 1, 2
+
+F_RETURN_ALL = 1
+F_ONLY_APPEARANCES = 2
+F_MODE_HEAD = 4
+F_EVT_POS = 8
+F_NO_EVENT_COLUMNS = 16
+
+E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMEM, E_REFERENCE_THROWS = -1, -2, -3, -4, -5
+
+
+class Pred(C.Structure):
+    _fields_ = [("attr", C.c_int32), ("op", C.c_int32), ("ref_state", C.c_int32),
+                ("reserved", C.c_int32), ("constant", C.c_int64)]
+
+
+class State(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_types", C.c_int32), ("types", C.c_int32 * MAX_OR_TYPES),
+                ("n_preds", C.c_int32), ("reserved", C.c_int32), ("preds", Pred * MAX_PREDS)]
+
+
+class Nfa(C.Structure):
+    _fields_ = [("n_states", C.c_int32), ("reserved", C.c_int32), ("states", State * MAX_STATES)]
+
+
+class EventSymbolC(C.Structure):
+    _fields_ = [("activity", C.c_int32), ("position", C.c_int32), ("symbol", C.c_int32)]
+
+
+class ConstraintC(C.Structure):
+    _fields_ = [("pos_a", C.c_int32), ("pos_b", C.c_int32), ("kind", C.c_int32), ("method", C.c_int32),
+                ("value", C.c_int64), ("granularity", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Matches(C.Structure):
+    _fields_ = [("n_traces", C.c_int64), ("n_occurrences", C.c_int64), ("n_events", C.c_int64),
+                ("n_matches_emitted", C.c_int64), ("n_ref_errors", C.c_int64),
+                ("trace_idx", C.POINTER(C.c_int64)), ("occ_off", C.POINTER(C.c_int64)),
+                ("ev_off", C.POINTER(C.c_int64)), ("ev_pos", C.POINTER(C.c_int32)),
+                ("ev_rank", C.POINTER(C.c_int32)), ("ev_act", C.POINTER(C.c_int32)),
+                ("ev_ts_ms", C.POINTER(C.c_int64)), ("err_trace_idx", C.POINTER(C.c_int64)),
+                ("kernel_ms", C.c_double)]
+
+
+class DevMatches(C.Structure):
+    _fields_ = [("n_traces", C.c_int64), ("n_occurrences", C.c_int64), ("n_events", C.c_int64),
+                ("n_matches_emitted", C.c_int64), ("n_ref_errors", C.c_int64),
+                ("d_trace_idx", C.c_void_p), ("d_occ_off", C.c_void_p), ("d_ev_off", C.c_void_p),
+                ("d_ev_pos", C.c_void_p), ("d_ev_rank", C.c_void_p), ("d_ev_act", C.c_void_p),
+                ("d_ev_ts_ms", C.c_void_p), ("d_err_trace_idx", C.c_void_p),
+                ("kernel_ms", C.c_double), ("impl", C.c_void_p)]
+
+
+def make_nfa(states):
+    """states: list of dicts {kind, types:[...], preds:[(attr, op, ref_state, constant), ...]}"""
+    if not 1 <= len(states) <= MAX_STATES:
+        raise ValueError(f"NFA must have 1..{MAX_STATES} states")
+    nfa = Nfa()
+    nfa.n_states = len(states)
+    for i, s in enumerate(states):
+        st = nfa.states[i]
+        st.kind = s["kind"]
+        types = list(s["types"])
+        if not 1 <= len(types) <= MAX_OR_TYPES:
+            raise ValueError("bad type list")
+        st.n_types = len(types)
+        for k, t in enumerate(types):
+            st.types[k] = t
+        preds = list(s.get("preds", ()))
+        if len(preds) > MAX_PREDS:
+            raise ValueError("too many predicates on one state")
+        st.n_preds = len(preds)
+        for k, (attr, op, ref, const) in enumerate(preds):
+            st.preds[k].attr, st.preds[k].op, st.preds[k].ref_state, st.preds[k].constant = attr, op, ref, const
+    return nfa
+
+
+def _arr(ptr, n, dtype):
+    import numpy as np
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+class MatchResult:
+    """Host copy of a siesta_matches (CSR of selected occurrences per matching trace)."""
+
+    __slots__ = ("n_traces", "n_occurrences", "n_events", "n_matches_emitted", "n_ref_errors", "trace_idx",
+                 "occ_off", "ev_off", "ev_pos", "ev_rank", "ev_act", "ev_ts_ms", "err_trace_idx", "kernel_ms")
+
+    @classmethod
+    def from_struct(cls, m):
+        import numpy as np
+        r = cls()
+        r.n_traces, r.n_occurrences, r.n_events = m.n_traces, m.n_occurrences, m.n_events
+        r.n_matches_emitted, r.n_ref_errors, r.kernel_ms = m.n_matches_emitted, m.n_ref_errors, m.kernel_ms
+        r.trace_idx = _arr(m.trace_idx, m.n_traces, np.int64)
+        r.occ_off = _arr(m.occ_off, m.n_traces + 1, np.int64)
+        r.ev_off = _arr(m.ev_off, m.n_occurrences + 1, np.int64)
+        r.ev_pos = _arr(m.ev_pos, m.n_events, np.int32) if m.ev_pos else None
+        r.ev_rank = _arr(m.ev_rank, m.n_events, np.int32) if m.ev_rank else None
+        r.ev_act = _arr(m.ev_act, m.n_events, np.int32) if m.ev_act else None
+        r.ev_ts_ms = _arr(m.ev_ts_ms, m.n_events, np.int64) if m.ev_ts_ms else None
+        r.err_trace_idx = _arr(m.err_trace_idx, m.n_ref_errors, np.int64)
+        return r
+
+    def occurrences_of(self, i):
+        """List of occurrences (each a list of in-trace positions) of the i-th matching trace."""
+        out = []
+        for o in range(self.occ_off[i], self.occ_off[i + 1]):
+            out.append(self.ev_pos[self.ev_off[o]:self.ev_off[o + 1]].tolist())
+        return out
+
+    def as_dict(self):
+        return {int(t): self.occurrences_of(i) for i, t in enumerate(self.trace_idx)}
+
+    def same_as(self, other, columns=("ev_pos", "ev_rank", "ev_act", "ev_ts_ms")):
+        import numpy as np
+        keys = ["trace_idx", "occ_off", "ev_off", "err_trace_idx"] + list(columns)
+        for k in ("n_traces", "n_occurrences", "n_events", "n_matches_emitted", "n_ref_errors"):
+            if getattr(self, k) != getattr(other, k):
+                return False, k
+        for k in keys:
+            a, b = getattr(self, k), getattr(other, k)
+            if a is None or b is None:
+                continue
+            if a.shape != b.shape or not np.array_equal(a, b):
+                return False, k
+        return True, ""
