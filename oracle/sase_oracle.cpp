@@ -36,6 +36,7 @@ namespace {
 struct RefThrow {
     const char* what;
 };
+thread_local const char* g_last_throw = "";
 
 /* SaseEvent (J/SaseConnection/SaseEvent.java:18-153): id == position. */
 struct OEvent {
@@ -89,6 +90,12 @@ struct Nfa {
         return false;
     }
     int n_edges(int s) const { return is_kleene(d.states[s].kind) ? 3 : 1; }
+    /* nfa.getStates(i): a run whose cursor moved past a trailing negative state indexes states[size]
+     * (Run.java:203 increments currentState unconditionally) -> ArrayIndexOutOfBounds */
+    int kind_at(int s) const {
+        if (s < 0 || s >= size()) throw RefThrow{"getStates(currentState) out of bounds (Engine.java:656,691,1104)"};
+        return d.states[s].kind;
+    }
 };
 
 struct Run {
@@ -270,7 +277,8 @@ struct Engine {
         int prevId = r.getPreviousEventId();
         auto it = buffer.find(prevId);
         const OEvent* prev = it == buffer.end() ? nullptr : it->second;
-        if (r.state[cur] == 0 && nfa.d.states[cur].kind == SIESTA_STATE_KLEENE_PLUS) return false;
+        int kind = nfa.kind_at(cur); /* State s = nfa.getStates(currentState), Engine.java:1210 */
+        if (r.state[cur] == 0 && kind == SIESTA_STATE_KLEENE_PLUS) return false;
         return evalEdge(cur, 2, prev, r);
     }
     /* Engine.checkPredicatesForNextState, Engine.java:1165-1180 */
@@ -285,7 +293,7 @@ struct Engine {
     /* Engine.checkPredicate, Engine.java:1102-1163 */
     bool checkPredicate(const OEvent& e, const Run& r) const {
         int cur = r.cur;
-        int kind = nfa.d.states[cur].kind;
+        int kind = nfa.kind_at(cur);
         if (kind == SIESTA_STATE_NEGATIVE) {
             if (nfa.check_type(cur, e)) return evalEdge(cur, 0, &e, r);
             else if (nfa.size() > cur + 1) return checkPredicatesForNextState(cur, e, r);
@@ -313,7 +321,7 @@ struct Engine {
     void evaluateEventForSkipTillNext(const OEvent& e, RunP rp) {
         Run& r = *rp;
         int ts = r.cur;
-        if (nfa.d.states[ts].kind == SIESTA_STATE_KLEENE_STAR && !r.kinit && checkProceed(r) &&
+        if (nfa.kind_at(ts) == SIESTA_STATE_KLEENE_STAR && !r.kinit && checkProceed(r) &&
             nfa.d.states[ts].types[0] == e.type) {
             RunP nr = cloneRun(r);
             nr->proceed();
@@ -332,7 +340,7 @@ struct Engine {
                 }
             }
             ts = r.cur;
-            if (is_kleene(nfa.d.states[ts].kind)) {
+            if (is_kleene(nfa.kind_at(ts))) {
                 if (checkProceed(r)) {
                     RunP nr = cloneRun(r);
                     nr->kinit = true;
@@ -373,7 +381,7 @@ struct Engine {
                     RunP nr = std::make_shared<Run>();
                     nr->initialize(&nfa);
                     nr->addEvent(e);
-                    if (nfa.d.states[nr->cur].kind == SIESTA_STATE_KLEENE_STAR && checkProceed(*nr)) nr->proceed();
+                    if (nfa.kind_at(nr->cur) == SIESTA_STATE_KLEENE_STAR && checkProceed(*nr)) nr->proceed();
                     if (nr->checkMatch()) outputMatch(*nr);
                     else activeRuns.push_back(nr);
                 }
@@ -501,9 +509,10 @@ void run_trace(const Nfa& nfa, const std::vector<OEvent>& stream, uint32_t flags
         std::vector<int> sel = clearOccurrences(eng.matches, (flags & SIESTA_F_RETURN_ALL) != 0, (flags & SIESTA_F_EVT_POS) != 0);
         for (int i : sel) res.selected.push_back(eng.matches[i].events);
         res.status = 1;
-    } catch (const RefThrow&) {
+    } catch (const RefThrow& rt) {
         res = TraceResult();
         res.status = 2;
+        g_last_throw = rt.what;
     }
 }
 
@@ -551,6 +560,9 @@ int oracle_run_stream(const siesta_nfa* nfa_desc, const int32_t* type, const int
 }
 
 void oracle_free(void* p) { std::free(p); }
+
+/* message of the last modelled Java exception on this thread (debugging aid) */
+const char* oracle_last_throw(void) { return g_last_throw; }
 
 /* SaseConnector.evaluate + clearOccurrences over a CSR log; fills the same
  * siesta_matches layout the product returns.  n_threads > 1 splits the trace

@@ -1,0 +1,64 @@
+"""Loads libsiesta_gpu.so (built in-tree by csrc/Makefile) and declares the C-ABI of include/siesta_gpu.h.
+
+There is no CPU fallback: a missing library or a missing sm_100 device raises."""
+import ctypes as C
+import os
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsiesta_gpu.so")
+_lib = None
+
+EXPORTS = [
+    "siesta_last_error", "siesta_pattern_compile", "siesta_init", "siesta_shutdown", "siesta_log_load",
+    "siesta_log_wrap_device", "siesta_log_free", "siesta_log_n_traces", "siesta_log_n_events", "siesta_detect",
+    "siesta_matches_free", "siesta_evaluate_events", "siesta_detect_device", "siesta_dev_matches_free",
+    "siesta_kernel_launches",
+]
+
+
+class SiestaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libsiesta_gpu error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+                          "(python __graft_entry__.py build). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    i32, i64, u32, vp = C.c_int32, C.c_int64, C.c_uint32, C.c_void_p
+    P = C.POINTER
+    L.siesta_last_error.restype = C.c_char_p
+    L.siesta_pattern_compile.argtypes = [P(_abi.EventSymbolC), i32, P(_abi.ConstraintC), i32, i32, P(_abi.Nfa)]
+    L.siesta_init.argtypes = [i32, P(vp)]
+    L.siesta_shutdown.argtypes = [vp]
+    L.siesta_shutdown.restype = None
+    L.siesta_log_load.argtypes = [vp, vp, vp, vp, i64, i64, i32, P(vp)]
+    L.siesta_log_wrap_device.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, P(vp)]
+    L.siesta_log_free.argtypes = [vp]
+    L.siesta_log_free.restype = None
+    L.siesta_log_n_traces.argtypes = [vp]
+    L.siesta_log_n_traces.restype = i64
+    L.siesta_log_n_events.argtypes = [vp]
+    L.siesta_log_n_events.restype = i64
+    L.siesta_detect.argtypes = [vp, P(_abi.Nfa), vp, i64, u32, P(P(_abi.Matches))]
+    L.siesta_matches_free.argtypes = [P(_abi.Matches)]
+    L.siesta_matches_free.restype = None
+    L.siesta_evaluate_events.argtypes = [vp, vp, vp, vp, i64, i64, i32, P(_abi.Nfa), u32, P(P(_abi.Matches))]
+    L.siesta_detect_device.argtypes = [vp, P(_abi.Nfa), vp, i64, u32, vp, P(_abi.DevMatches)]
+    L.siesta_dev_matches_free.argtypes = [P(_abi.DevMatches)]
+    L.siesta_dev_matches_free.restype = None
+    L.siesta_kernel_launches.restype = i64
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise SiestaError(rc, lib().siesta_last_error().decode("utf-8", "replace"))

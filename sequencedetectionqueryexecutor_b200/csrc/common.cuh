@@ -1,0 +1,67 @@
+// common.cuh — shared host/device declarations of libsiesta_gpu (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/siesta_gpu.h"
+
+namespace siesta {
+
+void set_error(const std::string& msg);
+extern std::atomic<long long> g_kernel_launches;
+
+#define SIESTA_CUDA_OK(expr)                                                                      \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            ::siesta::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+            return SIESTA_E_CUDA;                                                                 \
+        }                                                                                         \
+    } while (0)
+
+#define SIESTA_LAUNCHED() (::siesta::g_kernel_launches.fetch_add(1, std::memory_order_relaxed))
+
+struct Ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+};
+
+// CSR event log resident in HBM.
+struct Log {
+    Ctx* ctx = nullptr;
+    const int64_t* d_trace_off = nullptr;  // [T+1]
+    const int32_t* d_act = nullptr;        // [E]
+    const int64_t* d_ts_ms = nullptr;      // [E]
+    int64_t n_traces = 0, n_events = 0;
+    int32_t n_activities = 0;
+    int32_t max_trace_len = 0;
+    bool owns = false;
+};
+
+// Device-side NFA: SIESTA's State[] flattened (S/query/State.java, AdditionalState.java).
+struct DevNfa {
+    int32_t n_states;
+    uint32_t init_st;   // Run.initializeRun: negative -> 2, kleeneClosure* -> 3 (S/engine/Run.java:146-155), 2 bits/state
+    uint32_t all2;      // st field of a complete run: every state == 2 (Run.checkMatch, Run.java:181-191)
+    uint8_t kind[SIESTA_MAX_STATES];
+    uint8_t n_preds[SIESTA_MAX_STATES];
+    uint8_t has_vv;     // bit k: some predicate references state k (NFA.hasValueVector, S/query/NFA.java:462-469)
+    uint8_t need_vv;
+    uint8_t any_kleene;
+    uint8_t pad;
+    uint8_t p_attr[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];
+    uint8_t p_op[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];
+    uint8_t p_ref[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];
+    int64_t p_c[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];
+};
+
+int validate_nfa(const siesta_nfa* nfa, uint32_t flags, DevNfa* out);
+void build_lut(const siesta_nfa* nfa, const DevNfa& dn, int32_t n_activities, uint32_t flags, std::vector<uint16_t>& lut,
+               int* needs_ts, int* n_positive);
+
+}  // namespace siesta

@@ -1,0 +1,622 @@
+// detect.cu — kernel K1: per-trace pattern verification over a CSR event log (sm_100a).
+//
+// Replaces SaseConnector.evaluate + Occurrences.clearOccurrences
+// (J/SaseConnection/SaseConnector.java:48-76, J/model/Occurrences.java:58-89).
+//
+// Launch shape: persistent CTAs of NT=128 threads (grid = SMs x resident CTAs), each looping
+// over tiles of NT traces.
+//   phase A (warp-cooperative, coalesced): a warp walks its 32 traces one after the other;
+//           lanes read consecutive int32 activity ids (128 B per warp load), look the pattern's
+//           state mask up, ballot, and compact the events that belong to the pattern into the
+//           trace's shared-memory slot (the reference's Trace.clearTrace / Utils.transformToSaseEvents).
+//           Timestamps (int64 ms) are loaded only for events that survive the filter.
+//   phase B (thread per trace): RunEngine over the compacted events (detect_engine.cuh).
+//   phase C: block scan of output sizes, one atomicAdd per CTA to reserve staging space, write.
+// A final gather orders the staged occurrences by trace index (dense per-candidate counts +
+// device scans), so the result is deterministic.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "detect_engine.cuh"
+
+namespace siesta {
+
+constexpr int NT = 128;  // threads per CTA == traces per tile
+
+struct DetectParams {
+    const int64_t* trace_off;
+    const int32_t* act;
+    const int64_t* ts_ms;
+    const int64_t* cand;      // candidate trace indices or nullptr (= identity)
+    const int64_t* work;      // indices into the candidate list to process, or nullptr (= all)
+    int64_t n_work;           // number of traces this launch verifies
+    const uint16_t* lut;      // [n_act] smask | fmask << 8
+    int32_t n_act;
+    uint32_t flags;
+    int32_t needs_ts;
+    int32_t n_tiles;
+    // dense per-candidate outputs
+    uint32_t* d_nocc;         // selected occurrences (0 = no match)
+    uint32_t* d_nev;          // events over the selected occurrences
+    int64_t* d_stage;         // staging base (events) of the trace
+    int64_t* d_stage_occ;     // staging base (occurrences) of the trace
+    // staging
+    int32_t* s_occ_nev;       // [cap_occ] events per staged occurrence
+    int32_t* s_ev_pos;        // [cap_ev]
+    int32_t* s_ev_rank;
+    int32_t* s_ev_act;
+    int64_t* s_ev_ts;
+    int64_t cap_occ, cap_ev;
+    // counters: 0 occ reserved, 1 ev reserved, 2 emitted, 3 errors, 4 overflow, 5 staging overflow, 6 matched traces
+    unsigned long long* counters;
+    int64_t* err_list;
+    int64_t* ovf_list;
+};
+
+__device__ __forceinline__ long long shfl_i64(long long v, int src) {
+    int lo = __shfl_sync(0xffffffffu, (int)(v & 0xffffffffll), src);
+    int hi = __shfl_sync(0xffffffffu, (int)(v >> 32), src);
+    return ((long long)hi << 32) | (unsigned int)lo;
+}
+
+// status codes of a trace inside the kernel
+enum { ST_NONE = 0, ST_MATCH = 1, ST_ERR = 2, ST_OVF = 3 };
+
+template <int W, int R, int NF>
+__global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ DevNfa nfa) {
+    typedef MaskOps<W> MO;
+    typedef typename MO::T mask_t;
+    constexpr int NE = 32 * W;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* s_meta = reinterpret_cast<uint32_t*>(smem_raw);                      // [NE][NT]
+    int32_t* s_ts = reinterpret_cast<int32_t*>(smem_raw + sizeof(uint32_t) * NE * NT);  // [NE][NT] when needs_ts
+    __shared__ unsigned long long s_scan[3][NT / 32];
+    __shared__ unsigned long long s_base[3];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const bool evt_pos = (P.flags & SIESTA_F_EVT_POS) != 0;
+    const bool return_all = (P.flags & SIESTA_F_RETURN_ALL) != 0;
+    const bool all_cols = (P.flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
+
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        // ------------------------------------------------------------------ phase A
+        const int64_t wi = (int64_t)tile * NT + threadIdx.x;  // index into the work list
+        int64_t ci = -1, t = -1;                               // candidate index, trace index
+        long long o0 = 0, o1 = 0;
+        if (wi < P.n_work) {
+            ci = P.work ? P.work[wi] : wi;
+            t = P.cand ? P.cand[ci] : ci;
+            o0 = P.trace_off[t];
+            o1 = P.trace_off[t + 1];
+        }
+        int my_cnt = 0;
+        for (int tt = 0; tt < 32; ++tt) {
+            const long long b0 = shfl_i64(o0, tt), b1 = shfl_i64(o1, tt);
+            if (b1 <= b0) continue;
+            const int slot = warp * 32 + tt;
+            int cnt = 0;
+            long long t0 = 0;
+            for (long long p = b0; p < b1; p += 32) {
+                const long long idx = p + lane;
+                int a = -1;
+                if (idx < b1) a = __ldg(P.act + idx);
+                uint32_t m = 0;
+                if (a >= 0 && a < P.n_act) m = __ldg(P.lut + a);
+                const unsigned ball = __ballot_sync(0xffffffffu, m != 0);
+                if (ball == 0) continue;
+                long long ts = 0;
+                if (P.needs_ts) {
+                    if (m) ts = __ldg(reinterpret_cast<const long long*>(P.ts_ms) + idx);
+                    if (cnt == 0) t0 = shfl_i64(ts, __ffs(ball) - 1);  // first event of the filtered list (Utils.java:51-53)
+                }
+                if (m) {
+                    const int r = cnt + __popc(ball & lt_mask);
+                    if (r < NE && (idx - b0) < 65536) {
+                        s_meta[r * NT + slot] = m | ((uint32_t)(idx - b0) << 16);
+                        // EventTs.transformSaseEvent: (int)((t - minTs) / 1000), truncating long division (EventTs.java:54)
+                        if (P.needs_ts) s_ts[r * NT + slot] = (int)((ts - t0) / 1000);
+                    }
+                }
+                cnt += __popc(ball);
+            }
+            if (b1 - b0 > 65536) cnt = NE + 1;  // in-trace index does not fit the packed word: overflow path
+            if (lane == tt) my_cnt = cnt;
+        }
+        __syncwarp();
+
+        // ------------------------------------------------------------------ phase B
+        int status = ST_NONE;
+        unsigned n_emitted = 0;
+        mask_t best = 0;
+        int nsel = 0;
+        mask_t sel_local[NE];
+        if (ci >= 0 && my_cnt > 0) {
+            if (my_cnt > NE) {
+                status = ST_OVF;
+            } else {
+                TraceEvents ev{s_meta + threadIdx.x, P.needs_ts ? s_ts + threadIdx.x : nullptr, NT, my_cnt, evt_pos};
+                RunEngine<W, R, NF> eng(nfa, ev);
+                BestEmit<W> be;
+                eng.run(be);
+                if (eng.ovf) status = ST_OVF;
+                else if (eng.err) status = ST_ERR;
+                else if (be.n > 0) {
+                    status = ST_MATCH;
+                    n_emitted = be.n;
+                    best = be.best;
+                    sel_local[0] = best;
+                    nsel = 1;
+                    if (return_all && be.n > 1) {
+                        GreedyEmit<W, NE> ge(ev, best, evt_pos);
+                        eng.run(ge);
+                        if (ge.ovf || eng.ovf) status = ST_OVF;
+                        else {
+                            nsel = ge.nsel;
+                            for (int o = 1; o < nsel; ++o) sel_local[o] = ge.sel[o];
+                        }
+                    }
+                }
+            }
+        }
+
+        // ------------------------------------------------------------------ phase C
+        unsigned my_occ = 0, my_ev = 0;
+        if (status == ST_MATCH) {
+            my_occ = (unsigned)nsel;
+            for (int o = 0; o < nsel; ++o) my_ev += MO::popc(sel_local[o]);
+        }
+        // block exclusive scan of (occ, ev), block sum of emitted
+        unsigned long long v0 = my_occ, v1 = my_ev, v2 = (status == ST_MATCH) ? n_emitted : 0u;
+        unsigned long long i0 = v0, i1 = v1, i2 = v2;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long y0 = __shfl_up_sync(0xffffffffu, i0, d), y1 = __shfl_up_sync(0xffffffffu, i1, d),
+                               y2 = __shfl_up_sync(0xffffffffu, i2, d);
+            if (lane >= d) { i0 += y0; i1 += y1; i2 += y2; }
+        }
+        if (lane == 31) { s_scan[0][warp] = i0; s_scan[1][warp] = i1; s_scan[2][warp] = i2; }
+        __syncthreads();
+        unsigned long long w0 = 0, w1 = 0, tot0 = 0, tot1 = 0, tot2 = 0;
+#pragma unroll
+        for (int k = 0; k < NT / 32; ++k) {
+            if (k < warp) { w0 += s_scan[0][k]; w1 += s_scan[1][k]; }
+            tot0 += s_scan[0][k]; tot1 += s_scan[1][k]; tot2 += s_scan[2][k];
+        }
+        if (threadIdx.x == 0) {
+            s_base[0] = tot0 ? atomicAdd(P.counters + 0, tot0) : 0ull;
+            s_base[1] = tot1 ? atomicAdd(P.counters + 1, tot1) : 0ull;
+            if (tot2) atomicAdd(P.counters + 2, tot2);
+        }
+        __syncthreads();
+        const long long occ_at = (long long)(s_base[0] + w0 + i0 - v0);
+        const long long ev_at = (long long)(s_base[1] + w1 + i1 - v1);
+        const bool stage_ok = (long long)(s_base[0] + tot0) <= P.cap_occ && (long long)(s_base[1] + tot1) <= P.cap_ev;
+        if (!stage_ok && threadIdx.x == 0) atomicAdd(P.counters + 5, 1ull);
+
+        if (ci >= 0) {
+            if (status == ST_MATCH) {
+                P.d_nocc[ci] = my_occ;
+                P.d_nev[ci] = my_ev;
+                P.d_stage[ci] = ev_at;
+                P.d_stage_occ[ci] = occ_at;
+                atomicAdd(P.counters + 6, 1ull);
+                if (stage_ok) {
+                    long long e = ev_at;
+                    const long long t0ms = (all_cols && !evt_pos) ? P.ts_ms[o0 + (s_meta[threadIdx.x] >> 16)] : 0;
+                    for (int o = 0; o < nsel; ++o) {
+                        mask_t m = sel_local[o];
+                        P.s_occ_nev[occ_at + o] = MO::popc(m);
+                        while (m) {
+                            const int j = MO::lo(m);
+                            m &= m - 1;
+                            const int src = (int)(s_meta[j * NT + threadIdx.x] >> 16);
+                            P.s_ev_pos[e] = src;
+                            if (all_cols) {
+                                P.s_ev_rank[e] = j;
+                                P.s_ev_act[e] = P.act[o0 + src];
+                                const long long raw = P.ts_ms[o0 + src];
+                                // SaseEvent.getEventBoth: timestamp * 1000 + minTs (SaseEvent.java:94-106)
+                                P.s_ev_ts[e] = evt_pos ? raw : (long long)((int)((raw - t0ms) / 1000)) * 1000 + t0ms;
+                            }
+                            ++e;
+                        }
+                    }
+                }
+            } else {
+                P.d_nocc[ci] = 0;
+                P.d_nev[ci] = 0;
+                if (status == ST_ERR) P.err_list[atomicAdd(P.counters + 3, 1ull)] = t;
+                else if (status == ST_OVF) P.ovf_list[atomicAdd(P.counters + 4, 1ull)] = ci;
+            }
+        }
+        __syncthreads();  // s_meta / s_scan are reused by the next tile
+    }
+}
+
+// Final placement.  The dense per-candidate counts (d_nocc, d_nev) are scanned in two levels
+// (per-block sums -> one-block scan of the sums -> in-block scan inside the gather), and the
+// gather copies each matching trace's staged occurrences to its final, trace-ordered position.
+constexpr int GT = 256;
+
+struct GatherParams {
+    const int64_t* cand;
+    int64_t n;
+    const uint32_t* d_nocc;
+    const uint32_t* d_nev;
+    const int64_t* d_stage;
+    const int64_t* d_stage_occ;
+    unsigned long long* blk;  // [3][n_blk] block sums -> exclusive bases
+    int64_t n_blk;
+    const int32_t* s_occ_nev;
+    const int32_t* s_ev_pos;
+    const int32_t* s_ev_rank;
+    const int32_t* s_ev_act;
+    const int64_t* s_ev_ts;
+    int64_t* trace_idx;
+    int64_t* occ_off;
+    int64_t* ev_off;
+    int32_t* ev_posv;
+    int32_t* ev_rank;
+    int32_t* ev_act;
+    int64_t* ev_ts;
+    int all_cols;
+};
+
+__device__ __forceinline__ void block_scan3(unsigned long long v[3], unsigned long long excl[3], unsigned long long tot[3]) {
+    __shared__ unsigned long long ws[3][GT / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc[3] = {v[0], v[1], v[2]};
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            unsigned long long y = __shfl_up_sync(0xffffffffu, inc[q], d);
+            if (lane >= d) inc[q] += y;
+        }
+    if (lane == 31)
+        for (int q = 0; q < 3; ++q) ws[q][warp] = inc[q];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        unsigned long long before = 0, all = 0;
+        for (int k = 0; k < GT / 32; ++k) {
+            if (k < warp) before += ws[q][k];
+            all += ws[q][k];
+        }
+        excl[q] = before + inc[q] - v[q];
+        tot[q] = all;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(GT) count_blocks_kernel(const __grid_constant__ GatherParams G) {
+    const int64_t i = (int64_t)blockIdx.x * GT + threadIdx.x;
+    unsigned long long v[3] = {0, 0, 0}, ex[3], tot[3];
+    if (i < G.n) {
+        const uint32_t c = G.d_nocc[i];
+        v[0] = c ? 1 : 0;
+        v[1] = c;
+        v[2] = c ? G.d_nev[i] : 0;
+    }
+    block_scan3(v, ex, tot);
+    if (threadIdx.x == 0)
+        for (int q = 0; q < 3; ++q) G.blk[q * G.n_blk + blockIdx.x] = tot[q];
+}
+
+// one block: exclusive scan of the three rows of block sums, in place
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(unsigned long long* blk, int64_t n_blk) {
+    __shared__ unsigned long long ws[32];
+    __shared__ unsigned long long carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = 0; q < 3; ++q) {
+        unsigned long long* row = blk + q * n_blk;
+        if (threadIdx.x == 0) carry_s = 0;
+        __syncthreads();
+        for (int64_t base = 0; base < n_blk; base += 1024) {
+            const int64_t i = base + threadIdx.x;
+            const unsigned long long v = i < n_blk ? row[i] : 0ull;
+            unsigned long long inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned long long y = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += y;
+            }
+            if (lane == 31) ws[warp] = inc;
+            __syncthreads();
+            unsigned long long before = 0, all = 0;
+            for (int k = 0; k < 32; ++k) {
+                if (k < warp) before += ws[k];
+                all += ws[k];
+            }
+            const unsigned long long carry = carry_s;
+            if (i < n_blk) row[i] = carry + before + inc - v;
+            __syncthreads();
+            if (threadIdx.x == 0) carry_s = carry + all;
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GT) gather_kernel(const __grid_constant__ GatherParams G) {
+    const int64_t i = (int64_t)blockIdx.x * GT + threadIdx.x;
+    unsigned long long v[3] = {0, 0, 0}, ex[3], tot[3];
+    uint32_t nocc = 0;
+    if (i < G.n) {
+        nocc = G.d_nocc[i];
+        v[0] = nocc ? 1 : 0;
+        v[1] = nocc;
+        v[2] = nocc ? G.d_nev[i] : 0;
+    }
+    block_scan3(v, ex, tot);
+    if (nocc == 0) return;
+    const int64_t tp = (int64_t)(G.blk[0 * G.n_blk + blockIdx.x] + ex[0]);
+    const int64_t op = (int64_t)(G.blk[1 * G.n_blk + blockIdx.x] + ex[1]);
+    int64_t ep = (int64_t)(G.blk[2 * G.n_blk + blockIdx.x] + ex[2]);
+    G.trace_idx[tp] = G.cand ? G.cand[i] : i;
+    G.occ_off[tp] = op;
+    int64_t se = G.d_stage[i];
+    const int64_t so = G.d_stage_occ[i];
+    for (uint32_t o = 0; o < nocc; ++o) {
+        const int ne = G.s_occ_nev[so + o];
+        G.ev_off[op + o] = ep;
+        for (int k = 0; k < ne; ++k) {
+            G.ev_posv[ep + k] = G.s_ev_pos[se + k];
+            if (G.all_cols) {
+                G.ev_rank[ep + k] = G.s_ev_rank[se + k];
+                G.ev_act[ep + k] = G.s_ev_act[se + k];
+                G.ev_ts[ep + k] = G.s_ev_ts[se + k];
+            }
+        }
+        ep += ne;
+        se += ne;
+    }
+}
+
+__global__ void set_tail_kernel(int64_t* occ_off, int64_t n_tr, int64_t n_occ, int64_t* ev_off, int64_t n_ev) {
+    occ_off[n_tr] = n_occ;
+    ev_off[n_occ] = n_ev;
+}
+
+// ---------------------------------------------------------------------------------- host side
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        if (p) { cudaFree(p); p = nullptr; }
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        if (e != cudaSuccess) {
+            set_error(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+            p = nullptr;
+            return SIESTA_E_NOMEM;
+        }
+        return SIESTA_OK;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+    void* release() { void* q = p; p = nullptr; return q; }
+};
+
+struct DevMatchesImpl {
+    void* bufs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+template <int W, int R, int NF>
+int launch_detect(const Ctx* ctx, cudaStream_t stream, DetectParams P, const DevNfa& nfa) {
+    constexpr int NE = 32 * W;
+    const size_t smem = sizeof(uint32_t) * NE * NT * (P.needs_ts ? 2 : 1);
+    auto kern = detect_kernel<W, R, NF>;
+    SIESTA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t n_tiles = (P.n_work + NT - 1) / NT;
+    P.n_tiles = (int32_t)n_tiles;
+    int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * per_sm);
+    if (grid < 1) grid = 1;
+    kern<<<grid, NT, smem, stream>>>(P, nfa);
+    SIESTA_LAUNCHED();
+    SIESTA_CUDA_OK(cudaGetLastError());
+    return SIESTA_OK;
+}
+
+
+int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand, uint32_t flags,
+                       cudaStream_t stream, siesta_dev_matches* out) {
+    std::memset(out, 0, sizeof(*out));
+    DevNfa dn;
+    int rc = validate_nfa(nfa, flags, &dn);
+    if (rc != SIESTA_OK) return rc;
+    const Ctx* ctx = log->ctx;
+    SIESTA_CUDA_OK(cudaSetDevice(ctx->device));
+    if (!stream) stream = ctx->stream;
+    const int64_t n = d_cand ? n_cand : log->n_traces;
+    const bool return_all = (flags & SIESTA_F_RETURN_ALL) != 0;
+    const bool all_cols = (flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
+
+    std::vector<uint16_t> lut;
+    int needs_ts = 0, n_positive = 0;
+    build_lut(nfa, dn, log->n_activities, flags, lut, &needs_ts, &n_positive);
+
+    // staging bounds: selected occurrences of a trace are disjoint, so their events never exceed the
+    // trace's filtered events (<= 64 on the widest engine configuration)
+    const int64_t wide = std::min<int64_t>(log->n_events, n * 64);
+    const int64_t cap_occ = return_all ? wide : n;
+    const int64_t cap_ev = (!return_all && !dn.any_kleene) ? n * std::max(1, n_positive) : wide;
+
+    DevBuf b_lut, b_nocc, b_nev, b_stage, b_stage_occ, b_counters, b_err, b_ovf, b_ovf2;
+    DevBuf s_occ_nev, s_ev_pos, s_ev_rank, s_ev_act, s_ev_ts, b_blk;
+    const size_t nn = (size_t)std::max<int64_t>(n, 1);
+    if ((rc = b_lut.alloc(lut.size() * sizeof(uint16_t))) || (rc = b_nocc.alloc(nn * 4)) || (rc = b_nev.alloc(nn * 4)) ||
+        (rc = b_stage.alloc(nn * 8)) || (rc = b_stage_occ.alloc(nn * 8)) || (rc = b_counters.alloc(8 * 8)) ||
+        (rc = b_err.alloc(nn * 8)) || (rc = b_ovf.alloc(nn * 8)) || (rc = s_occ_nev.alloc((size_t)cap_occ * 4)) ||
+        (rc = s_ev_pos.alloc((size_t)cap_ev * 4)))
+        return rc;
+    if (all_cols && ((rc = s_ev_rank.alloc((size_t)cap_ev * 4)) || (rc = s_ev_act.alloc((size_t)cap_ev * 4)) ||
+                     (rc = s_ev_ts.alloc((size_t)cap_ev * 8))))
+        return rc;
+
+    cudaEvent_t ev0, ev1;
+    SIESTA_CUDA_OK(cudaEventCreate(&ev0));
+    SIESTA_CUDA_OK(cudaEventCreate(&ev1));
+    SIESTA_CUDA_OK(cudaMemcpyAsync(b_lut.p, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
+    SIESTA_CUDA_OK(cudaMemsetAsync(b_counters.p, 0, 64, stream));
+    SIESTA_CUDA_OK(cudaEventRecord(ev0, stream));
+
+    DetectParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.trace_off = log->d_trace_off;
+    P.act = log->d_act;
+    P.ts_ms = log->d_ts_ms;
+    P.cand = d_cand;
+    P.work = nullptr;
+    P.n_work = n;
+    P.lut = b_lut.as<uint16_t>();
+    P.n_act = log->n_activities;
+    P.flags = flags;
+    P.needs_ts = needs_ts;
+    P.d_nocc = b_nocc.as<uint32_t>();
+    P.d_nev = b_nev.as<uint32_t>();
+    P.d_stage = b_stage.as<int64_t>();
+    P.d_stage_occ = b_stage_occ.as<int64_t>();
+    P.s_occ_nev = s_occ_nev.as<int32_t>();
+    P.s_ev_pos = s_ev_pos.as<int32_t>();
+    P.s_ev_rank = s_ev_rank.as<int32_t>();
+    P.s_ev_act = s_ev_act.as<int32_t>();
+    P.s_ev_ts = s_ev_ts.as<int64_t>();
+    P.cap_occ = cap_occ;
+    P.cap_ev = cap_ev;
+    P.counters = b_counters.as<unsigned long long>();
+    P.err_list = b_err.as<int64_t>();
+    P.ovf_list = b_ovf.as<int64_t>();
+
+    unsigned long long h_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (n > 0) {
+        if ((rc = launch_detect<1, 64, 64>(ctx, stream, P, dn))) return rc;
+        SIESTA_CUDA_OK(cudaMemcpyAsync(h_cnt, b_counters.p, 64, cudaMemcpyDeviceToHost, stream));
+        SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+        if (h_cnt[4] > 0) {
+            // traces beyond the narrow configuration (32 relevant events / 64 live runs): wide engine
+            const int64_t n_ovf = (int64_t)h_cnt[4];
+            if ((rc = b_ovf2.alloc((size_t)n_ovf * 8))) return rc;
+            SIESTA_CUDA_OK(cudaMemsetAsync(b_counters.as<unsigned long long>() + 4, 0, 8, stream));
+            DetectParams Q = P;
+            Q.work = b_ovf.as<int64_t>();
+            Q.n_work = n_ovf;
+            Q.ovf_list = b_ovf2.as<int64_t>();
+            if ((rc = launch_detect<2, 1024, 128>(ctx, stream, Q, dn))) return rc;
+            SIESTA_CUDA_OK(cudaMemcpyAsync(h_cnt, b_counters.p, 64, cudaMemcpyDeviceToHost, stream));
+            SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+            if (h_cnt[4] > 0) {
+                set_error(std::to_string(h_cnt[4]) + " trace(s) exceed the engine limits (64 pattern-relevant events, "
+                          "1024 live runs or 65536 events per trace)");
+                return SIESTA_E_UNSUPPORTED;
+            }
+        }
+        if (h_cnt[5] > 0) {
+            set_error("internal: occurrence staging overflow");
+            return SIESTA_E_NOMEM;
+        }
+    }
+    const int64_t n_occ = (int64_t)h_cnt[0], n_ev = (int64_t)h_cnt[1], n_tr = (int64_t)h_cnt[6], n_err = (int64_t)h_cnt[3];
+
+    DevBuf f_trace, f_occ_off, f_ev_off, f_pos, f_rank, f_act, f_ts, f_err;
+    if ((rc = f_trace.alloc((size_t)n_tr * 8)) || (rc = f_occ_off.alloc((size_t)(n_tr + 1) * 8)) ||
+        (rc = f_ev_off.alloc((size_t)(n_occ + 1) * 8)) || (rc = f_pos.alloc((size_t)n_ev * 4)) ||
+        (rc = f_err.alloc((size_t)n_err * 8)))
+        return rc;
+    if (all_cols && ((rc = f_rank.alloc((size_t)n_ev * 4)) || (rc = f_act.alloc((size_t)n_ev * 4)) || (rc = f_ts.alloc((size_t)n_ev * 8))))
+        return rc;
+
+    if (n > 0) {
+        GatherParams G;
+        std::memset(&G, 0, sizeof(G));
+        G.cand = d_cand;
+        G.n = n;
+        G.d_nocc = P.d_nocc;
+        G.d_nev = P.d_nev;
+        G.d_stage = P.d_stage;
+        G.d_stage_occ = P.d_stage_occ;
+        G.n_blk = (n + GT - 1) / GT;
+        if ((rc = b_blk.alloc((size_t)G.n_blk * 3 * 8))) return rc;
+        G.blk = b_blk.as<unsigned long long>();
+        G.s_occ_nev = P.s_occ_nev;
+        G.s_ev_pos = P.s_ev_pos;
+        G.s_ev_rank = P.s_ev_rank;
+        G.s_ev_act = P.s_ev_act;
+        G.s_ev_ts = P.s_ev_ts;
+        G.trace_idx = f_trace.as<int64_t>();
+        G.occ_off = f_occ_off.as<int64_t>();
+        G.ev_off = f_ev_off.as<int64_t>();
+        G.ev_posv = f_pos.as<int32_t>();
+        G.ev_rank = f_rank.as<int32_t>();
+        G.ev_act = f_act.as<int32_t>();
+        G.ev_ts = f_ts.as<int64_t>();
+        G.all_cols = all_cols ? 1 : 0;
+        count_blocks_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G);
+        SIESTA_LAUNCHED();
+        scan_blocks_kernel<<<1, 1024, 0, stream>>>(G.blk, G.n_blk);
+        SIESTA_LAUNCHED();
+        gather_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G);
+        SIESTA_LAUNCHED();
+        SIESTA_CUDA_OK(cudaGetLastError());
+    }
+    set_tail_kernel<<<1, 1, 0, stream>>>(f_occ_off.as<int64_t>(), n_tr, n_occ, f_ev_off.as<int64_t>(), n_ev);
+    SIESTA_LAUNCHED();
+    SIESTA_CUDA_OK(cudaEventRecord(ev1, stream));
+    if (n_err > 0) {  // order the (rare) error list
+        std::vector<int64_t> h((size_t)n_err);
+        SIESTA_CUDA_OK(cudaMemcpyAsync(h.data(), b_err.p, (size_t)n_err * 8, cudaMemcpyDeviceToHost, stream));
+        SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+        std::sort(h.begin(), h.end());
+        SIESTA_CUDA_OK(cudaMemcpyAsync(f_err.p, h.data(), (size_t)n_err * 8, cudaMemcpyHostToDevice, stream));
+    }
+    SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    SIESTA_CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+
+    DevMatchesImpl* impl = new DevMatchesImpl();
+    out->n_traces = n_tr;
+    out->n_occurrences = n_occ;
+    out->n_events = n_ev;
+    out->n_matches_emitted = (int64_t)h_cnt[2];
+    out->n_ref_errors = n_err;
+    out->kernel_ms = ms;
+    impl->bufs[0] = out->d_trace_idx = (int64_t*)f_trace.release();
+    impl->bufs[1] = out->d_occ_off = (int64_t*)f_occ_off.release();
+    impl->bufs[2] = out->d_ev_off = (int64_t*)f_ev_off.release();
+    impl->bufs[3] = out->d_ev_pos = (int32_t*)f_pos.release();
+    impl->bufs[4] = out->d_ev_rank = (int32_t*)f_rank.release();
+    impl->bufs[5] = out->d_ev_act = (int32_t*)f_act.release();
+    impl->bufs[6] = out->d_ev_ts_ms = (int64_t*)f_ts.release();
+    impl->bufs[7] = out->d_err_trace_idx = (int64_t*)f_err.release();
+    out->impl = impl;
+    return SIESTA_OK;
+}
+
+}  // namespace
+}  // namespace siesta
+
+extern "C" int siesta_detect_device(siesta_log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand,
+                                    uint32_t flags, void* stream, siesta_dev_matches* out) {
+    if (!log || !nfa || !out || (d_cand && n_cand < 0)) {
+        siesta::set_error("siesta_detect_device: null argument");
+        return SIESTA_E_INVALID;
+    }
+    return siesta::detect_device_impl(reinterpret_cast<siesta::Log*>(log), nfa, d_cand, n_cand, flags,
+                                      reinterpret_cast<cudaStream_t>(stream), out);
+}
+
+extern "C" void siesta_dev_matches_free(siesta_dev_matches* m) {
+    if (!m || !m->impl) return;
+    siesta::DevMatchesImpl* impl = reinterpret_cast<siesta::DevMatchesImpl*>(m->impl);
+    for (void* p : impl->bufs)
+        if (p) cudaFree(p);
+    delete impl;
+    m->impl = nullptr;
+}

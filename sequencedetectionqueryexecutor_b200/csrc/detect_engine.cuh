@@ -1,0 +1,437 @@
+// detect_engine.cuh — per-trace run-set engine (device), the heart of kernel K1.
+//
+// One thread owns one trace.  The thread walks the trace's events that belong to
+// the pattern (already compacted into shared memory by the warp-cooperative filter
+// phase) and keeps the engine's active-run list in a packed form:
+//
+//   run.mask  bitmask over the trace's filtered events = Run.eventIds (ids only ever
+//             grow in stream order, so the list is the set of bits, low to high)
+//   run.meta  cur:4 | state[]:2 bits x 8 | kleeneClosureInitialized | containsNegative |
+//             isFull | delete-marks:2            (S/engine/Run.java:40-111)
+//   run.fam   index of the value vector the run shares with every clone descending
+//             from the same initializeRun (Run.clone is shallow: Run.java:319-327)
+//
+// The transition rules restate S/engine/Engine.java (evaluateEventForSkipTillNext
+// :654-725, createNewRun :933-982, checkPredicate :1102-1180, checkProceed
+// :1205-1224, cleanRuns :1404-1418) and S/engine/Run.java (addEvent :196-278,
+// proceed :307-315).  Every place where the Java code would throw sets `err`.
+// Engine.createNewRun's trailing block (:983-996) is not implemented: the host
+// rejects SIESTA_F_MODE_HEAD for NFAs it would change.
+#pragma once
+#include "common.cuh"
+
+// The engine compiles for the device (product) and, unchanged, for the host: tests/host_harness
+// runs it on the CPU against the oracle before any GPU time is spent.  Nothing in the library's
+// product path calls the host instantiation.
+#define SIESTA_HD __host__ __device__
+
+namespace siesta {
+
+SIESTA_HD __forceinline__ int popc32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+SIESTA_HD __forceinline__ int popc64(unsigned long long x) {
+#ifdef __CUDA_ARCH__
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+SIESTA_HD __forceinline__ int clz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __clz(x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+SIESTA_HD __forceinline__ int clz64(unsigned long long x) {
+#ifdef __CUDA_ARCH__
+    return __clzll(x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
+SIESTA_HD __forceinline__ int ffs32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __ffs(x);
+#else
+    return __builtin_ffs((int)x);
+#endif
+}
+SIESTA_HD __forceinline__ int ffs64(unsigned long long x) {
+#ifdef __CUDA_ARCH__
+    return __ffsll(x);
+#else
+    return __builtin_ffsll((long long)x);
+#endif
+}
+
+template <int W>
+struct MaskOps;
+template <>
+struct MaskOps<1> {
+    typedef uint32_t T;
+    static SIESTA_HD __forceinline__ T bit(int j) { return 1u << j; }
+    static SIESTA_HD __forceinline__ int popc(T m) { return popc32(m); }
+    static SIESTA_HD __forceinline__ int hi(T m) { return 31 - clz32(m); }
+    static SIESTA_HD __forceinline__ int lo(T m) { return ffs32(m) - 1; }
+};
+template <>
+struct MaskOps<2> {
+    typedef unsigned long long T;
+    static SIESTA_HD __forceinline__ T bit(int j) { return 1ull << j; }
+    static SIESTA_HD __forceinline__ int popc(T m) { return popc64(m); }
+    static SIESTA_HD __forceinline__ int hi(T m) { return 63 - clz64(m); }
+    static SIESTA_HD __forceinline__ int lo(T m) { return ffs64(m) - 1; }
+};
+
+// meta layout
+#define M_CUR(m) ((m) & 15u)
+#define M_ST_SHIFT 4
+#define M_ST(m) (((m) >> M_ST_SHIFT) & 0xFFFFu)
+#define M_KINIT (1u << 20)
+#define M_CNEG (1u << 21)
+#define M_FULL (1u << 22)
+#define M_MARK_SHIFT 23
+#define M_MARKS(m) (((m) >> M_MARK_SHIFT) & 3u)
+
+// Events of one trace, compacted to the pattern's event types.  Shared memory,
+// transposed [event][thread] so that a warp stepping in lockstep is conflict-free.
+//   meta word: smask (bit k: type belongs to state k)  | fmask << 8 (bit k: type is
+//   state k's first type) | index-in-trace << 16
+struct TraceEvents {
+    const uint32_t* meta;  // stride = NT words between consecutive events of this thread
+    const int32_t* ts;     // relative seconds (EventTs route) or nullptr
+    int stride;
+    int n;
+    bool evt_pos;
+    SIESTA_HD __forceinline__ uint32_t word(int j) const { return meta[j * stride]; }
+    SIESTA_HD __forceinline__ int src(int j) const { return (int)(meta[j * stride] >> 16); }
+    // SaseEvent attributes (J/SaseConnection/SaseEvent.java:80-89) after
+    // Utils.transformToSaseEvents (J/model/Utils/Utils.java:48-65)
+    SIESTA_HD __forceinline__ int position(int j) const { return evt_pos ? src(j) : j; }
+    SIESTA_HD __forceinline__ int timestamp(int j) const { return evt_pos ? j : (ts ? ts[j * stride] : 0); }
+    SIESTA_HD __forceinline__ int attr(int j, int a) const { return a == SIESTA_ATTR_POSITION ? position(j) : timestamp(j); }
+};
+
+template <int W, int R, int NF>
+struct RunEngine {
+    typedef MaskOps<W> MO;
+    typedef typename MO::T mask_t;
+
+    const DevNfa& nfa;
+    const TraceEvents& ev;
+    mask_t rmask[R];
+    uint32_t rmeta[R];
+    uint16_t rfam[R];
+    unsigned long long famvv[NF];  // byte k = 1 + rank of the event last stored for state k; 0 = null
+    int nruns, nfam;
+    bool err, ovf;
+    unsigned n_emitted;
+
+    SIESTA_HD RunEngine(const DevNfa& n, const TraceEvents& e) : nfa(n), ev(e) {}
+
+    // ---- small helpers over a packed run -------------------------------------------------
+    SIESTA_HD __forceinline__ static uint32_t get_st(uint32_t m, int k) { return (m >> (M_ST_SHIFT + 2 * k)) & 3u; }
+    SIESTA_HD __forceinline__ static uint32_t set_st(uint32_t m, int k, uint32_t v) {
+        return (m & ~(3u << (M_ST_SHIFT + 2 * k))) | (v << (M_ST_SHIFT + 2 * k));
+    }
+    SIESTA_HD __forceinline__ static uint32_t set_cur(uint32_t m, int c) { return (m & ~15u) | (uint32_t)c; }
+    SIESTA_HD __forceinline__ bool is_kleene(int kind) const { return kind == SIESTA_STATE_KLEENE_PLUS || kind == SIESTA_STATE_KLEENE_STAR; }
+    // Run.checkMatch (Run.java:181-191)
+    SIESTA_HD __forceinline__ bool check_match(uint32_t m) const { return (m & M_FULL) && M_ST(m) == nfa.all2; }
+    // Run.proceed (Run.java:307-315)
+    SIESTA_HD __forceinline__ uint32_t proceed(uint32_t m) const {
+        int cur = M_CUR(m);
+        m = set_st(m, cur, 2);
+        if (cur == nfa.n_states - 1) m |= M_FULL;
+        else m = set_cur(m, cur + 1);
+        return m;
+    }
+    SIESTA_HD __forceinline__ int new_family() {
+        if (!nfa.need_vv) return 0;
+        if (nfam >= NF) { ovf = true; return 0; }
+        famvv[nfam] = 0ull;
+        return nfam++;
+    }
+    SIESTA_HD __forceinline__ void append(mask_t mask, uint32_t meta, int fam) {
+        if (nruns >= R) { ovf = true; return; }
+        rmask[nruns] = mask;
+        rmeta[nruns] = meta;
+        rfam[nruns] = (uint16_t)fam;
+        nruns++;
+    }
+    SIESTA_HD __forceinline__ int vv_get(int fam, int k) const { return (int)((famvv[fam] >> (8 * k)) & 0xFF) - 1; }
+    SIESTA_HD __forceinline__ void vv_set(int fam, int k, int j) {
+        famvv[fam] = (famvv[fam] & ~(0xFFull << (8 * k))) | ((unsigned long long)(j + 1) << (8 * k));
+    }
+
+    // Edge.evaluatePredicate(Event, Run, EventBuffer) over PredicateOptimized.evaluate (S/query/
+    // PredicateOptimized.java:331-368): self reference -> true; null value vector -> false.
+    SIESTA_HD bool eval_preds(int s, int j, int cur, int fam) const {
+        const int np = nfa.n_preds[s];
+        for (int k = 0; k < np; ++k) {
+            const int ref = nfa.p_ref[s][k];
+            if (ref == cur) continue;
+            const int rj = vv_get(fam, ref);
+            if (rj < 0) return false;
+            const int a = nfa.p_attr[s][k];
+            const long long lhs = ev.attr(j, a);
+            const long long rhs = (long long)ev.attr(rj, a) + nfa.p_c[s][k];
+            if (nfa.p_op[s][k] == SIESTA_OP_LE ? !(lhs <= rhs) : !(lhs >= rhs)) return false;
+        }
+        return true;
+    }
+    // State.canStartWithEvent (S/query/State.java:302-314): predicates see the event as its own reference
+    // (PredicateOptimized.evaluate(Event, Event) :302-323).
+    SIESTA_HD bool can_start(int s, int j, uint32_t w) const {
+        if (!((w >> s) & 1u)) return false;
+        const int np = nfa.n_preds[s];
+        for (int k = 0; k < np; ++k) {
+            const long long v = ev.attr(j, nfa.p_attr[s][k]);
+            const long long rhs = v + nfa.p_c[s][k];
+            if (nfa.p_op[s][k] == SIESTA_OP_LE ? !(v <= rhs) : !(v >= rhs)) return false;
+        }
+        return true;
+    }
+    // Engine.checkProceed (Engine.java:1205-1224); only ever reached on Kleene states here.
+    SIESTA_HD __forceinline__ bool check_proceed(mask_t mask, uint32_t meta) {
+        if (mask == 0) { err = true; return false; }  // eventIds.get(count-1) with count == 0
+        const int cur = M_CUR(meta);
+        if (get_st(meta, cur) == 0 && nfa.kind[cur] == SIESTA_STATE_KLEENE_PLUS) return false;
+        return true;  // SIESTA never attaches proceed-edge predicates
+    }
+    // Engine.checkPredicate (:1102-1163) + checkPredicatesForNextState (:1165-1180)
+    SIESTA_HD bool check_predicate(int j, uint32_t w, uint32_t meta, int fam) const {
+        const int cur = M_CUR(meta);
+        const int kind = nfa.kind[cur];
+        const bool mine = (w >> cur) & 1u;
+        if (kind == SIESTA_STATE_NEGATIVE) {
+            if (mine) return eval_preds(cur, j, cur, fam);
+            else if (nfa.n_states > cur + 1) {
+                if ((w >> (cur + 1)) & 1u) return eval_preds(cur + 1, j, cur, fam);
+                return false;
+            }
+        }
+        if (!mine) return false;
+        return eval_preds(cur, j, cur, fam);  // begin and take edges carry the same list
+    }
+    // Run.addEventToNormalorOr (Run.java:247-262)
+    SIESTA_HD __forceinline__ void add_normal(int j, mask_t& mask, uint32_t& meta, int fam) {
+        int cur = M_CUR(meta);
+        mask |= MO::bit(j);
+        meta = set_st(meta, cur, 2);
+        const uint32_t st = M_ST(meta);
+        const int c = popc32(st & 0xAAAAu & ~((st & 0x5555u) << 1));
+        if (cur == nfa.n_states - 1 || c == nfa.n_states) {
+            meta |= M_FULL;
+        } else {
+            if ((nfa.has_vv >> cur) & 1u) vv_set(fam, cur, j);
+            meta = set_cur(meta, cur + 1);
+        }
+    }
+    // Run.addEventToKleene (Run.java:264-278)
+    SIESTA_HD __forceinline__ void add_kleene(int j, mask_t& mask, uint32_t& meta, int fam) {
+        const int cur = M_CUR(meta);
+        mask |= MO::bit(j);
+        if ((nfa.has_vv >> cur) & 1u) {
+            if ((meta & M_KINIT) && vv_get(fam, cur) < 0) { err = true; return; }  // updateValueVector NPE (Run.java:361)
+            vv_set(fam, cur, j);
+        }
+        meta |= M_KINIT;
+        meta = set_st(meta, cur, 3);
+    }
+    // Run.addEventToNextState (Run.java:228-245)
+    SIESTA_HD __forceinline__ void add_next(int j, mask_t& mask, uint32_t& meta, int fam) {
+        const int cur = M_CUR(meta);
+        if (cur + 1 >= nfa.n_states) { err = true; return; }  // getStates(currentState+1)
+        const int nk = nfa.kind[cur + 1];
+        if (nk == SIESTA_STATE_NORMAL || nk == SIESTA_STATE_OR) {
+            meta = set_st(meta, cur, 2);
+            meta = set_cur(meta, cur + 1);
+            add_normal(j, mask, meta, fam);
+        } else if (is_kleene(nk)) {
+            meta = set_cur(meta, cur + 1);
+            add_kleene(j, mask, meta, fam);
+        } else {  // negative
+            meta |= M_CNEG;
+            meta = set_cur(meta, cur + 1);
+        }
+    }
+    // Run.addEvent (Run.java:196-225)
+    SIESTA_HD void add_event(int j, uint32_t w, mask_t& mask, uint32_t& meta, int fam) {
+        const int cur = M_CUR(meta);
+        const int k = nfa.kind[cur];
+        const bool mine = (w >> cur) & 1u;
+        if (k == SIESTA_STATE_NORMAL || k == SIESTA_STATE_OR) add_normal(j, mask, meta, fam);
+        else if (k == SIESTA_STATE_NEGATIVE) {
+            if (mine) { meta |= M_CNEG; meta = set_cur(meta, cur + 1); }
+            else add_next(j, mask, meta, fam);
+        } else if (k == SIESTA_STATE_KLEENE_STAR) {
+            if (mine) add_kleene(j, mask, meta, fam);
+            else add_next(j, mask, meta, fam);
+        } else add_kleene(j, mask, meta, fam);
+    }
+
+    // Engine.evaluateEventForSkipTillNext (Engine.java:654-725)
+    template <class Emit>
+    SIESTA_HD void evaluate(int j, uint32_t w, int r, Emit& emit) {
+        mask_t mask = rmask[r];
+        uint32_t meta = rmeta[r];
+        const int fam = rfam[r];
+        int cur = M_CUR(meta);
+        if (cur >= nfa.n_states) { err = true; return; }  // getStates(currentState) past a trailing negative
+        if (nfa.kind[cur] == SIESTA_STATE_KLEENE_STAR && !(meta & M_KINIT)) {
+            if (check_proceed(mask, meta) && ((w >> (8 + cur)) & 1u)) {
+                const uint32_t cm = proceed(meta);
+                if (check_match(cm)) emit(mask);  // emits r's ids (:665)
+                else append(mask, cm, fam);
+            }
+            if (err) return;
+        }
+        if (!check_predicate(j, w, meta, fam)) return;
+        add_event(j, w, mask, meta, fam);
+        if (err) return;
+        if (meta & M_CNEG) meta += (1u << M_MARK_SHIFT);
+        if ((meta & M_FULL) && check_match(meta)) {
+            emit(mask);
+            meta += (1u << M_MARK_SHIFT);
+        }
+        cur = M_CUR(meta);
+        if (cur >= nfa.n_states) { err = true; return; }
+        if (is_kleene(nfa.kind[cur])) {
+            if (check_proceed(mask, meta)) {
+                // the clone is a new object: it is not in toDeleteRuns even if its parent already is
+                append(mask, (meta | M_KINIT) & ~(3u << M_MARK_SHIFT), fam);
+                meta = proceed(meta);
+                if (check_match(meta)) {
+                    emit(mask);
+                    meta += (1u << M_MARK_SHIFT);
+                }
+            }
+            if (err) return;
+        }
+        if (M_MARKS(meta) >= 2) { err = true; return; }  // cleanRuns: second resetRun NPEs (Run.java:163)
+        rmask[r] = mask;
+        rmeta[r] = meta;
+    }
+
+    // Engine.createNewRun (Engine.java:933-982)
+    template <class Emit>
+    SIESTA_HD void create_new_run(int j, uint32_t w, Emit& emit) {
+        const int k0 = nfa.kind[0];
+        if (can_start(0, j, w)) {
+            if (is_kleene(k0)) {
+                const int fam = new_family();
+                mask_t mask = 0;
+                uint32_t meta = nfa.init_st << M_ST_SHIFT;
+                add_event(j, w, mask, meta, fam);
+                if (err) return;
+                if (check_proceed(mask, meta)) append(mask, proceed(meta), fam);
+                if (err) return;
+            }
+            const int fam = new_family();
+            mask_t mask = 0;
+            uint32_t meta = nfa.init_st << M_ST_SHIFT;
+            add_event(j, w, mask, meta, fam);
+            if (err) return;
+            if (check_match(meta)) emit(mask);
+            else append(mask, meta, fam);
+        } else if (k0 == SIESTA_STATE_KLEENE_STAR || k0 == SIESTA_STATE_NEGATIVE) {
+            if (nfa.n_states > 1 && can_start(1, j, w)) {
+                const int fam = new_family();
+                mask_t mask = 0;
+                uint32_t meta = nfa.init_st << M_ST_SHIFT;
+                add_event(j, w, mask, meta, fam);
+                if (err) return;
+                const int cur = M_CUR(meta);
+                if (cur >= nfa.n_states) { err = true; return; }
+                if (nfa.kind[cur] == SIESTA_STATE_KLEENE_STAR && check_proceed(mask, meta)) meta = proceed(meta);
+                if (err) return;
+                if (check_match(meta)) emit(mask);
+                else append(mask, meta, fam);
+            }
+        }
+    }
+
+    // Engine.runSkipTillNextEngine (Engine.java:207-224) over one trace.
+    template <class Emit>
+    SIESTA_HD void run(Emit& emit) {
+        nruns = 0;
+        nfam = 0;
+        err = false;
+        ovf = false;
+        n_emitted = 0;
+        for (int j = 0; j < ev.n; ++j) {
+            const uint32_t w = ev.word(j);
+            const int n0 = nruns;  // runs appended while evaluating this event are not visited (:361)
+            for (int r = 0; r < n0; ++r) {
+                if (rmeta[r] & M_FULL) continue;
+                evaluate(j, w, r, emit);
+                if (err || ovf) return;
+            }
+            // cleanRuns (:1404-1418): stable removal of marked runs
+            int k = 0;
+            for (int r = 0; r < nruns; ++r) {
+                if (M_MARKS(rmeta[r])) continue;
+                if (k != r) { rmask[k] = rmask[r]; rmeta[k] = rmeta[r]; rfam[k] = rfam[r]; }
+                ++k;
+            }
+            nruns = k;
+            create_new_run(j, w, emit);
+            if (err || ovf) return;
+        }
+    }
+};
+
+// Occurrences.clearOccurrences (J/model/Occurrences.java:58-89), streamed over the emission order.
+template <int W>
+struct BestEmit {
+    typedef MaskOps<W> MO;
+    typename MO::T best;
+    int best_cnt;
+    unsigned n;
+    SIESTA_HD BestEmit() : best(0), best_cnt(-1), n(0) {}
+    // the first occurrence of maximal size (:60-69)
+    SIESTA_HD __forceinline__ void operator()(typename MO::T m) {
+        const int c = MO::popc(m);
+        if (c > best_cnt) { best = m; best_cnt = c; }
+        ++n;
+    }
+};
+
+template <int W, int NSEL>
+struct GreedyEmit {
+    typedef MaskOps<W> MO;
+    typedef typename MO::T mask_t;
+    const TraceEvents& ev;
+    mask_t sel[NSEL];
+    int nsel;
+    unsigned idx;
+    bool by_pos;
+    bool ovf;
+    SIESTA_HD GreedyEmit(const TraceEvents& e, mask_t best, bool bp) : ev(e), nsel(1), idx(0), by_pos(bp), ovf(false) { sel[0] = best; }
+    // Occurrence.overlaps (J/model/Occurrence.java:36-49); a = this, b = argument
+    SIESTA_HD __forceinline__ bool overlaps(mask_t a, mask_t b) const {
+        const int af = MO::lo(a), al = MO::hi(a), bf = MO::lo(b), bl = MO::hi(b);
+        bool not_ov;
+        if (by_pos) not_ov = ev.position(al) < ev.position(bf) || ev.position(af) > ev.position(bl);
+        else not_ov = ev.timestamp(al) < ev.timestamp(bf) || ev.timestamp(af) > ev.timestamp(bl);
+        return !not_ov;
+    }
+    // returnAll branch (:74-87): matches 1..n-1 in emission order, kept if they overlap nothing chosen so far
+    SIESTA_HD void operator()(mask_t m) {
+        const unsigned i = idx++;
+        if (i == 0) return;
+        for (int o = 0; o < nsel; ++o)
+            if (overlaps(m, sel[o])) return;
+        if (nsel >= NSEL) { ovf = true; return; }
+        sel[nsel++] = m;
+    }
+};
+
+}  // namespace siesta

@@ -1,0 +1,99 @@
+// nfa.cpp — host-side NFA validation and the per-activity lookup table of kernel K1.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace siesta {
+
+int validate_nfa(const siesta_nfa* nfa, uint32_t flags, DevNfa* out) {
+    if (!nfa || nfa->n_states < 1 || nfa->n_states > SIESTA_MAX_STATES) {
+        set_error("NFA must have 1.." + std::to_string(SIESTA_MAX_STATES) + " states");
+        return SIESTA_E_INVALID;
+    }
+    DevNfa d;
+    std::memset(&d, 0, sizeof(d));
+    d.n_states = nfa->n_states;
+    const bool ignore_preds = (flags & SIESTA_F_ONLY_APPEARANCES) != 0;
+    for (int s = 0; s < nfa->n_states; ++s) {
+        const siesta_state& st = nfa->states[s];
+        if (st.kind < SIESTA_STATE_NORMAL || st.kind > SIESTA_STATE_OR) {
+            set_error("unknown state kind");
+            return SIESTA_E_INVALID;
+        }
+        if (st.n_types < 1 || st.n_types > SIESTA_MAX_OR_TYPES) {
+            set_error("state needs 1.." + std::to_string(SIESTA_MAX_OR_TYPES) + " event types");
+            return SIESTA_E_INVALID;
+        }
+        if ((st.kind == SIESTA_STATE_NORMAL || st.kind == SIESTA_STATE_KLEENE_PLUS) && st.n_types != 1) {
+            set_error("normal and kleeneClosure states carry exactly one event type (State.java:108-133)");
+            return SIESTA_E_INVALID;
+        }
+        if (st.n_preds < 0 || st.n_preds > SIESTA_MAX_PREDS) {
+            set_error("too many predicates on one state");
+            return SIESTA_E_INVALID;
+        }
+        d.kind[s] = (uint8_t)st.kind;
+        if (st.kind == SIESTA_STATE_NEGATIVE) d.init_st |= 2u << (2 * s);
+        if (st.kind == SIESTA_STATE_KLEENE_STAR) d.init_st |= 3u << (2 * s);
+        if (st.kind == SIESTA_STATE_KLEENE_STAR || st.kind == SIESTA_STATE_KLEENE_PLUS) d.any_kleene = 1;
+        d.all2 |= 2u << (2 * s);
+        const int np = ignore_preds ? 0 : st.n_preds;
+        d.n_preds[s] = (uint8_t)np;
+        for (int k = 0; k < np; ++k) {
+            const siesta_pred& p = st.preds[k];
+            if ((p.attr != SIESTA_ATTR_POSITION && p.attr != SIESTA_ATTR_TIMESTAMP) ||
+                (p.op != SIESTA_OP_LE && p.op != SIESTA_OP_GE) || p.ref_state < 0 || p.ref_state >= nfa->n_states ||
+                p.constant < 0) {
+                set_error("malformed predicate (attr/op/ref_state/constant)");
+                return SIESTA_E_INVALID;
+            }
+            d.p_attr[s][k] = (uint8_t)p.attr;
+            d.p_op[s][k] = (uint8_t)p.op;
+            d.p_ref[s][k] = (uint8_t)p.ref_state;
+            d.p_c[s][k] = p.constant;
+            d.has_vv |= (uint8_t)(1u << p.ref_state);
+            d.need_vv = 1;
+        }
+    }
+    if (flags & SIESTA_F_MODE_HEAD) {
+        // Engine.createNewRun's trailing block (Engine.java:983-996) only acts when states[1] is
+        // kleeneClosure*, and throws for single-state NFAs; both have no defined reference output.
+        if (nfa->n_states < 2 || nfa->states[1].kind == SIESTA_STATE_KLEENE_STAR) {
+            set_error("SIESTA_F_MODE_HEAD: the reference's HEAD engine has no defined output for this NFA "
+                      "(state 1 is kleeneClosure* or the NFA has one state); see DESIGN.md");
+            return SIESTA_E_UNSUPPORTED;
+        }
+    }
+    *out = d;
+    return SIESTA_OK;
+}
+
+
+// Per-activity lookup: bit k = the type belongs to state k (State.checkEventType / AdditionalState.checkEventType);
+// bit 8+k = the type is state k's first type (State.getEventType, used by Engine.java:661).
+void build_lut(const siesta_nfa* nfa, const DevNfa& dn, int32_t n_activities, uint32_t flags, std::vector<uint16_t>& lut,
+               int* needs_ts, int* n_positive) {
+    lut.assign((size_t)std::max(1, n_activities), 0);
+    bool time_pred = false;
+    int np = 0;
+    for (int s = 0; s < nfa->n_states; ++s) {
+        const siesta_state& st = nfa->states[s];
+        if (st.kind != SIESTA_STATE_NEGATIVE) ++np;
+        for (int k = 0; k < st.n_types; ++k) {
+            const int ty = st.types[k];
+            if (ty < 0 || ty >= n_activities) continue;  // activity absent from this log: never matches
+            lut[ty] |= (uint16_t)(1u << s);
+            if (k == 0) lut[ty] |= (uint16_t)(1u << (8 + s));
+        }
+        for (int k = 0; k < dn.n_preds[s]; ++k) time_pred |= st.preds[k].attr == SIESTA_ATTR_TIMESTAMP;
+    }
+    const bool evt_pos = (flags & SIESTA_F_EVT_POS) != 0;
+    const bool return_all = (flags & SIESTA_F_RETURN_ALL) != 0;
+    // relative seconds are needed by time predicates and by Occurrence.overlaps on the EventTs route
+    *needs_ts = (!evt_pos && (time_pred || return_all)) ? 1 : 0;
+    *n_positive = np;
+}
+
+}  // namespace siesta

@@ -1,0 +1,171 @@
+"""Host-side mirror of the reference's interface for the verification path.
+
+Names, argument meaning and error behaviour follow the Java classes so the parity tests read like the
+reference's own (paths relative to src/main/java/com/datalab/siesta/queryprocessor/):
+  EventSymbol            model/Events/EventSymbol.java
+  GapConstraint / TimeConstraint   model/Constraints/*.java
+  ComplexPattern         model/Patterns/ComplexPattern.java  (getNfa / getNfaWithoutConstraints)
+  Occurrence(s)          model/Occurrence.java, model/Occurrences.java
+  SaseConnector          SaseConnection/SaseConnector.java   (evaluate)
+All compute happens in libsiesta_gpu (CUDA); nothing here evaluates patterns on the CPU.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _abi
+from ._lib import check, lib
+
+_SYM = {"_": _abi.SYM_NORMAL, "": _abi.SYM_NORMAL, "+": _abi.SYM_PLUS, "*": _abi.SYM_STAR, "!": _abi.SYM_NOT,
+        "||": _abi.SYM_OR}
+_GRAN = {"seconds": _abi.GRAN_SECONDS, "minutes": _abi.GRAN_MINUTES, "hours": _abi.GRAN_HOURS}
+
+
+class ActivityDictionary:
+    """Activity name <-> dense id.  Names are folded case-insensitively because the engine compares event
+    types with equalsIgnoreCase (edu/umass/cs/sase/query/State.java:135-137)."""
+
+    def __init__(self, names=()):
+        self._ids: Dict[str, int] = {}
+        self.names: List[str] = []
+        for n in names:
+            self.add(n)
+
+    def add(self, name):
+        k = name.casefold()
+        if k not in self._ids:
+            self._ids[k] = len(self.names)
+            self.names.append(name)
+        return self._ids[k]
+
+    def id(self, name):
+        """-1 for a name the log has never seen (it can then never match an event)."""
+        return self._ids.get(name.casefold(), -1)
+
+    def __len__(self):
+        return len(self.names)
+
+
+@dataclass
+class EventSymbol:
+    name: str
+    position: int
+    symbol: str = "_"
+
+
+@dataclass
+class Constraint:
+    posA: int
+    posB: int
+    constraint: int
+    method: str = "within"  # "within" | "atleast"
+
+
+@dataclass
+class GapConstraint(Constraint):
+    pass
+
+
+@dataclass
+class TimeConstraint(Constraint):
+    granularity: str = "seconds"
+
+
+@dataclass
+class ComplexPattern:
+    eventsWithSymbols: List[EventSymbol] = field(default_factory=list)
+    constraints: List[Constraint] = field(default_factory=list)
+
+    def getEventTypes(self):
+        return {e.name for e in self.eventsWithSymbols}
+
+    def _compile(self, activities: ActivityDictionary, only_appearances):
+        n = len(self.eventsWithSymbols)
+        syms = (_abi.EventSymbolC * max(n, 1))()
+        for i, e in enumerate(self.eventsWithSymbols):
+            if e.symbol not in _SYM:
+                raise ValueError(f"unknown symbol {e.symbol!r}")
+            syms[i].activity, syms[i].position, syms[i].symbol = activities.id(e.name), e.position, _SYM[e.symbol]
+        nc = len(self.constraints)
+        cs = (_abi.ConstraintC * max(nc, 1))()
+        for i, c in enumerate(self.constraints):
+            cs[i].pos_a, cs[i].pos_b, cs[i].value = c.posA, c.posB, c.constraint
+            cs[i].kind = _abi.CONSTRAINT_TIME if isinstance(c, TimeConstraint) else _abi.CONSTRAINT_GAP
+            # SIESTAPattern.generatePredicates: "within" -> <=, anything else -> >= (SIESTAPattern.java:136-145)
+            cs[i].method = _abi.METHOD_WITHIN if c.method == "within" else _abi.METHOD_ATLEAST
+            cs[i].granularity = _GRAN.get(getattr(c, "granularity", "seconds"), _abi.GRAN_SECONDS)
+        nfa = _abi.Nfa()
+        check(lib().siesta_pattern_compile(syms, n, cs, nc, 1 if only_appearances else 0, C.byref(nfa)))
+        return nfa
+
+    def getNfa(self, activities):
+        return self._compile(activities, False)
+
+    def getNfaWithoutConstraints(self, activities):
+        return self._compile(activities, True)
+
+
+@dataclass
+class EventBoth:
+    name: str
+    position: int
+    timestamp_ms: Optional[int]
+
+
+@dataclass
+class Occurrence:
+    occurrence: List[EventBoth]
+
+
+@dataclass
+class Occurrences:
+    traceID: object
+    occurrences: List[Occurrence]
+
+
+class SaseConnector:
+    """evaluate(pattern, log, onlyAppearances) -> List[Occurrences], already passed through
+    Occurrences.clearOccurrences(returnAll) like QueryPlanPatternDetection.execute does (:121-122)."""
+
+    def __init__(self, activities: ActivityDictionary, trace_ids=None, positions_mode=False):
+        self.activities = activities
+        self.trace_ids = trace_ids
+        self.positions_mode = positions_mode  # events are EventPos (metadata mode "positions") instead of EventTs
+
+    def flags(self, only_appearances=False, return_all=False):
+        f = 0
+        if only_appearances:
+            f |= _abi.F_ONLY_APPEARANCES
+        if return_all:
+            f |= _abi.F_RETURN_ALL
+        if self.positions_mode:
+            f |= _abi.F_EVT_POS
+        return f
+
+    def evaluate_raw(self, pattern, log, only_appearances=False, return_all=False, cand=None):
+        nfa = pattern.getNfaWithoutConstraints(self.activities) if only_appearances else pattern.getNfa(self.activities)
+        res = log.detect(nfa, cand=cand, flags=self.flags(only_appearances, return_all))
+        if res.n_ref_errors:
+            # SaseConnector.java:60-62 rethrows engine exceptions as RuntimeException: the whole request fails
+            raise RuntimeError(f"the reference engine throws on {res.n_ref_errors} trace(s), first: "
+                               f"{int(res.err_trace_idx[0])}")
+        return res
+
+    def evaluate(self, pattern, log, onlyAppearances=False, returnAll=False, cand=None):
+        res = self.evaluate_raw(pattern, log, onlyAppearances, returnAll, cand)
+        out = []
+        names = self.activities.names
+        for i, t in enumerate(res.trace_idx):
+            occs = []
+            for o in range(res.occ_off[i], res.occ_off[i + 1]):
+                evs = []
+                for e in range(res.ev_off[o], res.ev_off[o + 1]):
+                    pos = int(res.ev_pos[e]) if self.positions_mode else int(res.ev_rank[e])
+                    ts = None if self.positions_mode else int(res.ev_ts_ms[e])
+                    evs.append(EventBoth(names[res.ev_act[e]], pos, ts))
+                occs.append(Occurrence(evs))
+            tid = self.trace_ids[t] if self.trace_ids is not None else int(t)
+            out.append(Occurrences(tid, occs))
+        return out

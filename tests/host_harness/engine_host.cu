@@ -1,0 +1,142 @@
+// engine_host.cu — TEST HARNESS (not the product): runs the device engine (detect_engine.cuh), compiled for the
+// host, over a CSR log on the CPU so tests can compare it with the oracle without a GPU.  The filter and the
+// output assembly here are simple serial restatements of kernel K1's phases A and C.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../sequencedetectionqueryexecutor_b200/csrc/detect_engine.cuh"
+
+namespace siesta {
+static thread_local std::string t_err;
+void set_error(const std::string& m) { t_err = m; }
+std::atomic<long long> g_kernel_launches{0};
+}  // namespace siesta
+
+using namespace siesta;
+
+template <class T>
+static T* dup(const std::vector<T>& v) {
+    T* p = (T*)std::malloc(sizeof(T) * (v.size() ? v.size() : 1));
+    if (!v.empty()) std::memcpy(p, v.data(), sizeof(T) * v.size());
+    return p;
+}
+
+struct Out {
+    std::vector<int64_t> trace_idx, occ_off{0}, ev_off{0}, ev_ts, err;
+    std::vector<int32_t> ev_pos, ev_rank, ev_act;
+    int64_t emitted = 0;
+};
+
+template <int W, int R, int NF>
+static int run_one(const DevNfa& dn, const std::vector<uint32_t>& meta, const std::vector<int32_t>& ts, int needs_ts, uint32_t flags,
+                   std::vector<typename MaskOps<W>::T>& sel, unsigned* n_emitted) {
+    constexpr int NE = 32 * W;
+    const bool evt_pos = (flags & SIESTA_F_EVT_POS) != 0;
+    if ((int)meta.size() > NE) return 3;
+    TraceEvents ev{meta.data(), needs_ts ? ts.data() : nullptr, 1, (int)meta.size(), evt_pos};
+    auto* eng = new RunEngine<W, R, NF>(dn, ev);
+    BestEmit<W> be;
+    eng->run(be);
+    int status = 0;
+    if (eng->ovf) status = 3;
+    else if (eng->err) status = 2;
+    else if (be.n > 0) {
+        status = 1;
+        *n_emitted = be.n;
+        sel.assign(1, be.best);
+        if ((flags & SIESTA_F_RETURN_ALL) && be.n > 1) {
+            GreedyEmit<W, NE> ge(ev, be.best, evt_pos);
+            eng->run(ge);
+            if (ge.ovf || eng->ovf) status = 3;
+            else sel.assign(ge.sel, ge.sel + ge.nsel);
+        }
+    }
+    delete eng;
+    return status;
+}
+
+extern "C" const char* engine_host_last_error() { return siesta::t_err.c_str(); }
+
+extern "C" int engine_host_detect(const int64_t* trace_off, const int32_t* act, const int64_t* ts_ms, int64_t n_traces,
+                                  int32_t n_act, const siesta_nfa* nfa, const int64_t* cand, int64_t n_cand, uint32_t flags,
+                                  int64_t* n_wide, siesta_matches** out) {
+    DevNfa dn;
+    int rc = validate_nfa(nfa, flags, &dn);
+    if (rc) return rc;
+    std::vector<uint16_t> lut;
+    int needs_ts = 0, n_pos = 0;
+    build_lut(nfa, dn, n_act, flags, lut, &needs_ts, &n_pos);
+    const bool evt_pos = (flags & SIESTA_F_EVT_POS) != 0;
+    Out o;
+    *n_wide = 0;
+    const int64_t n = cand ? n_cand : n_traces;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t t = cand ? cand[i] : i;
+        const int64_t b0 = trace_off[t], b1 = trace_off[t + 1];
+        std::vector<uint32_t> meta;
+        std::vector<int32_t> ts;
+        long long t0 = 0;
+        for (int64_t p = b0; p < b1; ++p) {
+            const int a = act[p];
+            const uint32_t m = (a >= 0 && a < n_act) ? lut[a] : 0;
+            if (!m) continue;
+            if (meta.empty()) t0 = ts_ms[p];
+            meta.push_back(m | ((uint32_t)(p - b0) << 16));
+            ts.push_back((int)((ts_ms[p] - t0) / 1000));
+        }
+        if (meta.empty()) continue;
+        if (b1 - b0 > 65536) return SIESTA_E_UNSUPPORTED;
+        unsigned emitted = 0;
+        int status;
+        std::vector<uint32_t> sel1;
+        std::vector<unsigned long long> sel2;
+        bool wide = false;
+        status = run_one<1, 64, 64>(dn, meta, ts, needs_ts, flags, sel1, &emitted);
+        if (status == 3) {
+            wide = true;
+            ++*n_wide;
+            status = run_one<2, 1024, 128>(dn, meta, ts, needs_ts, flags, sel2, &emitted);
+            if (status == 3) return SIESTA_E_UNSUPPORTED;
+        }
+        if (status == 2) {
+            o.err.push_back(t);
+            continue;
+        }
+        if (status != 1) continue;
+        o.emitted += emitted;
+        o.trace_idx.push_back(t);
+        const size_t ns = wide ? sel2.size() : sel1.size();
+        for (size_t k = 0; k < ns; ++k) {
+            unsigned long long m = wide ? sel2[k] : sel1[k];
+            while (m) {
+                const int j = __builtin_ffsll((long long)m) - 1;
+                m &= m - 1;
+                const int src = (int)(meta[j] >> 16);
+                o.ev_pos.push_back(src);
+                o.ev_rank.push_back(j);
+                o.ev_act.push_back(act[b0 + src]);
+                const long long raw = ts_ms[b0 + src];
+                o.ev_ts.push_back(evt_pos ? raw : (long long)((int)((raw - t0) / 1000)) * 1000 + t0);
+            }
+            o.ev_off.push_back((int64_t)o.ev_pos.size());
+        }
+        o.occ_off.push_back((int64_t)o.ev_off.size() - 1);
+    }
+    siesta_matches* m = (siesta_matches*)std::calloc(1, sizeof(siesta_matches));
+    m->n_traces = (int64_t)o.trace_idx.size();
+    m->n_occurrences = (int64_t)o.ev_off.size() - 1;
+    m->n_events = (int64_t)o.ev_pos.size();
+    m->n_matches_emitted = o.emitted;
+    m->n_ref_errors = (int64_t)o.err.size();
+    m->trace_idx = dup(o.trace_idx);
+    m->occ_off = dup(o.occ_off);
+    m->ev_off = dup(o.ev_off);
+    m->ev_pos = dup(o.ev_pos);
+    m->ev_rank = dup(o.ev_rank);
+    m->ev_act = dup(o.ev_act);
+    m->ev_ts_ms = dup(o.ev_ts);
+    m->err_trace_idx = dup(o.err);
+    *out = m;
+    return 0;
+}

@@ -1,0 +1,179 @@
+"""Parity of the CUDA verification path (through the C-ABI) against the CPU oracle.  Bit-exact: matching
+trace ids, reference-throw trace ids, selected occurrences and every output column."""
+import numpy as np
+import pytest
+
+import oracle
+from sequencedetectionqueryexecutor_b200 import _abi as abi
+from tests import gen
+from tests.kat import KATS, STREAM_TYPES
+
+pytestmark = pytest.mark.gpu
+
+N_, P_, S_, X_, O_ = abi.STATE_NORMAL, abi.STATE_KLEENE_PLUS, abi.STATE_KLEENE_STAR, abi.STATE_NEGATIVE, abi.STATE_OR
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from sequencedetectionqueryexecutor_b200 import api
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def _check(ctx, off, act, ts, n_act, states, flags, cand=None):
+    nfa = abi.make_nfa(states)
+    log = ctx.load_log(off, act, ts, n_act)
+    try:
+        got = log.detect(nfa, cand=cand, flags=flags)
+    finally:
+        log.close()
+    want = oracle.detect(off, act, ts, nfa, cand=cand, flags=flags)
+    ok, why = got.same_as(want)
+    assert ok, f"mismatch in {why}: states={states} flags={flags}"
+    return got
+
+
+@pytest.mark.parametrize("kat", KATS, ids=[k["name"] for k in KATS])
+def test_reference_known_answer_tests(ctx, kat):
+    """The reference's engine KATs (stream A B A C D A B E as EventPos), through the GPU path."""
+    off = np.array([0, len(STREAM_TYPES)], dtype=np.int64)
+    act = np.array(STREAM_TYPES, dtype=np.int32)
+    ts = np.arange(len(STREAM_TYPES), dtype=np.int64) * 1000
+    got = _check(ctx, off, act, ts, 5, kat["states"], abi.F_EVT_POS)
+    assert got.n_matches_emitted == kat["expected"], kat["where"]
+    if kat["matches"]:
+        assert got.as_dict() == {0: [max(kat["matches"], key=len)]}
+    else:
+        assert got.n_traces == 0
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_nfas_all_kinds(ctx, seed):
+    rng = np.random.default_rng(5000 + seed)
+    n_ok = 0
+    for it in range(60):
+        n_act = int(rng.integers(3, 7))
+        off, act, ts = gen.make_log(300, 0, 24, n_act, seed=int(rng.integers(1 << 30)), max_gap_s=300,
+                                    jitter_ms=bool(rng.integers(0, 2)))
+        states = gen.random_nfa(rng, n_act)
+        flags = 0
+        if rng.random() < 0.5:
+            flags |= abi.F_EVT_POS
+        if rng.random() < 0.5:
+            flags |= abi.F_RETURN_ALL
+        if rng.random() < 0.15:
+            flags |= abi.F_ONLY_APPEARANCES
+        got = _check(ctx, off, act, ts, n_act, states, flags)
+        n_ok += got.n_ref_errors == 0
+    assert n_ok > 20
+
+
+@pytest.mark.parametrize("flags", [0, abi.F_RETURN_ALL, abi.F_EVT_POS, abi.F_EVT_POS | abi.F_RETURN_ALL])
+def test_baseline_config_shapes(ctx, flags):
+    # config 1: A_ B_ on 10k traces x ~40 events, 20 activities
+    off, act, ts = gen.make_log(10_000, 30, 50, 20, seed=0x51E57A01)
+    got = _check(ctx, off, act, ts, 20, [dict(kind=N_, types=[0]), dict(kind=N_, types=[1])], flags)
+    assert got.n_traces > 1000
+    # config 2 shape: a+ b* within 10 minutes
+    off, act, ts = gen.make_log(4000, 100, 100, 20, seed=0x51E57A02, max_gap_s=120)
+    st = [dict(kind=P_, types=[0]), dict(kind=S_, types=[1], preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 600)])]
+    got = _check(ctx, off, act, ts, 20, st, flags)
+    assert got.n_traces > 100
+    # config 5 shape: a, (b|c), !d, e, f ; gap within 10 (0,1), gap atleast 2 (3,4)
+    off, act, ts = gen.make_log(4000, 50, 50, 20, seed=0x51E57A05)
+    st = [dict(kind=N_, types=[0]), dict(kind=O_, types=[1, 2], preds=[(abi.ATTR_POSITION, abi.OP_LE, 0, 10)]),
+          dict(kind=X_, types=[3]), dict(kind=N_, types=[4]),
+          dict(kind=N_, types=[5], preds=[(abi.ATTR_POSITION, abi.OP_GE, 3, 2)])]
+    _check(ctx, off, act, ts, 20, st, flags)
+
+
+def test_ragged_and_empty_inputs(ctx):
+    # empty traces, traces with no relevant event, a single long trace, trace count not a multiple of the tile
+    off, act, ts = gen.make_log(1001, 0, 3, 4, seed=9)
+    _check(ctx, off, act, ts, 4, [dict(kind=N_, types=[0]), dict(kind=N_, types=[1])], 0)
+    off, act, ts = gen.make_log(3, 700, 900, 50, seed=10)
+    _check(ctx, off, act, ts, 50, [dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[2])], abi.F_RETURN_ALL)
+    # activity id unknown to the log and a log with zero events
+    off, act, ts = gen.make_log(50, 5, 9, 4, seed=11)
+    got = _check(ctx, off, act, ts, 4, [dict(kind=N_, types=[0]), dict(kind=N_, types=[17])], 0)
+    assert got.n_traces == 0
+    z = np.zeros(1, dtype=np.int64)
+    got = _check(ctx, np.zeros(6, dtype=np.int64), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int64), 4,
+                 [dict(kind=N_, types=[0])], 0)
+    assert got.n_traces == 0 and z[0] == 0
+
+
+def test_candidate_lists(ctx):
+    off, act, ts = gen.make_log(5000, 20, 40, 10, seed=12)
+    rng = np.random.default_rng(3)
+    cand = np.sort(rng.choice(5000, size=1777, replace=False)).astype(np.int64)
+    st = [dict(kind=N_, types=[0]), dict(kind=X_, types=[3]), dict(kind=N_, types=[1])]
+    got = _check(ctx, off, act, ts, 10, st, abi.F_RETURN_ALL, cand=cand)
+    assert set(got.trace_idx.tolist()) <= set(cand.tolist())
+    _check(ctx, off, act, ts, 10, st, 0, cand=np.zeros(0, dtype=np.int64))
+
+
+def test_wide_engine_path(ctx):
+    """Traces beyond the narrow configuration (32 relevant events / 64 live runs) re-run on the wide one."""
+    off, act, ts = gen.make_log(500, 20, 45, 3, seed=77)
+    _check(ctx, off, act, ts, 3, [dict(kind=P_, types=[0]), dict(kind=S_, types=[1])], 0)
+    _check(ctx, off, act, ts, 3, [dict(kind=N_, types=[0]), dict(kind=N_, types=[1]), dict(kind=N_, types=[2])], abi.F_RETURN_ALL)
+
+
+def test_limits_are_reported_not_silently_wrong(ctx):
+    from sequencedetectionqueryexecutor_b200._lib import SiestaError
+    off, act, ts = gen.make_log(4, 200, 200, 2, seed=5)  # ~100 relevant events per trace > 64
+    log = ctx.load_log(off, act, ts, 2)
+    with pytest.raises(SiestaError) as e:
+        log.detect(abi.make_nfa([dict(kind=N_, types=[0]), dict(kind=N_, types=[1])]))
+    log.close()
+    assert e.value.code == abi.E_UNSUPPORTED
+    log = ctx.load_log(*gen.make_log(4, 5, 5, 2, seed=5), 2)
+    with pytest.raises(SiestaError) as e:  # HEAD mode has no defined output when state 1 is kleeneClosure*
+        log.detect(abi.make_nfa([dict(kind=N_, types=[0]), dict(kind=S_, types=[1])]), flags=abi.F_MODE_HEAD)
+    log.close()
+    assert e.value.code == abi.E_UNSUPPORTED
+
+
+def test_evaluate_events_and_sase_connector_mirror(ctx):
+    """The reference-facing call shapes: SaseConnector.evaluate over host events, and the Python mirror."""
+    from sequencedetectionqueryexecutor_b200 import sase
+    off, act, ts = gen.make_log(2000, 30, 50, 20, seed=0x51E57A01, jitter_ms=True)
+    names = [f"act{i:02d}" for i in range(20)]
+    acts = sase.ActivityDictionary(names)
+    pattern = sase.ComplexPattern([sase.EventSymbol("ACT00", 0, "_"), sase.EventSymbol("act01", 1, "||"),
+                                   sase.EventSymbol("act02", 1, "_"), sase.EventSymbol("act03", 2, "!"),
+                                   sase.EventSymbol("act04", 3, "_")],
+                                  [sase.TimeConstraint(0, 1, 30, "within", "minutes")])
+    nfa = pattern.getNfa(acts)
+    want = oracle.detect(off, act, ts, nfa, flags=0)
+    got = ctx.evaluate_events(off, act, ts, 20, nfa, flags=0)
+    ok, why = got.same_as(want)
+    assert ok, why
+    log = ctx.load_log(off, act, ts, 20)
+    occs = sase.SaseConnector(acts).evaluate(pattern, log, onlyAppearances=False)
+    log.close()
+    assert len(occs) == want.n_traces
+    first = occs[0].occurrences[0].occurrence
+    assert [e.name for e in first][0] == "act00" and first[0].timestamp_ms == want.ev_ts_ms[0]
+
+
+def test_one_million_events_idempotent_and_sorted(ctx):
+    """Size-independent properties at a size the oracle does not need to see: ascending trace ids, CSR offsets
+    consistent, positions strictly increasing inside an occurrence, identical output on a second call."""
+    off, act, ts = gen.make_log(20_000, 40, 60, 20, seed=99)
+    log = ctx.load_log(off, act, ts, 20)
+    st = [dict(kind=P_, types=[0]), dict(kind=S_, types=[1], preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 600)])]
+    nfa = abi.make_nfa(st)
+    a = log.detect(nfa, flags=abi.F_RETURN_ALL)
+    b = log.detect(nfa, flags=abi.F_RETURN_ALL)
+    log.close()
+    assert a.same_as(b)[0]
+    assert np.all(np.diff(a.trace_idx) > 0)
+    assert a.occ_off[0] == 0 and a.occ_off[-1] == a.n_occurrences and a.ev_off[-1] == a.n_events
+    lens = np.diff(a.ev_off)
+    assert np.all(lens > 0)
+    inner = np.ones(a.n_events, dtype=bool)
+    inner[a.ev_off[:-1]] = False
+    assert np.all(np.diff(a.ev_pos)[inner[1:]] > 0)
