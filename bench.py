@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — events scanned/sec of the /detection verification path on B200 (BASELINE.json configs[1]).
+
+  python bench.py --gpus N --steps K --warmup W            # the CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+A step = one pass of the hot path (SaseConnector.evaluate + clearOccurrences == siesta_detect) over the
+whole synthetic log of this rank.  `value` has the log resident in HBM; `e2e` goes through the host-buffer
+C-ABI call (siesta_evaluate_events) with host->device and device->host copies inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from sequencedetectionqueryexecutor_b200 import _abi as abi  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: /detection Kleene pattern a+ b* with a within-10-minutes time constraint,
+    # 1M traces x 100 events (20 activity types, gaps U{1..120} s), 1 B200.  SURVEY.md §8(d) cfg 2.
+    "detection_kleene_1Mx100": dict(n_traces=1_000_000, min_len=100, max_len=100, n_act=20, max_gap_s=120, seed=0x51E57A02,
+                                    bytes_per_event=12,
+                                    states=[dict(kind=abi.STATE_KLEENE_PLUS, types=[0]),
+                                            dict(kind=abi.STATE_KLEENE_STAR, types=[1],
+                                                 preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 600)])]),
+}
+DEFAULT_WORKLOAD = "detection_kleene_1Mx100"
+
+
+def make_log_fast(n_traces, min_len, max_len, n_act, seed, max_gap_s, rank=0):
+    """Same distribution as tests/gen.make_log, vectorised for 10^8 events; keyed by (seed, rank)."""
+    rng = np.random.default_rng([seed, rank])
+    if min_len == max_len:
+        lens = np.full(n_traces, min_len, dtype=np.int64)
+    else:
+        lens = rng.integers(min_len, max_len + 1, size=n_traces, dtype=np.int64)
+    off = np.zeros(n_traces + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    E = int(off[-1])
+    act = rng.integers(0, n_act, size=E, dtype=np.int32)
+    ts = rng.integers(1, max_gap_s + 1, size=E, dtype=np.int64)
+    ts *= 1000
+    np.cumsum(ts, out=ts)
+    start = 1577836800000 + rng.integers(0, 30 * 86400, size=n_traces, dtype=np.int64) * 1000
+    first = np.minimum(off[:-1], max(E - 1, 0))
+    before = ts[first] - 0  # running sum at the first event of each trace (inclusive of its own gap)
+    shift = start - before
+    ts += np.repeat(shift, lens)
+    return off, act, ts
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(off, act, ts, nfa, n_sample_traces, threads):
+    """The oracle (port of the reference's engine) timed on a bounded sample of the same workload."""
+    import oracle
+    T = min(n_sample_traces, len(off) - 1)
+    e = int(off[T])
+    t0 = time.perf_counter()
+    res = oracle.detect(off[:T + 1], act[:e], ts[:e], nfa, flags=0, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return res, e / dt, dt, T
+
+
+def run_reference(args, wl, world, rank):
+    """--impl reference: the reference's own CPU implementation of the path (the oracle port; the Java original
+    cannot run here: no JVM) on all host threads, a bounded sample of the workload per step."""
+    if rank != 0:
+        return
+    states = wl["states"]
+    nfa = abi.make_nfa(states)
+    threads = os.cpu_count() or 1
+    n_sample = 40_000
+    off, act, ts = make_log_fast(n_sample, wl["min_len"], wl["max_len"], wl["n_act"], wl["seed"], wl["max_gap_s"])
+    import oracle
+    for _ in range(args.warmup):
+        oracle.detect(off, act, ts, nfa, flags=0, n_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.detect(off, act, ts, nfa, flags=0, n_threads=threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = len(act) / dt
+    sample = f"first {n_sample} traces x {wl['min_len']} events of the workload per step"
+    print(json.dumps({
+        "impl": "reference", "metric": "events scanned/sec (/detection verification)", "value": v, "unit": "events/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": args.workload, "pattern": "a+ b* within 10 minutes", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "events/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--traces", type=int, default=0, help="override traces per GPU (debugging; invalidates the metric)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    wl = dict(WORKLOADS[args.workload])
+    if args.traces:
+        wl["n_traces"] = args.traces
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, wl, world, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from sequencedetectionqueryexecutor_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic log of this rank (traces shard across ranks: weak scaling, fixed traces per GPU)
+    off, act, ts = make_log_fast(wl["n_traces"], wl["min_len"], wl["max_len"], wl["n_act"], wl["seed"], wl["max_gap_s"], rank)
+    T, E = len(off) - 1, len(act)
+    # pinned host copies: the e2e leg copies from these inside the timed region
+    h_off = torch.from_numpy(off).pin_memory()
+    h_act = torch.from_numpy(act).pin_memory()
+    h_ts = torch.from_numpy(ts).pin_memory()
+    d_off, d_act, d_ts = h_off.to(dev), h_act.to(dev), h_ts.to(dev)
+    nfa = abi.make_nfa(wl["states"])
+    ctx = api.Context(local_rank)
+    log = ctx.wrap_log(d_off, d_act, d_ts, wl["n_act"], max_trace_len=wl["max_len"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        dm = log.detect_device(nfa, flags=0)
+        if world > 1:
+            # the exchange step: every rank learns every shard's match list (trace ids of its matches)
+            cnt = torch.tensor([dm.n_traces], device=dev, dtype=torch.int64)
+            cnts = [torch.zeros_like(cnt) for _ in range(world)]
+            dist.all_gather(cnts, cnt)
+        out = (dm.n_traces, dm.n_occurrences, dm.n_events, dm.n_matches_emitted, dm.kernel_ms, dm.detect_ms)
+        dm.close()
+        return out
+
+    for _ in range(args.warmup):
+        r0 = step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = api.kernel_launches()
+    k_ms, d_ms = [], []
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = step_resident()
+        k_ms.append(r[4])
+        d_ms.append(r[5])
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = api.kernel_launches() - launches0
+    clocks = sampler.stop()
+    assert r[:4] == r0[:4], "result changed between steps"
+
+    t_step = torch.tensor([wall / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_step, op=dist.ReduceOp.MAX)
+    sec_per_step = float(t_step.item())
+    value = E * world / sec_per_step
+
+    # ---- e2e: the host-buffer C-ABI call (H2D of the events + verification + D2H of the occurrences)
+    e2e_steps = max(1, args.e2e_steps)
+    res = ctx.evaluate_events(h_off.numpy(), h_act.numpy(), h_ts.numpy(), wl["n_act"], nfa, flags=0)  # warm
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = ctx.evaluate_events(h_off.numpy(), h_act.numpy(), h_ts.numpy(), wl["n_act"], nfa, flags=0)
+    barrier()
+    e2e_sec = (time.perf_counter() - t0) / e2e_steps
+    t_e2e = torch.tensor([e2e_sec], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_sec = float(t_e2e.item())
+    h2d = 8 * (T + 1) + 12 * E
+    d2h = 8 * res.n_traces + 8 * (res.n_traces + 1) + 8 * (res.n_occurrences + 1) + (4 + 4 + 4 + 8) * res.n_events
+    assert (res.n_traces, res.n_occurrences, res.n_events) == tuple(r[:3])
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        det_ms = float(np.mean(d_ms))
+        # algorithmic bytes of one K1 launch: 12 B/event (int32 activity + int64 timestamp: the
+        # query has a time constraint) + 8 B/trace offsets + output bytes (trace id, offsets, 20 B/event columns)
+        out_bytes = d2h
+        alg_bytes = wl["bytes_per_event"] * E + 8 * T + out_bytes
+        achieved = alg_bytes / (det_ms * 1e-3) / 1e9
+        line = {
+            "metric": "events scanned/sec (/detection verification)", "value": value, "unit": "events/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": args.workload, "pattern": "a+ b* within 10 minutes (EventTs route, returnAll=false)",
+                       "traces_per_gpu": T, "events_per_gpu": E, "activities": wl["n_act"],
+                       "l2": "inputs (1.2 GB/GPU) larger than L2; no flush needed"},
+            "roofline": {"bound": "hbm", "kernel": "detect_kernel<1,64,64>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": det_ms, "all_kernels_ms": float(np.mean(k_ms))},
+            "e2e": {"value": E * world / e2e_sec, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_sec * 1e3, "call": "siesta_evaluate_events (host CSR in, host occurrences out)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "result": {"matching_traces": r[0], "occurrences": r[1], "events": r[2], "engine_matches": r[3]},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            n_sample = min(T, 20_000)
+            want, ev_s, dt, ns = cpu_baseline(off, act, ts, nfa, n_sample, 1)
+            # parity on the sample: the GPU result restricted to the sampled traces equals the oracle's
+            keep = res.trace_idx < ns
+            ok = (np.array_equal(res.trace_idx[keep], want.trace_idx) and
+                  np.array_equal(res.ev_pos[:want.n_events], want.ev_pos) and
+                  np.array_equal(res.ev_ts_ms[:want.n_events], want.ev_ts_ms))
+            line["cpu_baseline"] = {"value": ev_s, "unit": "events/s", "cores": 1, "kind": "port",
+                                    "sample": f"first {ns} traces ({int(off[ns])} events) of the same log, {dt:.1f} s",
+                                    "parity_on_sample": bool(ok)}
+        print(json.dumps(line))
+    log.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

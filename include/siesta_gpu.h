@@ -179,7 +179,8 @@ typedef struct siesta_matches {
     int32_t* ev_act;           /* [n_events] activity id                             */
     int64_t* ev_ts_ms;         /* [n_events] SaseEvent.getEventBoth timestamp: rel_s*1000 + t0 (SaseEvent.java:94-106) */
     int64_t* err_trace_idx;    /* [n_ref_errors] ascending                           */
-    double kernel_ms;          /* device time of the verification kernels            */
+    double kernel_ms;          /* device time of all kernels of the call (CUDA events) */
+    double detect_ms;          /* device time of the verification kernel K1 alone      */
 } siesta_matches;
 
 /* Replaces SaseConnector.evaluate(pattern, events, onlyAppearances) followed by
@@ -213,6 +214,7 @@ typedef struct siesta_dev_matches {
     int64_t* d_ev_ts_ms;
     int64_t* d_err_trace_idx;
     double kernel_ms;
+    double detect_ms;
     void* impl;
 } siesta_dev_matches;
 

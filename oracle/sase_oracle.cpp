@@ -646,6 +646,7 @@ int oracle_detect(const int64_t* trace_off, const int32_t* act, const int64_t* t
     m->ev_ts_ms = dup(ev_ts);
     m->err_trace_idx = dup(err);
     m->kernel_ms = ms;
+    m->detect_ms = ms;
     *out = m;
     return 0;
 }

@@ -53,7 +53,7 @@ class Matches(C.Structure):
                 ("ev_off", C.POINTER(C.c_int64)), ("ev_pos", C.POINTER(C.c_int32)),
                 ("ev_rank", C.POINTER(C.c_int32)), ("ev_act", C.POINTER(C.c_int32)),
                 ("ev_ts_ms", C.POINTER(C.c_int64)), ("err_trace_idx", C.POINTER(C.c_int64)),
-                ("kernel_ms", C.c_double)]
+                ("kernel_ms", C.c_double), ("detect_ms", C.c_double)]
 
 
 class DevMatches(C.Structure):
@@ -62,7 +62,7 @@ class DevMatches(C.Structure):
                 ("d_trace_idx", C.c_void_p), ("d_occ_off", C.c_void_p), ("d_ev_off", C.c_void_p),
                 ("d_ev_pos", C.c_void_p), ("d_ev_rank", C.c_void_p), ("d_ev_act", C.c_void_p),
                 ("d_ev_ts_ms", C.c_void_p), ("d_err_trace_idx", C.c_void_p),
-                ("kernel_ms", C.c_double), ("impl", C.c_void_p)]
+                ("kernel_ms", C.c_double), ("detect_ms", C.c_double), ("impl", C.c_void_p)]
 
 
 def make_nfa(states):
@@ -100,7 +100,7 @@ class MatchResult:
     """Host copy of a siesta_matches (CSR of selected occurrences per matching trace)."""
 
     __slots__ = ("n_traces", "n_occurrences", "n_events", "n_matches_emitted", "n_ref_errors", "trace_idx",
-                 "occ_off", "ev_off", "ev_pos", "ev_rank", "ev_act", "ev_ts_ms", "err_trace_idx", "kernel_ms")
+                 "occ_off", "ev_off", "ev_pos", "ev_rank", "ev_act", "ev_ts_ms", "err_trace_idx", "kernel_ms", "detect_ms")
 
     @classmethod
     def from_struct(cls, m):
@@ -108,6 +108,7 @@ class MatchResult:
         r = cls()
         r.n_traces, r.n_occurrences, r.n_events = m.n_traces, m.n_occurrences, m.n_events
         r.n_matches_emitted, r.n_ref_errors, r.kernel_ms = m.n_matches_emitted, m.n_ref_errors, m.kernel_ms
+        r.detect_ms = m.detect_ms
         r.trace_idx = _arr(m.trace_idx, m.n_traces, np.int64)
         r.occ_off = _arr(m.occ_off, m.n_traces + 1, np.int64)
         r.ev_off = _arr(m.ev_off, m.n_occurrences + 1, np.int64)

@@ -105,7 +105,7 @@ class EventLog:
 class DeviceMatches:
     def __init__(self, dm):
         self.dm = dm
-        for k in ("n_traces", "n_occurrences", "n_events", "n_matches_emitted", "n_ref_errors", "kernel_ms"):
+        for k in ("n_traces", "n_occurrences", "n_events", "n_matches_emitted", "n_ref_errors", "kernel_ms", "detect_ms"):
             setattr(self, k, getattr(dm, k))
 
     def close(self):

@@ -44,6 +44,11 @@ extern "C" int siesta_init(int32_t device_id, siesta_ctx** out) {
     c->device = device_id;
     c->sm_count = prop.multiProcessorCount;
     SIESTA_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // keep the stream-ordered pool warm between requests (workspaces are re-used, not returned to the driver)
+    cudaMemPool_t pool;
+    SIESTA_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, device_id));
+    unsigned long long keep = ~0ull;
+    SIESTA_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     *out = reinterpret_cast<siesta_ctx*>(c);
     return SIESTA_OK;
 }
@@ -219,6 +224,7 @@ extern "C" int siesta_detect(siesta_log* log, const siesta_nfa* nfa, const int64
         m->n_matches_emitted = dm.n_matches_emitted;
         m->n_ref_errors = dm.n_ref_errors;
         m->kernel_ms = dm.kernel_ms;
+        m->detect_ms = dm.detect_ms;
         if ((rc = fetch(&m->trace_idx, dm.d_trace_idx, dm.n_traces, stream)) ||
             (rc = fetch(&m->occ_off, dm.d_occ_off, dm.n_traces + 1, stream)) ||
             (rc = fetch(&m->ev_off, dm.d_ev_off, dm.n_occurrences + 1, stream)) ||

@@ -383,12 +383,17 @@ __global__ void set_tail_kernel(int64_t* occ_off, int64_t n_tr, int64_t n_occ, i
 // ---------------------------------------------------------------------------------- host side
 namespace {
 
+// Stream-ordered allocations from the device's default pool (kept warm: siesta_init raises the release
+// threshold), so a request costs no cudaMalloc/cudaFree round trips after the first one.
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
+    cudaStream_t s = nullptr;
+    explicit DevBuf(cudaStream_t stream) : s(stream) {}
+    DevBuf(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFreeAsync(p, s); }
     int alloc(size_t bytes) {
-        if (p) { cudaFree(p); p = nullptr; }
-        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        if (p) { cudaFreeAsync(p, s); p = nullptr; }
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, s);
         if (e != cudaSuccess) {
             set_error(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
             p = nullptr;
@@ -402,6 +407,8 @@ struct DevBuf {
 
 struct DevMatchesImpl {
     void* bufs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t free_stream = nullptr;
+    int device = 0;
 };
 
 template <int W, int R, int NF>
@@ -447,8 +454,9 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     const int64_t cap_occ = return_all ? wide : n;
     const int64_t cap_ev = (!return_all && !dn.any_kleene) ? n * std::max(1, n_positive) : wide;
 
-    DevBuf b_lut, b_nocc, b_nev, b_stage, b_stage_occ, b_counters, b_err, b_ovf, b_ovf2;
-    DevBuf s_occ_nev, s_ev_pos, s_ev_rank, s_ev_act, s_ev_ts, b_blk;
+    DevBuf b_lut(stream), b_nocc(stream), b_nev(stream), b_stage(stream), b_stage_occ(stream), b_counters(stream),
+        b_err(stream), b_ovf(stream), b_ovf2(stream);
+    DevBuf s_occ_nev(stream), s_ev_pos(stream), s_ev_rank(stream), s_ev_act(stream), s_ev_ts(stream), b_blk(stream);
     const size_t nn = (size_t)std::max<int64_t>(n, 1);
     if ((rc = b_lut.alloc(lut.size() * sizeof(uint16_t))) || (rc = b_nocc.alloc(nn * 4)) || (rc = b_nev.alloc(nn * 4)) ||
         (rc = b_stage.alloc(nn * 8)) || (rc = b_stage_occ.alloc(nn * 8)) || (rc = b_counters.alloc(8 * 8)) ||
@@ -459,9 +467,10 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
                      (rc = s_ev_ts.alloc((size_t)cap_ev * 8))))
         return rc;
 
-    cudaEvent_t ev0, ev1;
+    cudaEvent_t ev0, ev1, evd;
     SIESTA_CUDA_OK(cudaEventCreate(&ev0));
     SIESTA_CUDA_OK(cudaEventCreate(&ev1));
+    SIESTA_CUDA_OK(cudaEventCreate(&evd));
     SIESTA_CUDA_OK(cudaMemcpyAsync(b_lut.p, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
     SIESTA_CUDA_OK(cudaMemsetAsync(b_counters.p, 0, 64, stream));
     SIESTA_CUDA_OK(cudaEventRecord(ev0, stream));
@@ -496,6 +505,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     unsigned long long h_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (n > 0) {
         if ((rc = launch_detect<1, 64, 64>(ctx, stream, P, dn))) return rc;
+        SIESTA_CUDA_OK(cudaEventRecord(evd, stream));
         SIESTA_CUDA_OK(cudaMemcpyAsync(h_cnt, b_counters.p, 64, cudaMemcpyDeviceToHost, stream));
         SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
         if (h_cnt[4] > 0) {
@@ -523,7 +533,8 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     }
     const int64_t n_occ = (int64_t)h_cnt[0], n_ev = (int64_t)h_cnt[1], n_tr = (int64_t)h_cnt[6], n_err = (int64_t)h_cnt[3];
 
-    DevBuf f_trace, f_occ_off, f_ev_off, f_pos, f_rank, f_act, f_ts, f_err;
+    DevBuf f_trace(stream), f_occ_off(stream), f_ev_off(stream), f_pos(stream), f_rank(stream), f_act(stream), f_ts(stream),
+        f_err(stream);
     if ((rc = f_trace.alloc((size_t)n_tr * 8)) || (rc = f_occ_off.alloc((size_t)(n_tr + 1) * 8)) ||
         (rc = f_ev_off.alloc((size_t)(n_occ + 1) * 8)) || (rc = f_pos.alloc((size_t)n_ev * 4)) ||
         (rc = f_err.alloc((size_t)n_err * 8)))
@@ -575,10 +586,12 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
         SIESTA_CUDA_OK(cudaMemcpyAsync(f_err.p, h.data(), (size_t)n_err * 8, cudaMemcpyHostToDevice, stream));
     }
     SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
-    float ms = 0.f;
+    float ms = 0.f, dms = 0.f;
     SIESTA_CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1));
+    if (n > 0) SIESTA_CUDA_OK(cudaEventElapsedTime(&dms, ev0, evd));
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
+    cudaEventDestroy(evd);
 
     DevMatchesImpl* impl = new DevMatchesImpl();
     out->n_traces = n_tr;
@@ -587,6 +600,9 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     out->n_matches_emitted = (int64_t)h_cnt[2];
     out->n_ref_errors = n_err;
     out->kernel_ms = ms;
+    out->detect_ms = dms;
+    impl->free_stream = ctx->stream;
+    impl->device = ctx->device;
     impl->bufs[0] = out->d_trace_idx = (int64_t*)f_trace.release();
     impl->bufs[1] = out->d_occ_off = (int64_t*)f_occ_off.release();
     impl->bufs[2] = out->d_ev_off = (int64_t*)f_ev_off.release();
@@ -615,8 +631,9 @@ extern "C" int siesta_detect_device(siesta_log* log, const siesta_nfa* nfa, cons
 extern "C" void siesta_dev_matches_free(siesta_dev_matches* m) {
     if (!m || !m->impl) return;
     siesta::DevMatchesImpl* impl = reinterpret_cast<siesta::DevMatchesImpl*>(m->impl);
+    cudaSetDevice(impl->device);
     for (void* p : impl->bufs)
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, impl->free_stream);
     delete impl;
     m->impl = nullptr;
 }

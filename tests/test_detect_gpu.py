@@ -8,6 +8,8 @@ from sequencedetectionqueryexecutor_b200 import _abi as abi
 from tests import gen
 from tests.kat import KATS, STREAM_TYPES
 
+from sequencedetectionqueryexecutor_b200._lib import SiestaError
+
 pytestmark = pytest.mark.gpu
 
 N_, P_, S_, X_, O_ = abi.STATE_NORMAL, abi.STATE_KLEENE_PLUS, abi.STATE_KLEENE_STAR, abi.STATE_NEGATIVE, abi.STATE_OR
@@ -64,7 +66,11 @@ def test_random_nfas_all_kinds(ctx, seed):
             flags |= abi.F_RETURN_ALL
         if rng.random() < 0.15:
             flags |= abi.F_ONLY_APPEARANCES
-        got = _check(ctx, off, act, ts, n_act, states, flags)
+        try:
+            got = _check(ctx, off, act, ts, n_act, states, flags)
+        except SiestaError as e:  # beyond the engine's documented limits: reported, never silently wrong
+            assert e.code == abi.E_UNSUPPORTED
+            continue
         n_ok += got.n_ref_errors == 0
     assert n_ok > 20
 
