@@ -162,6 +162,11 @@ int64_t siesta_log_n_events(const siesta_log* log);
                                         (model/Utils/Utils.java:59-62); default EventTs/EventBoth:
                                         id = list index, timestamp = (t - t0)/1000 s (Utils.java:51-58)    */
 #define SIESTA_F_NO_EVENT_COLUMNS 16u /* return only trace_idx/occ_off/ev_off/ev_pos                       */
+#define SIESTA_F_COUNT_MATCHES 32u    /* also report the exact number of engine matches before selection
+                                         (n_matches_emitted); without it the engine may drop runs that can
+                                         never yield the selected occurrence and reports -1              */
+#define SIESTA_F_LITERAL_RUNS 64u     /* keep the run list exactly as the Java engine does (no inert-run pruning,
+                                         no dominated-run merging); same output, slower; for audits and tests  */
 
 /* Result of SaseConnector.evaluate + Occurrences.clearOccurrences, CSR-shaped.
  * Host memory owned by the library. */
@@ -169,7 +174,8 @@ typedef struct siesta_matches {
     int64_t n_traces;          /* traces with >= 1 match                             */
     int64_t n_occurrences;     /* selected occurrences over all traces               */
     int64_t n_events;          /* events over all selected occurrences               */
-    int64_t n_matches_emitted; /* engine matches before selection (Profiling.numberOfMatches) */
+    int64_t n_matches_emitted; /* engine matches before selection (Profiling.numberOfMatches); -1 unless
+                                  SIESTA_F_COUNT_MATCHES, SIESTA_F_RETURN_ALL or SIESTA_F_LITERAL_RUNS      */
     int64_t n_ref_errors;      /* traces on which the Java engine would throw        */
     int64_t* trace_idx;        /* [n_traces] ascending                               */
     int64_t* occ_off;          /* [n_traces+1] -> occurrence range of a trace        */

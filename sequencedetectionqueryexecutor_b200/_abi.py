@@ -19,6 +19,8 @@ F_ONLY_APPEARANCES = 2
 F_MODE_HEAD = 4
 F_EVT_POS = 8
 F_NO_EVENT_COLUMNS = 16
+F_COUNT_MATCHES = 32
+F_LITERAL_RUNS = 64
 
 E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMEM, E_REFERENCE_THROWS = -1, -2, -3, -4, -5
 
@@ -132,9 +134,11 @@ class MatchResult:
     def same_as(self, other, columns=("ev_pos", "ev_rank", "ev_act", "ev_ts_ms")):
         import numpy as np
         keys = ["trace_idx", "occ_off", "ev_off", "err_trace_idx"] + list(columns)
-        for k in ("n_traces", "n_occurrences", "n_events", "n_matches_emitted", "n_ref_errors"):
+        for k in ("n_traces", "n_occurrences", "n_events", "n_ref_errors"):
             if getattr(self, k) != getattr(other, k):
                 return False, k
+        if self.n_matches_emitted >= 0 and other.n_matches_emitted >= 0 and self.n_matches_emitted != other.n_matches_emitted:
+            return False, "n_matches_emitted"
         for k in keys:
             a, b = getattr(self, k), getattr(other, k)
             if a is None or b is None:

@@ -53,7 +53,7 @@ struct DevNfa {
     uint8_t has_vv;     // bit k: some predicate references state k (NFA.hasValueVector, S/query/NFA.java:462-469)
     uint8_t need_vv;
     uint8_t any_kleene;
-    uint8_t pad;
+    uint8_t merge_safe;  // dominated-run merging is exact for this NFA (see validate_nfa)
     uint8_t p_attr[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];
     uint8_t p_op[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];
     uint8_t p_ref[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];

@@ -80,6 +80,8 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
     const bool evt_pos = (P.flags & SIESTA_F_EVT_POS) != 0;
     const bool return_all = (P.flags & SIESTA_F_RETURN_ALL) != 0;
     const bool all_cols = (P.flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
+    const bool prune = (P.flags & SIESTA_F_LITERAL_RUNS) == 0;
+    const bool dedup = prune && !return_all && (P.flags & SIESTA_F_COUNT_MATCHES) == 0;
 
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
         // ------------------------------------------------------------------ phase A
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
                 TraceEvents ev{s_meta + threadIdx.x, P.needs_ts ? s_ts + threadIdx.x : nullptr, NT, my_cnt, evt_pos};
                 RunEngine<W, R, NF> eng(nfa, ev);
                 BestEmit<W> be;
-                eng.run(be);
+                eng.run(be, prune, dedup);
                 if (eng.ovf) status = ST_OVF;
                 else if (eng.err) status = ST_ERR;
                 else if (be.n > 0) {
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
                     nsel = 1;
                     if (return_all && be.n > 1) {
                         GreedyEmit<W, NE> ge(ev, best, evt_pos);
-                        eng.run(ge);
+                        eng.run(ge, prune, false);
                         if (ge.ovf || eng.ovf) status = ST_OVF;
                         else {
                             nsel = ge.nsel;
@@ -597,7 +599,8 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     out->n_traces = n_tr;
     out->n_occurrences = n_occ;
     out->n_events = n_ev;
-    out->n_matches_emitted = (int64_t)h_cnt[2];
+    const bool counted = (flags & (SIESTA_F_COUNT_MATCHES | SIESTA_F_RETURN_ALL | SIESTA_F_LITERAL_RUNS)) != 0;
+    out->n_matches_emitted = counted ? (int64_t)h_cnt[2] : -1;
     out->n_ref_errors = n_err;
     out->kernel_ms = ms;
     out->detect_ms = dms;

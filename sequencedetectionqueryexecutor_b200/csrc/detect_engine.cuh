@@ -358,14 +358,105 @@ struct RunEngine {
         }
     }
 
+    // ---- exact reductions of the run list (not in the reference; they never change its output) -------------
+    //
+    // (1) inert runs.  A run that is full but not complete is skipped for ever (Engine.java:364).  A run whose
+    //     current state carries a "within" predicate (attr <= $ref.attr + c) that fails at the current event fails
+    //     at every later event too, because position and timestamp never decrease along the stream, PROVIDED the
+    //     referenced value can no longer change: no run of the same family (the runs sharing one value vector)
+    //     sits at or before the referenced state.  Such a run never takes another event, never forks, never
+    //     emits and never writes the value vector; the reference keeps it only because SIESTA disables the
+    //     engine's time window (NFAWrapper.java:21-25).  Negative states and not-yet-initialised kleeneClosure*
+    //     states are never pruned (they can move without passing a predicate: Engine.java:658-671, Run.java:200-203).
+    // (2) dominated runs (only when just the first-largest occurrence is wanted: returnAll=false and no exact
+    //     match count).  Two runs with the same packed state and the same family take the same events, fork and
+    //     emit at the same events for ever; their matches differ only by the events selected so far.  Of the two,
+    //     the one with fewer events (or, at equal size, the later one in list order) can never be the FIRST
+    //     occurrence of maximal size (Occurrences.java:60-69), so it is dropped.  The survivor keeps its own list
+    //     position, so emission order among the remaining runs is untouched.  Runs that selected nothing yet are
+    //     never merged (Engine.checkProceed throws on them: Run.java:285).  Because runs are evaluated one after
+    //     the other inside an event and siblings share one value vector, "same events for ever" needs the static
+    //     condition DevNfa::merge_safe (nfa.cpp): no event type both writes a referenced slot and reads it.
+    bool opt_prune, opt_dedup, ts_monotone;
+    uint8_t fmin[NF];
+
+    SIESTA_HD bool is_inert(int j, mask_t mask, uint32_t meta, int fam, bool fam_shared) const {
+        if (meta & M_FULL) return true;
+        if (!opt_prune || !nfa.need_vv) return false;
+        const int cur = M_CUR(meta);
+        if (cur >= nfa.n_states) return false;
+        const int kind = nfa.kind[cur];
+        if (kind == SIESTA_STATE_NEGATIVE) return false;
+        if (kind == SIESTA_STATE_KLEENE_STAR && !(meta & M_KINIT)) return false;
+        const int np = nfa.n_preds[cur];
+        for (int k = 0; k < np; ++k) {
+            if (nfa.p_op[cur][k] != SIESTA_OP_LE) continue;
+            const int ref = nfa.p_ref[cur][k];
+            if (ref >= cur) continue;                       // self / forward reference
+            if (fam_shared && fmin[fam] <= ref) continue;   // a sibling can still rewrite the slot
+            const int rj = vv_get(fam, ref);
+            if (rj < 0) return true;                        // null for ever -> predicate false for ever
+            const int a = nfa.p_attr[cur][k];
+            if (a == SIESTA_ATTR_TIMESTAMP && !ts_monotone) continue;
+            if ((long long)ev.attr(j, a) > (long long)ev.attr(rj, a) + nfa.p_c[cur][k]) return true;
+        }
+        (void)mask;
+        return false;
+    }
+
+    SIESTA_HD void reduce_runs(int j) {
+        const bool fam_shared = nfa.any_kleene && nfa.need_vv;
+        if (opt_prune && fam_shared) {
+            for (int r = 0; r < nruns; ++r) fmin[rfam[r]] = 15;
+            for (int r = 0; r < nruns; ++r) {
+                if (M_MARKS(rmeta[r])) continue;
+                const int c = M_CUR(rmeta[r]);
+                if (c < fmin[rfam[r]]) fmin[rfam[r]] = (uint8_t)c;
+            }
+        }
+        const bool dedup = opt_dedup && nfa.merge_safe && (!nfa.need_vv || nfa.any_kleene);
+        bool any_drop = false;
+        for (int r = 0; r < nruns; ++r) {
+            const uint32_t meta = rmeta[r];
+            if (M_MARKS(meta)) { any_drop = true; continue; }   // cleanRuns (:1404-1418)
+            const mask_t mask = rmask[r];
+            const int fam = rfam[r];
+            bool drop = is_inert(j, mask, meta, fam, fam_shared);
+            if (!drop && dedup && mask != 0) {
+                const int cnt = MO::popc(mask);
+                for (int q = 0; q < nruns && !drop; ++q) {
+                    if (q == r || rmeta[q] != meta || rfam[q] != fam) continue;   // marked runs differ in meta
+                    const mask_t mq = rmask[q];
+                    if (mq == 0) continue;
+                    const int cq = MO::popc(mq);
+                    drop = cq > cnt || (cq == cnt && q < r);
+                }
+            }
+            if (drop) { rmeta[r] = meta | (1u << M_MARK_SHIFT) | (1u << 31); any_drop = true; }
+        }
+        if (!any_drop) return;
+        int k = 0;
+        for (int r = 0; r < nruns; ++r) {
+            if (M_MARKS(rmeta[r])) continue;
+            if (k != r) { rmask[k] = rmask[r]; rmeta[k] = rmeta[r]; rfam[k] = rfam[r]; }
+            ++k;
+        }
+        nruns = k;
+    }
+
     // Engine.runSkipTillNextEngine (Engine.java:207-224) over one trace.
     template <class Emit>
-    SIESTA_HD void run(Emit& emit) {
+    SIESTA_HD void run(Emit& emit, bool prune, bool dedup) {
         nruns = 0;
         nfam = 0;
         err = false;
         ovf = false;
         n_emitted = 0;
+        opt_prune = prune;
+        opt_dedup = dedup;
+        ts_monotone = true;
+        if (prune && ev.ts && !ev.evt_pos)
+            for (int j = 1; j < ev.n; ++j) ts_monotone = ts_monotone && ev.ts[j * ev.stride] >= ev.ts[(j - 1) * ev.stride];
         for (int j = 0; j < ev.n; ++j) {
             const uint32_t w = ev.word(j);
             const int n0 = nruns;  // runs appended while evaluating this event are not visited (:361)
@@ -374,14 +465,7 @@ struct RunEngine {
                 evaluate(j, w, r, emit);
                 if (err || ovf) return;
             }
-            // cleanRuns (:1404-1418): stable removal of marked runs
-            int k = 0;
-            for (int r = 0; r < nruns; ++r) {
-                if (M_MARKS(rmeta[r])) continue;
-                if (k != r) { rmask[k] = rmask[r]; rmeta[k] = rmeta[r]; rfam[k] = rfam[r]; }
-                ++k;
-            }
-            nruns = k;
+            if (nruns) reduce_runs(j);  // includes cleanRuns (:1404-1418): stable removal of marked runs
             create_new_run(j, w, emit);
             if (err || ovf) return;
         }

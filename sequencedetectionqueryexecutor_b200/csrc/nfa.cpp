@@ -57,6 +57,31 @@ int validate_nfa(const siesta_nfa* nfa, uint32_t flags, DevNfa* out) {
             d.need_vv = 1;
         }
     }
+    // Dominated-run merging (detect_engine.cuh) treats two runs with the same packed state and the same
+    // value-vector family as interchangeable.  Inside ONE event the engine evaluates runs sequentially and
+    // a sibling may rewrite the shared value vector between them (Run.clone is shallow, Run.java:319-327),
+    // so that only holds if no event type can both write a referenced slot (an event of state `ref`'s
+    // types) and trigger a predicate that reads it (an event of the predicate's own state's types).
+    d.merge_safe = 1;
+    for (int s = 0; s < nfa->n_states && d.merge_safe; ++s)
+        for (int k = 0; k < d.n_preds[s] && d.merge_safe; ++k) {
+            const siesta_state& a = nfa->states[s];
+            const siesta_state& b = nfa->states[nfa->states[s].preds[k].ref_state];
+            for (int i = 0; i < a.n_types; ++i)
+                for (int j = 0; j < b.n_types; ++j)
+                    if (a.types[i] == b.types[j]) d.merge_safe = 0;
+        }
+    // kleeneClosureInitialized is sticky across states (Run.proceed never resets it), so a run entering a SECOND
+    // Kleene state that owns a value vector calls updateValueVector on a slot only a sibling may have initialised
+    // (Run.java:266-274, 361): whether it throws depends on its list position relative to that sibling.
+    {
+        bool seen_kleene = false;
+        for (int s = 0; s < nfa->n_states; ++s) {
+            const bool kl = nfa->states[s].kind == SIESTA_STATE_KLEENE_PLUS || nfa->states[s].kind == SIESTA_STATE_KLEENE_STAR;
+            if (kl && seen_kleene && ((d.has_vv >> s) & 1u)) d.merge_safe = 0;
+            seen_kleene = seen_kleene || kl;
+        }
+    }
     if (flags & SIESTA_F_MODE_HEAD) {
         // Engine.createNewRun's trailing block (Engine.java:983-996) only acts when states[1] is
         // kleeneClosure*, and throws for single-state NFAs; both have no defined reference output.

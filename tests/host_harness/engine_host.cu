@@ -36,8 +36,10 @@ static int run_one(const DevNfa& dn, const std::vector<uint32_t>& meta, const st
     if ((int)meta.size() > NE) return 3;
     TraceEvents ev{meta.data(), needs_ts ? ts.data() : nullptr, 1, (int)meta.size(), evt_pos};
     auto* eng = new RunEngine<W, R, NF>(dn, ev);
+    const bool prune = (flags & SIESTA_F_LITERAL_RUNS) == 0;
+    const bool dedup = prune && !(flags & SIESTA_F_RETURN_ALL) && !(flags & SIESTA_F_COUNT_MATCHES);
     BestEmit<W> be;
-    eng->run(be);
+    eng->run(be, prune, dedup);
     int status = 0;
     if (eng->ovf) status = 3;
     else if (eng->err) status = 2;
@@ -47,7 +49,7 @@ static int run_one(const DevNfa& dn, const std::vector<uint32_t>& meta, const st
         sel.assign(1, be.best);
         if ((flags & SIESTA_F_RETURN_ALL) && be.n > 1) {
             GreedyEmit<W, NE> ge(ev, be.best, evt_pos);
-            eng->run(ge);
+            eng->run(ge, prune, false);
             if (ge.ovf || eng->ovf) status = 3;
             else sel.assign(ge.sel, ge.sel + ge.nsel);
         }
@@ -127,7 +129,7 @@ extern "C" int engine_host_detect(const int64_t* trace_off, const int32_t* act, 
     m->n_traces = (int64_t)o.trace_idx.size();
     m->n_occurrences = (int64_t)o.ev_off.size() - 1;
     m->n_events = (int64_t)o.ev_pos.size();
-    m->n_matches_emitted = o.emitted;
+    m->n_matches_emitted = (flags & (SIESTA_F_COUNT_MATCHES | SIESTA_F_RETURN_ALL | SIESTA_F_LITERAL_RUNS)) ? o.emitted : -1;
     m->n_ref_errors = (int64_t)o.err.size();
     m->trace_idx = dup(o.trace_idx);
     m->occ_off = dup(o.occ_off);

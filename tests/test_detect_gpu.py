@@ -42,7 +42,7 @@ def test_reference_known_answer_tests(ctx, kat):
     off = np.array([0, len(STREAM_TYPES)], dtype=np.int64)
     act = np.array(STREAM_TYPES, dtype=np.int32)
     ts = np.arange(len(STREAM_TYPES), dtype=np.int64) * 1000
-    got = _check(ctx, off, act, ts, 5, kat["states"], abi.F_EVT_POS)
+    got = _check(ctx, off, act, ts, 5, kat["states"], abi.F_EVT_POS | abi.F_COUNT_MATCHES)
     assert got.n_matches_emitted == kat["expected"], kat["where"]
     if kat["matches"]:
         assert got.as_dict() == {0: [max(kat["matches"], key=len)]}
@@ -66,6 +66,10 @@ def test_random_nfas_all_kinds(ctx, seed):
             flags |= abi.F_RETURN_ALL
         if rng.random() < 0.15:
             flags |= abi.F_ONLY_APPEARANCES
+        if rng.random() < 0.25:
+            flags |= abi.F_COUNT_MATCHES
+        if rng.random() < 0.15:
+            flags |= abi.F_LITERAL_RUNS
         try:
             got = _check(ctx, off, act, ts, n_act, states, flags)
         except SiestaError as e:  # beyond the engine's documented limits: reported, never silently wrong

@@ -15,7 +15,7 @@ def test_kat_through_device_engine(kat):
     off = np.array([0, len(STREAM_TYPES)], dtype=np.int64)
     act = np.array(STREAM_TYPES, dtype=np.int32)
     ts = np.arange(len(STREAM_TYPES), dtype=np.int64) * 1000
-    rc, res, _ = host_engine.detect(off, act, ts, 5, nfa, flags=abi.F_EVT_POS)
+    rc, res, _ = host_engine.detect(off, act, ts, 5, nfa, flags=abi.F_EVT_POS | abi.F_COUNT_MATCHES)
     assert rc == 0
     assert res.n_matches_emitted == kat["expected"]
     if kat["matches"]:
@@ -53,6 +53,10 @@ def test_random_nfas_all_kinds(seed):
             flags |= abi.F_RETURN_ALL
         if rng.random() < 0.15:
             flags |= abi.F_ONLY_APPEARANCES
+        if rng.random() < 0.25:
+            flags |= abi.F_COUNT_MATCHES
+        if rng.random() < 0.15:
+            flags |= abi.F_LITERAL_RUNS
         r, _ = _compare(off, act, ts, n_act, states, flags)
         stats[r] += 1
     assert stats["ok"] > 50
