@@ -7,7 +7,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsiesta_gpu.so")
+LIB_PATH = os.environ.get("SIESTA_GPU_LIB") or os.path.join(_HERE, "libsiesta_gpu.so")  # override: instrumented builds
 _lib = None
 
 EXPORTS = [

@@ -15,6 +15,7 @@
 // A final gather orders the staged occurrences by trace index (dense per-candidate counts +
 // device scans), so the result is deterministic.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -63,30 +64,54 @@ __device__ __forceinline__ long long shfl_i64(long long v, int src) {
 // status codes of a trace inside the kernel
 enum { ST_NONE = 0, ST_MATCH = 1, ST_ERR = 2, ST_OVF = 3 };
 
-template <int W, int R, int NF>
+// Shared memory of one warp (all arrays lane-transposed: element i of lane l at [i * 32 + l]).
+template <int W, int R, int NF, bool SMEM_RUNS>
+struct WarpSmem {
+    static constexpr int NE = 32 * W;
+    static constexpr size_t famvv_off = 0;
+    static constexpr size_t famvv_bytes = SMEM_RUNS ? sizeof(unsigned long long) * NF * 32 : 0;
+    static constexpr size_t rmask_off = famvv_off + famvv_bytes;
+    static constexpr size_t rmask_bytes = SMEM_RUNS ? sizeof(typename MaskOps<W>::T) * R * 32 : 0;
+    static constexpr size_t meta_off = rmask_off + rmask_bytes;
+    static constexpr size_t meta_bytes = sizeof(uint32_t) * NE * 32;
+    static constexpr size_t rmeta_off = meta_off + meta_bytes;
+    static constexpr size_t rmeta_bytes = SMEM_RUNS ? sizeof(uint32_t) * R * 32 : 0;
+    static constexpr size_t bytes_off = rmeta_off + rmeta_bytes;                 // rfam, fmin, fmin2, fcnt
+    static constexpr size_t bytes_bytes = SMEM_RUNS ? (size_t)(R + 3 * NF) * 32 : 0;
+    static constexpr size_t ts_off = (bytes_off + bytes_bytes + 15) & ~(size_t)15;  // only when the query needs seconds
+    static constexpr size_t ts_bytes = sizeof(int32_t) * NE * 32;
+    static __host__ __device__ constexpr size_t total(bool needs_ts) { return ts_off + (needs_ts ? ts_bytes : 0); }
+};
+
+// One warp owns a tile of 32 traces from start to finish: no block-level barrier anywhere.
+template <int W, int R, int NF, bool SMEM_RUNS>
 __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ DevNfa nfa) {
     typedef MaskOps<W> MO;
     typedef typename MO::T mask_t;
+    typedef WarpSmem<W, R, NF, SMEM_RUNS> L;
     constexpr int NE = 32 * W;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* s_meta = reinterpret_cast<uint32_t*>(smem_raw);                      // [NE][NT]
-    int32_t* s_ts = reinterpret_cast<int32_t*>(smem_raw + sizeof(uint32_t) * NE * NT);  // [NE][NT] when needs_ts
-    __shared__ unsigned long long s_scan[3][NT / 32];
-    __shared__ unsigned long long s_base[3];
-
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wbase = smem_raw + (size_t)warp * L::total(P.needs_ts != 0);
+    uint32_t* s_meta = reinterpret_cast<uint32_t*>(wbase + L::meta_off);  // [NE][32]
+    int32_t* s_ts = reinterpret_cast<int32_t*>(wbase + L::ts_off);        // [NE][32] when needs_ts
+
     const unsigned lt_mask = (1u << lane) - 1u;
     const bool evt_pos = (P.flags & SIESTA_F_EVT_POS) != 0;
     const bool return_all = (P.flags & SIESTA_F_RETURN_ALL) != 0;
     const bool all_cols = (P.flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
     const bool prune = (P.flags & SIESTA_F_LITERAL_RUNS) == 0;
     const bool dedup = prune && !return_all && (P.flags & SIESTA_F_COUNT_MATCHES) == 0;
+    const int warps_per_cta = blockDim.x >> 5;
 
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        // ------------------------------------------------------------------ phase A
-        const int64_t wi = (int64_t)tile * NT + threadIdx.x;  // index into the work list
-        int64_t ci = -1, t = -1;                               // candidate index, trace index
+    for (long long tile = (long long)blockIdx.x * warps_per_cta + warp; tile < P.n_tiles; tile += (long long)gridDim.x * warps_per_cta) {
+        // ------------------------------------------------------------------ phase A: filter + compact
+#ifdef SIESTA_PHASE_TIMING
+        long long tA = clock64();
+#endif
+        const int64_t wi = tile * 32 + lane;   // index into the work list
+        int64_t ci = -1, t = -1;               // candidate index, trace index
         long long o0 = 0, o1 = 0;
         if (wi < P.n_work) {
             ci = P.work ? P.work[wi] : wi;
@@ -98,7 +123,6 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
         for (int tt = 0; tt < 32; ++tt) {
             const long long b0 = shfl_i64(o0, tt), b1 = shfl_i64(o1, tt);
             if (b1 <= b0) continue;
-            const int slot = warp * 32 + tt;
             int cnt = 0;
             long long t0 = 0;
             for (long long p = b0; p < b1; p += 32) {
@@ -117,9 +141,9 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
                 if (m) {
                     const int r = cnt + __popc(ball & lt_mask);
                     if (r < NE && (idx - b0) < 65536) {
-                        s_meta[r * NT + slot] = m | ((uint32_t)(idx - b0) << 16);
+                        s_meta[r * 32 + tt] = m | ((uint32_t)(idx - b0) << 16);
                         // EventTs.transformSaseEvent: (int)((t - minTs) / 1000), truncating long division (EventTs.java:54)
-                        if (P.needs_ts) s_ts[r * NT + slot] = (int)((ts - t0) / 1000);
+                        if (P.needs_ts) s_ts[r * 32 + tt] = (int)((ts - t0) / 1000);
                     }
                 }
                 cnt += __popc(ball);
@@ -129,7 +153,10 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
         }
         __syncwarp();
 
-        // ------------------------------------------------------------------ phase B
+        // ------------------------------------------------------------------ phase B: run-set engine, one lane per trace
+#ifdef SIESTA_PHASE_TIMING
+        long long tB = clock64();
+#endif
         int status = ST_NONE;
         unsigned n_emitted = 0;
         mask_t best = 0;
@@ -139,64 +166,79 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
             if (my_cnt > NE) {
                 status = ST_OVF;
             } else {
-                TraceEvents ev{s_meta + threadIdx.x, P.needs_ts ? s_ts + threadIdx.x : nullptr, NT, my_cnt, evt_pos};
-                RunEngine<W, R, NF> eng(nfa, ev);
-                BestEmit<W> be;
-                eng.run(be, prune, dedup);
-                if (eng.ovf) status = ST_OVF;
-                else if (eng.err) status = ST_ERR;
-                else if (be.n > 0) {
-                    status = ST_MATCH;
-                    n_emitted = be.n;
-                    best = be.best;
-                    sel_local[0] = best;
-                    nsel = 1;
-                    if (return_all && be.n > 1) {
-                        GreedyEmit<W, NE> ge(ev, best, evt_pos);
-                        eng.run(ge, prune, false);
-                        if (ge.ovf || eng.ovf) status = ST_OVF;
-                        else {
-                            nsel = ge.nsel;
-                            for (int o = 1; o < nsel; ++o) sel_local[o] = ge.sel[o];
+                TraceEvents ev{s_meta + lane, P.needs_ts ? s_ts + lane : nullptr, 32, my_cnt, evt_pos};
+                auto body = [&](auto& eng) {
+                    BestEmit<W> be;
+                    eng.run(be, prune, dedup);
+                    if (eng.ovf) status = ST_OVF;
+                    else if (eng.err) status = ST_ERR;
+                    else if (be.n > 0) {
+                        status = ST_MATCH;
+                        n_emitted = be.n;
+                        best = be.best;
+                        sel_local[0] = best;
+                        nsel = 1;
+                        if (return_all && be.n > 1) {
+                            GreedyEmit<W, NE> ge(ev, best, evt_pos);
+                            eng.run(ge, prune, false);
+                            if (ge.ovf || eng.ovf) status = ST_OVF;
+                            else {
+                                nsel = ge.nsel;
+                                for (int o = 1; o < nsel; ++o) sel_local[o] = ge.sel[o];
+                            }
                         }
                     }
+                };
+                if constexpr (SMEM_RUNS) {
+                    uint8_t* bytes = wbase + L::bytes_off + lane;
+                    RunStore<W, R, NF, 32> store{reinterpret_cast<mask_t*>(wbase + L::rmask_off) + lane,
+                                                 reinterpret_cast<uint32_t*>(wbase + L::rmeta_off) + lane,
+                                                 bytes,
+                                                 reinterpret_cast<unsigned long long*>(wbase + L::famvv_off) + lane,
+                                                 bytes + (size_t)R * 32, bytes + (size_t)(R + NF) * 32, bytes + (size_t)(R + 2 * NF) * 32};
+                    RunEngine<RunStore<W, R, NF, 32>> eng(nfa, ev, store);
+                    body(eng);
+                } else {
+                    RunArrays<W, R, NF> arrays;
+                    RunEngine<RunStore<W, R, NF, 1>> eng(nfa, ev, arrays.store());
+                    body(eng);
                 }
             }
         }
 
-        // ------------------------------------------------------------------ phase C
+        // ------------------------------------------------------------------ phase C: reserve staging space per warp, write
+#ifdef SIESTA_PHASE_TIMING
+        __syncwarp();
+        long long tC = clock64();
+#endif
         unsigned my_occ = 0, my_ev = 0;
         if (status == ST_MATCH) {
             my_occ = (unsigned)nsel;
             for (int o = 0; o < nsel; ++o) my_ev += MO::popc(sel_local[o]);
         }
-        // block exclusive scan of (occ, ev), block sum of emitted
-        unsigned long long v0 = my_occ, v1 = my_ev, v2 = (status == ST_MATCH) ? n_emitted : 0u;
-        unsigned long long i0 = v0, i1 = v1, i2 = v2;
+        unsigned i0 = my_occ, i1 = my_ev;
+        unsigned long long i2 = (status == ST_MATCH) ? n_emitted : 0u;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            unsigned long long y0 = __shfl_up_sync(0xffffffffu, i0, d), y1 = __shfl_up_sync(0xffffffffu, i1, d),
-                               y2 = __shfl_up_sync(0xffffffffu, i2, d);
+            const unsigned y0 = __shfl_up_sync(0xffffffffu, i0, d), y1 = __shfl_up_sync(0xffffffffu, i1, d);
+            const unsigned long long y2 = __shfl_up_sync(0xffffffffu, i2, d);
             if (lane >= d) { i0 += y0; i1 += y1; i2 += y2; }
         }
-        if (lane == 31) { s_scan[0][warp] = i0; s_scan[1][warp] = i1; s_scan[2][warp] = i2; }
-        __syncthreads();
-        unsigned long long w0 = 0, w1 = 0, tot0 = 0, tot1 = 0, tot2 = 0;
-#pragma unroll
-        for (int k = 0; k < NT / 32; ++k) {
-            if (k < warp) { w0 += s_scan[0][k]; w1 += s_scan[1][k]; }
-            tot0 += s_scan[0][k]; tot1 += s_scan[1][k]; tot2 += s_scan[2][k];
+        const unsigned n_match = __popc(__ballot_sync(0xffffffffu, status == ST_MATCH));
+        unsigned long long base0 = 0, base1 = 0;
+        if (lane == 31) {
+            if (i0) base0 = atomicAdd(P.counters + 0, (unsigned long long)i0);
+            if (i1) base1 = atomicAdd(P.counters + 1, (unsigned long long)i1);
+            if (i2) atomicAdd(P.counters + 2, i2);
+            if (n_match) atomicAdd(P.counters + 6, (unsigned long long)n_match);
         }
-        if (threadIdx.x == 0) {
-            s_base[0] = tot0 ? atomicAdd(P.counters + 0, tot0) : 0ull;
-            s_base[1] = tot1 ? atomicAdd(P.counters + 1, tot1) : 0ull;
-            if (tot2) atomicAdd(P.counters + 2, tot2);
-        }
-        __syncthreads();
-        const long long occ_at = (long long)(s_base[0] + w0 + i0 - v0);
-        const long long ev_at = (long long)(s_base[1] + w1 + i1 - v1);
-        const bool stage_ok = (long long)(s_base[0] + tot0) <= P.cap_occ && (long long)(s_base[1] + tot1) <= P.cap_ev;
-        if (!stage_ok && threadIdx.x == 0) atomicAdd(P.counters + 5, 1ull);
+        const unsigned tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
+        base0 = __shfl_sync(0xffffffffu, base0, 31);
+        base1 = __shfl_sync(0xffffffffu, base1, 31);
+        const long long occ_at = (long long)(base0 + i0 - my_occ);
+        const long long ev_at = (long long)(base1 + i1 - my_ev);
+        const bool stage_ok = (long long)(base0 + tot0) <= P.cap_occ && (long long)(base1 + tot1) <= P.cap_ev;
+        if (!stage_ok && lane == 0) atomicAdd(P.counters + 5, 1ull);
 
         if (ci >= 0) {
             if (status == ST_MATCH) {
@@ -204,17 +246,16 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
                 P.d_nev[ci] = my_ev;
                 P.d_stage[ci] = ev_at;
                 P.d_stage_occ[ci] = occ_at;
-                atomicAdd(P.counters + 6, 1ull);
                 if (stage_ok) {
                     long long e = ev_at;
-                    const long long t0ms = (all_cols && !evt_pos) ? P.ts_ms[o0 + (s_meta[threadIdx.x] >> 16)] : 0;
+                    const long long t0ms = (all_cols && !evt_pos) ? P.ts_ms[o0 + (s_meta[lane] >> 16)] : 0;
                     for (int o = 0; o < nsel; ++o) {
                         mask_t m = sel_local[o];
                         P.s_occ_nev[occ_at + o] = MO::popc(m);
                         while (m) {
                             const int j = MO::lo(m);
                             m &= m - 1;
-                            const int src = (int)(s_meta[j * NT + threadIdx.x] >> 16);
+                            const int src = (int)(s_meta[j * 32 + lane] >> 16);
                             P.s_ev_pos[e] = src;
                             if (all_cols) {
                                 P.s_ev_rank[e] = j;
@@ -234,7 +275,17 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
                 else if (status == ST_OVF) P.ovf_list[atomicAdd(P.counters + 4, 1ull)] = ci;
             }
         }
-        __syncthreads();  // s_meta / s_scan are reused by the next tile
+#ifdef SIESTA_PHASE_TIMING
+        {
+            long long tD = clock64();
+            if (lane == 0) {
+                atomicAdd(P.counters + 8, (unsigned long long)(tB - tA));
+                atomicAdd(P.counters + 9, (unsigned long long)(tC - tB));
+                atomicAdd(P.counters + 10, (unsigned long long)(tD - tC));
+            }
+        }
+#endif
+        __syncwarp();  // the warp's shared-memory slot is reused by its next tile
     }
 }
 
@@ -413,25 +464,25 @@ struct DevMatchesImpl {
     int device = 0;
 };
 
-template <int W, int R, int NF>
+template <int W, int R, int NF, bool SMEM_RUNS>
 int launch_detect(const Ctx* ctx, cudaStream_t stream, DetectParams P, const DevNfa& nfa) {
-    constexpr int NE = 32 * W;
-    const size_t smem = sizeof(uint32_t) * NE * NT * (P.needs_ts ? 2 : 1);
-    auto kern = detect_kernel<W, R, NF>;
+    typedef WarpSmem<W, R, NF, SMEM_RUNS> L;
+    const size_t smem = L::total(P.needs_ts != 0) * (NT / 32);
+    auto kern = detect_kernel<W, R, NF, SMEM_RUNS>;
     SIESTA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
     if (per_sm < 1) per_sm = 1;
-    const int64_t n_tiles = (P.n_work + NT - 1) / NT;
+    const int64_t n_tiles = (P.n_work + 31) / 32;   // one tile = the 32 traces of one warp
     P.n_tiles = (int32_t)n_tiles;
-    int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * per_sm);
+    const int64_t ctas_needed = (n_tiles + NT / 32 - 1) / (NT / 32);
+    int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)ctx->sm_count * per_sm);
     if (grid < 1) grid = 1;
     kern<<<grid, NT, smem, stream>>>(P, nfa);
     SIESTA_LAUNCHED();
     SIESTA_CUDA_OK(cudaGetLastError());
     return SIESTA_OK;
 }
-
 
 int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand, uint32_t flags,
                        cudaStream_t stream, siesta_dev_matches* out) {
@@ -461,7 +512,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     DevBuf s_occ_nev(stream), s_ev_pos(stream), s_ev_rank(stream), s_ev_act(stream), s_ev_ts(stream), b_blk(stream);
     const size_t nn = (size_t)std::max<int64_t>(n, 1);
     if ((rc = b_lut.alloc(lut.size() * sizeof(uint16_t))) || (rc = b_nocc.alloc(nn * 4)) || (rc = b_nev.alloc(nn * 4)) ||
-        (rc = b_stage.alloc(nn * 8)) || (rc = b_stage_occ.alloc(nn * 8)) || (rc = b_counters.alloc(8 * 8)) ||
+        (rc = b_stage.alloc(nn * 8)) || (rc = b_stage_occ.alloc(nn * 8)) || (rc = b_counters.alloc(16 * 8)) ||
         (rc = b_err.alloc(nn * 8)) || (rc = b_ovf.alloc(nn * 8)) || (rc = s_occ_nev.alloc((size_t)cap_occ * 4)) ||
         (rc = s_ev_pos.alloc((size_t)cap_ev * 4)))
         return rc;
@@ -474,7 +525,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     SIESTA_CUDA_OK(cudaEventCreate(&ev1));
     SIESTA_CUDA_OK(cudaEventCreate(&evd));
     SIESTA_CUDA_OK(cudaMemcpyAsync(b_lut.p, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
-    SIESTA_CUDA_OK(cudaMemsetAsync(b_counters.p, 0, 64, stream));
+    SIESTA_CUDA_OK(cudaMemsetAsync(b_counters.p, 0, 128, stream));
     SIESTA_CUDA_OK(cudaEventRecord(ev0, stream));
 
     DetectParams P;
@@ -504,14 +555,14 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     P.err_list = b_err.as<int64_t>();
     P.ovf_list = b_ovf.as<int64_t>();
 
-    unsigned long long h_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long h_cnt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (n > 0) {
-        if ((rc = launch_detect<1, 64, 64>(ctx, stream, P, dn))) return rc;
+        if ((rc = launch_detect<1, 16, 16, true>(ctx, stream, P, dn))) return rc;
         SIESTA_CUDA_OK(cudaEventRecord(evd, stream));
-        SIESTA_CUDA_OK(cudaMemcpyAsync(h_cnt, b_counters.p, 64, cudaMemcpyDeviceToHost, stream));
+        SIESTA_CUDA_OK(cudaMemcpyAsync(h_cnt, b_counters.p, 128, cudaMemcpyDeviceToHost, stream));
         SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
         if (h_cnt[4] > 0) {
-            // traces beyond the narrow configuration (32 relevant events / 64 live runs): wide engine
+            // traces beyond the narrow configuration (32 relevant events / 16 live runs / 16 live families): wide engine
             const int64_t n_ovf = (int64_t)h_cnt[4];
             if ((rc = b_ovf2.alloc((size_t)n_ovf * 8))) return rc;
             SIESTA_CUDA_OK(cudaMemsetAsync(b_counters.as<unsigned long long>() + 4, 0, 8, stream));
@@ -519,8 +570,8 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
             Q.work = b_ovf.as<int64_t>();
             Q.n_work = n_ovf;
             Q.ovf_list = b_ovf2.as<int64_t>();
-            if ((rc = launch_detect<2, 1024, 128>(ctx, stream, Q, dn))) return rc;
-            SIESTA_CUDA_OK(cudaMemcpyAsync(h_cnt, b_counters.p, 64, cudaMemcpyDeviceToHost, stream));
+            if ((rc = launch_detect<2, 1024, 128, false>(ctx, stream, Q, dn))) return rc;
+            SIESTA_CUDA_OK(cudaMemcpyAsync(h_cnt, b_counters.p, 128, cudaMemcpyDeviceToHost, stream));
             SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
             if (h_cnt[4] > 0) {
                 set_error(std::to_string(h_cnt[4]) + " trace(s) exceed the engine limits (64 pattern-relevant events, "
@@ -533,6 +584,9 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
             return SIESTA_E_NOMEM;
         }
     }
+#ifdef SIESTA_PHASE_TIMING
+    fprintf(stderr, "[siesta phase timing] warp-cycles: filter %llu engine %llu output %llu\n", h_cnt[8], h_cnt[9], h_cnt[10]);
+#endif
     const int64_t n_occ = (int64_t)h_cnt[0], n_ev = (int64_t)h_cnt[1], n_tr = (int64_t)h_cnt[6], n_err = (int64_t)h_cnt[3];
 
     DevBuf f_trace(stream), f_occ_off(stream), f_ev_off(stream), f_pos(stream), f_rank(stream), f_act(stream), f_ts(stream),

@@ -118,22 +118,47 @@ struct TraceEvents {
     SIESTA_HD __forceinline__ int attr(int j, int a) const { return a == SIESTA_ATTR_POSITION ? position(j) : timestamp(j); }
 };
 
+// Backing store of one trace's run list and value-vector families.  The narrow (common) configuration lives in
+// shared memory, lane-transposed (element i of lane l at [i * 32 + l]) so a warp in lockstep is conflict-free;
+// the wide fallback and the host test harness use plain per-thread arrays (STRIDE 1).
+template <int W, int R_, int NF_, int STRIDE_>
+struct RunStore {
+    static constexpr int R = R_, NF = NF_, STRIDE = STRIDE_, WORDS = W;
+    typename MaskOps<W>::T* rmask;   // [R]  Run.eventIds as a bitmask over the trace's filtered events
+    uint32_t* rmeta;                 // [R]  packed run state
+    uint8_t* rfam;                   // [R]  value-vector family of the run
+    unsigned long long* famvv;       // [NF] byte k = 1 + rank of the event last stored for state k; 0 = null
+    uint8_t* fmin;                   // [NF] smallest cursor among the family's live runs
+    uint8_t* fmin2;                  // [NF] second smallest
+    uint8_t* fcnt;                   // [NF] live runs of the family
+};
+// per-thread arrays for STRIDE 1 stores
 template <int W, int R, int NF>
+struct RunArrays {
+    typename MaskOps<W>::T rmask[R];
+    uint32_t rmeta[R];
+    uint8_t rfam[R];
+    unsigned long long famvv[NF];
+    uint8_t fmin[NF], fmin2[NF], fcnt[NF];
+    SIESTA_HD RunStore<W, R, NF, 1> store() { return RunStore<W, R, NF, 1>{rmask, rmeta, rfam, famvv, fmin, fmin2, fcnt}; }
+};
+
+template <class Store>
 struct RunEngine {
+    static constexpr int W = Store::WORDS, R = Store::R, NF = Store::NF, STRIDE = Store::STRIDE;
+    static_assert(NF <= 255, "family ids are stored in a byte");
     typedef MaskOps<W> MO;
     typedef typename MO::T mask_t;
 
     const DevNfa& nfa;
     const TraceEvents& ev;
-    mask_t rmask[R];
-    uint32_t rmeta[R];
-    uint16_t rfam[R];
-    unsigned long long famvv[NF];  // byte k = 1 + rank of the event last stored for state k; 0 = null
-    int nruns, nfam;
+    Store st;
+    uint32_t fam_used[(NF + 31) / 32];  // allocated family ids (recycled once no live run refers to them)
+    int nruns;
     bool err, ovf;
     unsigned n_emitted;
 
-    SIESTA_HD RunEngine(const DevNfa& n, const TraceEvents& e) : nfa(n), ev(e) {}
+    SIESTA_HD RunEngine(const DevNfa& n, const TraceEvents& e, const Store& s) : nfa(n), ev(e), st(s) {}
 
     // ---- small helpers over a packed run -------------------------------------------------
     SIESTA_HD __forceinline__ static uint32_t get_st(uint32_t m, int k) { return (m >> (M_ST_SHIFT + 2 * k)) & 3u; }
@@ -154,20 +179,29 @@ struct RunEngine {
     }
     SIESTA_HD __forceinline__ int new_family() {
         if (!nfa.need_vv) return 0;
-        if (nfam >= NF) { ovf = true; return 0; }
-        famvv[nfam] = 0ull;
-        return nfam++;
+#pragma unroll
+        for (int w = 0; w < (NF + 31) / 32; ++w) {
+            const uint32_t free_bits = ~fam_used[w] & (NF - 32 * w >= 32 ? 0xffffffffu : ((1u << (NF - 32 * w)) - 1u));
+            if (free_bits) {
+                const int b = ffs32(free_bits) - 1;
+                fam_used[w] |= 1u << b;
+                st.famvv[(32 * w + b) * STRIDE] = 0ull;
+                return 32 * w + b;
+            }
+        }
+        ovf = true;
+        return 0;
     }
     SIESTA_HD __forceinline__ void append(mask_t mask, uint32_t meta, int fam) {
         if (nruns >= R) { ovf = true; return; }
-        rmask[nruns] = mask;
-        rmeta[nruns] = meta;
-        rfam[nruns] = (uint16_t)fam;
+        st.rmask[nruns * STRIDE] = mask;
+        st.rmeta[nruns * STRIDE] = meta;
+        st.rfam[nruns * STRIDE] = (uint8_t)fam;
         nruns++;
     }
-    SIESTA_HD __forceinline__ int vv_get(int fam, int k) const { return (int)((famvv[fam] >> (8 * k)) & 0xFF) - 1; }
+    SIESTA_HD __forceinline__ int vv_get(int fam, int k) const { return (int)((st.famvv[fam * STRIDE] >> (8 * k)) & 0xFF) - 1; }
     SIESTA_HD __forceinline__ void vv_set(int fam, int k, int j) {
-        famvv[fam] = (famvv[fam] & ~(0xFFull << (8 * k))) | ((unsigned long long)(j + 1) << (8 * k));
+        st.famvv[fam * STRIDE] = (st.famvv[fam * STRIDE] & ~(0xFFull << (8 * k))) | ((unsigned long long)(j + 1) << (8 * k));
     }
 
     // Edge.evaluatePredicate(Event, Run, EventBuffer) over PredicateOptimized.evaluate (S/query/
@@ -280,9 +314,9 @@ struct RunEngine {
     // Engine.evaluateEventForSkipTillNext (Engine.java:654-725)
     template <class Emit>
     SIESTA_HD void evaluate(int j, uint32_t w, int r, Emit& emit) {
-        mask_t mask = rmask[r];
-        uint32_t meta = rmeta[r];
-        const int fam = rfam[r];
+        mask_t mask = st.rmask[r * STRIDE];
+        uint32_t meta = st.rmeta[r * STRIDE];
+        const int fam = st.rfam[r * STRIDE];
         int cur = M_CUR(meta);
         if (cur >= nfa.n_states) { err = true; return; }  // getStates(currentState) past a trailing negative
         if (nfa.kind[cur] == SIESTA_STATE_KLEENE_STAR && !(meta & M_KINIT)) {
@@ -316,8 +350,8 @@ struct RunEngine {
             if (err) return;
         }
         if (M_MARKS(meta) >= 2) { err = true; return; }  // cleanRuns: second resetRun NPEs (Run.java:163)
-        rmask[r] = mask;
-        rmeta[r] = meta;
+        st.rmask[r * STRIDE] = mask;
+        st.rmeta[r * STRIDE] = meta;
     }
 
     // Engine.createNewRun (Engine.java:933-982)
@@ -377,10 +411,11 @@ struct RunEngine {
     //     never merged (Engine.checkProceed throws on them: Run.java:285).  Because runs are evaluated one after
     //     the other inside an event and siblings share one value vector, "same events for ever" needs the static
     //     condition DevNfa::merge_safe (nfa.cpp): no event type both writes a referenced slot and reads it.
+    //     Across families the same holds when the slots the run can still read (DevNfa::relmask) hold the same
+    //     events and nobody but the two runs themselves can rewrite them (same_future below).
     bool opt_prune, opt_dedup, ts_monotone;
-    uint8_t fmin[NF];
 
-    SIESTA_HD bool is_inert(int j, mask_t mask, uint32_t meta, int fam, bool fam_shared) const {
+    SIESTA_HD bool is_inert(int j, uint32_t meta, int fam) const {
         if (meta & M_FULL) return true;
         if (!opt_prune || !nfa.need_vv) return false;
         const int cur = M_CUR(meta);
@@ -393,62 +428,109 @@ struct RunEngine {
             if (nfa.p_op[cur][k] != SIESTA_OP_LE) continue;
             const int ref = nfa.p_ref[cur][k];
             if (ref >= cur) continue;                       // self / forward reference
-            if (fam_shared && fmin[fam] <= ref) continue;   // a sibling can still rewrite the slot
+            if (st.fmin[fam * STRIDE] <= ref) continue;     // a sibling can still rewrite the slot
             const int rj = vv_get(fam, ref);
             if (rj < 0) return true;                        // null for ever -> predicate false for ever
             const int a = nfa.p_attr[cur][k];
             if (a == SIESTA_ATTR_TIMESTAMP && !ts_monotone) continue;
             if ((long long)ev.attr(j, a) > (long long)ev.attr(rj, a) + nfa.p_c[cur][k]) return true;
         }
-        (void)mask;
         return false;
     }
 
+    // Is run q interchangeable with run r for everything r can still do?  (same packed state; the value-vector
+    // slots r can still read hold the same events and will be rewritten identically in both families)
+    SIESTA_HD __forceinline__ bool same_future(int q, uint32_t meta, int fam, int cur) const {
+        if (st.rmeta[q * STRIDE] != meta) return false;  // marked / already dropped runs differ in meta
+        const int fq = st.rfam[q * STRIDE];
+        if (fq == fam || !nfa.need_vv) return true;
+        if (!nfa.cross_safe) return false;
+        const unsigned long long rel = nfa.relmask[cur];
+        if (rel == 0) return true;                                   // neither lineage reads a value vector again
+        if ((st.famvv[fam * STRIDE] ^ st.famvv[fq * STRIDE]) & rel) return false;
+        if (st.fcnt[fam * STRIDE] != 1) return false;                // dropping r must not starve its siblings
+        const int nq = st.fcnt[fq * STRIDE];
+        if (nq == 1) return true;
+        const int mn = st.fmin[fq * STRIDE];
+        const int others = mn == cur ? st.fmin2[fq * STRIDE] : mn;   // smallest cursor among q's siblings
+        return others > nfa.kmax[cur];                               // nobody else in q's family rewrites those slots
+    }
+
     SIESTA_HD void reduce_runs(int j) {
-        const bool fam_shared = nfa.any_kleene && nfa.need_vv;
-        if (opt_prune && fam_shared) {
-            for (int r = 0; r < nruns; ++r) fmin[rfam[r]] = 15;
+        if (nfa.need_vv) {
+#pragma unroll
+            for (int w = 0; w < (NF + 31) / 32; ++w)
+                for (uint32_t m = fam_used[w]; m; m &= m - 1) {
+                    const int f = 32 * w + ffs32(m) - 1;
+                    st.fmin[f * STRIDE] = 15;
+                    st.fmin2[f * STRIDE] = 15;
+                    st.fcnt[f * STRIDE] = 0;
+                }
             for (int r = 0; r < nruns; ++r) {
-                if (M_MARKS(rmeta[r])) continue;
-                const int c = M_CUR(rmeta[r]);
-                if (c < fmin[rfam[r]]) fmin[rfam[r]] = (uint8_t)c;
+                const uint32_t m = st.rmeta[r * STRIDE];
+                if (M_MARKS(m) || (m & M_FULL)) continue;
+                const int f = st.rfam[r * STRIDE];
+                const int c = M_CUR(m);
+                const int mn = st.fmin[f * STRIDE];
+                if (c < mn) { st.fmin2[f * STRIDE] = (uint8_t)mn; st.fmin[f * STRIDE] = (uint8_t)c; }
+                else if (c < st.fmin2[f * STRIDE]) st.fmin2[f * STRIDE] = (uint8_t)c;
+                if (st.fcnt[f * STRIDE] < 255) ++st.fcnt[f * STRIDE];
             }
         }
-        const bool dedup = opt_dedup && nfa.merge_safe && (!nfa.need_vv || nfa.any_kleene);
+        const bool dedup = opt_dedup && nfa.merge_safe;
         bool any_drop = false;
         for (int r = 0; r < nruns; ++r) {
-            const uint32_t meta = rmeta[r];
+            const uint32_t meta = st.rmeta[r * STRIDE];
             if (M_MARKS(meta)) { any_drop = true; continue; }   // cleanRuns (:1404-1418)
-            const mask_t mask = rmask[r];
-            const int fam = rfam[r];
-            bool drop = is_inert(j, mask, meta, fam, fam_shared);
-            if (!drop && dedup && mask != 0) {
-                const int cnt = MO::popc(mask);
-                for (int q = 0; q < nruns && !drop; ++q) {
-                    if (q == r || rmeta[q] != meta || rfam[q] != fam) continue;   // marked runs differ in meta
-                    const mask_t mq = rmask[q];
-                    if (mq == 0) continue;
-                    const int cq = MO::popc(mq);
-                    drop = cq > cnt || (cq == cnt && q < r);
+            const int fam = st.rfam[r * STRIDE];
+            bool drop = is_inert(j, meta, fam);
+            if (!drop && dedup) {
+                const mask_t mask = st.rmask[r * STRIDE];
+                if (mask != 0) {
+                    const int cnt = MO::popc(mask);
+                    const int cur = M_CUR(meta);
+                    for (int q = 0; q < nruns && !drop; ++q) {
+                        if (q == r || !same_future(q, meta, fam, cur)) continue;
+                        const mask_t mq = st.rmask[q * STRIDE];
+                        if (mq == 0) continue;
+                        const int cq = MO::popc(mq);
+                        drop = cq > cnt || (cq == cnt && q < r);
+                    }
                 }
             }
-            if (drop) { rmeta[r] = meta | (1u << M_MARK_SHIFT) | (1u << 31); any_drop = true; }
+            if (drop) { st.rmeta[r * STRIDE] = meta | (1u << M_MARK_SHIFT) | (1u << 31); any_drop = true; }
         }
-        if (!any_drop) return;
-        int k = 0;
-        for (int r = 0; r < nruns; ++r) {
-            if (M_MARKS(rmeta[r])) continue;
-            if (k != r) { rmask[k] = rmask[r]; rmeta[k] = rmeta[r]; rfam[k] = rfam[r]; }
-            ++k;
+        if (any_drop) {
+            int k = 0;
+            for (int r = 0; r < nruns; ++r) {
+                const uint32_t m = st.rmeta[r * STRIDE];
+                if (M_MARKS(m)) continue;
+                if (k != r) {
+                    st.rmask[k * STRIDE] = st.rmask[r * STRIDE];
+                    st.rmeta[k * STRIDE] = m;
+                    st.rfam[k * STRIDE] = st.rfam[r * STRIDE];
+                }
+                ++k;
+            }
+            nruns = k;
         }
-        nruns = k;
+        if (nfa.need_vv) {
+            // recycle the ids of families no surviving run refers to
+#pragma unroll
+            for (int w = 0; w < (NF + 31) / 32; ++w) fam_used[w] = 0;
+            for (int r = 0; r < nruns; ++r) {
+                const int f = st.rfam[r * STRIDE];
+                fam_used[f >> 5] |= 1u << (f & 31);
+            }
+        }
     }
 
     // Engine.runSkipTillNextEngine (Engine.java:207-224) over one trace.
     template <class Emit>
     SIESTA_HD void run(Emit& emit, bool prune, bool dedup) {
         nruns = 0;
-        nfam = 0;
+#pragma unroll
+        for (int w = 0; w < (NF + 31) / 32; ++w) fam_used[w] = 0;
         err = false;
         ovf = false;
         n_emitted = 0;
@@ -461,13 +543,19 @@ struct RunEngine {
             const uint32_t w = ev.word(j);
             const int n0 = nruns;  // runs appended while evaluating this event are not visited (:361)
             for (int r = 0; r < n0; ++r) {
-                if (rmeta[r] & M_FULL) continue;
+                if (st.rmeta[r * STRIDE] & M_FULL) continue;
                 evaluate(j, w, r, emit);
                 if (err || ovf) return;
             }
-            if (nruns) reduce_runs(j);  // includes cleanRuns (:1404-1418): stable removal of marked runs
             create_new_run(j, w, emit);
             if (err || ovf) return;
+            // cleanRuns (:1404-1418) happens before createNewRun in the reference; the order is immaterial because
+            // marked runs are never looked at again, and folding it into the reduction pass saves one sweep.
+            if (nruns) reduce_runs(j);
+            else {
+#pragma unroll
+                for (int w2 = 0; w2 < (NF + 31) / 32; ++w2) fam_used[w2] = 0;
+            }
         }
     }
 };

@@ -82,6 +82,20 @@ int validate_nfa(const siesta_nfa* nfa, uint32_t flags, DevNfa* out) {
             seen_kleene = seen_kleene || kl;
         }
     }
+    // Which value-vector slots can a run sitting at state c still read?  Those referenced by predicates of states
+    // >= c (a negative state also evaluates the next state's predicates: Engine.java:1165-1180).
+    d.cross_safe = d.merge_safe;
+    for (int c = 0; c <= SIESTA_MAX_STATES; ++c) {
+        d.relmask[c] = 0;
+        d.kmax[c] = -1;
+        for (int s = c; s < nfa->n_states; ++s)
+            for (int k = 0; k < d.n_preds[s]; ++k) {
+                const int ref = nfa->states[s].preds[k].ref_state;
+                d.relmask[c] |= 0xFFull << (8 * ref);
+                if (ref > d.kmax[c]) d.kmax[c] = (int8_t)ref;
+                if (ref >= s) d.cross_safe = 0;
+            }
+    }
     if (flags & SIESTA_F_MODE_HEAD) {
         // Engine.createNewRun's trailing block (Engine.java:983-996) only acts when states[1] is
         // kleeneClosure*, and throws for single-state NFAs; both have no defined reference output.

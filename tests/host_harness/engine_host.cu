@@ -35,7 +35,8 @@ static int run_one(const DevNfa& dn, const std::vector<uint32_t>& meta, const st
     const bool evt_pos = (flags & SIESTA_F_EVT_POS) != 0;
     if ((int)meta.size() > NE) return 3;
     TraceEvents ev{meta.data(), needs_ts ? ts.data() : nullptr, 1, (int)meta.size(), evt_pos};
-    auto* eng = new RunEngine<W, R, NF>(dn, ev);
+    auto* arrays = new RunArrays<W, R, NF>();
+    auto* eng = new RunEngine<RunStore<W, R, NF, 1>>(dn, ev, arrays->store());
     const bool prune = (flags & SIESTA_F_LITERAL_RUNS) == 0;
     const bool dedup = prune && !(flags & SIESTA_F_RETURN_ALL) && !(flags & SIESTA_F_COUNT_MATCHES);
     BestEmit<W> be;
@@ -55,6 +56,7 @@ static int run_one(const DevNfa& dn, const std::vector<uint32_t>& meta, const st
         }
     }
     delete eng;
+    delete arrays;
     return status;
 }
 
@@ -94,7 +96,7 @@ extern "C" int engine_host_detect(const int64_t* trace_off, const int32_t* act, 
         std::vector<uint32_t> sel1;
         std::vector<unsigned long long> sel2;
         bool wide = false;
-        status = run_one<1, 64, 64>(dn, meta, ts, needs_ts, flags, sel1, &emitted);
+        status = run_one<1, 16, 16>(dn, meta, ts, needs_ts, flags, sel1, &emitted);
         if (status == 3) {
             wide = true;
             ++*n_wide;
