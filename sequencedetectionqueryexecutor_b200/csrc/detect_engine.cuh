@@ -155,6 +155,8 @@ struct RunEngine {
     Store st;
     uint32_t fam_used[(NF + 31) / 32];  // allocated family ids (recycled once no live run refers to them)
     int nruns;
+    bool dirty;      // a run moved, forked, was marked or created since the last reduction pass
+    unsigned moved;  // bit r (r < 32): run r changed its packed state or is new in this event; ~0u = unknown
     bool err, ovf;
     unsigned n_emitted;
 
@@ -194,6 +196,8 @@ struct RunEngine {
     }
     SIESTA_HD __forceinline__ void append(mask_t mask, uint32_t meta, int fam) {
         if (nruns >= R) { ovf = true; return; }
+        dirty = true;
+        moved |= nruns < 32 ? (1u << nruns) : ~0u;
         st.rmask[nruns * STRIDE] = mask;
         st.rmeta[nruns * STRIDE] = meta;
         st.rfam[nruns * STRIDE] = (uint8_t)fam;
@@ -350,6 +354,8 @@ struct RunEngine {
             if (err) return;
         }
         if (M_MARKS(meta) >= 2) { err = true; return; }  // cleanRuns: second resetRun NPEs (Run.java:163)
+        dirty = true;
+        moved |= r < 32 ? (1u << r) : ~0u;
         st.rmask[r * STRIDE] = mask;
         st.rmeta[r * STRIDE] = meta;
     }
@@ -478,6 +484,7 @@ struct RunEngine {
             }
         }
         const bool dedup = opt_dedup && nfa.merge_safe;
+        const bool all_moved = moved == ~0u || nruns > 32;
         bool any_drop = false;
         for (int r = 0; r < nruns; ++r) {
             const uint32_t meta = st.rmeta[r * STRIDE];
@@ -489,8 +496,11 @@ struct RunEngine {
                 if (mask != 0) {
                     const int cnt = MO::popc(mask);
                     const int cur = M_CUR(meta);
+                    // two runs that both sat still were already compared after an earlier event
+                    const bool r_moved = all_moved || ((moved >> r) & 1u);
                     for (int q = 0; q < nruns && !drop; ++q) {
-                        if (q == r || !same_future(q, meta, fam, cur)) continue;
+                        if (q == r || !(r_moved || ((moved >> q) & 1u))) continue;
+                        if (!same_future(q, meta, fam, cur)) continue;
                         const mask_t mq = st.rmask[q * STRIDE];
                         if (mq == 0) continue;
                         const int cq = MO::popc(mq);
@@ -514,6 +524,8 @@ struct RunEngine {
             }
             nruns = k;
         }
+        dirty = false;
+        moved = 0;
         if (nfa.need_vv) {
             // recycle the ids of families no surviving run refers to
 #pragma unroll
@@ -539,6 +551,8 @@ struct RunEngine {
         ts_monotone = true;
         if (prune && ev.ts && !ev.evt_pos)
             for (int j = 1; j < ev.n; ++j) ts_monotone = ts_monotone && ev.ts[j * ev.stride] >= ev.ts[(j - 1) * ev.stride];
+        dirty = false;
+        moved = 0;
         for (int j = 0; j < ev.n; ++j) {
             const uint32_t w = ev.word(j);
             const int n0 = nruns;  // runs appended while evaluating this event are not visited (:361)
@@ -551,8 +565,8 @@ struct RunEngine {
             if (err || ovf) return;
             // cleanRuns (:1404-1418) happens before createNewRun in the reference; the order is immaterial because
             // marked runs are never looked at again, and folding it into the reduction pass saves one sweep.
-            if (nruns) reduce_runs(j);
-            else {
+            if (nruns && dirty) reduce_runs(j);
+            else if (nruns == 0) {
 #pragma unroll
                 for (int w2 = 0; w2 < (NF + 31) / 32; ++w2) fam_used[w2] = 0;
             }
