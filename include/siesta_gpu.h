@@ -228,6 +228,49 @@ int siesta_detect_device(siesta_log* log, const siesta_nfa* nfa, const int64_t* 
                          int64_t n_cand, uint32_t flags, void* stream, siesta_dev_matches* out);
 void siesta_dev_matches_free(siesta_dev_matches* m);
 
+/* ------------------------------------------------- pair index + intersection */
+/* Kernel K2.  Replaces SparkDatabaseRepository.getCommonIds (storage/repositories/
+ * SparkDatabaseRepository.java:160-178): the traces that contain ALL true pairs = the intersection of the
+ * per-pair posting lists (ascending, duplicate-free dense trace indices). */
+typedef struct siesta_index siesta_index;
+
+/* Posting lists produced elsewhere (index.parquet rows of S3Connector.getAllEventPairs :236-292, mapped to dense
+ * trace indices and sorted by the caller): list p = trace_idx[post_off[p] .. post_off[p+1]). */
+int siesta_index_load(siesta_log* log, int32_t n_pairs, const int32_t* pair_a, const int32_t* pair_b,
+                      const int64_t* post_off, const int64_t* trace_idx, siesta_index** out);
+/* Posting lists derived on the GPU from the resident CSR log under the SeqTable view: a trace is listed under
+ * (A,B) iff it holds an A before a B (A == B: at least two occurrences).  <= 32 pairs / 32 distinct activities. */
+int siesta_index_build(siesta_log* log, const int32_t* pair_a, const int32_t* pair_b, int32_t n_pairs,
+                       siesta_index** out);
+void siesta_index_free(siesta_index* index);
+int64_t siesta_index_list_len(const siesta_index* index, int32_t pair);
+int siesta_index_get_list(const siesta_index* index, int32_t pair, int64_t* out, int64_t cap);
+/* Intersection of lists pair_ids[0..n): ascending trace indices, ready to be siesta_detect's `cand`. */
+int siesta_intersect(siesta_index* index, const int32_t* pair_ids, int32_t n, int64_t* out, int64_t cap, int64_t* out_n);
+/* Same, result left in HBM (*d_out, free with siesta_device_free) for siesta_detect_device's d_cand. */
+int siesta_intersect_device(siesta_index* index, const int32_t* pair_ids, int32_t n, int64_t** d_out, int64_t* out_n,
+                            double* kernel_ms);
+void siesta_device_free(siesta_log* log, void* d_ptr);
+
+/* ------------------------------------------------------- declare counting */
+/* Kernel K3.  Replaces the per-trace counting of the declare plans (declare/queryPlans/):
+ *   existence/QueryPlanExistences.java  createMapForSingle :136-142, extractUniqueTracesSingle :150-158,
+ *                                       joinUnionTraces :164-179 (over S3Connector.queryIndexTableDeclare :389-404)
+ *   orderedRelations/QueryPlanOrderedRelations.java  joinTables :97-116, evaluateConstraint :127-151 with
+ *                                       OrderedRelationsUtilityFunctions.countResponse / countPrecedence :25-44
+ *   position/QueryPlanPositions.java    execute :51-79
+ * over the SeqTable view of the pair index (a trace is listed under (A,B) iff it holds an A before a B).
+ * The result is ONE packed int64 array so that the multi-GPU combine is a single sum all-reduce:
+ *   tot[A] uniq[A] first[A] last[A] hist[A][k_cap+1] co[A][A] ordered[A][A] response[A][A] precedence[A][A]
+ *   hist_overflow n_nonempty_traces
+ * (meaning of each block: oracle/counting_oracle.cpp).  Supports and thresholds (one double division each:
+ * QueryPlanExistences templates :188-438, QueryPlanOrderedRelations.filterBasedOnSupport :161-233) stay with
+ * the caller.  n_activities <= 104 (the A x A matrices live in shared memory). */
+int64_t siesta_declare_counts_size(int32_t n_activities, int32_t k_cap);
+int siesta_declare_counts(siesta_log* log, int32_t k_cap, int64_t* out /* host, _size() values */, double* kernel_ms);
+int siesta_declare_counts_device(siesta_log* log, int32_t k_cap, int64_t* d_out /* device */, void* stream,
+                                 double* kernel_ms);
+
 /* Number of kernels this library has launched in this process (bench.py's
  * gpu_launches). */
 int64_t siesta_kernel_launches(void);

@@ -88,3 +88,40 @@ def detect(trace_off, act, ts_ms, nfa, cand=None, flags=0, n_threads=1):
     res = _abi.MatchResult.from_struct(out.contents)
     L.oracle_matches_free(out)
     return res
+
+
+def declare_counts(trace_off, act, n_activities, k_cap=64):
+    """Literal restatement of the declare counting jobs -> _abi.DeclareCounts."""
+    L = lib()
+    trace_off = np.ascontiguousarray(trace_off, dtype=np.int64)
+    act = np.ascontiguousarray(act, dtype=np.int32)
+    L.oracle_declare_size.restype = C.c_int64
+    n = L.oracle_declare_size(C.c_int32(n_activities), C.c_int32(k_cap))
+    out = np.zeros(n, dtype=np.int64)
+    L.oracle_declare_counts(_p(trace_off, C.c_int64), _p(act, C.c_int32), C.c_int64(len(trace_off) - 1),
+                            C.c_int32(n_activities), C.c_int32(k_cap), _p(out, C.c_int64))
+    return _abi.DeclareCounts(out, n_activities, k_cap)
+
+
+def posting_list(trace_off, act, a, b):
+    L = lib()
+    trace_off = np.ascontiguousarray(trace_off, dtype=np.int64)
+    act = np.ascontiguousarray(act, dtype=np.int32)
+    out = np.zeros(len(trace_off) - 1, dtype=np.int64)
+    L.oracle_posting_list.restype = C.c_int64
+    n = L.oracle_posting_list(_p(trace_off, C.c_int64), _p(act, C.c_int32), C.c_int64(len(trace_off) - 1), C.c_int32(a),
+                              C.c_int32(b), _p(out, C.c_int64))
+    return out[:n].copy()
+
+
+def intersect(lists):
+    L = lib()
+    lists = [np.ascontiguousarray(x, dtype=np.int64) for x in lists]
+    if not lists:
+        return np.zeros(0, dtype=np.int64)
+    ptrs = (C.POINTER(C.c_int64) * len(lists))(*[_p(x, C.c_int64) for x in lists])
+    lens = np.array([len(x) for x in lists], dtype=np.int64)
+    out = np.zeros(min(len(x) for x in lists), dtype=np.int64)
+    L.oracle_intersect.restype = C.c_int64
+    n = L.oracle_intersect(ptrs, _p(lens, C.c_int64), C.c_int32(len(lists)), _p(out, C.c_int64))
+    return out[:n].copy()

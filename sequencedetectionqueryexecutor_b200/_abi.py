@@ -146,3 +146,25 @@ class MatchResult:
             if a.shape != b.shape or not np.array_equal(a, b):
                 return False, k
         return True, ""
+
+
+class DeclareCounts:
+    """Named views over the packed int64 result of siesta_declare_counts (layout: include/siesta_gpu.h)."""
+
+    def __init__(self, packed, n_activities, k_cap, kernel_ms=0.0):
+        import numpy as np
+        A, K = n_activities, k_cap + 1
+        self.packed = np.asarray(packed, dtype=np.int64)
+        self.n_activities, self.k_cap, self.kernel_ms = A, k_cap, kernel_ms
+        o = 0
+        self.tot = self.packed[o:o + A]; o += A
+        self.uniq = self.packed[o:o + A]; o += A
+        self.first = self.packed[o:o + A]; o += A
+        self.last = self.packed[o:o + A]; o += A
+        self.hist = self.packed[o:o + A * K].reshape(A, K); o += A * K
+        self.co = self.packed[o:o + A * A].reshape(A, A); o += A * A
+        self.ordered = self.packed[o:o + A * A].reshape(A, A); o += A * A
+        self.response = self.packed[o:o + A * A].reshape(A, A); o += A * A
+        self.precedence = self.packed[o:o + A * A].reshape(A, A); o += A * A
+        self.hist_overflow = int(self.packed[o])
+        self.n_nonempty = int(self.packed[o + 1])

@@ -14,7 +14,9 @@ EXPORTS = [
     "siesta_last_error", "siesta_pattern_compile", "siesta_init", "siesta_shutdown", "siesta_log_load",
     "siesta_log_wrap_device", "siesta_log_free", "siesta_log_n_traces", "siesta_log_n_events", "siesta_detect",
     "siesta_matches_free", "siesta_evaluate_events", "siesta_detect_device", "siesta_dev_matches_free",
-    "siesta_kernel_launches",
+    "siesta_kernel_launches", "siesta_declare_counts_size", "siesta_declare_counts", "siesta_declare_counts_device",
+    "siesta_index_load", "siesta_index_build", "siesta_index_free", "siesta_index_list_len", "siesta_index_get_list",
+    "siesta_intersect", "siesta_intersect_device", "siesta_device_free",
 ]
 
 
@@ -55,6 +57,21 @@ def lib():
     L.siesta_dev_matches_free.argtypes = [P(_abi.DevMatches)]
     L.siesta_dev_matches_free.restype = None
     L.siesta_kernel_launches.restype = i64
+    L.siesta_declare_counts_size.argtypes = [i32, i32]
+    L.siesta_declare_counts_size.restype = i64
+    L.siesta_declare_counts.argtypes = [vp, i32, vp, P(C.c_double)]
+    L.siesta_declare_counts_device.argtypes = [vp, i32, vp, vp, P(C.c_double)]
+    L.siesta_index_load.argtypes = [vp, i32, vp, vp, vp, vp, P(vp)]
+    L.siesta_index_build.argtypes = [vp, vp, vp, i32, P(vp)]
+    L.siesta_index_free.argtypes = [vp]
+    L.siesta_index_free.restype = None
+    L.siesta_index_list_len.argtypes = [vp, i32]
+    L.siesta_index_list_len.restype = i64
+    L.siesta_index_get_list.argtypes = [vp, i32, vp, i64]
+    L.siesta_intersect.argtypes = [vp, vp, i32, vp, i64, P(i64)]
+    L.siesta_intersect_device.argtypes = [vp, vp, i32, P(vp), P(i64), P(C.c_double)]
+    L.siesta_device_free.argtypes = [vp, vp]
+    L.siesta_device_free.restype = None
     _lib = L
     return L
 

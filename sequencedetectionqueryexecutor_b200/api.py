@@ -102,6 +102,72 @@ class EventLog:
         return DeviceMatches(dm)
 
 
+    def declare_counts(self, k_cap=None):
+        """siesta_declare_counts: the integer matrices behind /declare (host copy, DeclareCounts)."""
+        import numpy as np
+        k_cap = int(k_cap if k_cap is not None else 64)
+        n = lib().siesta_declare_counts_size(self.n_activities, k_cap)
+        out = np.zeros(n, dtype=np.int64)
+        ms = C.c_double(0.0)
+        check(lib().siesta_declare_counts(self._h, k_cap, _ptr(out), C.byref(ms)))
+        return _abi.DeclareCounts(out, self.n_activities, k_cap, ms.value)
+
+    def declare_counts_device(self, d_out, k_cap, stream=None):
+        """siesta_declare_counts_device: packed int64 result into a caller-owned CUDA tensor (for all-reduce)."""
+        ms = C.c_double(0.0)
+        check(lib().siesta_declare_counts_device(self._h, int(k_cap), C.c_void_p(d_out.data_ptr()),
+                                                 C.c_void_p(stream) if stream else None, C.byref(ms)))
+        return ms.value
+
+
+    def build_index(self, pairs):
+        """siesta_index_build: posting lists of the (A,B) pairs from the resident log (SeqTable view)."""
+        return PairIndex(self, pairs)
+
+    def load_index(self, pairs, lists):
+        """siesta_index_load: posting lists (ascending trace indices) produced elsewhere, e.g. index.parquet."""
+        return PairIndex(self, pairs, lists=lists)
+
+
+class PairIndex:
+    """siesta_index: per-pair posting lists in HBM + the sorted trace-id intersection (kernel K2)."""
+
+    def __init__(self, log, pairs, lists=None):
+        self.log = log
+        self.pairs = [(int(a), int(b)) for a, b in pairs]
+        pa = np.array([p[0] for p in self.pairs], dtype=np.int32)
+        pb = np.array([p[1] for p in self.pairs], dtype=np.int32)
+        self._h = C.c_void_p()
+        if lists is None:
+            check(lib().siesta_index_build(log._h, _ptr(pa), _ptr(pb), len(self.pairs), C.byref(self._h)))
+        else:
+            lists = [np.ascontiguousarray(x, dtype=np.int64) for x in lists]
+            off = np.zeros(len(lists) + 1, dtype=np.int64)
+            np.cumsum([len(x) for x in lists], out=off[1:])
+            flat = np.concatenate(lists) if lists and off[-1] else np.zeros(0, dtype=np.int64)
+            check(lib().siesta_index_load(log._h, len(self.pairs), _ptr(pa), _ptr(pb), _ptr(off), _ptr(flat), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().siesta_index_free(self._h)
+            self._h = C.c_void_p()
+
+    def posting_list(self, i):
+        n = lib().siesta_index_list_len(self._h, i)
+        out = np.zeros(max(n, 0), dtype=np.int64)
+        check(lib().siesta_index_get_list(self._h, i, _ptr(out), len(out)))
+        return out
+
+    def intersect(self, pair_ids=None):
+        """getCommonIds: ascending trace indices present in every selected posting list."""
+        ids = np.arange(len(self.pairs), dtype=np.int32) if pair_ids is None else np.asarray(pair_ids, dtype=np.int32)
+        cap = min(lib().siesta_index_list_len(self._h, int(i)) for i in ids) if len(ids) else 0
+        out = np.zeros(max(cap, 0), dtype=np.int64)
+        n = C.c_int64(0)
+        check(lib().siesta_intersect(self._h, _ptr(ids), len(ids), _ptr(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+
 class DeviceMatches:
     def __init__(self, dm):
         self.dm = dm

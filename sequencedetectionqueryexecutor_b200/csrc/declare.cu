@@ -1,0 +1,272 @@
+// declare.cu — kernel K3: per-trace counting behind /declare (existences, ordered relations, positions).
+//
+// Replaces the Spark jobs of QueryPlanExistences (createMapForSingle :136-142, joinUnionTraces :164-179),
+// QueryPlanOrderedRelations (joinTables :97-116, evaluateConstraint :127-151 with
+// OrderedRelationsUtilityFunctions.countResponse/countPrecedence :25-44) and QueryPlanPositions.execute :51-79
+// (all under J/declare/queryPlans/).  The kernel produces integer count matrices; supports (one double division)
+// and thresholds stay on the host, fed by these integers.
+//
+// One warp per trace.  Pass 1 (lanes = events, coalesced int32 loads): per-activity count / first / last position
+// in the warp's shared-memory scratch.  Pass 2 (lanes = activities): existence histogram and the A x A presence
+// matrices from (count, first, last) alone.  Pass 3 (serial over the trace, lanes = activities): response and
+// precedence through running per-activity counts, touched only at the first / last occurrence of an activity:
+//     response[a][b]   = #{a : some b after a}  = (# a before last[b])
+//     precedence[a][b] = #{b : some a before b} = count[b] - (# b before first[a])
+// All counters of a CTA live in shared memory (uint32) and are flushed with 64-bit atomics once per CTA.
+// Bound: integer ALU / shared-memory atomics, not HBM (4 B/event + 8 B/trace of traffic); see DESIGN.md.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace siesta {
+
+constexpr int DT = 256;      // threads per CTA
+constexpr int HS = 16;       // histogram buckets kept in shared memory (k < HS)
+constexpr int MAX_A_SMEM = 104;
+
+struct DeclareParams {
+    const int64_t* trace_off;
+    const int32_t* act;
+    int64_t n_traces;
+    int32_t A;
+    int32_t k_cap;
+    unsigned long long* out;  // packed layout, see siesta_declare_counts_size
+};
+
+__device__ __forceinline__ long long shfl64(long long v, int src) {
+    int lo = __shfl_sync(0xffffffffu, (int)(v & 0xffffffffll), src);
+    int hi = __shfl_sync(0xffffffffu, (int)(v >> 32), src);
+    return ((long long)hi << 32) | (unsigned int)lo;
+}
+
+template <int NB>  // NB = ceil(A / 32) activity blocks held in registers per lane
+__global__ void __launch_bounds__(DT) declare_kernel(const __grid_constant__ DeclareParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int A = P.A;
+    const int AA = A * A;
+    uint32_t* s_co = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* s_ord = s_co + AA;
+    uint32_t* s_respT = s_ord + AA;   // transposed: [b][a]
+    uint32_t* s_prec = s_respT + AA;  // [a][b]
+    uint32_t* s_tot = s_prec + AA;
+    uint32_t* s_uniq = s_tot + A;
+    uint32_t* s_first = s_uniq + A;
+    uint32_t* s_last = s_first + A;
+    uint32_t* s_hist = s_last + A;    // [A][HS]
+    uint32_t* s_warp = s_hist + A * HS;  // per warp: cnt[A], first[A], last[A]
+    __shared__ unsigned long long s_misc[2];  // hist_overflow, n_nonempty
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* w_cnt = s_warp + warp * 3 * A;
+    uint32_t* w_first = w_cnt + A;
+    uint32_t* w_last = w_first + A;
+
+    for (int i = threadIdx.x; i < 4 * AA + 4 * A + A * HS; i += DT) s_co[i] = 0;
+    if (threadIdx.x < 2) s_misc[threadIdx.x] = 0;
+    __syncthreads();
+
+    const long long warps_total = (long long)gridDim.x * (DT / 32);
+    for (long long t = (long long)blockIdx.x * (DT / 32) + warp; t < P.n_traces; t += warps_total) {
+        long long lo = 0, hi = 0;
+        if (lane == 0) { lo = P.trace_off[t]; hi = P.trace_off[t + 1]; }
+        lo = shfl64(lo, 0);
+        hi = shfl64(hi, 0);
+        if (hi <= lo) continue;
+        const int len = (int)(hi - lo);
+        for (int a = lane; a < A; a += 32) { w_cnt[a] = 0; w_first[a] = 0xffffffffu; w_last[a] = 0; }
+        __syncwarp();
+        // pass 1: per-activity count / first / last
+        for (int i = lane; i < len; i += 32) {
+            const int x = __ldg(P.act + lo + i);
+            if (x >= 0 && x < A) {
+                atomicAdd(&w_cnt[x], 1u);
+                atomicMin(&w_first[x], (uint32_t)i);
+                atomicMax(&w_last[x], (uint32_t)i);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            atomicAdd(&s_misc[1], 1ull);
+            const int xf = P.act[lo], xl = P.act[hi - 1];
+            if (xf >= 0 && xf < A) atomicAdd(&s_first[xf], 1u);
+            if (xl >= 0 && xl < A) atomicAdd(&s_last[xl], 1u);
+        }
+        // pass 2: existence counts and presence matrices
+        uint32_t cnt_r[NB], run_r[NB];
+#pragma unroll
+        for (int kb = 0; kb < NB; ++kb) {
+            const int b = kb * 32 + lane;
+            cnt_r[kb] = b < A ? w_cnt[b] : 0;
+            run_r[kb] = 0;
+            if (cnt_r[kb]) {
+                atomicAdd(&s_tot[b], cnt_r[kb]);
+                atomicAdd(&s_uniq[b], 1u);
+                if (cnt_r[kb] > (uint32_t)P.k_cap) atomicAdd(&s_misc[0], 1ull);   // beyond the caller's histogram
+                else if (cnt_r[kb] < (uint32_t)HS) atomicAdd(&s_hist[b * HS + cnt_r[kb]], 1u);
+                else atomicAdd(P.out + 4ll * A + (long long)b * (P.k_cap + 1) + cnt_r[kb], 1ull);
+            }
+        }
+        for (int a = 0; a < A; ++a) {
+            const uint32_t ca = w_cnt[a];
+            if (ca == 0) continue;  // uniform
+            const uint32_t fa = w_first[a];
+#pragma unroll
+            for (int kb = 0; kb < NB; ++kb) {
+                const int b = kb * 32 + lane;
+                if (b >= A || cnt_r[kb] == 0) continue;
+                if (b == a) {
+                    if (ca >= 2) { atomicAdd(&s_ord[a * A + b], 1u); atomicAdd(&s_co[a * A + b], 1u); }
+                } else {
+                    atomicAdd(&s_co[a * A + b], 1u);
+                    if (fa < w_last[b]) atomicAdd(&s_ord[a * A + b], 1u);
+                }
+            }
+        }
+        // pass 3: response / precedence at first / last occurrences, running counts in registers
+        for (int i = 0; i < len; ++i) {
+            const int x = __ldg(P.act + lo + i);  // uniform address: one broadcast transaction
+            if (x < 0 || x >= A) continue;
+            const bool is_last = w_last[x] == (uint32_t)i, is_first = w_first[x] == (uint32_t)i;
+            if (is_last || is_first) {
+#pragma unroll
+                for (int kb = 0; kb < NB; ++kb) {
+                    const int o = kb * 32 + lane;
+                    if (o >= A || o == x || cnt_r[kb] == 0) continue;
+                    if (is_last && run_r[kb]) atomicAdd(&s_respT[x * A + o], run_r[kb]);               // response[o][x]
+                    if (is_first && cnt_r[kb] > run_r[kb]) atomicAdd(&s_prec[x * A + o], cnt_r[kb] - run_r[kb]);  // precedence[x][o]
+                }
+            }
+#pragma unroll
+            for (int kb = 0; kb < NB; ++kb)
+                if (x == kb * 32 + lane) ++run_r[kb];
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // flush: packed layout tot uniq first last hist co ordered response precedence overflow nonempty
+    unsigned long long* o_tot = P.out;
+    unsigned long long* o_uniq = o_tot + A;
+    unsigned long long* o_first = o_uniq + A;
+    unsigned long long* o_last = o_first + A;
+    unsigned long long* o_hist = o_last + A;
+    unsigned long long* o_co = o_hist + (long long)A * (P.k_cap + 1);
+    unsigned long long* o_ord = o_co + AA;
+    unsigned long long* o_resp = o_ord + AA;
+    unsigned long long* o_prec = o_resp + AA;
+    for (int i = threadIdx.x; i < A; i += DT) {
+        if (s_tot[i]) atomicAdd(o_tot + i, (unsigned long long)s_tot[i]);
+        if (s_uniq[i]) atomicAdd(o_uniq + i, (unsigned long long)s_uniq[i]);
+        if (s_first[i]) atomicAdd(o_first + i, (unsigned long long)s_first[i]);
+        if (s_last[i]) atomicAdd(o_last + i, (unsigned long long)s_last[i]);
+    }
+    for (int i = threadIdx.x; i < A * HS; i += DT) {
+        const int a = i / HS, k = i % HS;
+        if (s_hist[i] && k <= P.k_cap) atomicAdd(o_hist + (long long)a * (P.k_cap + 1) + k, (unsigned long long)s_hist[i]);
+    }
+    for (int i = threadIdx.x; i < AA; i += DT) {
+        if (s_co[i]) atomicAdd(o_co + i, (unsigned long long)s_co[i]);
+        if (s_ord[i]) atomicAdd(o_ord + i, (unsigned long long)s_ord[i]);
+        if (s_prec[i]) atomicAdd(o_prec + i, (unsigned long long)s_prec[i]);
+        if (s_respT[i]) {
+            const int b = i / A, a = i % A;  // transposed in shared memory
+            atomicAdd(o_resp + (long long)a * A + b, (unsigned long long)s_respT[i]);
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (s_misc[0]) atomicAdd(o_prec + AA, s_misc[0]);
+        if (s_misc[1]) atomicAdd(o_prec + AA + 1, s_misc[1]);
+    }
+}
+
+static size_t declare_smem(int A) { return sizeof(uint32_t) * ((size_t)4 * A * A + 4 * A + (size_t)A * HS + (size_t)(DT / 32) * 3 * A); }
+
+template <int NB>
+static int launch_declare(const Ctx* ctx, cudaStream_t stream, const DeclareParams& P) {
+    const size_t smem = declare_smem(P.A);
+    auto kern = declare_kernel<NB>;
+    SIESTA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DT, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t ctas_needed = (P.n_traces + DT / 32 - 1) / (DT / 32);
+    int grid = (int)std::min<int64_t>(std::max<int64_t>(ctas_needed, 1), (int64_t)ctx->sm_count * per_sm);
+    kern<<<grid, DT, smem, stream>>>(P);
+    SIESTA_LAUNCHED();
+    SIESTA_CUDA_OK(cudaGetLastError());
+    return SIESTA_OK;
+}
+
+}  // namespace siesta
+
+using namespace siesta;
+
+extern "C" int64_t siesta_declare_counts_size(int32_t A, int32_t k_cap) {
+    return 4ll * A + (int64_t)A * (k_cap + 1) + 4ll * A * A + 2;
+}
+
+extern "C" int siesta_declare_counts_device(siesta_log* log, int32_t k_cap, int64_t* d_out, void* stream_, double* kernel_ms) {
+    if (!log || !d_out || k_cap < 1) {
+        set_error("siesta_declare_counts_device: bad argument");
+        return SIESTA_E_INVALID;
+    }
+    Log* L = reinterpret_cast<Log*>(log);
+    const int A = L->n_activities;
+    if (A < 1 || A > MAX_A_SMEM) {
+        set_error("declare counting keeps the A x A matrices in shared memory: 1 <= n_activities <= " + std::to_string(MAX_A_SMEM));
+        return SIESTA_E_UNSUPPORTED;
+    }
+    SIESTA_CUDA_OK(cudaSetDevice(L->ctx->device));
+    cudaStream_t stream = stream_ ? reinterpret_cast<cudaStream_t>(stream_) : L->ctx->stream;
+    DeclareParams P;
+    P.trace_off = L->d_trace_off;
+    P.act = L->d_act;
+    P.n_traces = L->n_traces;
+    P.A = A;
+    P.k_cap = k_cap;
+    P.out = reinterpret_cast<unsigned long long*>(d_out);
+    cudaEvent_t e0, e1;
+    SIESTA_CUDA_OK(cudaEventCreate(&e0));
+    SIESTA_CUDA_OK(cudaEventCreate(&e1));
+    SIESTA_CUDA_OK(cudaMemsetAsync(d_out, 0, sizeof(int64_t) * (size_t)siesta_declare_counts_size(A, k_cap), stream));
+    SIESTA_CUDA_OK(cudaEventRecord(e0, stream));
+    int rc;
+    const int nb = (A + 31) / 32;
+    if (nb == 1) rc = launch_declare<1>(L->ctx, stream, P);
+    else if (nb == 2) rc = launch_declare<2>(L->ctx, stream, P);
+    else if (nb == 3) rc = launch_declare<3>(L->ctx, stream, P);
+    else rc = launch_declare<4>(L->ctx, stream, P);
+    if (rc) return rc;
+    SIESTA_CUDA_OK(cudaEventRecord(e1, stream));
+    SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    SIESTA_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (kernel_ms) *kernel_ms = ms;
+    return SIESTA_OK;
+}
+
+extern "C" int siesta_declare_counts(siesta_log* log, int32_t k_cap, int64_t* out, double* kernel_ms) {
+    if (!log || !out) {
+        set_error("siesta_declare_counts: null argument");
+        return SIESTA_E_INVALID;
+    }
+    Log* L = reinterpret_cast<Log*>(log);
+    SIESTA_CUDA_OK(cudaSetDevice(L->ctx->device));
+    const size_t bytes = sizeof(int64_t) * (size_t)siesta_declare_counts_size(L->n_activities, k_cap);
+    int64_t* d = nullptr;
+    SIESTA_CUDA_OK(cudaMallocAsync((void**)&d, bytes, L->ctx->stream));
+    int rc = siesta_declare_counts_device(log, k_cap, d, L->ctx->stream, kernel_ms);
+    if (rc == SIESTA_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, L->ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(L->ctx->stream);
+        if (e != cudaSuccess) {
+            set_error(std::string("siesta_declare_counts: D2H: ") + cudaGetErrorString(e));
+            rc = SIESTA_E_CUDA;
+        }
+    }
+    cudaFreeAsync(d, L->ctx->stream);
+    return rc;
+}

@@ -1,0 +1,88 @@
+"""Parity of the CUDA counting kernels (declare counts K3, pair index + intersection K2) against the oracle."""
+import numpy as np
+import pytest
+
+import oracle
+from tests import gen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from sequencedetectionqueryexecutor_b200 import api
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("n_act,n_traces,lens,zipf", [(3, 50, (0, 12), None), (20, 3000, (30, 70), None),
+                                                      (20, 3000, (30, 70), 1.1), (100, 1500, (50, 50), None),
+                                                      (33, 700, (0, 90), 1.1), (64, 300, (1, 300), None)])
+def test_declare_counts_match_oracle(ctx, n_act, n_traces, lens, zipf):
+    off, act, ts = gen.make_log(n_traces, lens[0], lens[1], n_act, seed=100 + n_act, zipf=zipf)
+    log = ctx.load_log(off, act, ts, n_act)
+    got = log.declare_counts(k_cap=40)
+    log.close()
+    want = oracle.declare_counts(off, act, n_act, 40)
+    for name in ("tot", "uniq", "first", "last", "hist", "co", "ordered", "response", "precedence"):
+        assert np.array_equal(getattr(got, name), getattr(want, name)), name
+    assert got.hist_overflow == want.hist_overflow and got.n_nonempty == want.n_nonempty
+
+
+def test_declare_counts_histogram_cap_and_limits(ctx):
+    from sequencedetectionqueryexecutor_b200._lib import SiestaError
+    off, act, ts = gen.make_log(500, 20, 60, 4, seed=8)
+    log = ctx.load_log(off, act, ts, 4)
+    got = log.declare_counts(k_cap=5)
+    want = oracle.declare_counts(off, act, 4, 5)
+    log.close()
+    assert np.array_equal(got.packed, want.packed) and got.hist_overflow > 0
+    log = ctx.load_log(*gen.make_log(10, 5, 5, 200, seed=8), 200)
+    with pytest.raises(SiestaError):
+        log.declare_counts()
+    log.close()
+
+
+@pytest.mark.parametrize("n_act,n_traces,lens", [(5, 2000, (0, 12)), (20, 20000, (30, 50)), (3, 777, (0, 4))])
+def test_pair_index_and_intersection_match_oracle(ctx, n_act, n_traces, lens):
+    off, act, ts = gen.make_log(n_traces, lens[0], lens[1], n_act, seed=300 + n_act)
+    log = ctx.load_log(off, act, ts, n_act)
+    pairs = [(0, 1), (1, 0), (0, 0), (1, 2), (0, 2), (2, 2), (0, n_act + 5)]  # the last names an unknown activity
+    idx = log.build_index(pairs)
+    lists = []
+    for i, (a, b) in enumerate(pairs):
+        got = idx.posting_list(i)
+        want = oracle.posting_list(off, act, a, b)
+        assert np.array_equal(got, want), (a, b)
+        lists.append(want)
+    # getCommonIds for A B C: all ordered pairs i<j must be present
+    for sel in ([0, 3, 4], [0], [0, 1], [2, 5], [0, 1, 2, 3, 4, 5], [0, 6]):
+        got = idx.intersect(sel)
+        want = oracle.intersect([lists[i] for i in sel])
+        assert np.array_equal(got, want), sel
+    idx.close()
+    # posting lists supplied by the caller (index.parquet route)
+    idx2 = log.load_index(pairs[:3], lists[:3])
+    assert np.array_equal(idx2.intersect(), oracle.intersect(lists[:3]))
+    idx2.close()
+    log.close()
+
+
+def test_pruning_then_verification_pipeline(ctx):
+    """P1 -> V: the intersection feeds siesta_detect's candidate list; result equals verifying every trace,
+    because traces without all true pairs cannot match (QueryPlanPatternDetection.getMiddleResults :146-164)."""
+    from sequencedetectionqueryexecutor_b200 import _abi as abi
+    off, act, ts = gen.make_log(8000, 10, 30, 12, seed=41)
+    log = ctx.load_log(off, act, ts, 12)
+    nfa = abi.make_nfa([dict(kind=abi.STATE_NORMAL, types=[0]), dict(kind=abi.STATE_NORMAL, types=[1]),
+                        dict(kind=abi.STATE_NORMAL, types=[2])])
+    idx = log.build_index([(0, 1), (0, 2), (1, 2)])
+    cand = idx.intersect()
+    idx.close()
+    pruned = log.detect(nfa, cand=cand)
+    full = log.detect(nfa)
+    log.close()
+    assert len(cand) < 8000 and pruned.same_as(full)[0]
+    want = oracle.detect(off, act, ts, nfa, cand=cand)
+    assert pruned.same_as(want)[0]
