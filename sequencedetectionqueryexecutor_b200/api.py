@@ -179,6 +179,31 @@ class DeviceMatches:
             lib().siesta_dev_matches_free(C.byref(self.dm))
             self.dm = None
 
+    def tensors(self, device_index=0):
+        """Zero-copy torch views of the device result (valid until close()); keys as in MatchResult."""
+        import torch
+
+        class _View:
+            def __init__(self, ptr, n, typestr):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+        def view(ptr, n, typestr, dtype):
+            if not ptr or n == 0:
+                return torch.zeros(0, dtype=dtype, device=f"cuda:{device_index}")
+            return torch.as_tensor(_View(ptr, n, typestr), device=f"cuda:{device_index}")
+
+        d = self.dm
+        out = {"trace_idx": view(d.d_trace_idx, d.n_traces, "<i8", torch.int64),
+               "occ_off": view(d.d_occ_off, d.n_traces + 1, "<i8", torch.int64),
+               "ev_off": view(d.d_ev_off, d.n_occurrences + 1, "<i8", torch.int64),
+               "ev_pos": view(d.d_ev_pos, d.n_events, "<i4", torch.int32),
+               "err_trace_idx": view(d.d_err_trace_idx, d.n_ref_errors, "<i8", torch.int64)}
+        if d.d_ev_rank:
+            out["ev_rank"] = view(d.d_ev_rank, d.n_events, "<i4", torch.int32)
+            out["ev_act"] = view(d.d_ev_act, d.n_events, "<i4", torch.int32)
+            out["ev_ts_ms"] = view(d.d_ev_ts_ms, d.n_events, "<i8", torch.int64)
+        return out
+
 
 def kernel_launches():
     return int(lib().siesta_kernel_launches())

@@ -187,3 +187,19 @@ def test_one_million_events_idempotent_and_sorted(ctx):
     inner = np.ones(a.n_events, dtype=bool)
     inner[a.ev_off[:-1]] = False
     assert np.all(np.diff(a.ev_pos)[inner[1:]] > 0)
+
+
+def test_device_result_views_and_single_rank_gather(ctx):
+    """DeviceMatches.tensors(): zero-copy torch views of the HBM-resident result equal the host-buffer result."""
+    import torch
+    off, act, ts = gen.make_log(3000, 20, 40, 10, seed=21)
+    nfa = abi.make_nfa([dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[2])])
+    log = ctx.load_log(off, act, ts, 10)
+    host = log.detect(nfa, flags=abi.F_RETURN_ALL)
+    dm = log.detect_device(nfa, flags=abi.F_RETURN_ALL)
+    t = dm.tensors(0)
+    torch.cuda.synchronize()
+    for k in ("trace_idx", "occ_off", "ev_off", "ev_pos", "ev_rank", "ev_act", "ev_ts_ms"):
+        assert np.array_equal(t[k].cpu().numpy(), getattr(host, k)), k
+    dm.close()
+    log.close()
