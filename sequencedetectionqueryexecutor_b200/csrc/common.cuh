@@ -55,6 +55,7 @@ struct DevNfa {
     uint8_t any_kleene;
     uint8_t merge_safe;  // dominated-run merging is exact for this NFA (see validate_nfa)
     uint8_t cross_safe;  // ... also across value-vector families (all predicates reference earlier states)
+    uint8_t fast_class;  // FAST_* (detect_fast.cuh): the NFA and the flags admit a closed-form evaluator
     int8_t kmax[SIESTA_MAX_STATES + 1];                 // largest slot a run at state c can still read, -1 = none
     unsigned long long relmask[SIESTA_MAX_STATES + 1];  // byte k = 0xFF iff a predicate of a state >= c references state k
     uint8_t p_attr[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];

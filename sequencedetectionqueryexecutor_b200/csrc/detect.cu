@@ -19,7 +19,7 @@
 #include <cstring>
 #include <vector>
 
-#include "detect_engine.cuh"
+#include "detect_fast.cuh"
 
 namespace siesta {
 
@@ -33,6 +33,10 @@ struct DetectParams {
     const int64_t* work;      // indices into the candidate list to process, or nullptr (= all)
     int64_t n_work;           // number of traces this launch verifies
     const uint16_t* lut;      // [n_act] smask | fmask << 8
+    unsigned long long relbits;  // small_alphabet: bit a = activity a belongs to the pattern
+    int64_t n_events;         // events of the whole log (bound of the vector loads)
+    int32_t small_alphabet;   // n_act <= 64
+    int32_t vec_ok;           // act is 16-byte aligned: 128-bit loads
     int32_t n_act;
     uint32_t flags;
     int32_t needs_ts;
@@ -80,11 +84,16 @@ struct WarpSmem {
     static constexpr size_t bytes_bytes = SMEM_RUNS ? (size_t)(R + 3 * NF) * 32 : 0;
     static constexpr size_t ts_off = (bytes_off + bytes_bytes + 15) & ~(size_t)15;  // only when the query needs seconds
     static constexpr size_t ts_bytes = sizeof(int32_t) * NE * 32;
-    static __host__ __device__ constexpr size_t total(bool needs_ts) { return ts_off + (needs_ts ? ts_bytes : 0); }
+    static constexpr size_t aux_bytes = sizeof(typename MaskOps<W>::T) * NE * 32;   // NK + returnAll: one mask per start
+    static __host__ __device__ constexpr size_t aux_off(bool needs_ts) { return ts_off + (needs_ts ? ts_bytes : 0); }
+    static __host__ __device__ constexpr size_t total(bool needs_ts, bool needs_aux) {
+        return aux_off(needs_ts) + (needs_aux ? aux_bytes : 0);
+    }
 };
 
 // One warp owns a tile of 32 traces from start to finish: no block-level barrier anywhere.
-template <int W, int R, int NF, bool SMEM_RUNS>
+// MODE: FAST_NONE = run-list engine, FAST_NK / FAST_FK2 = closed-form evaluators (detect_fast.cuh).
+template <int W, int R, int NF, bool SMEM_RUNS, int MODE>
 __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ DevNfa nfa) {
     typedef MaskOps<W> MO;
     typedef typename MO::T mask_t;
@@ -93,20 +102,24 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* wbase = smem_raw + (size_t)warp * L::total(P.needs_ts != 0);
+    const bool evt_pos = (P.flags & SIESTA_F_EVT_POS) != 0;
+    const bool return_all = (P.flags & SIESTA_F_RETURN_ALL) != 0;
+    const bool needs_aux = MODE == FAST_NK && return_all;
+    unsigned char* wbase = smem_raw + (size_t)warp * L::total(P.needs_ts != 0, needs_aux);
     uint32_t* s_meta = reinterpret_cast<uint32_t*>(wbase + L::meta_off);  // [NE][32]
     int32_t* s_ts = reinterpret_cast<int32_t*>(wbase + L::ts_off);        // [NE][32] when needs_ts
 
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const bool evt_pos = (P.flags & SIESTA_F_EVT_POS) != 0;
-    const bool return_all = (P.flags & SIESTA_F_RETURN_ALL) != 0;
     const bool all_cols = (P.flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
     const bool prune = (P.flags & SIESTA_F_LITERAL_RUNS) == 0;
     const bool dedup = prune && !return_all && (P.flags & SIESTA_F_COUNT_MATCHES) == 0;
     const int warps_per_cta = blockDim.x >> 5;
 
     for (long long tile = (long long)blockIdx.x * warps_per_cta + warp; tile < P.n_tiles; tile += (long long)gridDim.x * warps_per_cta) {
-        // ------------------------------------------------------------------ phase A: filter + compact
+        // ------------------------------------------------------------------ phase A: filter + compact, one lane per trace
+        // Each lane streams its own trace in 32-byte sectors (two 128-bit loads = 8 activity ids), tests the ids against
+        // the pattern's type set in registers, and appends the surviving events to its lane-transposed shared-memory
+        // column (the reference's Trace.clearTrace / Utils.transformToSaseEvents).  Timestamps (int64 ms) are loaded
+        // only for surviving events, after the scan, as independent loads.
 #ifdef SIESTA_PHASE_TIMING
         long long tA = clock64();
 #endif
@@ -119,89 +132,124 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
             o0 = P.trace_off[t];
             o1 = P.trace_off[t + 1];
         }
-        int my_cnt = 0;
-        for (int tt = 0; tt < 32; ++tt) {
-            const long long b0 = shfl_i64(o0, tt), b1 = shfl_i64(o1, tt);
-            if (b1 <= b0) continue;
-            int cnt = 0;
-            long long t0 = 0;
-            for (long long p = b0; p < b1; p += 32) {
-                const long long idx = p + lane;
-                int a = -1;
-                if (idx < b1) a = __ldg(P.act + idx);
-                uint32_t m = 0;
-                if (a >= 0 && a < P.n_act) m = __ldg(P.lut + a);
-                const unsigned ball = __ballot_sync(0xffffffffu, m != 0);
-                if (ball == 0) continue;
-                long long ts = 0;
-                if (P.needs_ts) {
-                    if (m) ts = __ldg(reinterpret_cast<const long long*>(P.ts_ms) + idx);
-                    if (cnt == 0) t0 = shfl_i64(ts, __ffs(ball) - 1);  // first event of the filtered list (Utils.java:51-53)
+        int cnt = 0;
+        for (long long e = o0 & ~7LL; e < o1; e += 32) {
+            int4 v[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const long long c = e + 8 * q;
+                if (c < o1 && P.vec_ok && c + 8 <= P.n_events) {
+                    v[2 * q] = __ldg(reinterpret_cast<const int4*>(P.act + c));
+                    v[2 * q + 1] = __ldg(reinterpret_cast<const int4*>(P.act + c + 4));
+                } else {
+                    int a[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a[i] = (c + i < o1 && c + i >= o0) ? __ldg(P.act + c + i) : -1;
+                    v[2 * q] = make_int4(a[0], a[1], a[2], a[3]);
+                    v[2 * q + 1] = make_int4(a[4], a[5], a[6], a[7]);
                 }
-                if (m) {
-                    const int r = cnt + __popc(ball & lt_mask);
-                    if (r < NE && (idx - b0) < 65536) {
-                        s_meta[r * 32 + tt] = m | ((uint32_t)(idx - b0) << 16);
-                        // EventTs.transformSaseEvent: (int)((t - minTs) / 1000), truncating long division (EventTs.java:54)
-                        if (P.needs_ts) s_ts[r * 32 + tt] = (int)((ts - t0) / 1000);
-                    }
-                }
-                cnt += __popc(ball);
             }
-            if (b1 - b0 > 65536) cnt = NE + 1;  // in-trace index does not fit the packed word: overflow path
-            if (lane == tt) my_cnt = cnt;
+            uint32_t pend = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int a[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    bool rel;
+                    if (P.small_alphabet) rel = ((unsigned)a[i] < 64u) && ((P.relbits >> (a[i] & 63)) & 1ull);
+                    else rel = ((unsigned)a[i] < (unsigned)P.n_act) && __ldg(P.lut + a[i]) != 0;
+                    pend |= (rel ? 1u : 0u) << (4 * q + i);
+                }
+            }
+            // events of the neighbouring traces that share the first / last sector
+            if (e < o0) pend &= ~((1u << (int)(o0 - e)) - 1u);
+            if (o1 - e < 32) pend &= (1u << (int)(o1 - e)) - 1u;
+            while (pend) {
+                const int j = __ffs(pend) - 1;
+                pend &= pend - 1;
+                const long long idx = e + j;
+                const long long src = idx - o0;
+                if (cnt < NE && src < 65536) {
+                    const uint32_t m = __ldg(P.lut + __ldg(P.act + idx));
+                    s_meta[cnt * 32 + lane] = m | ((uint32_t)src << 16);
+                }
+                ++cnt;
+            }
+        }
+        if (o1 - o0 > 65536) cnt = NE + 1;  // in-trace index does not fit the packed word: overflow path
+        const int my_cnt = cnt;
+        if (P.needs_ts && my_cnt > 0 && my_cnt <= NE) {
+            const long long* tsp = reinterpret_cast<const long long*>(P.ts_ms) + o0;
+            // first event of the filtered list (Utils.java:51-53)
+            const long long t0 = __ldg(tsp + (s_meta[lane] >> 16));
+#pragma unroll 4
+            for (int r = 0; r < my_cnt; ++r) {
+                const long long ts = __ldg(tsp + (s_meta[r * 32 + lane] >> 16));
+                // EventTs.transformSaseEvent: (int)((t - minTs) / 1000), truncating long division (EventTs.java:54)
+                s_ts[r * 32 + lane] = (int)((ts - t0) / 1000);
+            }
         }
         __syncwarp();
 
-        // ------------------------------------------------------------------ phase B: run-set engine, one lane per trace
+        // ------------------------------------------------------------------ phase B: one lane per trace
 #ifdef SIESTA_PHASE_TIMING
         long long tB = clock64();
 #endif
         int status = ST_NONE;
         unsigned n_emitted = 0;
-        mask_t best = 0;
         int nsel = 0;
-        mask_t sel_local[NE];
+        mask_t sel_local[(MODE == FAST_FK2) ? 1 : NE];
         if (ci >= 0 && my_cnt > 0) {
             if (my_cnt > NE) {
                 status = ST_OVF;
             } else {
                 TraceEvents ev{s_meta + lane, P.needs_ts ? s_ts + lane : nullptr, 32, my_cnt, evt_pos};
-                auto body = [&](auto& eng) {
-                    BestEmit<W> be;
-                    eng.run(be, prune, dedup);
-                    if (eng.ovf) status = ST_OVF;
-                    else if (eng.err) status = ST_ERR;
-                    else if (be.n > 0) {
+                if constexpr (MODE == FAST_FK2) {
+                    mask_t m = 0;
+                    if (fk2_eval<W>(nfa, ev, m)) {
                         status = ST_MATCH;
-                        n_emitted = be.n;
-                        best = be.best;
-                        sel_local[0] = best;
+                        sel_local[0] = m;
                         nsel = 1;
-                        if (return_all && be.n > 1) {
-                            GreedyEmit<W, NE> ge(ev, best, evt_pos);
-                            eng.run(ge, prune, false);
-                            if (ge.ovf || eng.ovf) status = ST_OVF;
-                            else {
-                                nsel = ge.nsel;
-                                for (int o = 1; o < nsel; ++o) sel_local[o] = ge.sel[o];
+                    }
+                } else if constexpr (MODE == FAST_NK) {
+                    mask_t* aux = reinterpret_cast<mask_t*>(wbase + L::aux_off(P.needs_ts != 0)) + lane;
+                    if (nk_eval<W>(nfa, ev, return_all, evt_pos, aux, 32, sel_local, nsel, n_emitted)) status = ST_MATCH;
+                } else {
+                    auto body = [&](auto& eng) {
+                        BestEmit<W> be;
+                        eng.run(be, prune, dedup);
+                        if (eng.ovf) status = ST_OVF;
+                        else if (eng.err) status = ST_ERR;
+                        else if (be.n > 0) {
+                            status = ST_MATCH;
+                            n_emitted = be.n;
+                            sel_local[0] = be.best;
+                            nsel = 1;
+                            if (return_all && be.n > 1) {
+                                GreedyEmit<W, NE> ge(ev, be.best, evt_pos);
+                                eng.run(ge, prune, false);
+                                if (ge.ovf || eng.ovf) status = ST_OVF;
+                                else {
+                                    nsel = ge.nsel;
+                                    for (int o = 1; o < nsel; ++o) sel_local[o] = ge.sel[o];
+                                }
                             }
                         }
+                    };
+                    if constexpr (SMEM_RUNS) {
+                        uint8_t* bytes = wbase + L::bytes_off + lane;
+                        RunStore<W, R, NF, 32> store{reinterpret_cast<mask_t*>(wbase + L::rmask_off) + lane,
+                                                     reinterpret_cast<uint32_t*>(wbase + L::rmeta_off) + lane,
+                                                     bytes,
+                                                     reinterpret_cast<unsigned long long*>(wbase + L::famvv_off) + lane,
+                                                     bytes + (size_t)R * 32, bytes + (size_t)(R + NF) * 32, bytes + (size_t)(R + 2 * NF) * 32};
+                        RunEngine<RunStore<W, R, NF, 32>> eng(nfa, ev, store);
+                        body(eng);
+                    } else {
+                        RunArrays<W, R, NF> arrays;
+                        RunEngine<RunStore<W, R, NF, 1>> eng(nfa, ev, arrays.store());
+                        body(eng);
                     }
-                };
-                if constexpr (SMEM_RUNS) {
-                    uint8_t* bytes = wbase + L::bytes_off + lane;
-                    RunStore<W, R, NF, 32> store{reinterpret_cast<mask_t*>(wbase + L::rmask_off) + lane,
-                                                 reinterpret_cast<uint32_t*>(wbase + L::rmeta_off) + lane,
-                                                 bytes,
-                                                 reinterpret_cast<unsigned long long*>(wbase + L::famvv_off) + lane,
-                                                 bytes + (size_t)R * 32, bytes + (size_t)(R + NF) * 32, bytes + (size_t)(R + 2 * NF) * 32};
-                    RunEngine<RunStore<W, R, NF, 32>> eng(nfa, ev, store);
-                    body(eng);
-                } else {
-                    RunArrays<W, R, NF> arrays;
-                    RunEngine<RunStore<W, R, NF, 1>> eng(nfa, ev, arrays.store());
-                    body(eng);
                 }
             }
         }
@@ -464,11 +512,12 @@ struct DevMatchesImpl {
     int device = 0;
 };
 
-template <int W, int R, int NF, bool SMEM_RUNS>
+template <int W, int R, int NF, bool SMEM_RUNS, int MODE>
 int launch_detect(const Ctx* ctx, cudaStream_t stream, DetectParams P, const DevNfa& nfa) {
     typedef WarpSmem<W, R, NF, SMEM_RUNS> L;
-    const size_t smem = L::total(P.needs_ts != 0) * (NT / 32);
-    auto kern = detect_kernel<W, R, NF, SMEM_RUNS>;
+    const bool needs_aux = MODE == FAST_NK && (P.flags & SIESTA_F_RETURN_ALL) != 0;
+    const size_t smem = L::total(P.needs_ts != 0, needs_aux) * (NT / 32);
+    auto kern = detect_kernel<W, R, NF, SMEM_RUNS, MODE>;
     SIESTA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -538,6 +587,13 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     P.n_work = n;
     P.lut = b_lut.as<uint16_t>();
     P.n_act = log->n_activities;
+    P.n_events = log->n_events;
+    P.small_alphabet = log->n_activities <= 64 ? 1 : 0;
+    P.relbits = 0;
+    if (P.small_alphabet)
+        for (size_t a = 0; a < lut.size() && a < 64; ++a)
+            if (lut[a]) P.relbits |= 1ull << a;
+    P.vec_ok = (reinterpret_cast<uintptr_t>(log->d_act) & 15u) == 0 ? 1 : 0;
     P.flags = flags;
     P.needs_ts = needs_ts;
     P.d_nocc = b_nocc.as<uint32_t>();
@@ -557,7 +613,10 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
 
     unsigned long long h_cnt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (n > 0) {
-        if ((rc = launch_detect<1, 16, 16, true>(ctx, stream, P, dn))) return rc;
+        if (dn.fast_class == FAST_FK2) rc = launch_detect<1, 0, 0, false, FAST_FK2>(ctx, stream, P, dn);
+        else if (dn.fast_class == FAST_NK) rc = launch_detect<1, 0, 0, false, FAST_NK>(ctx, stream, P, dn);
+        else rc = launch_detect<1, 16, 16, true, FAST_NONE>(ctx, stream, P, dn);
+        if (rc) return rc;
         SIESTA_CUDA_OK(cudaEventRecord(evd, stream));
         SIESTA_CUDA_OK(cudaMemcpyAsync(h_cnt, b_counters.p, 128, cudaMemcpyDeviceToHost, stream));
         SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
@@ -570,7 +629,10 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
             Q.work = b_ovf.as<int64_t>();
             Q.n_work = n_ovf;
             Q.ovf_list = b_ovf2.as<int64_t>();
-            if ((rc = launch_detect<2, 1024, 128, false>(ctx, stream, Q, dn))) return rc;
+            if (dn.fast_class == FAST_FK2) rc = launch_detect<2, 0, 0, false, FAST_FK2>(ctx, stream, Q, dn);
+            else if (dn.fast_class == FAST_NK) rc = launch_detect<2, 0, 0, false, FAST_NK>(ctx, stream, Q, dn);
+            else rc = launch_detect<2, 1024, 128, false, FAST_NONE>(ctx, stream, Q, dn);
+            if (rc) return rc;
             SIESTA_CUDA_OK(cudaMemcpyAsync(h_cnt, b_counters.p, 128, cudaMemcpyDeviceToHost, stream));
             SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
             if (h_cnt[4] > 0) {

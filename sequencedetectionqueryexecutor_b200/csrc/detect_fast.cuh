@@ -1,0 +1,256 @@
+// detect_fast.cuh — closed-form evaluators of kernel K1 for two NFA classes (device + host harness).
+//
+// The general RunEngine (detect_engine.cuh) replays the reference's run list event by event.  For two classes of
+// NFAs the selected occurrences have a closed form that needs no run list at all; both forms are derived from the
+// same reference code the engine restates (S/engine/Engine.java:654-725, 933-982, 1102-1224; S/engine/Run.java:
+// 196-327; J/model/Occurrences.java:58-89) and are checked bit for bit against the oracle by
+// tests/test_fast_paths_host_vs_oracle.py and tests/soak_fast.py.  validate_nfa (nfa.cpp) decides the class; every
+// NFA outside the two classes runs on the general engine.
+//
+// Class NK  — only normal / or / negative states (no Kleene state), first and last state positive, no two
+//             negative states in a row, every predicate references an earlier positive state.
+//   Without Kleene states a run never forks: each event of state 0's types starts one run, and a run takes, for each
+//   state in turn, the FIRST later event of that state's types that passes the state's predicates (events that fail
+//   are skipped, Engine.java:1102-1163).  At a negative state the first later event that is either of the negative
+//   type (and passes its predicates: the run is deleted, Engine.java:679-682) or of the next state's types (and
+//   passes the next state's predicates, Engine.java:1165-1180: the run moves on) decides.  Runs never change their
+//   list position, so matches are emitted in ascending (completion event, start event) order; they all have the same
+//   number of events, hence "first largest" (Occurrences.java:60-69) = the smallest (completion, start).
+//
+// Class FK2 — two states `a+ b*` (kleeneClosure, kleeneClosure*), one type each, a != b, predicates only on state 1
+//             and only referencing state 0, first-largest occurrence only (returnAll = false).
+//   Let A[0..M] be the a-events.  The run list only ever holds (Engine.createNewRun :933-982 creates two runs per
+//   a-event, each with its own value vector):
+//     P(i)   = [a_i] proceeded at once to state 1; its value vector keeps a_i for ever, so it takes every later b with
+//              pass(b, a_i);
+//     Z(i)   = [a_i ..] staying in state 0; it takes EVERY later a (state 0 has no predicates) and forks each time:
+//              the proceeding branch Q(i,m) = [a_i..a_m] keeps the list slot, the staying clone goes to the tail
+//              (Engine.java:704-708);
+//     Q(i,m) shares Z(i)'s value vector (Run.clone is shallow, Run.java:319-327), whose state-0 slot is the LATEST a
+//              of the stream, so every Q takes exactly the b's with pass(b, last a before b) ("good" b's).
+//   A state-1 run that takes b emits [run + b] and is replaced by a clone at the TAIL of the list (Engine.java:
+//   704-713).  Q(i,m), i > 0, is always smaller than Q(0,m), so the first-largest occurrence is among P(i) and Q(0,m),
+//   each reaching its final size at the last b it takes.  Ties (same size at the same event) go to the run that sits
+//   earlier in the list.  List order = order of last placement at the tail; two runs placed at the same b keep their
+//   previous order.  Hence: with pl(X) = the set of events at which X was placed (its creation slot + every b it
+//   took), X precedes Y at event k iff the highest event below k in pl(X) xor pl(Y) belongs to pl(Y).  Q(0,m) is
+//   created in Z(0)'s slot, which was placed at a_{m-1}; at a_q, q >= 1, Z(0) is re-appended before P(q) is created,
+//   at a_0 P(0) is appended first.
+#pragma once
+#include "detect_engine.cuh"
+
+namespace siesta {
+
+enum { FAST_NONE = 0, FAST_NK = 1, FAST_FK2 = 2 };
+
+template <int W>
+struct MaskX : MaskOps<W> {
+    typedef typename MaskOps<W>::T T;
+    static SIESTA_HD __forceinline__ T below(int j) { return MaskOps<W>::bit(j) - 1; }                  // bits < j
+    static SIESTA_HD __forceinline__ T above(int j) { return ~(below(j) | MaskOps<W>::bit(j)); }        // bits > j
+};
+
+// "attr(e) op attr(ref) + c" for every predicate of state s; vv(ref) gives the event stored for state `ref`.
+// A predicate that references state `cur` itself is true (PredicateOptimized.java:331-340).
+template <class VV>
+SIESTA_HD __forceinline__ bool fast_preds(const DevNfa& nfa, const TraceEvents& ev, int s, int e, int cur, const VV& vv) {
+    const int np = nfa.n_preds[s];
+    for (int k = 0; k < np; ++k) {
+        const int ref = nfa.p_ref[s][k];
+        if (ref == cur) continue;
+        const int rj = vv(ref);
+        const int a = nfa.p_attr[s][k];
+        const long long lhs = ev.attr(e, a);
+        const long long rhs = (long long)ev.attr(rj, a) + nfa.p_c[s][k];
+        if (nfa.p_op[s][k] == SIESTA_OP_LE ? !(lhs <= rhs) : !(lhs >= rhs)) return false;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ class FK2
+template <int W>
+SIESTA_HD bool fk2_eval(const DevNfa& nfa, const TraceEvents& ev, typename MaskOps<W>::T& out) {
+    typedef MaskX<W> MO;
+    typedef typename MO::T mask_t;
+    mask_t am = 0, bm = 0;
+    for (int j = 0; j < ev.n; ++j) {
+        const uint32_t w = ev.word(j);
+        am |= (mask_t)(w & 1u) << j;
+        bm |= (mask_t)((w >> 1) & 1u) << j;
+    }
+    if (!am) return false;
+    const int a_first = MO::lo(am);
+    bm &= MO::above(a_first);  // b's before the first a meet no run
+    if (!bm) return false;
+    auto pass = [&](int b, int a) { return fast_preds(nfa, ev, 1, b, 1, [a](int) { return a; }); };
+
+    // good b's: pass against the latest a before them
+    mask_t good = 0;
+    for (mask_t m = bm; m; m &= m - 1) {
+        const int j = MO::lo(m);
+        if (pass(j, MO::hi(am & MO::below(j)))) good |= MO::bit(j);
+    }
+
+    int best_size = 0, best_k = 0;
+    mask_t best_pl = 0, best_out = 0;
+    bool best_is_p = false;
+    auto consider = [&](int size, int k, mask_t pl, mask_t o, bool is_p) {
+        bool better = size > best_size || (size == best_size && k < best_k);
+        if (!better && size == best_size && k == best_k) {
+            const mask_t x = (pl ^ best_pl) & MO::below(k);
+            if (x) better = (best_pl >> MO::hi(x)) & 1;
+            else if (is_p != best_is_p) {
+                // P(q) and Q(0,q+1) were both placed at a_q and moved together ever since
+                const bool q0 = (pl >> a_first) & 1;
+                better = is_p == q0;
+            }
+        }
+        if (better) { best_size = size; best_k = k; best_pl = pl; best_out = o; best_is_p = is_p; }
+    };
+
+    // Q(0,m), m >= 1
+    if (good) {
+        const int kq = MO::hi(good);
+        int m = 0, prev = a_first;
+        for (mask_t r = am & MO::above(a_first); r; r &= r - 1) {
+            const int j = MO::lo(r);
+            ++m;
+            const mask_t g = good & MO::above(j);
+            if (!g) break;  // later a's have no good b either
+            consider(m + 1 + MO::popc(g), kq, MO::bit(prev) | g, (am & MO::below(j)) | MO::bit(j) | g, false);
+            prev = j;
+        }
+    }
+    // P(i)
+    for (mask_t r = am; r; r &= r - 1) {
+        const int j = MO::lo(r);
+        const mask_t cand = bm & MO::above(j);
+        if (1 + MO::popc(cand) < best_size) continue;
+        mask_t pm = 0;
+        for (mask_t c = cand; c; c &= c - 1) {
+            const int b = MO::lo(c);
+            if (pass(b, j)) pm |= MO::bit(b);
+        }
+        if (!pm) continue;
+        consider(1 + MO::popc(pm), MO::hi(pm), MO::bit(j) | pm, MO::bit(j) | pm, true);
+    }
+    if (best_size == 0) return false;
+    out = best_out;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------- class NK
+// Greedy walk of the run started at event s.  Returns the run's events as a mask (0 = the run never completes or
+// is deleted at a negative state).
+template <int W>
+SIESTA_HD typename MaskOps<W>::T nk_walk(const DevNfa& nfa, const TraceEvents& ev, const typename MaskOps<W>::T* T, int s) {
+    typedef MaskX<W> MO;
+    typedef typename MO::T mask_t;
+    const int S = nfa.n_states;
+    unsigned long long vvw = (unsigned long long)s;  // byte k = event taken for state k
+    auto vv = [&vvw](int ref) { return (int)((vvw >> (8 * ref)) & 0xFF); };
+    mask_t taken = MO::bit(s);
+    int p = s;
+    int k_next = 1;
+    // fully unrolled over the state index so that T[k] stays in registers
+#pragma unroll
+    for (int k = 1; k < SIESTA_MAX_STATES; ++k) {
+        if (k >= S) break;
+        if (k != k_next) continue;
+        const bool neg = nfa.kind[k] == SIESTA_STATE_NEGATIVE;
+        mask_t c = (neg ? (T[k] | T[k + 1]) : T[k]) & MO::above(p);
+        int got = -1;
+        while (c) {
+            const int e = MO::lo(c);
+            c &= c - 1;
+            if (neg) {
+                if ((T[k] >> e) & 1) {
+                    if (fast_preds(nfa, ev, k, e, k, vv)) return 0;   // containsNegative: deleted (Engine.java:679-682)
+                } else if (fast_preds(nfa, ev, k + 1, e, k, vv)) {    // Engine.checkPredicatesForNextState :1165-1180
+                    got = e;
+                    break;
+                }
+            } else if (fast_preds(nfa, ev, k, e, k, vv)) {
+                got = e;
+                break;
+            }
+        }
+        if (got < 0) return 0;
+        const int ks = neg ? k + 1 : k;  // the state the event was taken for
+        taken |= MO::bit(got);
+        vvw |= (unsigned long long)got << (8 * ks);
+        p = got;
+        k_next = ks + 1;
+    }
+    return taken;
+}
+
+// aux: scratch of NE masks (one per possible start), element i at aux[i * aux_stride]; only used when return_all.
+// sel[0..nsel) = the selected occurrences (Occurrences.clearOccurrences); n_emitted = engine matches.
+template <int W>
+SIESTA_HD bool nk_eval(const DevNfa& nfa, const TraceEvents& ev, bool return_all, bool by_pos, typename MaskOps<W>::T* aux,
+                       int aux_stride, typename MaskOps<W>::T* sel, int& nsel, unsigned& n_emitted) {
+    typedef MaskX<W> MO;
+    typedef typename MO::T mask_t;
+    const int S = nfa.n_states;
+    mask_t T[SIESTA_MAX_STATES + 1];
+#pragma unroll
+    for (int k = 0; k <= SIESTA_MAX_STATES; ++k) T[k] = 0;
+    for (int j = 0; j < ev.n; ++j) {
+        const uint32_t w = ev.word(j);
+#pragma unroll
+        for (int k = 0; k < SIESTA_MAX_STATES; ++k) T[k] |= (mask_t)((w >> k) & 1u) << j;
+    }
+    nsel = 0;
+    n_emitted = 0;
+    // every state's types must occur at all (cheap reject of most traces)
+    for (int k = 0; k < S; ++k)
+        if (nfa.kind[k] != SIESTA_STATE_NEGATIVE && T[k] == 0) return false;
+
+    mask_t best = 0, done = 0;  // done: starts whose run completed
+    int best_c = 0;
+    for (mask_t r = T[0]; r; r &= r - 1) {
+        const int s = MO::lo(r);
+        const mask_t m = nk_walk<W>(nfa, ev, T, s);
+        if (!m) continue;
+        ++n_emitted;
+        const int c = MO::hi(m);
+        if (!best || c < best_c) { best = m; best_c = c; }  // starts ascend: an equal completion keeps the earlier start
+        if (return_all) {
+            aux[s * aux_stride] = m;
+            done |= MO::bit(s);
+        }
+    }
+    if (!best) return false;
+    sel[0] = best;
+    nsel = 1;
+    if (return_all && n_emitted > 1) {
+        // Occurrences.java:74-87: matches 1..n-1 in emission order (completion, start), kept if they overlap nothing chosen.
+        // M[0] (= best here) is skipped.
+        done &= ~MO::bit(MO::lo(best));
+        auto overlaps = [&](mask_t a, mask_t b) {
+            const int af = MO::lo(a), al = MO::hi(a), bf = MO::lo(b), bl = MO::hi(b);
+            bool not_ov;
+            if (by_pos) not_ov = ev.position(al) < ev.position(bf) || ev.position(af) > ev.position(bl);
+            else not_ov = ev.timestamp(al) < ev.timestamp(bf) || ev.timestamp(af) > ev.timestamp(bl);
+            return !not_ov;
+        };
+        while (done) {
+            int ps = -1, pc = 0;
+            mask_t pm = 0;
+            for (mask_t r = done; r; r &= r - 1) {
+                const int s = MO::lo(r);
+                const mask_t m = aux[s * aux_stride];
+                const int c = MO::hi(m);
+                if (ps < 0 || c < pc) { ps = s; pc = c; pm = m; }
+            }
+            done &= ~MO::bit(ps);
+            bool ov = false;
+            for (int o = 0; o < nsel && !ov; ++o) ov = overlaps(pm, sel[o]);
+            if (!ov) sel[nsel++] = pm;
+        }
+    }
+    return true;
+}
+
+}  // namespace siesta

@@ -7,6 +7,34 @@
 
 namespace siesta {
 
+// Which closed-form evaluator (detect_fast.cuh) may replace the run-list engine for this NFA and these flags?
+// 0 = none, 1 = NK (no Kleene state), 2 = FK2 (`a+ b*`).  The conditions are exactly the ones the derivations in
+// detect_fast.cuh rely on; anything else keeps the general engine.
+static int classify_fast(const siesta_nfa* nfa, const DevNfa& d, uint32_t flags) {
+    if (flags & SIESTA_F_LITERAL_RUNS) return 0;
+    const int S = nfa->n_states;
+    auto positive = [&](int s) { return nfa->states[s].kind == SIESTA_STATE_NORMAL || nfa->states[s].kind == SIESTA_STATE_OR; };
+    if (!d.any_kleene) {
+        if (!positive(0) || !positive(S - 1) || d.n_preds[0] != 0) return 0;
+        for (int s = 0; s < S; ++s) {
+            if (s > 0 && !positive(s) && !positive(s - 1)) return 0;  // two negative states in a row
+            for (int k = 0; k < d.n_preds[s]; ++k) {
+                const int ref = d.p_ref[s][k];
+                if (ref >= s || !positive(ref)) return 0;
+            }
+        }
+        return 1;
+    }
+    if (S == 2 && nfa->states[0].kind == SIESTA_STATE_KLEENE_PLUS && nfa->states[1].kind == SIESTA_STATE_KLEENE_STAR &&
+        nfa->states[0].n_types == 1 && nfa->states[1].n_types == 1 && nfa->states[0].types[0] != nfa->states[1].types[0] &&
+        d.n_preds[0] == 0 && !(flags & (SIESTA_F_RETURN_ALL | SIESTA_F_COUNT_MATCHES | SIESTA_F_MODE_HEAD))) {
+        for (int k = 0; k < d.n_preds[1]; ++k)
+            if (d.p_ref[1][k] != 0) return 0;
+        return 2;
+    }
+    return 0;
+}
+
 int validate_nfa(const siesta_nfa* nfa, uint32_t flags, DevNfa* out) {
     if (!nfa || nfa->n_states < 1 || nfa->n_states > SIESTA_MAX_STATES) {
         set_error("NFA must have 1.." + std::to_string(SIESTA_MAX_STATES) + " states");
@@ -105,6 +133,7 @@ int validate_nfa(const siesta_nfa* nfa, uint32_t flags, DevNfa* out) {
             return SIESTA_E_UNSUPPORTED;
         }
     }
+    d.fast_class = (uint8_t)classify_fast(nfa, d, flags);
     *out = d;
     return SIESTA_OK;
 }

@@ -5,7 +5,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../../sequencedetectionqueryexecutor_b200/csrc/detect_engine.cuh"
+#include "../../sequencedetectionqueryexecutor_b200/csrc/detect_fast.cuh"
 
 namespace siesta {
 static thread_local std::string t_err;
@@ -35,6 +35,21 @@ static int run_one(const DevNfa& dn, const std::vector<uint32_t>& meta, const st
     const bool evt_pos = (flags & SIESTA_F_EVT_POS) != 0;
     if ((int)meta.size() > NE) return 3;
     TraceEvents ev{meta.data(), needs_ts ? ts.data() : nullptr, 1, (int)meta.size(), evt_pos};
+    // same dispatch as kernel K1: closed-form evaluators for the NK / FK2 classes (detect_fast.cuh)
+    if (dn.fast_class == FAST_FK2) {
+        typename MaskOps<W>::T m = 0;
+        *n_emitted = 0;
+        if (!fk2_eval<W>(dn, ev, m)) return 0;
+        sel.assign(1, m);
+        return 1;
+    }
+    if (dn.fast_class == FAST_NK) {
+        std::vector<typename MaskOps<W>::T> aux(NE), s(NE);
+        int nsel = 0;
+        if (!nk_eval<W>(dn, ev, (flags & SIESTA_F_RETURN_ALL) != 0, evt_pos, aux.data(), 1, s.data(), nsel, *n_emitted)) return 0;
+        sel.assign(s.begin(), s.begin() + nsel);
+        return 1;
+    }
     auto* arrays = new RunArrays<W, R, NF>();
     auto* eng = new RunEngine<RunStore<W, R, NF, 1>>(dn, ev, arrays->store());
     const bool prune = (flags & SIESTA_F_LITERAL_RUNS) == 0;

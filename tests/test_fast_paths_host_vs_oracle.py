@@ -1,0 +1,59 @@
+"""The closed-form evaluators of kernel K1 (detect_fast.cuh: class NK = no Kleene state, class FK2 = `a+ b*`),
+compiled for the host, must agree with the oracle bit for bit.  tests/soak_fast.py is the long-running version."""
+import numpy as np
+import pytest
+
+import oracle
+from sequencedetectionqueryexecutor_b200 import _abi as abi
+from tests import gen, host_engine, soak_fast
+
+N_, P_, S_, X_, O_ = abi.STATE_NORMAL, abi.STATE_KLEENE_PLUS, abi.STATE_KLEENE_STAR, abi.STATE_NEGATIVE, abi.STATE_OR
+
+
+@pytest.mark.parametrize("seed0", [0, 500, 1000, 1500])
+def test_random_nfas_of_the_fast_classes(seed0):
+    assert soak_fast.main(seed0, 120) == 0
+
+
+def _first_largest(matches):
+    return max(matches, key=len) if matches else None  # max() returns the first maximal element
+
+
+def test_fk2_ties_follow_the_run_list_order():
+    """Streams built to tie: Q(0,m) vs Q(0,m'), P(i) vs Q(0,m).  Checked against the oracle's full emission list."""
+    nfa = abi.make_nfa([dict(kind=P_, types=[0]), dict(kind=S_, types=[1], preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 3)])])
+    rng = np.random.default_rng(7)
+    for _ in range(400):
+        n = int(rng.integers(2, 12))
+        types = rng.integers(0, 2, size=n).astype(np.int32)
+        ts_s = np.cumsum(rng.integers(0, 3, size=n))
+        _, matches = oracle.run_stream(nfa, types, np.arange(n), ts_s)
+        want = _first_largest(matches)
+        off = np.array([0, n], dtype=np.int64)
+        rc, got, _ = host_engine.detect(off, types, ts_s.astype(np.int64) * 1000, 2, nfa)
+        assert rc == 0
+        if want is None:
+            assert got.n_traces == 0
+        else:
+            assert got.as_dict() == {0: [want]}
+
+
+def test_class_boundaries_fall_back_to_the_engine():
+    """NFAs just outside the two classes (same type twice, predicate on state 0, trailing negative ...) still agree
+    with the oracle: they must be routed to the general engine."""
+    off, act, ts = gen.make_log(200, 5, 40, 4, seed=11, max_gap_s=200)
+    cases = [
+        [dict(kind=P_, types=[0]), dict(kind=S_, types=[0])],                                      # a+ a*
+        [dict(kind=P_, types=[0]), dict(kind=S_, types=[1]), dict(kind=N_, types=[2])],            # three states
+        [dict(kind=X_, types=[0]), dict(kind=N_, types=[1])],                                      # leading negative
+        [dict(kind=N_, types=[0]), dict(kind=X_, types=[1]), dict(kind=X_, types=[2]), dict(kind=N_, types=[3])],
+        [dict(kind=N_, types=[0]), dict(kind=N_, types=[1], preds=[(abi.ATTR_POSITION, abi.OP_LE, 1, 2)])],  # self reference
+    ]
+    for states in cases:
+        for flags in (0, abi.F_RETURN_ALL, abi.F_EVT_POS):
+            nfa = abi.make_nfa(states)
+            rc, got, _ = host_engine.detect(off, act, ts, 4, nfa, flags=flags)
+            assert rc == 0
+            want = oracle.detect(off, act, ts, nfa, flags=flags)
+            ok, why = got.same_as(want)
+            assert ok, (why, states, flags)
