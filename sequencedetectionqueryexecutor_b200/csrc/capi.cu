@@ -61,6 +61,37 @@ extern "C" void siesta_shutdown(siesta_ctx* ctx) {
     delete c;
 }
 
+// One pass over the activity column when a log becomes resident: are all ids inside [0, n_activities)?
+// (kernel K1's filter then tests ids with two shift instructions per event instead of a checked table lookup)
+__global__ void act_range_kernel(const int32_t* act, int64_t n, int32_t n_act, int* bad) {
+    int any = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        any |= (unsigned)act[i] >= (unsigned)n_act;
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(bad, 1);
+}
+
+static int validate_act(Log* L) {
+    L->act_valid = false;
+    if (L->n_events == 0) {
+        L->act_valid = true;
+        return SIESTA_OK;
+    }
+    Ctx* c = L->ctx;
+    int* d_bad = nullptr;
+    SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_bad, sizeof(int), c->stream));
+    SIESTA_CUDA_OK(cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream));
+    const int64_t want = (L->n_events + 255) / 256;
+    const int grid = (int)(want < (int64_t)c->sm_count * 16 ? want : (int64_t)c->sm_count * 16);
+    act_range_kernel<<<grid, 256, 0, c->stream>>>(L->d_act, L->n_events, L->n_activities, d_bad);
+    SIESTA_LAUNCHED();
+    int bad = 1;
+    SIESTA_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SIESTA_CUDA_OK(cudaStreamSynchronize(c->stream));
+    cudaFreeAsync(d_bad, c->stream);
+    L->act_valid = bad == 0;
+    return SIESTA_OK;
+}
+
 static int check_csr(const int64_t* trace_off, int64_t n_traces, int64_t n_events, int32_t* max_len) {
     if (n_traces < 0 || n_events < 0 || trace_off[0] != 0 || trace_off[n_traces] != n_events) {
         set_error("CSR log: trace_off must start at 0 and end at n_events");
@@ -118,6 +149,10 @@ extern "C" int siesta_log_load(siesta_ctx* ctx, const int64_t* trace_off, const 
         SIESTA_CUDA_OK(cudaMemcpyAsync(d_ts, ts_ms, (size_t)n_events * 8, cudaMemcpyHostToDevice, c->stream));
     }
     SIESTA_CUDA_OK(cudaStreamSynchronize(c->stream));
+    if ((rc = validate_act(L))) {
+        siesta_log_free(reinterpret_cast<siesta_log*>(L));
+        return rc;
+    }
     *out = reinterpret_cast<siesta_log*>(L);
     return SIESTA_OK;
 }
@@ -139,6 +174,12 @@ extern "C" int siesta_log_wrap_device(siesta_ctx* ctx, const int64_t* d_trace_of
     L->n_activities = n_activities;
     L->max_trace_len = max_trace_len;
     L->owns = false;
+    SIESTA_CUDA_OK(cudaSetDevice(L->ctx->device));
+    int rc = validate_act(L);
+    if (rc) {
+        delete L;
+        return rc;
+    }
     *out = reinterpret_cast<siesta_log*>(L);
     return SIESTA_OK;
 }

@@ -41,6 +41,7 @@ struct Log {
     int32_t n_activities = 0;
     int32_t max_trace_len = 0;
     bool owns = false;
+    bool act_valid = false;  // every activity id lies in [0, n_activities): kernels may skip the per-event range check
 };
 
 // Device-side NFA: SIESTA's State[] flattened (S/query/State.java, AdditionalState.java).

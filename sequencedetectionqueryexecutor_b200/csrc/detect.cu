@@ -33,9 +33,10 @@ struct DetectParams {
     const int64_t* work;      // indices into the candidate list to process, or nullptr (= all)
     int64_t n_work;           // number of traces this launch verifies
     const uint16_t* lut;      // [n_act] smask | fmask << 8
-    unsigned long long relbits;  // small_alphabet: bit a = activity a belongs to the pattern
+    uint32_t relrev_a, relrev_b;  // alpha_mode 0/1: bit-reversed activity set of the pattern (ids 0..31, 32..63)
+    uint16_t lutc[64];        // alpha_mode 0/1: the lut in kernel-parameter space
     int64_t n_events;         // events of the whole log (bound of the vector loads)
-    int32_t small_alphabet;   // n_act <= 64
+    int32_t alpha_mode;       // 0: n_act <= 32, 1: n_act <= 64 (both: ids validated at log load), 2: general (lut in HBM)
     int32_t vec_ok;           // act is 16-byte aligned: 128-bit loads
     int32_t n_act;
     uint32_t flags;
@@ -68,6 +69,54 @@ __device__ __forceinline__ long long shfl_i64(long long v, int src) {
 // status codes of a trace inside the kernel
 enum { ST_NONE = 0, ST_MATCH = 1, ST_ERR = 2, ST_OVF = 3 };
 
+// 32 activity ids (four 32-byte sectors, two 128-bit loads each) starting at element e of this lane's trace [o0, o1).
+// Sectors past the trace are not touched; the scalar path serves unaligned logs and the last sector of the log.
+__device__ __forceinline__ void load_sectors(const DetectParams& P, long long e, long long o0, long long o1, int4 (&v)[8]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const long long c = e + 8 * q;
+        if (c < o1 && P.vec_ok && c + 8 <= P.n_events) {
+            v[2 * q] = __ldg(reinterpret_cast<const int4*>(P.act + c));
+            v[2 * q + 1] = __ldg(reinterpret_cast<const int4*>(P.act + c + 4));
+        } else {
+            int a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = (c + i < o1 && c + i >= o0) ? __ldg(P.act + c + i) : -1;
+            v[2 * q] = make_int4(a[0], a[1], a[2], a[3]);
+            v[2 * q + 1] = make_int4(a[4], a[5], a[6], a[7]);
+        }
+    }
+}
+
+// Relevance test of the filter: relrev holds the pattern's activity set bit-reversed (bit 31 - a <=> activity a), so
+// `relrev << a` moves activity a's bit to the top and one funnel shift pushes it into the survivor mask: two
+// instructions per event.  shl.b32 clamps shift amounts above 31, so a masked-out slot (a = -1) pushes 0.
+__device__ __forceinline__ uint32_t rel_push32(uint32_t pend, uint32_t relrev, int a) {
+    uint32_t t;
+    asm("shl.b32 %0, %1, %2;" : "=r"(t) : "r"(relrev), "r"(a));
+    return __funnelshift_r(t, pend, 31);
+}
+// activities 0..31 in relrev_a, 32..63 in relrev_b
+__device__ __forceinline__ uint32_t rel_push64(uint32_t pend, uint32_t relrev_a, uint32_t relrev_b, int a) {
+    uint32_t t;
+    const uint32_t w = ((unsigned)a < 32u) ? relrev_a : (((unsigned)a < 64u) ? relrev_b : 0u);
+    asm("shl.b32 %0, %1, %2;" : "=r"(t) : "r"(w), "r"(a & 31));
+    return __funnelshift_r(t, pend, 31);
+}
+
+// EventTs.transformSaseEvent: (int)((t - minTs) / 1000), truncating long division (J/model/Events/EventTs.java:54).
+// Differences below 2^32 ms (49 days) take a 32-bit multiply-high instead of the emulated 64-bit division.
+__device__ __forceinline__ int rel_seconds(long long diff_ms) {
+    if ((unsigned long long)diff_ms < (1ull << 32)) return (int)((uint32_t)diff_ms / 1000u);
+    return (int)(diff_ms / 1000);
+}
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // Shared memory of one warp (all arrays lane-transposed: element i of lane l at [i * 32 + l]).
 template <int W, int R, int NF, bool SMEM_RUNS>
 struct WarpSmem {
@@ -82,13 +131,12 @@ struct WarpSmem {
     static constexpr size_t rmeta_bytes = SMEM_RUNS ? sizeof(uint32_t) * R * 32 : 0;
     static constexpr size_t bytes_off = rmeta_off + rmeta_bytes;                 // rfam, fmin, fmin2, fcnt
     static constexpr size_t bytes_bytes = SMEM_RUNS ? (size_t)(R + 3 * NF) * 32 : 0;
-    static constexpr size_t ts_off = (bytes_off + bytes_bytes + 15) & ~(size_t)15;  // only when the query needs seconds
-    static constexpr size_t ts_bytes = sizeof(int32_t) * NE * 32;
+    // one 8-byte slot per event: first the raw int64 timestamp (cp.async target), then {relative seconds, activity id}
+    static constexpr size_t slot_off = (bytes_off + bytes_bytes + 15) & ~(size_t)15;
+    static constexpr size_t slot_bytes = sizeof(unsigned long long) * NE * 32;
+    static constexpr size_t aux_off = slot_off + slot_bytes;
     static constexpr size_t aux_bytes = sizeof(typename MaskOps<W>::T) * NE * 32;   // NK + returnAll: one mask per start
-    static __host__ __device__ constexpr size_t aux_off(bool needs_ts) { return ts_off + (needs_ts ? ts_bytes : 0); }
-    static __host__ __device__ constexpr size_t total(bool needs_ts, bool needs_aux) {
-        return aux_off(needs_ts) + (needs_aux ? aux_bytes : 0);
-    }
+    static __host__ __device__ constexpr size_t total(bool needs_aux) { return aux_off + (needs_aux ? aux_bytes : 0); }
 };
 
 // One warp owns a tile of 32 traces from start to finish: no block-level barrier anywhere.
@@ -105,9 +153,10 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
     const bool evt_pos = (P.flags & SIESTA_F_EVT_POS) != 0;
     const bool return_all = (P.flags & SIESTA_F_RETURN_ALL) != 0;
     const bool needs_aux = MODE == FAST_NK && return_all;
-    unsigned char* wbase = smem_raw + (size_t)warp * L::total(P.needs_ts != 0, needs_aux);
-    uint32_t* s_meta = reinterpret_cast<uint32_t*>(wbase + L::meta_off);  // [NE][32]
-    int32_t* s_ts = reinterpret_cast<int32_t*>(wbase + L::ts_off);        // [NE][32] when needs_ts
+    unsigned char* wbase = smem_raw + (size_t)warp * L::total(needs_aux);
+    uint32_t* s_meta = reinterpret_cast<uint32_t*>(wbase + L::meta_off);                      // [NE][32]
+    unsigned long long* s_slot = reinterpret_cast<unsigned long long*>(wbase + L::slot_off);  // [NE][32]
+    const int32_t* s_ts = reinterpret_cast<const int32_t*>(s_slot);                           // low words: relative seconds
 
     const bool all_cols = (P.flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
     const bool prune = (P.flags & SIESTA_F_LITERAL_RUNS) == 0;
@@ -133,32 +182,39 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
             o1 = P.trace_off[t + 1];
         }
         int cnt = 0;
+        const long long* tsp = reinterpret_cast<const long long*>(P.ts_ms) + o0;
+        int4 v[8];
+        load_sectors(P, o0 & ~7LL, o0, o1, v);
         for (long long e = o0 & ~7LL; e < o1; e += 32) {
-            int4 v[8];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const long long c = e + 8 * q;
-                if (c < o1 && P.vec_ok && c + 8 <= P.n_events) {
-                    v[2 * q] = __ldg(reinterpret_cast<const int4*>(P.act + c));
-                    v[2 * q + 1] = __ldg(reinterpret_cast<const int4*>(P.act + c + 4));
-                } else {
-                    int a[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) a[i] = (c + i < o1 && c + i >= o0) ? __ldg(P.act + c + i) : -1;
-                    v[2 * q] = make_int4(a[0], a[1], a[2], a[3]);
-                    v[2 * q + 1] = make_int4(a[4], a[5], a[6], a[7]);
-                }
-            }
+            int4 nv[8];
+            if (e + 32 < o1) load_sectors(P, e + 32, o0, o1, nv);  // the next 32 events are in flight while these are tested
+            // bit i of pend = event e + i belongs to the pattern (built last event first: shift left, insert at bit 0)
             uint32_t pend = 0;
+            if (P.alpha_mode == 0) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int a[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+                for (int q = 7; q >= 0; --q) {
+                    pend = rel_push32(pend, P.relrev_a, v[q].w);
+                    pend = rel_push32(pend, P.relrev_a, v[q].z);
+                    pend = rel_push32(pend, P.relrev_a, v[q].y);
+                    pend = rel_push32(pend, P.relrev_a, v[q].x);
+                }
+            } else if (P.alpha_mode == 1) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    bool rel;
-                    if (P.small_alphabet) rel = ((unsigned)a[i] < 64u) && ((P.relbits >> (a[i] & 63)) & 1ull);
-                    else rel = ((unsigned)a[i] < (unsigned)P.n_act) && __ldg(P.lut + a[i]) != 0;
-                    pend |= (rel ? 1u : 0u) << (4 * q + i);
+                for (int q = 7; q >= 0; --q) {
+                    pend = rel_push64(pend, P.relrev_a, P.relrev_b, v[q].w);
+                    pend = rel_push64(pend, P.relrev_a, P.relrev_b, v[q].z);
+                    pend = rel_push64(pend, P.relrev_a, P.relrev_b, v[q].y);
+                    pend = rel_push64(pend, P.relrev_a, P.relrev_b, v[q].x);
+                }
+            } else {
+#pragma unroll
+                for (int q = 7; q >= 0; --q) {
+                    const int a[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                    for (int i = 3; i >= 0; --i) {
+                        const bool rel = ((unsigned)a[i] < (unsigned)P.n_act) && __ldg(P.lut + a[i]) != 0;
+                        pend = (pend << 1) | (rel ? 1u : 0u);
+                    }
                 }
             }
             // events of the neighbouring traces that share the first / last sector
@@ -167,26 +223,34 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
             while (pend) {
                 const int j = __ffs(pend) - 1;
                 pend &= pend - 1;
-                const long long idx = e + j;
-                const long long src = idx - o0;
-                if (cnt < NE && src < 65536) {
-                    const uint32_t m = __ldg(P.lut + __ldg(P.act + idx));
-                    s_meta[cnt * 32 + lane] = m | ((uint32_t)src << 16);
+                if (cnt < NE) {
+                    const long long src = e + j - o0;
+                    s_meta[cnt * 32 + lane] = (uint32_t)src;
+                    // the raw timestamp of a surviving event goes straight to its shared-memory slot (no register, no stall)
+                    if (P.needs_ts) cp_async8(s_slot + cnt * 32 + lane, tsp + src);
                 }
                 ++cnt;
             }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = nv[q];
         }
         if (o1 - o0 > 65536) cnt = NE + 1;  // in-trace index does not fit the packed word: overflow path
         const int my_cnt = cnt;
-        if (P.needs_ts && my_cnt > 0 && my_cnt <= NE) {
-            const long long* tsp = reinterpret_cast<const long long*>(P.ts_ms) + o0;
-            // first event of the filtered list (Utils.java:51-53)
-            const long long t0 = __ldg(tsp + (s_meta[lane] >> 16));
+        cp_async_wait_all();
+        // second pass over the survivors only: activity -> state-mask word, timestamp -> relative seconds
+        long long t0ms = 0;  // first event of the filtered list (Utils.java:51-53)
+        if (my_cnt > 0 && my_cnt <= NE) {
+            if (P.needs_ts) t0ms = (long long)s_slot[lane];
+            else if (all_cols && !evt_pos) t0ms = __ldg(tsp + s_meta[lane]);
 #pragma unroll 4
             for (int r = 0; r < my_cnt; ++r) {
-                const long long ts = __ldg(tsp + (s_meta[r * 32 + lane] >> 16));
-                // EventTs.transformSaseEvent: (int)((t - minTs) / 1000), truncating long division (EventTs.java:54)
-                s_ts[r * 32 + lane] = (int)((ts - t0) / 1000);
+                const uint32_t src = s_meta[r * 32 + lane];
+                const int a = __ldg(P.act + o0 + src);
+                const uint32_t m = P.alpha_mode == 2 ? (uint32_t)__ldg(P.lut + a) : (uint32_t)P.lutc[a & 63];
+                s_meta[r * 32 + lane] = m | (src << 16);
+                int rel = 0;
+                if (P.needs_ts) rel = rel_seconds((long long)s_slot[r * 32 + lane] - t0ms);
+                s_slot[r * 32 + lane] = (unsigned long long)(uint32_t)rel | ((unsigned long long)(uint32_t)a << 32);
             }
         }
         __syncwarp();
@@ -203,7 +267,7 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
             if (my_cnt > NE) {
                 status = ST_OVF;
             } else {
-                TraceEvents ev{s_meta + lane, P.needs_ts ? s_ts + lane : nullptr, 32, my_cnt, evt_pos};
+                TraceEvents ev{s_meta + lane, P.needs_ts ? s_ts + 2 * lane : nullptr, 32, my_cnt, evt_pos, 64};
                 if constexpr (MODE == FAST_FK2) {
                     mask_t m = 0;
                     if (fk2_eval<W>(nfa, ev, m)) {
@@ -212,7 +276,7 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
                         nsel = 1;
                     }
                 } else if constexpr (MODE == FAST_NK) {
-                    mask_t* aux = reinterpret_cast<mask_t*>(wbase + L::aux_off(P.needs_ts != 0)) + lane;
+                    mask_t* aux = reinterpret_cast<mask_t*>(wbase + L::aux_off) + lane;
                     if (nk_eval<W>(nfa, ev, return_all, evt_pos, aux, 32, sel_local, nsel, n_emitted)) status = ST_MATCH;
                 } else {
                     auto body = [&](auto& eng) {
@@ -294,33 +358,86 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
                 P.d_nev[ci] = my_ev;
                 P.d_stage[ci] = ev_at;
                 P.d_stage_occ[ci] = occ_at;
-                if (stage_ok) {
-                    long long e = ev_at;
-                    const long long t0ms = (all_cols && !evt_pos) ? P.ts_ms[o0 + (s_meta[lane] >> 16)] : 0;
-                    for (int o = 0; o < nsel; ++o) {
-                        mask_t m = sel_local[o];
-                        P.s_occ_nev[occ_at + o] = MO::popc(m);
-                        while (m) {
-                            const int j = MO::lo(m);
-                            m &= m - 1;
-                            const int src = (int)(s_meta[j * 32 + lane] >> 16);
-                            P.s_ev_pos[e] = src;
-                            if (all_cols) {
-                                P.s_ev_rank[e] = j;
-                                P.s_ev_act[e] = P.act[o0 + src];
-                                const long long raw = P.ts_ms[o0 + src];
-                                // SaseEvent.getEventBoth: timestamp * 1000 + minTs (SaseEvent.java:94-106)
-                                P.s_ev_ts[e] = evt_pos ? raw : (long long)((int)((raw - t0ms) / 1000)) * 1000 + t0ms;
-                            }
-                            ++e;
-                        }
-                    }
-                }
             } else {
                 P.d_nocc[ci] = 0;
                 P.d_nev[ci] = 0;
                 if (status == ST_ERR) P.err_list[atomicAdd(P.counters + 3, 1ull)] = t;
                 else if (status == ST_OVF) P.ovf_list[atomicAdd(P.counters + 4, 1ull)] = ci;
+            }
+        }
+        if (stage_ok && tot1 > 0) {
+            if (!return_all) {
+                // One occurrence per trace: the warp writes the tile's events as one flat, coalesced stream.  Flat slot
+                // f belongs to the lane whose inclusive event count first exceeds f (binary search over shuffles); the
+                // k-th set bit of that lane's occurrence mask names the event; activity and timestamp are re-read
+                // from the log by 32 lanes at once (one memory latency per 32 events instead of one per event).
+                const mask_t my_mask = status == ST_MATCH ? sel_local[0] : (mask_t)0;
+                if (status == ST_MATCH) P.s_occ_nev[occ_at] = (int32_t)my_ev;
+                for (unsigned f0 = 0; f0 < tot1; f0 += 32) {
+                    const unsigned f = f0 + lane;
+                    int lo = 0, hi = 31;
+#pragma unroll
+                    for (int it = 0; it < 5; ++it) {
+                        const int mid = (lo + hi) >> 1;
+                        const unsigned vmid = __shfl_sync(0xffffffffu, i1, mid);
+                        if (vmid > f) hi = mid; else lo = mid + 1;
+                    }
+                    const int owner = lo & 31;
+                    const unsigned o_incl = __shfl_sync(0xffffffffu, i1, owner);
+                    const unsigned o_ev = __shfl_sync(0xffffffffu, my_ev, owner);
+                    mask_t m;
+                    if constexpr (W == 1) m = __shfl_sync(0xffffffffu, my_mask, owner);
+                    else m = (mask_t)shfl_i64((long long)my_mask, owner);
+                    const long long o_o0 = shfl_i64(o0, owner);
+                    const long long o_t0 = shfl_i64(t0ms, owner);
+                    if (f < tot1) {
+                        int k = (int)(f - (o_incl - o_ev));  // k-th event of the owner's occurrence
+                        for (; k > 0; --k) m &= m - 1;
+                        const int j = MO::lo(m);
+                        const int src = (int)(s_meta[j * 32 + owner] >> 16);
+                        const long long at = (long long)base1 + f;
+                        P.s_ev_pos[at] = src;
+                        if (all_cols) {
+                            const unsigned long long slot = s_slot[j * 32 + owner];  // {relative seconds, activity id}
+                            P.s_ev_rank[at] = j;
+                            P.s_ev_act[at] = (int32_t)(slot >> 32);
+                            // SaseEvent.getEventBoth: timestamp * 1000 + minTs (SaseEvent.java:94-106)
+                            long long out_ts;
+                            if (P.needs_ts) out_ts = (long long)(int32_t)(uint32_t)slot * 1000 + o_t0;
+                            else {
+                                const long long raw = __ldg(reinterpret_cast<const long long*>(P.ts_ms) + o_o0 + src);
+                                out_ts = evt_pos ? raw : (long long)rel_seconds(raw - o_t0) * 1000 + o_t0;
+                            }
+                            P.s_ev_ts[at] = out_ts;
+                        }
+                    }
+                }
+            } else if (status == ST_MATCH) {
+                long long e = ev_at;
+                for (int o = 0; o < nsel; ++o) {
+                    mask_t m = sel_local[o];
+                    P.s_occ_nev[occ_at + o] = MO::popc(m);
+                    while (m) {
+                        const int j = MO::lo(m);
+                        m &= m - 1;
+                        const int src = (int)(s_meta[j * 32 + lane] >> 16);
+                        P.s_ev_pos[e] = src;
+                        if (all_cols) {
+                            const unsigned long long slot = s_slot[j * 32 + lane];  // {relative seconds, activity id}
+                            P.s_ev_rank[e] = j;
+                            P.s_ev_act[e] = (int32_t)(slot >> 32);
+                            // SaseEvent.getEventBoth: timestamp * 1000 + minTs (SaseEvent.java:94-106)
+                            long long out_ts;
+                            if (P.needs_ts) out_ts = (long long)(int32_t)(uint32_t)slot * 1000 + t0ms;
+                            else {
+                                const long long raw = __ldg(reinterpret_cast<const long long*>(P.ts_ms) + o0 + src);
+                                out_ts = evt_pos ? raw : (long long)rel_seconds(raw - t0ms) * 1000 + t0ms;
+                            }
+                            P.s_ev_ts[e] = out_ts;
+                        }
+                        ++e;
+                    }
+                }
             }
         }
 #ifdef SIESTA_PHASE_TIMING
@@ -516,7 +633,7 @@ template <int W, int R, int NF, bool SMEM_RUNS, int MODE>
 int launch_detect(const Ctx* ctx, cudaStream_t stream, DetectParams P, const DevNfa& nfa) {
     typedef WarpSmem<W, R, NF, SMEM_RUNS> L;
     const bool needs_aux = MODE == FAST_NK && (P.flags & SIESTA_F_RETURN_ALL) != 0;
-    const size_t smem = L::total(P.needs_ts != 0, needs_aux) * (NT / 32);
+    const size_t smem = L::total(needs_aux) * (NT / 32);
     auto kern = detect_kernel<W, R, NF, SMEM_RUNS, MODE>;
     SIESTA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -588,11 +705,14 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     P.lut = b_lut.as<uint16_t>();
     P.n_act = log->n_activities;
     P.n_events = log->n_events;
-    P.small_alphabet = log->n_activities <= 64 ? 1 : 0;
-    P.relbits = 0;
-    if (P.small_alphabet)
-        for (size_t a = 0; a < lut.size() && a < 64; ++a)
-            if (lut[a]) P.relbits |= 1ull << a;
+    P.alpha_mode = !log->act_valid ? 2 : (log->n_activities <= 32 ? 0 : (log->n_activities <= 64 ? 1 : 2));
+    P.relrev_a = P.relrev_b = 0;
+    std::memset(P.lutc, 0, sizeof(P.lutc));
+    if (P.alpha_mode != 2)
+        for (size_t a = 0; a < lut.size() && a < 64; ++a) {
+            P.lutc[a] = lut[a];
+            if (lut[a]) (a < 32 ? P.relrev_a : P.relrev_b) |= 0x80000000u >> (a & 31);
+        }
     P.vec_ok = (reinterpret_cast<uintptr_t>(log->d_act) & 15u) == 0 ? 1 : 0;
     P.flags = flags;
     P.needs_ts = needs_ts;

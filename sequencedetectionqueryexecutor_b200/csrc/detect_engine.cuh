@@ -109,12 +109,13 @@ struct TraceEvents {
     int stride;
     int n;
     bool evt_pos;
+    int ts_stride;         // words between consecutive events in ts
     SIESTA_HD __forceinline__ uint32_t word(int j) const { return meta[j * stride]; }
     SIESTA_HD __forceinline__ int src(int j) const { return (int)(meta[j * stride] >> 16); }
     // SaseEvent attributes (J/SaseConnection/SaseEvent.java:80-89) after
     // Utils.transformToSaseEvents (J/model/Utils/Utils.java:48-65)
     SIESTA_HD __forceinline__ int position(int j) const { return evt_pos ? src(j) : j; }
-    SIESTA_HD __forceinline__ int timestamp(int j) const { return evt_pos ? j : (ts ? ts[j * stride] : 0); }
+    SIESTA_HD __forceinline__ int timestamp(int j) const { return evt_pos ? j : (ts ? ts[j * ts_stride] : 0); }
     SIESTA_HD __forceinline__ int attr(int j, int a) const { return a == SIESTA_ATTR_POSITION ? position(j) : timestamp(j); }
 };
 
@@ -550,7 +551,7 @@ struct RunEngine {
         opt_dedup = dedup;
         ts_monotone = true;
         if (prune && ev.ts && !ev.evt_pos)
-            for (int j = 1; j < ev.n; ++j) ts_monotone = ts_monotone && ev.ts[j * ev.stride] >= ev.ts[(j - 1) * ev.stride];
+            for (int j = 1; j < ev.n; ++j) ts_monotone = ts_monotone && ev.ts[j * ev.ts_stride] >= ev.ts[(j - 1) * ev.ts_stride];
         dirty = false;
         moved = 0;
         for (int j = 0; j < ev.n; ++j) {

@@ -72,24 +72,48 @@ template <int W>
 SIESTA_HD bool fk2_eval(const DevNfa& nfa, const TraceEvents& ev, typename MaskOps<W>::T& out) {
     typedef MaskX<W> MO;
     typedef typename MO::T mask_t;
-    mask_t am = 0, bm = 0;
+    // state 1's predicates, decoded once: where the attribute of event j lives (0 = j itself, 1 = in-trace position,
+    // 2 = relative seconds; SaseEvent attributes after Utils.transformToSaseEvents, see TraceEvents), operator, constant
+    const int np = nfa.n_preds[1];
+    int p_mode[SIESTA_MAX_PREDS];
+    bool p_le[SIESTA_MAX_PREDS];
+    long long p_c[SIESTA_MAX_PREDS];
+#pragma unroll
+    for (int k = 0; k < SIESTA_MAX_PREDS; ++k) {
+        const bool is_pos = nfa.p_attr[1][k] == SIESTA_ATTR_POSITION;
+        p_mode[k] = is_pos ? (ev.evt_pos ? 1 : 0) : (ev.evt_pos ? 0 : (ev.ts ? 2 : 3));
+        p_le[k] = nfa.p_op[1][k] == SIESTA_OP_LE;
+        p_c[k] = nfa.p_c[1][k];
+    }
+    auto val = [&](int mode, int j) -> int { return mode == 0 ? j : (mode == 1 ? ev.src(j) : (mode == 2 ? ev.ts[j * ev.ts_stride] : 0)); };
+    auto pass = [&](int b, int a) -> bool {
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < SIESTA_MAX_PREDS; ++k) {
+            if (k < np) {
+                const long long lhs = val(p_mode[k], b);
+                const long long rhs = (long long)val(p_mode[k], a) + p_c[k];
+                ok = ok && (p_le[k] ? lhs <= rhs : lhs >= rhs);
+            }
+        }
+        return ok;
+    };
+
+    // one pass over the events: a's, b's that follow an a, and the good b's (pass against the latest a before them)
+    mask_t am = 0, bm = 0, good = 0;
+    int la = -1;
     for (int j = 0; j < ev.n; ++j) {
         const uint32_t w = ev.word(j);
-        am |= (mask_t)(w & 1u) << j;
-        bm |= (mask_t)((w >> 1) & 1u) << j;
+        if (w & 1u) {
+            am |= MO::bit(j);
+            la = j;
+        } else if ((w & 2u) && la >= 0) {  // b's before the first a meet no run
+            bm |= MO::bit(j);
+            if (pass(j, la)) good |= MO::bit(j);
+        }
     }
-    if (!am) return false;
-    const int a_first = MO::lo(am);
-    bm &= MO::above(a_first);  // b's before the first a meet no run
     if (!bm) return false;
-    auto pass = [&](int b, int a) { return fast_preds(nfa, ev, 1, b, 1, [a](int) { return a; }); };
-
-    // good b's: pass against the latest a before them
-    mask_t good = 0;
-    for (mask_t m = bm; m; m &= m - 1) {
-        const int j = MO::lo(m);
-        if (pass(j, MO::hi(am & MO::below(j)))) good |= MO::bit(j);
-    }
+    const int a_first = MO::lo(am);
 
     int best_size = 0, best_k = 0;
     mask_t best_pl = 0, best_out = 0;
@@ -121,7 +145,7 @@ SIESTA_HD bool fk2_eval(const DevNfa& nfa, const TraceEvents& ev, typename MaskO
             prev = j;
         }
     }
-    // P(i)
+    // P(i): only if it can still reach the best size
     for (mask_t r = am; r; r &= r - 1) {
         const int j = MO::lo(r);
         const mask_t cand = bm & MO::above(j);

@@ -34,7 +34,7 @@ static int run_one(const DevNfa& dn, const std::vector<uint32_t>& meta, const st
     constexpr int NE = 32 * W;
     const bool evt_pos = (flags & SIESTA_F_EVT_POS) != 0;
     if ((int)meta.size() > NE) return 3;
-    TraceEvents ev{meta.data(), needs_ts ? ts.data() : nullptr, 1, (int)meta.size(), evt_pos};
+    TraceEvents ev{meta.data(), needs_ts ? ts.data() : nullptr, 1, (int)meta.size(), evt_pos, 1};
     // same dispatch as kernel K1: closed-form evaluators for the NK / FK2 classes (detect_fast.cuh)
     if (dn.fast_class == FAST_FK2) {
         typename MaskOps<W>::T m = 0;
