@@ -33,10 +33,15 @@ struct DetectParams {
     const int64_t* work;      // indices into the candidate list to process, or nullptr (= all)
     int64_t n_work;           // number of traces this launch verifies
     const uint16_t* lut;      // [n_act] smask | fmask << 8
-    uint32_t relrev_a, relrev_b;  // alpha_mode 0/1: bit-reversed activity set of the pattern (ids 0..31, 32..63)
-    uint16_t lutc[64];        // alpha_mode 0/1: the lut in kernel-parameter space
+    // alpha_mode 0/1: the pattern's activities are numbered 1..K (K <= 7, "class"); plane p holds, bit-reversed, the
+    // activities whose class has bit p set (ids 0..31 in [p][0], 32..63 in [p][1]); cls_word / cls_act give the lut
+    // word and the activity id of a class, so the filter needs no table lookup and no re-read of the activity column
+    uint32_t relrev[3][2];
+    uint16_t cls_word[8];
+    int32_t cls_act[8];
+    int32_t n_planes;
     int64_t n_events;         // events of the whole log (bound of the vector loads)
-    int32_t alpha_mode;       // 0: n_act <= 32, 1: n_act <= 64 (both: ids validated at log load), 2: general (lut in HBM)
+    int32_t alpha_mode;       // 0: n_act <= 32, 1: n_act <= 64 (both: ids validated at log load, K <= 7), 2: general (lut in HBM)
     int32_t vec_ok;           // act is 16-byte aligned: 128-bit loads
     int32_t n_act;
     uint32_t flags;
@@ -75,7 +80,9 @@ __device__ __forceinline__ void load_sectors(const DetectParams& P, long long e,
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const long long c = e + 8 * q;
-        if (c < o1 && P.vec_ok && c + 8 <= P.n_events) {
+        if (c >= o1) {
+            v[2 * q] = v[2 * q + 1] = make_int4(-1, -1, -1, -1);
+        } else if (P.vec_ok && c + 8 <= P.n_events) {
             v[2 * q] = __ldg(reinterpret_cast<const int4*>(P.act + c));
             v[2 * q + 1] = __ldg(reinterpret_cast<const int4*>(P.act + c + 4));
         } else {
@@ -104,6 +111,21 @@ __device__ __forceinline__ uint32_t rel_push64(uint32_t pend, uint32_t relrev_a,
     return __funnelshift_r(t, pend, 31);
 }
 
+// Class bit-planes of 32 consecutive events (bit i = event i), last event first.
+template <int NPL, bool WIDE>
+__device__ __forceinline__ void scan_block(const DetectParams& P, const int4 (&v)[8], uint32_t (&pl)[3]) {
+#pragma unroll
+    for (int q = 7; q >= 0; --q) {
+        const int a[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+        for (int i = 3; i >= 0; --i) {
+#pragma unroll
+            for (int p = 0; p < NPL; ++p)
+                pl[p] = WIDE ? rel_push64(pl[p], P.relrev[p][0], P.relrev[p][1], a[i]) : rel_push32(pl[p], P.relrev[p][0], a[i]);
+        }
+    }
+}
+
 // EventTs.transformSaseEvent: (int)((t - minTs) / 1000), truncating long division (J/model/Events/EventTs.java:54).
 // Differences below 2^32 ms (49 days) take a 32-bit multiply-high instead of the emulated 64-bit division.
 __device__ __forceinline__ int rel_seconds(long long diff_ms) {
@@ -114,6 +136,10 @@ __device__ __forceinline__ int rel_seconds(long long diff_ms) {
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -188,24 +214,16 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
         for (long long e = o0 & ~7LL; e < o1; e += 32) {
             int4 nv[8];
             if (e + 32 < o1) load_sectors(P, e + 32, o0, o1, nv);  // the next 32 events are in flight while these are tested
-            // bit i of pend = event e + i belongs to the pattern (built last event first: shift left, insert at bit 0)
-            uint32_t pend = 0;
+            // class bit-planes of the 32 events (bit i = event e + i); pend = events that belong to the pattern
+            uint32_t pl[3] = {0u, 0u, 0u};
             if (P.alpha_mode == 0) {
-#pragma unroll
-                for (int q = 7; q >= 0; --q) {
-                    pend = rel_push32(pend, P.relrev_a, v[q].w);
-                    pend = rel_push32(pend, P.relrev_a, v[q].z);
-                    pend = rel_push32(pend, P.relrev_a, v[q].y);
-                    pend = rel_push32(pend, P.relrev_a, v[q].x);
-                }
+                if (P.n_planes == 1) scan_block<1, false>(P, v, pl);
+                else if (P.n_planes == 2) scan_block<2, false>(P, v, pl);
+                else scan_block<3, false>(P, v, pl);
             } else if (P.alpha_mode == 1) {
-#pragma unroll
-                for (int q = 7; q >= 0; --q) {
-                    pend = rel_push64(pend, P.relrev_a, P.relrev_b, v[q].w);
-                    pend = rel_push64(pend, P.relrev_a, P.relrev_b, v[q].z);
-                    pend = rel_push64(pend, P.relrev_a, P.relrev_b, v[q].y);
-                    pend = rel_push64(pend, P.relrev_a, P.relrev_b, v[q].x);
-                }
+                if (P.n_planes == 1) scan_block<1, true>(P, v, pl);
+                else if (P.n_planes == 2) scan_block<2, true>(P, v, pl);
+                else scan_block<3, true>(P, v, pl);
             } else {
 #pragma unroll
                 for (int q = 7; q >= 0; --q) {
@@ -213,10 +231,11 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
 #pragma unroll
                     for (int i = 3; i >= 0; --i) {
                         const bool rel = ((unsigned)a[i] < (unsigned)P.n_act) && __ldg(P.lut + a[i]) != 0;
-                        pend = (pend << 1) | (rel ? 1u : 0u);
+                        pl[0] = (pl[0] << 1) | (rel ? 1u : 0u);
                     }
                 }
             }
+            uint32_t pend = pl[0] | pl[1] | pl[2];
             // events of the neighbouring traces that share the first / last sector
             if (e < o0) pend &= ~((1u << (int)(o0 - e)) - 1u);
             if (o1 - e < 32) pend &= (1u << (int)(o1 - e)) - 1u;
@@ -225,7 +244,8 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
                 pend &= pend - 1;
                 if (cnt < NE) {
                     const long long src = e + j - o0;
-                    s_meta[cnt * 32 + lane] = (uint32_t)src;
+                    const uint32_t cls = ((pl[0] >> j) & 1u) | (((pl[1] >> j) & 1u) << 1) | (((pl[2] >> j) & 1u) << 2);
+                    s_meta[cnt * 32 + lane] = cls | ((uint32_t)src << 16);
                     // the raw timestamp of a surviving event goes straight to its shared-memory slot (no register, no stall)
                     if (P.needs_ts) cp_async8(s_slot + cnt * 32 + lane, tsp + src);
                 }
@@ -241,12 +261,20 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
         long long t0ms = 0;  // first event of the filtered list (Utils.java:51-53)
         if (my_cnt > 0 && my_cnt <= NE) {
             if (P.needs_ts) t0ms = (long long)s_slot[lane];
-            else if (all_cols && !evt_pos) t0ms = __ldg(tsp + s_meta[lane]);
+            else if (all_cols && !evt_pos) t0ms = __ldg(tsp + (s_meta[lane] >> 16));
 #pragma unroll 4
             for (int r = 0; r < my_cnt; ++r) {
-                const uint32_t src = s_meta[r * 32 + lane];
-                const int a = __ldg(P.act + o0 + src);
-                const uint32_t m = P.alpha_mode == 2 ? (uint32_t)__ldg(P.lut + a) : (uint32_t)P.lutc[a & 63];
+                const uint32_t cw = s_meta[r * 32 + lane];
+                const uint32_t src = cw >> 16;
+                int a;
+                uint32_t m;
+                if (P.alpha_mode == 2) {  // general alphabet: re-read the activity (L2 hit) and look its word up
+                    a = __ldg(P.act + o0 + src);
+                    m = (uint32_t)__ldg(P.lut + a);
+                } else {
+                    a = P.cls_act[cw & 7u];
+                    m = (uint32_t)P.cls_word[cw & 7u];
+                }
                 s_meta[r * 32 + lane] = m | (src << 16);
                 int rel = 0;
                 if (P.needs_ts) rel = rel_seconds((long long)s_slot[r * 32 + lane] - t0ms);
@@ -705,14 +733,29 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     P.lut = b_lut.as<uint16_t>();
     P.n_act = log->n_activities;
     P.n_events = log->n_events;
+    // classes: the pattern's activities numbered 1..K
     P.alpha_mode = !log->act_valid ? 2 : (log->n_activities <= 32 ? 0 : (log->n_activities <= 64 ? 1 : 2));
-    P.relrev_a = P.relrev_b = 0;
-    std::memset(P.lutc, 0, sizeof(P.lutc));
-    if (P.alpha_mode != 2)
-        for (size_t a = 0; a < lut.size() && a < 64; ++a) {
-            P.lutc[a] = lut[a];
-            if (lut[a]) (a < 32 ? P.relrev_a : P.relrev_b) |= 0x80000000u >> (a & 31);
+    std::memset(P.relrev, 0, sizeof(P.relrev));
+    std::memset(P.cls_word, 0, sizeof(P.cls_word));
+    std::memset(P.cls_act, 0, sizeof(P.cls_act));
+    P.n_planes = 1;
+    if (P.alpha_mode != 2) {
+        int K = 0;
+        for (size_t a = 0; a < lut.size(); ++a) K += lut[a] != 0;
+        if (K > 7) P.alpha_mode = 2;
+        else {
+            int c = 0;
+            for (size_t a = 0; a < lut.size(); ++a) {
+                if (!lut[a]) continue;
+                ++c;
+                P.cls_word[c] = lut[a];
+                P.cls_act[c] = (int32_t)a;
+                for (int p = 0; p < 3; ++p)
+                    if ((c >> p) & 1) P.relrev[p][a >> 5] |= 0x80000000u >> (a & 31);
+            }
+            P.n_planes = K <= 1 ? 1 : (K <= 3 ? 2 : 3);
         }
+    }
     P.vec_ok = (reinterpret_cast<uintptr_t>(log->d_act) & 15u) == 0 ? 1 : 0;
     P.flags = flags;
     P.needs_ts = needs_ts;

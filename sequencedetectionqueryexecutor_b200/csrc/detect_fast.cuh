@@ -85,7 +85,11 @@ SIESTA_HD bool fk2_eval(const DevNfa& nfa, const TraceEvents& ev, typename MaskO
         p_le[k] = nfa.p_op[1][k] == SIESTA_OP_LE;
         p_c[k] = nfa.p_c[1][k];
     }
-    auto val = [&](int mode, int j) -> int { return mode == 0 ? j : (mode == 1 ? ev.src(j) : (mode == 2 ? ev.ts[j * ev.ts_stride] : 0)); };
+    auto val = [&](int mode, int j) -> int {
+        if (mode == 2) return ev.ts[j * ev.ts_stride];
+        if (mode == 1) return ev.src(j);
+        return mode == 0 ? j : 0;
+    };
     auto pass = [&](int b, int a) -> bool {
         bool ok = true;
 #pragma unroll
@@ -99,17 +103,41 @@ SIESTA_HD bool fk2_eval(const DevNfa& nfa, const TraceEvents& ev, typename MaskO
         return ok;
     };
 
-    // one pass over the events: a's, b's that follow an a, and the good b's (pass against the latest a before them)
+    // one pass over the events: a's, b's that follow an a, and the good b's (pass against the latest a before them).
+    // mono_le: every predicate is a `within` (<=) and its attribute never decreases along the events; then
+    // pass(b, a_i) implies good(b), so P(i), i >= 1, is always smaller than Q(0,i) and only P(0) can be selected.
     mask_t am = 0, bm = 0, good = 0;
     int la = -1;
+    bool mono_le = true;
+    int prev_v[SIESTA_MAX_PREDS];
+    long long la_v[SIESTA_MAX_PREDS];
+#pragma unroll
+    for (int k = 0; k < SIESTA_MAX_PREDS; ++k) {
+        prev_v[k] = -2147483647 - 1;
+        la_v[k] = 0;
+        if (k < np) mono_le = mono_le && p_le[k];
+    }
     for (int j = 0; j < ev.n; ++j) {
         const uint32_t w = ev.word(j);
-        if (w & 1u) {
+        const bool is_a = w & 1u;
+        const bool is_b = !is_a && (w & 2u) && la >= 0;  // b's before the first a meet no run
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < SIESTA_MAX_PREDS; ++k) {
+            if (k < np) {
+                const int vj = val(p_mode[k], j);
+                mono_le = mono_le && vj >= prev_v[k];
+                prev_v[k] = vj;
+                ok = ok && (p_le[k] ? (long long)vj <= la_v[k] : (long long)vj >= la_v[k]);
+                if (is_a) la_v[k] = (long long)vj + p_c[k];
+            }
+        }
+        if (is_a) {
             am |= MO::bit(j);
             la = j;
-        } else if ((w & 2u) && la >= 0) {  // b's before the first a meet no run
+        } else if (is_b) {
             bm |= MO::bit(j);
-            if (pass(j, la)) good |= MO::bit(j);
+            if (ok) good |= MO::bit(j);
         }
     }
     if (!bm) return false;
@@ -148,12 +176,14 @@ SIESTA_HD bool fk2_eval(const DevNfa& nfa, const TraceEvents& ev, typename MaskO
     // P(i): only if it can still reach the best size
     for (mask_t r = am; r; r &= r - 1) {
         const int j = MO::lo(r);
+        if (mono_le && j != a_first) break;
         const mask_t cand = bm & MO::above(j);
         if (1 + MO::popc(cand) < best_size) continue;
         mask_t pm = 0;
         for (mask_t c = cand; c; c &= c - 1) {
             const int b = MO::lo(c);
             if (pass(b, j)) pm |= MO::bit(b);
+            else if (mono_le) break;  // the passing b's are a prefix
         }
         if (!pm) continue;
         consider(1 + MO::popc(pm), MO::hi(pm), MO::bit(j) | pm, MO::bit(j) | pm, true);
