@@ -16,6 +16,8 @@
 // device scans), so the result is deterministic.
 #include <algorithm>
 #include <cstdio>
+#include <type_traits>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -23,7 +25,8 @@
 
 namespace siesta {
 
-constexpr int NT = 128;  // threads per CTA == traces per tile
+constexpr int NT = 128;      // default threads per CTA (one warp = one tile of 32 traces)
+constexpr int NT_MAX = 256;  // launch bound
 
 struct DetectParams {
     const int64_t* trace_off;
@@ -151,13 +154,16 @@ struct WarpSmem {
     static constexpr size_t famvv_bytes = SMEM_RUNS ? sizeof(unsigned long long) * NF * 32 : 0;
     static constexpr size_t rmask_off = famvv_off + famvv_bytes;
     static constexpr size_t rmask_bytes = SMEM_RUNS ? sizeof(typename MaskOps<W>::T) * R * 32 : 0;
-    static constexpr size_t meta_off = rmask_off + rmask_bytes;
-    static constexpr size_t meta_bytes = sizeof(uint32_t) * NE * 32;
-    static constexpr size_t rmeta_off = meta_off + meta_bytes;
+    // per event, while the trace is scanned: class | in-trace index << 3; afterwards: the activity id
+    // (16 bits in the narrow configuration: traces longer than 8192 events go to the wide one)
+    typedef typename std::conditional<W == 1, uint16_t, uint32_t>::type small_t;
+    static constexpr size_t small_off = rmask_off + rmask_bytes;
+    static constexpr size_t small_bytes = sizeof(small_t) * NE * 32;
+    static constexpr size_t rmeta_off = (small_off + small_bytes + 15) & ~(size_t)15;
     static constexpr size_t rmeta_bytes = SMEM_RUNS ? sizeof(uint32_t) * R * 32 : 0;
     static constexpr size_t bytes_off = rmeta_off + rmeta_bytes;                 // rfam, fmin, fmin2, fcnt
     static constexpr size_t bytes_bytes = SMEM_RUNS ? (size_t)(R + 3 * NF) * 32 : 0;
-    // one 8-byte slot per event: first the raw int64 timestamp (cp.async target), then {relative seconds, activity id}
+    // one 8-byte slot per event: first the raw int64 timestamp (cp.async target), then {relative seconds, lut word | index << 16}
     static constexpr size_t slot_off = (bytes_off + bytes_bytes + 15) & ~(size_t)15;
     static constexpr size_t slot_bytes = sizeof(unsigned long long) * NE * 32;
     static constexpr size_t aux_off = slot_off + slot_bytes;
@@ -168,7 +174,7 @@ struct WarpSmem {
 // One warp owns a tile of 32 traces from start to finish: no block-level barrier anywhere.
 // MODE: FAST_NONE = run-list engine, FAST_NK / FAST_FK2 = closed-form evaluators (detect_fast.cuh).
 template <int W, int R, int NF, bool SMEM_RUNS, int MODE>
-__global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ DevNfa nfa) {
+__global__ void __launch_bounds__(NT_MAX) detect_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ DevNfa nfa) {
     typedef MaskOps<W> MO;
     typedef typename MO::T mask_t;
     typedef WarpSmem<W, R, NF, SMEM_RUNS> L;
@@ -180,9 +186,12 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
     const bool return_all = (P.flags & SIESTA_F_RETURN_ALL) != 0;
     const bool needs_aux = MODE == FAST_NK && return_all;
     unsigned char* wbase = smem_raw + (size_t)warp * L::total(needs_aux);
-    uint32_t* s_meta = reinterpret_cast<uint32_t*>(wbase + L::meta_off);                      // [NE][32]
+    typedef typename L::small_t small_t;
+    constexpr unsigned ACT_NONE = W == 1 ? 0xFFFFu : 0xFFFFFFFFu;  // the activity id does not fit small_t: re-read it from the log
+    constexpr long long MAX_LEN = W == 1 ? 8192 : 65536;  // the in-trace index must fit small_t next to the class (and 16 bits of the word)
+    small_t* s_small = reinterpret_cast<small_t*>(wbase + L::small_off);                      // [NE][32]
     unsigned long long* s_slot = reinterpret_cast<unsigned long long*>(wbase + L::slot_off);  // [NE][32]
-    const int32_t* s_ts = reinterpret_cast<const int32_t*>(s_slot);                           // low words: relative seconds
+    const uint32_t* s_w32 = reinterpret_cast<const uint32_t*>(s_slot);  // slot j of lane l: words [(j * 32 + l) * 2 + {0: seconds, 1: word}]
 
     const bool all_cols = (P.flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
     const bool prune = (P.flags & SIESTA_F_LITERAL_RUNS) == 0;
@@ -211,7 +220,7 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
         const long long* tsp = reinterpret_cast<const long long*>(P.ts_ms) + o0;
         int4 v[8];
         load_sectors(P, o0 & ~7LL, o0, o1, v);
-        for (long long e = o0 & ~7LL; e < o1; e += 32) {
+        for (long long e = o0 & ~7LL; e < o1; e += 32) {  // lanes whose trace has ended leave the loop
             int4 nv[8];
             if (e + 32 < o1) load_sectors(P, e + 32, o0, o1, nv);  // the next 32 events are in flight while these are tested
             // class bit-planes of the 32 events (bit i = event e + i); pend = events that belong to the pattern
@@ -245,7 +254,7 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
                 if (cnt < NE) {
                     const long long src = e + j - o0;
                     const uint32_t cls = ((pl[0] >> j) & 1u) | (((pl[1] >> j) & 1u) << 1) | (((pl[2] >> j) & 1u) << 2);
-                    s_meta[cnt * 32 + lane] = cls | ((uint32_t)src << 16);
+                    s_small[cnt * 32 + lane] = (small_t)(cls | ((uint32_t)src << 3));
                     // the raw timestamp of a surviving event goes straight to its shared-memory slot (no register, no stall)
                     if (P.needs_ts) cp_async8(s_slot + cnt * 32 + lane, tsp + src);
                 }
@@ -254,18 +263,18 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[q] = nv[q];
         }
-        if (o1 - o0 > 65536) cnt = NE + 1;  // in-trace index does not fit the packed word: overflow path
+        if (o1 - o0 > MAX_LEN) cnt = NE + 1;  // in-trace index does not fit the packed word: overflow path
         const int my_cnt = cnt;
         cp_async_wait_all();
         // second pass over the survivors only: activity -> state-mask word, timestamp -> relative seconds
         long long t0ms = 0;  // first event of the filtered list (Utils.java:51-53)
         if (my_cnt > 0 && my_cnt <= NE) {
             if (P.needs_ts) t0ms = (long long)s_slot[lane];
-            else if (all_cols && !evt_pos) t0ms = __ldg(tsp + (s_meta[lane] >> 16));
+            else if (all_cols && !evt_pos) t0ms = __ldg(tsp + (s_small[lane] >> 3));
 #pragma unroll 4
             for (int r = 0; r < my_cnt; ++r) {
-                const uint32_t cw = s_meta[r * 32 + lane];
-                const uint32_t src = cw >> 16;
+                const uint32_t cw = s_small[r * 32 + lane];
+                const uint32_t src = cw >> 3;
                 int a;
                 uint32_t m;
                 if (P.alpha_mode == 2) {  // general alphabet: re-read the activity (L2 hit) and look its word up
@@ -275,10 +284,10 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
                     a = P.cls_act[cw & 7u];
                     m = (uint32_t)P.cls_word[cw & 7u];
                 }
-                s_meta[r * 32 + lane] = m | (src << 16);
                 int rel = 0;
                 if (P.needs_ts) rel = rel_seconds((long long)s_slot[r * 32 + lane] - t0ms);
-                s_slot[r * 32 + lane] = (unsigned long long)(uint32_t)rel | ((unsigned long long)(uint32_t)a << 32);
+                s_slot[r * 32 + lane] = (unsigned long long)(uint32_t)rel | ((unsigned long long)(m | (src << 16)) << 32);
+                s_small[r * 32 + lane] = (small_t)((unsigned)a < ACT_NONE ? (unsigned)a : ACT_NONE);
             }
         }
         __syncwarp();
@@ -295,7 +304,8 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
             if (my_cnt > NE) {
                 status = ST_OVF;
             } else {
-                TraceEvents ev{s_meta + lane, P.needs_ts ? s_ts + 2 * lane : nullptr, 32, my_cnt, evt_pos, 64};
+                TraceEvents ev{s_w32 + 2 * lane + 1, P.needs_ts ? reinterpret_cast<const int32_t*>(s_w32) + 2 * lane : nullptr,
+                               64, my_cnt, evt_pos, 64};
                 if constexpr (MODE == FAST_FK2) {
                     mask_t m = 0;
                     if (fk2_eval<W>(nfa, ev, m)) {
@@ -305,7 +315,10 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
                     }
                 } else if constexpr (MODE == FAST_NK) {
                     mask_t* aux = reinterpret_cast<mask_t*>(wbase + L::aux_off) + lane;
-                    if (nk_eval<W>(nfa, ev, return_all, evt_pos, aux, 32, sel_local, nsel, n_emitted)) status = ST_MATCH;
+                    NkMasks<W> nkm;
+                    nkm.init();
+                    for (int j = 0; j < ev.n; ++j) nkm.on_event(j, ev.word(j));
+                    if (nk_eval<W>(nfa, ev, nkm.T, return_all, evt_pos, aux, 32, sel_local, nsel, n_emitted)) status = ST_MATCH;
                 } else {
                     auto body = [&](auto& eng) {
                         BestEmit<W> be;
@@ -422,13 +435,14 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
                         int k = (int)(f - (o_incl - o_ev));  // k-th event of the owner's occurrence
                         for (; k > 0; --k) m &= m - 1;
                         const int j = MO::lo(m);
-                        const int src = (int)(s_meta[j * 32 + owner] >> 16);
+                        const unsigned long long slot = s_slot[j * 32 + owner];  // {relative seconds, lut word | index << 16}
+                        const int src = (int)(slot >> 48);
                         const long long at = (long long)base1 + f;
                         P.s_ev_pos[at] = src;
                         if (all_cols) {
-                            const unsigned long long slot = s_slot[j * 32 + owner];  // {relative seconds, activity id}
+                            const uint32_t sa = s_small[j * 32 + owner];
                             P.s_ev_rank[at] = j;
-                            P.s_ev_act[at] = (int32_t)(slot >> 32);
+                            P.s_ev_act[at] = sa != ACT_NONE ? (int32_t)sa : __ldg(P.act + o_o0 + src);
                             // SaseEvent.getEventBoth: timestamp * 1000 + minTs (SaseEvent.java:94-106)
                             long long out_ts;
                             if (P.needs_ts) out_ts = (long long)(int32_t)(uint32_t)slot * 1000 + o_t0;
@@ -448,12 +462,13 @@ __global__ void __launch_bounds__(NT) detect_kernel(const __grid_constant__ Dete
                     while (m) {
                         const int j = MO::lo(m);
                         m &= m - 1;
-                        const int src = (int)(s_meta[j * 32 + lane] >> 16);
+                        const unsigned long long slot = s_slot[j * 32 + lane];  // {relative seconds, lut word | index << 16}
+                        const int src = (int)(slot >> 48);
                         P.s_ev_pos[e] = src;
                         if (all_cols) {
-                            const unsigned long long slot = s_slot[j * 32 + lane];  // {relative seconds, activity id}
+                            const uint32_t sa = s_small[j * 32 + lane];
                             P.s_ev_rank[e] = j;
-                            P.s_ev_act[e] = (int32_t)(slot >> 32);
+                            P.s_ev_act[e] = sa != ACT_NONE ? (int32_t)sa : __ldg(P.act + o0 + src);
                             // SaseEvent.getEventBoth: timestamp * 1000 + minTs (SaseEvent.java:94-106)
                             long long out_ts;
                             if (P.needs_ts) out_ts = (long long)(int32_t)(uint32_t)slot * 1000 + t0ms;
@@ -552,42 +567,45 @@ __global__ void __launch_bounds__(GT) count_blocks_kernel(const __grid_constant_
         for (int q = 0; q < 3; ++q) G.blk[q * G.n_blk + blockIdx.x] = tot[q];
 }
 
-// one block: exclusive scan of the three rows of block sums, in place
+// one block: exclusive scan of the three rows of block sums, in place.  Each thread owns a contiguous segment of all
+// three rows (serial sum), the 1024 partial sums are scanned with shuffles, then the segment is rewritten.
 __global__ void __launch_bounds__(1024) scan_blocks_kernel(unsigned long long* blk, int64_t n_blk) {
-    __shared__ unsigned long long ws[32];
-    __shared__ unsigned long long carry_s;
+    __shared__ unsigned long long ws[3][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int q = 0; q < 3; ++q) {
-        unsigned long long* row = blk + q * n_blk;
-        if (threadIdx.x == 0) carry_s = 0;
-        __syncthreads();
-        for (int64_t base = 0; base < n_blk; base += 1024) {
-            const int64_t i = base + threadIdx.x;
-            const unsigned long long v = i < n_blk ? row[i] : 0ull;
-            unsigned long long inc = v;
+    const int64_t per = (n_blk + 1023) / 1024;
+    const int64_t lo = (int64_t)threadIdx.x * per, hi = lo + per < n_blk ? lo + per : n_blk;
+    unsigned long long part[3] = {0, 0, 0};
+    for (int64_t i = lo; i < hi; ++i)
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                unsigned long long y = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += y;
-            }
-            if (lane == 31) ws[warp] = inc;
-            __syncthreads();
-            unsigned long long before = 0, all = 0;
-            for (int k = 0; k < 32; ++k) {
-                if (k < warp) before += ws[k];
-                all += ws[k];
-            }
-            const unsigned long long carry = carry_s;
-            if (i < n_blk) row[i] = carry + before + inc - v;
-            __syncthreads();
-            if (threadIdx.x == 0) carry_s = carry + all;
-            __syncthreads();
+        for (int q = 0; q < 3; ++q) part[q] += blk[q * n_blk + i];
+    unsigned long long inc[3] = {part[0], part[1], part[2]};
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, inc[q], d);
+            if (lane >= d) inc[q] += y;
+        }
+    if (lane == 31)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) ws[q][warp] = inc[q];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        unsigned long long before = 0;
+        for (int k = 0; k < warp; ++k) before += ws[q][k];
+        unsigned long long run = before + inc[q] - part[q];  // exclusive base of this thread's segment
+        for (int64_t i = lo; i < hi; ++i) {
+            const unsigned long long v = blk[q * n_blk + i];
+            blk[q * n_blk + i] = run;
+            run += v;
         }
     }
 }
 
 __global__ void __launch_bounds__(GT) gather_kernel(const __grid_constant__ GatherParams G) {
     const int64_t i = (int64_t)blockIdx.x * GT + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     unsigned long long v[3] = {0, 0, 0}, ex[3], tot[3];
     uint32_t nocc = 0;
     if (i < G.n) {
@@ -597,27 +615,64 @@ __global__ void __launch_bounds__(GT) gather_kernel(const __grid_constant__ Gath
         v[2] = nocc ? G.d_nev[i] : 0;
     }
     block_scan3(v, ex, tot);
-    if (nocc == 0) return;
     const int64_t tp = (int64_t)(G.blk[0 * G.n_blk + blockIdx.x] + ex[0]);
     const int64_t op = (int64_t)(G.blk[1 * G.n_blk + blockIdx.x] + ex[1]);
-    int64_t ep = (int64_t)(G.blk[2 * G.n_blk + blockIdx.x] + ex[2]);
-    G.trace_idx[tp] = G.cand ? G.cand[i] : i;
-    G.occ_off[tp] = op;
-    int64_t se = G.d_stage[i];
-    const int64_t so = G.d_stage_occ[i];
-    for (uint32_t o = 0; o < nocc; ++o) {
-        const int ne = G.s_occ_nev[so + o];
-        G.ev_off[op + o] = ep;
-        for (int k = 0; k < ne; ++k) {
-            G.ev_posv[ep + k] = G.s_ev_pos[se + k];
+    const int64_t ep = (int64_t)(G.blk[2 * G.n_blk + blockIdx.x] + ex[2]);
+    long long se = 0;
+    if (nocc) {
+        G.trace_idx[tp] = G.cand ? G.cand[i] : i;
+        G.occ_off[tp] = op;
+        se = G.d_stage[i];
+        const int64_t so = G.d_stage_occ[i];
+        int64_t e = ep;
+        for (uint32_t o = 0; o < nocc; ++o) {
+            G.ev_off[op + o] = e;
+            e += G.s_occ_nev[so + o];
+        }
+    }
+    // The events of a warp's 32 candidates are contiguous in the output (ep ascends with the lane) and, per candidate,
+    // contiguous in the staging area: copy them as one flat stream, 32 events per step, all four columns coalesced.
+    const unsigned my_ev = (unsigned)v[2];
+    unsigned incl = my_ev;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    const unsigned wtot = __shfl_sync(0xffffffffu, incl, 31);
+    const long long wbase = shfl_i64(ep, 0);  // lane 0's exclusive base = first output slot of the warp
+    for (unsigned f0 = 0; f0 < wtot; f0 += 32) {
+        const unsigned f = f0 + lane;
+        int lo = 0, hi = 31;
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+            const int mid = (lo + hi) >> 1;
+            const unsigned vmid = __shfl_sync(0xffffffffu, incl, mid);
+            if (vmid > f) hi = mid; else lo = mid + 1;
+        }
+        const int owner = lo & 31;
+        const unsigned o_incl = __shfl_sync(0xffffffffu, incl, owner);
+        const unsigned o_ev = __shfl_sync(0xffffffffu, my_ev, owner);
+        const long long o_se = shfl_i64(se, owner);
+        if (f < wtot) {
+            const long long from = o_se + (long long)(f - (o_incl - o_ev));
+            const long long to = wbase + f;
+            // all loads first: one memory latency per step, not four
+            const int32_t c_pos = __ldg(G.s_ev_pos + from);
+            int32_t c_rank = 0, c_act = 0;
+            long long c_ts = 0;
             if (G.all_cols) {
-                G.ev_rank[ep + k] = G.s_ev_rank[se + k];
-                G.ev_act[ep + k] = G.s_ev_act[se + k];
-                G.ev_ts[ep + k] = G.s_ev_ts[se + k];
+                c_rank = __ldg(G.s_ev_rank + from);
+                c_act = __ldg(G.s_ev_act + from);
+                c_ts = __ldg(reinterpret_cast<const long long*>(G.s_ev_ts) + from);
+            }
+            G.ev_posv[to] = c_pos;
+            if (G.all_cols) {
+                G.ev_rank[to] = c_rank;
+                G.ev_act[to] = c_act;
+                G.ev_ts[to] = c_ts;
             }
         }
-        ep += ne;
-        se += ne;
     }
 }
 
@@ -661,18 +716,31 @@ template <int W, int R, int NF, bool SMEM_RUNS, int MODE>
 int launch_detect(const Ctx* ctx, cudaStream_t stream, DetectParams P, const DevNfa& nfa) {
     typedef WarpSmem<W, R, NF, SMEM_RUNS> L;
     const bool needs_aux = MODE == FAST_NK && (P.flags & SIESTA_F_RETURN_ALL) != 0;
-    const size_t smem = L::total(needs_aux) * (NT / 32);
+    int nt = NT;
+    if (const char* env = std::getenv("SIESTA_K1_THREADS")) {  // tuning aid: threads per CTA (multiple of 32, <= NT)
+        const int v = std::atoi(env);
+        if (v >= 32 && v <= NT_MAX && v % 32 == 0) nt = v;
+    }
+    const size_t smem = L::total(needs_aux) * (nt / 32);
     auto kern = detect_kernel<W, R, NF, SMEM_RUNS, MODE>;
     SIESTA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (const char* env = std::getenv("SIESTA_K1_CARVEOUT")) {  // tuning aid: shared-memory carveout in percent
+        const int v = std::atoi(env);
+        if (v >= 0 && v <= 100) SIESTA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, v));
+    }
     int per_sm = 0;
-    SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));
     if (per_sm < 1) per_sm = 1;
     const int64_t n_tiles = (P.n_work + 31) / 32;   // one tile = the 32 traces of one warp
     P.n_tiles = (int32_t)n_tiles;
-    const int64_t ctas_needed = (n_tiles + NT / 32 - 1) / (NT / 32);
+    const int64_t ctas_needed = (n_tiles + nt / 32 - 1) / (nt / 32);
+    if (const char* env = std::getenv("SIESTA_K1_CTAS_PER_SM")) {  // tuning aid: cap on resident CTAs per SM
+        const int v = std::atoi(env);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
     int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)ctx->sm_count * per_sm);
     if (grid < 1) grid = 1;
-    kern<<<grid, NT, smem, stream>>>(P, nfa);
+    kern<<<grid, nt, smem, stream>>>(P, nfa);
     SIESTA_LAUNCHED();
     SIESTA_CUDA_OK(cudaGetLastError());
     return SIESTA_OK;

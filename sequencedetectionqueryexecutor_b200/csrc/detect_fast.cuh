@@ -68,64 +68,53 @@ SIESTA_HD __forceinline__ bool fast_preds(const DevNfa& nfa, const TraceEvents& 
 }
 
 // ------------------------------------------------------------------------------------------------ class FK2
-template <int W>
-SIESTA_HD bool fk2_eval(const DevNfa& nfa, const TraceEvents& ev, typename MaskOps<W>::T& out) {
+// Streaming form: kernel K1 feeds on_event() from the pass that builds the trace's shared-memory columns, so the
+// events are not read back; finish() then needs the columns only for P(i).
+// NPMAX = compile-time bound of state 1's predicate count (1 covers the usual single constraint; 4 = any)
+template <int W, int NPMAX = SIESTA_MAX_PREDS>
+struct Fk2Eval {
     typedef MaskX<W> MO;
     typedef typename MO::T mask_t;
     // state 1's predicates, decoded once: where the attribute of event j lives (0 = j itself, 1 = in-trace position,
-    // 2 = relative seconds; SaseEvent attributes after Utils.transformToSaseEvents, see TraceEvents), operator, constant
-    const int np = nfa.n_preds[1];
-    int p_mode[SIESTA_MAX_PREDS];
-    bool p_le[SIESTA_MAX_PREDS];
-    long long p_c[SIESTA_MAX_PREDS];
-#pragma unroll
-    for (int k = 0; k < SIESTA_MAX_PREDS; ++k) {
-        const bool is_pos = nfa.p_attr[1][k] == SIESTA_ATTR_POSITION;
-        p_mode[k] = is_pos ? (ev.evt_pos ? 1 : 0) : (ev.evt_pos ? 0 : (ev.ts ? 2 : 3));
-        p_le[k] = nfa.p_op[1][k] == SIESTA_OP_LE;
-        p_c[k] = nfa.p_c[1][k];
-    }
-    auto val = [&](int mode, int j) -> int {
-        if (mode == 2) return ev.ts[j * ev.ts_stride];
-        if (mode == 1) return ev.src(j);
-        return mode == 0 ? j : 0;
-    };
-    auto pass = [&](int b, int a) -> bool {
-        bool ok = true;
-#pragma unroll
-        for (int k = 0; k < SIESTA_MAX_PREDS; ++k) {
-            if (k < np) {
-                const long long lhs = val(p_mode[k], b);
-                const long long rhs = (long long)val(p_mode[k], a) + p_c[k];
-                ok = ok && (p_le[k] ? lhs <= rhs : lhs >= rhs);
-            }
-        }
-        return ok;
-    };
-
-    // one pass over the events: a's, b's that follow an a, and the good b's (pass against the latest a before them).
+    // 2 = relative seconds, 3 = constant 0; SaseEvent attributes after Utils.transformToSaseEvents, see TraceEvents)
+    int np;
+    int p_mode[NPMAX];
+    bool p_le[NPMAX];
+    long long p_c[NPMAX];
+    // a's, b's that follow an a, and the good b's (pass against the latest a before them).
     // mono_le: every predicate is a `within` (<=) and its attribute never decreases along the events; then
     // pass(b, a_i) implies good(b), so P(i), i >= 1, is always smaller than Q(0,i) and only P(0) can be selected.
-    mask_t am = 0, bm = 0, good = 0;
-    int la = -1;
-    bool mono_le = true;
-    int prev_v[SIESTA_MAX_PREDS];
-    long long la_v[SIESTA_MAX_PREDS];
+    mask_t am, bm, good;
+    bool seen_a, mono_le;
+    int prev_v[NPMAX];
+    long long la_v[NPMAX];
+
+    SIESTA_HD __forceinline__ void init(const DevNfa& nfa, bool evt_pos, bool has_ts) {
+        np = nfa.n_preds[1];
+        am = bm = good = 0;
+        seen_a = false;
+        mono_le = true;
 #pragma unroll
-    for (int k = 0; k < SIESTA_MAX_PREDS; ++k) {
-        prev_v[k] = -2147483647 - 1;
-        la_v[k] = 0;
-        if (k < np) mono_le = mono_le && p_le[k];
+        for (int k = 0; k < NPMAX; ++k) {
+            const bool is_pos = nfa.p_attr[1][k] == SIESTA_ATTR_POSITION;
+            p_mode[k] = is_pos ? (evt_pos ? 1 : 0) : (evt_pos ? 0 : (has_ts ? 2 : 3));
+            p_le[k] = nfa.p_op[1][k] == SIESTA_OP_LE;
+            p_c[k] = nfa.p_c[1][k];
+            prev_v[k] = -2147483647 - 1;
+            la_v[k] = 0;
+            if (k < np) mono_le = mono_le && p_le[k];
+        }
     }
-    for (int j = 0; j < ev.n; ++j) {
-        const uint32_t w = ev.word(j);
+    // event j of the filtered list: lut word, in-trace position, relative seconds
+    SIESTA_HD __forceinline__ void on_event(int j, uint32_t w, int src, int rel) {
         const bool is_a = w & 1u;
-        const bool is_b = !is_a && (w & 2u) && la >= 0;  // b's before the first a meet no run
+        const bool is_b = !is_a && (w & 2u) && seen_a;  // b's before the first a meet no run
         bool ok = true;
 #pragma unroll
-        for (int k = 0; k < SIESTA_MAX_PREDS; ++k) {
+        for (int k = 0; k < NPMAX; ++k) {
             if (k < np) {
-                const int vj = val(p_mode[k], j);
+                const int m = p_mode[k];
+                const int vj = m == 2 ? rel : (m == 1 ? src : (m == 0 ? j : 0));
                 mono_le = mono_le && vj >= prev_v[k];
                 prev_v[k] = vj;
                 ok = ok && (p_le[k] ? (long long)vj <= la_v[k] : (long long)vj >= la_v[k]);
@@ -134,63 +123,95 @@ SIESTA_HD bool fk2_eval(const DevNfa& nfa, const TraceEvents& ev, typename MaskO
         }
         if (is_a) {
             am |= MO::bit(j);
-            la = j;
+            seen_a = true;
         } else if (is_b) {
             bm |= MO::bit(j);
             if (ok) good |= MO::bit(j);
         }
     }
-    if (!bm) return false;
-    const int a_first = MO::lo(am);
+    SIESTA_HD bool finish(const TraceEvents& ev, mask_t& out) const {
+        if (!bm) return false;
+        const int a_first = MO::lo(am);
+        auto val = [&](int mode, int j) -> int {
+            if (mode == 2) return ev.ts[j * ev.ts_stride];
+            if (mode == 1) return ev.src(j);
+            return mode == 0 ? j : 0;
+        };
+        auto pass = [&](int b, int a) -> bool {
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < NPMAX; ++k) {
+                if (k < np) {
+                    const long long lhs = val(p_mode[k], b);
+                    const long long rhs = (long long)val(p_mode[k], a) + p_c[k];
+                    ok = ok && (p_le[k] ? lhs <= rhs : lhs >= rhs);
+                }
+            }
+            return ok;
+        };
 
-    int best_size = 0, best_k = 0;
-    mask_t best_pl = 0, best_out = 0;
-    bool best_is_p = false;
-    auto consider = [&](int size, int k, mask_t pl, mask_t o, bool is_p) {
-        bool better = size > best_size || (size == best_size && k < best_k);
-        if (!better && size == best_size && k == best_k) {
-            const mask_t x = (pl ^ best_pl) & MO::below(k);
-            if (x) better = (best_pl >> MO::hi(x)) & 1;
-            else if (is_p != best_is_p) {
-                // P(q) and Q(0,q+1) were both placed at a_q and moved together ever since
-                const bool q0 = (pl >> a_first) & 1;
-                better = is_p == q0;
+        int best_size = 0, best_k = 0;
+        mask_t best_pl = 0, best_out = 0;
+        bool best_is_p = false;
+        auto consider = [&](int size, int k, mask_t pl, mask_t o, bool is_p) {
+            bool better = size > best_size || (size == best_size && k < best_k);
+            if (!better && size == best_size && k == best_k) {
+                const mask_t x = (pl ^ best_pl) & MO::below(k);
+                if (x) better = (best_pl >> MO::hi(x)) & 1;
+                else if (is_p != best_is_p) {
+                    // P(q) and Q(0,q+1) were both placed at a_q and moved together ever since
+                    const bool q0 = (pl >> a_first) & 1;
+                    better = is_p == q0;
+                }
+            }
+            if (better) { best_size = size; best_k = k; best_pl = pl; best_out = o; best_is_p = is_p; }
+        };
+
+        // Q(0,m), m >= 1
+        if (good) {
+            const int kq = MO::hi(good);
+            int m = 0, prev = a_first;
+            for (mask_t r = am & MO::above(a_first); r; r &= r - 1) {
+                const int j = MO::lo(r);
+                ++m;
+                const mask_t g = good & MO::above(j);
+                if (!g) break;  // later a's have no good b either
+                consider(m + 1 + MO::popc(g), kq, MO::bit(prev) | g, (am & MO::below(j)) | MO::bit(j) | g, false);
+                prev = j;
             }
         }
-        if (better) { best_size = size; best_k = k; best_pl = pl; best_out = o; best_is_p = is_p; }
-    };
-
-    // Q(0,m), m >= 1
-    if (good) {
-        const int kq = MO::hi(good);
-        int m = 0, prev = a_first;
-        for (mask_t r = am & MO::above(a_first); r; r &= r - 1) {
+        // P(i): only if it can still reach the best size
+        for (mask_t r = am; r; r &= r - 1) {
             const int j = MO::lo(r);
-            ++m;
-            const mask_t g = good & MO::above(j);
-            if (!g) break;  // later a's have no good b either
-            consider(m + 1 + MO::popc(g), kq, MO::bit(prev) | g, (am & MO::below(j)) | MO::bit(j) | g, false);
-            prev = j;
+            if (mono_le && j != a_first) break;
+            const mask_t cand = bm & MO::above(j);
+            if (1 + MO::popc(cand) < best_size) continue;
+            mask_t pm = 0;
+            for (mask_t c = cand; c; c &= c - 1) {
+                const int b = MO::lo(c);
+                if (pass(b, j)) pm |= MO::bit(b);
+                else if (mono_le) break;  // the passing b's are a prefix
+            }
+            if (!pm) continue;
+            consider(1 + MO::popc(pm), MO::hi(pm), MO::bit(j) | pm, MO::bit(j) | pm, true);
         }
+        if (best_size == 0) return false;
+        out = best_out;
+        return true;
     }
-    // P(i): only if it can still reach the best size
-    for (mask_t r = am; r; r &= r - 1) {
-        const int j = MO::lo(r);
-        if (mono_le && j != a_first) break;
-        const mask_t cand = bm & MO::above(j);
-        if (1 + MO::popc(cand) < best_size) continue;
-        mask_t pm = 0;
-        for (mask_t c = cand; c; c &= c - 1) {
-            const int b = MO::lo(c);
-            if (pass(b, j)) pm |= MO::bit(b);
-            else if (mono_le) break;  // the passing b's are a prefix
-        }
-        if (!pm) continue;
-        consider(1 + MO::popc(pm), MO::hi(pm), MO::bit(j) | pm, MO::bit(j) | pm, true);
-    }
-    if (best_size == 0) return false;
-    out = best_out;
-    return true;
+};
+
+template <int W, int NPMAX>
+SIESTA_HD bool fk2_eval_n(const DevNfa& nfa, const TraceEvents& ev, typename MaskOps<W>::T& out) {
+    Fk2Eval<W, NPMAX> f;
+    f.init(nfa, ev.evt_pos, ev.ts != nullptr);
+    for (int j = 0; j < ev.n; ++j) f.on_event(j, ev.word(j), ev.src(j), ev.ts ? ev.ts[j * ev.ts_stride] : 0);
+    return f.finish(ev, out);
+}
+template <int W>
+SIESTA_HD bool fk2_eval(const DevNfa& nfa, const TraceEvents& ev, typename MaskOps<W>::T& out) {
+    if (nfa.n_preds[1] <= 1) return fk2_eval_n<W, 1>(nfa, ev, out);
+    return fk2_eval_n<W, SIESTA_MAX_PREDS>(nfa, ev, out);
 }
 
 // ------------------------------------------------------------------------------------------------- class NK
@@ -241,20 +262,26 @@ SIESTA_HD typename MaskOps<W>::T nk_walk(const DevNfa& nfa, const TraceEvents& e
 
 // aux: scratch of NE masks (one per possible start), element i at aux[i * aux_stride]; only used when return_all.
 // sel[0..nsel) = the selected occurrences (Occurrences.clearOccurrences); n_emitted = engine matches.
+// T[k] = events whose type belongs to state k (T[SIESTA_MAX_STATES] stays 0)
 template <int W>
-SIESTA_HD bool nk_eval(const DevNfa& nfa, const TraceEvents& ev, bool return_all, bool by_pos, typename MaskOps<W>::T* aux,
-                       int aux_stride, typename MaskOps<W>::T* sel, int& nsel, unsigned& n_emitted) {
+struct NkMasks {
+    typename MaskOps<W>::T T[SIESTA_MAX_STATES + 1];
+    SIESTA_HD __forceinline__ void init() {
+#pragma unroll
+        for (int k = 0; k <= SIESTA_MAX_STATES; ++k) T[k] = 0;
+    }
+    SIESTA_HD __forceinline__ void on_event(int j, uint32_t w) {
+#pragma unroll
+        for (int k = 0; k < SIESTA_MAX_STATES; ++k) T[k] |= (typename MaskOps<W>::T)((w >> k) & 1u) << j;
+    }
+};
+
+template <int W>
+SIESTA_HD bool nk_eval(const DevNfa& nfa, const TraceEvents& ev, const typename MaskOps<W>::T* T, bool return_all, bool by_pos,
+                       typename MaskOps<W>::T* aux, int aux_stride, typename MaskOps<W>::T* sel, int& nsel, unsigned& n_emitted) {
     typedef MaskX<W> MO;
     typedef typename MO::T mask_t;
     const int S = nfa.n_states;
-    mask_t T[SIESTA_MAX_STATES + 1];
-#pragma unroll
-    for (int k = 0; k <= SIESTA_MAX_STATES; ++k) T[k] = 0;
-    for (int j = 0; j < ev.n; ++j) {
-        const uint32_t w = ev.word(j);
-#pragma unroll
-        for (int k = 0; k < SIESTA_MAX_STATES; ++k) T[k] |= (mask_t)((w >> k) & 1u) << j;
-    }
     nsel = 0;
     n_emitted = 0;
     // every state's types must occur at all (cheap reject of most traces)

@@ -46,7 +46,10 @@ static int run_one(const DevNfa& dn, const std::vector<uint32_t>& meta, const st
     if (dn.fast_class == FAST_NK) {
         std::vector<typename MaskOps<W>::T> aux(NE), s(NE);
         int nsel = 0;
-        if (!nk_eval<W>(dn, ev, (flags & SIESTA_F_RETURN_ALL) != 0, evt_pos, aux.data(), 1, s.data(), nsel, *n_emitted)) return 0;
+        NkMasks<W> nm;
+        nm.init();
+        for (int j = 0; j < ev.n; ++j) nm.on_event(j, ev.word(j));
+        if (!nk_eval<W>(dn, ev, nm.T, (flags & SIESTA_F_RETURN_ALL) != 0, evt_pos, aux.data(), 1, s.data(), nsel, *n_emitted)) return 0;
         sel.assign(s.begin(), s.begin() + nsel);
         return 1;
     }
