@@ -91,34 +91,53 @@ def make_nfa(states):
     return nfa
 
 
-def _arr(ptr, n, dtype):
+def _arr(ptr, n, dtype, copy=True):
     import numpy as np
     if n == 0 or not ptr:
         return np.zeros(0, dtype=dtype)
-    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+    a = np.ctypeslib.as_array(ptr, shape=(n,))
+    return a.astype(dtype, copy=True) if copy else a
 
 
 class MatchResult:
     """Host copy of a siesta_matches (CSR of selected occurrences per matching trace)."""
 
     __slots__ = ("n_traces", "n_occurrences", "n_events", "n_matches_emitted", "n_ref_errors", "trace_idx",
-                 "occ_off", "ev_off", "ev_pos", "ev_rank", "ev_act", "ev_ts_ms", "err_trace_idx", "kernel_ms", "detect_ms")
+                 "occ_off", "ev_off", "ev_pos", "ev_rank", "ev_act", "ev_ts_ms", "err_trace_idx", "kernel_ms", "detect_ms",
+                 "_free")
+
+    def close(self):
+        """Release the library-owned block behind zero-copy views (from_struct(copy=False)); the arrays die with it."""
+        f = getattr(self, "_free", None)
+        if f is not None:
+            self._free = None
+            for k in ("trace_idx", "occ_off", "ev_off", "ev_pos", "ev_rank", "ev_act", "ev_ts_ms", "err_trace_idx"):
+                setattr(self, k, None)
+            f()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     @classmethod
-    def from_struct(cls, m):
+    def from_struct(cls, m, copy=True, free=None):
+        """copy=False: the arrays are views of the library's (pinned) result block, which `free` releases on close()."""
         import numpy as np
         r = cls()
+        r._free = None if copy else free
         r.n_traces, r.n_occurrences, r.n_events = m.n_traces, m.n_occurrences, m.n_events
         r.n_matches_emitted, r.n_ref_errors, r.kernel_ms = m.n_matches_emitted, m.n_ref_errors, m.kernel_ms
         r.detect_ms = m.detect_ms
-        r.trace_idx = _arr(m.trace_idx, m.n_traces, np.int64)
-        r.occ_off = _arr(m.occ_off, m.n_traces + 1, np.int64)
-        r.ev_off = _arr(m.ev_off, m.n_occurrences + 1, np.int64)
-        r.ev_pos = _arr(m.ev_pos, m.n_events, np.int32) if m.ev_pos else None
-        r.ev_rank = _arr(m.ev_rank, m.n_events, np.int32) if m.ev_rank else None
-        r.ev_act = _arr(m.ev_act, m.n_events, np.int32) if m.ev_act else None
-        r.ev_ts_ms = _arr(m.ev_ts_ms, m.n_events, np.int64) if m.ev_ts_ms else None
-        r.err_trace_idx = _arr(m.err_trace_idx, m.n_ref_errors, np.int64)
+        r.trace_idx = _arr(m.trace_idx, m.n_traces, np.int64, copy)
+        r.occ_off = _arr(m.occ_off, m.n_traces + 1, np.int64, copy)
+        r.ev_off = _arr(m.ev_off, m.n_occurrences + 1, np.int64, copy)
+        r.ev_pos = _arr(m.ev_pos, m.n_events, np.int32, copy) if m.ev_pos else None
+        r.ev_rank = _arr(m.ev_rank, m.n_events, np.int32, copy) if m.ev_rank else None
+        r.ev_act = _arr(m.ev_act, m.n_events, np.int32, copy) if m.ev_act else None
+        r.ev_ts_ms = _arr(m.ev_ts_ms, m.n_events, np.int64, copy) if m.ev_ts_ms else None
+        r.err_trace_idx = _arr(m.err_trace_idx, m.n_ref_errors, np.int64, copy)
         return r
 
     def occurrences_of(self, i):

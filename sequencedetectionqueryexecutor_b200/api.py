@@ -38,14 +38,17 @@ class Context:
         return EventLog(self, None, None, None, n_activities, device_tensors=(d_trace_off, d_act, d_ts_ms),
                         max_trace_len=max_trace_len)
 
-    def evaluate_events(self, trace_off, act, ts_ms, n_activities, nfa, flags=0):
-        """Literal SaseConnector.evaluate: events travel host -> device inside the call."""
+    def evaluate_events(self, trace_off, act, ts_ms, n_activities, nfa, flags=0, copy=True):
+        """Literal SaseConnector.evaluate: events travel host -> device inside the call (streamed in chunks).
+        copy=False returns zero-copy views of the library's pinned result block; call .close() on the result."""
         trace_off = np.ascontiguousarray(trace_off, dtype=np.int64)
         act = np.ascontiguousarray(act, dtype=np.int32)
         ts_ms = np.ascontiguousarray(ts_ms, dtype=np.int64)
         out = C.POINTER(_abi.Matches)()
         check(lib().siesta_evaluate_events(self._h, _ptr(trace_off), _ptr(act), _ptr(ts_ms), len(trace_off) - 1, len(act),
                                            n_activities, C.byref(nfa), flags, C.byref(out)))
+        if not copy:
+            return _abi.MatchResult.from_struct(out.contents, copy=False, free=lambda: lib().siesta_matches_free(out))
         res = _abi.MatchResult.from_struct(out.contents)
         lib().siesta_matches_free(out)
         return res

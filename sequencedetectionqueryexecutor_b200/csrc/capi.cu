@@ -1,4 +1,5 @@
 // capi.cu — context, log residency and the host-buffer entry points of include/siesta_gpu.h.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -58,6 +59,7 @@ extern "C" void siesta_shutdown(siesta_ctx* ctx) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamDestroy(c->stream);
+    for (HostBlock& b : c->arena) cudaFreeHost(b.p);  // result objects must have been freed before the ctx
     delete c;
 }
 
@@ -70,26 +72,30 @@ __global__ void act_range_kernel(const int32_t* act, int64_t n, int32_t n_act, i
     if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(bad, 1);
 }
 
-static int validate_act(Log* L) {
-    L->act_valid = false;
-    if (L->n_events == 0) {
-        L->act_valid = true;
-        return SIESTA_OK;
-    }
+namespace siesta {
+// Marks L->act_valid = false if events [first_event, first_event + n_events) hold an id outside [0, n_activities).
+int validate_act_range(Log* L, int64_t first_event, int64_t n_events, cudaStream_t stream) {
+    if (n_events == 0) return SIESTA_OK;
     Ctx* c = L->ctx;
     int* d_bad = nullptr;
-    SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_bad, sizeof(int), c->stream));
-    SIESTA_CUDA_OK(cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream));
-    const int64_t want = (L->n_events + 255) / 256;
+    SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_bad, sizeof(int), stream));
+    SIESTA_CUDA_OK(cudaMemsetAsync(d_bad, 0, sizeof(int), stream));
+    const int64_t want = (n_events + 255) / 256;
     const int grid = (int)(want < (int64_t)c->sm_count * 16 ? want : (int64_t)c->sm_count * 16);
-    act_range_kernel<<<grid, 256, 0, c->stream>>>(L->d_act, L->n_events, L->n_activities, d_bad);
+    act_range_kernel<<<grid, 256, 0, stream>>>(L->d_act + first_event, n_events, L->n_activities, d_bad);
     SIESTA_LAUNCHED();
     int bad = 1;
-    SIESTA_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    SIESTA_CUDA_OK(cudaStreamSynchronize(c->stream));
-    cudaFreeAsync(d_bad, c->stream);
-    L->act_valid = bad == 0;
+    SIESTA_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+    cudaFreeAsync(d_bad, stream);
+    if (bad) L->act_valid = false;
     return SIESTA_OK;
+}
+}  // namespace siesta
+
+static int validate_act(Log* L) {
+    L->act_valid = true;
+    return validate_act_range(L, 0, L->n_events, L->ctx->stream);
 }
 
 static int check_csr(const int64_t* trace_off, int64_t n_traces, int64_t n_events, int32_t* max_len) {
@@ -199,25 +205,162 @@ extern "C" void siesta_log_free(siesta_log* log) {
 extern "C" int64_t siesta_log_n_traces(const siesta_log* log) { return log ? reinterpret_cast<const Log*>(log)->n_traces : 0; }
 extern "C" int64_t siesta_log_n_events(const siesta_log* log) { return log ? reinterpret_cast<const Log*>(log)->n_events : 0; }
 
-template <class T>
-static int fetch(T** dst, const void* d_src, int64_t n, cudaStream_t s) {
-    *dst = (T*)std::malloc(sizeof(T) * (size_t)(n > 0 ? n : 1));
-    if (!*dst) return SIESTA_E_NOMEM;
-    if (n > 0 && d_src) SIESTA_CUDA_OK(cudaMemcpyAsync(*dst, d_src, sizeof(T) * (size_t)n, cudaMemcpyDeviceToHost, s));
+// ------------------------------------------------------------------------------------------ host result objects
+// One block per result: [ResultHeader][siesta_matches][arrays ...].  Large results live in pinned memory from the
+// ctx arena (device -> host copies run at PCIe speed and the block is reused by the next request).
+namespace {
+constexpr uint64_t RESULT_MAGIC = 0x5349455354414d31ull;  // "SIESTAM1"
+constexpr size_t PIN_THRESHOLD = 256 * 1024;
+constexpr size_t ARENA_KEEP_BYTES = (size_t)4 << 30;
+
+struct ResultHeader {
+    uint64_t magic;
+    Ctx* ctx;       // arena owner, or nullptr for a malloc block
+    void* base;
+    uint64_t pad[5];
+};
+static_assert(sizeof(ResultHeader) == 64, "ResultHeader is one cache line");
+
+void* arena_alloc(Ctx* c, size_t bytes) {
+    size_t want = (size_t)1 << 20;
+    while (want < bytes) want <<= 1;
+    {
+        std::lock_guard<std::mutex> g(c->arena_mu);
+        for (HostBlock& b : c->arena)
+            if (!b.used && b.size >= bytes && b.size <= 4 * want) {
+                b.used = true;
+                return b.p;
+            }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> g(c->arena_mu);
+    c->arena.push_back(HostBlock{p, want, true});
+    return p;
+}
+
+void arena_free(Ctx* c, void* p) {
+    std::lock_guard<std::mutex> g(c->arena_mu);
+    size_t kept = 0;
+    for (HostBlock& b : c->arena) kept += b.used ? 0 : b.size;
+    for (size_t i = 0; i < c->arena.size(); ++i)
+        if (c->arena[i].p == p) {
+            if (kept + c->arena[i].size > ARENA_KEEP_BYTES) {
+                cudaFreeHost(p);
+                c->arena.erase(c->arena.begin() + i);
+            } else {
+                c->arena[i].used = false;
+            }
+            return;
+        }
+}
+
+inline size_t align64(size_t x) { return (x + 63) & ~(size_t)63; }
+
+// Device results of one or more consecutive chunks (already rebased: see RebaseOffsets) -> one host siesta_matches.
+int assemble_matches(Ctx* c, std::vector<siesta_dev_matches>& parts, uint32_t flags, cudaStream_t stream, siesta_matches** out) {
+    int64_t n_tr = 0, n_occ = 0, n_ev = 0, n_err = 0, n_emit = 0;
+    double k_ms = 0, d_ms = 0;
+    bool counted = true;
+    for (const siesta_dev_matches& p : parts) {
+        n_tr += p.n_traces;
+        n_occ += p.n_occurrences;
+        n_ev += p.n_events;
+        n_err += p.n_ref_errors;
+        if (p.n_matches_emitted < 0) counted = false;
+        else n_emit += p.n_matches_emitted;
+        k_ms += p.kernel_ms;
+        d_ms += p.detect_ms;
+    }
+    const bool all_cols = !(flags & SIESTA_F_NO_EVENT_COLUMNS);
+    size_t off = sizeof(ResultHeader) + align64(sizeof(siesta_matches));
+    const size_t o_trace = off; off += align64((size_t)(n_tr ? n_tr : 1) * 8);
+    const size_t o_occ = off;   off += align64((size_t)(n_tr + 1) * 8);
+    const size_t o_evoff = off; off += align64((size_t)(n_occ + 1) * 8);
+    const size_t o_pos = off;   off += align64((size_t)(n_ev ? n_ev : 1) * 4);
+    const size_t o_err = off;   off += align64((size_t)(n_err ? n_err : 1) * 8);
+    size_t o_rank = 0, o_act = 0, o_ts = 0;
+    if (all_cols) {
+        o_rank = off; off += align64((size_t)(n_ev ? n_ev : 1) * 4);
+        o_act = off;  off += align64((size_t)(n_ev ? n_ev : 1) * 4);
+        o_ts = off;   off += align64((size_t)(n_ev ? n_ev : 1) * 8);
+    }
+    char* base = nullptr;
+    Ctx* owner = nullptr;
+    if (off >= PIN_THRESHOLD) {
+        base = (char*)arena_alloc(c, off);
+        if (base) owner = c;
+    }
+    if (!base) base = (char*)std::malloc(off);
+    if (!base) return SIESTA_E_NOMEM;
+    ResultHeader* h = reinterpret_cast<ResultHeader*>(base);
+    h->magic = RESULT_MAGIC;
+    h->ctx = owner;
+    h->base = base;
+    siesta_matches* m = reinterpret_cast<siesta_matches*>(base + sizeof(ResultHeader));
+    std::memset(m, 0, sizeof(*m));
+    m->n_traces = n_tr;
+    m->n_occurrences = n_occ;
+    m->n_events = n_ev;
+    m->n_matches_emitted = counted ? n_emit : -1;
+    m->n_ref_errors = n_err;
+    m->kernel_ms = k_ms;
+    m->detect_ms = d_ms;
+    m->trace_idx = reinterpret_cast<int64_t*>(base + o_trace);
+    m->occ_off = reinterpret_cast<int64_t*>(base + o_occ);
+    m->ev_off = reinterpret_cast<int64_t*>(base + o_evoff);
+    m->ev_pos = reinterpret_cast<int32_t*>(base + o_pos);
+    m->err_trace_idx = reinterpret_cast<int64_t*>(base + o_err);
+    if (all_cols) {
+        m->ev_rank = reinterpret_cast<int32_t*>(base + o_rank);
+        m->ev_act = reinterpret_cast<int32_t*>(base + o_act);
+        m->ev_ts_ms = reinterpret_cast<int64_t*>(base + o_ts);
+    }
+    m->occ_off[0] = 0;
+    m->ev_off[0] = 0;
+    int64_t a_tr = 0, a_occ = 0, a_ev = 0, a_err = 0;
+    cudaError_t e = cudaSuccess;
+    auto d2h = [&](void* dst, const void* src, size_t bytes) {
+        if (bytes && src && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream);
+    };
+    for (const siesta_dev_matches& p : parts) {
+        d2h(m->trace_idx + a_tr, p.d_trace_idx, (size_t)p.n_traces * 8);
+        // each part carries its own tail entry; the next part overwrites it with the same value
+        d2h(m->occ_off + a_tr, p.d_occ_off, (size_t)(p.n_traces + 1) * 8);
+        d2h(m->ev_off + a_occ, p.d_ev_off, (size_t)(p.n_occurrences + 1) * 8);
+        d2h(m->ev_pos + a_ev, p.d_ev_pos, (size_t)p.n_events * 4);
+        d2h(m->err_trace_idx + a_err, p.d_err_trace_idx, (size_t)p.n_ref_errors * 8);
+        if (all_cols) {
+            d2h(m->ev_rank + a_ev, p.d_ev_rank, (size_t)p.n_events * 4);
+            d2h(m->ev_act + a_ev, p.d_ev_act, (size_t)p.n_events * 4);
+            d2h(m->ev_ts_ms + a_ev, p.d_ev_ts_ms, (size_t)p.n_events * 8);
+        }
+        a_tr += p.n_traces;
+        a_occ += p.n_occurrences;
+        a_ev += p.n_events;
+        a_err += p.n_ref_errors;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        set_error(std::string("device -> host copy of the occurrences: ") + cudaGetErrorString(e));
+        siesta_matches_free(m);
+        return SIESTA_E_CUDA;
+    }
+    *out = m;
     return SIESTA_OK;
 }
+}  // namespace
 
 extern "C" void siesta_matches_free(siesta_matches* m) {
     if (!m) return;
-    std::free(m->trace_idx);
-    std::free(m->occ_off);
-    std::free(m->ev_off);
-    std::free(m->ev_pos);
-    std::free(m->ev_rank);
-    std::free(m->ev_act);
-    std::free(m->ev_ts_ms);
-    std::free(m->err_trace_idx);
-    std::free(m);
+    ResultHeader* h = reinterpret_cast<ResultHeader*>(reinterpret_cast<char*>(m) - sizeof(ResultHeader));
+    if (h->magic != RESULT_MAGIC) return;  // not ours (or freed twice)
+    h->magic = 0;
+    if (h->ctx) arena_free(h->ctx, h->base);
+    else std::free(h->base);
 }
 
 extern "C" int siesta_detect(siesta_log* log, const siesta_nfa* nfa, const int64_t* cand, int64_t n_cand, uint32_t flags,
@@ -233,9 +376,8 @@ extern "C" int siesta_detect(siesta_log* log, const siesta_nfa* nfa, const int64
     SIESTA_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     int64_t* d_cand = nullptr;
     int rc = SIESTA_OK;
-    siesta_dev_matches dm;
-    std::memset(&dm, 0, sizeof(dm));
-    siesta_matches* m = nullptr;
+    std::vector<siesta_dev_matches> parts(1);
+    std::memset(&parts[0], 0, sizeof(siesta_dev_matches));
     do {
         if (cand) {
             for (int64_t i = 0; i < n_cand; ++i)
@@ -245,7 +387,7 @@ extern "C" int siesta_detect(siesta_log* log, const siesta_nfa* nfa, const int64
                     break;
                 }
             if (rc) break;
-            if (cudaMalloc((void**)&d_cand, (size_t)(n_cand > 0 ? n_cand : 1) * 8) != cudaSuccess) {
+            if (cudaMallocAsync((void**)&d_cand, (size_t)(n_cand > 0 ? n_cand : 1) * 8, stream) != cudaSuccess) {
                 set_error("siesta_detect: cudaMalloc(candidates)");
                 rc = SIESTA_E_NOMEM;
                 break;
@@ -256,51 +398,123 @@ extern "C" int siesta_detect(siesta_log* log, const siesta_nfa* nfa, const int64
                 break;
             }
         }
-        rc = siesta_detect_device(log, nfa, d_cand, n_cand, flags, stream, &dm);
+        rc = siesta_detect_device(log, nfa, d_cand, n_cand, flags, stream, &parts[0]);
         if (rc) break;
-        m = (siesta_matches*)std::calloc(1, sizeof(siesta_matches));
-        m->n_traces = dm.n_traces;
-        m->n_occurrences = dm.n_occurrences;
-        m->n_events = dm.n_events;
-        m->n_matches_emitted = dm.n_matches_emitted;
-        m->n_ref_errors = dm.n_ref_errors;
-        m->kernel_ms = dm.kernel_ms;
-        m->detect_ms = dm.detect_ms;
-        if ((rc = fetch(&m->trace_idx, dm.d_trace_idx, dm.n_traces, stream)) ||
-            (rc = fetch(&m->occ_off, dm.d_occ_off, dm.n_traces + 1, stream)) ||
-            (rc = fetch(&m->ev_off, dm.d_ev_off, dm.n_occurrences + 1, stream)) ||
-            (rc = fetch(&m->ev_pos, dm.d_ev_pos, dm.n_events, stream)) ||
-            (rc = fetch(&m->err_trace_idx, dm.d_err_trace_idx, dm.n_ref_errors, stream)))
-            break;
-        if (!(flags & SIESTA_F_NO_EVENT_COLUMNS)) {
-            if ((rc = fetch(&m->ev_rank, dm.d_ev_rank, dm.n_events, stream)) ||
-                (rc = fetch(&m->ev_act, dm.d_ev_act, dm.n_events, stream)) ||
-                (rc = fetch(&m->ev_ts_ms, dm.d_ev_ts_ms, dm.n_events, stream)))
-                break;
-        }
-        if (cudaStreamSynchronize(stream) != cudaSuccess) {
-            set_error("siesta_detect: D2H");
-            rc = SIESTA_E_CUDA;
-        }
+        rc = assemble_matches(L->ctx, parts, flags, stream, out);
     } while (0);
-    siesta_dev_matches_free(&dm);
-    if (d_cand) cudaFree(d_cand);
+    siesta_dev_matches_free(&parts[0]);
+    if (d_cand) cudaFreeAsync(d_cand, stream);
+    cudaStreamSynchronize(stream);
     cudaStreamDestroy(stream);
-    if (rc) {
-        siesta_matches_free(m);
-        return rc;
-    }
-    *out = m;
-    return SIESTA_OK;
+    return rc;
 }
 
+// Literal SaseConnector.evaluate signature: the request's events arrive in host buffers.  The log is cut into chunks
+// of whole traces; chunk c + 1 (and c + 2) travel host -> device on a copy stream while chunk c is verified, so the
+// call runs at the speed of the host link.  Chunk results are rebased on the device (RebaseOffsets) and land in one
+// host block.
 extern "C" int siesta_evaluate_events(siesta_ctx* ctx, const int64_t* trace_off, const int32_t* act, const int64_t* ts_ms,
                                       int64_t n_traces, int64_t n_events, int32_t n_activities, const siesta_nfa* nfa,
                                       uint32_t flags, siesta_matches** out) {
-    siesta_log* log = nullptr;
-    int rc = siesta_log_load(ctx, trace_off, act, ts_ms, n_traces, n_events, n_activities, &log);
+    if (!ctx || !trace_off || (!act && n_events) || (!ts_ms && n_events) || !nfa || !out || n_activities < 0) {
+        set_error("siesta_evaluate_events: null argument");
+        return SIESTA_E_INVALID;
+    }
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    int32_t max_len = 0;
+    int rc = check_csr(trace_off, n_traces, n_events, &max_len);
     if (rc) return rc;
-    rc = siesta_detect(log, nfa, nullptr, 0, flags, out);
-    siesta_log_free(log);
+    {
+        DevNfa dn;  // fail on a malformed NFA before anything is copied
+        if ((rc = validate_nfa(nfa, flags, &dn))) return rc;
+    }
+    SIESTA_CUDA_OK(cudaSetDevice(c->device));
+
+    // chunk boundaries: whole traces, about CHUNK_EVENTS events each
+    int64_t CHUNK_EVENTS = 4 << 20;
+    if (const char* env = std::getenv("SIESTA_CHUNK_EVENTS")) {  // test aid: force many small chunks
+        const long long v = std::atoll(env);
+        if (v > 0) CHUNK_EVENTS = v;
+    }
+    std::vector<int64_t> cut{0};
+    while (cut.back() < n_traces) {
+        const int64_t t0 = cut.back();
+        const int64_t* lim = std::upper_bound(trace_off + t0 + 1, trace_off + n_traces + 1, trace_off[t0] + CHUNK_EVENTS);
+        int64_t t1 = (int64_t)(lim - trace_off) - 1;   // last trace end <= budget
+        if (t1 <= t0) t1 = t0 + 1;                      // a single trace longer than the budget
+        cut.push_back(t1);
+    }
+    const int n_chunks = (int)cut.size() - 1;
+
+    cudaStream_t s_copy = nullptr, s_run = nullptr;
+    SIESTA_CUDA_OK(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+    SIESTA_CUDA_OK(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking));
+    int64_t* d_off = nullptr;
+    int32_t* d_act = nullptr;
+    int64_t* d_ts = nullptr;
+    std::vector<cudaEvent_t> ready((size_t)n_chunks, nullptr);
+    std::vector<siesta_dev_matches> parts;
+    parts.reserve((size_t)n_chunks);
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t x) {
+        if (e == cudaSuccess) e = x;
+        return e == cudaSuccess;
+    };
+    const size_t ne = (size_t)(n_events ? n_events : 1);
+    ok(cudaMallocAsync((void**)&d_off, (size_t)(n_traces + 1) * 8, s_copy));
+    ok(cudaMallocAsync((void**)&d_act, ne * 4 + 32, s_copy));
+    ok(cudaMallocAsync((void**)&d_ts, ne * 8 + 32, s_copy));
+    int enq = 0;
+    auto enqueue_copy = [&](int k) {
+        const int64_t t0 = cut[k], t1 = cut[k + 1], e0 = trace_off[t0], e1 = trace_off[t1];
+        ok(cudaMemcpyAsync(d_off + t0, trace_off + t0, (size_t)(t1 - t0 + 1) * 8, cudaMemcpyHostToDevice, s_copy));
+        if (e1 > e0) {
+            ok(cudaMemcpyAsync(d_act + e0, act + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, s_copy));
+            ok(cudaMemcpyAsync(d_ts + e0, ts_ms + e0, (size_t)(e1 - e0) * 8, cudaMemcpyHostToDevice, s_copy));
+        }
+        ok(cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming));
+        ok(cudaEventRecord(ready[k], s_copy));
+    };
+    RebaseOffsets base{0, 0, 0};
+    for (int k = 0; k < n_chunks && e == cudaSuccess && rc == SIESTA_OK; ++k) {
+        while (enq < n_chunks && enq <= k + 2) enqueue_copy(enq++);
+        if (e != cudaSuccess) break;
+        ok(cudaStreamWaitEvent(s_run, ready[k], 0));
+        Log view;
+        view.ctx = c;
+        view.d_trace_off = d_off + cut[k];  // offsets are global event indices: act / ts_ms stay whole
+        view.d_act = d_act;
+        view.d_ts_ms = d_ts;
+        view.n_traces = cut[k + 1] - cut[k];
+        view.n_events = n_events;
+        view.n_activities = n_activities;
+        view.max_trace_len = max_len;
+        view.owns = false;
+        view.act_valid = true;
+        if ((rc = validate_act_range(&view, trace_off[cut[k]], trace_off[cut[k + 1]] - trace_off[cut[k]], s_run))) break;
+        siesta_dev_matches dm;
+        base.trace = cut[k];
+        rc = detect_device_impl(&view, nfa, nullptr, 0, flags, s_run, base, &dm);
+        if (rc) break;
+        parts.push_back(dm);
+        base.occ += dm.n_occurrences;
+        base.ev += dm.n_events;
+    }
+    if (e != cudaSuccess && rc == SIESTA_OK) {
+        set_error(std::string("siesta_evaluate_events: ") + cudaGetErrorString(e));
+        rc = SIESTA_E_CUDA;
+    }
+    if (rc == SIESTA_OK) rc = assemble_matches(c, parts, flags, s_run, out);
+    for (siesta_dev_matches& p : parts) siesta_dev_matches_free(&p);
+    cudaStreamSynchronize(s_copy);
+    cudaStreamSynchronize(s_run);
+    if (d_off) cudaFreeAsync(d_off, s_run);
+    if (d_act) cudaFreeAsync(d_act, s_run);
+    if (d_ts) cudaFreeAsync(d_ts, s_run);
+    for (cudaEvent_t ev : ready)
+        if (ev) cudaEventDestroy(ev);
+    cudaStreamSynchronize(s_run);
+    cudaStreamDestroy(s_copy);
+    cudaStreamDestroy(s_run);
     return rc;
 }

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -25,10 +26,20 @@ extern std::atomic<long long> g_kernel_launches;
 
 #define SIESTA_LAUNCHED() (::siesta::g_kernel_launches.fetch_add(1, std::memory_order_relaxed))
 
+// Pinned host blocks that result objects (siesta_matches) are carved from; blocks return here on siesta_matches_free
+// and are reused by later calls, so a steady-state request pays no cudaHostAlloc.
+struct HostBlock {
+    void* p;
+    size_t size;
+    bool used;
+};
+
 struct Ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    std::mutex arena_mu;
+    std::vector<HostBlock> arena;
 };
 
 // CSR event log resident in HBM.
@@ -64,6 +75,14 @@ struct DevNfa {
     uint8_t p_ref[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];
     int64_t p_c[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];
 };
+
+// Chunked evaluation (siesta_evaluate_events): where a chunk's results sit in the whole result.
+struct RebaseOffsets {
+    int64_t trace, occ, ev;
+};
+int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand, uint32_t flags, cudaStream_t stream,
+                       RebaseOffsets base, siesta_dev_matches* out);
+int validate_act_range(Log* L, int64_t first_event, int64_t n_events, cudaStream_t stream);
 
 int validate_nfa(const siesta_nfa* nfa, uint32_t flags, DevNfa* out);
 void build_lut(const siesta_nfa* nfa, const DevNfa& dn, int32_t n_activities, uint32_t flags, std::vector<uint16_t>& lut,

@@ -516,6 +516,7 @@ struct GatherParams {
     const int32_t* s_ev_rank;
     const int32_t* s_ev_act;
     const int64_t* s_ev_ts;
+    RebaseOffsets base;  // added to trace_idx / occ_off / ev_off (chunked evaluation: the chunk's place in the whole result)
     int64_t* trace_idx;
     int64_t* occ_off;
     int64_t* ev_off;
@@ -620,13 +621,13 @@ __global__ void __launch_bounds__(GT) gather_kernel(const __grid_constant__ Gath
     const int64_t ep = (int64_t)(G.blk[2 * G.n_blk + blockIdx.x] + ex[2]);
     long long se = 0;
     if (nocc) {
-        G.trace_idx[tp] = G.cand ? G.cand[i] : i;
-        G.occ_off[tp] = op;
+        G.trace_idx[tp] = (G.cand ? G.cand[i] : i) + G.base.trace;
+        G.occ_off[tp] = op + G.base.occ;
         se = G.d_stage[i];
         const int64_t so = G.d_stage_occ[i];
         int64_t e = ep;
         for (uint32_t o = 0; o < nocc; ++o) {
-            G.ev_off[op + o] = e;
+            G.ev_off[op + o] = e + G.base.ev;
             e += G.s_occ_nev[so + o];
         }
     }
@@ -676,9 +677,9 @@ __global__ void __launch_bounds__(GT) gather_kernel(const __grid_constant__ Gath
     }
 }
 
-__global__ void set_tail_kernel(int64_t* occ_off, int64_t n_tr, int64_t n_occ, int64_t* ev_off, int64_t n_ev) {
-    occ_off[n_tr] = n_occ;
-    ev_off[n_occ] = n_ev;
+__global__ void set_tail_kernel(int64_t* occ_off, int64_t n_tr, int64_t n_occ, int64_t* ev_off, int64_t n_ev, RebaseOffsets base) {
+    occ_off[n_tr] = n_occ + base.occ;
+    ev_off[n_occ] = n_ev + base.ev;
 }
 
 // ---------------------------------------------------------------------------------- host side
@@ -746,8 +747,10 @@ int launch_detect(const Ctx* ctx, cudaStream_t stream, DetectParams P, const Dev
     return SIESTA_OK;
 }
 
+}  // namespace
+
 int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand, uint32_t flags,
-                       cudaStream_t stream, siesta_dev_matches* out) {
+                       cudaStream_t stream, RebaseOffsets base, siesta_dev_matches* out) {
     std::memset(out, 0, sizeof(*out));
     DevNfa dn;
     int rc = validate_nfa(nfa, flags, &dn);
@@ -895,6 +898,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
         GatherParams G;
         std::memset(&G, 0, sizeof(G));
         G.cand = d_cand;
+        G.base = base;
         G.n = n;
         G.d_nocc = P.d_nocc;
         G.d_nev = P.d_nev;
@@ -924,7 +928,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
         SIESTA_LAUNCHED();
         SIESTA_CUDA_OK(cudaGetLastError());
     }
-    set_tail_kernel<<<1, 1, 0, stream>>>(f_occ_off.as<int64_t>(), n_tr, n_occ, f_ev_off.as<int64_t>(), n_ev);
+    set_tail_kernel<<<1, 1, 0, stream>>>(f_occ_off.as<int64_t>(), n_tr, n_occ, f_ev_off.as<int64_t>(), n_ev, base);
     SIESTA_LAUNCHED();
     SIESTA_CUDA_OK(cudaEventRecord(ev1, stream));
     if (n_err > 0) {  // order the (rare) error list
@@ -932,6 +936,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
         SIESTA_CUDA_OK(cudaMemcpyAsync(h.data(), b_err.p, (size_t)n_err * 8, cudaMemcpyDeviceToHost, stream));
         SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
         std::sort(h.begin(), h.end());
+        for (int64_t& x : h) x += base.trace;
         SIESTA_CUDA_OK(cudaMemcpyAsync(f_err.p, h.data(), (size_t)n_err * 8, cudaMemcpyHostToDevice, stream));
     }
     SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
@@ -965,7 +970,6 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     return SIESTA_OK;
 }
 
-}  // namespace
 }  // namespace siesta
 
 extern "C" int siesta_detect_device(siesta_log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand,
@@ -975,7 +979,7 @@ extern "C" int siesta_detect_device(siesta_log* log, const siesta_nfa* nfa, cons
         return SIESTA_E_INVALID;
     }
     return siesta::detect_device_impl(reinterpret_cast<siesta::Log*>(log), nfa, d_cand, n_cand, flags,
-                                      reinterpret_cast<cudaStream_t>(stream), out);
+                                      reinterpret_cast<cudaStream_t>(stream), siesta::RebaseOffsets{0, 0, 0}, out);
 }
 
 extern "C" void siesta_dev_matches_free(siesta_dev_matches* m) {

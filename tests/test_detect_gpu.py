@@ -203,3 +203,58 @@ def test_device_result_views_and_single_rank_gather(ctx):
         assert np.array_equal(t[k].cpu().numpy(), getattr(host, k)), k
     dm.close()
     log.close()
+
+
+def test_evaluate_events_streams_in_chunks(ctx, monkeypatch):
+    """siesta_evaluate_events cuts the request into chunks of whole traces (copy of chunk c+1 overlaps the scan of
+    chunk c) and rebases the chunk results on the device: the joined result must equal the oracle's, including the
+    reference-throw list and empty / ragged traces at chunk borders."""
+    monkeypatch.setenv("SIESTA_CHUNK_EVENTS", "3000")
+    off, act, ts = gen.make_log(3000, 0, 60, 6, seed=31, jitter_ms=True)
+    cases = [
+        ([dict(kind=P_, types=[0]), dict(kind=S_, types=[1], preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 600)])], 0),
+        ([dict(kind=N_, types=[0]), dict(kind=O_, types=[1, 2]), dict(kind=X_, types=[3]), dict(kind=N_, types=[4])], abi.F_RETURN_ALL),
+        ([dict(kind=X_, types=[1]), dict(kind=P_, types=[2])], abi.F_EVT_POS),   # shape on which the Java engine throws
+        ([dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[2])], abi.F_COUNT_MATCHES),
+    ]
+    for states, flags in cases:
+        nfa = abi.make_nfa(states)
+        want = oracle.detect(off, act, ts, nfa, flags=flags)
+        got = ctx.evaluate_events(off, act, ts, 6, nfa, flags=flags)
+        ok, why = got.same_as(want)
+        assert ok, (why, states, flags)
+    # one trace longer than the chunk budget, and a request without events
+    off2, act2, ts2 = gen.make_log(3, 5000, 6000, 1000, seed=32)
+    nfa = abi.make_nfa([dict(kind=N_, types=[0]), dict(kind=N_, types=[1])])
+    assert ctx.evaluate_events(off2, act2, ts2, 1000, nfa).same_as(oracle.detect(off2, act2, ts2, nfa))[0]
+    z = ctx.evaluate_events(np.zeros(4, dtype=np.int64), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int64), 4, nfa)
+    assert z.n_traces == 0 and z.occ_off.tolist() == [0]
+
+
+def test_filter_variants_long_traces_large_alphabets_bad_ids(ctx):
+    """The filter of kernel K1 has three forms (<= 32 activities, <= 64, general) and two row widths; all must agree
+    with the oracle.  Also: traces longer than 8192 events leave the narrow configuration, more than 7 pattern
+    activities leave the class-plane filter, and activity ids outside [0, n_activities) never match."""
+    N = N_
+    for n_act, seed in ((20, 41), (50, 42), (300, 43)):
+        off, act, ts = gen.make_log(1500, 10, 120, n_act, seed=seed, zipf=1.2 if n_act > 64 else None)
+        st = [dict(kind=N, types=[0]), dict(kind=O_, types=[1, 2, 3]), dict(kind=X_, types=[4]), dict(kind=N, types=[5]),
+              dict(kind=N, types=[0], preds=[(abi.ATTR_POSITION, abi.OP_GE, 3, 2)])]
+        _check(ctx, off, act, ts, n_act, st, 0)
+        _check(ctx, off, act, ts, n_act, [dict(kind=P_, types=[n_act - 1]), dict(kind=S_, types=[0])], abi.F_EVT_POS)
+    # 9 pattern activities (> 7 classes)
+    off, act, ts = gen.make_log(800, 20, 60, 12, seed=44)
+    st = [dict(kind=O_, types=[0, 1, 2]), dict(kind=O_, types=[3, 4, 5]), dict(kind=O_, types=[6, 7, 8])]
+    _check(ctx, off, act, ts, 12, st, abi.F_RETURN_ALL)
+    # long traces: 9000-event traces with few relevant events
+    off, act, ts = gen.make_log(6, 9000, 9500, 2000, seed=45)
+    _check(ctx, off, act, ts, 2000, [dict(kind=N, types=[0]), dict(kind=N, types=[1])], 0)
+    _check(ctx, off, act, ts, 2000, [dict(kind=P_, types=[3]), dict(kind=S_, types=[4])], 0)
+    # ids outside the alphabet
+    off, act, ts = gen.make_log(400, 10, 40, 8, seed=46)
+    act = act.copy()
+    act[::7] = -3
+    act[3::11] = 8
+    act[5::13] = 1 << 20
+    _check(ctx, off, act, ts, 8, [dict(kind=N, types=[0]), dict(kind=N, types=[1])], 0)
+    _check(ctx, off, act, ts, 8, [dict(kind=P_, types=[2]), dict(kind=S_, types=[3])], 0)
