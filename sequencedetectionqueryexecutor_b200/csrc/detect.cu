@@ -25,8 +25,12 @@
 
 namespace siesta {
 
-constexpr int NT = 128;      // default threads per CTA (one warp = one tile of 32 traces)
-constexpr int NT_MAX = 256;  // launch bound
+constexpr int NT = 128;      // threads per CTA (one warp = one tile of 32 traces)
+constexpr int NT_MAX = 128;  // launch bound
+// Rows of a trace's shared-memory columns.  The narrow configuration keeps 24 (not 32) so that five CTAs fit beside an
+// L1 of ~90 KB (the kernel is sensitive to both, profiles/r01_k1_tuning.md); traces with more relevant events re-run
+// on the wide configuration (64 rows, 64-bit masks).
+#define ROWS_OF(W) ((W) == 1 ? 24 : 64)
 
 struct DetectParams {
     const int64_t* trace_off;
@@ -34,7 +38,9 @@ struct DetectParams {
     const int64_t* ts_ms;
     const int64_t* cand;      // candidate trace indices or nullptr (= identity)
     const int64_t* work;      // indices into the candidate list to process, or nullptr (= all)
-    int64_t n_work;           // number of traces this launch verifies
+    int64_t n_work;           // number of traces this launch verifies ...
+    const unsigned long long* n_work_dev;  // ... or, if set, read from device memory (the narrow launch's overflow count)
+    int32_t ovf_slot;         // counter that counts the traces this launch could not hold (4 narrow, 7 wide)
     const uint16_t* lut;      // [n_act] smask | fmask << 8
     // alpha_mode 0/1: the pattern's activities are numbered 1..K (K <= 7, "class"); plane p holds, bit-reversed, the
     // activities whose class has bit p set (ids 0..31 in [p][0], 32..63 in [p][1]); cls_word / cls_act give the lut
@@ -49,7 +55,6 @@ struct DetectParams {
     int32_t n_act;
     uint32_t flags;
     int32_t needs_ts;
-    int32_t n_tiles;
     // dense per-candidate outputs
     uint32_t* d_nocc;         // selected occurrences (0 = no match)
     uint32_t* d_nev;          // events over the selected occurrences
@@ -149,7 +154,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Shared memory of one warp (all arrays lane-transposed: element i of lane l at [i * 32 + l]).
 template <int W, int R, int NF, bool SMEM_RUNS>
 struct WarpSmem {
-    static constexpr int NE = 32 * W;
+    static constexpr int NE = ROWS_OF(W);
     static constexpr size_t famvv_off = 0;
     static constexpr size_t famvv_bytes = SMEM_RUNS ? sizeof(unsigned long long) * NF * 32 : 0;
     static constexpr size_t rmask_off = famvv_off + famvv_bytes;
@@ -174,11 +179,11 @@ struct WarpSmem {
 // One warp owns a tile of 32 traces from start to finish: no block-level barrier anywhere.
 // MODE: FAST_NONE = run-list engine, FAST_NK / FAST_FK2 = closed-form evaluators (detect_fast.cuh).
 template <int W, int R, int NF, bool SMEM_RUNS, int MODE>
-__global__ void __launch_bounds__(NT_MAX) detect_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ DevNfa nfa) {
+__global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4) detect_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ DevNfa nfa) {
     typedef MaskOps<W> MO;
     typedef typename MO::T mask_t;
     typedef WarpSmem<W, R, NF, SMEM_RUNS> L;
-    constexpr int NE = 32 * W;
+    constexpr int NE = ROWS_OF(W);  // pattern-relevant events a trace may hold in this configuration
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -198,7 +203,9 @@ __global__ void __launch_bounds__(NT_MAX) detect_kernel(const __grid_constant__ 
     const bool dedup = prune && !return_all && (P.flags & SIESTA_F_COUNT_MATCHES) == 0;
     const int warps_per_cta = blockDim.x >> 5;
 
-    for (long long tile = (long long)blockIdx.x * warps_per_cta + warp; tile < P.n_tiles; tile += (long long)gridDim.x * warps_per_cta) {
+    const long long n_work = P.n_work_dev ? (long long)__ldg(P.n_work_dev) : (long long)P.n_work;
+    const long long n_tiles = (n_work + 31) / 32;
+    for (long long tile = (long long)blockIdx.x * warps_per_cta + warp; tile < n_tiles; tile += (long long)gridDim.x * warps_per_cta) {
         // ------------------------------------------------------------------ phase A: filter + compact, one lane per trace
         // Each lane streams its own trace in 32-byte sectors (two 128-bit loads = 8 activity ids), tests the ids against
         // the pattern's type set in registers, and appends the surviving events to its lane-transposed shared-memory
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(NT_MAX) detect_kernel(const __grid_constant__ 
         const int64_t wi = tile * 32 + lane;   // index into the work list
         int64_t ci = -1, t = -1;               // candidate index, trace index
         long long o0 = 0, o1 = 0;
-        if (wi < P.n_work) {
+        if (wi < n_work) {
             ci = P.work ? P.work[wi] : wi;
             t = P.cand ? P.cand[ci] : ci;
             o0 = P.trace_off[t];
@@ -403,7 +410,10 @@ __global__ void __launch_bounds__(NT_MAX) detect_kernel(const __grid_constant__ 
                 P.d_nocc[ci] = 0;
                 P.d_nev[ci] = 0;
                 if (status == ST_ERR) P.err_list[atomicAdd(P.counters + 3, 1ull)] = t;
-                else if (status == ST_OVF) P.ovf_list[atomicAdd(P.counters + 4, 1ull)] = ci;
+                else if (status == ST_OVF) {
+                    const unsigned long long at = atomicAdd(P.counters + P.ovf_slot, 1ull);
+                    if (P.ovf_list) P.ovf_list[at] = ci;
+                }
             }
         }
         if (stage_ok && tot1 > 0) {
@@ -707,6 +717,12 @@ struct DevBuf {
     void* release() { void* q = p; p = nullptr; return q; }
 };
 
+// a slice of a DevBuf
+struct View {
+    void* p;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 struct DevMatchesImpl {
     void* bufs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t free_stream = nullptr;
@@ -732,8 +748,7 @@ int launch_detect(const Ctx* ctx, cudaStream_t stream, DetectParams P, const Dev
     int per_sm = 0;
     SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));
     if (per_sm < 1) per_sm = 1;
-    const int64_t n_tiles = (P.n_work + 31) / 32;   // one tile = the 32 traces of one warp
-    P.n_tiles = (int32_t)n_tiles;
+    const int64_t n_tiles = (P.n_work + 31) / 32;   // one tile = the 32 traces of one warp (upper bound if the count is on the device)
     const int64_t ctas_needed = (n_tiles + nt / 32 - 1) / (nt / 32);
     if (const char* env = std::getenv("SIESTA_K1_CTAS_PER_SM")) {  // tuning aid: cap on resident CTAs per SM
         const int v = std::atoi(env);
@@ -772,18 +787,31 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     const int64_t cap_occ = return_all ? wide : n;
     const int64_t cap_ev = (!return_all && !dn.any_kleene) ? n * std::max(1, n_positive) : wide;
 
-    DevBuf b_lut(stream), b_nocc(stream), b_nev(stream), b_stage(stream), b_stage_occ(stream), b_counters(stream),
-        b_err(stream), b_ovf(stream), b_ovf2(stream);
-    DevBuf s_occ_nev(stream), s_ev_pos(stream), s_ev_rank(stream), s_ev_act(stream), s_ev_ts(stream), b_blk(stream);
+    // one stream-ordered allocation for all scratch of the call, carved by a bump pointer
+    DevBuf work(stream);
     const size_t nn = (size_t)std::max<int64_t>(n, 1);
-    if ((rc = b_lut.alloc(lut.size() * sizeof(uint16_t))) || (rc = b_nocc.alloc(nn * 4)) || (rc = b_nev.alloc(nn * 4)) ||
-        (rc = b_stage.alloc(nn * 8)) || (rc = b_stage_occ.alloc(nn * 8)) || (rc = b_counters.alloc(16 * 8)) ||
-        (rc = b_err.alloc(nn * 8)) || (rc = b_ovf.alloc(nn * 8)) || (rc = s_occ_nev.alloc((size_t)cap_occ * 4)) ||
-        (rc = s_ev_pos.alloc((size_t)cap_ev * 4)))
-        return rc;
-    if (all_cols && ((rc = s_ev_rank.alloc((size_t)cap_ev * 4)) || (rc = s_ev_act.alloc((size_t)cap_ev * 4)) ||
-                     (rc = s_ev_ts.alloc((size_t)cap_ev * 8))))
-        return rc;
+    size_t w_off = 0;
+    auto carve = [&w_off](size_t bytes) {
+        const size_t at = w_off;
+        w_off += (bytes + 255) & ~(size_t)255;
+        return at;
+    };
+    const size_t n_blk = (nn + GT - 1) / GT;
+    const size_t o_lut = carve(lut.size() * sizeof(uint16_t)), o_nocc = carve(nn * 4), o_nev = carve(nn * 4), o_stage = carve(nn * 8),
+                 o_stage_occ = carve(nn * 8), o_counters = carve(16 * 8), o_err = carve(nn * 8), o_ovf = carve(nn * 8),
+                 o_blk = carve(n_blk * 3 * 8), o_occ_nev = carve((size_t)cap_occ * 4), o_pos = carve((size_t)cap_ev * 4);
+    size_t o_rank = 0, o_act = 0, o_ts = 0;
+    if (all_cols) {
+        o_rank = carve((size_t)cap_ev * 4);
+        o_act = carve((size_t)cap_ev * 4);
+        o_ts = carve((size_t)cap_ev * 8);
+    }
+    if ((rc = work.alloc(w_off))) return rc;
+    char* wb = work.as<char>();
+    const View b_lut{wb + o_lut}, b_nocc{wb + o_nocc}, b_nev{wb + o_nev}, b_stage{wb + o_stage}, b_stage_occ{wb + o_stage_occ},
+        b_counters{wb + o_counters}, b_err{wb + o_err}, b_ovf{wb + o_ovf}, b_blk{wb + o_blk}, s_occ_nev{wb + o_occ_nev},
+        s_ev_pos{wb + o_pos}, s_ev_rank{all_cols ? wb + o_rank : nullptr}, s_ev_act{all_cols ? wb + o_act : nullptr},
+        s_ev_ts{all_cols ? wb + o_ts : nullptr};
 
     cudaEvent_t ev0, ev1, evd;
     SIESTA_CUDA_OK(cudaEventCreate(&ev0));
@@ -845,6 +873,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     P.err_list = b_err.as<int64_t>();
     P.ovf_list = b_ovf.as<int64_t>();
 
+    P.ovf_slot = 4;
     unsigned long long h_cnt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (n > 0) {
         if (dn.fast_class == FAST_FK2) rc = launch_detect<1, 0, 0, false, FAST_FK2>(ctx, stream, P, dn);
@@ -852,28 +881,24 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
         else rc = launch_detect<1, 16, 16, true, FAST_NONE>(ctx, stream, P, dn);
         if (rc) return rc;
         SIESTA_CUDA_OK(cudaEventRecord(evd, stream));
+        // Traces beyond the narrow configuration (24 relevant events; run-list engine: 16 live runs / 16 live families)
+        // re-run on the wide one.  The launch is unconditional and reads its work count from the device, so the host
+        // does not have to wait for the narrow launch first; with nothing to do it costs a few microseconds.
+        DetectParams Q = P;
+        Q.work = b_ovf.as<int64_t>();
+        Q.n_work_dev = b_counters.as<unsigned long long>() + 4;
+        Q.ovf_list = nullptr;
+        Q.ovf_slot = 7;
+        if (dn.fast_class == FAST_FK2) rc = launch_detect<2, 0, 0, false, FAST_FK2>(ctx, stream, Q, dn);
+        else if (dn.fast_class == FAST_NK) rc = launch_detect<2, 0, 0, false, FAST_NK>(ctx, stream, Q, dn);
+        else rc = launch_detect<2, 1024, 128, false, FAST_NONE>(ctx, stream, Q, dn);
+        if (rc) return rc;
         SIESTA_CUDA_OK(cudaMemcpyAsync(h_cnt, b_counters.p, 128, cudaMemcpyDeviceToHost, stream));
         SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
-        if (h_cnt[4] > 0) {
-            // traces beyond the narrow configuration (32 relevant events / 16 live runs / 16 live families): wide engine
-            const int64_t n_ovf = (int64_t)h_cnt[4];
-            if ((rc = b_ovf2.alloc((size_t)n_ovf * 8))) return rc;
-            SIESTA_CUDA_OK(cudaMemsetAsync(b_counters.as<unsigned long long>() + 4, 0, 8, stream));
-            DetectParams Q = P;
-            Q.work = b_ovf.as<int64_t>();
-            Q.n_work = n_ovf;
-            Q.ovf_list = b_ovf2.as<int64_t>();
-            if (dn.fast_class == FAST_FK2) rc = launch_detect<2, 0, 0, false, FAST_FK2>(ctx, stream, Q, dn);
-            else if (dn.fast_class == FAST_NK) rc = launch_detect<2, 0, 0, false, FAST_NK>(ctx, stream, Q, dn);
-            else rc = launch_detect<2, 1024, 128, false, FAST_NONE>(ctx, stream, Q, dn);
-            if (rc) return rc;
-            SIESTA_CUDA_OK(cudaMemcpyAsync(h_cnt, b_counters.p, 128, cudaMemcpyDeviceToHost, stream));
-            SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
-            if (h_cnt[4] > 0) {
-                set_error(std::to_string(h_cnt[4]) + " trace(s) exceed the engine limits (64 pattern-relevant events, "
-                          "1024 live runs or 65536 events per trace)");
-                return SIESTA_E_UNSUPPORTED;
-            }
+        if (h_cnt[7] > 0) {
+            set_error(std::to_string(h_cnt[7]) + " trace(s) exceed the engine limits (64 pattern-relevant events, "
+                      "1024 live runs or 65536 events per trace)");
+            return SIESTA_E_UNSUPPORTED;
         }
         if (h_cnt[5] > 0) {
             set_error("internal: occurrence staging overflow");
@@ -885,14 +910,26 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
 #endif
     const int64_t n_occ = (int64_t)h_cnt[0], n_ev = (int64_t)h_cnt[1], n_tr = (int64_t)h_cnt[6], n_err = (int64_t)h_cnt[3];
 
-    DevBuf f_trace(stream), f_occ_off(stream), f_ev_off(stream), f_pos(stream), f_rank(stream), f_act(stream), f_ts(stream),
-        f_err(stream);
-    if ((rc = f_trace.alloc((size_t)n_tr * 8)) || (rc = f_occ_off.alloc((size_t)(n_tr + 1) * 8)) ||
-        (rc = f_ev_off.alloc((size_t)(n_occ + 1) * 8)) || (rc = f_pos.alloc((size_t)n_ev * 4)) ||
-        (rc = f_err.alloc((size_t)n_err * 8)))
-        return rc;
-    if (all_cols && ((rc = f_rank.alloc((size_t)n_ev * 4)) || (rc = f_act.alloc((size_t)n_ev * 4)) || (rc = f_ts.alloc((size_t)n_ev * 8))))
-        return rc;
+    // the result columns: one allocation, owned by the returned object
+    DevBuf fin(stream);
+    size_t f_off = 0;
+    auto fcarve = [&f_off](size_t bytes) {
+        const size_t at = f_off;
+        f_off += (bytes + 255) & ~(size_t)255;
+        return at;
+    };
+    const size_t q_trace = fcarve((size_t)n_tr * 8), q_occ = fcarve((size_t)(n_tr + 1) * 8), q_evoff = fcarve((size_t)(n_occ + 1) * 8),
+                 q_pos = fcarve((size_t)n_ev * 4), q_err = fcarve((size_t)n_err * 8);
+    size_t q_rank = 0, q_act = 0, q_ts = 0;
+    if (all_cols) {
+        q_rank = fcarve((size_t)n_ev * 4);
+        q_act = fcarve((size_t)n_ev * 4);
+        q_ts = fcarve((size_t)n_ev * 8);
+    }
+    if ((rc = fin.alloc(f_off))) return rc;
+    char* fb = fin.as<char>();
+    const View f_trace{fb + q_trace}, f_occ_off{fb + q_occ}, f_ev_off{fb + q_evoff}, f_pos{fb + q_pos}, f_err{fb + q_err},
+        f_rank{all_cols ? fb + q_rank : nullptr}, f_act{all_cols ? fb + q_act : nullptr}, f_ts{all_cols ? fb + q_ts : nullptr};
 
     if (n > 0) {
         GatherParams G;
@@ -904,8 +941,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
         G.d_nev = P.d_nev;
         G.d_stage = P.d_stage;
         G.d_stage_occ = P.d_stage_occ;
-        G.n_blk = (n + GT - 1) / GT;
-        if ((rc = b_blk.alloc((size_t)G.n_blk * 3 * 8))) return rc;
+        G.n_blk = (int64_t)n_blk;
         G.blk = b_blk.as<unsigned long long>();
         G.s_occ_nev = P.s_occ_nev;
         G.s_ev_pos = P.s_ev_pos;
@@ -958,14 +994,15 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     out->detect_ms = dms;
     impl->free_stream = ctx->stream;
     impl->device = ctx->device;
-    impl->bufs[0] = out->d_trace_idx = (int64_t*)f_trace.release();
-    impl->bufs[1] = out->d_occ_off = (int64_t*)f_occ_off.release();
-    impl->bufs[2] = out->d_ev_off = (int64_t*)f_ev_off.release();
-    impl->bufs[3] = out->d_ev_pos = (int32_t*)f_pos.release();
-    impl->bufs[4] = out->d_ev_rank = (int32_t*)f_rank.release();
-    impl->bufs[5] = out->d_ev_act = (int32_t*)f_act.release();
-    impl->bufs[6] = out->d_ev_ts_ms = (int64_t*)f_ts.release();
-    impl->bufs[7] = out->d_err_trace_idx = (int64_t*)f_err.release();
+    out->d_trace_idx = f_trace.as<int64_t>();
+    out->d_occ_off = f_occ_off.as<int64_t>();
+    out->d_ev_off = f_ev_off.as<int64_t>();
+    out->d_ev_pos = f_pos.as<int32_t>();
+    out->d_ev_rank = f_rank.as<int32_t>();
+    out->d_ev_act = f_act.as<int32_t>();
+    out->d_ev_ts_ms = f_ts.as<int64_t>();
+    out->d_err_trace_idx = f_err.as<int64_t>();
+    impl->bufs[0] = fin.release();
     out->impl = impl;
     return SIESTA_OK;
 }
