@@ -28,10 +28,26 @@ WORKLOADS = {
     # BASELINE.json configs[1]: /detection Kleene pattern a+ b* with a within-10-minutes time constraint,
     # 1M traces x 100 events (20 activity types, gaps U{1..120} s), 1 B200.  SURVEY.md §8(d) cfg 2.
     "detection_kleene_1Mx100": dict(n_traces=1_000_000, min_len=100, max_len=100, n_act=20, max_gap_s=120, seed=0x51E57A02,
-                                    bytes_per_event=12,
+                                    bytes_per_event=12, pattern="a+ b* within 10 minutes (EventTs route, returnAll=false)",
+                                    kernel="detect_kernel<W=1, FAST_FK2> (K1: filter + a+ b* closed form + staged output)",
                                     states=[dict(kind=abi.STATE_KLEENE_PLUS, types=[0]),
                                             dict(kind=abi.STATE_KLEENE_STAR, types=[1],
                                                  preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 600)])]),
+    # Secondary workloads (not the headline; `--workload ...`), used for profiles/ and DESIGN.md:
+    # configs[0] shape: A_ B_ on 10k traces x ~40 events (no constraint: 4 B/event).
+    "detection_ab_10kx40": dict(n_traces=10_000, min_len=30, max_len=50, n_act=20, max_gap_s=600, seed=0x51E57A01,
+                                bytes_per_event=4, pattern="A_ B_ (EventTs route, returnAll=false)",
+                                kernel="detect_kernel<W=1, FAST_NK> (K1: filter + greedy-walk closed form + staged output)",
+                                states=[dict(kind=abi.STATE_NORMAL, types=[0]), dict(kind=abi.STATE_NORMAL, types=[1])]),
+    # configs[4] shape: a, (b|c), !d, e, f with gap within 10 (0,1) and gap atleast 2 (3,4); 50 events per trace.
+    # 4M traces per GPU by default (the 100M-trace log of configs[4] is 12.5M traces per GPU on 8 GPUs; --traces sets it).
+    "detection_gap6_4Mx50": dict(n_traces=4_000_000, min_len=50, max_len=50, n_act=20, max_gap_s=600, seed=0x51E57A05,
+                                 bytes_per_event=4, pattern="a (b|c) !d e f; gap within 10 (0,1), gap atleast 2 (3,4) (returnAll=false)",
+                                 kernel="detect_kernel<W=1, FAST_NK> (K1: filter + greedy-walk closed form + staged output)",
+                                 states=[dict(kind=abi.STATE_NORMAL, types=[0]),
+                                         dict(kind=abi.STATE_OR, types=[1, 2], preds=[(abi.ATTR_POSITION, abi.OP_LE, 0, 10)]),
+                                         dict(kind=abi.STATE_NEGATIVE, types=[3]), dict(kind=abi.STATE_NORMAL, types=[4]),
+                                         dict(kind=abi.STATE_NORMAL, types=[5], preds=[(abi.ATTR_POSITION, abi.OP_GE, 3, 2)])]),
 }
 DEFAULT_WORKLOAD = "detection_kleene_1Mx100"
 
@@ -147,7 +163,7 @@ def run_reference(args, wl, world, rank):
     states = wl["states"]
     nfa = abi.make_nfa(states)
     threads = os.cpu_count() or 1
-    n_sample = 400_000
+    n_sample = min(400_000, wl["n_traces"])
     off, act, ts = make_log_fast(n_sample, wl["min_len"], wl["max_len"], wl["n_act"], wl["seed"], wl["max_gap_s"])
     import oracle
     for _ in range(args.warmup):
@@ -162,7 +178,7 @@ def run_reference(args, wl, world, rank):
         "impl": "reference", "metric": "events scanned/sec (/detection verification)", "value": v, "unit": "events/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": args.workload, "pattern": "a+ b* within 10 minutes", "sample": sample},
+        "config": {"workload": args.workload, "pattern": wl["pattern"], "sample": sample},
         "cpu_baseline": {"value": v, "unit": "events/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -226,7 +242,11 @@ def main():
 
     first_trace = rank * T  # weak scaling: rank r owns global traces [r*T, (r+1)*T)
 
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if wl["bytes_per_event"] * E <= 2.6e8 else None
+
     def step_resident():
+        if flush is not None:
+            flush.add_(1)  # inputs smaller than L2: evict them between steps
         dm = log.detect_device(nfa, flags=0)
         n_all = dm.n_traces
         if world > 1:
@@ -297,11 +317,13 @@ def main():
             "metric": "events scanned/sec (/detection verification)", "value": value, "unit": "events/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": args.workload, "pattern": "a+ b* within 10 minutes (EventTs route, returnAll=false)",
+            "config": {"workload": args.workload, "pattern": wl["pattern"],
                        "traces_per_gpu": T, "events_per_gpu": E, "activities": wl["n_act"],
                        "parallelism": f"traces sharded over {world} GPU(s); match lists joined by NCCL all-gather",
-                       "l2": "inputs (1.2 GB/GPU) larger than L2; no flush needed"},
-            "roofline": {"bound": "hbm", "kernel": "detect_kernel<W=1, FAST_FK2> (K1: filter + a+ b* closed form + staged output)",
+                       "l2": (f"inputs ({12 * E / 1e9:.2f} GB/GPU resident, {wl['bytes_per_event']} B/event read) "
+                              + ("larger than L2; no flush needed" if wl["bytes_per_event"] * E > 2.6e8 else
+                                 "SMALLER than L2: a 512 MB buffer is rewritten between steps"))},
+            "roofline": {"bound": "hbm", "kernel": wl["kernel"],
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic_bytes(args.workload, T),
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": det_ms, "all_kernels_ms": float(np.mean(k_ms))},

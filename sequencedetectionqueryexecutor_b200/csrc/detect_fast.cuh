@@ -271,8 +271,10 @@ struct NkMasks {
         for (int k = 0; k <= SIESTA_MAX_STATES; ++k) T[k] = 0;
     }
     SIESTA_HD __forceinline__ void on_event(int j, uint32_t w) {
+        const typename MaskOps<W>::T b = MaskOps<W>::bit(j);
 #pragma unroll
-        for (int k = 0; k < SIESTA_MAX_STATES; ++k) T[k] |= (typename MaskOps<W>::T)((w >> k) & 1u) << j;
+        for (int k = 0; k < SIESTA_MAX_STATES; ++k)
+            if (w & (1u << k)) T[k] |= b;  // one bits-to-predicates move + predicated ORs
     }
 };
 
