@@ -126,6 +126,20 @@ int siesta_pattern_compile(const siesta_event_symbol* symbols, int32_t n_symbols
                            const siesta_constraint* constraints, int32_t n_constraints,
                            int32_t only_appearances, siesta_nfa* out);
 
+/* Replaces ComplexPattern.extractPairsForPatternDetection(fromOrTillSet) (ComplexPattern.java:75-128) and
+ * SIESTAPattern.extractPairsForPatternDetection (SIESTAPattern.java:34-69): per OR-expansion of the pattern
+ * (splitWithOr, ComplexPattern.java:130-171) the "true" pairs (every ordered pair of "_" / "+" events: a trace must
+ * hold all of them) and "all" pairs (true pairs + the pairs fetched for "*", "!", self pairs).  Pair sets are sets of
+ * (a, b) activity ids (EventPair equality is by name, EventPair.java:65-81), returned sorted; expansion x owns
+ * true_a/b[true_off[x] .. true_off[x+1]) and all_a/b[all_off[x] .. all_off[x+1]).  Returns
+ * SIESTA_E_REFERENCE_THROWS for the patterns on which the Java code loops forever (ComplexPattern.java:108-113).
+ * Host only. */
+int siesta_pattern_extract_pairs(const siesta_event_symbol* symbols, int32_t n_symbols,
+                                 const siesta_constraint* constraints, int32_t n_constraints, int32_t from_or_till_set,
+                                 int32_t cap_expansions, int32_t cap_pairs, int32_t* n_expansions,
+                                 int32_t* true_off /* [cap_expansions + 1] */, int32_t* true_a, int32_t* true_b,
+                                 int32_t* all_off /* [cap_expansions + 1] */, int32_t* all_a, int32_t* all_b);
+
 /* ------------------------------------------------------------ ctx and log */
 typedef struct siesta_ctx siesta_ctx;
 typedef struct siesta_log siesta_log;
@@ -250,6 +264,13 @@ int siesta_intersect(siesta_index* index, const int32_t* pair_ids, int32_t n, in
 /* Same, result left in HBM (*d_out, free with siesta_device_free) for siesta_detect_device's d_cand. */
 int siesta_intersect_device(siesta_index* index, const int32_t* pair_ids, int32_t n, int64_t** d_out, int64_t* out_n,
                             double* kernel_ms);
+/* The candidate traces of a pattern with OR-expansions: the union over the expansions of the intersection of each
+ * expansion's true-pair lists (QueryPlanPatternDetection.getMiddleResults :146-164 merges the per-expansion results).
+ * Expansion x uses lists pair_ids[exp_off[x] .. exp_off[x+1]).  Ascending trace indices. */
+int siesta_candidates_device(siesta_index* index, const int32_t* exp_off, const int32_t* pair_ids, int32_t n_expansions,
+                             int64_t** d_out, int64_t* out_n, double* kernel_ms);
+int siesta_candidates(siesta_index* index, const int32_t* exp_off, const int32_t* pair_ids, int32_t n_expansions,
+                      int64_t* out, int64_t cap, int64_t* out_n);
 void siesta_device_free(siesta_log* log, void* d_ptr);
 
 /* ------------------------------------------------------- declare counting */

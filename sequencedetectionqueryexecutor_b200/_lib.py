@@ -16,7 +16,8 @@ EXPORTS = [
     "siesta_matches_free", "siesta_evaluate_events", "siesta_detect_device", "siesta_dev_matches_free",
     "siesta_kernel_launches", "siesta_declare_counts_size", "siesta_declare_counts", "siesta_declare_counts_device",
     "siesta_index_load", "siesta_index_build", "siesta_index_free", "siesta_index_list_len", "siesta_index_get_list",
-    "siesta_intersect", "siesta_intersect_device", "siesta_device_free",
+    "siesta_intersect", "siesta_intersect_device", "siesta_device_free", "siesta_pattern_extract_pairs",
+    "siesta_candidates", "siesta_candidates_device",
 ]
 
 
@@ -70,6 +71,11 @@ def lib():
     L.siesta_index_get_list.argtypes = [vp, i32, vp, i64]
     L.siesta_intersect.argtypes = [vp, vp, i32, vp, i64, P(i64)]
     L.siesta_intersect_device.argtypes = [vp, vp, i32, P(vp), P(i64), P(C.c_double)]
+    P32 = P(i32)
+    L.siesta_pattern_extract_pairs.argtypes = [P(_abi.EventSymbolC), i32, P(_abi.ConstraintC), i32, i32, i32, i32, P32,
+                                               P32, P32, P32, P32, P32, P32]
+    L.siesta_candidates.argtypes = [vp, vp, vp, i32, vp, i64, P(i64)]
+    L.siesta_candidates_device.argtypes = [vp, vp, vp, i32, P(vp), P(i64), P(C.c_double)]
     L.siesta_device_free.argtypes = [vp, vp]
     L.siesta_device_free.restype = None
     _lib = L

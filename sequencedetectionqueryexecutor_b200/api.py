@@ -171,6 +171,17 @@ class PairIndex:
         return out[:n.value].copy()
 
 
+    def candidates(self, expansions):
+        """siesta_candidates: union over the expansions (lists of pair ids) of the intersection of their posting lists."""
+        off = np.zeros(len(expansions) + 1, dtype=np.int32)
+        np.cumsum([len(x) for x in expansions], out=off[1:])
+        ids = np.array([i for x in expansions for i in x], dtype=np.int32)
+        out = np.zeros(max(self.log.n_traces, 1), dtype=np.int64)
+        n = C.c_int64(0)
+        check(lib().siesta_candidates(self._h, _ptr(off), _ptr(ids), len(expansions), _ptr(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+
 class DeviceMatches:
     def __init__(self, dm):
         self.dm = dm

@@ -151,6 +151,7 @@ struct ProbeParams {
     const int64_t* lists[MAX_BUILD_PAIRS];
     int64_t lens[MAX_BUILD_PAIRS];
     uint8_t* flags;
+    uint8_t* mark;          // if set: [n_traces] flags indexed by trace, written instead of `flags`
 };
 
 __global__ void __launch_bounds__(IT) probe_flags_kernel(const __grid_constant__ ProbeParams P) {
@@ -168,7 +169,11 @@ __global__ void __launch_bounds__(IT) probe_flags_kernel(const __grid_constant__
         }
         all = lo < P.lens[k] && __ldg(L + lo) == v;
     }
-    P.flags[i] = all ? 1 : 0;
+    if (P.mark) {
+        if (all) P.mark[v] = 1;  // union over expansions: flag the trace itself
+    } else {
+        P.flags[i] = all ? 1 : 0;
+    }
 }
 
 static int compact_rows(cudaStream_t stream, const uint8_t* d_flags, const int64_t* d_values, int64_t n, int n_rows,
@@ -395,6 +400,99 @@ extern "C" int siesta_intersect_device(siesta_index* index, const int32_t* pair_
     *out_n = counts[0];
     if (kernel_ms) *kernel_ms = ms;
     return SIESTA_OK;
+}
+
+extern "C" int siesta_candidates_device(siesta_index* index, const int32_t* exp_off, const int32_t* pair_ids, int32_t n_exp,
+                                        int64_t** d_out, int64_t* out_n, double* kernel_ms) {
+    Index* ix = reinterpret_cast<Index*>(index);
+    if (!ix || !exp_off || !pair_ids || n_exp < 1 || !d_out || !out_n) {
+        set_error("siesta_candidates: bad argument");
+        return SIESTA_E_INVALID;
+    }
+    for (int x = 0; x < n_exp; ++x) {
+        const int n = exp_off[x + 1] - exp_off[x];
+        if (n < 1 || n > MAX_BUILD_PAIRS) {
+            set_error("siesta_candidates: every expansion needs 1.." + std::to_string(MAX_BUILD_PAIRS) + " true pairs "
+                      "(patterns without a true pair take the Single plan: verify all traces)");
+            return SIESTA_E_INVALID;
+        }
+        for (int k = exp_off[x]; k < exp_off[x + 1]; ++k)
+            if (pair_ids[k] < 0 || pair_ids[k] >= ix->n_pairs) {
+                set_error("siesta_candidates: pair id out of range");
+                return SIESTA_E_INVALID;
+            }
+    }
+    SIESTA_CUDA_OK(cudaSetDevice(ix->log->ctx->device));
+    cudaStream_t stream = ix->log->ctx->stream;
+    const int64_t T = ix->log->n_traces;
+    cudaEvent_t e0, e1;
+    SIESTA_CUDA_OK(cudaEventCreate(&e0));
+    SIESTA_CUDA_OK(cudaEventCreate(&e1));
+    SIESTA_CUDA_OK(cudaEventRecord(e0, stream));
+    uint8_t* d_mark = nullptr;
+    SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_mark, (size_t)std::max<int64_t>(T, 1), stream));
+    SIESTA_CUDA_OK(cudaMemsetAsync(d_mark, 0, (size_t)std::max<int64_t>(T, 1), stream));
+    for (int x = 0; x < n_exp; ++x) {
+        const int32_t* ids = pair_ids + exp_off[x];
+        const int n = exp_off[x + 1] - exp_off[x];
+        int best = 0;  // probe with the shortest list
+        for (int k = 1; k < n; ++k)
+            if (ix->off[ids[k] + 1] - ix->off[ids[k]] < ix->off[ids[best] + 1] - ix->off[ids[best]]) best = k;
+        ProbeParams P;
+        std::memset(&P, 0, sizeof(P));
+        P.probe = ix->d_lists + ix->off[ids[best]];
+        P.n_probe = ix->off[ids[best] + 1] - ix->off[ids[best]];
+        for (int k = 0; k < n; ++k) {
+            if (k == best) continue;
+            P.lists[P.n_others] = ix->d_lists + ix->off[ids[k]];
+            P.lens[P.n_others] = ix->off[ids[k] + 1] - ix->off[ids[k]];
+            ++P.n_others;
+        }
+        P.mark = d_mark;
+        if (P.n_probe > 0) {
+            probe_flags_kernel<<<(unsigned)((P.n_probe + IT - 1) / IT), IT, 0, stream>>>(P);
+            SIESTA_LAUNCHED();
+            SIESTA_CUDA_OK(cudaGetLastError());
+        }
+    }
+    std::vector<int64_t> counts, row_off;
+    int rc = compact_rows(stream, d_mark, nullptr, T, 1, counts, d_out, row_off);
+    SIESTA_CUDA_OK(cudaEventRecord(e1, stream));
+    SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFreeAsync(d_mark, stream);
+    if (rc) return rc;
+    *out_n = counts[0];
+    if (kernel_ms) *kernel_ms = ms;
+    return SIESTA_OK;
+}
+
+extern "C" int siesta_candidates(siesta_index* index, const int32_t* exp_off, const int32_t* pair_ids, int32_t n_exp, int64_t* out,
+                                 int64_t cap, int64_t* out_n) {
+    if (!out_n || (cap && !out)) {
+        set_error("siesta_candidates: null output");
+        return SIESTA_E_INVALID;
+    }
+    int64_t* d = nullptr;
+    int rc = siesta_candidates_device(index, exp_off, pair_ids, n_exp, &d, out_n, nullptr);
+    if (rc) return rc;
+    Index* ix = reinterpret_cast<Index*>(index);
+    if (*out_n > cap) {
+        set_error("siesta_candidates: output buffer too small");
+        rc = SIESTA_E_INVALID;
+    } else if (*out_n) {
+        cudaError_t e = cudaMemcpyAsync(out, d, sizeof(int64_t) * (size_t)*out_n, cudaMemcpyDeviceToHost, ix->log->ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ix->log->ctx->stream);
+        if (e != cudaSuccess) {
+            set_error(std::string("siesta_candidates: D2H: ") + cudaGetErrorString(e));
+            rc = SIESTA_E_CUDA;
+        }
+    }
+    cudaFreeAsync(d, ix->log->ctx->stream);
+    return rc;
 }
 
 extern "C" void siesta_device_free(siesta_log* log, void* d_ptr) {

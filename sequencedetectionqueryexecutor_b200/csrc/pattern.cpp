@@ -113,3 +113,128 @@ extern "C" int siesta_pattern_compile(const siesta_event_symbol* symbols, int32_
     }
     return SIESTA_OK;
 }
+
+// ---------------------------------------------------------------------------------------------- pair extraction (P3)
+// Restates ComplexPattern.extractPairsForPatternDetection / splitWithOr / generateCombinations
+// (J/model/Patterns/ComplexPattern.java:75-171) over SIESTAPattern.extractPairsForPatternDetection
+// (J/model/Patterns/SIESTAPattern.java:34-69).  EventPair equality is by the two names only
+// (J/model/Events/EventPair.java:65-81), so a pair set is a set of (a, b) activity ids.
+#include <algorithm>
+#include <set>
+#include <utility>
+#include <vector>
+
+namespace {
+typedef std::pair<int32_t, int32_t> Pair;
+struct Sym {
+    int32_t activity, symbol;
+    bool operator<(const Sym& o) const { return activity != o.activity ? activity < o.activity : symbol < o.symbol; }
+    bool operator==(const Sym& o) const { return activity == o.activity && symbol == o.symbol; }
+};
+inline bool non_empty(int32_t symbol) { return symbol == SIESTA_SYM_NORMAL || symbol == SIESTA_SYM_PLUS; }
+}  // namespace
+
+extern "C" int siesta_pattern_extract_pairs(const siesta_event_symbol* symbols, int32_t n_symbols,
+                                            const siesta_constraint* constraints, int32_t n_constraints, int32_t from_or_till_set,
+                                            int32_t cap_expansions, int32_t cap_pairs, int32_t* n_expansions, int32_t* true_off,
+                                            int32_t* true_a, int32_t* true_b, int32_t* all_off, int32_t* all_a, int32_t* all_b) {
+    if (!symbols || n_symbols < 1 || n_constraints < 0 || (n_constraints && !constraints) || !n_expansions || !true_off || !all_off ||
+        cap_expansions < 1 || cap_pairs < 0 || (cap_pairs && (!true_a || !true_b || !all_a || !all_b))) {
+        siesta::set_error("siesta_pattern_extract_pairs: bad argument");
+        return SIESTA_E_INVALID;
+    }
+    // splitWithOr (:130-152): one set of symbols per pattern position; "||" entries become "_"
+    std::vector<std::vector<Sym>> same_pos;
+    for (int i = 0; i < n_symbols; ++i) {
+        Sym s{symbols[i].activity, symbols[i].symbol == SIESTA_SYM_OR ? SIESTA_SYM_NORMAL : symbols[i].symbol};
+        const int pos = symbols[i].position;
+        if ((int)same_pos.size() == pos) same_pos.push_back({s});
+        else if (pos >= 0 && pos < (int)same_pos.size()) {
+            std::vector<Sym>& v = same_pos[pos];
+            if (std::find(v.begin(), v.end(), s) == v.end()) v.push_back(s);  // HashSet<EventSymbol>
+        } else {
+            siesta::set_error("symbol positions must be 0, 1, 2 ... without gaps (ComplexPattern.splitWithOr indexes by position)");
+            return SIESTA_E_REFERENCE_THROWS;
+        }
+    }
+    // generateCombinations (:161-171), duplicates removed (the reference returns a HashSet of the lists)
+    std::set<std::vector<Sym>> seen;
+    std::vector<std::vector<Sym>> expansions;
+    std::vector<size_t> choice(same_pos.size(), 0);
+    while (true) {
+        std::vector<Sym> cur;
+        for (size_t p = 0; p < same_pos.size(); ++p) cur.push_back(same_pos[p][choice[p]]);
+        if (seen.insert(cur).second) expansions.push_back(cur);
+        int p = (int)same_pos.size() - 1;
+        while (p >= 0 && ++choice[p] == same_pos[p].size()) choice[p--] = 0;
+        if (p < 0) break;
+        if ((int)expansions.size() > cap_expansions) break;
+    }
+    if ((int)expansions.size() > cap_expansions) {
+        siesta::set_error("more OR-expansions than cap_expansions");
+        return SIESTA_E_INVALID;
+    }
+    std::set<int32_t> constraint_pos;
+    for (int c = 0; c < n_constraints; ++c) {
+        constraint_pos.insert(constraints[c].pos_a);
+        constraint_pos.insert(constraints[c].pos_b);
+    }
+    int n_true = 0, n_all = 0;
+    true_off[0] = all_off[0] = 0;
+    for (size_t x = 0; x < expansions.size(); ++x) {
+        const std::vector<Sym>& ev = expansions[x];
+        std::set<Pair> tp, ap;
+        std::vector<std::pair<int32_t, int>> l;  // (activity, position in the expansion) of the "_" and "+" events
+        bool have_first = false;
+        int32_t first_non_empty = 0;
+        for (int i = 0; i < (int)ev.size(); ++i) {
+            const Sym& es = ev[i];
+            if (!have_first && non_empty(es.symbol)) {
+                have_first = true;
+                first_non_empty = es.activity;
+            }
+            switch (es.symbol) {
+                case SIESTA_SYM_NORMAL: l.push_back({es.activity, i}); break;
+                case SIESTA_SYM_PLUS:
+                    l.push_back({es.activity, i});
+                    ap.insert({es.activity, es.activity});
+                    break;
+                case SIESTA_SYM_NOT:
+                case SIESTA_SYM_STAR:
+                    if (have_first) ap.insert({first_non_empty, es.activity});
+                    else if (i + 1 < (int)ev.size()) {
+                        // the reference's search loop (:108-113) never advances k: it ends only if the very next symbol is "_" / "+"
+                        if (!non_empty(ev[i + 1].symbol)) {
+                            siesta::set_error("the reference loops forever on a leading '*' / '!' that is not followed by a '_' / '+' symbol "
+                                              "(ComplexPattern.java:108-113)");
+                            return SIESTA_E_REFERENCE_THROWS;
+                        }
+                        ap.insert({es.activity, ev[i + 1].activity});
+                    }
+                    ap.insert({es.activity, es.activity});
+                    break;
+                default:
+                    siesta::set_error("unknown symbol");
+                    return SIESTA_E_INVALID;
+            }
+        }
+        // SIESTAPattern.extractPairsForPatternDetection (:34-69)
+        for (int i = 0; i + 1 < (int)l.size(); ++i) {
+            if (constraint_pos.count(l[i].second)) ap.insert({l[i].first, l[i].first});
+            for (int j = i + 1; j < (int)l.size(); ++j) tp.insert({l[i].first, l[j].first});
+        }
+        if (from_or_till_set)
+            for (const auto& e : l) ap.insert({e.first, e.first});
+        ap.insert(tp.begin(), tp.end());
+        if (n_true + (int)tp.size() > cap_pairs || n_all + (int)ap.size() > cap_pairs) {
+            siesta::set_error("more pairs than cap_pairs");
+            return SIESTA_E_INVALID;
+        }
+        for (const Pair& p : tp) { true_a[n_true] = p.first; true_b[n_true] = p.second; ++n_true; }
+        for (const Pair& p : ap) { all_a[n_all] = p.first; all_b[n_all] = p.second; ++n_all; }
+        true_off[x + 1] = n_true;
+        all_off[x + 1] = n_all;
+    }
+    *n_expansions = (int32_t)expansions.size();
+    return SIESTA_OK;
+}

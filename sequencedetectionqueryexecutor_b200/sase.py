@@ -100,11 +100,69 @@ class ComplexPattern:
         check(lib().siesta_pattern_compile(syms, n, cs, nc, 1 if only_appearances else 0, C.byref(nfa)))
         return nfa
 
+    def _c_arrays(self, activities):
+        n = len(self.eventsWithSymbols)
+        syms = (_abi.EventSymbolC * max(n, 1))()
+        for i, e in enumerate(self.eventsWithSymbols):
+            if e.symbol not in _SYM:
+                raise ValueError(f"unknown symbol {e.symbol!r}")
+            syms[i].activity, syms[i].position, syms[i].symbol = activities.id(e.name), e.position, _SYM[e.symbol]
+        nc = len(self.constraints)
+        cs = (_abi.ConstraintC * max(nc, 1))()
+        for i, c in enumerate(self.constraints):
+            cs[i].pos_a, cs[i].pos_b, cs[i].value = c.posA, c.posB, c.constraint
+            cs[i].kind = _abi.CONSTRAINT_TIME if isinstance(c, TimeConstraint) else _abi.CONSTRAINT_GAP
+            cs[i].method = _abi.METHOD_WITHIN if c.method == "within" else _abi.METHOD_ATLEAST
+            cs[i].granularity = _GRAN.get(getattr(c, "granularity", "seconds"), _abi.GRAN_SECONDS)
+        return syms, n, cs, nc
+
+    def extractPairsForPatternDetection(self, activities, fromOrTillSet=False):
+        """List of ExtractedPairsForPatternDetection, one per OR-expansion (ComplexPattern.java:75-128)."""
+        syms, n, cs, nc = self._c_arrays(activities)
+        cap_x, cap_p = 256, 4096
+        n_x = C.c_int32(0)
+        t_off, a_off = (C.c_int32 * (cap_x + 1))(), (C.c_int32 * (cap_x + 1))()
+        ta, tb, aa, ab = ((C.c_int32 * cap_p)() for _ in range(4))
+        check(lib().siesta_pattern_extract_pairs(syms, n, cs, nc, 1 if fromOrTillSet else 0, cap_x, cap_p, C.byref(n_x),
+                                                 t_off, ta, tb, a_off, aa, ab))
+        out = []
+        for x in range(n_x.value):
+            out.append(ExtractedPairsForPatternDetection(
+                truePairs=[(ta[k], tb[k]) for k in range(t_off[x], t_off[x + 1])],
+                allPairs=[(aa[k], ab[k]) for k in range(a_off[x], a_off[x + 1])]))
+        return out
+
     def getNfa(self, activities):
         return self._compile(activities, False)
 
     def getNfaWithoutConstraints(self, activities):
         return self._compile(activities, True)
+
+
+@dataclass
+class ExtractedPairsForPatternDetection:
+    """model/ExtractedPairsForPatternDetection.java: pairs as (activity id, activity id), sorted."""
+    truePairs: List[tuple]
+    allPairs: List[tuple]
+
+
+def pattern_candidates(pattern, log, activities, fromOrTillSet=False):
+    """DatabaseRepository.patterDetectionTraceIds under the SeqTable view (SparkDatabaseRepository.java:243-253 ->
+    getCommonIds :160-178, merged over the OR-expansions as QueryPlanPatternDetection.getMiddleResults :146-164 does):
+    ascending indices of the traces that hold every true pair of at least one expansion.  None when the pattern has
+    no true pair (the reference then takes the Single plan and verifies every trace holding the pattern's types)."""
+    exps = pattern.extractPairsForPatternDetection(activities, fromOrTillSet)
+    if any(len(x.truePairs) == 0 for x in exps):
+        return None
+    pairs = sorted({p for x in exps for p in x.truePairs})
+    if any(a < 0 or b < 0 for a, b in pairs):
+        return np.zeros(0, dtype=np.int64)  # a pattern activity the log has never seen: no trace can hold the pair
+    idx = log.build_index(pairs)
+    try:
+        pid = {p: i for i, p in enumerate(pairs)}
+        return idx.candidates([[pid[p] for p in x.truePairs] for x in exps])
+    finally:
+        idx.close()
 
 
 @dataclass

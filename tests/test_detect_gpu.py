@@ -259,3 +259,38 @@ def test_filter_variants_long_traces_large_alphabets_bad_ids(ctx):
     act[5::13] = 1 << 20
     _check(ctx, off, act, ts, 8, [dict(kind=N, types=[0]), dict(kind=N, types=[1])], 0)
     _check(ctx, off, act, ts, 8, [dict(kind=P_, types=[2]), dict(kind=S_, types=[3])], 0)
+
+
+def test_pruning_then_verification_equals_verifying_everything(ctx):
+    """Rows P1-P3 in front of V*: true pairs of the pattern (siesta_pattern_extract_pairs) -> posting lists of the
+    resident log (siesta_index_build) -> union over the OR-expansions of the per-expansion intersections
+    (siesta_candidates) -> siesta_detect(cand).  Under the SeqTable view a trace that lacks a true pair cannot match,
+    so the pruned run must return exactly what the unpruned run and the oracle return."""
+    from sequencedetectionqueryexecutor_b200 import sase
+    off, act, ts = gen.make_log(6000, 5, 40, 12, seed=61)
+    acts = sase.ActivityDictionary([f"act{i:02d}" for i in range(12)])
+    patterns = [
+        sase.ComplexPattern([sase.EventSymbol("act00", 0, "_"), sase.EventSymbol("act01", 1, "||"), sase.EventSymbol("act02", 1, "_"),
+                             sase.EventSymbol("act03", 2, "!"), sase.EventSymbol("act04", 3, "_"), sase.EventSymbol("act05", 4, "_")],
+                            [sase.GapConstraint(0, 1, 10, "within"), sase.GapConstraint(3, 4, 2, "atleast")]),
+        sase.ComplexPattern([sase.EventSymbol("act00", 0, "_"), sase.EventSymbol("act01", 1, "+"), sase.EventSymbol("act02", 2, "*"),
+                             sase.EventSymbol("act03", 3, "_")], []),
+        sase.ComplexPattern([sase.EventSymbol("act06", 0, "_"), sase.EventSymbol("act07", 1, "_"), sase.EventSymbol("act06", 2, "_")], []),
+    ]
+    log = ctx.load_log(off, act, ts, 12)
+    try:
+        for p in patterns:
+            cand = sase.pattern_candidates(p, log, acts)
+            exps = p.extractPairsForPatternDetection(acts)
+            want_c = np.zeros(0, dtype=np.int64)
+            for x in exps:  # oracle: intersection per expansion, union over expansions
+                want_c = np.union1d(want_c, oracle.intersect([oracle.posting_list(off, act, a, b) for a, b in x.truePairs]))
+            assert np.array_equal(cand, want_c)
+            assert 0 < len(cand) < 6000
+            nfa = p.getNfa(acts)
+            want = oracle.detect(off, act, ts, nfa, flags=abi.F_RETURN_ALL)
+            pruned = log.detect(nfa, cand=cand, flags=abi.F_RETURN_ALL)
+            ok, why = pruned.same_as(want)
+            assert ok, why
+    finally:
+        log.close()
