@@ -283,7 +283,11 @@ void siesta_device_free(siesta_log* log, void* d_ptr);
  * over the SeqTable view of the pair index (a trace is listed under (A,B) iff it holds an A before a B).
  * The result is ONE packed int64 array so that the multi-GPU combine is a single sum all-reduce:
  *   tot[A] uniq[A] first[A] last[A] hist[A][k_cap+1] co[A][A] ordered[A][A] response[A][A] precedence[A][A]
+ *   alt_response[A][A] alt_precedence[A][A] chain_response[A][A] chain_precedence[A][A]
  *   hist_overflow n_nonempty_traces
+ * alt_* / chain_*: the alternate and chain modes (orderedRelations/QueryPlanOrderedRelationsAlternate.java,
+ * ...Chain.java over OrderedRelationsUtilityFunctions.countResponseAlternate :51-60, countPrecedenceAlternate :67-76,
+ * countResponseChain :83-89, countPrecedenceChain :96-102).
  * (meaning of each block: oracle/counting_oracle.cpp).  Supports and thresholds (one double division each:
  * QueryPlanExistences templates :188-438, QueryPlanOrderedRelations.filterBasedOnSupport :161-233) stay with
  * the caller.  n_activities <= 104 (the A x A matrices live in shared memory). */
@@ -291,6 +295,40 @@ int64_t siesta_declare_counts_size(int32_t n_activities, int32_t k_cap);
 int siesta_declare_counts(siesta_log* log, int32_t k_cap, int64_t* out /* host, _size() values */, double* kernel_ms);
 int siesta_declare_counts_device(siesta_log* log, int32_t k_cap, int64_t* d_out /* device */, void* stream,
                                  double* kernel_ms);
+
+/* ------------------------------------------------------------- pair statistics */
+/* Kernel K4.  The record /stats returns per consecutive pair of the pattern (QueryPlanStats.execute, model/Queries/
+ * QueryPlans/QueryPlanStats.java:43-48; record: model/DBModel/Count.java:12-24).  In the reference the numbers are
+ * READ from count.parquet, which the separate, un-vendored SIESTA preprocess writes; here they are computed from the
+ * resident log under SIESTA's published pairing policy (non-overlapping skip-till-next-match pairs: first A, first B
+ * after it, continue after that B).  PARITY UNPINNED: no source or golden vector of the preprocess is in the
+ * reference repository.  Durations are ts_ms(B) - ts_ms(A); the sum of squares is exact (128 bit). */
+typedef struct siesta_pair_count {
+    int64_t count;
+    int64_t sum_duration_ms;
+    int64_t min_duration_ms; /* 0 when count == 0 */
+    int64_t max_duration_ms;
+    uint64_t sum_squares_lo, sum_squares_hi; /* sum of duration_ms^2 as a 128-bit integer */
+} siesta_pair_count;
+int siesta_pair_stats(siesta_log* log, const int32_t* pair_a, const int32_t* pair_b, int32_t n_pairs /* <= 32 */,
+                      siesta_pair_count* out, double* kernel_ms);
+/* Device form for the multi-GPU combine: d_out[8 * n_pairs] int64 = count, sum, min, max, and the sum of squares as
+ * four 32-bit limbs (one per int64).  count / sum / limbs combine with a SUM all-reduce (carry-normalise afterwards),
+ * min / max with MIN / MAX; with count == 0, min = INT64_MAX and max = INT64_MIN. */
+int siesta_pair_stats_device(siesta_log* log, const int32_t* pair_a, const int32_t* pair_b, int32_t n_pairs,
+                             int64_t* d_out, void* stream, double* kernel_ms);
+
+/* ------------------------------------------------------------------- /explore */
+/* Replaces QueryPlanExplorationAccurate.patternDetection (model/Queries/QueryPlans/Exploration/
+ * QueryPlanExplorationAccurate.java:82-102) for every candidate continuation: the pattern (all "_" events, a
+ * SimplePattern) extended by candidate c is detected with clearOccurrences(true) in every trace;
+ * completions[c] = number of occurrences, sum_duration_ms[c] = sum over them of last.timestamp - first.timestamp in
+ * milliseconds (Occurrence.getDuration, model/Occurrence.java:55-61, is this / 1000.0; 0 under SIESTA_F_EVT_POS,
+ * where events carry no timestamp).  The caller divides (average = sum / 1000.0 / completions) and sorts
+ * (Proposition.compareTo, model/Proposition.java:51-60).  flags: 0 or SIESTA_F_EVT_POS. */
+int siesta_explore_accurate(siesta_log* log, const int32_t* pattern_activities, int32_t n_pattern,
+                            const int32_t* candidates, int32_t n_candidates, uint32_t flags,
+                            int64_t* completions, int64_t* sum_duration_ms, double* kernel_ms);
 
 /* Number of kernels this library has launched in this process (bench.py's
  * gpu_launches). */

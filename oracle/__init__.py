@@ -103,6 +103,26 @@ def declare_counts(trace_off, act, n_activities, k_cap=64):
     return _abi.DeclareCounts(out, n_activities, k_cap)
 
 
+def pair_stats(trace_off, act, ts_ms, pairs):
+    """Pair statistics under the stated pairing policy (parity unpinned, see counting_oracle.cpp) ->
+    list of dicts count / sum / min / max / sum_squares (python int, exact)."""
+    L = lib()
+    trace_off = np.ascontiguousarray(trace_off, dtype=np.int64)
+    act = np.ascontiguousarray(act, dtype=np.int32)
+    ts_ms = np.ascontiguousarray(ts_ms, dtype=np.int64)
+    pa = np.array([p[0] for p in pairs], dtype=np.int32)
+    pb = np.array([p[1] for p in pairs], dtype=np.int32)
+    out = np.zeros(6 * len(pairs), dtype=np.int64)
+    L.oracle_pair_stats(_p(trace_off, C.c_int64), _p(act, C.c_int32), _p(ts_ms, C.c_int64), C.c_int64(len(trace_off) - 1),
+                        _p(pa, C.c_int32), _p(pb, C.c_int32), C.c_int32(len(pairs)), _p(out, C.c_int64))
+    res = []
+    for p in range(len(pairs)):
+        o = out[6 * p:6 * p + 6]
+        res.append({"count": int(o[0]), "sum": int(o[1]), "min": int(o[2]), "max": int(o[3]),
+                    "sum_squares": (int(o[4]) & (2 ** 64 - 1)) | ((int(o[5]) & (2 ** 64 - 1)) << 64)})
+    return res
+
+
 def posting_list(trace_off, act, a, b):
     L = lib()
     trace_off = np.ascontiguousarray(trace_off, dtype=np.int64)

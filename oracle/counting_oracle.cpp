@@ -21,12 +21,13 @@ extern "C" {
 
 /* Number of int64 values of the packed result (same layout as the product's siesta_declare_counts_device). */
 int64_t oracle_declare_size(int32_t A, int32_t k_cap) {
-    return 4ll * A + (int64_t)A * (k_cap + 1) + 4ll * A * A + 2;
+    return 4ll * A + (int64_t)A * (k_cap + 1) + 8ll * A * A + 2;
 }
 
 /*
  * Packed layout (int64): tot[A] uniq[A] first[A] last[A] hist[A][k_cap+1] co[A][A] ordered[A][A]
- *                        response[A][A] precedence[A][A] hist_overflow n_nonempty
+ *                        response[A][A] precedence[A][A] alt_response[A][A] alt_precedence[A][A]
+ *                        chain_response[A][A] chain_precedence[A][A] hist_overflow n_nonempty
  *
  *  tot[a]        total occurrences of a                  (S3Connector.querySingleTableDeclare :317-335 summed in
  *                                                         QueryPlanOrderedRelations.execute :73-77)
@@ -38,6 +39,9 @@ int64_t oracle_declare_size(int32_t A, int32_t k_cap) {
  *  response[a][b]   sum over traces listed under (a,b), a != b, of #{a : exists b after a}
  *                   (OrderedRelationsUtilityFunctions.countResponse :25-31 via joinTables :97-116)
  *  precedence[a][b] same with #{b : exists a before b}   (countPrecedence :38-44)
+ *  alt_response / alt_precedence / chain_response / chain_precedence: the same sums with
+ *                   countResponseAlternate :51-60, countPrecedenceAlternate :67-76, countResponseChain :83-89,
+ *                   countPrecedenceChain :96-102 (QueryPlanOrderedRelationsAlternate / ...Chain.evaluateConstraint)
  *  first[a]/last[a] traces whose first/last event is a   (QueryPlanPositions.execute :51-79)
  */
 int oracle_declare_counts(const int64_t* trace_off, const int32_t* act, int64_t n_traces, int32_t A, int32_t k_cap,
@@ -53,7 +57,11 @@ int oracle_declare_counts(const int64_t* trace_off, const int32_t* act, int64_t 
     int64_t* ordered = co + (int64_t)A * A;
     int64_t* response = ordered + (int64_t)A * A;
     int64_t* precedence = response + (int64_t)A * A;
-    int64_t* hist_overflow = precedence + (int64_t)A * A;
+    int64_t* alt_r = precedence + (int64_t)A * A;
+    int64_t* alt_p = alt_r + (int64_t)A * A;
+    int64_t* chain_r = alt_p + (int64_t)A * A;
+    int64_t* chain_p = chain_r + (int64_t)A * A;
+    int64_t* hist_overflow = chain_p + (int64_t)A * A;
     int64_t* n_nonempty = hist_overflow + 1;
 
     std::vector<std::vector<int>> pos((size_t)A);
@@ -101,6 +109,44 @@ int oracle_declare_counts(const int64_t* trace_off, const int32_t* act, int64_t 
                     }
                     response[(int64_t)a * A + b] += r;
                     precedence[(int64_t)a * A + b] += p;
+                    /* literal restatements of the alternate / chain counters; pos[] is ascending = the "sorted" lists */
+                    const std::vector<int>& la = pos[a];
+                    const std::vector<int>& lb = pos[b];
+                    int64_t ar = 0, ap = 0, cr = 0, cp = 0;
+                    for (size_t i = 0; i + 1 < la.size(); ++i) {
+                        bool any = false;
+                        for (int y : lb) any = any || (y > la[i] && y < la[i + 1]);
+                        ar += any;
+                    }
+                    {
+                        bool any = false;
+                        for (int y : lb) any = any || y > la.back();
+                        ar += any;
+                    }
+                    for (size_t i = 1; i < lb.size(); ++i) {
+                        bool any = false;
+                        for (int y : la) any = any || (y < lb[i] && y > lb[i - 1]);
+                        ap += any;
+                    }
+                    {
+                        bool any = false;
+                        for (int y : la) any = any || y < lb[0];
+                        ap += any;
+                    }
+                    for (int x : la) {
+                        bool any = false;
+                        for (int y : lb) any = any || y == x + 1;
+                        cr += any;
+                    }
+                    for (int y : lb) {
+                        bool any = false;
+                        for (int x : la) any = any || x == y - 1;
+                        cp += any;
+                    }
+                    alt_r[(int64_t)a * A + b] += ar;
+                    alt_p[(int64_t)a * A + b] += ap;
+                    chain_r[(int64_t)a * A + b] += cr;
+                    chain_p[(int64_t)a * A + b] += cp;
                 }
             }
         }
@@ -136,6 +182,48 @@ int64_t oracle_intersect(const int64_t* const* lists, const int64_t* lens, int32
     }
     std::copy(cur.begin(), cur.end(), out);
     return (int64_t)cur.size();
+}
+
+/*
+ * Pair statistics behind /stats.  PARITY UNPINNED: the reference only READS these numbers from count.parquet
+ * (QueryPlanStats.execute, J/model/Queries/QueryPlans/QueryPlanStats.java:43-48; J/model/DBModel/Count.java:12-24);
+ * the table is written by the SIESTA preprocess component, which is not in the reference repository.  This restates
+ * the pairing policy SIESTA publishes for its index — non-overlapping skip-till-next-match pairs: per trace and pair
+ * (a,b) take the first a, the first b after it, emit (a,b), continue after that b — so the oracle and the GPU kernel
+ * agree on a stated definition, not on a reference run.
+ * out[p] = count, sum, min, max (0 if none), sum of squares low / high 64 bits.
+ */
+int oracle_pair_stats(const int64_t* trace_off, const int32_t* act, const int64_t* ts_ms, int64_t n_traces,
+                      const int32_t* pair_a, const int32_t* pair_b, int32_t n_pairs, int64_t* out) {
+    for (int p = 0; p < n_pairs; ++p) {
+        int64_t cnt = 0, sum = 0, mn = 0, mx = 0;
+        unsigned __int128 sq = 0;
+        for (int64_t t = 0; t < n_traces; ++t) {
+            bool waiting_b = false;
+            int64_t ta = 0;
+            for (int64_t i = trace_off[t]; i < trace_off[t + 1]; ++i) {
+                if (waiting_b) {
+                    if (act[i] == pair_b[p]) {
+                        const int64_t d = ts_ms[i] - ta;
+                        mn = cnt == 0 ? d : std::min(mn, d);
+                        mx = cnt == 0 ? d : std::max(mx, d);
+                        ++cnt;
+                        sum += d;
+                        sq += (unsigned __int128)((__int128)d * (__int128)d);
+                        waiting_b = false;
+                    }
+                } else if (act[i] == pair_a[p]) {
+                    waiting_b = true;
+                    ta = ts_ms[i];
+                }
+            }
+        }
+        int64_t* o = out + (int64_t)p * 6;
+        o[0] = cnt; o[1] = sum; o[2] = mn; o[3] = mx;
+        o[4] = (int64_t)(uint64_t)sq;
+        o[5] = (int64_t)(uint64_t)(sq >> 64);
+    }
+    return 0;
 }
 
 }  /* extern "C" */

@@ -58,6 +58,11 @@ class Matches(C.Structure):
                 ("kernel_ms", C.c_double), ("detect_ms", C.c_double)]
 
 
+class PairCount(C.Structure):
+    _fields_ = [("count", C.c_int64), ("sum_duration_ms", C.c_int64), ("min_duration_ms", C.c_int64),
+                ("max_duration_ms", C.c_int64), ("sum_squares_lo", C.c_uint64), ("sum_squares_hi", C.c_uint64)]
+
+
 class DevMatches(C.Structure):
     _fields_ = [("n_traces", C.c_int64), ("n_occurrences", C.c_int64), ("n_events", C.c_int64),
                 ("n_matches_emitted", C.c_int64), ("n_ref_errors", C.c_int64),
@@ -185,5 +190,9 @@ class DeclareCounts:
         self.ordered = self.packed[o:o + A * A].reshape(A, A); o += A * A
         self.response = self.packed[o:o + A * A].reshape(A, A); o += A * A
         self.precedence = self.packed[o:o + A * A].reshape(A, A); o += A * A
+        self.alt_response = self.packed[o:o + A * A].reshape(A, A); o += A * A
+        self.alt_precedence = self.packed[o:o + A * A].reshape(A, A); o += A * A
+        self.chain_response = self.packed[o:o + A * A].reshape(A, A); o += A * A
+        self.chain_precedence = self.packed[o:o + A * A].reshape(A, A); o += A * A
         self.hist_overflow = int(self.packed[o])
         self.n_nonempty = int(self.packed[o + 1])

@@ -17,7 +17,8 @@ EXPORTS = [
     "siesta_kernel_launches", "siesta_declare_counts_size", "siesta_declare_counts", "siesta_declare_counts_device",
     "siesta_index_load", "siesta_index_build", "siesta_index_free", "siesta_index_list_len", "siesta_index_get_list",
     "siesta_intersect", "siesta_intersect_device", "siesta_device_free", "siesta_pattern_extract_pairs",
-    "siesta_candidates", "siesta_candidates_device",
+    "siesta_candidates", "siesta_candidates_device", "siesta_pair_stats", "siesta_pair_stats_device",
+    "siesta_explore_accurate",
 ]
 
 
@@ -76,6 +77,9 @@ def lib():
                                                P32, P32, P32, P32, P32, P32]
     L.siesta_candidates.argtypes = [vp, vp, vp, i32, vp, i64, P(i64)]
     L.siesta_candidates_device.argtypes = [vp, vp, vp, i32, P(vp), P(i64), P(C.c_double)]
+    L.siesta_pair_stats.argtypes = [vp, vp, vp, i32, P(_abi.PairCount), P(C.c_double)]
+    L.siesta_pair_stats_device.argtypes = [vp, vp, vp, i32, vp, vp, P(C.c_double)]
+    L.siesta_explore_accurate.argtypes = [vp, vp, i32, vp, i32, u32, vp, vp, P(C.c_double)]
     L.siesta_device_free.argtypes = [vp, vp]
     L.siesta_device_free.restype = None
     _lib = L

@@ -123,6 +123,36 @@ class EventLog:
         return ms.value
 
 
+    def pair_stats(self, pairs):
+        """siesta_pair_stats: the Count record of each (A,B) pair (kernel K4) -> list of dicts with exact python ints."""
+        pa = np.array([p[0] for p in pairs], dtype=np.int32)
+        pb = np.array([p[1] for p in pairs], dtype=np.int32)
+        out = (_abi.PairCount * len(pairs))()
+        ms = C.c_double(0.0)
+        check(lib().siesta_pair_stats(self._h, _ptr(pa), _ptr(pb), len(pairs), out, C.byref(ms)))
+        return [{"count": o.count, "sum": o.sum_duration_ms, "min": o.min_duration_ms, "max": o.max_duration_ms,
+                 "sum_squares": o.sum_squares_lo | (o.sum_squares_hi << 64)} for o in out], ms.value
+
+    def pair_stats_device(self, pairs, d_out, stream=None):
+        """siesta_pair_stats_device: packed int64[8 * n_pairs] (count, sum, min, max, 4 limbs) into a CUDA tensor."""
+        pa = np.array([p[0] for p in pairs], dtype=np.int32)
+        pb = np.array([p[1] for p in pairs], dtype=np.int32)
+        ms = C.c_double(0.0)
+        check(lib().siesta_pair_stats_device(self._h, _ptr(pa), _ptr(pb), len(pairs), C.c_void_p(d_out.data_ptr()),
+                                             C.c_void_p(stream) if stream else None, C.byref(ms)))
+        return ms.value
+
+    def explore_accurate(self, pattern_activities, candidates, flags=0):
+        """siesta_explore_accurate -> (completions int64[n], sum_duration_ms int64[n], kernel_ms)."""
+        pa = np.asarray(pattern_activities, dtype=np.int32)
+        ca = np.asarray(candidates, dtype=np.int32)
+        comp = np.zeros(max(len(ca), 1), dtype=np.int64)
+        dur = np.zeros(max(len(ca), 1), dtype=np.int64)
+        ms = C.c_double(0.0)
+        check(lib().siesta_explore_accurate(self._h, _ptr(pa), len(pa), _ptr(ca), len(ca), flags, _ptr(comp), _ptr(dur),
+                                            C.byref(ms)))
+        return comp[:len(ca)], dur[:len(ca)], ms.value
+
     def build_index(self, pairs):
         """siesta_index_build: posting lists of the (A,B) pairs from the resident log (SeqTable view)."""
         return PairIndex(self, pairs)

@@ -175,9 +175,95 @@ __global__ void __launch_bounds__(DT) declare_kernel(const __grid_constant__ Dec
         }
     }
     if (threadIdx.x == 0) {
-        if (s_misc[0]) atomicAdd(o_prec + AA, s_misc[0]);
-        if (s_misc[1]) atomicAdd(o_prec + AA + 1, s_misc[1]);
+        if (s_misc[0]) atomicAdd(o_prec + 5ll * AA, s_misc[0]);
+        if (s_misc[1]) atomicAdd(o_prec + 5ll * AA + 1, s_misc[1]);
     }
+}
+
+// Alternate and chain modes of the ordered relations (OrderedRelationsUtilityFunctions.java:51-102).  Per trace listed
+// under (a,b), a != b:
+//   countResponseAlternate   = #{ i : some b strictly between a_i and a_(i+1) } + [some b after the last a]
+//   countPrecedenceAlternate = #{ i : some a strictly between b_(i-1) and b_i } + [some a before the first b]
+// Both count the b's whose nearest earlier event among {a, b} is an a, so they are equal; likewise
+//   countResponseChain = #{a : b at position a + 1} = #{b : a at position b - 1} = countPrecedenceChain.
+// (tests/test_counting_oracle.py checks the four literal restatements of the oracle against each other.)
+// One warp per trace, serial over the events, lanes = activities: lane o keeps the last position of activity o; at an
+// event of activity x every lane whose last position is later than x's previous one adds 1 to alternate[o][x].
+template <int NB>
+__global__ void __launch_bounds__(DT) declare_alt_chain_kernel(const __grid_constant__ DeclareParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int A = P.A;
+    const int AA = A * A;
+    uint32_t* s_altT = reinterpret_cast<uint32_t*>(smem_raw);  // transposed: [x][o] = alternate[o][x]
+    uint32_t* s_chain = s_altT + AA;                           // [a][b]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 2 * AA; i += DT) s_altT[i] = 0;
+    __syncthreads();
+    const long long warps_total = (long long)gridDim.x * (DT / 32);
+    for (long long t = (long long)blockIdx.x * (DT / 32) + warp; t < P.n_traces; t += warps_total) {
+        long long lo = 0, hi = 0;
+        if (lane == 0) { lo = P.trace_off[t]; hi = P.trace_off[t + 1]; }
+        lo = shfl64(lo, 0);
+        hi = shfl64(hi, 0);
+        const int len = (int)(hi - lo);
+        int last_r[NB];
+#pragma unroll
+        for (int kb = 0; kb < NB; ++kb) last_r[kb] = -1;
+        int px = -1;  // activity of the previous event
+        for (int base = 0; base < len; base += 32) {
+            const int mine = base + lane < len ? __ldg(P.act + lo + base + lane) : -1;  // 32 events per coalesced load
+            const int n_here = len - base < 32 ? len - base : 32;
+            for (int k = 0; k < n_here; ++k) {
+                const int x = __shfl_sync(0xffffffffu, mine, k);
+                const int i = base + k;
+                if (x < 0 || x >= A) { px = -1; continue; }
+                int prev = -1;  // previous position of x: register (x >> 5) of lane (x & 31)
+#pragma unroll
+                for (int kb = 0; kb < NB; ++kb)
+                    if ((x >> 5) == kb) prev = __shfl_sync(0xffffffffu, last_r[kb], x & 31);
+#pragma unroll
+                for (int kb = 0; kb < NB; ++kb) {
+                    const int o = kb * 32 + lane;
+                    if (o < A && o != x && last_r[kb] > prev) atomicAdd(&s_altT[x * A + o], 1u);
+                    if (o == x) last_r[kb] = i;
+                }
+                if (lane == 0 && px >= 0 && px != x) atomicAdd(&s_chain[px * A + x], 1u);
+                px = x;
+            }
+        }
+    }
+    __syncthreads();
+    unsigned long long* o_alt_r = P.out + 4ll * A + (long long)A * (P.k_cap + 1) + 4ll * AA;
+    unsigned long long* o_alt_p = o_alt_r + AA;
+    unsigned long long* o_chain_r = o_alt_p + AA;
+    unsigned long long* o_chain_p = o_chain_r + AA;
+    for (int i = threadIdx.x; i < AA; i += DT) {
+        if (s_altT[i]) {
+            const int x = i / A, o = i % A;
+            atomicAdd(o_alt_r + (long long)o * A + x, (unsigned long long)s_altT[i]);
+            atomicAdd(o_alt_p + (long long)o * A + x, (unsigned long long)s_altT[i]);
+        }
+        if (s_chain[i]) {
+            atomicAdd(o_chain_r + i, (unsigned long long)s_chain[i]);
+            atomicAdd(o_chain_p + i, (unsigned long long)s_chain[i]);
+        }
+    }
+}
+
+template <int NB>
+static int launch_alt_chain(const Ctx* ctx, cudaStream_t stream, const DeclareParams& P) {
+    const size_t smem = sizeof(uint32_t) * (size_t)2 * P.A * P.A;
+    auto kern = declare_alt_chain_kernel<NB>;
+    SIESTA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DT, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t ctas_needed = (P.n_traces + DT / 32 - 1) / (DT / 32);
+    int grid = (int)std::min<int64_t>(std::max<int64_t>(ctas_needed, 1), (int64_t)ctx->sm_count * per_sm);
+    kern<<<grid, DT, smem, stream>>>(P);
+    SIESTA_LAUNCHED();
+    SIESTA_CUDA_OK(cudaGetLastError());
+    return SIESTA_OK;
 }
 
 static size_t declare_smem(int A) { return sizeof(uint32_t) * ((size_t)4 * A * A + 4 * A + (size_t)A * HS + (size_t)(DT / 32) * 3 * A); }
@@ -203,7 +289,7 @@ static int launch_declare(const Ctx* ctx, cudaStream_t stream, const DeclarePara
 using namespace siesta;
 
 extern "C" int64_t siesta_declare_counts_size(int32_t A, int32_t k_cap) {
-    return 4ll * A + (int64_t)A * (k_cap + 1) + 4ll * A * A + 2;
+    return 4ll * A + (int64_t)A * (k_cap + 1) + 8ll * A * A + 2;
 }
 
 extern "C" int siesta_declare_counts_device(siesta_log* log, int32_t k_cap, int64_t* d_out, void* stream_, double* kernel_ms) {
@@ -237,6 +323,11 @@ extern "C" int siesta_declare_counts_device(siesta_log* log, int32_t k_cap, int6
     else if (nb == 2) rc = launch_declare<2>(L->ctx, stream, P);
     else if (nb == 3) rc = launch_declare<3>(L->ctx, stream, P);
     else rc = launch_declare<4>(L->ctx, stream, P);
+    if (rc) return rc;
+    if (nb == 1) rc = launch_alt_chain<1>(L->ctx, stream, P);
+    else if (nb == 2) rc = launch_alt_chain<2>(L->ctx, stream, P);
+    else if (nb == 3) rc = launch_alt_chain<3>(L->ctx, stream, P);
+    else rc = launch_alt_chain<4>(L->ctx, stream, P);
     if (rc) return rc;
     SIESTA_CUDA_OK(cudaEventRecord(e1, stream));
     SIESTA_CUDA_OK(cudaStreamSynchronize(stream));

@@ -227,3 +227,36 @@ class SaseConnector:
             tid = self.trace_ids[t] if self.trace_ids is not None else int(t)
             out.append(Occurrences(tid, occs))
         return out
+
+
+@dataclass
+class Proposition:
+    """model/Proposition.java: a possible continuation, its exact completions and the average duration (seconds)."""
+    event: str
+    completions: int
+    averageDuration: float
+
+    def score(self):
+        # Proposition.compareTo (:51-60): completions / averageDuration (IEEE: x / 0.0 = inf, as in Java)
+        return self.completions / self.averageDuration if self.averageDuration != 0 else float("inf")
+
+
+def explore_accurate(pattern_names, log, activities: ActivityDictionary, candidates=None, positions_mode=False):
+    """QueryPlanExplorationAccurate.execute (model/Queries/QueryPlans/Exploration/QueryPlanExplorationAccurate.java:
+    54-72): for every possible next event after the pattern's last event, the exact number of occurrences of the
+    extended pattern and their average duration, sorted best first (Collections.reverseOrder over compareTo).
+    `candidates` defaults to the activities that follow the last event in some trace (the CountTable rows with
+    eventA = last event)."""
+    ids = [activities.id(n) for n in pattern_names]
+    if candidates is None:
+        d = log.declare_counts()
+        candidates = [b for b in range(len(activities)) if ids[-1] >= 0 and d.ordered[ids[-1], b] > 0]
+    else:
+        candidates = [activities.id(c) if isinstance(c, str) else int(c) for c in candidates]
+    comp, dur, _ = log.explore_accurate(ids, candidates, _abi.F_EVT_POS if positions_mode else 0)
+    props = [Proposition(activities.names[c], int(n), (int(ms) / 1000.0) / int(n))
+             for c, n, ms in zip(candidates, comp, dur) if n > 0]
+    # reverse order of compareTo: higher score first; equal scores: compareTo falls back to t.event.compareTo(this.event),
+    # reversed once more by reverseOrder -> ascending event name
+    props.sort(key=lambda p: (-p.score(), p.event))
+    return props

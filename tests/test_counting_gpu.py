@@ -25,7 +25,8 @@ def test_declare_counts_match_oracle(ctx, n_act, n_traces, lens, zipf):
     got = log.declare_counts(k_cap=40)
     log.close()
     want = oracle.declare_counts(off, act, n_act, 40)
-    for name in ("tot", "uniq", "first", "last", "hist", "co", "ordered", "response", "precedence"):
+    for name in ("tot", "uniq", "first", "last", "hist", "co", "ordered", "response", "precedence", "alt_response",
+                 "alt_precedence", "chain_response", "chain_precedence"):
         assert np.array_equal(getattr(got, name), getattr(want, name)), name
     assert got.hist_overflow == want.hist_overflow and got.n_nonempty == want.n_nonempty
 
@@ -86,3 +87,22 @@ def test_pruning_then_verification_pipeline(ctx):
     assert len(cand) < 8000 and pruned.same_as(full)[0]
     want = oracle.detect(off, act, ts, nfa, cand=cand)
     assert pruned.same_as(want)[0]
+
+
+def test_pair_stats_match_oracle(ctx):
+    """Kernel K4 against the oracle's restatement of the stated pairing policy (both unpinned by the reference)."""
+    off, act, ts = gen.make_log(4000, 0, 80, 9, seed=71, jitter_ms=True)
+    pairs = [(a, b) for a in range(9) for b in range(9)][:32]
+    log = ctx.load_log(off, act, ts, 9)
+    got, ms = log.pair_stats(pairs)
+    assert got == oracle.pair_stats(off, act, ts, pairs)
+    # a pair nobody holds, an activity outside the alphabet, durations of years (128-bit sum of squares)
+    off2 = np.array([0, 4], dtype=np.int64)
+    act2 = np.array([0, 1, 0, 1], dtype=np.int32)
+    ts2 = np.array([0, 3_000_000_000_000, 3_000_000_000_001, 9_000_000_000_000], dtype=np.int64)
+    log2 = ctx.load_log(off2, act2, ts2, 3)
+    got2, _ = log2.pair_stats([(0, 1), (2, 0), (7, 1)])
+    assert got2 == oracle.pair_stats(off2, act2, ts2, [(0, 1), (2, 0), (7, 1)])
+    assert got2[0]["sum_squares"] > 2 ** 64 and got2[1]["count"] == 0
+    log2.close()
+    log.close()

@@ -19,6 +19,11 @@ def test_hand_example():
     # countResponse(A,B) on t0: both A's have a later B -> 2 ; countPrecedence(A,C) on t0: the C has an earlier A -> 1
     assert d.response.tolist() == [[0, 2, 2], [1, 0, 1], [2, 1, 0]]
     assert d.precedence.tolist() == [[0, 2, 1], [1, 0, 1], [1, 1, 0]]
+    # alternate: A=[0,2] B=[1,4] on t0 -> a B inside (0,2) and one after 2 -> 2 ; chain: only "A B" at 0,1 -> 1
+    assert d.alt_response.tolist() == [[0, 2, 1], [1, 0, 1], [1, 1, 0]]
+    assert d.alt_precedence.tolist() == d.alt_response.tolist()
+    assert d.chain_response.tolist() == [[0, 1, 1], [1, 0, 0], [1, 1, 0]]
+    assert d.chain_precedence.tolist() == d.chain_response.tolist()
     assert oracle.posting_list(off, act, 0, 1).tolist() == [0]
     assert oracle.posting_list(off, act, 2, 0).tolist() == [2]
     assert oracle.posting_list(off, act, 2, 2).tolist() == [2]
@@ -44,6 +49,35 @@ def test_identities_on_random_log():
                 assert both == d.co[a, b]                                  # joinUnionTraces
                 assert (d.response[a, b] > 0) == (d.ordered[a, b] > 0) == (d.precedence[a, b] > 0)
                 assert d.response[a, b] <= d.tot[a] and d.precedence[a, b] <= d.tot[b]
+    # the four literal restatements of the alternate / chain counters: response and precedence forms count the same
+    # events, chain <= alternate <= simple
+    assert np.array_equal(d.alt_response, d.alt_precedence) and np.array_equal(d.chain_response, d.chain_precedence)
+    assert np.all(d.chain_response <= d.alt_response) and np.all(d.alt_response <= d.response)
+    assert np.all(d.alt_precedence <= d.precedence)
+    # chain = adjacent pairs of different activities
+    adj = np.zeros((A, A), dtype=np.int64)
+    for t in range(len(off) - 1):
+        tr = act[off[t]:off[t + 1]]
+        for x, y in zip(tr[:-1], tr[1:]):
+            if x != y:
+                adj[x, y] += 1
+    assert np.array_equal(adj, d.chain_response)
     # histogram cap: occurrences beyond k_cap are reported, not dropped silently
     d2 = oracle.declare_counts(off, act, A, 2)
     assert d2.hist_overflow == d.hist[:, 3:].sum()
+
+
+def test_pair_stats_hand_example():
+    """Stated pairing policy (parity unpinned: the producer of count.parquet is not in the reference repository):
+    non-overlapping skip-till-next-match pairs."""
+    # t0 = A A B A B B (ts 0,1,3,6,10,15 s) ; t1 = B A ; t2 = A A A A   (A=0, B=1)
+    off = np.array([0, 6, 8, 12])
+    act = np.array([0, 0, 1, 0, 1, 1, 1, 0, 0, 0, 0, 0], dtype=np.int32)
+    ts = np.array([0, 1, 3, 6, 10, 15, 0, 5, 0, 2, 5, 9], dtype=np.int64) * 1000
+    ab, aa, ba = oracle.pair_stats(off, act, ts, [(0, 1), (0, 0), (1, 0)])
+    # (A,B) on t0: (0 -> 3) and (6 -> 10): durations 3 s, 4 s
+    assert ab == {"count": 2, "sum": 7000, "min": 3000, "max": 4000, "sum_squares": 3000 ** 2 + 4000 ** 2}
+    # (A,A): t0 pairs (0,1) then the third A waits; t2 pairs (0,2) and (5,9)
+    assert aa == {"count": 3, "sum": 1000 + 2000 + 4000, "min": 1000, "max": 4000, "sum_squares": 1000 ** 2 + 2000 ** 2 + 4000 ** 2}
+    # (B,A): t0 (3 -> 6), then B at 10 waits for an A that never comes; t1 (0 -> 5)
+    assert ba == {"count": 2, "sum": 8000, "min": 3000, "max": 5000, "sum_squares": 3000 ** 2 + 5000 ** 2}

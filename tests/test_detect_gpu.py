@@ -294,3 +294,28 @@ def test_pruning_then_verification_equals_verifying_everything(ctx):
             assert ok, why
     finally:
         log.close()
+
+
+def test_explore_accurate_matches_per_candidate_detection(ctx):
+    """Row X: siesta_explore_accurate = for every candidate, detection of pattern + candidate with
+    clearOccurrences(true); completions and summed durations must equal what the oracle's detection gives."""
+    from sequencedetectionqueryexecutor_b200 import sase
+    n_act = 12
+    off, act, ts = gen.make_log(5000, 10, 50, n_act, seed=81, jitter_ms=True)
+    acts = sase.ActivityDictionary([f"act{i:02d}" for i in range(n_act)])
+    base = [0, 1]
+    log = ctx.load_log(off, act, ts, n_act)
+    try:
+        comp, dur, _ = log.explore_accurate(base, list(range(n_act)))
+        for c in range(n_act):
+            nfa = abi.make_nfa([dict(kind=N_, types=[x]) for x in base + [c]])
+            want = oracle.detect(off, act, ts, nfa, flags=abi.F_RETURN_ALL)
+            assert comp[c] == want.n_occurrences, c
+            d = sum(int(want.ev_ts_ms[want.ev_off[o + 1] - 1] - want.ev_ts_ms[want.ev_off[o]]) for o in range(want.n_occurrences))
+            assert dur[c] == d, c
+        props = sase.explore_accurate(["act00", "act01"], log, acts)
+        assert [p.event for p in props] == [p.event for p in sorted(props, key=lambda p: (-p.completions / p.averageDuration, p.event))]
+        assert {p.event for p in props} == {acts.names[c] for c in range(n_act) if comp[c] > 0}
+        assert all(abs(p.averageDuration - dur[acts.id(p.event)] / 1000.0 / p.completions) < 1e-9 for p in props)
+    finally:
+        log.close()
