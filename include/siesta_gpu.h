@@ -162,6 +162,9 @@ int siesta_log_load(siesta_ctx* ctx, const int64_t* trace_off, const int32_t* ac
 int siesta_log_wrap_device(siesta_ctx* ctx, const int64_t* d_trace_off, const int32_t* d_act,
                            const int64_t* d_ts_ms, int64_t n_traces, int64_t n_events,
                            int32_t n_activities, int32_t max_trace_len, siesta_log** out);
+/* Multi-GPU: this log is the shard [first_trace, first_trace + n_traces) of a larger log.  Every trace index the
+ * library RETURNS for it (trace_idx, err_trace_idx) is then global; candidate lists stay local to the shard. */
+void siesta_log_set_first_trace(siesta_log* log, int64_t first_trace);
 void siesta_log_free(siesta_log* log);
 int64_t siesta_log_n_traces(const siesta_log* log);
 int64_t siesta_log_n_events(const siesta_log* log);
@@ -235,6 +238,11 @@ typedef struct siesta_dev_matches {
     int64_t* d_err_trace_idx;
     double kernel_ms;
     double detect_ms;
+    /* all eight arrays above live in ONE device allocation [d_block, d_block + block_bytes), each at a 256-byte
+     * aligned offset, in the order trace_idx, occ_off, ev_off, ev_pos, err_trace_idx, ev_rank, ev_act, ev_ts_ms:
+     * the multi-GPU exchange ships the block with a single all-gather */
+    void* d_block;
+    int64_t block_bytes;
     void* impl;
 } siesta_dev_matches;
 

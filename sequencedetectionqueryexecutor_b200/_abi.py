@@ -69,7 +69,8 @@ class DevMatches(C.Structure):
                 ("d_trace_idx", C.c_void_p), ("d_occ_off", C.c_void_p), ("d_ev_off", C.c_void_p),
                 ("d_ev_pos", C.c_void_p), ("d_ev_rank", C.c_void_p), ("d_ev_act", C.c_void_p),
                 ("d_ev_ts_ms", C.c_void_p), ("d_err_trace_idx", C.c_void_p),
-                ("kernel_ms", C.c_double), ("detect_ms", C.c_double), ("impl", C.c_void_p)]
+                ("kernel_ms", C.c_double), ("detect_ms", C.c_double), ("d_block", C.c_void_p), ("block_bytes", C.c_int64),
+                ("impl", C.c_void_p)]
 
 
 def make_nfa(states):

@@ -18,7 +18,7 @@ EXPORTS = [
     "siesta_index_load", "siesta_index_build", "siesta_index_free", "siesta_index_list_len", "siesta_index_get_list",
     "siesta_intersect", "siesta_intersect_device", "siesta_device_free", "siesta_pattern_extract_pairs",
     "siesta_candidates", "siesta_candidates_device", "siesta_pair_stats", "siesta_pair_stats_device",
-    "siesta_explore_accurate",
+    "siesta_explore_accurate", "siesta_log_set_first_trace",
 ]
 
 
@@ -45,6 +45,8 @@ def lib():
     L.siesta_shutdown.restype = None
     L.siesta_log_load.argtypes = [vp, vp, vp, vp, i64, i64, i32, P(vp)]
     L.siesta_log_wrap_device.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, P(vp)]
+    L.siesta_log_set_first_trace.argtypes = [vp, i64]
+    L.siesta_log_set_first_trace.restype = None
     L.siesta_log_free.argtypes = [vp]
     L.siesta_log_free.restype = None
     L.siesta_log_n_traces.argtypes = [vp]

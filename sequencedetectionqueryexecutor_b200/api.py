@@ -79,6 +79,10 @@ class EventLog:
         self.n_traces = lib().siesta_log_n_traces(self._h)
         self.n_events = lib().siesta_log_n_events(self._h)
 
+    def set_first_trace(self, first_trace):
+        """This log is the shard starting at global trace `first_trace`: returned trace indices become global."""
+        lib().siesta_log_set_first_trace(self._h, int(first_trace))
+
     def close(self):
         if self._h:
             lib().siesta_log_free(self._h)
@@ -222,6 +226,20 @@ class DeviceMatches:
         if self.dm is not None:
             lib().siesta_dev_matches_free(C.byref(self.dm))
             self.dm = None
+
+    def block(self, device_index=0):
+        """The whole result as one uint8 CUDA tensor (zero-copy view of the library's allocation; valid until close())
+        plus its header (n_traces, n_occurrences, n_events, n_ref_errors, has_event_columns); see distributed.py."""
+        import torch
+
+        class _View:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+        d = self.dm
+        t = (torch.as_tensor(_View(d.d_block, d.block_bytes), device=f"cuda:{device_index}") if d.block_bytes
+             else torch.zeros(0, dtype=torch.uint8, device=f"cuda:{device_index}"))
+        return t, (d.n_traces, d.n_occurrences, d.n_events, d.n_ref_errors, 1 if d.d_ev_rank else 0)
 
     def tensors(self, device_index=0):
         """Zero-copy torch views of the device result (valid until close()); keys as in MatchResult."""

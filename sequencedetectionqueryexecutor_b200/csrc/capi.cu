@@ -190,6 +190,10 @@ extern "C" int siesta_log_wrap_device(siesta_ctx* ctx, const int64_t* d_trace_of
     return SIESTA_OK;
 }
 
+extern "C" void siesta_log_set_first_trace(siesta_log* log, int64_t first_trace) {
+    if (log) reinterpret_cast<Log*>(log)->first_trace = first_trace;
+}
+
 extern "C" void siesta_log_free(siesta_log* log) {
     if (!log) return;
     Log* L = reinterpret_cast<Log*>(log);

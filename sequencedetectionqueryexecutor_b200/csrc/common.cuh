@@ -52,6 +52,7 @@ struct Log {
     int32_t n_activities = 0;
     int32_t max_trace_len = 0;
     bool owns = false;
+    int64_t first_trace = 0;  // global index of trace 0 (multi-GPU shards)
     bool act_valid = false;  // every activity id lies in [0, n_activities): kernels may skip the per-event range check
 };
 

@@ -41,6 +41,7 @@ struct DetectParams {
     int64_t n_work;           // number of traces this launch verifies ...
     const unsigned long long* n_work_dev;  // ... or, if set, read from device memory (the narrow launch's overflow count)
     int32_t ovf_slot;         // counter that counts the traces this launch could not hold (4 narrow, 7 wide)
+    int32_t tile_slot;        // counter that hands out tiles (11 narrow, 12 wide)
     const uint16_t* lut;      // [n_act] smask | fmask << 8
     // alpha_mode 0/1: the pattern's activities are numbered 1..K (K <= 7, "class"); plane p holds, bit-reversed, the
     // activities whose class has bit p set (ids 0..31 in [p][0], 32..63 in [p][1]); cls_word / cls_act give the lut
@@ -67,7 +68,8 @@ struct DetectParams {
     int32_t* s_ev_act;
     int64_t* s_ev_ts;
     int64_t cap_occ, cap_ev;
-    // counters: 0 occ reserved, 1 ev reserved, 2 emitted, 3 errors, 4 overflow, 5 staging overflow, 6 matched traces
+    // counters: 0 occ reserved, 1 ev reserved, 2 emitted, 3 errors, 4 overflow, 5 staging overflow, 6 matched traces,
+    // 7 wide overflow, 8-10 phase timing, 11 / 12 next tile of the narrow / wide launch
     unsigned long long* counters;
     int64_t* err_list;
     int64_t* ovf_list;
@@ -201,11 +203,18 @@ __global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4)
     const bool all_cols = (P.flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
     const bool prune = (P.flags & SIESTA_F_LITERAL_RUNS) == 0;
     const bool dedup = prune && !return_all && (P.flags & SIESTA_F_COUNT_MATCHES) == 0;
-    const int warps_per_cta = blockDim.x >> 5;
 
     const long long n_work = P.n_work_dev ? (long long)__ldg(P.n_work_dev) : (long long)P.n_work;
     const long long n_tiles = (n_work + 31) / 32;
-    for (long long tile = (long long)blockIdx.x * warps_per_cta + warp; tile < n_tiles; tile += (long long)gridDim.x * warps_per_cta) {
+    // Tiles are handed out by an atomic counter, not by a static stride: when another kernel (an NCCL all-gather of the
+    // previous request's results, a copy) holds some SMs, the CTAs that start late simply take fewer tiles.  The next
+    // tile is requested at the top of the loop so that the atomic's latency hides behind the current tile.
+    long long tile = 0;
+    if (lane == 0) tile = (long long)atomicAdd(P.counters + P.tile_slot, 1ull);
+    tile = shfl_i64(tile, 0);
+    while (tile < n_tiles) {
+        long long next_tile = 0;
+        if (lane == 0) next_tile = (long long)atomicAdd(P.counters + P.tile_slot, 1ull);
         // ------------------------------------------------------------------ phase A: filter + compact, one lane per trace
         // Each lane streams its own trace in 32-byte sectors (two 128-bit loads = 8 activity ids), tests the ids against
         // the pattern's type set in registers, and appends the surviving events to its lane-transposed shared-memory
@@ -504,6 +513,7 @@ __global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4)
         }
 #endif
         __syncwarp();  // the warp's shared-memory slot is reused by its next tile
+        tile = shfl_i64(next_tile, 0);
     }
 }
 
@@ -767,6 +777,7 @@ int launch_detect(const Ctx* ctx, cudaStream_t stream, DetectParams P, const Dev
 int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand, uint32_t flags,
                        cudaStream_t stream, RebaseOffsets base, siesta_dev_matches* out) {
     std::memset(out, 0, sizeof(*out));
+    base.trace += log->first_trace;
     DevNfa dn;
     int rc = validate_nfa(nfa, flags, &dn);
     if (rc != SIESTA_OK) return rc;
@@ -874,6 +885,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     P.ovf_list = b_ovf.as<int64_t>();
 
     P.ovf_slot = 4;
+    P.tile_slot = 11;
     unsigned long long h_cnt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (n > 0) {
         if (dn.fast_class == FAST_FK2) rc = launch_detect<1, 0, 0, false, FAST_FK2>(ctx, stream, P, dn);
@@ -889,6 +901,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
         Q.n_work_dev = b_counters.as<unsigned long long>() + 4;
         Q.ovf_list = nullptr;
         Q.ovf_slot = 7;
+        Q.tile_slot = 12;
         if (dn.fast_class == FAST_FK2) rc = launch_detect<2, 0, 0, false, FAST_FK2>(ctx, stream, Q, dn);
         else if (dn.fast_class == FAST_NK) rc = launch_detect<2, 0, 0, false, FAST_NK>(ctx, stream, Q, dn);
         else rc = launch_detect<2, 1024, 128, false, FAST_NONE>(ctx, stream, Q, dn);
@@ -1002,7 +1015,8 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     out->d_ev_act = f_act.as<int32_t>();
     out->d_ev_ts_ms = f_ts.as<int64_t>();
     out->d_err_trace_idx = f_err.as<int64_t>();
-    impl->bufs[0] = fin.release();
+    out->block_bytes = (int64_t)f_off;
+    impl->bufs[0] = out->d_block = fin.release();
     out->impl = impl;
     return SIESTA_OK;
 }

@@ -68,10 +68,167 @@ def allgather_matches(local, first_trace, group=None):
     return out
 
 
+# ---------------------------------------------------------------------------------------------- block exchange
+# siesta_dev_matches keeps a result in ONE allocation (include/siesta_gpu.h): eight arrays at 256-byte aligned
+# offsets.  The /detection exchange ships that block as it is: a header all-gather (5 int64 per rank), one copy of
+# the own block into the receive buffer, one padded all-gather of bytes.  The joined match list is the sequence of
+# per-rank parts (each a self-contained CSR with GLOBAL trace indices, see siesta_log_set_first_trace); ranks own
+# ascending disjoint trace ranges, so the parts in rank order are the trace-ordered result.  Nothing is re-packed,
+# and the all-gather may still be in flight when the next request's kernels start (JoinedMatches.wait()).
+
+def _align256(n):
+    return (n + 255) & ~255
+
+
+def block_layout(n_tr, n_occ, n_ev, n_err, all_cols):
+    """Byte offsets of the arrays inside a result block (mirror of detect_device_impl's carve order)."""
+    off, o = {}, 0
+    for name, nbytes in (("trace_idx", n_tr * 8), ("occ_off", (n_tr + 1) * 8), ("ev_off", (n_occ + 1) * 8), ("ev_pos", n_ev * 4),
+                         ("err_trace_idx", n_err * 8)):
+        off[name] = (o, nbytes)
+        o += _align256(nbytes)
+    if all_cols:
+        for name, nbytes in (("ev_rank", n_ev * 4), ("ev_act", n_ev * 4), ("ev_ts_ms", n_ev * 8)):
+            off[name] = (o, nbytes)
+            o += _align256(nbytes)
+    return off, o
+
+
+_DT = {"trace_idx": torch.int64, "occ_off": torch.int64, "ev_off": torch.int64, "ev_pos": torch.int32,
+       "err_trace_idx": torch.int64, "ev_rank": torch.int32, "ev_act": torch.int32, "ev_ts_ms": torch.int64}
+
+
+class JoinedMatches:
+    """The match lists of all ranks after exchange_blocks: parts[r] = dict of tensor views into the receive buffer."""
+
+    def __init__(self, recv, headers, work):
+        self.recv, self.headers, self._work = recv, headers, work
+        self.n_traces = int(sum(h[0] for h in headers))
+        self.n_occurrences = int(sum(h[1] for h in headers))
+        self.n_events = int(sum(h[2] for h in headers))
+
+    def wait(self):
+        """Block the current stream (not the host) until the all-gather has delivered every part."""
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        return self
+
+    @property
+    def parts(self):
+        self.wait()
+        out = []
+        for r, (n_tr, n_occ, n_ev, n_err, all_cols) in enumerate(self.headers):
+            lay, _ = block_layout(n_tr, n_occ, n_ev, n_err, all_cols)
+            row = self.recv[r]
+            out.append({k: row[o:o + nb].view(_DT[k]) for k, (o, nb) in lay.items()})
+        return out
+
+    def concatenated(self):
+        """One CSR over all ranks (copies; for consumers that want a single array per column)."""
+        parts = self.parts
+        out = {"trace_idx": torch.cat([p["trace_idx"] for p in parts]),
+               "err_trace_idx": torch.cat([p["err_trace_idx"] for p in parts])}
+        for name in ("occ_off", "ev_off"):
+            c = torch.cat([p[name][1:] - p[name][:-1] for p in parts])
+            off = torch.zeros(c.numel() + 1, dtype=torch.int64, device=c.device)
+            torch.cumsum(c, 0, out=off[1:])
+            out[name] = off
+        for k in ("ev_pos", "ev_rank", "ev_act", "ev_ts_ms"):
+            if k in parts[0]:
+                out[k] = torch.cat([p[k] for p in parts])
+        return out
+
+
+def exchange_blocks(block, header, group=None, async_op=True):
+    """All-gather of result blocks.  block: uint8 tensor (DeviceMatches.block() or pack_block()), header: its
+    (n_traces, n_occurrences, n_events, n_ref_errors, has_event_columns).  After this call returns the caller may
+    free `block` (it has been copied into the receive buffer); the all-gather itself may still be running."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = block.device
+    h = torch.tensor(list(header) + [block.numel()], dtype=torch.int64, device=dev)
+    hs = torch.empty(world * 6, dtype=torch.int64, device=dev)
+    if dev.type == "cuda":
+        dist.all_gather_into_tensor(hs, h, group=group)
+    else:
+        parts = [torch.empty_like(h) for _ in range(world)]
+        dist.all_gather(parts, h, group=group)
+        hs = torch.cat(parts)
+    hs = hs.view(world, 6).cpu().tolist()          # the only host synchronisation of the exchange
+    maxb = max(max(x[5] for x in hs), 256)
+    recv = torch.empty((world, maxb), dtype=torch.uint8, device=dev)
+    recv[rank, :block.numel()].copy_(block)
+    work = None
+    if dev.type == "cuda":
+        torch.cuda.current_stream(dev).synchronize()  # the copy is done: `block` may be freed by the caller
+        work = dist.all_gather_into_tensor(recv.view(-1), recv[rank], group=group, async_op=async_op)
+        if not async_op:
+            work = None
+    else:
+        rows = [torch.empty(maxb, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(rows, recv[rank].clone(), group=group)
+        for r in range(world):
+            recv[r].copy_(rows[r])
+    return JoinedMatches(recv, [tuple(x[:5]) for x in hs], work)
+
+
+def pack_block(tensors):
+    """dict of 1-D tensors (as DeviceMatches.tensors() / match_result_to_tensors) -> (uint8 block, header): the layout
+    the library produces natively; used where the result did not come from the library (CPU tests)."""
+    n_tr, n_occ = tensors["trace_idx"].numel(), tensors["ev_off"].numel() - 1
+    n_ev, n_err = tensors["ev_pos"].numel(), tensors["err_trace_idx"].numel()
+    all_cols = 1 if tensors.get("ev_rank") is not None else 0
+    lay, total = block_layout(n_tr, n_occ, n_ev, n_err, all_cols)
+    block = torch.zeros(max(total, 1), dtype=torch.uint8, device=tensors["trace_idx"].device)
+    for k, (o, nb) in lay.items():
+        if nb:
+            block[o:o + nb].copy_(tensors[k].contiguous().view(torch.uint8))
+    return block, (n_tr, n_occ, n_ev, n_err, all_cols)
+
+
 def allreduce_counts(packed, group=None):
     """Sum all-reduce of the packed int64 count array of siesta_declare_counts (in place)."""
     dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
     return packed
+
+
+def allreduce_pair_stats(packed, group=None):
+    """Combine siesta_pair_stats_device results (int64[8 * n_pairs]: count, sum, min, max, four 32-bit limbs of the
+    sum of squares) across ranks: SUM for count / sum / limbs, MIN / MAX for the extremes, then carry-normalise the
+    limbs.  In place; returns the tensor."""
+    v = packed.view(-1, 8)
+    sums = v[:, [0, 1, 4, 5, 6, 7]].contiguous()
+    mn = v[:, 2].contiguous()
+    mx = v[:, 3].contiguous()
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    limbs = sums[:, 2:6].clone()
+    for k in range(3):
+        carry = limbs[:, k] >> 32
+        limbs[:, k] &= 0xFFFFFFFF
+        limbs[:, k + 1] += carry
+    v[:, 0], v[:, 1], v[:, 2], v[:, 3] = sums[:, 0], sums[:, 1], mn, mx
+    v[:, 4:8] = limbs
+    return packed
+
+
+def pair_stats_records(packed):
+    """packed int64[8 * n_pairs] (after allreduce_pair_stats) -> list of dicts like EventLog.pair_stats."""
+    out = []
+    for r in packed.view(-1, 8).cpu().tolist():
+        cnt = r[0]
+        sq = r[4] | (r[5] << 32) | (r[6] << 64) | (r[7] << 96)
+        out.append({"count": cnt, "sum": r[1], "min": r[2] if cnt else 0, "max": r[3] if cnt else 0, "sum_squares": sq})
+    return out
+
+
+def allreduce_explore(completions, sum_duration_ms, group=None):
+    """Combine siesta_explore_accurate results across ranks (both are plain sums over traces)."""
+    dist.all_reduce(completions, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(sum_duration_ms, op=dist.ReduceOp.SUM, group=group)
+    return completions, sum_duration_ms
 
 
 def to_match_result(g, n_matches_emitted=-1):

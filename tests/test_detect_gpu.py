@@ -319,3 +319,27 @@ def test_explore_accurate_matches_per_candidate_detection(ctx):
         assert all(abs(p.averageDuration - dur[acts.id(p.event)] / 1000.0 / p.completions) < 1e-9 for p in props)
     finally:
         log.close()
+
+
+def test_result_block_and_shard_offsets(ctx):
+    """The device result is one allocation with a documented layout (shipped whole by the multi-GPU exchange), and a
+    log marked as a shard returns global trace indices."""
+    import torch
+    from sequencedetectionqueryexecutor_b200 import distributed as D
+    off, act, ts = gen.make_log(3000, 0, 40, 8, seed=91)
+    nfa = abi.make_nfa([dict(kind=X_, types=[3]), dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[2])])
+    want = oracle.detect(off, act, ts, nfa, flags=abi.F_RETURN_ALL)
+    log = ctx.load_log(off, act, ts, 8)
+    log.set_first_trace(1_000_000)
+    dm = log.detect_device(nfa, flags=abi.F_RETURN_ALL)
+    block, header = dm.block(0)
+    lay, total = D.block_layout(*header)
+    assert total == block.numel() and header[:4] == (want.n_traces, want.n_occurrences, want.n_events, want.n_ref_errors)
+    views = {k: block[o:o + nb].view(D._DT[k]).cpu().numpy() for k, (o, nb) in lay.items()}
+    torch.cuda.synchronize()
+    assert np.array_equal(views["trace_idx"], want.trace_idx + 1_000_000)
+    assert np.array_equal(views["err_trace_idx"], want.err_trace_idx + 1_000_000)
+    for k in ("occ_off", "ev_off", "ev_pos", "ev_rank", "ev_act", "ev_ts_ms"):
+        assert np.array_equal(views[k], getattr(want, k)), k
+    dm.close()
+    log.close()

@@ -34,4 +34,4 @@ def test_gloo_allgather_and_allreduce(world, tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     res = json.loads(out.read_text())
     assert res["world"] == world and res["ok_detect"], res
-    assert res["ok_declare"] and res["n_traces"] > 10
+    assert res["ok_declare"] and res["ok_stats"] and res["n_traces"] > 10
