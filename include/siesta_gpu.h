@@ -250,6 +250,16 @@ int siesta_detect_device(siesta_log* log, const siesta_nfa* nfa, const int64_t* 
                          int64_t n_cand, uint32_t flags, void* stream, siesta_dev_matches* out);
 void siesta_dev_matches_free(siesta_dev_matches* m);
 
+/* Compact wire format of a device result for the multi-GPU exchange (13 B per trace + 1 B per occurrence + 9 B per
+ * event instead of 24 + 8 + 20; layout: csrc/explore.cu, decoder: distributed.unpack_block).  d_out is device memory of
+ * at least siesta_packed_block_bytes(...) bytes; `stream` a cudaStream_t (NULL = ctx stream).  trace_base is
+ * subtracted from trace_idx (the shard's first trace).  Returns SIESTA_E_UNSUPPORTED when a value does not fit
+ * (activity id >= 65 536, a timestamp delta outside int32 ...): ship the plain block (d_block) then. */
+int64_t siesta_packed_block_bytes(int64_t n_traces, int64_t n_occurrences, int64_t n_events, int64_t n_ref_errors,
+                                  int32_t has_event_columns);
+int siesta_dev_matches_pack(siesta_log* log, const siesta_dev_matches* m, uint32_t flags, int64_t trace_base,
+                            void* d_out, int64_t out_bytes, void* stream);
+
 /* ------------------------------------------------- pair index + intersection */
 /* Kernel K2.  Replaces SparkDatabaseRepository.getCommonIds (storage/repositories/
  * SparkDatabaseRepository.java:160-178): the traces that contain ALL true pairs = the intersection of the

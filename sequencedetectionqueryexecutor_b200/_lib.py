@@ -19,6 +19,7 @@ EXPORTS = [
     "siesta_intersect", "siesta_intersect_device", "siesta_device_free", "siesta_pattern_extract_pairs",
     "siesta_candidates", "siesta_candidates_device", "siesta_pair_stats", "siesta_pair_stats_device",
     "siesta_explore_accurate", "siesta_log_set_first_trace",
+    "siesta_packed_block_bytes", "siesta_dev_matches_pack",
 ]
 
 
@@ -45,6 +46,9 @@ def lib():
     L.siesta_shutdown.restype = None
     L.siesta_log_load.argtypes = [vp, vp, vp, vp, i64, i64, i32, P(vp)]
     L.siesta_log_wrap_device.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, P(vp)]
+    L.siesta_packed_block_bytes.argtypes = [i64, i64, i64, i64, i32]
+    L.siesta_packed_block_bytes.restype = i64
+    L.siesta_dev_matches_pack.argtypes = [vp, P(_abi.DevMatches), u32, i64, vp, i64, vp]
     L.siesta_log_set_first_trace.argtypes = [vp, i64]
     L.siesta_log_set_first_trace.restype = None
     L.siesta_log_free.argtypes = [vp]

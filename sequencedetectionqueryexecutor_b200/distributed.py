@@ -98,8 +98,52 @@ _DT = {"trace_idx": torch.int64, "occ_off": torch.int64, "ev_off": torch.int64, 
        "err_trace_idx": torch.int64, "ev_rank": torch.int32, "ev_act": torch.int32, "ev_ts_ms": torch.int64}
 
 
+def packed_layout(n_tr, n_occ, n_ev, n_err, all_cols):
+    """Byte offsets inside a compact block (mirror of siesta_dev_matches_pack, csrc/explore.cu)."""
+    off, o = {}, 0
+    secs = [("trace_local", n_tr * 4), ("occ_cnt", n_tr), ("ev_cnt", n_occ), ("ev_pos", n_ev * 2), ("err_trace_idx", n_err * 8)]
+    if all_cols:
+        secs += [("ev_rank", n_ev), ("ev_act", n_ev * 2), ("ts_base", n_tr * 8), ("ts_delta", n_ev * 4)]
+    for name, nbytes in secs:
+        off[name] = (o, nbytes)
+        o += _align256(nbytes)
+    return off, o
+
+
+_PDT = {"trace_local": torch.int32, "occ_cnt": torch.uint8, "ev_cnt": torch.uint8, "ev_pos": torch.int16,
+        "err_trace_idx": torch.int64, "ev_rank": torch.uint8, "ev_act": torch.int16, "ts_base": torch.int64,
+        "ts_delta": torch.int32}
+
+
+def unpack_block(row, header):
+    """Compact block -> the standard columns (dict of tensors, global trace indices)."""
+    n_tr, n_occ, n_ev, n_err, all_cols, fmt, trace_base, seconds = header[:8]
+    lay, _ = packed_layout(n_tr, n_occ, n_ev, n_err, all_cols)
+    v = {k: row[o:o + nb].view(_PDT[k]) for k, (o, nb) in lay.items()}
+    dev = row.device
+
+    def offsets(cnt, n):
+        off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(cnt.to(torch.int64), 0, out=off[1:])
+        return off
+
+    out = {"trace_idx": v["trace_local"].to(torch.int64) + trace_base, "occ_off": offsets(v["occ_cnt"], n_tr),
+           "ev_off": offsets(v["ev_cnt"], n_occ), "ev_pos": v["ev_pos"].to(torch.int32) & 0xFFFF,
+           "err_trace_idx": v["err_trace_idx"]}
+    if all_cols:
+        out["ev_rank"] = v["ev_rank"].to(torch.int32)
+        out["ev_act"] = v["ev_act"].to(torch.int32) & 0xFFFF
+        # event -> its trace: events per trace = sum of ev_cnt over the trace's occurrences
+        ev_per_occ = v["ev_cnt"].to(torch.int64)
+        occ_trace = torch.repeat_interleave(torch.arange(n_tr, device=dev), v["occ_cnt"].to(torch.int64))
+        ev_trace = torch.repeat_interleave(occ_trace, ev_per_occ)
+        out["ev_ts_ms"] = v["ts_base"][ev_trace] + v["ts_delta"].to(torch.int64) * (1000 if seconds else 1)
+    return out
+
+
 class JoinedMatches:
-    """The match lists of all ranks after exchange_blocks: parts[r] = dict of tensor views into the receive buffer."""
+    """The match lists of all ranks after exchange_blocks: parts[r] = dict of tensors (views into the receive buffer
+    for plain blocks, decoded columns for compact ones)."""
 
     def __init__(self, recv, headers, work):
         self.recv, self.headers, self._work = recv, headers, work
@@ -118,10 +162,14 @@ class JoinedMatches:
     def parts(self):
         self.wait()
         out = []
-        for r, (n_tr, n_occ, n_ev, n_err, all_cols) in enumerate(self.headers):
-            lay, _ = block_layout(n_tr, n_occ, n_ev, n_err, all_cols)
+        for r, h in enumerate(self.headers):
+            n_tr, n_occ, n_ev, n_err, all_cols, fmt = h[:6]
             row = self.recv[r]
-            out.append({k: row[o:o + nb].view(_DT[k]) for k, (o, nb) in lay.items()})
+            if fmt == 1:
+                out.append(unpack_block(row, h))
+            else:
+                lay, _ = block_layout(n_tr, n_occ, n_ev, n_err, all_cols)
+                out.append({k: row[o:o + nb].view(_DT[k]) for k, (o, nb) in lay.items()})
         return out
 
     def concatenated(self):
@@ -141,22 +189,24 @@ class JoinedMatches:
 
 
 def exchange_blocks(block, header, group=None, async_op=True):
-    """All-gather of result blocks.  block: uint8 tensor (DeviceMatches.block() or pack_block()), header: its
-    (n_traces, n_occurrences, n_events, n_ref_errors, has_event_columns).  After this call returns the caller may
-    free `block` (it has been copied into the receive buffer); the all-gather itself may still be running."""
+    """All-gather of result blocks.  block: uint8 tensor; header: (n_traces, n_occurrences, n_events, n_ref_errors,
+    has_event_columns[, format, trace_base, seconds]) with format 0 = the library's plain block (DeviceMatches.block(),
+    pack_block()) and 1 = the compact wire format (DeviceMatches.packed_block()).  After this call returns the caller
+    may free `block` (it has been copied into the receive buffer); the all-gather itself may still be running."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = block.device
-    h = torch.tensor(list(header) + [block.numel()], dtype=torch.int64, device=dev)
-    hs = torch.empty(world * 6, dtype=torch.int64, device=dev)
+    header = (list(header) + [0, 0, 0])[:8]
+    h = torch.tensor(header + [block.numel()], dtype=torch.int64, device=dev)
+    hs = torch.empty(world * 9, dtype=torch.int64, device=dev)
     if dev.type == "cuda":
         dist.all_gather_into_tensor(hs, h, group=group)
     else:
         parts = [torch.empty_like(h) for _ in range(world)]
         dist.all_gather(parts, h, group=group)
         hs = torch.cat(parts)
-    hs = hs.view(world, 6).cpu().tolist()          # the only host synchronisation of the exchange
-    maxb = max(max(x[5] for x in hs), 256)
+    hs = hs.view(world, 9).cpu().tolist()          # the only host synchronisation of the exchange
+    maxb = max(max(x[8] for x in hs), 256)
     recv = torch.empty((world, maxb), dtype=torch.uint8, device=dev)
     recv[rank, :block.numel()].copy_(block)
     work = None
@@ -170,7 +220,7 @@ def exchange_blocks(block, header, group=None, async_op=True):
         dist.all_gather(rows, recv[rank].clone(), group=group)
         for r in range(world):
             recv[r].copy_(rows[r])
-    return JoinedMatches(recv, [tuple(x[:5]) for x in hs], work)
+    return JoinedMatches(recv, [tuple(x[:8]) for x in hs], work)
 
 
 def pack_block(tensors):

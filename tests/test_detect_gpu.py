@@ -343,3 +343,43 @@ def test_result_block_and_shard_offsets(ctx):
         assert np.array_equal(views[k], getattr(want, k)), k
     dm.close()
     log.close()
+
+
+def test_compact_wire_format_round_trip(ctx):
+    """siesta_dev_matches_pack + distributed.unpack_block reproduce every column of the device result (EventTs and
+    EventPos routes, returnAll, reference-throw traces); values that do not fit are refused, not truncated."""
+    import torch
+    from sequencedetectionqueryexecutor_b200 import distributed as D
+    off, act, ts = gen.make_log(4000, 0, 50, 8, seed=93, jitter_ms=True)
+    cases = [([dict(kind=P_, types=[0]), dict(kind=S_, types=[1], preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 900)])], 0),
+             ([dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[2])], abi.F_RETURN_ALL),
+             ([dict(kind=N_, types=[0]), dict(kind=N_, types=[1])], abi.F_EVT_POS | abi.F_RETURN_ALL),
+             ([dict(kind=X_, types=[1]), dict(kind=P_, types=[2])], 0)]
+    log = ctx.load_log(off, act, ts, 8)
+    log.set_first_trace(7_000_000_000)
+    try:
+        for states, flags in cases:
+            dm = log.detect_device(abi.make_nfa(states), flags=flags)
+            want = {k: v.clone() for k, v in dm.tensors(0).items()}
+            packed = dm.packed_block(log, flags, 7_000_000_000, 0)
+            assert packed is not None
+            block, header = packed
+            plain, _ = dm.block(0)
+            assert block.numel() < 0.6 * plain.numel() or dm.n_events < 20_000  # small results are all alignment padding
+            got = D.unpack_block(block, header)
+            torch.cuda.synchronize()
+            for k, v in want.items():
+                assert torch.equal(got[k], v), (k, states, flags)
+            dm.close()
+    finally:
+        log.close()
+    # an activity id beyond 65 535 does not fit ev_act: the pack call refuses, the plain block is shipped instead
+    off2, act2, ts2 = gen.make_log(50, 10, 20, 5, seed=94)
+    act2 = act2.copy()
+    act2[act2 == 0] = 66_000
+    act2[act2 == 1] = 66_001
+    log2 = ctx.load_log(off2, act2, ts2, 70_000)
+    dm = log2.detect_device(abi.make_nfa([dict(kind=N_, types=[66_000]), dict(kind=N_, types=[66_001])]), flags=0)
+    assert dm.n_traces >= 1 and dm.packed_block(log2, 0, 0, 0) is None
+    dm.close()
+    log2.close()
