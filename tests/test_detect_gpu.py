@@ -383,3 +383,39 @@ def test_compact_wire_format_round_trip(ctx):
     assert dm.n_traces >= 1 and dm.packed_block(log2, 0, 0, 0) is None
     dm.close()
     log2.close()
+
+
+def test_concurrent_requests_on_one_log(ctx):
+    """The reference serves concurrent requests (request-scoped plans on Tomcat threads): siesta_detect, siesta_evaluate_events
+    and the counting calls on ONE log / ctx from several threads must each return their own exact result."""
+    import threading
+    off, act, ts = gen.make_log(20_000, 10, 60, 10, seed=101)
+    log = ctx.load_log(off, act, ts, 10)
+    jobs = [([dict(kind=P_, types=[0]), dict(kind=S_, types=[1], preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 900)])], 0),
+            ([dict(kind=N_, types=[2]), dict(kind=O_, types=[3, 4]), dict(kind=X_, types=[5]), dict(kind=N_, types=[6])], abi.F_RETURN_ALL),
+            ([dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[2])], abi.F_RETURN_ALL),
+            ([dict(kind=S_, types=[7]), dict(kind=N_, types=[8])], abi.F_EVT_POS)]
+    wants = [oracle.detect(off, act, ts, abi.make_nfa(s), flags=f) for s, f in jobs]
+    want_counts = oracle.declare_counts(off, act, 10, 40)
+    errors = []
+
+    def worker(i):
+        try:
+            s, f = jobs[i % len(jobs)]
+            for rep in range(6):
+                got = log.detect(abi.make_nfa(s), flags=f) if rep % 2 == 0 else ctx.evaluate_events(off, act, ts, 10, abi.make_nfa(s), flags=f)
+                ok, why = got.same_as(wants[i % len(jobs)])
+                if not ok:
+                    errors.append((i, rep, why))
+            if i == 0 and not np.array_equal(log.declare_counts(k_cap=40).packed, want_counts.packed):
+                errors.append((i, "declare"))
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    log.close()
+    assert not errors, errors
