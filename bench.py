@@ -74,6 +74,29 @@ def make_log_fast(n_traces, min_len, max_len, n_act, seed, max_gap_s, rank=0):
     return off, act, ts
 
 
+def make_log_device(torch, dev, n_traces, length, n_act, seed, max_gap_s, rank=0, chunk=5_000_000):
+    """Fixed-length workloads generated on the GPU (the 100 M-trace log of configs[4] is 60.8 GB: it never exists on
+    the host).  Same distribution as make_log_fast; chunked so that the temporaries stay small."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed) * 1000003 + rank)
+    E = n_traces * length
+    off = torch.arange(0, E + 1, length, dtype=torch.int64, device=dev)
+    act = torch.empty(E, dtype=torch.int32, device=dev)
+    ts = torch.empty(E, dtype=torch.int64, device=dev)
+    for t0 in range(0, n_traces, chunk):
+        t1 = min(n_traces, t0 + chunk)
+        n = t1 - t0
+        act[t0 * length:t1 * length] = torch.randint(0, n_act, (n * length,), dtype=torch.int32, device=dev, generator=g)
+        gaps = torch.randint(1, max_gap_s + 1, (n, length), dtype=torch.int64, device=dev, generator=g)
+        gaps *= 1000
+        torch.cumsum(gaps, dim=1, out=gaps)
+        start = 1577836800000 + torch.randint(0, 30 * 86400, (n, 1), dtype=torch.int64, device=dev, generator=g) * 1000
+        gaps += start
+        ts[t0 * length:t1 * length] = gaps.view(-1)
+        del gaps, start
+    return off, act, ts
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 
@@ -195,6 +218,8 @@ def main():
     ap.add_argument("--traces", type=int, default=0, help="override traces per GPU (debugging; invalidates the metric)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-gen", action="store_true",
+                    help="generate the log on the GPU (fixed-length workloads; skips the e2e leg: no host copy of the log exists)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -224,13 +249,23 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic log of this rank (traces shard across ranks: weak scaling, fixed traces per GPU)
-    off, act, ts = make_log_fast(wl["n_traces"], wl["min_len"], wl["max_len"], wl["n_act"], wl["seed"], wl["max_gap_s"], rank)
-    T, E = len(off) - 1, len(act)
-    # pinned host copies: the e2e leg copies from these inside the timed region
-    h_off = torch.from_numpy(off).pin_memory()
-    h_act = torch.from_numpy(act).pin_memory()
-    h_ts = torch.from_numpy(ts).pin_memory()
-    d_off, d_act, d_ts = h_off.to(dev), h_act.to(dev), h_ts.to(dev)
+    if args.device_gen:
+        assert wl["min_len"] == wl["max_len"], "--device-gen needs a fixed-length workload"
+        d_off, d_act, d_ts = make_log_device(torch, dev, wl["n_traces"], wl["min_len"], wl["n_act"], wl["seed"], wl["max_gap_s"], rank)
+        T, E = d_off.numel() - 1, d_act.numel()
+        ns0 = min(T, 200_000)  # host copy of a prefix only: the CPU baseline / parity sample
+        off = d_off[:ns0 + 1].cpu().numpy()
+        act = d_act[:ns0 * wl["min_len"]].cpu().numpy()
+        ts = d_ts[:ns0 * wl["min_len"]].cpu().numpy()
+        h_off = h_act = h_ts = None
+    else:
+        off, act, ts = make_log_fast(wl["n_traces"], wl["min_len"], wl["max_len"], wl["n_act"], wl["seed"], wl["max_gap_s"], rank)
+        T, E = len(off) - 1, len(act)
+        # pinned host copies: the e2e leg copies from these inside the timed region
+        h_off = torch.from_numpy(off).pin_memory()
+        h_act = torch.from_numpy(act).pin_memory()
+        h_ts = torch.from_numpy(ts).pin_memory()
+        d_off, d_act, d_ts = h_off.to(dev), h_act.to(dev), h_ts.to(dev)
     nfa = abi.make_nfa(wl["states"])
     ctx = api.Context(local_rank)
     log = ctx.wrap_log(d_off, d_act, d_ts, wl["n_act"], max_trace_len=wl["max_len"])
@@ -294,27 +329,37 @@ def main():
     value = E * world / sec_per_step
 
     # ---- e2e: the host-buffer C-ABI call (H2D of the events + verification + D2H of the occurrences)
-    e2e_steps = max(1, args.e2e_steps)
-    np_off, np_act, np_ts = h_off.numpy(), h_act.numpy(), h_ts.numpy()  # views of the pinned buffers
-    for _ in range(2):  # warm: stream-ordered pool, pinned result arena
-        ctx.evaluate_events(np_off, np_act, np_ts, wl["n_act"], nfa, flags=0, copy=False).close()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        # host CSR in, host occurrences out (zero-copy views of the library's pinned result block)
-        res = ctx.evaluate_events(np_off, np_act, np_ts, wl["n_act"], nfa, flags=0, copy=False)
-        n_res = (res.n_traces, res.n_occurrences, res.n_events, int(res.trace_idx[-1]) if res.n_traces else -1)
-        res.close()
-    barrier()
-    e2e_sec = (time.perf_counter() - t0) / e2e_steps
-    res = ctx.evaluate_events(np_off, np_act, np_ts, wl["n_act"], nfa, flags=0)  # untimed copy for the parity check below
-    t_e2e = torch.tensor([e2e_sec], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_sec = float(t_e2e.item())
     h2d = 8 * (T + 1) + 12 * E
-    d2h = 8 * res.n_traces + 8 * (res.n_traces + 1) + 8 * (res.n_occurrences + 1) + (4 + 4 + 4 + 8) * res.n_events
-    assert n_res[:3] == tuple(r[:3]) and (res.n_traces, res.n_occurrences, res.n_events) == tuple(r[:3])
+    d2h = 8 * r[0] + 8 * (r[0] + 1) + 8 * (r[1] + 1) + (4 + 4 + 4 + 8) * r[2]
+    if args.device_gen:
+        e2e = None   # the log exists only in HBM
+        # parity sample: the same kernels over the prefix whose host copy exists
+        plog = ctx.wrap_log(d_off[:len(off)], d_act[:len(act)], d_ts[:len(ts)], wl["n_act"], max_trace_len=wl["max_len"])
+        res = plog.detect(nfa, flags=0)
+        plog.close()
+    else:
+        e2e_steps = max(1, args.e2e_steps)
+        np_off, np_act, np_ts = h_off.numpy(), h_act.numpy(), h_ts.numpy()  # views of the pinned buffers
+        for _ in range(2):  # warm: stream-ordered pool, pinned result arena
+            ctx.evaluate_events(np_off, np_act, np_ts, wl["n_act"], nfa, flags=0, copy=False).close()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            # host CSR in, host occurrences out (zero-copy views of the library's pinned result block)
+            res = ctx.evaluate_events(np_off, np_act, np_ts, wl["n_act"], nfa, flags=0, copy=False)
+            n_res = (res.n_traces, res.n_occurrences, res.n_events, int(res.trace_idx[-1]) if res.n_traces else -1)
+            res.close()
+        barrier()
+        e2e_sec = (time.perf_counter() - t0) / e2e_steps
+        res = ctx.evaluate_events(np_off, np_act, np_ts, wl["n_act"], nfa, flags=0)  # untimed copy for the parity check below
+        t_e2e = torch.tensor([e2e_sec], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t_e2e.item())
+        assert n_res[:3] == tuple(r[:3]) and (res.n_traces, res.n_occurrences, res.n_events) == tuple(r[:3])
+        e2e = {"value": E * world / e2e_sec, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_sec * 1e3,
+               "call": "siesta_evaluate_events (pinned host CSR in, chunked H2D overlapped with K1, host occurrences out)"}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -338,16 +383,14 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic_bytes(args.workload, T),
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": det_ms, "all_kernels_ms": float(np.mean(k_ms))},
-            "e2e": {"value": E * world / e2e_sec, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_sec * 1e3,
-                    "call": "siesta_evaluate_events (pinned host CSR in, chunked H2D overlapped with K1, host occurrences out)"},
+            "e2e": e2e,
             "gpu_launches": launches,
             "clocks": clocks,
             "result": {"matching_traces_rank0": r[0], "occurrences_rank0": r[1], "events_rank0": r[2],
                        "matching_traces_all_ranks": r[6]},
         }
         if not args.no_cpu_baseline and world == 1:
-            n_sample = min(T, 1_000_000)  # ~10 s of single-thread CPU work
+            n_sample = min(len(off) - 1, 1_000_000)  # ~10 s of single-thread CPU work
             want, ev_s, dt, ns = cpu_baseline(off, act, ts, nfa, n_sample, 1)
             # parity on the sample: the GPU result restricted to the sampled traces equals the oracle's
             keep = res.trace_idx < ns
