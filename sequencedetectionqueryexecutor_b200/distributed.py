@@ -223,6 +223,75 @@ def exchange_blocks(block, header, group=None, async_op=True):
     return JoinedMatches(recv, [tuple(x[:8]) for x in hs], work)
 
 
+class PeerExchanger:
+    """exchange_blocks with the payload moved by the copy engines over NVLink peer memory instead of an SM-based NCCL
+    kernel: every rank stages its block in a symmetric-memory buffer and PULLS the other ranks' blocks with plain
+    device-to-device copies on a side stream (the pattern of torch's low-contention all-gather).  The copies use no SM,
+    so the next request's verification kernel runs beside them at full speed; only the 9-value header still goes
+    through NCCL.  One node only (symmetric memory needs peer access); `depth` requests may be in flight."""
+
+    def __init__(self, device, group=None, capacity=64 << 20, depth=3):
+        import torch.distributed._symmetric_memory as symm
+        self._symm = symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.device, self.depth = device, depth
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.stream = torch.cuda.Stream(device)
+        self.k = 0
+        self._alloc(capacity)
+
+    def _alloc(self, capacity):
+        self.capacity = int(capacity)
+        self.bufs = [self._symm.empty(self.capacity, dtype=torch.uint8, device=self.device) for _ in range(self.depth)]
+        self.hdls = [self._symm.rendezvous(b, self.group) for b in self.bufs]
+        self.free = [None] * self.depth   # event: every rank has finished pulling from this slot
+
+    def exchange(self, block, header):
+        """Same contract as exchange_blocks: on return `block` may be freed; the pulls may still be running."""
+        world, rank, dev = self.world, self.rank, self.device
+        header = (list(header) + [0, 0, 0])[:8]
+        h = torch.tensor(header + [block.numel()], dtype=torch.int64, device=dev)
+        hs = torch.empty(world * 9, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(hs, h, group=self.group)
+        hs = hs.view(world, 9).cpu().tolist()
+        maxb = max(max(x[8] for x in hs), 256)
+        if maxb > self.capacity:            # every rank sees the same sizes: a collective, deterministic decision
+            torch.cuda.synchronize(dev)
+            self._alloc(max(2 * maxb, 2 * self.capacity))
+        slot = self.k % self.depth
+        self.k += 1
+        cur = torch.cuda.current_stream(dev)
+        if self.free[slot] is not None:
+            cur.wait_event(self.free[slot])
+        self.bufs[slot][:block.numel()].copy_(block)
+        cur.synchronize()                    # the own block is staged: the caller may free it
+        recv = torch.empty((world, maxb), dtype=torch.uint8, device=dev)
+        hdl = self.hdls[slot]
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            hdl.barrier()                    # every rank has staged its block
+            for step in range(world):
+                r = (rank - step) % world
+                n = hs[r][8]
+                if n:
+                    src = hdl.get_buffer(r, (self.capacity,), torch.uint8)
+                    recv[r, :n].copy_(src[:n])
+            hdl.barrier()                    # every rank has pulled: the slot may be overwritten
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self.free[slot] = done
+        recv.record_stream(self.stream)
+        return JoinedMatches(recv, [tuple(x[:8]) for x in hs], _EventWork(done))
+
+
+class _EventWork:
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
 def pack_block(tensors):
     """dict of 1-D tensors (as DeviceMatches.tensors() / match_result_to_tensors) -> (uint8 block, header): the layout
     the library produces natively; used where the result did not come from the library (CPU tests)."""
