@@ -317,8 +317,11 @@ def main():
     k_ms, d_ms = [], []
     barrier()
     t0 = time.perf_counter()
+    lat_ms = []   # per-request latency: the call returns after the result sizes are back on the host (one stream sync)
     for _ in range(args.steps):
+        ts0 = time.perf_counter()
         r = step_resident()
+        lat_ms.append((time.perf_counter() - ts0) * 1e3)
         k_ms.append(r[4])
         d_ms.append(r[5])
     for j in in_flight:
@@ -393,6 +396,7 @@ def main():
                          "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic_bytes(args.workload, T),
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": det_ms, "all_kernels_ms": float(np.mean(k_ms))},
             "e2e": e2e,
+            "p50_latency_ms": float(np.median(lat_ms)),   # /detection request on the resident shard (rank 0), incl. the exchange call at N > 1
             "gpu_launches": launches,
             "clocks": clocks,
             "result": {"matching_traces_rank0": r[0], "occurrences_rank0": r[1], "events_rank0": r[2],

@@ -41,7 +41,7 @@ struct DetectParams {
     int64_t n_work;           // number of traces this launch verifies ...
     const unsigned long long* n_work_dev;  // ... or, if set, read from device memory (the narrow launch's overflow count)
     int32_t ovf_slot;         // counter that counts the traces this launch could not hold (4 narrow, 7 wide)
-    int32_t tile_slot;        // counter that hands out tiles (11 narrow, 12 wide)
+    int32_t tile_slot;        // counter that hands out tiles (16 narrow, 17 wide, 18 K1-P)
     const uint16_t* lut;      // [n_act] smask | fmask << 8
     // alpha_mode 0/1: the pattern's activities are numbered 1..K (K <= 7, "class"); plane p holds, bit-reversed, the
     // activities whose class has bit p set (ids 0..31 in [p][0], 32..63 in [p][1]); cls_word / cls_act give the lut
@@ -68,8 +68,13 @@ struct DetectParams {
     int32_t* s_ev_act;
     int64_t* s_ev_ts;
     int64_t cap_occ, cap_ev;
+    // K1-P stages at fixed places (no atomic on its critical path): tile i owns the event slots
+    // [fix_ev + 32 i fix_np, + 32 fix_np) of a second staging region behind the first one
+    int64_t fix_ev;
+    int32_t fix_np;
     // counters: 0 occ reserved, 1 ev reserved, 2 emitted, 3 errors, 4 overflow, 5 staging overflow, 6 matched traces,
-    // 7 wide overflow, 8-10 phase timing, 11 / 12 next tile of the narrow / wide launch
+    // 7 wide overflow, 8-10 phase timing, 13 K1-P overflow; second 128-byte line: 16 / 17 / 18 next tile of the narrow /
+    // wide / K1-P launch
     unsigned long long* counters;
     int64_t* err_list;
     int64_t* ovf_list;
@@ -212,6 +217,9 @@ __global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4)
     long long tile = 0;
     if (lane == 0) tile = (long long)atomicAdd(P.counters + P.tile_slot, 1ull);
     tile = shfl_i64(tile, 0);
+    // Totals that nobody waits for are summed per warp (lane 31) and flushed once after the last tile: all counters of
+    // a launch share one 128-byte line, and same-line atomics are served one at a time by the L2.
+    unsigned long long acc_occ = 0, acc_emit = 0, acc_match = 0;
     while (tile < n_tiles) {
         long long next_tile = 0;
         if (lane == 0) next_tile = (long long)atomicAdd(P.counters + P.tile_slot, 1ull);
@@ -396,17 +404,19 @@ __global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4)
         const unsigned n_match = __popc(__ballot_sync(0xffffffffu, status == ST_MATCH));
         unsigned long long base0 = 0, base1 = 0;
         if (lane == 31) {
-            if (i0) base0 = atomicAdd(P.counters + 0, (unsigned long long)i0);
+            // with one occurrence per trace the occurrence is staged at the candidate's own index: one reservation per tile
+            if (return_all) { if (i0) base0 = atomicAdd(P.counters + 0, (unsigned long long)i0); }
+            else acc_occ += i0;
             if (i1) base1 = atomicAdd(P.counters + 1, (unsigned long long)i1);
-            if (i2) atomicAdd(P.counters + 2, i2);
-            if (n_match) atomicAdd(P.counters + 6, (unsigned long long)n_match);
+            acc_emit += i2;
+            acc_match += n_match;
         }
         const unsigned tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
         base0 = __shfl_sync(0xffffffffu, base0, 31);
         base1 = __shfl_sync(0xffffffffu, base1, 31);
-        const long long occ_at = (long long)(base0 + i0 - my_occ);
+        const long long occ_at = return_all ? (long long)(base0 + i0 - my_occ) : (long long)ci;
         const long long ev_at = (long long)(base1 + i1 - my_ev);
-        const bool stage_ok = (long long)(base0 + tot0) <= P.cap_occ && (long long)(base1 + tot1) <= P.cap_ev;
+        const bool stage_ok = (!return_all || (long long)(base0 + tot0) <= P.cap_occ) && (long long)(base1 + tot1) <= P.cap_ev;
         if (!stage_ok && lane == 0) atomicAdd(P.counters + 5, 1ull);
 
         if (ci >= 0) {
@@ -514,6 +524,172 @@ __global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4)
 #endif
         __syncwarp();  // the warp's shared-memory slot is reused by its next tile
         tile = shfl_i64(next_tile, 0);
+    }
+    if (lane == 31) {
+        if (acc_occ) atomicAdd(P.counters + 0, acc_occ);
+        if (acc_emit) atomicAdd(P.counters + 2, acc_emit);
+        if (acc_match) atomicAdd(P.counters + 6, acc_match);
+    }
+}
+
+// ---------------------------------------------------------------------------------- K1-P: class NK over raw position slots
+// For NFAs of class NK (detect_fast.cuh) whose first-largest occurrence is asked for and whose predicates read no
+// relative seconds, nothing has to be compacted or staged: the trace is addressed by its raw position slots.  One lane
+// per trace streams the trace's 32-byte sectors (at most 64 slots from the sector of its first event: up to 7 slots of
+// the previous trace, then the trace), keeps the class bit-planes of the 64 slots in registers, combines them into one
+// 64-bit mask per NFA state (minterm of the class number, OR-ed into every state that owns the class) and runs the
+// greedy walks on those masks; the index in the filtered list, which the EventTs route calls `position`, is the
+// popcount of the relevant-slot mask below a slot.  No shared memory, no second pass, no per-event loop after the
+// plane scan.  Traces that do not fit 64 slots go to the overflow list and re-run on the staged kernel above.
+// Output and counters are those of detect_kernel (phase C), so the placement kernels below serve both.
+template <int NPL, bool WIDE, bool EVT>
+__global__ void __launch_bounds__(NT_MAX, 5) detect_nkp_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ DevNfa nfa) {
+    typedef MaskX<2> MO;
+    typedef unsigned long long mask_t;
+    const int lane = threadIdx.x & 31;
+    constexpr bool evt_pos = EVT;
+    const bool all_cols = (P.flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
+    const bool first_only = (P.flags & SIESTA_F_COUNT_MATCHES) == 0;  // monotone walks: the first completed start wins
+
+    const long long n_work = P.n_work_dev ? (long long)__ldg(P.n_work_dev) : (long long)P.n_work;
+    const long long n_tiles = (n_work + 31) / 32;
+    long long tile = 0;
+    if (lane == 0) tile = (long long)atomicAdd(P.counters + P.tile_slot, 1ull);
+    tile = shfl_i64(tile, 0);
+    unsigned long long acc_occ = 0, acc_ev = 0, acc_emit = 0;  // totals, flushed once per warp (see detect_kernel)
+    while (tile < n_tiles) {
+        long long next_tile = 0;
+        if (lane == 0) next_tile = (long long)atomicAdd(P.counters + P.tile_slot, 1ull);
+        const int64_t wi = tile * 32 + lane;
+        int64_t ci = -1, t = -1;
+        long long o0 = 0, o1 = 0;
+        if (wi < n_work) {
+            ci = P.work ? P.work[wi] : wi;
+            t = P.cand ? P.cand[ci] : ci;
+            o0 = P.trace_off[t];
+            o1 = P.trace_off[t + 1];
+        }
+        const long long e0 = o0 & ~7LL;
+        const int lead = (int)(o0 - e0);
+        const long long span = (o1 - o0) + lead;  // slots the trace needs
+        const bool fits = span <= 64;
+        const long long o1s = fits ? o1 : o0;     // a trace that does not fit is not read here
+        int4 v0[8], v1[8];
+        load_sectors(P, e0, o0, o1s, v0);
+        load_sectors(P, e0 + 32, o0, o1s, v1);
+        uint32_t pa[3] = {0u, 0u, 0u}, pb[3] = {0u, 0u, 0u};
+        scan_block<NPL, WIDE>(P, v0, pa);
+        if (__any_sync(0xffffffffu, fits && span > 32)) scan_block<NPL, WIDE>(P, v1, pb);
+        mask_t valid = 0;
+        if (fits && o1 > o0) valid = (span == 64 ? ~0ull : ((1ull << (int)span) - 1ull)) & ~((1ull << lead) - 1ull);
+        mask_t pl[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) pl[p] = p < NPL ? (((mask_t)pa[p] | ((mask_t)pb[p] << 32)) & valid) : 0ull;
+        const mask_t R = pl[0] | pl[1] | pl[2];
+        // state masks: class c (1..7) = minterm of the planes; cls_word[c] bit k <=> class c belongs to state k
+        mask_t T[SIESTA_MAX_STATES + 1];
+#pragma unroll
+        for (int k = 0; k <= SIESTA_MAX_STATES; ++k) T[k] = 0;
+#pragma unroll
+        for (int c = 1; c < (1 << NPL); ++c) {
+            const uint32_t w = P.cls_word[c];
+            if (w == 0) continue;  // uniform
+            mask_t m = R;
+#pragma unroll
+            for (int p = 0; p < NPL; ++p) m &= ((c >> p) & 1) ? pl[p] : ~pl[p];
+#pragma unroll
+            for (int k = 0; k < SIESTA_MAX_STATES; ++k)
+                if (w & (1u << k)) T[k] |= m;
+        }
+
+        int status = ST_NONE;
+        unsigned n_emitted = 0;
+        mask_t best = 0;
+        if (ci >= 0 && o1 > o0) {
+            if (!fits) status = ST_OVF;
+            else if (R && nkp_eval<EVT>(nfa, R, lead, T, best, n_emitted, first_only)) status = ST_MATCH;
+        }
+
+        // ------------------------------------------------------------------ output: as phase C of detect_kernel
+        const unsigned my_occ = status == ST_MATCH ? 1u : 0u;
+        const unsigned my_ev = status == ST_MATCH ? (unsigned)MO::popc(best) : 0u;
+        unsigned i0 = my_occ, i1 = my_ev;
+        unsigned long long i2 = (status == ST_MATCH) ? n_emitted : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned y0 = __shfl_up_sync(0xffffffffu, i0, d), y1 = __shfl_up_sync(0xffffffffu, i1, d);
+            const unsigned long long y2 = __shfl_up_sync(0xffffffffu, i2, d);
+            if (lane >= d) { i0 += y0; i1 += y1; i2 += y2; }
+        }
+        // the staging place of the tile is fixed: no atomic on the critical path, totals are flushed after the last tile
+        acc_occ += i0;
+        acc_ev += i1;
+        acc_emit += i2;
+        const unsigned tot1 = __shfl_sync(0xffffffffu, i1, 31);
+        const long long base1 = P.fix_ev + tile * 32 * P.fix_np;
+        const long long occ_at = (long long)ci;
+        const long long ev_at = base1 + (long long)(i1 - my_ev);
+        const bool stage_ok = true;
+        if (ci >= 0) {
+            P.d_nocc[ci] = my_occ;
+            P.d_nev[ci] = my_ev;
+            if (status == ST_MATCH) {
+                P.d_stage[ci] = ev_at;
+                P.d_stage_occ[ci] = occ_at;
+            } else if (status == ST_OVF) {
+                const unsigned long long at = atomicAdd(P.counters + P.ovf_slot, 1ull);
+                P.ovf_list[at] = ci;
+            }
+        }
+        if (stage_ok && tot1 > 0) {
+            // first event of the filtered list (Utils.java:51-53): base of the relative seconds of the EventTs route
+            long long t0ms = 0;
+            if (status == ST_MATCH) {
+                P.s_occ_nev[occ_at] = (int32_t)my_ev;
+                if (all_cols && !evt_pos) t0ms = __ldg(reinterpret_cast<const long long*>(P.ts_ms) + o0 + (MO::lo(R) - lead));
+            }
+            for (unsigned f0 = 0; f0 < tot1; f0 += 32) {
+                const unsigned f = f0 + lane;
+                int lo = 0, hi = 31;
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    const int mid = (lo + hi) >> 1;
+                    const unsigned vmid = __shfl_sync(0xffffffffu, i1, mid);
+                    if (vmid > f) hi = mid; else lo = mid + 1;
+                }
+                const int owner = lo & 31;
+                const unsigned o_incl = __shfl_sync(0xffffffffu, i1, owner);
+                const unsigned o_ev = __shfl_sync(0xffffffffu, my_ev, owner);
+                mask_t m = (mask_t)shfl_i64((long long)best, owner);
+                const mask_t o_R = (mask_t)shfl_i64((long long)R, owner);
+                const long long o_o0 = shfl_i64(o0, owner);
+                const long long o_t0 = shfl_i64(t0ms, owner);
+                if (f < tot1) {
+                    int k = (int)(f - (o_incl - o_ev));  // k-th event of the owner's occurrence
+                    for (; k > 0; --k) m &= m - 1;
+                    const int j = MO::lo(m);
+                    const int src = j - (int)(o_o0 & 7);
+                    const long long at = base1 + f;
+                    P.s_ev_pos[at] = src;
+                    if (all_cols) {
+                        P.s_ev_rank[at] = MO::popc(o_R & MO::below(j));
+                        P.s_ev_act[at] = __ldg(P.act + o_o0 + src);
+                        const long long raw = __ldg(reinterpret_cast<const long long*>(P.ts_ms) + o_o0 + src);
+                        // SaseEvent.getEventBoth: timestamp * 1000 + minTs (SaseEvent.java:94-106)
+                        P.s_ev_ts[at] = evt_pos ? raw : (long long)rel_seconds(raw - o_t0) * 1000 + o_t0;
+                    }
+                }
+            }
+        }
+        tile = shfl_i64(next_tile, 0);
+    }
+    if (lane == 31) {
+        if (acc_occ) {
+            atomicAdd(P.counters + 0, acc_occ);
+            atomicAdd(P.counters + 6, acc_occ);  // one occurrence per matching trace
+        }
+        if (acc_ev) atomicAdd(P.counters + 1, acc_ev);
+        if (acc_emit) atomicAdd(P.counters + 2, acc_emit);
     }
 }
 
@@ -772,6 +948,26 @@ int launch_detect(const Ctx* ctx, cudaStream_t stream, DetectParams P, const Dev
     return SIESTA_OK;
 }
 
+template <int NPL, bool WIDE, bool EVT>
+int launch_nkp(const Ctx* ctx, cudaStream_t stream, const DetectParams& P, const DevNfa& nfa) {
+    auto kern = detect_nkp_kernel<NPL, WIDE, EVT>;
+    int per_sm = 0;
+    SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (const char* env = std::getenv("SIESTA_K1_CTAS_PER_SM")) {  // tuning aid: cap on resident CTAs per SM
+        const int v = std::atoi(env);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
+    const int64_t n_tiles = (P.n_work + 31) / 32;
+    const int64_t ctas_needed = (n_tiles + NT / 32 - 1) / (NT / 32);
+    int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)ctx->sm_count * per_sm);
+    if (grid < 1) grid = 1;
+    kern<<<grid, NT, 0, stream>>>(P, nfa);
+    SIESTA_LAUNCHED();
+    SIESTA_CUDA_OK(cudaGetLastError());
+    return SIESTA_OK;
+}
+
 }  // namespace
 
 int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand, uint32_t flags,
@@ -807,15 +1003,24 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
         w_off += (bytes + 255) & ~(size_t)255;
         return at;
     };
+    // class NK, first-largest only, no relative seconds: the raw-slot kernel K1-P goes first (its overflow list feeds
+    // the staged kernel).  Decided before the scratch is carved: it needs a second overflow list.
+    int n_cls = 0;
+    for (size_t a = 0; a < lut.size(); ++a) n_cls += lut[a] != 0;
+    const int alpha_mode = !log->act_valid ? 2 : (n_cls > 7 ? 2 : (log->n_activities <= 32 ? 0 : (log->n_activities <= 64 ? 1 : 2)));
+    const bool use_nkp = dn.fast_class == FAST_NK && !return_all && !needs_ts && alpha_mode != 2 &&
+                         std::getenv("SIESTA_K1_NO_NKP") == nullptr;
+    const size_t n_reg = use_nkp ? 2 : 1;  // staging regions: [0, cap) by atomics (staged kernels), [cap, 2 cap) fixed tile slots (K1-P)
     const size_t n_blk = (nn + GT - 1) / GT;
+    const size_t o_ovf2 = use_nkp ? carve(nn * 8) : 0;
     const size_t o_lut = carve(lut.size() * sizeof(uint16_t)), o_nocc = carve(nn * 4), o_nev = carve(nn * 4), o_stage = carve(nn * 8),
-                 o_stage_occ = carve(nn * 8), o_counters = carve(16 * 8), o_err = carve(nn * 8), o_ovf = carve(nn * 8),
-                 o_blk = carve(n_blk * 3 * 8), o_occ_nev = carve((size_t)cap_occ * 4), o_pos = carve((size_t)cap_ev * 4);
+                 o_stage_occ = carve(nn * 8), o_counters = carve(32 * 8), o_err = carve(nn * 8), o_ovf = carve(nn * 8),
+                 o_blk = carve(n_blk * 3 * 8), o_occ_nev = carve((size_t)cap_occ * 4), o_pos = carve((size_t)cap_ev * 4 * n_reg);
     size_t o_rank = 0, o_act = 0, o_ts = 0;
     if (all_cols) {
-        o_rank = carve((size_t)cap_ev * 4);
-        o_act = carve((size_t)cap_ev * 4);
-        o_ts = carve((size_t)cap_ev * 8);
+        o_rank = carve((size_t)cap_ev * 4 * n_reg);
+        o_act = carve((size_t)cap_ev * 4 * n_reg);
+        o_ts = carve((size_t)cap_ev * 8 * n_reg);
     }
     if ((rc = work.alloc(w_off))) return rc;
     char* wb = work.as<char>();
@@ -829,7 +1034,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     SIESTA_CUDA_OK(cudaEventCreate(&ev1));
     SIESTA_CUDA_OK(cudaEventCreate(&evd));
     SIESTA_CUDA_OK(cudaMemcpyAsync(b_lut.p, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
-    SIESTA_CUDA_OK(cudaMemsetAsync(b_counters.p, 0, 128, stream));
+    SIESTA_CUDA_OK(cudaMemsetAsync(b_counters.p, 0, 256, stream));
     SIESTA_CUDA_OK(cudaEventRecord(ev0, stream));
 
     DetectParams P;
@@ -885,9 +1090,32 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     P.ovf_list = b_ovf.as<int64_t>();
 
     P.ovf_slot = 4;
-    P.tile_slot = 11;
+    P.tile_slot = 16;   // the tile counters live on their own 128-byte line (slots 16..)
     unsigned long long h_cnt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (n > 0) {
+        if (use_nkp) {
+            DetectParams N = P;
+            N.ovf_list = reinterpret_cast<int64_t*>(wb + o_ovf2);
+            N.ovf_slot = 13;
+            N.tile_slot = 18;
+            N.fix_ev = cap_ev;
+            N.fix_np = std::max(1, n_positive);
+            const bool evt = (flags & SIESTA_F_EVT_POS) != 0;
+            auto go = [&](auto npl, auto wide) {
+                constexpr int NPL = decltype(npl)::value;
+                constexpr bool WIDE = decltype(wide)::value;
+                return evt ? launch_nkp<NPL, WIDE, true>(ctx, stream, N, dn) : launch_nkp<NPL, WIDE, false>(ctx, stream, N, dn);
+            };
+            typedef std::integral_constant<int, 1> I1;
+            typedef std::integral_constant<int, 2> I2;
+            typedef std::integral_constant<int, 3> I3;
+            if (P.alpha_mode == 0) rc = P.n_planes == 1 ? go(I1(), std::false_type()) : (P.n_planes == 2 ? go(I2(), std::false_type()) : go(I3(), std::false_type()));
+            else rc = P.n_planes == 1 ? go(I1(), std::true_type()) : (P.n_planes == 2 ? go(I2(), std::true_type()) : go(I3(), std::true_type()));
+            if (rc) return rc;
+            // the staged kernel below re-runs the traces that did not fit 64 slots (count read from the device)
+            P.work = N.ovf_list;
+            P.n_work_dev = b_counters.as<unsigned long long>() + 13;
+        }
         if (dn.fast_class == FAST_FK2) rc = launch_detect<1, 0, 0, false, FAST_FK2>(ctx, stream, P, dn);
         else if (dn.fast_class == FAST_NK) rc = launch_detect<1, 0, 0, false, FAST_NK>(ctx, stream, P, dn);
         else rc = launch_detect<1, 16, 16, true, FAST_NONE>(ctx, stream, P, dn);
@@ -901,7 +1129,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
         Q.n_work_dev = b_counters.as<unsigned long long>() + 4;
         Q.ovf_list = nullptr;
         Q.ovf_slot = 7;
-        Q.tile_slot = 12;
+        Q.tile_slot = 17;
         if (dn.fast_class == FAST_FK2) rc = launch_detect<2, 0, 0, false, FAST_FK2>(ctx, stream, Q, dn);
         else if (dn.fast_class == FAST_NK) rc = launch_detect<2, 0, 0, false, FAST_NK>(ctx, stream, Q, dn);
         else rc = launch_detect<2, 1024, 128, false, FAST_NONE>(ctx, stream, Q, dn);

@@ -16,6 +16,15 @@
 //   passes the next state's predicates, Engine.java:1165-1180: the run moves on) decides.  Runs never change their
 //   list position, so matches are emitted in ascending (completion event, start event) order; they all have the same
 //   number of events, hence "first largest" (Occurrences.java:60-69) = the smallest (completion, start).
+//   Monotone walks: if every attribute a predicate reads never decreases along the events (list index and in-trace
+//   position always; relative seconds only when the caller's timestamps are sorted, which is not assumed), a later
+//   start takes, state by state, events that are not earlier than those of an earlier start (a lower bound `>=` only
+//   grows with the referenced event; an upper bound `<=` that an earlier start fails on an event, it fails on every
+//   later event as well, so that start never completes).  Completed runs therefore complete in start order, and the
+//   first-largest occurrence is the FIRST start whose walk completes: `first_only` stops there.
+//   The evaluator is generic in the event accessor: TraceEvents (filtered list in shared memory, masks over list
+//   indices) or PosEvents (masks over the trace's raw 64 position slots, list index = popcount of the relevant-event
+//   mask below the slot) for kernel K1-P, which needs no shared memory at all.
 //
 // Class FK2 — two states `a+ b*` (kleeneClosure, kleeneClosure*), one type each, a != b, predicates only on state 1
 //             and only referencing state 0, first-largest occurrence only (returnAll = false).
@@ -46,14 +55,29 @@ enum { FAST_NONE = 0, FAST_NK = 1, FAST_FK2 = 2 };
 template <int W>
 struct MaskX : MaskOps<W> {
     typedef typename MaskOps<W>::T T;
-    static SIESTA_HD __forceinline__ T below(int j) { return MaskOps<W>::bit(j) - 1; }                  // bits < j
-    static SIESTA_HD __forceinline__ T above(int j) { return ~(below(j) | MaskOps<W>::bit(j)); }        // bits > j
+    static SIESTA_HD __forceinline__ T below(int j) { return ~(~(T)0 << j); }   // bits < j   (0 <= j < bits of T)
+    static SIESTA_HD __forceinline__ T above(int j) { return ~(T)1 << j; }      // bits > j
 };
 
 // "attr(e) op attr(ref) + c" for every predicate of state s; vv(ref) gives the event stored for state `ref`.
 // A predicate that references state `cur` itself is true (PredicateOptimized.java:331-340).
-template <class VV>
-SIESTA_HD __forceinline__ bool fast_preds(const DevNfa& nfa, const TraceEvents& ev, int s, int e, int cur, const VV& vv) {
+// Events of a trace addressed by raw slot: slot j = in-trace position j - lead (lead = events of the previous trace
+// that share the first 32-byte sector); R = slots that hold an event of the pattern's types.  The SaseEvent attributes
+// after Utils.transformToSaseEvents (J/model/Utils/Utils.java:48-65): EventTs route position = index in the filtered
+// list (= rank); EventPos route position = in-trace position, timestamp = index in the filtered list.  Relative
+// seconds are not available here: NFAs with a time predicate on the EventTs route never take this path.
+struct PosEvents {
+    unsigned long long R;
+    int lead;
+    bool evt_pos;
+    SIESTA_HD __forceinline__ int rank(int j) const { return popc64(R & ((1ull << j) - 1ull)); }
+    SIESTA_HD __forceinline__ int position(int j) const { return evt_pos ? j - lead : rank(j); }
+    SIESTA_HD __forceinline__ int timestamp(int j) const { return evt_pos ? rank(j) : 0; }
+    SIESTA_HD __forceinline__ int attr(int j, int a) const { return a == SIESTA_ATTR_POSITION ? position(j) : timestamp(j); }
+};
+
+template <class EV, class VV>
+SIESTA_HD __forceinline__ bool fast_preds(const DevNfa& nfa, const EV& ev, int s, int e, int cur, const VV& vv) {
     const int np = nfa.n_preds[s];
     for (int k = 0; k < np; ++k) {
         const int ref = nfa.p_ref[s][k];
@@ -217,8 +241,8 @@ SIESTA_HD bool fk2_eval(const DevNfa& nfa, const TraceEvents& ev, typename MaskO
 // ------------------------------------------------------------------------------------------------- class NK
 // Greedy walk of the run started at event s.  Returns the run's events as a mask (0 = the run never completes or
 // is deleted at a negative state).
-template <int W>
-SIESTA_HD typename MaskOps<W>::T nk_walk(const DevNfa& nfa, const TraceEvents& ev, const typename MaskOps<W>::T* T, int s) {
+template <int W, class EV>
+SIESTA_HD __forceinline__ typename MaskOps<W>::T nk_walk(const DevNfa& nfa, const EV& ev, const typename MaskOps<W>::T* T, int s) {
     typedef MaskX<W> MO;
     typedef typename MO::T mask_t;
     const int S = nfa.n_states;
@@ -278,17 +302,21 @@ struct NkMasks {
     }
 };
 
-template <int W>
-SIESTA_HD bool nk_eval(const DevNfa& nfa, const TraceEvents& ev, const typename MaskOps<W>::T* T, bool return_all, bool by_pos,
-                       typename MaskOps<W>::T* aux, int aux_stride, typename MaskOps<W>::T* sel, int& nsel, unsigned& n_emitted) {
+// first_only: stop at the first start whose walk completes (valid for monotone walks, see the header; n_emitted is
+// then not the engine's match count and must not be reported).
+template <int W, class EV>
+SIESTA_HD __forceinline__ bool nk_eval(const DevNfa& nfa, const EV& ev, const typename MaskOps<W>::T* T, bool return_all, bool by_pos,
+                       typename MaskOps<W>::T* aux, int aux_stride, typename MaskOps<W>::T* sel, int& nsel, unsigned& n_emitted,
+                       bool first_only = false) {
     typedef MaskX<W> MO;
     typedef typename MO::T mask_t;
     const int S = nfa.n_states;
     nsel = 0;
     n_emitted = 0;
-    // every state's types must occur at all (cheap reject of most traces)
-    for (int k = 0; k < S; ++k)
-        if (nfa.kind[k] != SIESTA_STATE_NEGATIVE && T[k] == 0) return false;
+    // every state's types must occur at all (cheap reject of most traces); unrolled: T[] stays in registers
+#pragma unroll
+    for (int k = 0; k < SIESTA_MAX_STATES; ++k)
+        if (k < S && nfa.kind[k] != SIESTA_STATE_NEGATIVE && T[k] == 0) return false;
 
     mask_t best = 0, done = 0;  // done: starts whose run completed
     int best_c = 0;
@@ -299,6 +327,7 @@ SIESTA_HD bool nk_eval(const DevNfa& nfa, const TraceEvents& ev, const typename 
         ++n_emitted;
         const int c = MO::hi(m);
         if (!best || c < best_c) { best = m; best_c = c; }  // starts ascend: an equal completion keeps the earlier start
+        if (first_only) break;
         if (return_all) {
             aux[s * aux_stride] = m;
             done |= MO::bit(s);
@@ -334,6 +363,118 @@ SIESTA_HD bool nk_eval(const DevNfa& nfa, const TraceEvents& ev, const typename 
         }
     }
     return true;
+}
+
+// ------------------------------------------------------------------------------- class NK over raw position slots
+// The same greedy walk and selection as nk_walk / nk_eval, specialised for kernel K1-P: events are single bits of the
+// 64 raw slots (no slot index is ever materialised: `b - 1` is the mask below bit b), the attributes of the event taken
+// for state k are kept as byte k of two packed words (attribute values are below 64 here), and the route is a template
+// parameter.  Attributes after Utils.transformToSaseEvents (J/model/Utils/Utils.java:48-65): EventTs route position =
+// index in the filtered list = popcount of the relevant slots below the event; EventPos route position = in-trace
+// position = slot - lead, timestamp = index in the filtered list.  (EventTs-route time predicates never come here.)
+// NK class invariant (classify_fast): every predicate references an earlier POSITIVE state, so the "reference to the
+// current state is true" rule of PredicateOptimized.java:331-340 never applies.
+template <bool EVT>
+struct NkpWalk {
+    typedef unsigned long long u64;
+    const DevNfa& nfa;
+    u64 R;
+    int lead;
+    u64 v0, v1;  // byte k: position / timestamp attribute of the event taken for state k
+    SIESTA_HD __forceinline__ NkpWalk(const DevNfa& n, u64 r, int l) : nfa(n), R(r), lead(l), v0(0), v1(0) {}
+    SIESTA_HD __forceinline__ void attrs(u64 b, int& a0, int& a1) const {
+        const int r = popc64(R & (b - 1));
+        a0 = EVT ? popc64(b - 1) - lead : r;
+        a1 = EVT ? r : 0;
+    }
+    SIESTA_HD __forceinline__ bool preds(int s, u64 b) const {
+        const int np = nfa.n_preds[s];
+        if (np == 0) return true;
+        int a0, a1;
+        attrs(b, a0, a1);
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < SIESTA_MAX_PREDS; ++k) {
+            if (k < np) {
+                const bool is_pos = nfa.p_attr[s][k] == SIESTA_ATTR_POSITION;
+                const int sh = 8 * nfa.p_ref[s][k];
+                const long long lhs = is_pos ? a0 : a1;
+                const long long rhs = (long long)(((is_pos ? v0 : v1) >> sh) & 0xFFull) + nfa.p_c[s][k];
+                ok = ok && (nfa.p_op[s][k] == SIESTA_OP_LE ? lhs <= rhs : lhs >= rhs);
+            }
+        }
+        return ok;
+    }
+    SIESTA_HD __forceinline__ void take(int s, u64 b) {
+        int a0, a1;
+        attrs(b, a0, a1);
+        v0 |= (u64)(unsigned)a0 << (8 * s);
+        if (EVT) v1 |= (u64)(unsigned)a1 << (8 * s);
+    }
+    // run started at the event with bit sb: its events as a mask, 0 = never completes / deleted at a negative state
+    SIESTA_HD __forceinline__ u64 walk(const u64* T, u64 sb) {
+        const int S = nfa.n_states;
+        v0 = v1 = 0;
+        if (nfa.need_vv) take(0, sb);
+        u64 taken = sb, pb = sb;
+        int k_next = 1;
+#pragma unroll
+        for (int k = 1; k < SIESTA_MAX_STATES; ++k) {
+            if (k >= S) break;
+            if (k != k_next) continue;
+            const bool neg = nfa.kind[k] == SIESTA_STATE_NEGATIVE;
+            u64 c = (neg ? (T[k] | T[k + 1]) : T[k]) & ~(pb | (pb - 1));
+            u64 got = 0;
+            while (c) {
+                const u64 eb = c & (0ull - c);
+                c ^= eb;
+                if (neg) {
+                    if (T[k] & eb) {
+                        if (preds(k, eb)) return 0;     // containsNegative: deleted (Engine.java:679-682)
+                    } else if (preds(k + 1, eb)) {      // Engine.checkPredicatesForNextState :1165-1180
+                        got = eb;
+                        break;
+                    }
+                } else if (preds(k, eb)) {
+                    got = eb;
+                    break;
+                }
+            }
+            if (!got) return 0;
+            const int ks = neg ? k + 1 : k;
+            if (nfa.need_vv) take(ks, got);
+            taken |= got;
+            pb = got;
+            k_next = ks + 1;
+        }
+        return taken;
+    }
+};
+
+// first-largest occurrence = smallest (completion, start); first_only as in nk_eval
+template <bool EVT>
+SIESTA_HD __forceinline__ bool nkp_eval(const DevNfa& nfa, unsigned long long R, int lead, const unsigned long long* T,
+                                        unsigned long long& best, unsigned& n_emitted, bool first_only) {
+    typedef unsigned long long u64;
+    const int S = nfa.n_states;
+    n_emitted = 0;
+    best = 0;
+#pragma unroll
+    for (int k = 0; k < SIESTA_MAX_STATES; ++k)
+        if (k < S && nfa.kind[k] != SIESTA_STATE_NEGATIVE && T[k] == 0) return false;
+    NkpWalk<EVT> w(nfa, R, lead);
+    int best_c = 0;
+    for (u64 r = T[0]; r;) {
+        const u64 sb = r & (0ull - r);
+        r ^= sb;
+        const u64 m = w.walk(T, sb);
+        if (!m) continue;
+        ++n_emitted;
+        const int c = 63 - clz64(m);
+        if (!best || c < best_c) { best = m; best_c = c; }
+        if (first_only) break;
+    }
+    return best != 0;
 }
 
 }  // namespace siesta

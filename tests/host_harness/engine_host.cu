@@ -49,7 +49,9 @@ static int run_one(const DevNfa& dn, const std::vector<uint32_t>& meta, const st
         NkMasks<W> nm;
         nm.init();
         for (int j = 0; j < ev.n; ++j) nm.on_event(j, ev.word(j));
-        if (!nk_eval<W>(dn, ev, nm.T, (flags & SIESTA_F_RETURN_ALL) != 0, evt_pos, aux.data(), 1, s.data(), nsel, *n_emitted)) return 0;
+        // same rule as kernel K1: stop at the first completed start when the walks are monotone and nothing is counted
+        const bool first_only = !(flags & (SIESTA_F_RETURN_ALL | SIESTA_F_COUNT_MATCHES)) && !needs_ts;
+        if (!nk_eval<W>(dn, ev, nm.T, (flags & SIESTA_F_RETURN_ALL) != 0, evt_pos, aux.data(), 1, s.data(), nsel, *n_emitted, first_only)) return 0;
         sel.assign(s.begin(), s.begin() + nsel);
         return 1;
     }
@@ -110,6 +112,46 @@ extern "C" int engine_host_detect(const int64_t* trace_off, const int32_t* act, 
         if (meta.empty()) continue;
         if (b1 - b0 > 65536) return SIESTA_E_UNSUPPORTED;
         unsigned emitted = 0;
+        // kernel K1-P (detect_nkp_kernel): class NK, first-largest only, no relative seconds needed, the trace fits the
+        // 64 raw position slots that start at the 32-byte sector of its first event
+        const int lead = (int)(b0 & 7);
+        if (dn.fast_class == FAST_NK && !(flags & SIESTA_F_RETURN_ALL) && !needs_ts && (b1 - b0) + lead <= 64) {
+            unsigned long long T[SIESTA_MAX_STATES + 1] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, R = 0;
+            for (uint32_t m : meta) {
+                const int slot = (int)(m >> 16) + lead;
+                R |= 1ull << slot;
+                for (int k = 0; k < SIESTA_MAX_STATES; ++k)
+                    if (m & (1u << k)) T[k] |= 1ull << slot;
+            }
+            PosEvents pe{R, lead, evt_pos};
+            unsigned long long sel[1], sel_g[1];
+            int nsel = 0;
+            unsigned emitted_g = 0;
+            const bool first_only = !(flags & SIESTA_F_COUNT_MATCHES);
+            // the kernel's specialised evaluator, cross-checked here against the generic one on the PosEvents accessor
+            const bool hit = evt_pos ? nkp_eval<true>(dn, R, lead, T, sel[0], emitted, first_only)
+                                     : nkp_eval<false>(dn, R, lead, T, sel[0], emitted, first_only);
+            const bool hit_g = nk_eval<2>(dn, pe, T, false, evt_pos, (unsigned long long*)nullptr, 0, sel_g, nsel, emitted_g, first_only);
+            if (hit != hit_g || (hit && (sel[0] != sel_g[0] || emitted != emitted_g))) {
+                siesta::set_error("nkp_eval disagrees with nk_eval<PosEvents>");
+                return -99;
+            }
+            if (!hit) continue;
+            o.emitted += emitted;
+            o.trace_idx.push_back(t);
+            for (unsigned long long m = sel[0]; m; m &= m - 1) {
+                const int j = __builtin_ffsll((long long)m) - 1;
+                const int src = j - lead;
+                o.ev_pos.push_back(src);
+                o.ev_rank.push_back(pe.rank(j));
+                o.ev_act.push_back(act[b0 + src]);
+                const long long raw = ts_ms[b0 + src];
+                o.ev_ts.push_back(evt_pos ? raw : (long long)((int)((raw - t0) / 1000)) * 1000 + t0);
+            }
+            o.ev_off.push_back((int64_t)o.ev_pos.size());
+            o.occ_off.push_back((int64_t)o.ev_off.size() - 1);
+            continue;
+        }
         int status;
         std::vector<uint32_t> sel1;
         std::vector<unsigned long long> sel2;

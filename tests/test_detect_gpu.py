@@ -419,3 +419,35 @@ def test_concurrent_requests_on_one_log(ctx):
         t.join()
     log.close()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_raw_slot_kernel_nk_class(ctx, seed):
+    """Kernel K1-P (class NK over raw position slots): random NK NFAs, trace lengths on both sides of the 64-slot
+    limit (longer traces re-run on the staged kernel, > 24 relevant events on the wide one), alphabets of <= 32 and
+    <= 64 activities, EventTs / EventPos routes, exact match counts, candidate lists."""
+    from tests import soak_fast
+    rng = np.random.default_rng(9100 + seed)
+    n_match = 0
+    for it in range(40):
+        n_act = int(rng.choice([3, 5, 8, 20, 40, 64]))
+        lo, hi = [(0, 30), (40, 70), (55, 66), (0, 130)][it % 4]
+        off, act, ts = gen.make_log(700, lo, hi, n_act, seed=int(rng.integers(1 << 30)), max_gap_s=300)
+        states = soak_fast.nk_nfa(rng, min(n_act, 8))
+        for st in states:   # no time predicates on the EventTs route: those need relative seconds (staged kernel)
+            st["preds"] = [p for p in st["preds"] if p[0] == abi.ATTR_POSITION or it % 2 == 0]
+        flags = abi.F_EVT_POS if it % 2 == 0 else 0
+        if rng.random() < 0.3:
+            flags |= abi.F_COUNT_MATCHES
+        if rng.random() < 0.2:
+            flags |= abi.F_NO_EVENT_COLUMNS
+        cand = None
+        if rng.random() < 0.3:
+            cand = np.sort(rng.choice(700, size=300, replace=False)).astype(np.int64)
+        try:
+            got = _check(ctx, off, act, ts, n_act, states, flags, cand=cand)
+        except SiestaError as e:  # a trace with more than 64 relevant events: reported, never silently wrong
+            assert e.code == abi.E_UNSUPPORTED
+            continue
+        n_match += got.n_traces
+    assert n_match > 1000
