@@ -542,8 +542,11 @@ __global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4)
 // popcount of the relevant-slot mask below a slot.  No shared memory, no second pass, no per-event loop after the
 // plane scan.  Traces that do not fit 64 slots go to the overflow list and re-run on the staged kernel above.
 // Output and counters are those of detect_kernel (phase C), so the placement kernels below serve both.
+#ifndef SIESTA_NKP_MIN_CTAS
+#define SIESTA_NKP_MIN_CTAS 6   // 80 registers (a few spills in the scan): measured 0.584 ms vs 0.601 ms with 5 on the configs[4] shape
+#endif
 template <int NPL, bool WIDE, bool EVT>
-__global__ void __launch_bounds__(NT_MAX, 5) detect_nkp_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ DevNfa nfa) {
+__global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ DevNfa nfa) {
     typedef MaskX<2> MO;
     typedef unsigned long long mask_t;
     const int lane = threadIdx.x & 31;
@@ -587,19 +590,26 @@ __global__ void __launch_bounds__(NT_MAX, 5) detect_nkp_kernel(const __grid_cons
         for (int p = 0; p < 3; ++p) pl[p] = p < NPL ? (((mask_t)pa[p] | ((mask_t)pb[p] << 32)) & valid) : 0ull;
         const mask_t R = pl[0] | pl[1] | pl[2];
         // state masks: class c (1..7) = minterm of the planes; cls_word[c] bit k <=> class c belongs to state k
+        mask_t M[8];
+#pragma unroll
+        for (int c = 1; c < 8; ++c) {
+            M[c] = 0;
+            if (c < (1 << NPL)) {
+                mask_t m = R;
+#pragma unroll
+                for (int p = 0; p < NPL; ++p) m &= ((c >> p) & 1) ? pl[p] : ~pl[p];
+                M[c] = m;
+            }
+        }
         mask_t T[SIESTA_MAX_STATES + 1];
 #pragma unroll
-        for (int k = 0; k <= SIESTA_MAX_STATES; ++k) T[k] = 0;
+        for (int k = 0; k <= SIESTA_MAX_STATES; ++k) {
+            T[k] = 0;
+            if (k < nfa.n_states) {  // uniform
 #pragma unroll
-        for (int c = 1; c < (1 << NPL); ++c) {
-            const uint32_t w = P.cls_word[c];
-            if (w == 0) continue;  // uniform
-            mask_t m = R;
-#pragma unroll
-            for (int p = 0; p < NPL; ++p) m &= ((c >> p) & 1) ? pl[p] : ~pl[p];
-#pragma unroll
-            for (int k = 0; k < SIESTA_MAX_STATES; ++k)
-                if (w & (1u << k)) T[k] |= m;
+                for (int c = 1; c < (1 << NPL); ++c)
+                    if (P.cls_word[c] & (1u << k)) T[k] |= M[c];
+            }
         }
 
         int status = ST_NONE;
