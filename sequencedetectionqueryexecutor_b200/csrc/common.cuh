@@ -50,7 +50,8 @@ struct Log {
     const int64_t* d_ts_ms = nullptr;      // [E]
     int64_t n_traces = 0, n_events = 0;
     int32_t n_activities = 0;
-    int32_t max_trace_len = 0;
+    int32_t max_trace_len = 0;             // caller's hint (wrapped logs) or exact (loaded logs)
+    int64_t true_max_len = -1;             // exact, measured on the device on first use (declare counting); -1 = not yet
     bool owns = false;
     int64_t first_trace = 0;  // global index of trace 0 (multi-GPU shards)
     bool act_valid = false;  // every activity id lies in [0, n_activities): kernels may skip the per-event range check

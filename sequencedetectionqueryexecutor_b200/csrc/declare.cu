@@ -15,6 +15,7 @@
 // All counters of a CTA live in shared memory (uint32) and are flushed with 64-bit atomics once per CTA.
 // Bound: integer ALU / shared-memory atomics, not HBM (4 B/event + 8 B/trace of traffic); see DESIGN.md.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -250,6 +251,279 @@ __global__ void __launch_bounds__(DT) declare_alt_chain_kernel(const __grid_cons
     }
 }
 
+
+// ---------------------------------------------------------------------------------- K3 v2: position masks + pair-owned counters
+// For alphabets of at most 32 activities and traces of at most 64 * NW2 events every count of a trace follows from the
+// per-activity POSITION MASKS M[a] (bit i <=> event i is an a), with BL[b] = bits below the last b and AF[a] = bits
+// above the first a:
+//     response[a][b]   += popc(M[a] & BL[b])              #{a : some b after a}   (countResponse :25-31)
+//     precedence[a][b] += popc(M[b] & AF[a])              #{b : some a before b}  (countPrecedence :38-44)
+//     ordered[a][b]    += (M[a] & BL[b]) != 0             first a < last b        (queryIndexTableDeclare :389-404)
+//     co[a][b]         += ordered(a,b) or ordered(b,a)    both present, a != b    (joinUnionTraces :164-179)
+//     alternate[a][b]  += popc((~M[b] + M[a]) & M[b])     the b's whose nearest earlier event among {a, b} is an a: adding
+//                         M[a] to ~M[b] lets a carry run from every a through the slots that hold no b and land on the next
+//                         b (countResponseAlternate :51-60 = countPrecedenceAlternate :67-76, see declare_alt_chain_kernel)
+// A CTA works on batches of TB traces.  Phase 1, one warp per trace, lanes = events: __match_any_sync groups the 32
+// events of a chunk by activity and the group's leader stores the group mask as one word of M[activity] (shared memory);
+// then lanes = activities derive BL / AF, the existence counts (tot, uniq, hist, diagonal) and lanes = events count the
+// chain pairs.  Phase 2, one THREAD per unordered activity pair {a < b}: it reads the six masks of its pair for each of
+// the TB traces and keeps the nine counters of the pair in registers for the whole launch: no atomics, no serial pass
+// over the events.  Cost per trace: ~70 warp instructions (phase 1) + 54 per pair-thread warp (phase 2), against ~2 000
+// of the serial kernels above.  Longer traces or larger alphabets keep those kernels.
+constexpr int TB = 32;  // traces per batch
+
+template <int NW2>
+struct PosMask;
+template <>
+struct PosMask<1> {
+    typedef unsigned long long T;
+    static __device__ __forceinline__ int popc(T m) { return __popcll(m); }
+    static __device__ __forceinline__ T below_last(T m) { return m ? ~(~0ull << (63 - __clzll(m))) : 0ull; }
+    static __device__ __forceinline__ T above_first(T m) { const T b = m & (0ull - m); return m ? ~(b | (b - 1)) : 0ull; }
+    static __device__ __forceinline__ int alt(T ma, T mb) { return __popcll((~mb + ma) & mb); }
+    static __device__ __forceinline__ bool any(T m) { return m != 0; }
+};
+template <>
+struct PosMask<2> {
+    typedef ulonglong2 T;  // x = slots 0..63, y = slots 64..127
+    static __device__ __forceinline__ int popc(T m) { return __popcll(m.x) + __popcll(m.y); }
+    static __device__ __forceinline__ T below_last(T m) {
+        T r;
+        if (m.y) { r.x = ~0ull; r.y = ~(~0ull << (63 - __clzll(m.y))); }
+        else { r.y = 0; r.x = m.x ? ~(~0ull << (63 - __clzll(m.x))) : 0ull; }
+        return r;
+    }
+    static __device__ __forceinline__ T above_first(T m) {
+        T r;
+        if (m.x) { const unsigned long long b = m.x & (0ull - m.x); r.x = ~(b | (b - 1)); r.y = ~0ull; }
+        else { const unsigned long long b = m.y & (0ull - m.y); r.x = 0; r.y = m.y ? ~(b | (b - 1)) : 0ull; }
+        return r;
+    }
+    static __device__ __forceinline__ int alt(T ma, T mb) {
+        const unsigned __int128 s = (((unsigned __int128)~mb.y << 64) | ~mb.x) + (((unsigned __int128)ma.y << 64) | ma.x);  // one carry chain
+        return __popcll((unsigned long long)s & mb.x) + __popcll((unsigned long long)(s >> 64) & mb.y);
+    }
+    static __device__ __forceinline__ bool any(T m) { return (m.x | m.y) != 0; }
+};
+template <int NW2>
+__device__ __forceinline__ typename PosMask<NW2>::T mask_and(typename PosMask<NW2>::T a, typename PosMask<NW2>::T b);
+template <>
+__device__ __forceinline__ unsigned long long mask_and<1>(unsigned long long a, unsigned long long b) { return a & b; }
+template <>
+__device__ __forceinline__ ulonglong2 mask_and<2>(ulonglong2 a, ulonglong2 b) { return make_ulonglong2(a.x & b.x, a.y & b.y); }
+
+// NW2 = 64-bit words per mask (1: traces <= 64 events, 2: <= 128); PPT = activity pairs per thread
+template <int NW2, int PPT>
+__global__ void __launch_bounds__(256, 3) declare_pairs_kernel(const __grid_constant__ DeclareParams P) {
+    typedef PosMask<NW2> PM;
+    typedef typename PM::T mask_t;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int A = P.A, AA = A * A;
+    mask_t* sM = reinterpret_cast<mask_t*>(smem_raw);   // [TB][A]
+    mask_t* sBL = sM + TB * A;
+    mask_t* sAF = sBL + TB * A;
+    uint32_t* s_chain = reinterpret_cast<uint32_t*>(sAF + TB * A);  // [A][A]
+    uint32_t* s_first = s_chain + AA;
+    uint32_t* s_last = s_first + A;
+    uint32_t* s_hist = s_last + A;                                   // [A][HS]
+    __shared__ unsigned long long s_misc[2];                         // hist_overflow, n_nonempty
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < AA + 2 * A + A * HS; i += blockDim.x) s_chain[i] = 0;
+    if (threadIdx.x < 2) s_misc[threadIdx.x] = 0;
+
+    // the pairs {a < b} of this thread: pair index q = threadIdx.x + j * blockDim.x, row-major over a
+    int pa[PPT], pb[PPT];
+    const int n_pairs = A * (A - 1) / 2;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        int q = threadIdx.x + j * blockDim.x;
+        pa[j] = pb[j] = -1;
+        if (q < n_pairs) {
+            int a = 0;
+            while (q >= A - 1 - a) { q -= A - 1 - a; ++a; }
+            pa[j] = a;
+            pb[j] = a + 1 + q;
+        }
+    }
+    uint32_t c_co[PPT], c_ord_ab[PPT], c_ord_ba[PPT], c_r_ab[PPT], c_r_ba[PPT], c_p_ab[PPT], c_p_ba[PPT], c_alt_ab[PPT], c_alt_ba[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) c_co[j] = c_ord_ab[j] = c_ord_ba[j] = c_r_ab[j] = c_r_ba[j] = c_p_ab[j] = c_p_ba[j] = c_alt_ab[j] = c_alt_ba[j] = 0;
+    // lanes = activities (phase 1): existence counts of activity `lane`, summed over the traces this warp builds
+    unsigned long long a_tot = 0, a_uniq = 0, a_diag = 0, w_nonempty = 0, w_hist_ovf = 0;
+    __syncthreads();
+
+    unsigned long long* o_tot = P.out;
+    unsigned long long* o_uniq = o_tot + A;
+    unsigned long long* o_first = o_uniq + A;
+    unsigned long long* o_last = o_first + A;
+    unsigned long long* o_hist = o_last + A;
+    unsigned long long* o_co = o_hist + (long long)A * (P.k_cap + 1);
+    unsigned long long* o_ord = o_co + AA;
+    unsigned long long* o_resp = o_ord + AA;
+    unsigned long long* o_prec = o_resp + AA;
+    unsigned long long* o_alt_r = o_prec + AA;
+    unsigned long long* o_alt_p = o_alt_r + AA;
+    unsigned long long* o_chain_r = o_alt_p + AA;
+    unsigned long long* o_chain_p = o_chain_r + AA;
+
+    auto flush_pairs = [&]() {
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            if (pa[j] < 0) continue;
+            const long long ab = (long long)pa[j] * A + pb[j], ba = (long long)pb[j] * A + pa[j];
+            if (c_co[j]) { atomicAdd(o_co + ab, (unsigned long long)c_co[j]); atomicAdd(o_co + ba, (unsigned long long)c_co[j]); }
+            if (c_ord_ab[j]) atomicAdd(o_ord + ab, (unsigned long long)c_ord_ab[j]);
+            if (c_ord_ba[j]) atomicAdd(o_ord + ba, (unsigned long long)c_ord_ba[j]);
+            if (c_r_ab[j]) atomicAdd(o_resp + ab, (unsigned long long)c_r_ab[j]);
+            if (c_r_ba[j]) atomicAdd(o_resp + ba, (unsigned long long)c_r_ba[j]);
+            if (c_p_ab[j]) atomicAdd(o_prec + ab, (unsigned long long)c_p_ab[j]);
+            if (c_p_ba[j]) atomicAdd(o_prec + ba, (unsigned long long)c_p_ba[j]);
+            if (c_alt_ab[j]) { atomicAdd(o_alt_r + ab, (unsigned long long)c_alt_ab[j]); atomicAdd(o_alt_p + ab, (unsigned long long)c_alt_ab[j]); }
+            if (c_alt_ba[j]) { atomicAdd(o_alt_r + ba, (unsigned long long)c_alt_ba[j]); atomicAdd(o_alt_p + ba, (unsigned long long)c_alt_ba[j]); }
+            c_co[j] = c_ord_ab[j] = c_ord_ba[j] = c_r_ab[j] = c_r_ba[j] = c_p_ab[j] = c_p_ba[j] = c_alt_ab[j] = c_alt_ba[j] = 0;
+        }
+    };
+
+    const long long n_batches = (P.n_traces + TB - 1) / TB;
+    int since_flush = 0;
+    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+        // ---------------------------------------------------------------- phase 1: masks of the batch's traces
+        for (int slot = warp; slot < TB; slot += n_warps) {
+            const long long t = batch * TB + slot;
+            mask_t* M = sM + slot * A;
+            if (lane < A) {
+                mask_t z;
+                memset(&z, 0, sizeof(z));
+                M[lane] = z;
+            }
+            long long lo = 0, hi = 0;
+            if (t < P.n_traces && lane == 0) { lo = P.trace_off[t]; hi = P.trace_off[t + 1]; }
+            lo = shfl64(lo, 0);
+            hi = shfl64(hi, 0);
+            const int len = (int)(hi - lo);
+            __syncwarp();
+            uint32_t* Mw = reinterpret_cast<uint32_t*>(M);  // word w of activity x at [x * 2 * NW2 + w]
+            int px = -1;  // activity of the event before this chunk
+            for (int base = 0; base < len; base += 32) {
+                const int x = base + lane < len ? __ldg(P.act + lo + base + lane) : -1;
+                const bool valid = x >= 0 && x < A;
+                const unsigned grp = __match_any_sync(0xffffffffu, x);
+                if (valid && lane == __ffs(grp) - 1) Mw[x * 2 * NW2 + (base >> 5)] = grp;
+                // chain pairs (countResponseChain :83-89 = countPrecedenceChain :96-102): adjacent events a b, a != b
+                int prev = __shfl_up_sync(0xffffffffu, x, 1);
+                if (lane == 0) prev = px;
+                const bool pvalid = prev >= 0 && prev < A;
+                if (valid && pvalid && prev != x) atomicAdd(&s_chain[prev * A + x], 1u);
+                px = __shfl_sync(0xffffffffu, x, 31);
+                if (base == 0 && lane == 0 && valid) atomicAdd(&s_first[x], 1u);                 // QueryPlanPositions :51-79
+                if (base + 32 >= len && lane == ((len - 1) & 31) && valid) atomicAdd(&s_last[x], 1u);
+            }
+            __syncwarp();
+            if (len > 0) ++w_nonempty;
+            if (lane < A) {
+                const mask_t m = M[lane];
+                const int cnt = PM::popc(m);
+                sBL[slot * A + lane] = PM::below_last(m);
+                sAF[slot * A + lane] = PM::above_first(m);
+                if (cnt) {
+                    a_tot += cnt;
+                    ++a_uniq;
+                    if (cnt >= 2) ++a_diag;
+                    if (cnt > P.k_cap) ++w_hist_ovf;
+                    else if (cnt < HS) atomicAdd(&s_hist[lane * HS + cnt], 1u);
+                    else atomicAdd(o_hist + (long long)lane * (P.k_cap + 1) + cnt, 1ull);
+                }
+            }
+        }
+        __syncthreads();
+        // ---------------------------------------------------------------- phase 2: one thread per activity pair
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            if (pa[j] < 0) continue;
+            const int a = pa[j], b = pb[j];
+#pragma unroll 2
+            for (int slot = 0; slot < TB; ++slot) {
+                const mask_t Ma = sM[slot * A + a], Mb = sM[slot * A + b];
+                const mask_t BLa = sBL[slot * A + a], BLb = sBL[slot * A + b];
+                const mask_t AFa = sAF[slot * A + a], AFb = sAF[slot * A + b];
+                const int r_ab = PM::popc(mask_and<NW2>(Ma, BLb)), r_ba = PM::popc(mask_and<NW2>(Mb, BLa));
+                c_r_ab[j] += r_ab;
+                c_r_ba[j] += r_ba;
+                c_p_ab[j] += PM::popc(mask_and<NW2>(Mb, AFa));
+                c_p_ba[j] += PM::popc(mask_and<NW2>(Ma, AFb));
+                c_ord_ab[j] += r_ab != 0;
+                c_ord_ba[j] += r_ba != 0;
+                c_co[j] += (r_ab | r_ba) != 0;
+                c_alt_ab[j] += PM::alt(Ma, Mb);
+                c_alt_ba[j] += PM::alt(Mb, Ma);
+            }
+        }
+        __syncthreads();
+        // 32-bit counters: a pair gains at most 64 * NW2 per trace
+        if (++since_flush >= (1 << 24) / (TB * 64 * NW2)) { flush_pairs(); since_flush = 0; }
+    }
+    flush_pairs();
+    if (lane < A) {
+        if (a_tot) atomicAdd(o_tot + lane, a_tot);
+        if (a_uniq) atomicAdd(o_uniq + lane, a_uniq);
+        if (a_diag) { atomicAdd(o_co + (long long)lane * A + lane, a_diag); atomicAdd(o_ord + (long long)lane * A + lane, a_diag); }
+    }
+    if (lane == 0) {
+        if (w_nonempty) atomicAdd(&s_misc[1], w_nonempty);
+    }
+    if (w_hist_ovf) atomicAdd(&s_misc[0], w_hist_ovf);
+    __syncthreads();
+    for (int i = threadIdx.x; i < A; i += blockDim.x) {
+        if (s_first[i]) atomicAdd(o_first + i, (unsigned long long)s_first[i]);
+        if (s_last[i]) atomicAdd(o_last + i, (unsigned long long)s_last[i]);
+    }
+    for (int i = threadIdx.x; i < A * HS; i += blockDim.x) {
+        const int a = i / HS, k = i % HS;
+        if (s_hist[i] && k <= P.k_cap) atomicAdd(o_hist + (long long)a * (P.k_cap + 1) + k, (unsigned long long)s_hist[i]);
+    }
+    for (int i = threadIdx.x; i < AA; i += blockDim.x)
+        if (s_chain[i]) {
+            atomicAdd(o_chain_r + i, (unsigned long long)s_chain[i]);
+            atomicAdd(o_chain_p + i, (unsigned long long)s_chain[i]);
+        }
+    if (threadIdx.x == 0) {
+        if (s_misc[0]) atomicAdd(o_prec + 5ll * AA, s_misc[0]);
+        if (s_misc[1]) atomicAdd(o_prec + 5ll * AA + 1, s_misc[1]);
+    }
+}
+
+__global__ void max_trace_len_kernel(const int64_t* trace_off, int64_t n_traces, unsigned long long* out) {
+    unsigned long long m = 0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_traces; t += (int64_t)gridDim.x * blockDim.x) {
+        const long long d = trace_off[t + 1] - trace_off[t];
+        if (d > 0 && (unsigned long long)d > m) m = (unsigned long long)d;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(0xffffffffu, m, d);
+        m = y > m ? y : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+template <int NW2, int PPT>
+static int launch_pairs(const Ctx* ctx, cudaStream_t stream, const DeclareParams& P, int threads) {
+    const int A = P.A;
+    const size_t smem = (size_t)3 * TB * A * sizeof(typename PosMask<NW2>::T) + sizeof(uint32_t) * ((size_t)A * A + 2 * A + (size_t)A * HS);
+    auto kern = declare_pairs_kernel<NW2, PPT>;
+    SIESTA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t n_batches = (P.n_traces + TB - 1) / TB;
+    int grid = (int)std::min<int64_t>(std::max<int64_t>(n_batches, 1), (int64_t)ctx->sm_count * per_sm);
+    kern<<<grid, threads, smem, stream>>>(P);
+    SIESTA_LAUNCHED();
+    SIESTA_CUDA_OK(cudaGetLastError());
+    return SIESTA_OK;
+}
+
 template <int NB>
 static int launch_alt_chain(const Ctx* ctx, cudaStream_t stream, const DeclareParams& P) {
     const size_t smem = sizeof(uint32_t) * (size_t)2 * P.A * P.A;
@@ -316,19 +590,45 @@ extern "C" int siesta_declare_counts_device(siesta_log* log, int32_t k_cap, int6
     SIESTA_CUDA_OK(cudaEventCreate(&e0));
     SIESTA_CUDA_OK(cudaEventCreate(&e1));
     SIESTA_CUDA_OK(cudaMemsetAsync(d_out, 0, sizeof(int64_t) * (size_t)siesta_declare_counts_size(A, k_cap), stream));
+    int rc = SIESTA_OK;
+    // exact length of the longest trace (the caller's hint is not trusted); cached on the log
+    if (L->true_max_len < 0) {
+        unsigned long long* d_max = nullptr;
+        SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_max, 8, stream));
+        SIESTA_CUDA_OK(cudaMemsetAsync(d_max, 0, 8, stream));
+        if (L->n_traces > 0) {
+            max_trace_len_kernel<<<(unsigned)std::min<int64_t>((L->n_traces + 255) / 256, 4 * L->ctx->sm_count), 256, 0, stream>>>(L->d_trace_off, L->n_traces, d_max);
+            SIESTA_LAUNCHED();
+        }
+        unsigned long long h_max = 0;
+        SIESTA_CUDA_OK(cudaMemcpyAsync(&h_max, d_max, 8, cudaMemcpyDeviceToHost, stream));
+        SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+        cudaFreeAsync(d_max, stream);
+        L->true_max_len = (int64_t)h_max;
+    }
     SIESTA_CUDA_OK(cudaEventRecord(e0, stream));
-    int rc;
-    const int nb = (A + 31) / 32;
-    if (nb == 1) rc = launch_declare<1>(L->ctx, stream, P);
-    else if (nb == 2) rc = launch_declare<2>(L->ctx, stream, P);
-    else if (nb == 3) rc = launch_declare<3>(L->ctx, stream, P);
-    else rc = launch_declare<4>(L->ctx, stream, P);
-    if (rc) return rc;
-    if (nb == 1) rc = launch_alt_chain<1>(L->ctx, stream, P);
-    else if (nb == 2) rc = launch_alt_chain<2>(L->ctx, stream, P);
-    else if (nb == 3) rc = launch_alt_chain<3>(L->ctx, stream, P);
-    else rc = launch_alt_chain<4>(L->ctx, stream, P);
-    if (rc) return rc;
+    const bool pairs_path = A <= 32 && L->true_max_len <= 128 && std::getenv("SIESTA_K3_SERIAL") == nullptr;
+    if (pairs_path) {
+        // one kernel: position masks + pair-owned counters
+        const int n_pairs = A * (A - 1) / 2;
+        const int ppt = n_pairs > 256 ? 2 : 1;
+        const int threads = std::max(32, std::min(256, ((ppt == 1 ? n_pairs : (n_pairs + 1) / 2) + 31) / 32 * 32));
+        if (L->true_max_len <= 64) rc = ppt == 1 ? launch_pairs<1, 1>(L->ctx, stream, P, threads) : launch_pairs<1, 2>(L->ctx, stream, P, threads);
+        else rc = ppt == 1 ? launch_pairs<2, 1>(L->ctx, stream, P, threads) : launch_pairs<2, 2>(L->ctx, stream, P, threads);
+        if (rc) return rc;
+    } else {
+        const int nb = (A + 31) / 32;
+        if (nb == 1) rc = launch_declare<1>(L->ctx, stream, P);
+        else if (nb == 2) rc = launch_declare<2>(L->ctx, stream, P);
+        else if (nb == 3) rc = launch_declare<3>(L->ctx, stream, P);
+        else rc = launch_declare<4>(L->ctx, stream, P);
+        if (rc) return rc;
+        if (nb == 1) rc = launch_alt_chain<1>(L->ctx, stream, P);
+        else if (nb == 2) rc = launch_alt_chain<2>(L->ctx, stream, P);
+        else if (nb == 3) rc = launch_alt_chain<3>(L->ctx, stream, P);
+        else rc = launch_alt_chain<4>(L->ctx, stream, P);
+        if (rc) return rc;
+    }
     SIESTA_CUDA_OK(cudaEventRecord(e1, stream));
     SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
     float ms = 0.f;

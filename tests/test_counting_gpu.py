@@ -18,7 +18,12 @@ def ctx():
 
 @pytest.mark.parametrize("n_act,n_traces,lens,zipf", [(3, 50, (0, 12), None), (20, 3000, (30, 70), None),
                                                       (20, 3000, (30, 70), 1.1), (100, 1500, (50, 50), None),
-                                                      (33, 700, (0, 90), 1.1), (64, 300, (1, 300), None)])
+                                                      (33, 700, (0, 90), 1.1), (64, 300, (1, 300), None),
+                                                      # K3 v2 (position masks, pair-owned counters): <= 32 activities and
+                                                      # <= 64 / <= 128 events per trace; one event more falls back
+                                                      (32, 2500, (0, 64), None), (24, 2000, (60, 64), 1.1), (23, 1500, (0, 128), None),
+                                                      (32, 900, (100, 128), 1.1), (2, 3000, (0, 40), None), (1, 500, (0, 9), None),
+                                                      (20, 800, (0, 129), None), (7, 4099, (33, 33), None)])
 def test_declare_counts_match_oracle(ctx, n_act, n_traces, lens, zipf):
     off, act, ts = gen.make_log(n_traces, lens[0], lens[1], n_act, seed=100 + n_act, zipf=zipf)
     log = ctx.load_log(off, act, ts, n_act)

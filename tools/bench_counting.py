@@ -26,7 +26,7 @@ def main():
     dev = torch.device("cuda", 0)
     peak, _ = bench.measured_peak_gbs()
     out = []
-    for name, n_act, lo, hi in (("cfg3_declare_20act", 20, 30, 70), ("cfg4_stats_100act", 100, 50, 50)):
+    for name, n_act, lo, hi in (("cfg3_declare_20act", 20, 30, 70), ("declare_20act_len50", 20, 50, 50), ("cfg4_stats_100act", 100, 50, 50)):
         off, act, ts = bench.make_log_fast(args.traces, lo, hi, n_act, 0x51E57A03, 600)
         T, E = len(off) - 1, len(act)
         d = [torch.from_numpy(x).to(dev) for x in (off, act, ts)]
