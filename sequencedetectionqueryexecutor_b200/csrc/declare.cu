@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(DT) declare_alt_chain_kernel(const __grid_cons
 
 
 // ---------------------------------------------------------------------------------- K3 v2: position masks + pair-owned counters
-// For alphabets of at most 32 activities and traces of at most 64 * NW2 events every count of a trace follows from the
+// For alphabets of at most 32 activities and traces of at most 32 * NW <= 128 events every count of a trace follows from the
 // per-activity POSITION MASKS M[a] (bit i <=> event i is an a), with BL[b] = bits below the last b and AF[a] = bits
 // above the first a:
 //     response[a][b]   += popc(M[a] & BL[b])              #{a : some b after a}   (countResponse :25-31)
@@ -272,50 +272,76 @@ __global__ void __launch_bounds__(DT) declare_alt_chain_kernel(const __grid_cons
 // of the serial kernels above.  Longer traces or larger alphabets keep those kernels.
 constexpr int TB = 32;  // traces per batch
 
-template <int NW2>
-struct PosMask;
-template <>
-struct PosMask<1> {
-    typedef unsigned long long T;
-    static __device__ __forceinline__ int popc(T m) { return __popcll(m); }
-    static __device__ __forceinline__ T below_last(T m) { return m ? ~(~0ull << (63 - __clzll(m))) : 0ull; }
-    static __device__ __forceinline__ T above_first(T m) { const T b = m & (0ull - m); return m ? ~(b | (b - 1)) : 0ull; }
-    static __device__ __forceinline__ int alt(T ma, T mb) { return __popcll((~mb + ma) & mb); }
-    static __device__ __forceinline__ bool any(T m) { return m != 0; }
-};
-template <>
-struct PosMask<2> {
-    typedef ulonglong2 T;  // x = slots 0..63, y = slots 64..127
-    static __device__ __forceinline__ int popc(T m) { return __popcll(m.x) + __popcll(m.y); }
-    static __device__ __forceinline__ T below_last(T m) {
+// Position mask of NW 32-bit words (2: traces <= 64 events, 3: <= 96, 4: <= 128); 3 words are stored padded to 16 bytes.
+template <int NW>
+struct PosMask {
+    static constexpr int STORE = NW == 3 ? 4 : NW;
+    struct alignas(NW == 2 ? 8 : 16) T { uint32_t w[STORE]; };
+    static __device__ __forceinline__ T zero() {
         T r;
-        if (m.y) { r.x = ~0ull; r.y = ~(~0ull << (63 - __clzll(m.y))); }
-        else { r.y = 0; r.x = m.x ? ~(~0ull << (63 - __clzll(m.x))) : 0ull; }
+#pragma unroll
+        for (int i = 0; i < STORE; ++i) r.w[i] = 0;
         return r;
     }
-    static __device__ __forceinline__ T above_first(T m) {
-        T r;
-        if (m.x) { const unsigned long long b = m.x & (0ull - m.x); r.x = ~(b | (b - 1)); r.y = ~0ull; }
-        else { const unsigned long long b = m.y & (0ull - m.y); r.x = 0; r.y = m.y ? ~(b | (b - 1)) : 0ull; }
+    static __device__ __forceinline__ int popc(const T& m) {
+        int n = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) n += __popc(m.w[i]);
+        return n;
+    }
+    static __device__ __forceinline__ int popc_and(const T& a, const T& b) {
+        int n = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) n += __popc(a.w[i] & b.w[i]);
+        return n;
+    }
+    // bits below the highest set bit (0 for an empty mask)
+    static __device__ __forceinline__ T below_last(const T& m) {
+        T r = zero();
+        bool found = false;
+#pragma unroll
+        for (int i = NW - 1; i >= 0; --i) {
+            if (found) r.w[i] = ~0u;
+            else if (m.w[i]) { r.w[i] = ~(~0u << (31 - __clz(m.w[i]))); found = true; }
+        }
         return r;
     }
-    static __device__ __forceinline__ int alt(T ma, T mb) {
-        const unsigned __int128 s = (((unsigned __int128)~mb.y << 64) | ~mb.x) + (((unsigned __int128)ma.y << 64) | ma.x);  // one carry chain
-        return __popcll((unsigned long long)s & mb.x) + __popcll((unsigned long long)(s >> 64) & mb.y);
+    // bits above the lowest set bit (0 for an empty mask)
+    static __device__ __forceinline__ T above_first(const T& m) {
+        T r = zero();
+        bool found = false;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            if (found) r.w[i] = ~0u;
+            else if (m.w[i]) { const uint32_t b = m.w[i] & (0u - m.w[i]); r.w[i] = ~(b | (b - 1u)); found = true; }
+        }
+        return r;
     }
-    static __device__ __forceinline__ bool any(T m) { return (m.x | m.y) != 0; }
+    // popc((~mb + ma) & mb): one carry chain over the NW words
+    static __device__ __forceinline__ int alt(const T& ma, const T& mb) {
+        uint32_t s[NW];
+        // one asm statement per chain: the carry flag is not visible to the compiler
+        if constexpr (NW == 2)
+            asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;"
+                : "=r"(s[0]), "=r"(s[1]) : "r"(~mb.w[0]), "r"(~mb.w[1]), "r"(ma.w[0]), "r"(ma.w[1]));
+        else if constexpr (NW == 3)
+            asm("add.cc.u32 %0, %3, %6;\n\taddc.cc.u32 %1, %4, %7;\n\taddc.u32 %2, %5, %8;"
+                : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]) : "r"(~mb.w[0]), "r"(~mb.w[1]), "r"(~mb.w[2]), "r"(ma.w[0]), "r"(ma.w[1]), "r"(ma.w[2]));
+        else
+            asm("add.cc.u32 %0, %4, %8;\n\taddc.cc.u32 %1, %5, %9;\n\taddc.cc.u32 %2, %6, %10;\n\taddc.u32 %3, %7, %11;"
+                : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3])
+                : "r"(~mb.w[0]), "r"(~mb.w[1]), "r"(~mb.w[2]), "r"(~mb.w[3]), "r"(ma.w[0]), "r"(ma.w[1]), "r"(ma.w[2]), "r"(ma.w[3]));
+        int n = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) n += __popc(s[i] & mb.w[i]);
+        return n;
+    }
 };
-template <int NW2>
-__device__ __forceinline__ typename PosMask<NW2>::T mask_and(typename PosMask<NW2>::T a, typename PosMask<NW2>::T b);
-template <>
-__device__ __forceinline__ unsigned long long mask_and<1>(unsigned long long a, unsigned long long b) { return a & b; }
-template <>
-__device__ __forceinline__ ulonglong2 mask_and<2>(ulonglong2 a, ulonglong2 b) { return make_ulonglong2(a.x & b.x, a.y & b.y); }
 
-// NW2 = 64-bit words per mask (1: traces <= 64 events, 2: <= 128); PPT = activity pairs per thread
-template <int NW2, int PPT>
+// NW = 32-bit words per mask; PPT = activity pairs per thread
+template <int NW, int PPT>
 __global__ void __launch_bounds__(256, 3) declare_pairs_kernel(const __grid_constant__ DeclareParams P) {
-    typedef PosMask<NW2> PM;
+    typedef PosMask<NW> PM;
     typedef typename PM::T mask_t;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int A = P.A, AA = A * A;
@@ -392,24 +418,20 @@ __global__ void __launch_bounds__(256, 3) declare_pairs_kernel(const __grid_cons
         for (int slot = warp; slot < TB; slot += n_warps) {
             const long long t = batch * TB + slot;
             mask_t* M = sM + slot * A;
-            if (lane < A) {
-                mask_t z;
-                memset(&z, 0, sizeof(z));
-                M[lane] = z;
-            }
+            if (lane < A) M[lane] = PM::zero();
             long long lo = 0, hi = 0;
             if (t < P.n_traces && lane == 0) { lo = P.trace_off[t]; hi = P.trace_off[t + 1]; }
             lo = shfl64(lo, 0);
             hi = shfl64(hi, 0);
             const int len = (int)(hi - lo);
             __syncwarp();
-            uint32_t* Mw = reinterpret_cast<uint32_t*>(M);  // word w of activity x at [x * 2 * NW2 + w]
+            uint32_t* Mw = reinterpret_cast<uint32_t*>(M);  // word w of activity x at [x * STORE + w]
             int px = -1;  // activity of the event before this chunk
             for (int base = 0; base < len; base += 32) {
                 const int x = base + lane < len ? __ldg(P.act + lo + base + lane) : -1;
                 const bool valid = x >= 0 && x < A;
                 const unsigned grp = __match_any_sync(0xffffffffu, x);
-                if (valid && lane == __ffs(grp) - 1) Mw[x * 2 * NW2 + (base >> 5)] = grp;
+                if (valid && lane == __ffs(grp) - 1) Mw[x * PM::STORE + (base >> 5)] = grp;
                 // chain pairs (countResponseChain :83-89 = countPrecedenceChain :96-102): adjacent events a b, a != b
                 int prev = __shfl_up_sync(0xffffffffu, x, 1);
                 if (lane == 0) prev = px;
@@ -447,11 +469,11 @@ __global__ void __launch_bounds__(256, 3) declare_pairs_kernel(const __grid_cons
                 const mask_t Ma = sM[slot * A + a], Mb = sM[slot * A + b];
                 const mask_t BLa = sBL[slot * A + a], BLb = sBL[slot * A + b];
                 const mask_t AFa = sAF[slot * A + a], AFb = sAF[slot * A + b];
-                const int r_ab = PM::popc(mask_and<NW2>(Ma, BLb)), r_ba = PM::popc(mask_and<NW2>(Mb, BLa));
+                const int r_ab = PM::popc_and(Ma, BLb), r_ba = PM::popc_and(Mb, BLa);
                 c_r_ab[j] += r_ab;
                 c_r_ba[j] += r_ba;
-                c_p_ab[j] += PM::popc(mask_and<NW2>(Mb, AFa));
-                c_p_ba[j] += PM::popc(mask_and<NW2>(Ma, AFb));
+                c_p_ab[j] += PM::popc_and(Mb, AFa);
+                c_p_ba[j] += PM::popc_and(Ma, AFb);
                 c_ord_ab[j] += r_ab != 0;
                 c_ord_ba[j] += r_ba != 0;
                 c_co[j] += (r_ab | r_ba) != 0;
@@ -460,8 +482,8 @@ __global__ void __launch_bounds__(256, 3) declare_pairs_kernel(const __grid_cons
             }
         }
         __syncthreads();
-        // 32-bit counters: a pair gains at most 64 * NW2 per trace
-        if (++since_flush >= (1 << 24) / (TB * 64 * NW2)) { flush_pairs(); since_flush = 0; }
+        // 32-bit counters: a pair gains at most 32 * NW per trace
+        if (++since_flush >= (1 << 24) / (TB * 32 * NW)) { flush_pairs(); since_flush = 0; }
     }
     flush_pairs();
     if (lane < A) {
@@ -507,11 +529,11 @@ __global__ void max_trace_len_kernel(const int64_t* trace_off, int64_t n_traces,
     if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
-template <int NW2, int PPT>
+template <int NW, int PPT>
 static int launch_pairs(const Ctx* ctx, cudaStream_t stream, const DeclareParams& P, int threads) {
     const int A = P.A;
-    const size_t smem = (size_t)3 * TB * A * sizeof(typename PosMask<NW2>::T) + sizeof(uint32_t) * ((size_t)A * A + 2 * A + (size_t)A * HS);
-    auto kern = declare_pairs_kernel<NW2, PPT>;
+    const size_t smem = (size_t)3 * TB * A * sizeof(typename PosMask<NW>::T) + sizeof(uint32_t) * ((size_t)A * A + 2 * A + (size_t)A * HS);
+    auto kern = declare_pairs_kernel<NW, PPT>;
     SIESTA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
@@ -613,8 +635,9 @@ extern "C" int siesta_declare_counts_device(siesta_log* log, int32_t k_cap, int6
         const int n_pairs = A * (A - 1) / 2;
         const int ppt = n_pairs > 256 ? 2 : 1;
         const int threads = std::max(32, std::min(256, ((ppt == 1 ? n_pairs : (n_pairs + 1) / 2) + 31) / 32 * 32));
-        if (L->true_max_len <= 64) rc = ppt == 1 ? launch_pairs<1, 1>(L->ctx, stream, P, threads) : launch_pairs<1, 2>(L->ctx, stream, P, threads);
-        else rc = ppt == 1 ? launch_pairs<2, 1>(L->ctx, stream, P, threads) : launch_pairs<2, 2>(L->ctx, stream, P, threads);
+        if (L->true_max_len <= 64) rc = ppt == 1 ? launch_pairs<2, 1>(L->ctx, stream, P, threads) : launch_pairs<2, 2>(L->ctx, stream, P, threads);
+        else if (L->true_max_len <= 96) rc = ppt == 1 ? launch_pairs<3, 1>(L->ctx, stream, P, threads) : launch_pairs<3, 2>(L->ctx, stream, P, threads);
+        else rc = ppt == 1 ? launch_pairs<4, 1>(L->ctx, stream, P, threads) : launch_pairs<4, 2>(L->ctx, stream, P, threads);
         if (rc) return rc;
     } else {
         const int nb = (A + 31) / 32;
