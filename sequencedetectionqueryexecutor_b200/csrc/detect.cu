@@ -57,10 +57,9 @@ struct DetectParams {
     uint32_t flags;
     int32_t needs_ts;
     // dense per-candidate outputs
-    uint32_t* d_nocc;         // selected occurrences (0 = no match)
-    uint32_t* d_nev;          // events over the selected occurrences
+    uint32_t* d_cnt;          // selected occurrences (0 = no match) | events over the selected occurrences << 16
     int64_t* d_stage;         // staging base (events) of the trace
-    int64_t* d_stage_occ;     // staging base (occurrences) of the trace
+    int64_t* d_stage_occ;     // staging base (occurrences) of the trace; only with returnAll (else = the candidate's index)
     // staging
     int32_t* s_occ_nev;       // [cap_occ] events per staged occurrence
     int32_t* s_ev_pos;        // [cap_ev]
@@ -421,13 +420,11 @@ __global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4)
 
         if (ci >= 0) {
             if (status == ST_MATCH) {
-                P.d_nocc[ci] = my_occ;
-                P.d_nev[ci] = my_ev;
+                P.d_cnt[ci] = my_occ | (my_ev << 16);
                 P.d_stage[ci] = ev_at;
-                P.d_stage_occ[ci] = occ_at;
+                if (return_all) P.d_stage_occ[ci] = occ_at;
             } else {
-                P.d_nocc[ci] = 0;
-                P.d_nev[ci] = 0;
+                P.d_cnt[ci] = 0;
                 if (status == ST_ERR) P.err_list[atomicAdd(P.counters + 3, 1ull)] = t;
                 else if (status == ST_OVF) {
                     const unsigned long long at = atomicAdd(P.counters + P.ovf_slot, 1ull);
@@ -442,7 +439,6 @@ __global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4)
                 // k-th set bit of that lane's occurrence mask names the event; activity and timestamp are re-read
                 // from the log by 32 lanes at once (one memory latency per 32 events instead of one per event).
                 const mask_t my_mask = status == ST_MATCH ? sel_local[0] : (mask_t)0;
-                if (status == ST_MATCH) P.s_occ_nev[occ_at] = (int32_t)my_ev;
                 for (unsigned f0 = 0; f0 < tot1; f0 += 32) {
                     const unsigned f = f0 + lane;
                     int lo = 0, hi = 31;
@@ -641,11 +637,9 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
         const long long ev_at = base1 + (long long)(i1 - my_ev);
         const bool stage_ok = true;
         if (ci >= 0) {
-            P.d_nocc[ci] = my_occ;
-            P.d_nev[ci] = my_ev;
+            P.d_cnt[ci] = my_occ | (my_ev << 16);
             if (status == ST_MATCH) {
                 P.d_stage[ci] = ev_at;
-                P.d_stage_occ[ci] = occ_at;
             } else if (status == ST_OVF) {
                 const unsigned long long at = atomicAdd(P.counters + P.ovf_slot, 1ull);
                 P.ovf_list[at] = ci;
@@ -655,7 +649,6 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
             // first event of the filtered list (Utils.java:51-53): base of the relative seconds of the EventTs route
             long long t0ms = 0;
             if (status == ST_MATCH) {
-                P.s_occ_nev[occ_at] = (int32_t)my_ev;
                 if (all_cols && !evt_pos) t0ms = __ldg(reinterpret_cast<const long long*>(P.ts_ms) + o0 + (MO::lo(R) - lead));
             }
             for (unsigned f0 = 0; f0 < tot1; f0 += 32) {
@@ -703,20 +696,21 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
     }
 }
 
-// Final placement.  The dense per-candidate counts (d_nocc, d_nev) are scanned in two levels
-// (per-block sums -> one-block scan of the sums -> in-block scan inside the gather), and the
+// Final placement.  The dense per-candidate counts (d_nocc, d_nev) are scanned in three levels
+// (per-block sums -> chunks of 1024 block sums -> chunk sums, + the in-block scan inside the gather), and the
 // gather copies each matching trace's staged occurrences to its final, trace-ordered position.
 constexpr int GT = 256;
 
 struct GatherParams {
     const int64_t* cand;
     int64_t n;
-    const uint32_t* d_nocc;
-    const uint32_t* d_nev;
+    const uint32_t* d_cnt;
     const int64_t* d_stage;
-    const int64_t* d_stage_occ;
-    unsigned long long* blk;  // [3][n_blk] block sums -> exclusive bases
+    const int64_t* d_stage_occ;  // nullptr without returnAll: the occurrence is staged at the candidate's index
+    unsigned long long* blk;  // [3][n_blk] block sums -> exclusive bases inside their chunk of 1024 blocks
     int64_t n_blk;
+    unsigned long long* top;  // [3][n_chunks] chunk sums -> exclusive bases
+    int64_t n_chunks;
     const int32_t* s_occ_nev;
     const int32_t* s_ev_pos;
     const int32_t* s_ev_rank;
@@ -733,8 +727,9 @@ struct GatherParams {
     int all_cols;
 };
 
+template <int NTHR = GT>
 __device__ __forceinline__ void block_scan3(unsigned long long v[3], unsigned long long excl[3], unsigned long long tot[3]) {
-    __shared__ unsigned long long ws[3][GT / 32];
+    __shared__ unsigned long long ws[3][NTHR / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long inc[3] = {v[0], v[1], v[2]};
 #pragma unroll
@@ -750,7 +745,7 @@ __device__ __forceinline__ void block_scan3(unsigned long long v[3], unsigned lo
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
         unsigned long long before = 0, all = 0;
-        for (int k = 0; k < GT / 32; ++k) {
+        for (int k = 0; k < NTHR / 32; ++k) {
             if (k < warp) before += ws[q][k];
             all += ws[q][k];
         }
@@ -764,49 +759,48 @@ __global__ void __launch_bounds__(GT) count_blocks_kernel(const __grid_constant_
     const int64_t i = (int64_t)blockIdx.x * GT + threadIdx.x;
     unsigned long long v[3] = {0, 0, 0}, ex[3], tot[3];
     if (i < G.n) {
-        const uint32_t c = G.d_nocc[i];
+        const uint32_t w = G.d_cnt[i], c = w & 0xFFFFu;
         v[0] = c ? 1 : 0;
         v[1] = c;
-        v[2] = c ? G.d_nev[i] : 0;
+        v[2] = w >> 16;
     }
     block_scan3(v, ex, tot);
     if (threadIdx.x == 0)
         for (int q = 0; q < 3; ++q) G.blk[q * G.n_blk + blockIdx.x] = tot[q];
 }
 
-// one block: exclusive scan of the three rows of block sums, in place.  Each thread owns a contiguous segment of all
-// three rows (serial sum), the 1024 partial sums are scanned with shuffles, then the segment is rewritten.
-__global__ void __launch_bounds__(1024) scan_blocks_kernel(unsigned long long* blk, int64_t n_blk) {
-    __shared__ unsigned long long ws[3][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t per = (n_blk + 1023) / 1024;
-    const int64_t lo = (int64_t)threadIdx.x * per, hi = lo + per < n_blk ? lo + per : n_blk;
-    unsigned long long part[3] = {0, 0, 0};
-    for (int64_t i = lo; i < hi; ++i)
+// Exclusive scan of the three rows of block sums in two levels, all loads coalesced: every block of scan_chunks_kernel
+// scans one chunk of 1024 sums in place and reports the chunk totals; scan_top_kernel (one block) scans the chunk
+// totals; the gather adds blk[block] + top[block / 1024].
+constexpr int SC = 1024;
+__global__ void __launch_bounds__(SC) scan_chunks_kernel(unsigned long long* blk, int64_t n_blk, unsigned long long* top, int64_t n_chunks) {
+    const int64_t i = (int64_t)blockIdx.x * SC + threadIdx.x;
+    unsigned long long v[3] = {0, 0, 0}, ex[3], tot[3];
+    if (i < n_blk)
 #pragma unroll
-        for (int q = 0; q < 3; ++q) part[q] += blk[q * n_blk + i];
-    unsigned long long inc[3] = {part[0], part[1], part[2]};
+        for (int q = 0; q < 3; ++q) v[q] = blk[q * n_blk + i];
+    block_scan3<SC>(v, ex, tot);
+    if (i < n_blk)
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1)
+        for (int q = 0; q < 3; ++q) blk[q * n_blk + i] = ex[q];
+    if (threadIdx.x == 0)
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const unsigned long long y = __shfl_up_sync(0xffffffffu, inc[q], d);
-            if (lane >= d) inc[q] += y;
-        }
-    if (lane == 31)
+        for (int q = 0; q < 3; ++q) top[q * n_chunks + blockIdx.x] = tot[q];
+}
+__global__ void __launch_bounds__(SC) scan_top_kernel(unsigned long long* top, int64_t n_chunks) {
+    unsigned long long carry[3] = {0, 0, 0};
+    for (int64_t base = 0; base < n_chunks; base += SC) {
+        const int64_t i = base + threadIdx.x;
+        unsigned long long v[3] = {0, 0, 0}, ex[3], tot[3];
+        if (i < n_chunks)
 #pragma unroll
-        for (int q = 0; q < 3; ++q) ws[q][warp] = inc[q];
-    __syncthreads();
+            for (int q = 0; q < 3; ++q) v[q] = top[q * n_chunks + i];
+        block_scan3<SC>(v, ex, tot);
+        if (i < n_chunks)
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        unsigned long long before = 0;
-        for (int k = 0; k < warp; ++k) before += ws[q][k];
-        unsigned long long run = before + inc[q] - part[q];  // exclusive base of this thread's segment
-        for (int64_t i = lo; i < hi; ++i) {
-            const unsigned long long v = blk[q * n_blk + i];
-            blk[q * n_blk + i] = run;
-            run += v;
-        }
+            for (int q = 0; q < 3; ++q) top[q * n_chunks + i] = carry[q] + ex[q];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) carry[q] += tot[q];
     }
 }
 
@@ -815,26 +809,39 @@ __global__ void __launch_bounds__(GT) gather_kernel(const __grid_constant__ Gath
     const int lane = threadIdx.x & 31;
     unsigned long long v[3] = {0, 0, 0}, ex[3], tot[3];
     uint32_t nocc = 0;
+    long long se = 0;
+    int64_t cand_i = i;
+    // everything the placement needs is requested up front (one memory latency instead of four in a row): the block's
+    // bases, the staging place (read speculatively: unwritten and unused for a trace without a match), the trace id
+    const int64_t chunk = blockIdx.x / SC;
+    unsigned long long bb[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) bb[q] = G.top[q * G.n_chunks + chunk] + G.blk[q * G.n_blk + blockIdx.x];
     if (i < G.n) {
-        nocc = G.d_nocc[i];
+        const uint32_t w = G.d_cnt[i];
+        se = G.d_stage[i];
+        if (G.cand) cand_i = G.cand[i];
+        nocc = w & 0xFFFFu;
         v[0] = nocc ? 1 : 0;
         v[1] = nocc;
-        v[2] = nocc ? G.d_nev[i] : 0;
+        v[2] = w >> 16;
     }
     block_scan3(v, ex, tot);
-    const int64_t tp = (int64_t)(G.blk[0 * G.n_blk + blockIdx.x] + ex[0]);
-    const int64_t op = (int64_t)(G.blk[1 * G.n_blk + blockIdx.x] + ex[1]);
-    const int64_t ep = (int64_t)(G.blk[2 * G.n_blk + blockIdx.x] + ex[2]);
-    long long se = 0;
+    const int64_t tp = (int64_t)(bb[0] + ex[0]);
+    const int64_t op = (int64_t)(bb[1] + ex[1]);
+    const int64_t ep = (int64_t)(bb[2] + ex[2]);
     if (nocc) {
-        G.trace_idx[tp] = (G.cand ? G.cand[i] : i) + G.base.trace;
+        G.trace_idx[tp] = cand_i + G.base.trace;
         G.occ_off[tp] = op + G.base.occ;
-        se = G.d_stage[i];
-        const int64_t so = G.d_stage_occ[i];
-        int64_t e = ep;
-        for (uint32_t o = 0; o < nocc; ++o) {
-            G.ev_off[op + o] = e + G.base.ev;
-            e += G.s_occ_nev[so + o];
+        if (G.d_stage_occ) {
+            const int64_t so = G.d_stage_occ[i];
+            int64_t e = ep;
+            for (uint32_t o = 0; o < nocc; ++o) {
+                G.ev_off[op + o] = e + G.base.ev;
+                e += G.s_occ_nev[so + o];
+            }
+        } else {
+            G.ev_off[op] = ep + G.base.ev;  // one occurrence per trace
         }
     }
     // The events of a warp's 32 candidates are contiguous in the output (ep ascends with the lane) and, per candidate,
@@ -1023,9 +1030,9 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     const size_t n_reg = use_nkp ? 2 : 1;  // staging regions: [0, cap) by atomics (staged kernels), [cap, 2 cap) fixed tile slots (K1-P)
     const size_t n_blk = (nn + GT - 1) / GT;
     const size_t o_ovf2 = use_nkp ? carve(nn * 8) : 0;
-    const size_t o_lut = carve(lut.size() * sizeof(uint16_t)), o_nocc = carve(nn * 4), o_nev = carve(nn * 4), o_stage = carve(nn * 8),
-                 o_stage_occ = carve(nn * 8), o_counters = carve(32 * 8), o_err = carve(nn * 8), o_ovf = carve(nn * 8),
-                 o_blk = carve(n_blk * 3 * 8), o_occ_nev = carve((size_t)cap_occ * 4), o_pos = carve((size_t)cap_ev * 4 * n_reg);
+    const size_t o_lut = carve(lut.size() * sizeof(uint16_t)), o_nocc = carve(nn * 4), o_stage = carve(nn * 8),
+                 o_stage_occ = carve(return_all ? nn * 8 : 0), o_counters = carve(32 * 8), o_err = carve(nn * 8), o_ovf = carve(nn * 8),
+                 o_blk = carve(n_blk * 3 * 8), o_top = carve(((n_blk + 1023) / 1024) * 3 * 8), o_occ_nev = carve(return_all ? (size_t)cap_occ * 4 : 0), o_pos = carve((size_t)cap_ev * 4 * n_reg);
     size_t o_rank = 0, o_act = 0, o_ts = 0;
     if (all_cols) {
         o_rank = carve((size_t)cap_ev * 4 * n_reg);
@@ -1034,7 +1041,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     }
     if ((rc = work.alloc(w_off))) return rc;
     char* wb = work.as<char>();
-    const View b_lut{wb + o_lut}, b_nocc{wb + o_nocc}, b_nev{wb + o_nev}, b_stage{wb + o_stage}, b_stage_occ{wb + o_stage_occ},
+    const View b_lut{wb + o_lut}, b_nocc{wb + o_nocc}, b_stage{wb + o_stage}, b_stage_occ{wb + o_stage_occ},
         b_counters{wb + o_counters}, b_err{wb + o_err}, b_ovf{wb + o_ovf}, b_blk{wb + o_blk}, s_occ_nev{wb + o_occ_nev},
         s_ev_pos{wb + o_pos}, s_ev_rank{all_cols ? wb + o_rank : nullptr}, s_ev_act{all_cols ? wb + o_act : nullptr},
         s_ev_ts{all_cols ? wb + o_ts : nullptr};
@@ -1084,8 +1091,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     P.vec_ok = (reinterpret_cast<uintptr_t>(log->d_act) & 15u) == 0 ? 1 : 0;
     P.flags = flags;
     P.needs_ts = needs_ts;
-    P.d_nocc = b_nocc.as<uint32_t>();
-    P.d_nev = b_nev.as<uint32_t>();
+    P.d_cnt = b_nocc.as<uint32_t>();
     P.d_stage = b_stage.as<int64_t>();
     P.d_stage_occ = b_stage_occ.as<int64_t>();
     P.s_occ_nev = s_occ_nev.as<int32_t>();
@@ -1188,12 +1194,13 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
         G.cand = d_cand;
         G.base = base;
         G.n = n;
-        G.d_nocc = P.d_nocc;
-        G.d_nev = P.d_nev;
+        G.d_cnt = P.d_cnt;
         G.d_stage = P.d_stage;
-        G.d_stage_occ = P.d_stage_occ;
+        G.d_stage_occ = return_all ? P.d_stage_occ : nullptr;
         G.n_blk = (int64_t)n_blk;
         G.blk = b_blk.as<unsigned long long>();
+        G.n_chunks = (int64_t)((n_blk + 1023) / 1024);
+        G.top = reinterpret_cast<unsigned long long*>(wb + o_top);
         G.s_occ_nev = P.s_occ_nev;
         G.s_ev_pos = P.s_ev_pos;
         G.s_ev_rank = P.s_ev_rank;
@@ -1209,7 +1216,9 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
         G.all_cols = all_cols ? 1 : 0;
         count_blocks_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G);
         SIESTA_LAUNCHED();
-        scan_blocks_kernel<<<1, 1024, 0, stream>>>(G.blk, G.n_blk);
+        scan_chunks_kernel<<<(unsigned)G.n_chunks, SC, 0, stream>>>(G.blk, G.n_blk, G.top, G.n_chunks);
+        SIESTA_LAUNCHED();
+        scan_top_kernel<<<1, SC, 0, stream>>>(G.top, G.n_chunks);
         SIESTA_LAUNCHED();
         gather_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G);
         SIESTA_LAUNCHED();
