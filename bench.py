@@ -37,13 +37,13 @@ WORKLOADS = {
     # configs[0] shape: A_ B_ on 10k traces x ~40 events (no constraint: 4 B/event).
     "detection_ab_10kx40": dict(n_traces=10_000, min_len=30, max_len=50, n_act=20, max_gap_s=600, seed=0x51E57A01,
                                 bytes_per_event=4, pattern="A_ B_ (EventTs route, returnAll=false)",
-                                kernel="detect_kernel<W=1, FAST_NK> (K1: filter + greedy-walk closed form + staged output)",
+                                kernel="detect_nkp_kernel<NPL=2> (K1-P: raw-slot class planes + greedy-walk closed form, no shared memory)",
                                 states=[dict(kind=abi.STATE_NORMAL, types=[0]), dict(kind=abi.STATE_NORMAL, types=[1])]),
     # configs[4] shape: a, (b|c), !d, e, f with gap within 10 (0,1) and gap atleast 2 (3,4); 50 events per trace.
     # 4M traces per GPU by default (the 100M-trace log of configs[4] is 12.5M traces per GPU on 8 GPUs; --traces sets it).
     "detection_gap6_4Mx50": dict(n_traces=4_000_000, min_len=50, max_len=50, n_act=20, max_gap_s=600, seed=0x51E57A05,
                                  bytes_per_event=4, pattern="a (b|c) !d e f; gap within 10 (0,1), gap atleast 2 (3,4) (returnAll=false)",
-                                 kernel="detect_kernel<W=1, FAST_NK> (K1: filter + greedy-walk closed form + staged output)",
+                                 kernel="detect_nkp_kernel<NPL=3> (K1-P: raw-slot class planes + greedy-walk closed form, no shared memory)",
                                  states=[dict(kind=abi.STATE_NORMAL, types=[0]),
                                          dict(kind=abi.STATE_OR, types=[1, 2], preds=[(abi.ATTR_POSITION, abi.OP_LE, 0, 10)]),
                                          dict(kind=abi.STATE_NEGATIVE, types=[3]), dict(kind=abi.STATE_NORMAL, types=[4]),

@@ -204,6 +204,13 @@ class PairIndex:
         check(lib().siesta_intersect(self._h, _ptr(ids), len(ids), _ptr(out), len(out), C.byref(n)))
         return out[:n.value].copy()
 
+    def intersect_device_ms(self, pair_ids=None):
+        """siesta_intersect_device with the result left (and freed) in HBM -> (n_common, kernel_ms): the device-side cost."""
+        ids = np.arange(len(self.pairs), dtype=np.int32) if pair_ids is None else np.asarray(pair_ids, dtype=np.int32)
+        d_out, n, ms = C.c_void_p(), C.c_int64(0), C.c_double(0.0)
+        check(lib().siesta_intersect_device(self._h, _ptr(ids), len(ids), C.byref(d_out), C.byref(n), C.byref(ms)))
+        lib().siesta_device_free(self.log._h, d_out)
+        return n.value, ms.value
 
     def candidates(self, expansions):
         """siesta_candidates: union over the expansions (lists of pair ids) of the intersection of their posting lists."""

@@ -9,7 +9,9 @@
 // Kernels
 //   pair_flags_kernel   one warp per trace: first / last position and count of the (<= 32) activities the requested
 //                       pairs mention, then one lane per pair writes flag[pair][trace]
-//   probe_flags_kernel  one thread per element of the shortest list: binary search in every other list
+//   list_hits_kernel    one thread per element of every list: hit[trace] += 1 (byte counters, word atomics); a trace is in
+//                       the intersection of n duplicate-free lists iff its counter reaches n: every list is read
+//                       exactly once, coalesced (8 B x sum |list_i|), no search
 //   compaction          block counts -> one-block scan -> ordered write (ascending output, deterministic)
 #include <algorithm>
 #include <cstring>
@@ -32,10 +34,13 @@ struct Index {
 
 // ------------------------------------------------------------------------------------------------ compaction
 // flags: u8 [n_rows][n]; out rows start at row_off[row]; counts per row returned in row_cnt.
-__global__ void __launch_bounds__(IT) flag_count_kernel(const uint8_t* flags, int64_t n, int64_t n_blk, unsigned long long* blk) {
+// a flag counts if it is non-zero (want == 0) or equal to `want`
+__device__ __forceinline__ bool flag_set(uint8_t f, int want) { return want ? f == want : f != 0; }
+
+__global__ void __launch_bounds__(IT) flag_count_kernel(const uint8_t* flags, int64_t n, int64_t n_blk, unsigned long long* blk, int want) {
     const int row = blockIdx.y;
     const int64_t i = (int64_t)blockIdx.x * IT + threadIdx.x;
-    const unsigned f = (i < n && flags[(int64_t)row * n + i]) ? 1u : 0u;
+    const unsigned f = (i < n && flag_set(flags[(int64_t)row * n + i], want)) ? 1u : 0u;
     const unsigned ball = __ballot_sync(0xffffffffu, f);
     __shared__ unsigned s[IT / 32];
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = __popc(ball);
@@ -82,10 +87,10 @@ __global__ void __launch_bounds__(1024) row_scan_kernel(unsigned long long* blk,
 
 // values[i] (or i itself when values == nullptr) of the flagged elements, in order, to out + row_off[row]
 __global__ void __launch_bounds__(IT) flag_write_kernel(const uint8_t* flags, const int64_t* values, int64_t n, int64_t n_blk,
-                                                       const unsigned long long* blk, const int64_t* row_off, int64_t* out) {
+                                                       const unsigned long long* blk, const int64_t* row_off, int64_t* out, int want) {
     const int row = blockIdx.y;
     const int64_t i = (int64_t)blockIdx.x * IT + threadIdx.x;
-    const unsigned f = (i < n && flags[(int64_t)row * n + i]) ? 1u : 0u;
+    const unsigned f = (i < n && flag_set(flags[(int64_t)row * n + i], want)) ? 1u : 0u;
     const unsigned ball = __ballot_sync(0xffffffffu, f);
     __shared__ unsigned s[IT / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -144,47 +149,61 @@ __global__ void __launch_bounds__(IT) pair_flags_kernel(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------ intersection
-struct ProbeParams {
-    const int64_t* probe;
-    int64_t n_probe;
-    int32_t n_others;
+struct HitParams {
+    int32_t n_lists;
     const int64_t* lists[MAX_BUILD_PAIRS];
-    int64_t lens[MAX_BUILD_PAIRS];
-    uint8_t* flags;
-    uint8_t* mark;          // if set: [n_traces] flags indexed by trace, written instead of `flags`
+    int64_t start[MAX_BUILD_PAIRS + 1];  // list k owns the flat element range [start[k], start[k + 1])
+    int64_t n_traces;
+    uint32_t* hit;  // [ceil(n_traces / 4)] words = one byte counter per trace
 };
 
-__global__ void __launch_bounds__(IT) probe_flags_kernel(const __grid_constant__ ProbeParams P) {
+// One thread per element of every list.  Lists are duplicate-free and n_lists <= 32, so a byte never overflows into
+// its neighbour; ascending ids make the atomics of a warp fall into a few adjacent words.
+__global__ void __launch_bounds__(IT) list_hits_kernel(const __grid_constant__ HitParams P) {
     const int64_t i = (int64_t)blockIdx.x * IT + threadIdx.x;
-    if (i >= P.n_probe) return;
-    const int64_t v = P.probe[i];
-    bool all = true;
-    for (int k = 0; k < P.n_others && all; ++k) {
-        const int64_t* L = P.lists[k];
-        int64_t lo = 0, hi = P.lens[k];
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (__ldg(L + mid) < v) lo = mid + 1;
-            else hi = mid;
-        }
-        all = lo < P.lens[k] && __ldg(L + lo) == v;
+    if (i >= P.start[P.n_lists]) return;
+    int k = 0;
+    while (i >= P.start[k + 1]) ++k;
+    const int64_t t = __ldg(P.lists[k] + (i - P.start[k]));
+    if (t >= 0 && t < P.n_traces) atomicAdd(P.hit + (t >> 2), 1u << (8 * (int)(t & 3)));
+}
+
+// union over the OR-expansions: mark the traces whose counter reached `want`, and clear the counters for the next one
+__global__ void __launch_bounds__(IT) mark_hits_kernel(uint8_t* hit, uint8_t* mark, int64_t n, int want) {
+    const int64_t i = (int64_t)blockIdx.x * IT + threadIdx.x;
+    if (i >= n) return;
+    if (hit[i] == want) mark[i] = 1;
+    hit[i] = 0;
+}
+
+// hit[t] = number of the given lists that hold trace t (hit must be zero on entry)
+static int count_list_hits(Index* ix, const int32_t* ids, int n, uint32_t* d_hit, cudaStream_t stream) {
+    HitParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.n_lists = n;
+    for (int k = 0; k < n; ++k) {
+        P.lists[k] = ix->d_lists + ix->off[ids[k]];
+        P.start[k + 1] = P.start[k] + (ix->off[ids[k] + 1] - ix->off[ids[k]]);
     }
-    if (P.mark) {
-        if (all) P.mark[v] = 1;  // union over expansions: flag the trace itself
-    } else {
-        P.flags[i] = all ? 1 : 0;
+    P.n_traces = ix->log->n_traces;
+    P.hit = d_hit;
+    if (P.start[n] > 0) {
+        list_hits_kernel<<<(unsigned)((P.start[n] + IT - 1) / IT), IT, 0, stream>>>(P);
+        SIESTA_LAUNCHED();
+        SIESTA_CUDA_OK(cudaGetLastError());
     }
+    return SIESTA_OK;
 }
 
 static int compact_rows(cudaStream_t stream, const uint8_t* d_flags, const int64_t* d_values, int64_t n, int n_rows,
-                        std::vector<int64_t>& counts, int64_t** d_out_all, std::vector<int64_t>& row_off) {
+                        std::vector<int64_t>& counts, int64_t** d_out_all, std::vector<int64_t>& row_off, int want = 0) {
     const int64_t n_blk = std::max<int64_t>((n + IT - 1) / IT, 1);
     unsigned long long *d_blk = nullptr, *d_cnt = nullptr;
     int64_t* d_off = nullptr;
     SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_blk, sizeof(unsigned long long) * (size_t)n_blk * n_rows, stream));
     SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_cnt, sizeof(unsigned long long) * (size_t)n_rows, stream));
     dim3 grid((unsigned)n_blk, (unsigned)n_rows);
-    flag_count_kernel<<<grid, IT, 0, stream>>>(d_flags, n, n_blk, d_blk);
+    flag_count_kernel<<<grid, IT, 0, stream>>>(d_flags, n, n_blk, d_blk, want);
     SIESTA_LAUNCHED();
     row_scan_kernel<<<n_rows, 1024, 0, stream>>>(d_blk, n_blk, d_cnt);
     SIESTA_LAUNCHED();
@@ -200,7 +219,7 @@ static int compact_rows(cudaStream_t stream, const uint8_t* d_flags, const int64
     SIESTA_CUDA_OK(cudaMallocAsync((void**)d_out_all, sizeof(int64_t) * (size_t)std::max<int64_t>(row_off[n_rows], 1), stream));
     SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_off, sizeof(int64_t) * (size_t)(n_rows + 1), stream));
     SIESTA_CUDA_OK(cudaMemcpyAsync(d_off, row_off.data(), sizeof(int64_t) * (size_t)(n_rows + 1), cudaMemcpyHostToDevice, stream));
-    flag_write_kernel<<<grid, IT, 0, stream>>>(d_flags, d_values, n, n_blk, d_blk, d_off, *d_out_all);
+    flag_write_kernel<<<grid, IT, 0, stream>>>(d_flags, d_values, n, n_blk, d_blk, d_off, *d_out_all, want);
     SIESTA_LAUNCHED();
     SIESTA_CUDA_OK(cudaGetLastError());
     SIESTA_CUDA_OK(cudaStreamSynchronize(stream));  // row_off (host vector) was the source of an async copy
@@ -361,41 +380,30 @@ extern "C" int siesta_intersect_device(siesta_index* index, const int32_t* pair_
         }
     SIESTA_CUDA_OK(cudaSetDevice(ix->log->ctx->device));
     cudaStream_t stream = ix->log->ctx->stream;
-    // probe with the shortest list
-    int best = 0;
-    for (int k = 1; k < n; ++k)
-        if (ix->off[pair_ids[k] + 1] - ix->off[pair_ids[k]] < ix->off[pair_ids[best] + 1] - ix->off[pair_ids[best]]) best = k;
-    ProbeParams P;
-    std::memset(&P, 0, sizeof(P));
-    P.probe = ix->d_lists + ix->off[pair_ids[best]];
-    P.n_probe = ix->off[pair_ids[best] + 1] - ix->off[pair_ids[best]];
-    for (int k = 0; k < n; ++k) {
-        if (k == best) continue;
-        P.lists[P.n_others] = ix->d_lists + ix->off[pair_ids[k]];
-        P.lens[P.n_others] = ix->off[pair_ids[k] + 1] - ix->off[pair_ids[k]];
-        ++P.n_others;
-    }
+    // a list named twice would be counted twice: count each distinct list once
+    std::vector<int32_t> ids(pair_ids, pair_ids + n);
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    const int nd = (int)ids.size();
+    const int64_t T = ix->log->n_traces;
+    const size_t hit_bytes = (size_t)((std::max<int64_t>(T, 1) + 3) / 4) * 4;
     cudaEvent_t e0, e1;
     SIESTA_CUDA_OK(cudaEventCreate(&e0));
     SIESTA_CUDA_OK(cudaEventCreate(&e1));
     SIESTA_CUDA_OK(cudaEventRecord(e0, stream));
-    uint8_t* d_flags = nullptr;
-    SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_flags, (size_t)std::max<int64_t>(P.n_probe, 1), stream));
-    P.flags = d_flags;
-    if (P.n_probe > 0) {
-        probe_flags_kernel<<<(unsigned)((P.n_probe + IT - 1) / IT), IT, 0, stream>>>(P);
-        SIESTA_LAUNCHED();
-        SIESTA_CUDA_OK(cudaGetLastError());
-    }
+    uint32_t* d_hit = nullptr;
+    SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_hit, hit_bytes, stream));
+    SIESTA_CUDA_OK(cudaMemsetAsync(d_hit, 0, hit_bytes, stream));
+    int rc = count_list_hits(ix, ids.data(), nd, d_hit, stream);
     std::vector<int64_t> counts, row_off;
-    int rc = compact_rows(stream, d_flags, P.probe, P.n_probe, 1, counts, d_out, row_off);
+    if (rc == SIESTA_OK) rc = compact_rows(stream, reinterpret_cast<const uint8_t*>(d_hit), nullptr, T, 1, counts, d_out, row_off, nd);
     SIESTA_CUDA_OK(cudaEventRecord(e1, stream));
     SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFreeAsync(d_flags, stream);
+    cudaFreeAsync(d_hit, stream);
     if (rc) return rc;
     *out_n = counts[0];
     if (kernel_ms) *kernel_ms = ms;
@@ -430,27 +438,20 @@ extern "C" int siesta_candidates_device(siesta_index* index, const int32_t* exp_
     SIESTA_CUDA_OK(cudaEventCreate(&e1));
     SIESTA_CUDA_OK(cudaEventRecord(e0, stream));
     uint8_t* d_mark = nullptr;
+    uint32_t* d_hit = nullptr;
+    const size_t hit_bytes = (size_t)((std::max<int64_t>(T, 1) + 3) / 4) * 4;
     SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_mark, (size_t)std::max<int64_t>(T, 1), stream));
     SIESTA_CUDA_OK(cudaMemsetAsync(d_mark, 0, (size_t)std::max<int64_t>(T, 1), stream));
+    SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_hit, hit_bytes, stream));
+    SIESTA_CUDA_OK(cudaMemsetAsync(d_hit, 0, hit_bytes, stream));
     for (int x = 0; x < n_exp; ++x) {
-        const int32_t* ids = pair_ids + exp_off[x];
-        const int n = exp_off[x + 1] - exp_off[x];
-        int best = 0;  // probe with the shortest list
-        for (int k = 1; k < n; ++k)
-            if (ix->off[ids[k] + 1] - ix->off[ids[k]] < ix->off[ids[best] + 1] - ix->off[ids[best]]) best = k;
-        ProbeParams P;
-        std::memset(&P, 0, sizeof(P));
-        P.probe = ix->d_lists + ix->off[ids[best]];
-        P.n_probe = ix->off[ids[best] + 1] - ix->off[ids[best]];
-        for (int k = 0; k < n; ++k) {
-            if (k == best) continue;
-            P.lists[P.n_others] = ix->d_lists + ix->off[ids[k]];
-            P.lens[P.n_others] = ix->off[ids[k] + 1] - ix->off[ids[k]];
-            ++P.n_others;
-        }
-        P.mark = d_mark;
-        if (P.n_probe > 0) {
-            probe_flags_kernel<<<(unsigned)((P.n_probe + IT - 1) / IT), IT, 0, stream>>>(P);
+        std::vector<int32_t> ids(pair_ids + exp_off[x], pair_ids + exp_off[x + 1]);
+        std::sort(ids.begin(), ids.end());
+        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+        int rcx = count_list_hits(ix, ids.data(), (int)ids.size(), d_hit, stream);
+        if (rcx) return rcx;
+        if (T > 0) {
+            mark_hits_kernel<<<(unsigned)((T + IT - 1) / IT), IT, 0, stream>>>(reinterpret_cast<uint8_t*>(d_hit), d_mark, T, (int)ids.size());
             SIESTA_LAUNCHED();
             SIESTA_CUDA_OK(cudaGetLastError());
         }
@@ -464,6 +465,7 @@ extern "C" int siesta_candidates_device(siesta_index* index, const int32_t* exp_
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFreeAsync(d_mark, stream);
+    cudaFreeAsync(d_hit, stream);
     if (rc) return rc;
     *out_n = counts[0];
     if (kernel_ms) *kernel_ms = ms;
