@@ -313,6 +313,25 @@ def test_explore_accurate_matches_per_candidate_detection(ctx):
             assert comp[c] == want.n_occurrences, c
             d = sum(int(want.ev_ts_ms[want.ev_off[o + 1] - 1] - want.ev_ts_ms[want.ev_off[o]]) for o in range(want.n_occurrences))
             assert dur[c] == d, c
+        # shapes around the shared pass: traces beyond 64 events and more than 16 starts (overflow list -> general kernels),
+        # the EventPos route, one- and three-event patterns, a candidate that repeats a pattern activity, unsorted timestamps
+        for n_a, lens, pat, fl, shuffle in [(6, (40, 80), [0, 1], 0, False), (6, (0, 64), [2], abi.F_EVT_POS, False),
+                                            (9, (20, 70), [0, 1, 2], 0, True), (4, (60, 64), [1, 1], abi.F_EVT_POS, False),
+                                            (40, (50, 50), [0, 1, 2], 0, False)]:
+            o2, a2, t2 = gen.make_log(3000, lens[0], lens[1], n_a, seed=83 + n_a, jitter_ms=True, max_gap_s=5)
+            if shuffle:
+                t2 = t2.copy()
+                np.random.default_rng(5).shuffle(t2)
+            l2 = ctx.load_log(o2, a2, t2, n_a)
+            try:
+                comp2, dur2, _ = l2.explore_accurate(pat, list(range(n_a)), fl)
+            finally:
+                l2.close()
+            for c in range(n_a):
+                nfa = abi.make_nfa([dict(kind=N_, types=[x]) for x in pat + [c]])
+                want = oracle.detect(o2, a2, t2, nfa, flags=abi.F_RETURN_ALL | fl)
+                d = sum(int(want.ev_ts_ms[want.ev_off[o + 1] - 1] - want.ev_ts_ms[want.ev_off[o]]) for o in range(want.n_occurrences))
+                assert (comp2[c], dur2[c]) == (want.n_occurrences, d), (n_a, lens, pat, fl, c)
         props = sase.explore_accurate(["act00", "act01"], log, acts)
         assert [p.event for p in props] == [p.event for p in sorted(props, key=lambda p: (-p.completions / p.averageDuration, p.event))]
         assert {p.event for p in props} == {acts.names[c] for c in range(n_act) if comp[c] > 0}
