@@ -8,6 +8,8 @@ percent of the scan), so they are issued once per request on padded buffers.
 Works on CPU tensors with the gloo backend too (tests/test_distributed_cpu.py).
 """
 import numpy as np
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -230,13 +232,15 @@ class PeerExchanger:
     so the next request's verification kernel runs beside them at full speed; only the 9-value header still goes
     through NCCL.  One node only (symmetric memory needs peer access); `depth` requests may be in flight."""
 
-    def __init__(self, device, group=None, capacity=64 << 20, depth=3):
+    def __init__(self, device, group=None, capacity=64 << 20, depth=3, n_streams=4):
         import torch.distributed._symmetric_memory as symm
         self._symm = symm
         self.group = group if group is not None else dist.group.WORLD
         self.device, self.depth = device, depth
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         self.stream = torch.cuda.Stream(device)
+        # one copy engine does not fill an NVLink port: the pulls of one request are spread over several streams
+        self.pull_streams = [torch.cuda.Stream(device) for _ in range(max(1, int(os.environ.get("SIESTA_PEER_STREAMS", n_streams))))]
         self.k = 0
         self._alloc(capacity)
 
@@ -270,12 +274,21 @@ class PeerExchanger:
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
             hdl.barrier()                    # every rank has staged its block
-            for step in range(world):
-                r = (rank - step) % world
-                n = hs[r][8]
-                if n:
+            staged = torch.cuda.Event()
+            staged.record(self.stream)
+        for step in range(world):
+            r = (rank - step) % world
+            n = hs[r][8]
+            if n:
+                st = self.pull_streams[step % len(self.pull_streams)]
+                st.wait_event(staged)
+                with torch.cuda.stream(st):
                     src = hdl.get_buffer(r, (self.capacity,), torch.uint8)
-                    recv[r, :n].copy_(src[:n])
+                    recv[r, :n].copy_(src[:n], non_blocking=True)
+        for st in self.pull_streams:
+            self.stream.wait_stream(st)
+            recv.record_stream(st)
+        with torch.cuda.stream(self.stream):
             hdl.barrier()                    # every rank has pulled: the slot may be overwritten
             done = torch.cuda.Event()
             done.record(self.stream)
