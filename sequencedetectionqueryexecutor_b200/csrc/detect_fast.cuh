@@ -413,6 +413,12 @@ struct NkpWalk {
     }
     // run started at the event with bit sb: its events as a mask, 0 = never completes / deleted at a negative state
     SIESTA_HD __forceinline__ u64 walk(const u64* T, u64 sb) {
+        return walk_on([T](int k) { return T[k]; }, sb);
+    }
+    // tget(k) = mask of state k's events (k <= SIESTA_MAX_STATES; registers or, for a walk done on behalf of another
+    // lane's trace, shared memory)
+    template <class TGet>
+    SIESTA_HD __forceinline__ u64 walk_on(const TGet& tget, u64 sb) {
         const int S = nfa.n_states;
         v0 = v1 = 0;
         if (nfa.need_vv) take(0, sb);
@@ -423,13 +429,14 @@ struct NkpWalk {
             if (k >= S) break;
             if (k != k_next) continue;
             const bool neg = nfa.kind[k] == SIESTA_STATE_NEGATIVE;
-            u64 c = (neg ? (T[k] | T[k + 1]) : T[k]) & ~(pb | (pb - 1));
+            const u64 Tk = tget(k);
+            u64 c = (neg ? (Tk | tget(k + 1)) : Tk) & ~(pb | (pb - 1));
             u64 got = 0;
             while (c) {
                 const u64 eb = c & (0ull - c);
                 c ^= eb;
                 if (neg) {
-                    if (T[k] & eb) {
+                    if (Tk & eb) {
                         if (preds(k, eb)) return 0;     // containsNegative: deleted (Engine.java:679-682)
                     } else if (preds(k + 1, eb)) {      // Engine.checkPredicatesForNextState :1165-1180
                         got = eb;

@@ -76,65 +76,79 @@ __device__ __forceinline__ long long ex_shfl64(long long v, int src) {
     return ((long long)hi << 32) | (unsigned int)lo;
 }
 
+constexpr int EX_BATCH = 4;  // traces a warp has in flight (their loads are issued before the first is used)
+
 __global__ void __launch_bounds__(256) explore_prefix_kernel(const __grid_constant__ ExploreParams P) {
     const int lane = threadIdx.x & 31;
     const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < P.n_traces; t += warps_total) {
-        long long lo = 0, hi = 0;
-        if (lane == 0) { lo = P.trace_off[t]; hi = P.trace_off[t + 1]; }
-        lo = ex_shfl64(lo, 0);
-        hi = ex_shfl64(hi, 0);
-        const long long len = hi - lo;
-        if (len <= 0) continue;
-        if (len > 64) {
-            if (lane == 0) P.ovf[atomicAdd(P.counters + 1, 1ull)] = t;
-            continue;
-        }
-        const int a0 = lane < len ? __ldg(P.act + lo + lane) : -1;
-        const int a1 = 32 + lane < len ? __ldg(P.act + lo + 32 + lane) : -1;
-        unsigned long long T[SIESTA_MAX_STATES];
-        bool all = true;
+    for (long long tb = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * EX_BATCH; tb < P.n_traces;
+         tb += warps_total * EX_BATCH) {
+        // offsets of the batch: lane k holds trace_off[tb + k], k = 0 .. EX_BATCH
+        long long myoff = 0;
+        if (lane <= EX_BATCH && tb + lane <= P.n_traces) myoff = P.trace_off[tb + lane];
+        long long lo[EX_BATCH], len[EX_BATCH];
+        int a0[EX_BATCH], a1[EX_BATCH];
 #pragma unroll
-        for (int k = 0; k < SIESTA_MAX_STATES; ++k) {
-            T[k] = 0;
-            if (k < P.m) {
-                const int x = P.pat[k];
-                T[k] = (unsigned long long)__ballot_sync(0xffffffffu, a0 == x) | ((unsigned long long)__ballot_sync(0xffffffffu, a1 == x) << 32);
-                all = all && T[k] != 0;
+        for (int u = 0; u < EX_BATCH; ++u) {
+            lo[u] = ex_shfl64(myoff, u);
+            const long long hi = ex_shfl64(myoff, u + 1);
+            len[u] = tb + u < P.n_traces ? hi - lo[u] : 0;
+            a0[u] = (len[u] <= 64 && lane < len[u]) ? __ldg(P.act + lo[u] + lane) : -1;
+            a1[u] = (len[u] <= 64 && 32 + lane < len[u]) ? __ldg(P.act + lo[u] + 32 + lane) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < EX_BATCH; ++u) {
+            const long long t = tb + u;
+            if (len[u] <= 0) continue;
+            if (len[u] > 64) {
+                if (lane == 0) P.ovf[atomicAdd(P.counters + 1, 1ull)] = t;
+                continue;
             }
-        }
-        if (!all) continue;  // uniform: the prefix's activities do not all occur
-        // greedy prefix walk of every start (uniform: every lane computes the same; lane 0 writes)
-        unsigned long long uni = 0;
+            unsigned long long T[SIESTA_MAX_STATES];
+            bool all = true;
 #pragma unroll
-        for (int k = 0; k < SIESTA_MAX_STATES; ++k) uni |= T[k];
-        ExploreRecord r;
-        r.trace = t;
-        r.n = 0;
-        r.first_pat = (uint8_t)(__ffsll((long long)uni) - 1);
-        bool too_many = false;
-        for (unsigned long long st = T[0]; st; st &= st - 1) {
-            const unsigned long long sb = st & (0ull - st);
-            unsigned long long pb = sb;
-            bool ok = true;
-#pragma unroll
-            for (int k = 1; k < SIESTA_MAX_STATES; ++k) {
-                if (k < P.m && ok) {
-                    const unsigned long long c = T[k] & ~(pb | (pb - 1));
-                    if (!c) ok = false;
-                    else pb = c & (0ull - c);
+            for (int k = 0; k < SIESTA_MAX_STATES; ++k) {
+                T[k] = 0;
+                if (k < P.m) {
+                    const int x = P.pat[k];
+                    T[k] = (unsigned long long)__ballot_sync(0xffffffffu, a0[u] == x) |
+                           ((unsigned long long)__ballot_sync(0xffffffffu, a1[u] == x) << 32);
+                    all = all && T[k] != 0;
                 }
             }
-            if (!ok) break;  // prefix ends never decrease with the start: a later start fails as well
-            if (r.n == EX_STARTS) { too_many = true; break; }
-            r.s[r.n] = (uint8_t)(__ffsll((long long)sb) - 1);
-            r.e[r.n] = (uint8_t)(__ffsll((long long)pb) - 1);
-            ++r.n;
-        }
-        if (too_many) {
-            if (lane == 0) P.ovf[atomicAdd(P.counters + 1, 1ull)] = t;
-        } else if (r.n && lane == 0) {
-            P.rec[atomicAdd(P.counters + 0, 1ull)] = r;
+            if (!all) continue;  // uniform: the prefix's activities do not all occur
+            // greedy prefix walk of every start (uniform: every lane computes the same; lane 0 writes)
+            unsigned long long uni = 0;
+#pragma unroll
+            for (int k = 0; k < SIESTA_MAX_STATES; ++k) uni |= T[k];
+            ExploreRecord r;
+            r.trace = t;
+            r.n = 0;
+            r.first_pat = (uint8_t)(__ffsll((long long)uni) - 1);
+            bool too_many = false;
+            for (unsigned long long st = T[0]; st; st &= st - 1) {
+                const unsigned long long sb = st & (0ull - st);
+                unsigned long long pb = sb;
+                bool ok = true;
+#pragma unroll
+                for (int k = 1; k < SIESTA_MAX_STATES; ++k) {
+                    if (k < P.m && ok) {
+                        const unsigned long long c = T[k] & ~(pb | (pb - 1));
+                        if (!c) ok = false;
+                        else pb = c & (0ull - c);
+                    }
+                }
+                if (!ok) break;  // prefix ends never decrease with the start: a later start fails as well
+                if (r.n == EX_STARTS) { too_many = true; break; }
+                r.s[r.n] = (uint8_t)(__ffsll((long long)sb) - 1);
+                r.e[r.n] = (uint8_t)(__ffsll((long long)pb) - 1);
+                ++r.n;
+            }
+            if (too_many) {
+                if (lane == 0) P.ovf[atomicAdd(P.counters + 1, 1ull)] = t;
+            } else if (r.n && lane == 0) {
+                P.rec[atomicAdd(P.counters + 0, 1ull)] = r;
+            }
         }
     }
 }
@@ -246,7 +260,7 @@ extern "C" int siesta_explore_accurate(siesta_log* log, const int32_t* pattern_a
     P.sum_ms = d_acc + nc;
     unsigned long long h_cnt[2] = {0, 0};
     if (T > 0 && n_candidates > 0) {
-        const int grid = (int)std::min<int64_t>((T + 7) / 8, (int64_t)L->ctx->sm_count * 8);
+        const int grid = (int)std::min<int64_t>((T + 8 * EX_BATCH - 1) / (8 * EX_BATCH), (int64_t)L->ctx->sm_count * 8);
         explore_prefix_kernel<<<grid, 256, 0, stream>>>(P);
         SIESTA_LAUNCHED();
         SIESTA_CUDA_OK(cudaGetLastError());
