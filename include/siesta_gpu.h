@@ -341,9 +341,12 @@ int siesta_pair_stats_device(siesta_log* log, const int32_t* pair_a, const int32
  * QueryPlanExplorationAccurate.java:82-102) for every candidate continuation: the pattern (all "_" events, a
  * SimplePattern) extended by candidate c is detected with clearOccurrences(true) in every trace;
  * completions[c] = number of occurrences, sum_duration_ms[c] = sum over them of last.timestamp - first.timestamp in
- * milliseconds (Occurrence.getDuration, model/Occurrence.java:55-61, is this / 1000.0; 0 under SIESTA_F_EVT_POS,
- * where events carry no timestamp).  The caller divides (average = sum / 1000.0 / completions) and sorts
- * (Proposition.compareTo, model/Proposition.java:51-60).  flags: 0 or SIESTA_F_EVT_POS. */
+ * milliseconds (Occurrence.getDuration, model/Occurrence.java:55-61, is this / 1000.0; the timestamps are those
+ * siesta_detect reports: relative seconds * 1000 + the first filtered event on the EventTs route, the log's own
+ * timestamps under SIESTA_F_EVT_POS).  The caller divides (average = sum / 1000.0 / completions) and sorts
+ * (Proposition.compareTo, model/Proposition.java:51-60).  flags: 0 or SIESTA_F_EVT_POS.
+ * One pass over the log serves all candidates (csrc/explore.cu); the result equals one siesta_detect with
+ * SIESTA_F_RETURN_ALL per candidate. */
 int siesta_explore_accurate(siesta_log* log, const int32_t* pattern_activities, int32_t n_pattern,
                             const int32_t* candidates, int32_t n_candidates, uint32_t flags,
                             int64_t* completions, int64_t* sum_duration_ms, double* kernel_ms);
