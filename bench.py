@@ -288,10 +288,23 @@ def main():
 
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if wl["bytes_per_event"] * E <= 2.6e8 else None
 
+    # At N > 1 two requests are in flight (what a server under load does): the verification kernels of request i+1 are
+    # enqueued (siesta_detect_device_begin) BEFORE the host packs and exchanges the result of request i, so the
+    # exchange's host-side chain (pack, header all-gather, two synchronisations) runs while the GPU scans the next
+    # request; siesta_detect_device_finish then only waits for the sizes and places the result.
+    pipelined = world > 1 and os.environ.get("SIESTA_BENCH_PIPELINE", "1") != "0"
+    pending = [None]
+
     def step_resident():
         if flush is not None:
             flush.add_(1)  # inputs smaller than L2: evict them between steps
-        dm = log.detect_device(nfa, flags=0)
+        if pipelined:
+            if pending[0] is None:
+                pending[0] = log.detect_device_begin(nfa, flags=0)
+            dm = pending[0].finish()
+            pending[0] = log.detect_device_begin(nfa, flags=0)   # the next request starts scanning now
+        else:
+            dm = log.detect_device(nfa, flags=0)
         n_all = dm.n_traces
         if world > 1:
             # the exchange step: every rank ends up with the match lists of all ranks (one padded NCCL all-gather of
@@ -330,6 +343,9 @@ def main():
     wall = time.perf_counter() - t0
     launches = api.kernel_launches() - launches0
     clocks = sampler.stop()
+    if pending[0] is not None:   # the request begun for the step after the last timed one: finish and drop it (untimed)
+        pending[0].finish().close()
+        pending[0] = None
     assert r[:4] == r0[:4], "result changed between steps"
 
     t_step = torch.tensor([wall / args.steps], device=dev, dtype=torch.float64)
@@ -385,7 +401,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": args.workload, "pattern": wl["pattern"],
                        "traces_per_gpu": T, "events_per_gpu": E, "activities": wl["n_act"],
-                       "parallelism": f"traces sharded over {world} GPU(s); match lists joined by " +
+                       "parallelism": f"traces sharded over {world} GPU(s){'; two requests in flight (begin / finish)' if pipelined else ''}; match lists joined by " +
                                       ("copy-engine pulls of compact result blocks over NVLink peer memory" if peer is not None
                                        else "one NCCL all-gather of compact result blocks"),
                        "l2": (f"inputs ({12 * E / 1e9:.2f} GB/GPU resident, {wl['bytes_per_event']} B/event read) "

@@ -248,6 +248,16 @@ typedef struct siesta_dev_matches {
 
 int siesta_detect_device(siesta_log* log, const siesta_nfa* nfa, const int64_t* d_cand,
                          int64_t n_cand, uint32_t flags, void* stream, siesta_dev_matches* out);
+/* The same request in two halves, for callers that keep several requests in flight (the reference serves concurrent
+ * requests; the multi-GPU exchange of request i then overlaps the scan of request i + 1): _begin enqueues the
+ * verification kernels and returns without waiting for the device; _finish waits for them, allocates the result,
+ * places it and fills `out` exactly as siesta_detect_device does.  _finish consumes `pending` whatever it returns; every
+ * _begin must be followed by exactly one _finish (also to release the request after an error elsewhere).  `nfa` and
+ * `d_cand` are borrowed until _finish returns. */
+typedef struct siesta_detect_pending siesta_detect_pending;
+int siesta_detect_device_begin(siesta_log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand,
+                               uint32_t flags, void* stream, siesta_detect_pending** out);
+int siesta_detect_device_finish(siesta_detect_pending* pending, siesta_dev_matches* out);
 void siesta_dev_matches_free(siesta_dev_matches* m);
 
 /* Compact wire format of a device result for the multi-GPU exchange (13 B per trace + 1 B per occurrence + 9 B per

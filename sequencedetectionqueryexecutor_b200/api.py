@@ -108,6 +108,14 @@ class EventLog:
                                          C.byref(dm)))
         return DeviceMatches(dm)
 
+    def detect_device_begin(self, nfa, d_cand=None, flags=0, stream=None):
+        """siesta_detect_device_begin: enqueue the verification and return at once; .finish() -> DeviceMatches."""
+        h = C.c_void_p()
+        cp = C.c_void_p(d_cand.data_ptr()) if d_cand is not None else None
+        n = 0 if d_cand is None else d_cand.numel()
+        check(lib().siesta_detect_device_begin(self._h, C.byref(nfa), cp, n, flags, C.c_void_p(stream) if stream else None,
+                                               C.byref(h)))
+        return PendingDetect(h, (nfa, d_cand))
 
     def declare_counts(self, k_cap=None):
         """siesta_declare_counts: the integer matrices behind /declare (host copy, DeclareCounts)."""
@@ -221,6 +229,22 @@ class PairIndex:
         n = C.c_int64(0)
         check(lib().siesta_candidates(self._h, _ptr(off), _ptr(ids), len(expansions), _ptr(out), len(out), C.byref(n)))
         return out[:n.value].copy()
+
+
+class PendingDetect:
+    """A verification request whose kernels are enqueued (siesta_detect_device_begin); finish() exactly once."""
+
+    def __init__(self, h, keep):
+        self._h, self._keep = h, keep   # nfa / candidates stay alive until finish()
+
+    def finish(self):
+        dm = _abi.DevMatches()
+        h, self._h = self._h, None
+        if h is None:
+            raise RuntimeError("PendingDetect.finish() called twice")
+        check(lib().siesta_detect_device_finish(h, C.byref(dm)))
+        self._keep = None
+        return DeviceMatches(dm)
 
 
 class DeviceMatches:

@@ -60,6 +60,7 @@ extern "C" void siesta_shutdown(siesta_ctx* ctx) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (HostBlock& b : c->arena) cudaFreeHost(b.p);  // result objects must have been freed before the ctx
+    for (unsigned long long* p : c->pinned_counters) cudaFreeHost(p);
     delete c;
 }
 

@@ -40,6 +40,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     std::mutex arena_mu;
     std::vector<HostBlock> arena;
+    std::vector<unsigned long long*> pinned_counters;  // free 128-byte pinned blocks for the requests' counters
 };
 
 // CSR event log resident in HBM.

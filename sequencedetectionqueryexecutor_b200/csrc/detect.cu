@@ -987,9 +987,60 @@ int launch_nkp(const Ctx* ctx, cudaStream_t stream, const DetectParams& P, const
 
 }  // namespace
 
-int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand, uint32_t flags,
-                       cudaStream_t stream, RebaseOffsets base, siesta_dev_matches* out) {
-    std::memset(out, 0, sizeof(*out));
+// A verification request between its two halves (siesta_detect_device_begin / _finish): everything the second half
+// needs.  The first half enqueues the verification kernels and the copy of the counters and returns without waiting;
+// the second half waits for the counters, allocates the result and enqueues the placement.  A caller with several
+// requests in flight (a server, the multi-GPU bench) issues the next request's first half before it exchanges the
+// results of the previous one, so the host-side work of one request overlaps the scan of the next.
+struct DetectPending {
+    Log* log = nullptr;
+    cudaStream_t stream = nullptr;
+    int64_t n = 0;
+    uint32_t flags = 0;
+    RebaseOffsets base{0, 0, 0};
+    const int64_t* d_cand = nullptr;
+    DetectParams P;
+    size_t n_blk = 0;
+    unsigned long long *d_blk = nullptr, *d_top = nullptr, *d_counters = nullptr;
+    int64_t* d_err = nullptr;
+    void* work = nullptr;                 // scratch of the call (freed by the second half)
+    cudaEvent_t ev0 = nullptr, evd = nullptr;
+    unsigned long long* h_cnt = nullptr;  // pinned, 16 words
+};
+
+static unsigned long long* pinned_counters_get(Ctx* c) {
+    {
+        std::lock_guard<std::mutex> g(c->arena_mu);
+        if (!c->pinned_counters.empty()) {
+            unsigned long long* p = c->pinned_counters.back();
+            c->pinned_counters.pop_back();
+            return p;
+        }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, 128, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return reinterpret_cast<unsigned long long*>(p);
+}
+static void pinned_counters_put(Ctx* c, unsigned long long* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(c->arena_mu);
+    c->pinned_counters.push_back(p);
+}
+
+static void pending_discard(DetectPending* q) {
+    if (!q) return;
+    if (q->work) cudaFreeAsync(q->work, q->stream);
+    if (q->ev0) cudaEventDestroy(q->ev0);
+    if (q->evd) cudaEventDestroy(q->evd);
+    pinned_counters_put(q->log->ctx, q->h_cnt);
+    delete q;
+}
+
+int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out);
+
+int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand, uint32_t flags,
+                             cudaStream_t stream, RebaseOffsets base, DetectPending** pending) {
+    *pending = nullptr;
     base.trace += log->first_trace;
     DevNfa dn;
     int rc = validate_nfa(nfa, flags, &dn);
@@ -1046,10 +1097,22 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
         s_ev_pos{wb + o_pos}, s_ev_rank{all_cols ? wb + o_rank : nullptr}, s_ev_act{all_cols ? wb + o_act : nullptr},
         s_ev_ts{all_cols ? wb + o_ts : nullptr};
 
-    cudaEvent_t ev0, ev1, evd;
+    cudaEvent_t ev0 = nullptr, evd = nullptr;
     SIESTA_CUDA_OK(cudaEventCreate(&ev0));
-    SIESTA_CUDA_OK(cudaEventCreate(&ev1));
     SIESTA_CUDA_OK(cudaEventCreate(&evd));
+    unsigned long long* h_cnt = nullptr;
+    struct BeginGuard {   // an error return of the first half releases what it holds so far
+        cudaEvent_t &a, &b;
+        unsigned long long*& h;
+        Ctx* c;
+        bool armed;
+        ~BeginGuard() {
+            if (!armed) return;
+            if (a) cudaEventDestroy(a);
+            if (b) cudaEventDestroy(b);
+            pinned_counters_put(c, h);
+        }
+    } begin_guard{ev0, evd, h_cnt, log->ctx, true};
     SIESTA_CUDA_OK(cudaMemcpyAsync(b_lut.p, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
     SIESTA_CUDA_OK(cudaMemsetAsync(b_counters.p, 0, 256, stream));
     SIESTA_CUDA_OK(cudaEventRecord(ev0, stream));
@@ -1107,7 +1170,12 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
 
     P.ovf_slot = 4;
     P.tile_slot = 16;   // the tile counters live on their own 128-byte line (slots 16..)
-    unsigned long long h_cnt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    h_cnt = pinned_counters_get(log->ctx);
+    if (!h_cnt) {
+        set_error("cudaHostAlloc (counters) failed");
+        return SIESTA_E_NOMEM;
+    }
+    std::memset(h_cnt, 0, 128);
     if (n > 0) {
         if (use_nkp) {
             DetectParams N = P;
@@ -1151,7 +1219,55 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
         else rc = launch_detect<2, 1024, 128, false, FAST_NONE>(ctx, stream, Q, dn);
         if (rc) return rc;
         SIESTA_CUDA_OK(cudaMemcpyAsync(h_cnt, b_counters.p, 128, cudaMemcpyDeviceToHost, stream));
-        SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+    }
+    // ---- end of the first half: nothing above waits for the device
+    DetectPending* q = new DetectPending();
+    q->log = log;
+    q->stream = stream;
+    q->n = n;
+    q->flags = flags;
+    q->base = base;
+    q->d_cand = d_cand;
+    q->P = P;
+    q->n_blk = n_blk;
+    q->d_blk = b_blk.as<unsigned long long>();
+    q->d_top = reinterpret_cast<unsigned long long*>(wb + o_top);
+    q->d_counters = b_counters.as<unsigned long long>();
+    q->d_err = b_err.as<int64_t>();
+    q->work = work.release();
+    q->ev0 = ev0;
+    q->evd = evd;
+    q->h_cnt = h_cnt;
+    begin_guard.armed = false;
+    *pending = q;
+    return SIESTA_OK;
+}
+
+// Second half: waits for the counters of the first half, allocates the result, enqueues the placement and waits for it.
+// Consumes (frees) the pending request whatever the outcome.
+int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out) {
+    std::memset(out, 0, sizeof(*out));
+    struct Guard {
+        DetectPending* q;
+        ~Guard() { pending_discard(q); }
+    } guard{q};
+    Log* log = q->log;
+    const Ctx* ctx = log->ctx;
+    SIESTA_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t stream = q->stream;
+    const int64_t n = q->n;
+    const uint32_t flags = q->flags;
+    const bool return_all = (flags & SIESTA_F_RETURN_ALL) != 0;
+    const bool all_cols = (flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
+    const RebaseOffsets base = q->base;
+    const int64_t* d_cand = q->d_cand;
+    const DetectParams& P = q->P;
+    const size_t n_blk = q->n_blk;
+    unsigned long long* h_cnt = q->h_cnt;
+    cudaEvent_t ev0 = q->ev0, evd = q->evd, ev1;
+    int rc = SIESTA_OK;
+    SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+    if (n > 0) {
         if (h_cnt[7] > 0) {
             set_error(std::to_string(h_cnt[7]) + " trace(s) exceed the engine limits (64 pattern-relevant events, "
                       "1024 live runs or 65536 events per trace)");
@@ -1162,6 +1278,11 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
             return SIESTA_E_NOMEM;
         }
     }
+    SIESTA_CUDA_OK(cudaEventCreate(&ev1));
+    struct EvGuard {
+        cudaEvent_t e;
+        ~EvGuard() { cudaEventDestroy(e); }
+    } ev1_guard{ev1};
 #ifdef SIESTA_PHASE_TIMING
     fprintf(stderr, "[siesta phase timing] warp-cycles: filter %llu engine %llu output %llu\n", h_cnt[8], h_cnt[9], h_cnt[10]);
 #endif
@@ -1198,9 +1319,9 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
         G.d_stage = P.d_stage;
         G.d_stage_occ = return_all ? P.d_stage_occ : nullptr;
         G.n_blk = (int64_t)n_blk;
-        G.blk = b_blk.as<unsigned long long>();
+        G.blk = q->d_blk;
         G.n_chunks = (int64_t)((n_blk + 1023) / 1024);
-        G.top = reinterpret_cast<unsigned long long*>(wb + o_top);
+        G.top = q->d_top;
         G.s_occ_nev = P.s_occ_nev;
         G.s_ev_pos = P.s_ev_pos;
         G.s_ev_rank = P.s_ev_rank;
@@ -1229,7 +1350,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     SIESTA_CUDA_OK(cudaEventRecord(ev1, stream));
     if (n_err > 0) {  // order the (rare) error list
         std::vector<int64_t> h((size_t)n_err);
-        SIESTA_CUDA_OK(cudaMemcpyAsync(h.data(), b_err.p, (size_t)n_err * 8, cudaMemcpyDeviceToHost, stream));
+        SIESTA_CUDA_OK(cudaMemcpyAsync(h.data(), q->d_err, (size_t)n_err * 8, cudaMemcpyDeviceToHost, stream));
         SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
         std::sort(h.begin(), h.end());
         for (int64_t& x : h) x += base.trace;
@@ -1239,9 +1360,7 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     float ms = 0.f, dms = 0.f;
     SIESTA_CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1));
     if (n > 0) SIESTA_CUDA_OK(cudaEventElapsedTime(&dms, ev0, evd));
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
-    cudaEventDestroy(evd);
+    // (the events and the scratch are released by the guards)
 
     DevMatchesImpl* impl = new DevMatchesImpl();
     out->n_traces = n_tr;
@@ -1268,7 +1387,37 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
     return SIESTA_OK;
 }
 
+int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand, uint32_t flags,
+                       cudaStream_t stream, RebaseOffsets base, siesta_dev_matches* out) {
+    std::memset(out, 0, sizeof(*out));
+    DetectPending* q = nullptr;
+    const int rc = detect_device_begin_impl(log, nfa, d_cand, n_cand, flags, stream, base, &q);
+    if (rc != SIESTA_OK) return rc;
+    return detect_device_finish_impl(q, out);
+}
+
 }  // namespace siesta
+
+extern "C" int siesta_detect_device_begin(siesta_log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand,
+                                          uint32_t flags, void* stream, siesta_detect_pending** out) {
+    if (!log || !nfa || !out || (d_cand && n_cand < 0)) {
+        siesta::set_error("siesta_detect_device_begin: null argument");
+        return SIESTA_E_INVALID;
+    }
+    siesta::DetectPending* q = nullptr;
+    const int rc = siesta::detect_device_begin_impl(reinterpret_cast<siesta::Log*>(log), nfa, d_cand, n_cand, flags,
+                                                    reinterpret_cast<cudaStream_t>(stream), siesta::RebaseOffsets{0, 0, 0}, &q);
+    *out = reinterpret_cast<siesta_detect_pending*>(q);
+    return rc;
+}
+
+extern "C" int siesta_detect_device_finish(siesta_detect_pending* pending, siesta_dev_matches* out) {
+    if (!pending || !out) {
+        siesta::set_error("siesta_detect_device_finish: null argument");
+        return SIESTA_E_INVALID;
+    }
+    return siesta::detect_device_finish_impl(reinterpret_cast<siesta::DetectPending*>(pending), out);
+}
 
 extern "C" int siesta_detect_device(siesta_log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand,
                                     uint32_t flags, void* stream, siesta_dev_matches* out) {

@@ -470,3 +470,32 @@ def test_raw_slot_kernel_nk_class(ctx, seed):
             continue
         n_match += got.n_traces
     assert n_match > 1000
+
+
+def test_begin_finish_requests_in_flight(ctx):
+    """siesta_detect_device_begin / _finish: several requests enqueued before any is finished, finished out of order,
+    each equal to the oracle's result (and to the one-call form)."""
+    off, act, ts = gen.make_log(6000, 10, 70, 10, seed=111)
+    log = ctx.load_log(off, act, ts, 10)
+    jobs = [([dict(kind=P_, types=[0]), dict(kind=S_, types=[1], preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 900)])], 0),
+            ([dict(kind=N_, types=[2]), dict(kind=O_, types=[3, 4]), dict(kind=X_, types=[5]), dict(kind=N_, types=[6])], 0),
+            ([dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[2])], abi.F_RETURN_ALL),
+            ([dict(kind=N_, types=[7]), dict(kind=N_, types=[8])], abi.F_EVT_POS | abi.F_COUNT_MATCHES)]
+    try:
+        pend = [log.detect_device_begin(abi.make_nfa(s), flags=f) for s, f in jobs]
+        for i in (2, 0, 3, 1):
+            dm = pend[i].finish()
+            want = oracle.detect(off, act, ts, abi.make_nfa(jobs[i][0]), flags=jobs[i][1])
+            assert (dm.n_traces, dm.n_occurrences, dm.n_events) == (want.n_traces, want.n_occurrences, want.n_events), i
+            t = dm.tensors(0)
+            assert np.array_equal(t["trace_idx"].cpu().numpy(), want.trace_idx) and np.array_equal(t["ev_pos"].cpu().numpy(), want.ev_pos), i
+            assert np.array_equal(t["ev_ts_ms"].cpu().numpy(), want.ev_ts_ms) and np.array_equal(t["ev_off"].cpu().numpy(), want.ev_off), i
+            dm.close()
+        # a request that is begun and finished at once equals the one-call form
+        a = log.detect_device_begin(abi.make_nfa(jobs[1][0]), flags=0).finish()
+        b = log.detect_device(abi.make_nfa(jobs[1][0]), flags=0)
+        assert (a.n_traces, a.n_events) == (b.n_traces, b.n_events)
+        a.close()
+        b.close()
+    finally:
+        log.close()
