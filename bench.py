@@ -288,11 +288,11 @@ def main():
 
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if wl["bytes_per_event"] * E <= 2.6e8 else None
 
-    # At N > 1 two requests are in flight (what a server under load does): the verification kernels of request i+1 are
-    # enqueued (siesta_detect_device_begin) BEFORE the host packs and exchanges the result of request i, so the
-    # exchange's host-side chain (pack, header all-gather, two synchronisations) runs while the GPU scans the next
-    # request; siesta_detect_device_finish then only waits for the sizes and places the result.
-    pipelined = world > 1 and os.environ.get("SIESTA_BENCH_PIPELINE", "1") != "0"
+    # Two requests in flight (siesta_detect_device_begin / _finish): the verification kernels of request i+1 are enqueued
+    # BEFORE the host packs and exchanges the result of request i.  Opt-in (SIESTA_BENCH_PIPELINE=1): measured on 2 GPUs
+    # 0.794 vs 0.808 ms per step - the persistent scan fills every SM, so the pack kernels and the collectives of
+    # request i queue behind the scan of request i+1 instead of overlapping it.
+    pipelined = world > 1 and os.environ.get("SIESTA_BENCH_PIPELINE", "0") == "1"
     pending = [None]
 
     def step_resident():
