@@ -3,17 +3,25 @@
 // Replaces SaseConnector.evaluate + Occurrences.clearOccurrences
 // (J/SaseConnection/SaseConnector.java:48-76, J/model/Occurrences.java:58-89).
 //
-// Launch shape: persistent CTAs of NT=128 threads (grid = SMs x resident CTAs), each looping
-// over tiles of NT traces.
-//   phase A (warp-cooperative, coalesced): a warp walks its 32 traces one after the other;
-//           lanes read consecutive int32 activity ids (128 B per warp load), look the pattern's
-//           state mask up, ballot, and compact the events that belong to the pattern into the
-//           trace's shared-memory slot (the reference's Trace.clearTrace / Utils.transformToSaseEvents).
-//           Timestamps (int64 ms) are loaded only for events that survive the filter.
-//   phase B (thread per trace): RunEngine over the compacted events (detect_engine.cuh).
-//   phase C: block scan of output sizes, one atomicAdd per CTA to reserve staging space, write.
-// A final gather orders the staged occurrences by trace index (dense per-candidate counts +
-// device scans), so the result is deterministic.
+// Launch shape: persistent CTAs of NT = 128 threads (grid = SMs x resident CTAs); every WARP owns a tile of 32 traces
+// from start to finish, one lane per trace, no block-level barrier; tiles are handed out by an atomic counter.
+//   detect_kernel (staged, every NFA class)
+//     phase A  each lane streams its own trace in 32-byte sectors, tests the activity ids against the pattern's class
+//              bit-planes in registers and appends the surviving events (the reference's Trace.clearTrace /
+//              Utils.transformToSaseEvents) to its lane-transposed shared-memory column; timestamps (int64 ms) travel by
+//              cp.async, for surviving events only
+//     phase B  one lane per trace: closed-form evaluators (detect_fast.cuh: classes NK and FK2) or the run-list engine
+//              (detect_engine.cuh)
+//     phase C  warp scan of the output sizes, one reservation per tile, the tile's events written as one flat stream
+//   detect_nkp_kernel (K1-P: class NK, first-largest occurrence, no relative seconds)
+//              no shared memory: class planes of the trace's 64 raw position slots in registers, one mask per NFA
+//              state, greedy walks on the masks, fixed staging slots (no atomic on the critical path)
+//   count_blocks / scan_chunks / scan_top / gather
+//              order the staged occurrences by trace index (dense per-candidate counts + device scans), so the
+//              result is deterministic
+// A request is two host-side halves (detect_device_begin_impl: kernels enqueued, nothing waited for;
+// detect_device_finish_impl: sizes, result allocation, placement), exposed as siesta_detect_device_begin / _finish
+// and, in one call, siesta_detect_device.
 #include <algorithm>
 #include <cstdio>
 #include <type_traits>
