@@ -128,6 +128,23 @@ def read_index_table(src, log: SeqLog, pairs: Optional[Sequence[Tuple[str, str]]
     return out_pairs, lists
 
 
+def filter_time_range(trace_off, act, ts_ms, from_ms=None, till_ms=None):
+    """Trace.filter(from, till) (J/model/DBModel/Trace.java:25-29) for a whole CSR log: keeps the events with
+    from <= timestamp <= till (either bound may be None) -> (trace_off, act, ts_ms, kept) where `kept` are the indices of
+    the surviving events in the input (in-trace positions of the filtered log are ranks among the kept events, as in the
+    reference, which filters the list before Utils.transformToSaseEvents numbers it)."""
+    ts_ms = np.asarray(ts_ms, dtype=np.int64)
+    keep = np.ones(len(ts_ms), dtype=bool)
+    if from_ms is not None:
+        keep &= ts_ms >= from_ms
+    if till_ms is not None:
+        keep &= ts_ms <= till_ms
+    csum = np.concatenate(([0], np.cumsum(keep, dtype=np.int64)))
+    new_off = csum[np.asarray(trace_off, dtype=np.int64)]
+    kept = np.flatnonzero(keep)
+    return new_off, np.ascontiguousarray(np.asarray(act)[kept]), np.ascontiguousarray(ts_ms[kept]), kept
+
+
 # ------------------------------------------------------------------------------------------------ writers (tests, tooling)
 def _format_ts(ts_ms):
     base = ts_ms.astype("datetime64[ms]")

@@ -83,6 +83,30 @@ def test_index_table_gives_the_oracles_posting_lists(tmp_path):
     assert set(common.tolist()) <= set(both)
 
 
+def test_time_range_filter_equals_per_trace_filtering():
+    """Trace.filter(from, till): the vectorised CSR filter equals filtering every trace's list, and the oracle run on the
+    filtered log equals the oracle run on per-trace filtered lists."""
+    from sequencedetectionqueryexecutor_b200 import _abi as abi
+    off, act, ts = gen.make_log(400, 0, 30, 5, seed=12, max_gap_s=3600)
+    lo, hi = int(np.percentile(ts, 30)), int(np.percentile(ts, 80))
+    for f, t in [(lo, hi), (None, hi), (lo, None), (None, None), (hi, lo)]:
+        n_off, n_act, n_ts, kept = ingest.filter_time_range(off, act, ts, f, t)
+        assert len(n_off) == len(off) and n_off[-1] == len(n_act) == len(kept)
+        for i in range(len(off) - 1):
+            seg = slice(off[i], off[i + 1])
+            m = np.ones(off[i + 1] - off[i], dtype=bool)
+            if f is not None:
+                m &= ts[seg] >= f
+            if t is not None:
+                m &= ts[seg] <= t
+            assert np.array_equal(n_act[n_off[i]:n_off[i + 1]], act[seg][m])
+            assert np.array_equal(n_ts[n_off[i]:n_off[i + 1]], ts[seg][m])
+    n_off, n_act, n_ts, _ = ingest.filter_time_range(off, act, ts, lo, hi)
+    nfa = abi.make_nfa([dict(kind=abi.STATE_NORMAL, types=[0]), dict(kind=abi.STATE_NORMAL, types=[1])])
+    got = oracle.detect(n_off, n_act, n_ts, nfa)
+    assert got.n_traces > 0 and np.all(got.ev_ts_ms >= lo - 999) and np.all(got.ev_ts_ms <= hi)
+
+
 @pytest.mark.gpu
 def test_ingested_bucket_through_the_gpu_path(tmp_path):
     """seq.parquet + index.parquet -> load_log / load_index -> intersection -> detection on the candidates = the oracle."""
