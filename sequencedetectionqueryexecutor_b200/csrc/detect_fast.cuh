@@ -381,7 +381,23 @@ struct NkpWalk {
     u64 R;
     int lead;
     u64 v0, v1;  // byte k: position / timestamp attribute of the event taken for state k
-    SIESTA_HD __forceinline__ NkpWalk(const DevNfa& n, u64 r, int l) : nfa(n), R(r), lead(l), v0(0), v1(0) {}
+    // Two facts about consecutive starts of one trace (walks are monotone, see the header of this file):
+    //  exhausted   a walk found NO later event of a state's types at all: every later start stands even further right,
+    //              so no later start completes either;
+    //  memo        a walk took event e1 for the first positive state after state 0 and failed afterwards; if no predicate
+    //              of a later state references state 0, the rest of a walk depends on e1 alone, so the next start that
+    //              takes the same e1 fails as well (first events never move left, so remembering the last e1 is enough).
+    bool exhausted, memo_ok, memo_failed;
+    u64 memo_e1;
+    SIESTA_HD __forceinline__ NkpWalk(const DevNfa& n, u64 r, int l)
+        : nfa(n), R(r), lead(l), v0(0), v1(0), exhausted(false), memo_ok(true), memo_failed(false), memo_e1(0) {
+        const int ks1 = (n.n_states > 1 && n.kind[1] == SIESTA_STATE_NEGATIVE) ? 2 : 1;
+#pragma unroll
+        for (int s = 0; s < SIESTA_MAX_STATES; ++s)
+#pragma unroll
+            for (int k = 0; k < SIESTA_MAX_PREDS; ++k)
+                if (s > ks1 && s < n.n_states && k < n.n_preds[s] && n.p_ref[s][k] == 0) memo_ok = false;
+    }
     SIESTA_HD __forceinline__ void attrs(u64 b, int& a0, int& a1) const {
         const int r = popc64(R & (b - 1));
         a0 = EVT ? popc64(b - 1) - lead : r;
@@ -431,6 +447,10 @@ struct NkpWalk {
             const bool neg = nfa.kind[k] == SIESTA_STATE_NEGATIVE;
             const u64 Tk = tget(k);
             u64 c = (neg ? (Tk | tget(k + 1)) : Tk) & ~(pb | (pb - 1));
+            if (!c) {
+                exhausted = true;
+                return 0;
+            }
             u64 got = 0;
             while (c) {
                 const u64 eb = c & (0ull - c);
@@ -449,11 +469,17 @@ struct NkpWalk {
             }
             if (!got) return 0;
             const int ks = neg ? k + 1 : k;
+            if (k == 1) {  // the first event after the start
+                if (memo_ok && memo_failed && got == memo_e1) return 0;
+                memo_e1 = got;
+                memo_failed = true;   // until this walk completes
+            }
             if (nfa.need_vv) take(ks, got);
             taken |= got;
             pb = got;
             k_next = ks + 1;
         }
+        memo_failed = false;
         return taken;
     }
 };
@@ -471,7 +497,7 @@ SIESTA_HD __forceinline__ bool nkp_eval(const DevNfa& nfa, unsigned long long R,
         if (k < S && nfa.kind[k] != SIESTA_STATE_NEGATIVE && T[k] == 0) return false;
     NkpWalk<EVT> w(nfa, R, lead);
     int best_c = 0;
-    for (u64 r = T[0]; r;) {
+    for (u64 r = T[0]; r && !w.exhausted;) {
         const u64 sb = r & (0ull - r);
         r ^= sb;
         const u64 m = w.walk(T, sb);
