@@ -128,6 +128,70 @@ def read_index_table(src, log: SeqLog, pairs: Optional[Sequence[Tuple[str, str]]
     return out_pairs, lists
 
 
+@dataclass
+class Count:
+    """A CountTable record (J/model/DBModel/Count.java:12-24)."""
+    eventA: str
+    eventB: str
+    sum_duration: int
+    count: int
+    min_duration: int
+    max_duration: int
+    sum_squares: float
+
+
+def consecutive_pairs(pattern_names: Sequence[str]):
+    """SIESTAPattern.extractPairsConsecutive (J/model/Patterns/SIESTAPattern.java:96-105): the pairs (e_i, e_i+1) of the
+    pattern's events as a set.  The reference iterates a HashSet (order unspecified); here: pattern order."""
+    out = []
+    for a, b in zip(pattern_names[:-1], pattern_names[1:]):
+        if (a, b) not in out:
+            out.append((a, b))
+    return out
+
+
+def read_count_table(src, pairs: Sequence[Tuple[str, str]]) -> List[Count]:
+    """/stats as the reference answers it: a lookup in count.parquet (QueryPlanStats.execute, J/model/Queries/QueryPlans/
+    QueryPlanStats.java:43-48 -> S3Connector.getCounts :125-169).  A row holds `eventA` and an array of records
+    (eventB, sum_duration: long, count: int, min_duration: long, max_duration: long, sum_squares: double), read by
+    POSITION as the reference does (row.getSeq(0) / getString(1); struct fields 0..5).  Returns, for every requested pair
+    in the requested order, the FIRST stored record of that pair; pairs the table does not hold are skipped (getCounts'
+    final loop).  Names compare exactly (String.equals), not case-folded."""
+    import pyarrow as pa
+    tb = _table(src)
+    list_col = next(i for i, f in enumerate(tb.schema) if pa.types.is_list(f.type) or pa.types.is_large_list(f.type))
+    name_col = next(i for i, f in enumerate(tb.schema) if pa.types.is_string(f.type) or pa.types.is_large_string(f.type))
+    wanted_a = {a for a, _ in pairs}
+    found = {}
+    names = tb.column(name_col).to_pylist()
+    records = tb.column(list_col)
+    for r, event_a in enumerate(names):
+        if event_a not in wanted_a:          # the where-clause on eventA
+            continue
+        for rec in records[r].as_py() or []:
+            v = list(rec.values()) if isinstance(rec, dict) else list(rec)
+            key = (event_a, v[0])
+            if key not in found:
+                found[key] = Count(event_a, v[0], int(v[1]), int(v[2]), int(v[3]), int(v[4]), float(v[5]))
+    return [found[p] for p in pairs if p in found]
+
+
+def count_table_from_stats(stats: Sequence[Count]):
+    """count.parquet rows (pyarrow Table, column order of the preprocess: the record array first, eventA second) of the
+    given records - synthetic buckets and tests; the records themselves come from siesta_pair_stats (kernel K4) or from
+    the preprocess."""
+    import pyarrow as pa
+    by_a = {}
+    for c in stats:
+        by_a.setdefault(c.eventA, []).append({"eventB": c.eventB, "sum_duration": int(c.sum_duration), "count": int(c.count),
+                                              "min_duration": int(c.min_duration), "max_duration": int(c.max_duration),
+                                              "sum_squares": float(c.sum_squares)})
+    rec_t = pa.struct([("eventB", pa.string()), ("sum_duration", pa.int64()), ("count", pa.int32()),
+                       ("min_duration", pa.int64()), ("max_duration", pa.int64()), ("sum_squares", pa.float64())])
+    return pa.table({"times": pa.array(list(by_a.values()), type=pa.list_(rec_t)),
+                     "eventA": pa.array(list(by_a.keys()), type=pa.string())})
+
+
 def filter_time_range(trace_off, act, ts_ms, from_ms=None, till_ms=None):
     """Trace.filter(from, till) (J/model/DBModel/Trace.java:25-29) for a whole CSR log: keeps the events with
     from <= timestamp <= till (either bound may be None) -> (trace_off, act, ts_ms, kept) where `kept` are the indices of

@@ -83,6 +83,25 @@ def test_index_table_gives_the_oracles_posting_lists(tmp_path):
     assert set(common.tolist()) <= set(both)
 
 
+def test_stats_is_a_lookup_in_the_count_table(tmp_path):
+    """Row S: QueryPlanStats answers from count.parquet.  The records written from the oracle's pair statistics come back
+    exactly, in the order of the pattern's consecutive pairs, missing pairs skipped, first record per pair."""
+    off, act, ts = gen.make_log(500, 5, 40, 6, seed=21, jitter_ms=True)
+    names = [f"act{i:02d}" for i in range(6)]
+    pairs_id = [(0, 1), (1, 2), (2, 2), (4, 0)]
+    st = oracle.pair_stats(off, act, ts, pairs_id)
+    recs = [ingest.Count(names[a], names[b], s["sum"], s["count"], s["min"], s["max"], float(s["sum_squares"]))
+            for (a, b), s in zip(pairs_id, st)]
+    dup = ingest.Count("act00", "act01", 1, 1, 1, 1, 1.0)            # a second record of a pair is never returned
+    pq.write_table(ingest.count_table_from_stats(recs + [dup]), tmp_path / "count.parquet")
+    assert ingest.consecutive_pairs(["act00", "act01", "act02", "act02"]) == [("act00", "act01"), ("act01", "act02"), ("act02", "act02")]
+    got = ingest.read_count_table(str(tmp_path / "count.parquet"), ingest.consecutive_pairs(["act00", "act01", "act02", "act02"]))
+    assert got == recs[:3]
+    got = ingest.read_count_table(str(tmp_path / "count.parquet"), [("act04", "act00"), ("act05", "act00"), ("ACT00", "act01"), ("act00", "act01")])
+    assert got == [recs[3], recs[0]]                                   # unknown pair and wrong case skipped (String.equals)
+    assert isinstance(got[0].count, int) and isinstance(got[0].sum_squares, float)
+
+
 def test_time_range_filter_equals_per_trace_filtering():
     """Trace.filter(from, till): the vectorised CSR filter equals filtering every trace's list, and the oracle run on the
     filtered log equals the oracle run on per-trace filtered lists."""
