@@ -79,6 +79,21 @@ struct DevNfa {
     int64_t p_c[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];
 };
 
+// Window-walk program of an NK-class NFA for kernel K1-P (derivation: detect_fast.cuh), built by nkw_build (nfa.cpp),
+// which also decides the index space the masks live in (NKW_NONE: the NFA stays on the staged kernel).
+enum { NKW_NONE = 0, NKW_RANK = 1, NKW_RAW = 2 };
+
+struct NkwProgram {
+    int32_t n_states;
+    uint8_t neg[SIESTA_MAX_STATES];                      // state k is a negative state
+    uint8_t n_preds[SIESTA_MAX_STATES];
+    uint8_t le[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];     // 1: e below bit idx(ref) + cc, 0: e at or above it
+    uint8_t sh[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];     // 8 * referenced state (byte of the packed indices)
+    uint8_t cc[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];     // min(c, 64) (+ 1 for <=)
+};
+
+int nkw_build(const DevNfa& dn, uint32_t flags, NkwProgram* out);
+
 // Chunked evaluation (siesta_evaluate_events): where a chunk's results sit in the whole result.
 struct RebaseOffsets {
     int64_t trace, occ, ev;

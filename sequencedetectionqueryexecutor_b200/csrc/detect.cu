@@ -29,141 +29,9 @@
 #include <cstring>
 #include <vector>
 
-#include "detect_fast.cuh"
+#include "detect_common.cuh"
 
 namespace siesta {
-
-constexpr int NT = 128;      // threads per CTA (one warp = one tile of 32 traces)
-constexpr int NT_MAX = 128;  // launch bound
-// Rows of a trace's shared-memory columns.  The narrow configuration keeps 24 (not 32) so that five CTAs fit beside an
-// L1 of ~90 KB (the kernel is sensitive to both, profiles/r01_k1_tuning.md); traces with more relevant events re-run
-// on the wide configuration (64 rows, 64-bit masks).
-#define ROWS_OF(W) ((W) == 1 ? 24 : 64)
-
-struct DetectParams {
-    const int64_t* trace_off;
-    const int32_t* act;
-    const int64_t* ts_ms;
-    const int64_t* cand;      // candidate trace indices or nullptr (= identity)
-    const int64_t* work;      // indices into the candidate list to process, or nullptr (= all)
-    int64_t n_work;           // number of traces this launch verifies ...
-    const unsigned long long* n_work_dev;  // ... or, if set, read from device memory (the narrow launch's overflow count)
-    int32_t ovf_slot;         // counter that counts the traces this launch could not hold (4 narrow, 7 wide)
-    int32_t tile_slot;        // counter that hands out tiles (16 narrow, 17 wide, 18 K1-P)
-    const uint16_t* lut;      // [n_act] smask | fmask << 8
-    // alpha_mode 0/1: the pattern's activities are numbered 1..K (K <= 7, "class"); plane p holds, bit-reversed, the
-    // activities whose class has bit p set (ids 0..31 in [p][0], 32..63 in [p][1]); cls_word / cls_act give the lut
-    // word and the activity id of a class, so the filter needs no table lookup and no re-read of the activity column
-    uint32_t relrev[3][2];
-    uint16_t cls_word[8];
-    int32_t cls_act[8];
-    int32_t n_planes;
-    int64_t n_events;         // events of the whole log (bound of the vector loads)
-    int32_t alpha_mode;       // 0: n_act <= 32, 1: n_act <= 64 (both: ids validated at log load, K <= 7), 2: general (lut in HBM)
-    int32_t vec_ok;           // act is 16-byte aligned: 128-bit loads
-    int32_t n_act;
-    uint32_t flags;
-    int32_t needs_ts;
-    // dense per-candidate outputs
-    uint32_t* d_cnt;          // selected occurrences (0 = no match) | events over the selected occurrences << 16
-    int64_t* d_stage;         // staging base (events) of the trace
-    int64_t* d_stage_occ;     // staging base (occurrences) of the trace; only with returnAll (else = the candidate's index)
-    // staging
-    int32_t* s_occ_nev;       // [cap_occ] events per staged occurrence
-    int32_t* s_ev_pos;        // [cap_ev]
-    int32_t* s_ev_rank;
-    int32_t* s_ev_act;
-    int64_t* s_ev_ts;
-    int64_t cap_occ, cap_ev;
-    // K1-P stages at fixed places (no atomic on its critical path): tile i owns the event slots
-    // [fix_ev + 32 i fix_np, + 32 fix_np) of a second staging region behind the first one
-    int64_t fix_ev;
-    int32_t fix_np;
-    // counters: 0 occ reserved, 1 ev reserved, 2 emitted, 3 errors, 4 overflow, 5 staging overflow, 6 matched traces,
-    // 7 wide overflow, 8-10 phase timing, 13 K1-P overflow; second 128-byte line: 16 / 17 / 18 next tile of the narrow /
-    // wide / K1-P launch
-    unsigned long long* counters;
-    int64_t* err_list;
-    int64_t* ovf_list;
-};
-
-__device__ __forceinline__ long long shfl_i64(long long v, int src) {
-    int lo = __shfl_sync(0xffffffffu, (int)(v & 0xffffffffll), src);
-    int hi = __shfl_sync(0xffffffffu, (int)(v >> 32), src);
-    return ((long long)hi << 32) | (unsigned int)lo;
-}
-
-// status codes of a trace inside the kernel
-enum { ST_NONE = 0, ST_MATCH = 1, ST_ERR = 2, ST_OVF = 3 };
-
-// 32 activity ids (four 32-byte sectors, two 128-bit loads each) starting at element e of this lane's trace [o0, o1).
-// Sectors past the trace are not touched; the scalar path serves unaligned logs and the last sector of the log.
-__device__ __forceinline__ void load_sectors(const DetectParams& P, long long e, long long o0, long long o1, int4 (&v)[8]) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const long long c = e + 8 * q;
-        if (c >= o1) {
-            v[2 * q] = v[2 * q + 1] = make_int4(-1, -1, -1, -1);
-        } else if (P.vec_ok && c + 8 <= P.n_events) {
-            v[2 * q] = __ldg(reinterpret_cast<const int4*>(P.act + c));
-            v[2 * q + 1] = __ldg(reinterpret_cast<const int4*>(P.act + c + 4));
-        } else {
-            int a[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = (c + i < o1 && c + i >= o0) ? __ldg(P.act + c + i) : -1;
-            v[2 * q] = make_int4(a[0], a[1], a[2], a[3]);
-            v[2 * q + 1] = make_int4(a[4], a[5], a[6], a[7]);
-        }
-    }
-}
-
-// Relevance test of the filter: relrev holds the pattern's activity set bit-reversed (bit 31 - a <=> activity a), so
-// `relrev << a` moves activity a's bit to the top and one funnel shift pushes it into the survivor mask: two
-// instructions per event.  shl.b32 clamps shift amounts above 31, so a masked-out slot (a = -1) pushes 0.
-__device__ __forceinline__ uint32_t rel_push32(uint32_t pend, uint32_t relrev, int a) {
-    uint32_t t;
-    asm("shl.b32 %0, %1, %2;" : "=r"(t) : "r"(relrev), "r"(a));
-    return __funnelshift_r(t, pend, 31);
-}
-// activities 0..31 in relrev_a, 32..63 in relrev_b
-__device__ __forceinline__ uint32_t rel_push64(uint32_t pend, uint32_t relrev_a, uint32_t relrev_b, int a) {
-    uint32_t t;
-    const uint32_t w = ((unsigned)a < 32u) ? relrev_a : (((unsigned)a < 64u) ? relrev_b : 0u);
-    asm("shl.b32 %0, %1, %2;" : "=r"(t) : "r"(w), "r"(a & 31));
-    return __funnelshift_r(t, pend, 31);
-}
-
-// Class bit-planes of 32 consecutive events (bit i = event i), last event first.
-template <int NPL, bool WIDE>
-__device__ __forceinline__ void scan_block(const DetectParams& P, const int4 (&v)[8], uint32_t (&pl)[3]) {
-#pragma unroll
-    for (int q = 7; q >= 0; --q) {
-        const int a[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-#pragma unroll
-        for (int i = 3; i >= 0; --i) {
-#pragma unroll
-            for (int p = 0; p < NPL; ++p)
-                pl[p] = WIDE ? rel_push64(pl[p], P.relrev[p][0], P.relrev[p][1], a[i]) : rel_push32(pl[p], P.relrev[p][0], a[i]);
-        }
-    }
-}
-
-// EventTs.transformSaseEvent: (int)((t - minTs) / 1000), truncating long division (J/model/Events/EventTs.java:54).
-// Differences below 2^32 ms (49 days) take a 32-bit multiply-high instead of the emulated 64-bit division.
-__device__ __forceinline__ int rel_seconds(long long diff_ms) {
-    if ((unsigned long long)diff_ms < (1ull << 32)) return (int)((uint32_t)diff_ms / 1000u);
-    return (int)(diff_ms / 1000);
-}
-
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // Shared memory of one warp (all arrays lane-transposed: element i of lane l at [i * 32 + l]).
 template <int W, int R, int NF, bool SMEM_RUNS>
@@ -536,174 +404,6 @@ __global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4)
     }
 }
 
-// ---------------------------------------------------------------------------------- K1-P: class NK over raw position slots
-// For NFAs of class NK (detect_fast.cuh) whose first-largest occurrence is asked for and whose predicates read no
-// relative seconds, nothing has to be compacted or staged: the trace is addressed by its raw position slots.  One lane
-// per trace streams the trace's 32-byte sectors (at most 64 slots from the sector of its first event: up to 7 slots of
-// the previous trace, then the trace), keeps the class bit-planes of the 64 slots in registers, combines them into one
-// 64-bit mask per NFA state (minterm of the class number, OR-ed into every state that owns the class) and runs the
-// greedy walks on those masks; the index in the filtered list, which the EventTs route calls `position`, is the
-// popcount of the relevant-slot mask below a slot.  No shared memory, no second pass, no per-event loop after the
-// plane scan.  Traces that do not fit 64 slots go to the overflow list and re-run on the staged kernel above.
-// Output and counters are those of detect_kernel (phase C), so the placement kernels below serve both.
-#ifndef SIESTA_NKP_MIN_CTAS
-#define SIESTA_NKP_MIN_CTAS 6   // 80 registers (a few spills in the scan): measured 0.584 ms vs 0.601 ms with 5 on the configs[4] shape
-#endif
-template <int NPL, bool WIDE, bool EVT>
-__global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ DevNfa nfa) {
-    typedef MaskX<2> MO;
-    typedef unsigned long long mask_t;
-    const int lane = threadIdx.x & 31;
-    constexpr bool evt_pos = EVT;
-    const bool all_cols = (P.flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
-    const bool first_only = (P.flags & SIESTA_F_COUNT_MATCHES) == 0;  // monotone walks: the first completed start wins
-
-    const long long n_work = P.n_work_dev ? (long long)__ldg(P.n_work_dev) : (long long)P.n_work;
-    const long long n_tiles = (n_work + 31) / 32;
-    long long tile = 0;
-    if (lane == 0) tile = (long long)atomicAdd(P.counters + P.tile_slot, 1ull);
-    tile = shfl_i64(tile, 0);
-    unsigned long long acc_occ = 0, acc_ev = 0, acc_emit = 0;  // totals, flushed once per warp (see detect_kernel)
-    while (tile < n_tiles) {
-        long long next_tile = 0;
-        if (lane == 0) next_tile = (long long)atomicAdd(P.counters + P.tile_slot, 1ull);
-        const int64_t wi = tile * 32 + lane;
-        int64_t ci = -1, t = -1;
-        long long o0 = 0, o1 = 0;
-        if (wi < n_work) {
-            ci = P.work ? P.work[wi] : wi;
-            t = P.cand ? P.cand[ci] : ci;
-            o0 = P.trace_off[t];
-            o1 = P.trace_off[t + 1];
-        }
-        const long long e0 = o0 & ~7LL;
-        const int lead = (int)(o0 - e0);
-        const long long span = (o1 - o0) + lead;  // slots the trace needs
-        const bool fits = span <= 64;
-        const long long o1s = fits ? o1 : o0;     // a trace that does not fit is not read here
-        int4 v0[8], v1[8];
-        load_sectors(P, e0, o0, o1s, v0);
-        load_sectors(P, e0 + 32, o0, o1s, v1);
-        uint32_t pa[3] = {0u, 0u, 0u}, pb[3] = {0u, 0u, 0u};
-        scan_block<NPL, WIDE>(P, v0, pa);
-        if (__any_sync(0xffffffffu, fits && span > 32)) scan_block<NPL, WIDE>(P, v1, pb);
-        mask_t valid = 0;
-        if (fits && o1 > o0) valid = (span == 64 ? ~0ull : ((1ull << (int)span) - 1ull)) & ~((1ull << lead) - 1ull);
-        mask_t pl[3];
-#pragma unroll
-        for (int p = 0; p < 3; ++p) pl[p] = p < NPL ? (((mask_t)pa[p] | ((mask_t)pb[p] << 32)) & valid) : 0ull;
-        const mask_t R = pl[0] | pl[1] | pl[2];
-        // state masks: class c (1..7) = minterm of the planes; cls_word[c] bit k <=> class c belongs to state k
-        mask_t M[8];
-#pragma unroll
-        for (int c = 1; c < 8; ++c) {
-            M[c] = 0;
-            if (c < (1 << NPL)) {
-                mask_t m = R;
-#pragma unroll
-                for (int p = 0; p < NPL; ++p) m &= ((c >> p) & 1) ? pl[p] : ~pl[p];
-                M[c] = m;
-            }
-        }
-        mask_t T[SIESTA_MAX_STATES + 1];
-#pragma unroll
-        for (int k = 0; k <= SIESTA_MAX_STATES; ++k) {
-            T[k] = 0;
-            if (k < nfa.n_states) {  // uniform
-#pragma unroll
-                for (int c = 1; c < (1 << NPL); ++c)
-                    if (P.cls_word[c] & (1u << k)) T[k] |= M[c];
-            }
-        }
-
-        int status = ST_NONE;
-        unsigned n_emitted = 0;
-        mask_t best = 0;
-        if (ci >= 0 && o1 > o0) {
-            if (!fits) status = ST_OVF;
-            else if (R && nkp_eval<EVT>(nfa, R, lead, T, best, n_emitted, first_only)) status = ST_MATCH;
-        }
-
-        // ------------------------------------------------------------------ output: as phase C of detect_kernel
-        const unsigned my_occ = status == ST_MATCH ? 1u : 0u;
-        const unsigned my_ev = status == ST_MATCH ? (unsigned)MO::popc(best) : 0u;
-        unsigned i0 = my_occ, i1 = my_ev;
-        unsigned long long i2 = (status == ST_MATCH) ? n_emitted : 0u;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned y0 = __shfl_up_sync(0xffffffffu, i0, d), y1 = __shfl_up_sync(0xffffffffu, i1, d);
-            const unsigned long long y2 = __shfl_up_sync(0xffffffffu, i2, d);
-            if (lane >= d) { i0 += y0; i1 += y1; i2 += y2; }
-        }
-        // the staging place of the tile is fixed: no atomic on the critical path, totals are flushed after the last tile
-        acc_occ += i0;
-        acc_ev += i1;
-        acc_emit += i2;
-        const unsigned tot1 = __shfl_sync(0xffffffffu, i1, 31);
-        const long long base1 = P.fix_ev + tile * 32 * P.fix_np;
-        const long long occ_at = (long long)ci;
-        const long long ev_at = base1 + (long long)(i1 - my_ev);
-        const bool stage_ok = true;
-        if (ci >= 0) {
-            P.d_cnt[ci] = my_occ | (my_ev << 16);
-            if (status == ST_MATCH) {
-                P.d_stage[ci] = ev_at;
-            } else if (status == ST_OVF) {
-                const unsigned long long at = atomicAdd(P.counters + P.ovf_slot, 1ull);
-                P.ovf_list[at] = ci;
-            }
-        }
-        if (stage_ok && tot1 > 0) {
-            // first event of the filtered list (Utils.java:51-53): base of the relative seconds of the EventTs route
-            long long t0ms = 0;
-            if (status == ST_MATCH) {
-                if (all_cols && !evt_pos) t0ms = __ldg(reinterpret_cast<const long long*>(P.ts_ms) + o0 + (MO::lo(R) - lead));
-            }
-            for (unsigned f0 = 0; f0 < tot1; f0 += 32) {
-                const unsigned f = f0 + lane;
-                int lo = 0, hi = 31;
-#pragma unroll
-                for (int it = 0; it < 5; ++it) {
-                    const int mid = (lo + hi) >> 1;
-                    const unsigned vmid = __shfl_sync(0xffffffffu, i1, mid);
-                    if (vmid > f) hi = mid; else lo = mid + 1;
-                }
-                const int owner = lo & 31;
-                const unsigned o_incl = __shfl_sync(0xffffffffu, i1, owner);
-                const unsigned o_ev = __shfl_sync(0xffffffffu, my_ev, owner);
-                mask_t m = (mask_t)shfl_i64((long long)best, owner);
-                const mask_t o_R = (mask_t)shfl_i64((long long)R, owner);
-                const long long o_o0 = shfl_i64(o0, owner);
-                const long long o_t0 = shfl_i64(t0ms, owner);
-                if (f < tot1) {
-                    int k = (int)(f - (o_incl - o_ev));  // k-th event of the owner's occurrence
-                    for (; k > 0; --k) m &= m - 1;
-                    const int j = MO::lo(m);
-                    const int src = j - (int)(o_o0 & 7);
-                    const long long at = base1 + f;
-                    P.s_ev_pos[at] = src;
-                    if (all_cols) {
-                        P.s_ev_rank[at] = MO::popc(o_R & MO::below(j));
-                        P.s_ev_act[at] = __ldg(P.act + o_o0 + src);
-                        const long long raw = __ldg(reinterpret_cast<const long long*>(P.ts_ms) + o_o0 + src);
-                        // SaseEvent.getEventBoth: timestamp * 1000 + minTs (SaseEvent.java:94-106)
-                        P.s_ev_ts[at] = evt_pos ? raw : (long long)rel_seconds(raw - o_t0) * 1000 + o_t0;
-                    }
-                }
-            }
-        }
-        tile = shfl_i64(next_tile, 0);
-    }
-    if (lane == 31) {
-        if (acc_occ) {
-            atomicAdd(P.counters + 0, acc_occ);
-            atomicAdd(P.counters + 6, acc_occ);  // one occurrence per matching trace
-        }
-        if (acc_ev) atomicAdd(P.counters + 1, acc_ev);
-        if (acc_emit) atomicAdd(P.counters + 2, acc_emit);
-    }
-}
-
 // Final placement.  The dense per-candidate counts (d_nocc, d_nev) are scanned in three levels
 // (per-block sums -> chunks of 1024 block sums -> chunk sums, + the in-block scan inside the gather), and the
 // gather copies each matching trace's staged occurrences to its final, trace-ordered position.
@@ -973,26 +673,6 @@ int launch_detect(const Ctx* ctx, cudaStream_t stream, DetectParams P, const Dev
     return SIESTA_OK;
 }
 
-template <int NPL, bool WIDE, bool EVT>
-int launch_nkp(const Ctx* ctx, cudaStream_t stream, const DetectParams& P, const DevNfa& nfa) {
-    auto kern = detect_nkp_kernel<NPL, WIDE, EVT>;
-    int per_sm = 0;
-    SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, 0));
-    if (per_sm < 1) per_sm = 1;
-    if (const char* env = std::getenv("SIESTA_K1_CTAS_PER_SM")) {  // tuning aid: cap on resident CTAs per SM
-        const int v = std::atoi(env);
-        if (v >= 1 && v < per_sm) per_sm = v;
-    }
-    const int64_t n_tiles = (P.n_work + 31) / 32;
-    const int64_t ctas_needed = (n_tiles + NT / 32 - 1) / (NT / 32);
-    int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)ctx->sm_count * per_sm);
-    if (grid < 1) grid = 1;
-    kern<<<grid, NT, 0, stream>>>(P, nfa);
-    SIESTA_LAUNCHED();
-    SIESTA_CUDA_OK(cudaGetLastError());
-    return SIESTA_OK;
-}
-
 }  // namespace
 
 // A verification request between its two halves (siesta_detect_device_begin / _finish): everything the second half
@@ -1081,14 +761,21 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
     };
     // class NK, first-largest only, no relative seconds: the raw-slot kernel K1-P goes first (its overflow list feeds
     // the staged kernel).  Decided before the scratch is carved: it needs a second overflow list.
-    int n_cls = 0;
-    for (size_t a = 0; a < lut.size(); ++a) n_cls += lut[a] != 0;
-    const int alpha_mode = !log->act_valid ? 2 : (n_cls > 7 ? 2 : (log->n_activities <= 32 ? 0 : (log->n_activities <= 64 ? 1 : 2)));
-    const bool use_nkp = dn.fast_class == FAST_NK && !return_all && !needs_ts && alpha_mode != 2 &&
-                         std::getenv("SIESTA_K1_NO_NKP") == nullptr;
+    // K1-P numbers CLASSES by state-membership signature (activities of one `or` state share a class), so more patterns
+    // fit three planes than with one class per activity; it re-reads the activity id of the few reported events.
+    NkwProgram prog;
+    const int nkw_space = nkw_build(dn, flags, &prog);
+    std::vector<uint16_t> sigs;   // distinct signatures, class c = sigs[c - 1]
+    for (size_t a = 0; a < lut.size(); ++a) {
+        const uint16_t sg = lut[a] & 0xFFu;
+        if (sg && std::find(sigs.begin(), sigs.end(), sg) == sigs.end()) sigs.push_back(sg);
+    }
+    const bool use_nkp = nkw_space != NKW_NONE && !needs_ts && log->act_valid && log->n_activities <= 1023 && !sigs.empty() && sigs.size() <= 7 &&
+                         (reinterpret_cast<uintptr_t>(log->d_act) & 15u) == 0 && std::getenv("SIESTA_K1_NO_NKP") == nullptr;
     const size_t n_reg = use_nkp ? 2 : 1;  // staging regions: [0, cap) by atomics (staged kernels), [cap, 2 cap) fixed tile slots (K1-P)
     const size_t n_blk = (nn + GT - 1) / GT;
     const size_t o_ovf2 = use_nkp ? carve(nn * 8) : 0;
+    const size_t o_nlut = use_nkp ? carve((size_t)(log->n_activities + 1) * 16) : 0;
     const size_t o_lut = carve(lut.size() * sizeof(uint16_t)), o_nocc = carve(nn * 4), o_stage = carve(nn * 8),
                  o_stage_occ = carve(return_all ? nn * 8 : 0), o_counters = carve(32 * 8), o_err = carve(nn * 8), o_ovf = carve(nn * 8),
                  o_blk = carve(n_blk * 3 * 8), o_top = carve(((n_blk + 1023) / 1024) * 3 * 8), o_occ_nev = carve(return_all ? (size_t)cap_occ * 4 : 0), o_pos = carve((size_t)cap_ev * 4 * n_reg);
@@ -1192,18 +879,23 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
             N.tile_slot = 18;
             N.fix_ev = cap_ev;
             N.fix_np = std::max(1, n_positive);
-            const bool evt = (flags & SIESTA_F_EVT_POS) != 0;
-            auto go = [&](auto npl, auto wide) {
-                constexpr int NPL = decltype(npl)::value;
-                constexpr bool WIDE = decltype(wide)::value;
-                return evt ? launch_nkp<NPL, WIDE, true>(ctx, stream, N, dn) : launch_nkp<NPL, WIDE, false>(ctx, stream, N, dn);
-            };
-            typedef std::integral_constant<int, 1> I1;
-            typedef std::integral_constant<int, 2> I2;
-            typedef std::integral_constant<int, 3> I3;
-            if (P.alpha_mode == 0) rc = P.n_planes == 1 ? go(I1(), std::false_type()) : (P.n_planes == 2 ? go(I2(), std::false_type()) : go(I3(), std::false_type()));
-            else rc = P.n_planes == 1 ? go(I1(), std::true_type()) : (P.n_planes == 2 ? go(I2(), std::true_type()) : go(I3(), std::true_type()));
-            if (rc) return rc;
+            // the scan's table: {m, b0, b1, b2} per activity (detect_nkp.cu); class c = index of the signature + 1
+            std::vector<uint32_t> nlut((size_t)(log->n_activities + 1) * 4, 0u);
+            std::memset(N.cls_word, 0, sizeof(N.cls_word));
+            for (int a = 0; a <= log->n_activities; ++a) {
+                const uint16_t sg = a < log->n_activities ? (lut[a] & 0xFFu) : 0;
+                int c = 0;
+                if (sg) {
+                    c = (int)(std::find(sigs.begin(), sigs.end(), sg) - sigs.begin()) + 1;
+                    N.cls_word[c] = sg;
+                }
+                nlut[4 * a + 0] = (nkw_space == NKW_RAW || c) ? 2u : 1u;
+                for (int p = 0; p < 3; ++p) nlut[4 * a + 1 + p] = (c >> p) & 1;
+            }
+            SIESTA_CUDA_OK(cudaMemcpyAsync(wb + o_nlut, nlut.data(), nlut.size() * 4, cudaMemcpyHostToDevice, stream));
+            N.nkp_lut = reinterpret_cast<const uint4*>(wb + o_nlut);
+            N.n_planes = sigs.size() <= 1 ? 1 : (sigs.size() <= 3 ? 2 : 3);
+            if ((rc = launch_nkp(ctx, stream, N, prog, nkw_space))) return rc;
             // the staged kernel below re-runs the traces that did not fit 64 slots (count read from the device)
             P.work = N.ovf_list;
             P.n_work_dev = b_counters.as<unsigned long long>() + 13;

@@ -365,145 +365,131 @@ SIESTA_HD __forceinline__ bool nk_eval(const DevNfa& nfa, const EV& ev, const ty
     return true;
 }
 
-// ------------------------------------------------------------------------------- class NK over raw position slots
-// The same greedy walk and selection as nk_walk / nk_eval, specialised for kernel K1-P: events are single bits of the
-// 64 raw slots (no slot index is ever materialised: `b - 1` is the mask below bit b), the attributes of the event taken
-// for state k are kept as byte k of two packed words (attribute values are below 64 here), and the route is a template
-// parameter.  Attributes after Utils.transformToSaseEvents (J/model/Utils/Utils.java:48-65): EventTs route position =
-// index in the filtered list = popcount of the relevant slots below the event; EventPos route position = in-trace
-// position = slot - lead, timestamp = index in the filtered list.  (EventTs-route time predicates never come here.)
-// NK class invariant (classify_fast): every predicate references an earlier POSITIVE state, so the "reference to the
-// current state is true" rule of PredicateOptimized.java:331-340 never applies.
-template <bool EVT>
-struct NkpWalk {
-    typedef unsigned long long u64;
-    const DevNfa& nfa;
-    u64 R;
-    int lead;
-    u64 v0, v1;  // byte k: position / timestamp attribute of the event taken for state k
-    // Two facts about consecutive starts of one trace (walks are monotone, see the header of this file):
-    //  exhausted   a walk found NO later event of a state's types at all: every later start stands even further right,
-    //              so no later start completes either;
-    //  memo        a walk took event e1 for the first positive state after state 0 and failed afterwards; if no predicate
-    //              of a later state references state 0, the rest of a walk depends on e1 alone, so the next start that
-    //              takes the same e1 fails as well (first events never move left, so remembering the last e1 is enough).
-    bool exhausted, memo_ok, memo_failed;
-    u64 memo_e1;
-    SIESTA_HD __forceinline__ NkpWalk(const DevNfa& n, u64 r, int l)
-        : nfa(n), R(r), lead(l), v0(0), v1(0), exhausted(false), memo_ok(true), memo_failed(false), memo_e1(0) {
-        const int ks1 = (n.n_states > 1 && n.kind[1] == SIESTA_STATE_NEGATIVE) ? 2 : 1;
-#pragma unroll
-        for (int s = 0; s < SIESTA_MAX_STATES; ++s)
-#pragma unroll
-            for (int k = 0; k < SIESTA_MAX_PREDS; ++k)
-                if (s > ks1 && s < n.n_states && k < n.n_preds[s] && n.p_ref[s][k] == 0) memo_ok = false;
+// ------------------------------------------------------------------------- class NK as window walks (kernel K1-P)
+// Kernel K1-P addresses a trace's events by ONE index space in which every attribute the NFA's predicates read IS the
+// bit index of the event:
+//   rank space (32-bit masks): bit r = the r-th event of the list filtered to the pattern's types.  After
+//       Utils.transformToSaseEvents (J/model/Utils/Utils.java:48-65) that index is `position` on the EventTs route
+//       (Utils.java:54-57) and `timestamp` on the EventPos route (Utils.java:59-62).
+//   raw space (64-bit masks): bit j = position slot j of the trace (slot = in-trace position + lead, lead = events of
+//       the previous trace in the first 32-byte sector); `position` on the EventPos route is slot - lead, and the lead
+//       cancels on both sides of a predicate.
+// A predicate `attr(e) <= attr($ref) + c` (SIESTAPattern.java:136-145) then says "e lies below bit idx(ref) + c + 1",
+// `>=` says "e lies at or above bit idx(ref) + c": each predicate is a WINDOW mask built with one shift, and the first
+// later event of a state's types that passes all predicates (the greedy step of class NK, header of this file) is the
+// lowest set bit of `T[k] & above(previous) & windows` - no loop over candidate events, no popcount.  At a negative
+// state the run moves on with the first passing event of the next state's types unless a passing event of the negative
+// type lies before it (Engine.java:679-682, 1165-1180); an event of the negative type is never taken for the next state
+// (nk_walk tests the negative type first).  nkw_build (nfa.cpp) decides the space, or that the NFA needs relative
+// seconds / mixes attributes and stays on the staged kernel.
+template <class MT>
+struct NkwBits;
+template <>
+struct NkwBits<uint32_t> {
+    // 1 << n, and 0 once n reaches the width (PTX shl clamps the amount; C++ leaves it undefined)
+    static SIESTA_HD __forceinline__ uint32_t one_shl(int n) {
+#ifdef __CUDA_ARCH__
+        uint32_t r;
+        asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"(n));
+        return r;
+#else
+        return n >= 32 ? 0u : 1u << n;
+#endif
     }
-    SIESTA_HD __forceinline__ void attrs(u64 b, int& a0, int& a1) const {
-        const int r = popc64(R & (b - 1));
-        a0 = EVT ? popc64(b - 1) - lead : r;
-        a1 = EVT ? r : 0;
+    static SIESTA_HD __forceinline__ int idx(uint32_t b) { return 31 - clz32(b); }   // index of an isolated bit
+    static SIESTA_HD __forceinline__ int popc(uint32_t m) { return popc32(m); }
+};
+template <>
+struct NkwBits<unsigned long long> {
+    static SIESTA_HD __forceinline__ unsigned long long one_shl(int n) {
+#ifdef __CUDA_ARCH__
+        unsigned long long r;
+        asm("shl.b64 %0, 1, %1;" : "=l"(r) : "r"(n));
+        return r;
+#else
+        return n >= 64 ? 0ull : 1ull << n;
+#endif
     }
-    SIESTA_HD __forceinline__ bool preds(int s, u64 b) const {
-        const int np = nfa.n_preds[s];
-        if (np == 0) return true;
-        int a0, a1;
-        attrs(b, a0, a1);
-        bool ok = true;
+    static SIESTA_HD __forceinline__ int idx(unsigned long long b) { return 63 - clz64(b); }
+    static SIESTA_HD __forceinline__ int popc(unsigned long long m) { return popc64(m); }
+};
+
+template <class MT>
+struct NkwWalk {
+    typedef NkwBits<MT> B;
+    // events that pass every predicate of state s, given the indices taken so far (byte k of vv = state k's event)
+    static SIESTA_HD __forceinline__ MT window(const NkwProgram& P, int s, unsigned long long vv) {
+        MT w = ~(MT)0;
 #pragma unroll
-        for (int k = 0; k < SIESTA_MAX_PREDS; ++k) {
-            if (k < np) {
-                const bool is_pos = nfa.p_attr[s][k] == SIESTA_ATTR_POSITION;
-                const int sh = 8 * nfa.p_ref[s][k];
-                const long long lhs = is_pos ? a0 : a1;
-                const long long rhs = (long long)(((is_pos ? v0 : v1) >> sh) & 0xFFull) + nfa.p_c[s][k];
-                ok = ok && (nfa.p_op[s][k] == SIESTA_OP_LE ? lhs <= rhs : lhs >= rhs);
+        for (int j = 0; j < SIESTA_MAX_PREDS; ++j) {
+            if (j < P.n_preds[s]) {
+                const int n = (int)((vv >> P.sh[s][j]) & 0xFFull) + P.cc[s][j];
+                const MT below = B::one_shl(n) - 1;
+                w &= P.le[s][j] ? below : ~below;
             }
         }
-        return ok;
+        return w;
     }
-    SIESTA_HD __forceinline__ void take(int s, u64 b) {
-        int a0, a1;
-        attrs(b, a0, a1);
-        v0 |= (u64)(unsigned)a0 << (8 * s);
-        if (EVT) v1 |= (u64)(unsigned)a1 << (8 * s);
-    }
-    // run started at the event with bit sb: its events as a mask, 0 = never completes / deleted at a negative state
-    SIESTA_HD __forceinline__ u64 walk(const u64* T, u64 sb) {
-        return walk_on([T](int k) { return T[k]; }, sb);
-    }
-    // tget(k) = mask of state k's events (k <= SIESTA_MAX_STATES; registers or, for a walk done on behalf of another
-    // lane's trace, shared memory)
-    template <class TGet>
-    SIESTA_HD __forceinline__ u64 walk_on(const TGet& tget, u64 sb) {
-        const int S = nfa.n_states;
-        v0 = v1 = 0;
-        if (nfa.need_vv) take(0, sb);
-        u64 taken = sb, pb = sb;
+    // run started at the event with bit sb: its events as a mask, 0 = it never completes / is deleted at a negative
+    // state.  exhausted: no later event of some state's types exists at all, whatever the predicates say; walks are
+    // monotone (header of this file), so no later start completes either.
+    static SIESTA_HD __forceinline__ MT walk(const NkwProgram& P, const MT* T, MT sb, bool& exhausted) {
+        unsigned long long vv = (unsigned long long)B::idx(sb);
+        MT taken = sb, pb = sb;
         int k_next = 1;
 #pragma unroll
         for (int k = 1; k < SIESTA_MAX_STATES; ++k) {
-            if (k >= S) break;
+            if (k >= P.n_states) break;
             if (k != k_next) continue;
-            const bool neg = nfa.kind[k] == SIESTA_STATE_NEGATIVE;
-            const u64 Tk = tget(k);
-            u64 c = (neg ? (Tk | tget(k + 1)) : Tk) & ~(pb | (pb - 1));
-            if (!c) {
-                exhausted = true;
-                return 0;
-            }
-            u64 got = 0;
-            while (c) {
-                const u64 eb = c & (0ull - c);
-                c ^= eb;
-                if (neg) {
-                    if (Tk & eb) {
-                        if (preds(k, eb)) return 0;     // containsNegative: deleted (Engine.java:679-682)
-                    } else if (preds(k + 1, eb)) {      // Engine.checkPredicatesForNextState :1165-1180
-                        got = eb;
-                        break;
-                    }
-                } else if (preds(k, eb)) {
-                    got = eb;
-                    break;
+            const MT after = ~(pb | (pb - 1));
+            MT got;
+            int ks = k;
+            if (P.neg[k]) {
+                ks = k + 1;
+                const MT cy0 = T[k + 1] & ~T[k] & after;
+                const MT cy = cy0 & window(P, k + 1, vv);
+                if (!cy) {
+                    exhausted = exhausted || !cy0;
+                    return 0;
                 }
+                got = cy & ((MT)0 - cy);
+                if (T[k] & after & (got - 1) & window(P, k, vv)) return 0;   // containsNegative: deleted (Engine.java:679-682)
+            } else {
+                const MT c0 = T[k] & after;
+                const MT c = c0 & window(P, k, vv);
+                if (!c) {
+                    exhausted = exhausted || !c0;
+                    return 0;
+                }
+                got = c & ((MT)0 - c);
             }
-            if (!got) return 0;
-            const int ks = neg ? k + 1 : k;
-            if (k == 1) {  // the first event after the start
-                if (memo_ok && memo_failed && got == memo_e1) return 0;
-                memo_e1 = got;
-                memo_failed = true;   // until this walk completes
-            }
-            if (nfa.need_vv) take(ks, got);
+            vv |= (unsigned long long)B::idx(got) << (8 * ks);
             taken |= got;
             pb = got;
             k_next = ks + 1;
         }
-        memo_failed = false;
         return taken;
     }
 };
 
 // first-largest occurrence = smallest (completion, start); first_only as in nk_eval
-template <bool EVT>
-SIESTA_HD __forceinline__ bool nkp_eval(const DevNfa& nfa, unsigned long long R, int lead, const unsigned long long* T,
-                                        unsigned long long& best, unsigned& n_emitted, bool first_only) {
-    typedef unsigned long long u64;
-    const int S = nfa.n_states;
+template <class MT>
+SIESTA_HD __forceinline__ bool nkw_eval(const NkwProgram& P, const MT* T, MT& best, unsigned& n_emitted, bool first_only) {
+    typedef NkwBits<MT> B;
     n_emitted = 0;
     best = 0;
 #pragma unroll
     for (int k = 0; k < SIESTA_MAX_STATES; ++k)
-        if (k < S && nfa.kind[k] != SIESTA_STATE_NEGATIVE && T[k] == 0) return false;
-    NkpWalk<EVT> w(nfa, R, lead);
+        if (k < P.n_states && !P.neg[k] && T[k] == 0) return false;
+    bool exhausted = false;
     int best_c = 0;
-    for (u64 r = T[0]; r && !w.exhausted;) {
-        const u64 sb = r & (0ull - r);
+    for (MT r = T[0]; r && !exhausted;) {
+        const MT sb = r & ((MT)0 - r);
         r ^= sb;
-        const u64 m = w.walk(T, sb);
+        const MT m = NkwWalk<MT>::walk(P, T, sb, exhausted);
         if (!m) continue;
         ++n_emitted;
-        const int c = 63 - clz64(m);
+        const int c = B::idx(m);   // clz of the whole mask: its highest event
         if (!best || c < best_c) { best = m; best_c = c; }
         if (first_only) break;
     }

@@ -1,0 +1,310 @@
+// detect_nkp.cu — kernel K1-P: class NK (no Kleene state) as window walks over one index space (sm_100a).
+//
+// Replaces, for NFAs of class NK whose first-largest occurrence is asked for and whose predicates read no relative
+// seconds, SaseConnector.evaluate + Occurrences.clearOccurrences(false)
+// (J/SaseConnection/SaseConnector.java:48-76, J/model/Occurrences.java:58-72); derivation in detect_fast.cuh.
+//
+// One lane per trace, no shared memory, no per-event loop after the scan:
+//   scan     the lane streams the trace's 32-byte sectors (<= 64 position slots from the sector of its first event; all
+//            sixteen 128-bit loads are issued before the first is used) and pushes every activity id through the class
+//            bit-planes with shift instructions.  Rank space (NKW_RANK): a slot pushes its plane bits only if it holds
+//            an event of the pattern (funnel shift by 0 or 1), so the planes come out COMPACTED to the filtered list -
+//            bit r = r-th relevant event, 32-bit masks, and `position` (EventTs route) / `timestamp` (EventPos route)
+//            of an event is its bit index.  Raw space (NKW_RAW): one bit per slot, 64-bit masks, `position` of the
+//            EventPos route is the slot.
+//   compose  class c = minterm of the planes (one LOP3 each); state k's mask = OR of its classes (uniform branches)
+//   walk     NkwWalk: per state one AND of {state mask, above(previous event), predicate windows} and a lowest-set-bit;
+//            the first start whose walk completes is the first-largest occurrence (monotone walks)
+//   output   fixed staging slots per tile (no atomic on the critical path), the tile's events written as one flat
+//            coalesced stream; the placement kernels of detect.cu order them by trace
+// Traces that do not fit (more than 64 slots, or more than 32 relevant events in rank space) go to the overflow list
+// and re-run on the staged kernel, launched unconditionally with its work count read from the device.
+#include "detect_common.cuh"
+
+namespace siesta {
+
+#ifndef SIESTA_NKP_MIN_CTAS
+#define SIESTA_NKP_MIN_CTAS 6
+#endif
+
+// The scan.  Every activity id indexes a 16-byte table entry {m, b0, b1, b2} in shared memory (one LDS.128, entry
+// n_act = "no event": slots outside the trace) and every plane is advanced with ONE integer multiply-add,
+//     plane_p = plane_p * m + b_p,
+// which runs on the FMA pipe: shifts and logic ops share the ALU pipe, which takes one warp instruction every two
+// cycles, and the walks need that pipe.  Rank space: m = 2 and b_p = plane bit for an activity of the pattern, m = 1 and
+// b_p = 0 otherwise - a slot pushes its bits only if it holds a relevant event, so the planes come out compacted to
+// the filtered list; the raw relevance mask is advanced as r = 2 r + m (after 32 pushes r + 1 is the mask: each push
+// adds m - 1 = the relevance bit plus a constant that sums to 2^32 - 1).  Raw space: m = 2 for every entry.
+template <int NPL, bool RAW>
+__device__ __forceinline__ void scan32(const uint4* __restrict__ lut, const int4 (&v)[8], uint32_t (&pl)[3], uint32_t& racc) {
+#pragma unroll
+    for (int q = 7; q >= 0; --q) {   // last slot first: bit 0 = first slot / first relevant event
+        const int a[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+        for (int i = 3; i >= 0; --i) {
+            const uint4 w = lut[a[i]];
+            pl[0] = pl[0] * w.x + w.y;
+            if (NPL > 1) pl[1] = pl[1] * w.x + w.z;
+            if (NPL > 2) pl[2] = pl[2] * w.x + w.w;
+            if (!RAW) racc = racc * 2u + w.x;
+        }
+    }
+}
+
+// index of the r-th set bit of x (0-based; r < popc(x)): binary search over popcounts, branch-free
+__device__ __forceinline__ int select32(uint32_t x, int r) {
+    int pos = 0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const int c = __popc((x >> pos) & ((1u << w) - 1u));
+        if (r >= c) {
+            r -= c;
+            pos += w;
+        }
+    }
+    return pos;
+}
+__device__ __forceinline__ int select64(unsigned long long x, int r) {
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    const int c = __popc(lo);
+    return r >= c ? 32 + select32(hi, r - c) : select32(lo, r);
+}
+
+template <int NPL, bool RAW>
+__global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ NkwProgram prog) {
+    typedef typename std::conditional<RAW, unsigned long long, uint32_t>::type mask_t;
+    typedef unsigned long long u64;
+    typedef NkwBits<mask_t> B;
+    const int lane = threadIdx.x & 31;
+    extern __shared__ uint4 s_lut[];   // [n_act + 1]
+    for (int i = threadIdx.x; i <= P.n_act; i += blockDim.x) s_lut[i] = P.nkp_lut[i];
+    __syncthreads();
+    const bool evt_pos = (P.flags & SIESTA_F_EVT_POS) != 0;
+    const bool all_cols = (P.flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
+    const bool first_only = (P.flags & SIESTA_F_COUNT_MATCHES) == 0;  // monotone walks: the first completed start wins
+
+    const long long n_work = P.n_work_dev ? (long long)__ldg(P.n_work_dev) : (long long)P.n_work;
+    const long long n_tiles = (n_work + 31) / 32;
+    const int batch = P.tile_batch;
+    // Tiles are handed out by an atomic counter (a CTA that starts late because a collective or a copy holds its SM
+    // takes fewer), `batch` consecutive tiles per atomic; the next batch is requested while the current one runs.
+    long long tile = 0;
+    if (lane == 0) tile = (long long)atomicAdd(P.counters + P.tile_slot, (unsigned long long)batch);
+    tile = shfl_i64(tile, 0);
+    int left = batch;
+    long long next_tile = 0;
+    unsigned long long acc_occ = 0, acc_ev = 0, acc_emit = 0;  // totals, flushed once per warp
+    while (tile < n_tiles) {
+        if (left == batch && lane == 0) next_tile = (long long)atomicAdd(P.counters + P.tile_slot, (unsigned long long)batch);
+        const int64_t wi = tile * 32 + lane;
+        int64_t ci = -1, t = -1;
+        long long o0 = 0, o1 = 0;
+        if (wi < n_work) {
+            ci = P.work ? P.work[wi] : wi;
+            t = P.cand ? P.cand[ci] : ci;
+            o0 = P.trace_off[t];
+            o1 = P.trace_off[t + 1];
+        }
+        const long long e0 = o0 & ~7LL;
+        const int lead = (int)(o0 - e0);
+        const long long span = (o1 - o0) + lead;  // slots the trace needs
+        // a trace that needs more than 64 slots, or whose last sector crosses the end of the log, is not read here
+        bool fits = span <= 64 && ((o1 + 7) & ~7LL) <= P.n_events;
+        const long long o1s = fits ? o1 : o0;
+        int4 v0[8], v1[8];
+        load_sectors_vec(P, e0, o1s, v0);
+        load_sectors_vec(P, e0 + 32, o1s, v1);
+        u64 valid = 0;
+        if (fits && o1 > o0) valid = (span == 64 ? ~0ull : ((1ull << (int)span) - 1ull)) & ~((1ull << lead) - 1ull);
+        const bool second = __any_sync(0xffffffffu, fits && span > 32);
+
+        mask_t pl[3];
+        u64 Rv;   // slots of the trace that hold an event of the pattern
+        if constexpr (RAW) {
+            uint32_t pa[3] = {0u, 0u, 0u}, pb[3] = {0u, 0u, 0u}, unused = 0u;
+            scan32<NPL, true>(s_lut, v0, pa, unused);
+            if (second) scan32<NPL, true>(s_lut, v1, pb, unused);
+#pragma unroll
+            for (int p = 0; p < 3; ++p) pl[p] = p < NPL ? (((u64)pa[p] | ((u64)pb[p] << 32)) & valid) : 0ull;
+            Rv = pl[0] | pl[1] | pl[2];
+        } else {
+            uint32_t q[3] = {0u, 0u, 0u}, ra = 0u, rb = 0u;
+            if (second) {   // last slot first
+                scan32<NPL, false>(s_lut, v1, q, rb);
+                rb += 1u;
+            }
+            scan32<NPL, false>(s_lut, v0, q, ra);
+            ra += 1u;
+            const u64 Rraw = (u64)ra | ((u64)rb << 32);             // includes the neighbours' events in the end sectors
+            Rv = Rraw & valid;
+            const int n_lead = __popc(ra & ((1u << lead) - 1u));    // relevant events of the previous trace: ranks 0 ..
+            const int n_valid = __popcll(Rv);
+            if (n_lead + n_valid > 32) fits = false;                // the planes hold 32 ranks
+            const uint32_t keep = B::one_shl(n_valid) - 1u;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) pl[p] = p < NPL ? ((q[p] >> n_lead) & keep) : 0u;
+        }
+        // state masks: class c (1..7) = minterm of the planes; cls_word[c] bit k <=> class c belongs to state k
+        mask_t M[8];
+#pragma unroll
+        for (int c = 1; c < 8; ++c) {
+            M[c] = 0;
+            if (c < (1 << NPL)) {
+                mask_t m = ~(mask_t)0;
+#pragma unroll
+                for (int p = 0; p < NPL; ++p) m &= ((c >> p) & 1) ? pl[p] : ~pl[p];
+                M[c] = m;
+            }
+        }
+        mask_t T[SIESTA_MAX_STATES + 1];
+#pragma unroll
+        for (int k = 0; k <= SIESTA_MAX_STATES; ++k) {
+            T[k] = 0;
+            if (k < prog.n_states) {  // uniform
+#pragma unroll
+                for (int c = 1; c < (1 << NPL); ++c)
+                    if (P.cls_word[c] & (1u << k)) T[k] |= M[c];
+            }
+        }
+
+        int status = ST_NONE;
+        unsigned n_emitted = 0;
+        mask_t best = 0;
+        if (ci >= 0 && o1 > o0) {
+            if (!fits) status = ST_OVF;
+            else if (Rv && nkw_eval<mask_t>(prog, T, best, n_emitted, first_only)) status = ST_MATCH;
+        }
+
+        // ------------------------------------------------------------------ output: fixed staging slots of the tile
+        const unsigned my_occ = status == ST_MATCH ? 1u : 0u;
+        const unsigned my_ev = status == ST_MATCH ? (unsigned)B::popc(best) : 0u;
+        unsigned i1 = my_ev;
+        unsigned long long i2 = (status == ST_MATCH) ? n_emitted : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned y1 = __shfl_up_sync(0xffffffffu, i1, d);
+            if (lane >= d) i1 += y1;
+        }
+        if (!first_only) {
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long y2 = __shfl_up_sync(0xffffffffu, i2, d);
+                if (lane >= d) i2 += y2;
+            }
+        }
+        acc_occ += __popc(__ballot_sync(0xffffffffu, status == ST_MATCH));
+        acc_ev += i1;     // lane 31 holds the tile totals
+        acc_emit += i2;
+        const unsigned tot1 = __shfl_sync(0xffffffffu, i1, 31);
+        const long long base1 = P.fix_ev + tile * 32 * P.fix_np;
+        if (ci >= 0) {
+            P.d_cnt[ci] = my_occ | (my_ev << 16);
+            if (status == ST_MATCH) {
+                P.d_stage[ci] = base1 + (long long)(i1 - my_ev);
+            } else if (status == ST_OVF) {
+                const unsigned long long at = atomicAdd(P.counters + P.ovf_slot, 1ull);
+                P.ovf_list[at] = ci;
+            }
+        }
+        if (tot1 > 0) {
+            // first event of the filtered list (Utils.java:51-53): base of the relative seconds of the EventTs route
+            long long t0ms = 0;
+            if (status == ST_MATCH && all_cols && !evt_pos)
+                t0ms = __ldg(reinterpret_cast<const long long*>(P.ts_ms) + o0 + (__ffsll((long long)Rv) - 1 - lead));
+            for (unsigned f0 = 0; f0 < tot1; f0 += 32) {
+                const unsigned f = f0 + lane;
+                int lo = 0, hi = 31;
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    const int mid = (lo + hi) >> 1;
+                    const unsigned vmid = __shfl_sync(0xffffffffu, i1, mid);
+                    if (vmid > f) hi = mid; else lo = mid + 1;
+                }
+                const int owner = lo & 31;
+                const unsigned o_incl = __shfl_sync(0xffffffffu, i1, owner);
+                const unsigned o_ev = __shfl_sync(0xffffffffu, my_ev, owner);
+                mask_t m;
+                if constexpr (RAW) m = (mask_t)shfl_i64((long long)best, owner);
+                else m = __shfl_sync(0xffffffffu, best, owner);
+                const u64 o_R = (u64)shfl_i64((long long)Rv, owner);
+                const long long o_o0 = shfl_i64(o0, owner);
+                const long long o_t0 = shfl_i64(t0ms, owner);
+                if (f < tot1) {
+                    int k = (int)(f - (o_incl - o_ev));  // k-th event of the owner's occurrence
+                    for (; k > 0; --k) m &= m - 1;
+                    int j, rank;   // raw slot and index in the filtered list
+                    if constexpr (RAW) {
+                        j = __ffsll((long long)m) - 1;
+                        rank = __popcll(o_R & ((1ull << j) - 1ull));
+                    } else {
+                        rank = __ffs((int)m) - 1;
+                        j = select64(o_R, rank);
+                    }
+                    const int src = j - (int)(o_o0 & 7);
+                    const long long at = base1 + f;
+                    P.s_ev_pos[at] = src;
+                    if (all_cols) {
+                        P.s_ev_rank[at] = rank;
+                        P.s_ev_act[at] = __ldg(P.act + o_o0 + src);
+                        const long long raw = __ldg(reinterpret_cast<const long long*>(P.ts_ms) + o_o0 + src);
+                        // SaseEvent.getEventBoth: timestamp * 1000 + minTs (SaseEvent.java:94-106)
+                        P.s_ev_ts[at] = evt_pos ? raw : (long long)rel_seconds(raw - o_t0) * 1000 + o_t0;
+                    }
+                }
+            }
+        }
+        if (--left == 0) {
+            tile = shfl_i64(next_tile, 0);
+            left = batch;
+        } else {
+            ++tile;
+        }
+    }
+    if (lane == 31) {
+        if (acc_occ) {
+            atomicAdd(P.counters + 0, acc_occ);
+            atomicAdd(P.counters + 6, acc_occ);  // one occurrence per matching trace
+        }
+        if (acc_ev) atomicAdd(P.counters + 1, acc_ev);
+        if (acc_emit) atomicAdd(P.counters + 2, acc_emit);
+    }
+}
+
+namespace {
+template <int NPL, bool RAW>
+int launch_one(const Ctx* ctx, cudaStream_t stream, DetectParams P, const NkwProgram& prog) {
+    auto kern = detect_nkp_kernel<NPL, RAW>;
+    const size_t smem = (size_t)(P.n_act + 1) * sizeof(uint4);
+    int per_sm = 0;
+    SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (const char* env = std::getenv("SIESTA_K1_CTAS_PER_SM")) {  // tuning aid: cap on resident CTAs per SM
+        const int v = std::atoi(env);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
+    const int64_t n_tiles = (P.n_work + 31) / 32;
+    const int64_t ctas_needed = (n_tiles + NT / 32 - 1) / (NT / 32);
+    int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)ctx->sm_count * per_sm);
+    if (grid < 1) grid = 1;
+    // a batch of tiles per atomic once every warp has many batches to take (the tail stays balanced)
+    const int64_t per_warp = n_tiles / ((int64_t)grid * (NT / 32));
+    P.tile_batch = per_warp >= 64 ? 4 : (per_warp >= 16 ? 2 : 1);
+    if (const char* env = std::getenv("SIESTA_NKP_TILE_BATCH")) {
+        const int v = std::atoi(env);
+        if (v >= 1 && v <= 64) P.tile_batch = v;
+    }
+    kern<<<grid, NT, smem, stream>>>(P, prog);
+    SIESTA_LAUNCHED();
+    SIESTA_CUDA_OK(cudaGetLastError());
+    return SIESTA_OK;
+}
+}  // namespace
+
+int launch_nkp(const Ctx* ctx, cudaStream_t stream, const DetectParams& P, const NkwProgram& prog, int space) {
+    const bool raw = space == NKW_RAW;
+    if (P.n_planes == 1) return raw ? launch_one<1, true>(ctx, stream, P, prog) : launch_one<1, false>(ctx, stream, P, prog);
+    if (P.n_planes == 2) return raw ? launch_one<2, true>(ctx, stream, P, prog) : launch_one<2, false>(ctx, stream, P, prog);
+    return raw ? launch_one<3, true>(ctx, stream, P, prog) : launch_one<3, false>(ctx, stream, P, prog);
+}
+
+}  // namespace siesta

@@ -139,6 +139,35 @@ int validate_nfa(const siesta_nfa* nfa, uint32_t flags, DevNfa* out) {
 }
 
 
+// Kernel K1-P's window program (detect_fast.cuh).  Eligible: class NK, only the first-largest occurrence, and every
+// predicate reads the attribute that is the bit index of ONE index space:
+//   EventTs route  (Utils.java:51-58): position = index in the filtered list -> rank space; a timestamp predicate
+//                  needs relative seconds (staged kernel);
+//   EventPos route (Utils.java:59-62): timestamp = index in the filtered list -> rank space, position = in-trace
+//                  position -> raw slots; an NFA that mixes the two stays on the staged kernel.
+int nkw_build(const DevNfa& dn, uint32_t flags, NkwProgram* out) {
+    std::memset(out, 0, sizeof(*out));
+    if (dn.fast_class != 1 /* FAST_NK */ || (flags & SIESTA_F_RETURN_ALL)) return NKW_NONE;
+    const bool evt_pos = (flags & SIESTA_F_EVT_POS) != 0;
+    bool any_pos = false, any_ts = false;
+    out->n_states = dn.n_states;
+    for (int s = 0; s < dn.n_states; ++s) {
+        out->neg[s] = dn.kind[s] == SIESTA_STATE_NEGATIVE;
+        out->n_preds[s] = dn.n_preds[s];
+        for (int k = 0; k < dn.n_preds[s]; ++k) {
+            (dn.p_attr[s][k] == SIESTA_ATTR_POSITION ? any_pos : any_ts) = true;
+            const bool le = dn.p_op[s][k] == SIESTA_OP_LE;
+            const int64_t c = std::min<int64_t>(dn.p_c[s][k], 64);
+            out->le[s][k] = le;
+            out->sh[s][k] = (uint8_t)(8 * dn.p_ref[s][k]);
+            out->cc[s][k] = (uint8_t)(c + (le ? 1 : 0));
+        }
+    }
+    if (!evt_pos) return any_ts ? NKW_NONE : NKW_RANK;
+    if (any_pos && any_ts) return NKW_NONE;
+    return any_pos ? NKW_RAW : NKW_RANK;
+}
+
 // Per-activity lookup: bit k = the type belongs to state k (State.checkEventType / AdditionalState.checkEventType);
 // bit 8+k = the type is state k's first type (State.getEventType, used by Engine.java:661).
 void build_lut(const siesta_nfa* nfa, const DevNfa& dn, int32_t n_activities, uint32_t flags, std::vector<uint16_t>& lut,

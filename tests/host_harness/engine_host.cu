@@ -112,38 +112,57 @@ extern "C" int engine_host_detect(const int64_t* trace_off, const int32_t* act, 
         if (meta.empty()) continue;
         if (b1 - b0 > 65536) return SIESTA_E_UNSUPPORTED;
         unsigned emitted = 0;
-        // kernel K1-P (detect_nkp_kernel): class NK, first-largest only, no relative seconds needed, the trace fits the
-        // 64 raw position slots that start at the 32-byte sector of its first event
+        // kernel K1-P (detect_nkp_kernel): class NK as window walks in rank space (32 filtered events) or over the 64
+        // raw position slots that start at the 32-byte sector of the trace's first event (detect_fast.cuh)
         const int lead = (int)(b0 & 7);
-        if (dn.fast_class == FAST_NK && !(flags & SIESTA_F_RETURN_ALL) && !needs_ts && (b1 - b0) + lead <= 64) {
-            unsigned long long T[SIESTA_MAX_STATES + 1] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, R = 0;
-            for (uint32_t m : meta) {
-                const int slot = (int)(m >> 16) + lead;
-                R |= 1ull << slot;
-                for (int k = 0; k < SIESTA_MAX_STATES; ++k)
-                    if (m & (1u << k)) T[k] |= 1ull << slot;
-            }
-            PosEvents pe{R, lead, evt_pos};
-            unsigned long long sel[1], sel_g[1];
-            int nsel = 0;
-            unsigned emitted_g = 0;
-            const bool first_only = !(flags & SIESTA_F_COUNT_MATCHES);
-            // the kernel's specialised evaluator, cross-checked here against the generic one on the PosEvents accessor
-            const bool hit = evt_pos ? nkp_eval<true>(dn, R, lead, T, sel[0], emitted, first_only)
-                                     : nkp_eval<false>(dn, R, lead, T, sel[0], emitted, first_only);
-            const bool hit_g = nk_eval<2>(dn, pe, T, false, evt_pos, (unsigned long long*)nullptr, 0, sel_g, nsel, emitted_g, first_only);
-            if (hit != hit_g || (hit && (sel[0] != sel_g[0] || emitted != emitted_g))) {
-                siesta::set_error("nkp_eval disagrees with nk_eval<PosEvents>");
-                return -99;
+        NkwProgram prog;
+        const int space = nkw_build(dn, flags, &prog);
+        const bool first_only = !(flags & SIESTA_F_COUNT_MATCHES);
+        if (space != NKW_NONE && !needs_ts && (b1 - b0) + lead <= 64 && (space == NKW_RAW || meta.size() <= 32)) {
+            std::vector<int> sel_idx;   // the selected occurrence as indices into the filtered list
+            bool hit;
+            if (space == NKW_RANK) {
+                uint32_t T[SIESTA_MAX_STATES + 1] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, best = 0, sel_g[32], aux[32];
+                for (size_t j = 0; j < meta.size(); ++j)
+                    for (int k = 0; k < SIESTA_MAX_STATES; ++k)
+                        if (meta[j] & (1u << k)) T[k] |= 1u << j;
+                hit = nkw_eval<uint32_t>(prog, T, best, emitted, first_only);
+                // cross-check against the generic greedy walk on the filtered list (the staged kernel's evaluator)
+                TraceEvents ev{meta.data(), nullptr, 1, (int)meta.size(), evt_pos, 1};
+                int nsel = 0;
+                unsigned emitted_g = 0;
+                const bool hit_g = nk_eval<1>(dn, ev, T, false, evt_pos, aux, 1, sel_g, nsel, emitted_g, first_only);
+                if (hit != hit_g || (hit && (best != sel_g[0] || emitted != emitted_g))) {
+                    siesta::set_error("nkw_eval<rank> disagrees with nk_eval<TraceEvents>");
+                    return -99;
+                }
+                for (uint32_t m = best; m; m &= m - 1) sel_idx.push_back(__builtin_ffs((int)m) - 1);
+            } else {
+                unsigned long long T[SIESTA_MAX_STATES + 1] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, R = 0, best = 0, sel_g[1];
+                for (uint32_t m : meta) {
+                    const int slot = (int)(m >> 16) + lead;
+                    R |= 1ull << slot;
+                    for (int k = 0; k < SIESTA_MAX_STATES; ++k)
+                        if (m & (1u << k)) T[k] |= 1ull << slot;
+                }
+                hit = nkw_eval<unsigned long long>(prog, T, best, emitted, first_only);
+                PosEvents pe{R, lead, evt_pos};
+                int nsel = 0;
+                unsigned emitted_g = 0;
+                const bool hit_g = nk_eval<2>(dn, pe, T, false, evt_pos, (unsigned long long*)nullptr, 0, sel_g, nsel, emitted_g, first_only);
+                if (hit != hit_g || (hit && (best != sel_g[0] || emitted != emitted_g))) {
+                    siesta::set_error("nkw_eval<raw> disagrees with nk_eval<PosEvents>");
+                    return -99;
+                }
+                for (unsigned long long m = best; m; m &= m - 1) sel_idx.push_back(pe.rank(__builtin_ffsll((long long)m) - 1));
             }
             if (!hit) continue;
             o.emitted += emitted;
             o.trace_idx.push_back(t);
-            for (unsigned long long m = sel[0]; m; m &= m - 1) {
-                const int j = __builtin_ffsll((long long)m) - 1;
-                const int src = j - lead;
+            for (int j : sel_idx) {
+                const int src = (int)(meta[j] >> 16);
                 o.ev_pos.push_back(src);
-                o.ev_rank.push_back(pe.rank(j));
+                o.ev_rank.push_back(j);
                 o.ev_act.push_back(act[b0 + src]);
                 const long long raw = ts_ms[b0 + src];
                 o.ev_ts.push_back(evt_pos ? raw : (long long)((int)((raw - t0) / 1000)) * 1000 + t0);
