@@ -270,6 +270,58 @@ int64_t siesta_packed_block_bytes(int64_t n_traces, int64_t n_occurrences, int64
 int siesta_dev_matches_pack(siesta_log* log, const siesta_dev_matches* m, uint32_t flags, int64_t trace_base,
                             void* d_out, int64_t out_bytes, void* stream);
 
+/* ------------------------------------------------------- multi-GPU exchange */
+/* Traces are independent, so a log shards by contiguous trace range, one shard per GPU (siesta_log_set_first_trace),
+ * and every kernel of this library runs on every shard unchanged.  The results are joined on the devices, over NVLink
+ * peer memory: the match lists by an all-gather (siesta_detect_allgather), the count arrays of /declare, /stats and
+ * /explore by an all-reduce (siesta_exchange_allreduce_i64).  The reference has no counterpart (one JVM, Spark
+ * local[*]); the loop that the shards split is SaseConnector.evaluate's loop over all candidate traces
+ * (SaseConnection/SaseConnector.java:51-74) behind QueryPlanPatternDetection.execute (model/Queries/QueryPlans/
+ * Detection/QueryPlanPatternDetection.java:106-131).
+ *
+ * One siesta_exchange per rank (GPU).  Every rank owns a device region that all its peers map:
+ *   one process per GPU (torchrun, one JVM per GPU): siesta_exchange_export gives a 64-byte handle (cudaIpcMemHandle_t)
+ *     that the host layer hands to the other ranks by any means; each rank calls siesta_exchange_import once per peer;
+ *   one process driving all GPUs (a single JVM): siesta_exchange_connect_local once per ordered pair (peer access).
+ * Collective calls (siesta_detect_allgather, siesta_exchange_allreduce_i64) must be issued by every rank in the same
+ * order.  Sizes travel in-band and every device-side wait is bounded: a missing peer fails the call (SIESTA_E_CUDA)
+ * after 20 s instead of hanging the GPU.  csrc/multi.cu describes the protocol and the compact block format. */
+typedef struct siesta_exchange siesta_exchange;
+#define SIESTA_EXCHANGE_HANDLE_BYTES 64
+int siesta_exchange_create(siesta_ctx* ctx, int32_t world, int32_t rank, int64_t capacity_bytes, siesta_exchange** out);
+int siesta_exchange_export(siesta_exchange* x, void* handle_out /* SIESTA_EXCHANGE_HANDLE_BYTES */);
+int siesta_exchange_import(siesta_exchange* x, int32_t peer_rank, const void* handle);
+int siesta_exchange_connect_local(siesta_exchange* x, int32_t peer_rank, siesta_exchange* peer);
+void siesta_exchange_free(siesta_exchange* x);
+/* Bytes of exchange region a /detection request on this shard needs (worst case of its compact block): the host
+ * layer creates the exchanges with the maximum over the ranks. */
+int64_t siesta_exchange_required_bytes(siesta_log* log, const siesta_nfa* nfa, uint32_t flags);
+
+typedef struct siesta_exchange_stats {
+    int64_t local_traces, local_occurrences, local_events; /* this rank's share of the joined list              */
+    int64_t pulled_bytes;                                  /* bytes read from the peers' regions over NVLink      */
+    double k1_ms;    /* the verification kernels alone (device time)                                              */
+    double scan_ms;  /* verification + placement of this rank's block (device time)                               */
+    double wait_ms;  /* announce + wait for the slowest rank + fetch of the headers                               */
+    double pull_ms;  /* pull + decode of all blocks into the joined columns                                       */
+} siesta_exchange_stats;
+
+/* siesta_detect_device over this rank's shard FOLLOWED BY the all-gather: `out` holds the match list of ALL ranks in
+ * trace order (global trace indices), in the library's standard columns, on this rank's device.  The verification
+ * kernels place their result directly into the exchange region as a compact block whose header carries the sizes;
+ * one kernel then pulls every peer's block over NVLink and decodes it at its place in the joined list.  The host
+ * waits twice (sizes of all blocks; end of the request).  An error on any rank fails the call on every rank. */
+int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, uint32_t flags, siesta_exchange* x,
+                            siesta_dev_matches* out, siesta_exchange_stats* stats /* may be NULL */);
+
+#define SIESTA_REDUCE_SUM 0
+#define SIESTA_REDUCE_MIN 1
+#define SIESTA_REDUCE_MAX 2
+/* In-place all-reduce of a device array of int64 (the packed counts of siesta_declare_counts_device, the records of
+ * siesta_pair_stats_device, the completions of /explore): every rank ends with op over all ranks, combined in rank
+ * order (deterministic).  `stream` = the cudaStream_t that produced d_buf (NULL = the ctx stream); returns when done. */
+int siesta_exchange_allreduce_i64(siesta_exchange* x, int64_t* d_buf, int64_t n, int32_t op, void* stream);
+
 /* ------------------------------------------------- pair index + intersection */
 /* Kernel K2.  Replaces SparkDatabaseRepository.getCommonIds (storage/repositories/
  * SparkDatabaseRepository.java:160-178): the traces that contain ALL true pairs = the intersection of the

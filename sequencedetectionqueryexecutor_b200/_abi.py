@@ -73,6 +73,15 @@ class DevMatches(C.Structure):
                 ("impl", C.c_void_p)]
 
 
+class ExchangeStats(C.Structure):
+    _fields_ = [("local_traces", C.c_int64), ("local_occurrences", C.c_int64), ("local_events", C.c_int64),
+                ("pulled_bytes", C.c_int64), ("k1_ms", C.c_double), ("scan_ms", C.c_double), ("wait_ms", C.c_double), ("pull_ms", C.c_double)]
+
+
+EXCHANGE_HANDLE_BYTES = 64
+REDUCE_SUM, REDUCE_MIN, REDUCE_MAX = 0, 1, 2
+
+
 def make_nfa(states):
     """states: list of dicts {kind, types:[...], preds:[(attr, op, ref_state, constant), ...]}"""
     if not 1 <= len(states) <= MAX_STATES:

@@ -20,6 +20,8 @@ EXPORTS = [
     "siesta_candidates", "siesta_candidates_device", "siesta_pair_stats", "siesta_pair_stats_device",
     "siesta_explore_accurate", "siesta_log_set_first_trace",
     "siesta_packed_block_bytes", "siesta_dev_matches_pack",
+    "siesta_exchange_create", "siesta_exchange_export", "siesta_exchange_import", "siesta_exchange_connect_local",
+    "siesta_exchange_free", "siesta_exchange_required_bytes", "siesta_detect_allgather", "siesta_exchange_allreduce_i64",
 ]
 
 
@@ -88,6 +90,16 @@ def lib():
     L.siesta_pair_stats.argtypes = [vp, vp, vp, i32, P(_abi.PairCount), P(C.c_double)]
     L.siesta_pair_stats_device.argtypes = [vp, vp, vp, i32, vp, vp, P(C.c_double)]
     L.siesta_explore_accurate.argtypes = [vp, vp, i32, vp, i32, u32, vp, vp, P(C.c_double)]
+    L.siesta_exchange_create.argtypes = [vp, i32, i32, i64, P(vp)]
+    L.siesta_exchange_export.argtypes = [vp, vp]
+    L.siesta_exchange_import.argtypes = [vp, i32, vp]
+    L.siesta_exchange_connect_local.argtypes = [vp, i32, vp]
+    L.siesta_exchange_free.argtypes = [vp]
+    L.siesta_exchange_free.restype = None
+    L.siesta_exchange_required_bytes.argtypes = [vp, P(_abi.Nfa), u32]
+    L.siesta_exchange_required_bytes.restype = i64
+    L.siesta_detect_allgather.argtypes = [vp, P(_abi.Nfa), u32, vp, P(_abi.DevMatches), P(_abi.ExchangeStats)]
+    L.siesta_exchange_allreduce_i64.argtypes = [vp, vp, i64, i32, vp]
     L.siesta_device_free.argtypes = [vp, vp]
     L.siesta_device_free.restype = None
     _lib = L

@@ -231,6 +231,50 @@ class PairIndex:
         return out[:n.value].copy()
 
 
+class Exchange:
+    """siesta_exchange: this rank's end of the device-side joins (csrc/multi.cu).  Create one per rank with the same
+    world / capacity, connect the peers (export() / import_peer() across processes, connect_local() inside one), then
+    call the collectives in the same order on every rank."""
+
+    def __init__(self, ctx, world, rank, capacity_bytes):
+        self.ctx, self.world, self.rank, self.capacity = ctx, int(world), int(rank), int(capacity_bytes)
+        self._h = C.c_void_p()
+        check(lib().siesta_exchange_create(ctx._h, self.world, self.rank, self.capacity, C.byref(self._h)))
+
+    def export(self):
+        buf = (C.c_ubyte * _abi.EXCHANGE_HANDLE_BYTES)()
+        check(lib().siesta_exchange_export(self._h, buf))
+        return bytes(buf)
+
+    def import_peer(self, peer_rank, handle):
+        buf = (C.c_ubyte * _abi.EXCHANGE_HANDLE_BYTES).from_buffer_copy(handle)
+        check(lib().siesta_exchange_import(self._h, int(peer_rank), buf))
+
+    def connect_local(self, peer):
+        check(lib().siesta_exchange_connect_local(self._h, peer.rank, peer._h))
+
+    def detect_allgather(self, log, nfa, flags=0):
+        """siesta_detect_allgather -> (DeviceMatches of ALL ranks, ExchangeStats)."""
+        dm, st = _abi.DevMatches(), _abi.ExchangeStats()
+        check(lib().siesta_detect_allgather(log._h, C.byref(nfa), flags, self._h, C.byref(dm), C.byref(st)))
+        return DeviceMatches(dm), st
+
+    def allreduce_i64(self, d_buf, op=_abi.REDUCE_SUM, stream=None):
+        """In-place all-reduce of an int64 CUDA tensor over the peer regions."""
+        check(lib().siesta_exchange_allreduce_i64(self._h, C.c_void_p(d_buf.data_ptr()), d_buf.numel(), int(op),
+                                                  C.c_void_p(stream) if stream else None))
+        return d_buf
+
+    def close(self):
+        if self._h:
+            lib().siesta_exchange_free(self._h)
+            self._h = C.c_void_p()
+
+
+def exchange_required_bytes(log, nfa, flags=0):
+    return int(lib().siesta_exchange_required_bytes(log._h, C.byref(nfa), flags))
+
+
 class PendingDetect:
     """A verification request whose kernels are enqueued (siesta_detect_device_begin); finish() exactly once."""
 

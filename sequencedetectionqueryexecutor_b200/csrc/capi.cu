@@ -50,6 +50,12 @@ extern "C" int siesta_init(int32_t device_id, siesta_ctx** out) {
     SIESTA_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, device_id));
     unsigned long long keep = ~0ull;
     SIESTA_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    {   // the first slab of pinned counter blocks now, not inside a request
+        void* slab = nullptr;
+        SIESTA_CUDA_OK(cudaHostAlloc(&slab, 32 * 128, cudaHostAllocDefault));
+        c->pinned_slabs.push_back(slab);
+        for (int i = 0; i < 32; ++i) c->pinned_counters.push_back(reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(slab) + 128 * i));
+    }
     *out = reinterpret_cast<siesta_ctx*>(c);
     return SIESTA_OK;
 }
@@ -60,7 +66,7 @@ extern "C" void siesta_shutdown(siesta_ctx* ctx) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (HostBlock& b : c->arena) cudaFreeHost(b.p);  // result objects must have been freed before the ctx
-    for (unsigned long long* p : c->pinned_counters) cudaFreeHost(p);
+    for (void* p : c->pinned_slabs) cudaFreeHost(p);
     delete c;
 }
 

@@ -40,7 +40,9 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     std::mutex arena_mu;
     std::vector<HostBlock> arena;
-    std::vector<unsigned long long*> pinned_counters;  // free 128-byte pinned blocks for the requests' counters
+    std::vector<unsigned long long*> pinned_counters;  // free 128-byte pinned blocks for the requests' counters ...
+    std::vector<void*> pinned_slabs;                   // ... carved from slabs of 32 (one cudaHostAlloc each: the call may wait
+                                                       // for running kernels, and a request in flight may be spinning on a peer)
 };
 
 // CSR event log resident in HBM.
@@ -103,6 +105,40 @@ int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, i
 int validate_act_range(Log* L, int64_t first_event, int64_t n_events, cudaStream_t stream);
 
 int validate_nfa(const siesta_nfa* nfa, uint32_t flags, DevNfa* out);
+
+// ------------------------------------------------------------------------------------------ multi-GPU exchange (multi.cu)
+// Header of a rank's compact result block in its exchange region (wire format: multi.cu).  Written on the device when
+// the block is complete; every rank reads every header (sizes travel in-band: no size collective, no host round trip
+// before the payload moves).
+constexpr int XCHG_MAX_RANKS = 16;
+constexpr size_t XCHG_CTRL_BYTES = 4096;   // control page at the start of a region; the data area follows
+enum { XST_LIMITS = 1, XST_STAGING = 2, XST_RANGE = 4, XST_ERRCAP = 8, XST_TIMEOUT = 16 };
+struct XHeader {
+    unsigned long long seq;
+    int64_t n_tr, n_occ, n_ev, n_err, n_emitted;
+    int64_t trace_base;        // global index of the shard's first trace
+    int32_t all_cols, seconds; // event columns present; ts_delta in seconds (EventTs route) or milliseconds
+    int32_t uniform_k;         // > 0: one occurrence per trace and uniform_k events per occurrence (no offset sections)
+    int32_t status;            // XST_* bits: the request failed on this rank
+    int64_t o_trace, o_base, o_occ_off, o_ev_off, o_pos, o_rank, o_act, o_delta, o_err;   // byte offsets into the data area
+    int64_t pad[14];
+};
+static_assert(sizeof(XHeader) == 256, "XHeader is 256 bytes");
+// Where the placement writes the compact block (detect.cu: detect_device_pack_impl)
+struct PackTarget {
+    char* data;            // data area of the local exchange region
+    int64_t cap_bytes;
+    XHeader* hdr;          // header slot of the local region
+    unsigned long long seq;
+};
+struct DetectPending;
+int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand, uint32_t flags,
+                             cudaStream_t stream, RebaseOffsets base, DetectPending** pending);
+int detect_device_pack_impl(DetectPending* q, const PackTarget& tgt);   // enqueues only, no host wait
+void detect_pending_discard(DetectPending* q);
+float detect_pending_k1_ms(DetectPending* q);                            // releases the request (stream-ordered)
+int64_t detect_pack_required_bytes(int64_t n_cand_or_traces, int64_t n_events_log, int uniform_k, bool all_cols, bool return_all);
+int detect_uniform_k(const siesta_nfa* nfa, uint32_t flags);
 void build_lut(const siesta_nfa* nfa, const DevNfa& dn, int32_t n_activities, uint32_t flags, std::vector<uint16_t>& lut,
                int* needs_ts, int* n_positive);
 

@@ -692,22 +692,22 @@ struct DetectPending {
     unsigned long long *d_blk = nullptr, *d_top = nullptr, *d_counters = nullptr;
     int64_t* d_err = nullptr;
     void* work = nullptr;                 // scratch of the call (freed by the second half)
+    int uniform_k = 0;                    // > 0: one occurrence per trace, uniform_k events each (class NK, first-largest)
     cudaEvent_t ev0 = nullptr, evd = nullptr;
     unsigned long long* h_cnt = nullptr;  // pinned, 16 words
 };
 
 static unsigned long long* pinned_counters_get(Ctx* c) {
-    {
-        std::lock_guard<std::mutex> g(c->arena_mu);
-        if (!c->pinned_counters.empty()) {
-            unsigned long long* p = c->pinned_counters.back();
-            c->pinned_counters.pop_back();
-            return p;
-        }
+    std::lock_guard<std::mutex> g(c->arena_mu);
+    if (c->pinned_counters.empty()) {
+        void* slab = nullptr;
+        if (cudaHostAlloc(&slab, 32 * 128, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        c->pinned_slabs.push_back(slab);
+        for (int i = 0; i < 32; ++i) c->pinned_counters.push_back(reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(slab) + 128 * i));
     }
-    void* p = nullptr;
-    if (cudaHostAlloc(&p, 128, cudaHostAllocDefault) != cudaSuccess) return nullptr;
-    return reinterpret_cast<unsigned long long*>(p);
+    unsigned long long* p = c->pinned_counters.back();
+    c->pinned_counters.pop_back();
+    return p;
 }
 static void pinned_counters_put(Ctx* c, unsigned long long* p) {
     if (!p) return;
@@ -935,6 +935,7 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
     q->d_counters = b_counters.as<unsigned long long>();
     q->d_err = b_err.as<int64_t>();
     q->work = work.release();
+    q->uniform_k = (!return_all && !dn.any_kleene) ? std::max(1, n_positive) : 0;
     q->ev0 = ev0;
     q->evd = evd;
     q->h_cnt = h_cnt;
@@ -1084,6 +1085,264 @@ int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out) {
     out->block_bytes = (int64_t)f_off;
     impl->bufs[0] = out->d_block = fin.release();
     out->impl = impl;
+    return SIESTA_OK;
+}
+
+// ---------------------------------------------------------------------------------- packed placement (multi-GPU exchange)
+// The exchange (multi.cu) ships a rank's match list in a compact block.  Here the placement writes that block DIRECTLY
+// into the rank's exchange region - no intermediate result, no host wait for the sizes: the sections sit at offsets
+// derived from the request's CAPACITY (known before the scan), the actual sizes travel in the block's header.
+//   trace    u32[n_tr]  shard-local trace index            base   i64[n_tr]  ev_ts_ms of the trace's first reported event
+//   occ_off  u32[n_tr+1], ev_off u32[n_occ+1]              only when uniform_k == 0 (else one occurrence per trace,
+//                                                           uniform_k events per occurrence: offsets are arithmetic)
+//   pos u16[n_ev]  rank u8[n_ev]  act u16[n_ev]  delta i32[n_ev]  (ev_ts_ms - base) in seconds (EventTs route: exact,
+//                                                           both are rel_s * 1000 + t0) or milliseconds (EventPos route)
+//   err      i64[n_err] shard-local indices of the traces on which the Java engine would throw (<= XCHG_ERR_CAP)
+constexpr int64_t XCHG_ERR_CAP = 4096;
+struct PackSections {
+    uint32_t* trace;
+    int64_t* base;
+    uint32_t *occ_off, *ev_off;
+    uint16_t* pos;
+    uint8_t* rank;
+    uint16_t* act;
+    int32_t* delta;
+    int64_t* err;
+    int32_t seconds;
+    int* status;
+};
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+// byte offsets of the sections inside the data area, from the capacities; returns the bytes needed
+static size_t pack_layout(int64_t n, int64_t cap_occ, int64_t cap_ev, int uniform_k, bool all_cols, XHeader* h) {
+    size_t o = 0;
+    auto take = [&o](size_t bytes) { const size_t at = o; o += al256(bytes); return (int64_t)at; };
+    h->o_trace = take((size_t)n * 4);
+    h->o_base = all_cols ? take((size_t)n * 8) : 0;
+    h->o_occ_off = uniform_k ? 0 : take((size_t)(n + 1) * 4);
+    h->o_ev_off = uniform_k ? 0 : take((size_t)(cap_occ + 1) * 4);
+    h->o_pos = take((size_t)cap_ev * 2);
+    h->o_rank = all_cols ? take((size_t)cap_ev) : 0;
+    h->o_act = all_cols ? take((size_t)cap_ev * 2) : 0;
+    h->o_delta = all_cols ? take((size_t)cap_ev * 4) : 0;
+    h->o_err = take((size_t)XCHG_ERR_CAP * 8);
+    return o;
+}
+
+__global__ void __launch_bounds__(GT) gather_packed_kernel(const __grid_constant__ GatherParams G, const __grid_constant__ PackSections O, int uniform) {
+    const int64_t i = (int64_t)blockIdx.x * GT + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    unsigned long long v[3] = {0, 0, 0}, ex[3], tot[3];
+    uint32_t nocc = 0;
+    long long se = 0;
+    const int64_t chunk = blockIdx.x / SC;
+    unsigned long long bb[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) bb[q] = G.top[q * G.n_chunks + chunk] + G.blk[q * G.n_blk + blockIdx.x];
+    if (i < G.n) {
+        const uint32_t w = G.d_cnt[i];
+        se = G.d_stage[i];
+        nocc = w & 0xFFFFu;
+        v[0] = nocc ? 1 : 0;
+        v[1] = nocc;
+        v[2] = w >> 16;
+    }
+    block_scan3(v, ex, tot);
+    const int64_t tp = (int64_t)(bb[0] + ex[0]);
+    const int64_t op = (int64_t)(bb[1] + ex[1]);
+    const int64_t ep = (int64_t)(bb[2] + ex[2]);
+    int bad = 0;
+    if (nocc) {
+        bad |= (unsigned long long)i > 0xFFFFFFFFull;
+        O.trace[tp] = (uint32_t)i;   // index into the candidate list: the receiver adds the shard's first trace (no candidate
+                                     // list on the exchange path: the index IS the shard-local trace index)
+        if (O.base) O.base[tp] = G.s_ev_ts[se];
+        if (!uniform) {
+            bad |= (unsigned long long)(ep + (long long)v[2]) > 0xFFFFFFFFull;
+            O.occ_off[tp] = (uint32_t)op;
+            if (G.d_stage_occ) {
+                const int64_t so = G.d_stage_occ[i];
+                int64_t e = ep;
+                for (uint32_t o = 0; o < nocc; ++o) {
+                    O.ev_off[op + o] = (uint32_t)e;
+                    e += G.s_occ_nev[so + o];
+                }
+            } else {
+                O.ev_off[op] = (uint32_t)ep;
+            }
+        }
+    }
+    const unsigned my_ev = (unsigned)v[2];
+    unsigned incl = my_ev;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    const unsigned wtot = __shfl_sync(0xffffffffu, incl, 31);
+    const long long wbase = shfl_i64(ep, 0);
+    for (unsigned f0 = 0; f0 < wtot; f0 += 32) {
+        const unsigned f = f0 + lane;
+        int lo = 0, hi = 31;
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+            const int mid = (lo + hi) >> 1;
+            const unsigned vmid = __shfl_sync(0xffffffffu, incl, mid);
+            if (vmid > f) hi = mid; else lo = mid + 1;
+        }
+        const int owner = lo & 31;
+        const unsigned o_incl = __shfl_sync(0xffffffffu, incl, owner);
+        const unsigned o_ev = __shfl_sync(0xffffffffu, my_ev, owner);
+        const long long o_se = shfl_i64(se, owner);
+        if (f < wtot) {
+            const long long from = o_se + (long long)(f - (o_incl - o_ev));
+            const long long to = wbase + f;
+            const int32_t c_pos = __ldg(G.s_ev_pos + from);
+            int32_t c_rank = 0, c_act = 0;
+            long long c_ts = 0, c_base = 0;
+            if (G.all_cols) {
+                c_rank = __ldg(G.s_ev_rank + from);
+                c_act = __ldg(G.s_ev_act + from);
+                c_ts = __ldg(reinterpret_cast<const long long*>(G.s_ev_ts) + from);
+                c_base = __ldg(reinterpret_cast<const long long*>(G.s_ev_ts) + o_se);
+            }
+            bad |= (unsigned)c_pos > 0xFFFFu;
+            O.pos[to] = (uint16_t)c_pos;
+            if (G.all_cols) {
+                long long d = c_ts - c_base;
+                if (O.seconds) {
+                    bad |= d % 1000 != 0;
+                    d /= 1000;
+                }
+                bad |= (unsigned)c_rank > 0xFFu || (unsigned)c_act > 0xFFFFu || d < -0x7fffffffll - 1 || d > 0x7fffffffll;
+                O.rank[to] = (uint8_t)c_rank;
+                O.act[to] = (uint16_t)c_act;
+                O.delta[to] = (int32_t)d;
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(O.status, XST_RANGE);
+}
+
+// Header of the block: sizes from the request's counters, status, the tails of the offset sections, the error list.
+__global__ void pack_header_kernel(const unsigned long long* counters, const int64_t* err_list, XHeader proto, XHeader* hdr,
+                                   const __grid_constant__ PackSections O) {
+    const int64_t n_occ = (int64_t)counters[0], n_ev = (int64_t)counters[1], n_tr = (int64_t)counters[6], n_err = (int64_t)counters[3];
+    if (threadIdx.x == 0) {
+        int status = *O.status;
+        if (counters[7] > 0) status |= XST_LIMITS;
+        if (counters[5] > 0) status |= XST_STAGING;
+        if (n_err > XCHG_ERR_CAP) status |= XST_ERRCAP;
+        if (!proto.uniform_k && !(status & (XST_LIMITS | XST_STAGING))) {
+            O.occ_off[n_tr] = (uint32_t)n_occ;
+            O.ev_off[n_occ] = (uint32_t)n_ev;
+        }
+        proto.n_tr = n_tr;
+        proto.n_occ = n_occ;
+        proto.n_ev = n_ev;
+        proto.n_err = n_err;
+        proto.n_emitted = (int64_t)counters[2];
+        proto.status = status;
+        *hdr = proto;
+    }
+    for (int64_t i = threadIdx.x; i < n_err && i < XCHG_ERR_CAP; i += blockDim.x) O.err[i] = err_list[i];
+}
+
+int detect_uniform_k(const siesta_nfa* nfa, uint32_t flags) {
+    DevNfa dn;
+    if (validate_nfa(nfa, flags, &dn) != SIESTA_OK || (flags & SIESTA_F_RETURN_ALL) || dn.any_kleene) return 0;
+    int np = 0;
+    for (int s = 0; s < nfa->n_states; ++s) np += nfa->states[s].kind != SIESTA_STATE_NEGATIVE;
+    return std::max(1, np);
+}
+
+int64_t detect_pack_required_bytes(int64_t n, int64_t n_events_log, int uniform_k, bool all_cols, bool return_all) {
+    const int64_t wide = std::min<int64_t>(n_events_log, n * 64);
+    const int64_t cap_occ = return_all ? wide : n;
+    const int64_t cap_ev = uniform_k ? n * uniform_k : wide;
+    XHeader h;
+    return (int64_t)pack_layout(std::max<int64_t>(n, 1), cap_occ, cap_ev, uniform_k, all_cols, &h);
+}
+
+void detect_pending_discard(DetectPending* q) { pending_discard(q); }
+// device time of the verification kernels alone (K1-P + staged re-run); valid once the request's stream has been waited for
+float detect_pending_k1_ms(DetectPending* q) {
+    float ms = 0.f;
+    if (q && q->n > 0 && cudaEventElapsedTime(&ms, q->ev0, q->evd) != cudaSuccess) {
+        cudaGetLastError();
+        ms = 0.f;
+    }
+    return ms;
+}
+
+// Second half of a request on the exchange path: enqueues the placement into the exchange region and returns without
+// waiting for the device.  The caller synchronises once all ranks' headers are in and then releases q
+// (detect_pending_discard) - multi.cu.
+int detect_device_pack_impl(DetectPending* q, const PackTarget& tgt) {
+    Log* log = q->log;
+    SIESTA_CUDA_OK(cudaSetDevice(log->ctx->device));
+    cudaStream_t stream = q->stream;
+    const int64_t n = q->n;
+    const bool return_all = (q->flags & SIESTA_F_RETURN_ALL) != 0;
+    const bool all_cols = (q->flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
+    const DetectParams& P = q->P;
+    if (q->d_cand) {
+        set_error("exchange path: candidate lists are not supported (verify the whole shard)");
+        return SIESTA_E_UNSUPPORTED;
+    }
+    XHeader proto;
+    std::memset(&proto, 0, sizeof(proto));
+    const size_t need = pack_layout(std::max<int64_t>(n, 1), P.cap_occ, P.cap_ev, q->uniform_k, all_cols, &proto);
+    if ((int64_t)need > tgt.cap_bytes) {
+        set_error("exchange region too small: " + std::to_string(need) + " bytes needed, " + std::to_string(tgt.cap_bytes) +
+                  " available (siesta_exchange_required_bytes)");
+        return SIESTA_E_NOMEM;
+    }
+    proto.seq = tgt.seq;
+    proto.trace_base = q->base.trace;   // includes the shard's first trace
+    proto.all_cols = all_cols ? 1 : 0;
+    proto.seconds = (q->flags & SIESTA_F_EVT_POS) ? 0 : 1;
+    proto.uniform_k = q->uniform_k;
+    PackSections O;
+    O.trace = reinterpret_cast<uint32_t*>(tgt.data + proto.o_trace);
+    O.base = all_cols ? reinterpret_cast<int64_t*>(tgt.data + proto.o_base) : nullptr;
+    O.occ_off = reinterpret_cast<uint32_t*>(tgt.data + proto.o_occ_off);
+    O.ev_off = reinterpret_cast<uint32_t*>(tgt.data + proto.o_ev_off);
+    O.pos = reinterpret_cast<uint16_t*>(tgt.data + proto.o_pos);
+    O.rank = reinterpret_cast<uint8_t*>(tgt.data + proto.o_rank);
+    O.act = reinterpret_cast<uint16_t*>(tgt.data + proto.o_act);
+    O.delta = reinterpret_cast<int32_t*>(tgt.data + proto.o_delta);
+    O.err = reinterpret_cast<int64_t*>(tgt.data + proto.o_err);
+    O.seconds = proto.seconds;
+    O.status = reinterpret_cast<int*>(q->d_counters + 24);   // a zeroed word of the request's counter block
+    if (n > 0) {
+        GatherParams G;
+        std::memset(&G, 0, sizeof(G));
+        G.n = n;
+        G.d_cnt = P.d_cnt;
+        G.d_stage = P.d_stage;
+        G.d_stage_occ = return_all ? P.d_stage_occ : nullptr;
+        G.n_blk = (int64_t)q->n_blk;
+        G.blk = q->d_blk;
+        G.n_chunks = (int64_t)((q->n_blk + 1023) / 1024);
+        G.top = q->d_top;
+        G.s_occ_nev = P.s_occ_nev;
+        G.s_ev_pos = P.s_ev_pos;
+        G.s_ev_rank = P.s_ev_rank;
+        G.s_ev_act = P.s_ev_act;
+        G.s_ev_ts = P.s_ev_ts;
+        G.all_cols = all_cols ? 1 : 0;
+        count_blocks_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G);
+        SIESTA_LAUNCHED();
+        scan_chunks_kernel<<<(unsigned)G.n_chunks, SC, 0, stream>>>(G.blk, G.n_blk, G.top, G.n_chunks);
+        SIESTA_LAUNCHED();
+        scan_top_kernel<<<1, SC, 0, stream>>>(G.top, G.n_chunks);
+        SIESTA_LAUNCHED();
+        gather_packed_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G, O, q->uniform_k ? 1 : 0);
+        SIESTA_LAUNCHED();
+    }
+    pack_header_kernel<<<1, 256, 0, stream>>>(q->d_counters, q->d_err, proto, tgt.hdr, O);
+    SIESTA_LAUNCHED();
+    SIESTA_CUDA_OK(cudaGetLastError());
     return SIESTA_OK;
 }
 

@@ -4,14 +4,19 @@
 // seconds, SaseConnector.evaluate + Occurrences.clearOccurrences(false)
 // (J/SaseConnection/SaseConnector.java:48-76, J/model/Occurrences.java:58-72); derivation in detect_fast.cuh.
 //
-// One lane per trace, no shared memory, no per-event loop after the scan:
-//   scan     the lane streams the trace's 32-byte sectors (<= 64 position slots from the sector of its first event; all
-//            sixteen 128-bit loads are issued before the first is used) and pushes every activity id through the class
-//            bit-planes with shift instructions.  Rank space (NKW_RANK): a slot pushes its plane bits only if it holds
-//            an event of the pattern (funnel shift by 0 or 1), so the planes come out COMPACTED to the filtered list -
-//            bit r = r-th relevant event, 32-bit masks, and `position` (EventTs route) / `timestamp` (EventPos route)
-//            of an event is its bit index.  Raw space (NKW_RAW): one bit per slot, 64-bit masks, `position` of the
-//            EventPos route is the slot.
+// One lane per trace, no per-event loop after the scan:
+//   load     the lane streams the trace's 32-byte sectors (<= 64 position slots from the sector of its first event;
+//            sixteen 128-bit loads, all issued before the first is used); the offsets of the NEXT tile are requested a
+//            tile early, so a tile waits for one memory latency, not two.  (Staging the sectors of tile i + 1 by
+//            cp.async into a shared-memory column while tile i is evaluated was measured: long-scoreboard stalls fell
+//            from 5.0 to 1.7 per issue, but 33 KB of shared memory per CTA left 23 KB of L1 and the instruction-fetch
+//            stalls rose from 1.7 to 4.3 per issue - 0.504 ms against 0.462 ms; profiles/r02_k1p_ncu_summary.md.)
+//   scan     every activity id indexes a 16-byte table entry in shared memory and advances the class bit-planes with
+//            one integer multiply-add per plane (scan32 below).  Rank space (NKW_RANK): a slot pushes its plane bits
+//            only if it holds an event of the pattern, so the planes come out COMPACTED to the filtered list - bit r =
+//            r-th relevant event, 32-bit masks, and `position` (EventTs route) / `timestamp` (EventPos route) of an
+//            event is its bit index.  Raw space (NKW_RAW): one bit per slot, 64-bit masks, `position` of the EventPos
+//            route is the slot.
 //   compose  class c = minterm of the planes (one LOP3 each); state k's mask = OR of its classes (uniform branches)
 //   walk     NkwWalk: per state one AND of {state mask, above(previous event), predicate windows} and a lowest-set-bit;
 //            the first start whose walk completes is the first-largest occurrence (monotone walks)
@@ -25,6 +30,9 @@ namespace siesta {
 
 #ifndef SIESTA_NKP_MIN_CTAS
 #define SIESTA_NKP_MIN_CTAS 6
+#endif
+#ifndef SIESTA_NKP_PREFETCH   // 1: request the next tile's offsets a tile early (six more live registers)
+#define SIESTA_NKP_PREFETCH 0
 #endif
 
 // The scan.  Every activity id indexes a 16-byte table entry {m, b0, b1, b2} in shared memory (one LDS.128, entry
@@ -76,7 +84,7 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
     typedef unsigned long long u64;
     typedef NkwBits<mask_t> B;
     const int lane = threadIdx.x & 31;
-    extern __shared__ uint4 s_lut[];   // [n_act + 1]
+    extern __shared__ uint4 s_lut[];   // the table [n_act + 1]
     for (int i = threadIdx.x; i <= P.n_act; i += blockDim.x) s_lut[i] = P.nkp_lut[i];
     __syncthreads();
     const bool evt_pos = (P.flags & SIESTA_F_EVT_POS) != 0;
@@ -87,33 +95,51 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
     const long long n_tiles = (n_work + 31) / 32;
     const int batch = P.tile_batch;
     // Tiles are handed out by an atomic counter (a CTA that starts late because a collective or a copy holds its SM
-    // takes fewer), `batch` consecutive tiles per atomic; the next batch is requested while the current one runs.
-    long long tile = 0;
-    if (lane == 0) tile = (long long)atomicAdd(P.counters + P.tile_slot, (unsigned long long)batch);
+    // takes fewer), `batch` consecutive tiles per atomic.  The pipeline needs the next tile's index a whole tile early,
+    // so a warp always holds the batch after the current one (next_batch) and requests the one after that (next_batch2)
+    // when a batch starts: no atomic is ever waited for.
+    long long tile = 0, next_batch = 0, next_batch2 = 0;
+    if (lane == 0) {
+        tile = (long long)atomicAdd(P.counters + P.tile_slot, (unsigned long long)batch);
+        next_batch = (long long)atomicAdd(P.counters + P.tile_slot, (unsigned long long)batch);
+    }
     tile = shfl_i64(tile, 0);
     int left = batch;
-    long long next_tile = 0;
     unsigned long long acc_occ = 0, acc_ev = 0, acc_emit = 0;  // totals, flushed once per warp
-    while (tile < n_tiles) {
-        if (left == batch && lane == 0) next_tile = (long long)atomicAdd(P.counters + P.tile_slot, (unsigned long long)batch);
-        const int64_t wi = tile * 32 + lane;
-        int64_t ci = -1, t = -1;
-        long long o0 = 0, o1 = 0;
-        if (wi < n_work) {
-            ci = P.work ? P.work[wi] : wi;
-            t = P.cand ? P.cand[ci] : ci;
-            o0 = P.trace_off[t];
-            o1 = P.trace_off[t + 1];
+
+    // the trace of this lane in a tile: candidate index, trace offsets
+    auto locate = [&](long long tl, int64_t& ci_, long long& o0_, long long& o1_) {
+        const int64_t wi = tl * 32 + lane;
+        ci_ = -1;
+        o0_ = o1_ = 0;
+        if (tl < n_tiles && wi < n_work) {
+            ci_ = P.work ? P.work[wi] : wi;
+            const int64_t t = P.cand ? P.cand[ci_] : ci_;
+            o0_ = P.trace_off[t];
+            o1_ = P.trace_off[t + 1];
         }
+    };
+    int64_t ci;
+    long long o0, o1;
+    locate(tile, ci, o0, o1);
+    while (tile < n_tiles) {
+        if (left == batch && lane == 0) next_batch2 = (long long)atomicAdd(P.counters + P.tile_slot, (unsigned long long)batch);
+        const long long nxt = left > 1 ? tile + 1 : shfl_i64(next_batch, 0);
+#if SIESTA_NKP_PREFETCH
+        // the next tile's offsets: requested now, needed when this tile is done
+        int64_t nci;
+        long long no0, no1;
+        locate(nxt, nci, no0, no1);
+#endif
+
         const long long e0 = o0 & ~7LL;
         const int lead = (int)(o0 - e0);
         const long long span = (o1 - o0) + lead;  // slots the trace needs
-        // a trace that needs more than 64 slots, or whose last sector crosses the end of the log, is not read here
         bool fits = span <= 64 && ((o1 + 7) & ~7LL) <= P.n_events;
-        const long long o1s = fits ? o1 : o0;
+        const long long o1s = fits ? o1 : o0;     // a trace that does not fit is not read here
         int4 v0[8], v1[8];
+        load_sectors_vec(P, e0 + 32, o1s, v1);   // scanned first (last slot first)
         load_sectors_vec(P, e0, o1s, v0);
-        load_sectors_vec(P, e0 + 32, o1s, v1);
         u64 valid = 0;
         if (fits && o1 > o0) valid = (span == 64 ? ~0ull : ((1ull << (int)span) - 1ull)) & ~((1ull << lead) - 1ull);
         const bool second = __any_sync(0xffffffffu, fits && span > 32);
@@ -207,10 +233,6 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
             }
         }
         if (tot1 > 0) {
-            // first event of the filtered list (Utils.java:51-53): base of the relative seconds of the EventTs route
-            long long t0ms = 0;
-            if (status == ST_MATCH && all_cols && !evt_pos)
-                t0ms = __ldg(reinterpret_cast<const long long*>(P.ts_ms) + o0 + (__ffsll((long long)Rv) - 1 - lead));
             for (unsigned f0 = 0; f0 < tot1; f0 += 32) {
                 const unsigned f = f0 + lane;
                 int lo = 0, hi = 31;
@@ -228,7 +250,6 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
                 else m = __shfl_sync(0xffffffffu, best, owner);
                 const u64 o_R = (u64)shfl_i64((long long)Rv, owner);
                 const long long o_o0 = shfl_i64(o0, owner);
-                const long long o_t0 = shfl_i64(t0ms, owner);
                 if (f < tot1) {
                     int k = (int)(f - (o_incl - o_ev));  // k-th event of the owner's occurrence
                     for (; k > 0; --k) m &= m - 1;
@@ -244,21 +265,32 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
                     const long long at = base1 + f;
                     P.s_ev_pos[at] = src;
                     if (all_cols) {
+                        // all three loads leave together: the event's activity and timestamp, and the timestamp of the
+                        // first event of the filtered list (Utils.java:51-53: base of the EventTs route's seconds)
+                        const long long* tsp = reinterpret_cast<const long long*>(P.ts_ms) + o_o0;
+                        const int32_t c_act = __ldg(P.act + o_o0 + src);
+                        const long long raw = __ldg(tsp + src);
+                        const long long o_t0 = evt_pos ? 0 : __ldg(tsp + (__ffsll((long long)o_R) - 1 - (int)(o_o0 & 7)));
                         P.s_ev_rank[at] = rank;
-                        P.s_ev_act[at] = __ldg(P.act + o_o0 + src);
-                        const long long raw = __ldg(reinterpret_cast<const long long*>(P.ts_ms) + o_o0 + src);
+                        P.s_ev_act[at] = c_act;
                         // SaseEvent.getEventBoth: timestamp * 1000 + minTs (SaseEvent.java:94-106)
                         P.s_ev_ts[at] = evt_pos ? raw : (long long)rel_seconds(raw - o_t0) * 1000 + o_t0;
                     }
                 }
             }
         }
+        tile = nxt;
         if (--left == 0) {
-            tile = shfl_i64(next_tile, 0);
             left = batch;
-        } else {
-            ++tile;
+            next_batch = next_batch2;
         }
+#if SIESTA_NKP_PREFETCH
+        ci = nci;
+        o0 = no0;
+        o1 = no1;
+#else
+        locate(tile, ci, o0, o1);
+#endif
     }
     if (lane == 31) {
         if (acc_occ) {
@@ -281,6 +313,10 @@ int launch_one(const Ctx* ctx, cudaStream_t stream, DetectParams P, const NkwPro
     if (const char* env = std::getenv("SIESTA_K1_CTAS_PER_SM")) {  // tuning aid: cap on resident CTAs per SM
         const int v = std::atoi(env);
         if (v >= 1 && v < per_sm) per_sm = v;
+    }
+    if (const char* env = std::getenv("SIESTA_NKP_CARVEOUT")) {  // tuning aid: shared-memory carveout in percent
+        const int v = std::atoi(env);
+        if (v >= 0 && v <= 100) SIESTA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, v));
     }
     const int64_t n_tiles = (P.n_work + 31) / 32;
     const int64_t ctas_needed = (n_tiles + NT / 32 - 1) / (NT / 32);

@@ -1,0 +1,692 @@
+// multi.cu — the multi-GPU exchange of libsiesta_gpu: match lists joined by a device-side all-gather, counts by a
+// device-side all-reduce, both over NVLink peer memory, both behind the C-ABI (include/siesta_gpu.h, siesta_exchange_*).
+//
+// The reference has no counterpart (it is one JVM with Spark local[*]); the path it stands behind is
+// QueryPlanPatternDetection.execute (J/model/Queries/QueryPlans/Detection/QueryPlanPatternDetection.java:106-131), whose
+// SaseConnector.evaluate loop over ALL candidate traces is what the shards split.
+//
+// One exchange object per rank (GPU).  A rank owns ONE device region, [control page | data area], that every peer maps:
+// across processes through a CUDA IPC handle (siesta_exchange_export / _import: one process per GPU, e.g. under
+// torchrun), inside one process through peer access (siesta_exchange_connect_local: one JVM driving all GPUs).
+// A collective operation (every rank calls them in the same order) is numbered `seq` and runs as
+//   wait    until every peer has acknowledged pulling operation seq - 1 out of my region        (xchg_wait_acks_kernel)
+//   produce my block INTO my region: the placement of the match list (detect.cu, gather_packed_kernel) with the sizes
+//           in the block's header, or the count array
+//   signal  st.release.sys `seq` into every peer's ready slot; wait for every peer's; fetch their headers
+//                                                                                                 (xchg_signal_kernel)
+//   pull    read every peer's block over NVLink and, in the same kernel, decode it to the standard columns at its
+//           place in the joined list (xchg_decode_*_kernel) / reduce the count arrays in rank order (xchg_reduce_kernel)
+//   ack     st.release.sys `seq` into every peer's ack slot                                       (xchg_ack_kernel)
+// No size collective, no host round trip before the payload moves: the host waits once for the headers (it needs the
+// sizes to allocate the joined result) and once for the end of the request.  Every spin is bounded (XCHG_TIMEOUT_NS):
+// a missing peer fails the request, it does not hang the GPU.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace siesta {
+
+constexpr unsigned long long XCHG_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+
+struct XCtrl {
+    XHeader hdr;                                 // header of the block in this region's data area
+    unsigned long long ready[XCHG_MAX_RANKS];    // ready[p]: written by rank p - its block of operation `value` is complete
+    unsigned long long ack[XCHG_MAX_RANKS];      // ack[p]:   written by rank p - it has pulled my block of operation `value`
+};
+static_assert(sizeof(XCtrl) <= XCHG_CTRL_BYTES, "control page");
+
+struct XPeers {
+    char* region[XCHG_MAX_RANKS];
+};
+
+struct Exchange {
+    Ctx* ctx = nullptr;
+    int world = 1, rank = 0;
+    char* region = nullptr;
+    size_t cap_bytes = 0;
+    XPeers peers;
+    bool ipc[XCHG_MAX_RANKS];
+    bool connected[XCHG_MAX_RANKS];
+    unsigned long long seq = 0;
+    cudaStream_t stream = nullptr;
+    XHeader* d_hdrs = nullptr;   // [world] headers as fetched by the signal kernel
+    XHeader* h_hdrs = nullptr;   // pinned copy
+    std::mutex mu;               // one collective at a time per exchange
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spins until *p >= want; false on timeout
+__device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned long long want) {
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(p) < want) {
+        if (global_ns() - t0 > XCHG_TIMEOUT_NS) return false;
+        __nanosleep(200);
+    }
+    return true;
+}
+
+__global__ void xchg_wait_acks_kernel(XCtrl* me, int world, int rank, unsigned long long seq_prev, int* timed_out) {
+    const int p = threadIdx.x;
+    if (p < world && p != rank && !spin_until(&me->ack[p], seq_prev)) atomicOr(timed_out, 1);
+}
+
+__global__ void xchg_signal_kernel(const __grid_constant__ XPeers peers, int world, int rank, unsigned long long seq, XHeader* d_hdrs,
+                                   int* timed_out) {
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    __threadfence_system();   // the block written by the kernels before this one is visible system-wide before the flag
+    st_release_sys(&reinterpret_cast<XCtrl*>(peers.region[p])->ready[rank], seq);
+    const bool ok = spin_until(&reinterpret_cast<XCtrl*>(peers.region[rank])->ready[p], seq);
+    XHeader h;
+    if (ok) {
+        const volatile uint4* src = reinterpret_cast<const volatile uint4*>(&reinterpret_cast<XCtrl*>(peers.region[p])->hdr);
+        uint4* dst = reinterpret_cast<uint4*>(&h);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(XHeader) / 16); ++i) {
+            uint4 v;
+            v.x = src[i].x; v.y = src[i].y; v.z = src[i].z; v.w = src[i].w;
+            dst[i] = v;
+        }
+    } else {
+        memset(&h, 0, sizeof(h));
+        h.status = XST_TIMEOUT;
+        atomicOr(timed_out, 1);
+    }
+    d_hdrs[p] = h;
+}
+
+__global__ void xchg_ack_kernel(const __grid_constant__ XPeers peers, int world, int rank, unsigned long long seq) {
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    __threadfence_system();
+    st_release_sys(&reinterpret_cast<XCtrl*>(peers.region[p])->ack[rank], seq);
+}
+
+// ------------------------------------------------------------------------------------------------ pull + decode
+struct XDecode {
+    int world;
+    const char* data[XCHG_MAX_RANKS];   // data areas of all ranks (mine included)
+    const XHeader* hdrs;                // [world], device copy
+    int64_t tb[XCHG_MAX_RANKS + 1], ob[XCHG_MAX_RANKS + 1], eb[XCHG_MAX_RANKS + 1], rb[XCHG_MAX_RANKS + 1];  // exclusive prefixes
+    int64_t *trace_idx, *occ_off, *ev_off;
+    int32_t *pos, *rank, *act;
+    int64_t* ts;
+    int64_t* err;
+};
+
+// Uniform blocks (one occurrence per trace, K events per occurrence): a CTA takes tiles of TE events of one rank.  The
+// tile's four event sections come in with 16-byte loads (whole lines over NVLink), are widened out of shared memory and
+// leave as coalesced 4- and 8-byte stores at the rank's place in the joined list.
+constexpr int XD_THREADS = 256;
+constexpr int XD_TE = 2048;
+__global__ void __launch_bounds__(XD_THREADS) xchg_decode_uniform_kernel(const __grid_constant__ XDecode D) {
+    __shared__ __align__(16) uint16_t s_pos[XD_TE];
+    __shared__ __align__(16) uint8_t s_rank[XD_TE];
+    __shared__ __align__(16) uint16_t s_act[XD_TE];
+    __shared__ __align__(16) int32_t s_delta[XD_TE];
+    __shared__ long long s_base[XD_TE + 1];
+    const int r = blockIdx.y;
+    const XHeader h = D.hdrs[r];
+    if (h.status) return;
+    const int K = h.uniform_k;
+    const char* data = D.data[r];
+    const int tid = threadIdx.x;
+    const int64_t n_ev = h.n_ev, n_tr = h.n_tr;
+    const int64_t eb = D.eb[r], tb = D.tb[r];
+    const long long unit = h.seconds ? 1000 : 1;
+    const uint32_t* g_trace = reinterpret_cast<const uint32_t*>(data + h.o_trace);
+    const long long* g_base = reinterpret_cast<const long long*>(data + h.o_base);
+    for (int64_t e0 = (int64_t)blockIdx.x * XD_TE; e0 < n_ev; e0 += (int64_t)gridDim.x * XD_TE) {
+        const int cnt = (int)min((int64_t)XD_TE, n_ev - e0);
+        // 16-byte chunks that hold at least one event of the tile (sections are 256-byte aligned and e0 is a multiple
+        // of 2048: aligned; a chunk may end past n_ev: still inside the section's capacity)
+        {
+            const uint4* gp = reinterpret_cast<const uint4*>(data + h.o_pos) + e0 / 8;
+            if (tid * 8 < cnt) reinterpret_cast<uint4*>(s_pos)[tid] = __ldcv(gp + tid);
+            if (h.all_cols) {
+                const uint4* gr = reinterpret_cast<const uint4*>(data + h.o_rank) + e0 / 16;
+                const uint4* ga = reinterpret_cast<const uint4*>(data + h.o_act) + e0 / 8;
+                const uint4* gd = reinterpret_cast<const uint4*>(data + h.o_delta) + e0 / 4;
+                if (tid * 16 < cnt) reinterpret_cast<uint4*>(s_rank)[tid] = __ldcv(gr + tid);
+                if (tid * 8 < cnt) reinterpret_cast<uint4*>(s_act)[tid] = __ldcv(ga + tid);
+                if (tid * 4 < cnt) reinterpret_cast<uint4*>(s_delta)[tid] = __ldcv(gd + tid);
+                if ((tid + XD_THREADS) * 4 < cnt) reinterpret_cast<uint4*>(s_delta)[tid + XD_THREADS] = __ldcv(gd + tid + XD_THREADS);
+                const int64_t t0 = e0 / K, t1 = (e0 + cnt - 1) / K;   // traces that own the tile's events
+                for (int64_t t = t0 + tid; t <= t1; t += XD_THREADS) s_base[t - t0] = __ldcv(g_base + t);
+            }
+        }
+        __syncthreads();
+        const int64_t t0 = e0 / K;
+        for (int i = tid; i < cnt; i += XD_THREADS) {
+            const int64_t e = e0 + i;
+            D.pos[eb + e] = (int32_t)s_pos[i];
+            if (h.all_cols) {
+                D.rank[eb + e] = (int32_t)s_rank[i];
+                D.act[eb + e] = (int32_t)s_act[i];
+                D.ts[eb + e] = s_base[e / K - t0] + (long long)s_delta[i] * unit;
+            }
+        }
+        __syncthreads();
+    }
+    for (int64_t t = (int64_t)blockIdx.x * XD_THREADS + tid; t < n_tr; t += (int64_t)gridDim.x * XD_THREADS) {
+        D.trace_idx[tb + t] = h.trace_base + (int64_t)__ldcv(g_trace + t);
+        D.occ_off[tb + t] = tb + t;            // one occurrence per trace: occurrence index == trace index
+        D.ev_off[tb + t] = eb + t * K;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * XD_THREADS + tid; i < h.n_err; i += (int64_t)gridDim.x * XD_THREADS)
+        D.err[D.rb[r] + i] = h.trace_base + __ldcv(reinterpret_cast<const long long*>(data + h.o_err) + i);
+}
+
+// General blocks (any number of occurrences per trace and of events per occurrence): one thread per trace.
+__global__ void __launch_bounds__(XD_THREADS) xchg_decode_general_kernel(const __grid_constant__ XDecode D) {
+    const int r = blockIdx.y;
+    const XHeader h = D.hdrs[r];
+    if (h.status) return;
+    const char* data = D.data[r];
+    const uint32_t* g_trace = reinterpret_cast<const uint32_t*>(data + h.o_trace);
+    const long long* g_base = reinterpret_cast<const long long*>(data + h.o_base);
+    const uint32_t* g_occ = reinterpret_cast<const uint32_t*>(data + h.o_occ_off);
+    const uint32_t* g_evo = reinterpret_cast<const uint32_t*>(data + h.o_ev_off);
+    const uint16_t* g_pos = reinterpret_cast<const uint16_t*>(data + h.o_pos);
+    const uint8_t* g_rank = reinterpret_cast<const uint8_t*>(data + h.o_rank);
+    const uint16_t* g_act = reinterpret_cast<const uint16_t*>(data + h.o_act);
+    const int32_t* g_delta = reinterpret_cast<const int32_t*>(data + h.o_delta);
+    const int64_t tb = D.tb[r], ob = D.ob[r], eb = D.eb[r];
+    const long long unit = h.seconds ? 1000 : 1;
+    for (int64_t t = (int64_t)blockIdx.x * XD_THREADS + threadIdx.x; t < h.n_tr; t += (int64_t)gridDim.x * XD_THREADS) {
+        D.trace_idx[tb + t] = h.trace_base + (int64_t)__ldcv(g_trace + t);
+        const int64_t o0 = __ldcv(g_occ + t), o1 = __ldcv(g_occ + t + 1);
+        D.occ_off[tb + t] = ob + o0;
+        const long long base = h.all_cols ? __ldcv(g_base + t) : 0;
+        for (int64_t o = o0; o < o1; ++o) {
+            const int64_t a = __ldcv(g_evo + o), b = __ldcv(g_evo + o + 1);
+            D.ev_off[ob + o] = eb + a;
+            for (int64_t e = a; e < b; ++e) {
+                D.pos[eb + e] = (int32_t)__ldcv(g_pos + e);
+                if (h.all_cols) {
+                    D.rank[eb + e] = (int32_t)__ldcv(g_rank + e);
+                    D.act[eb + e] = (int32_t)__ldcv(g_act + e);
+                    D.ts[eb + e] = base + (long long)__ldcv(g_delta + e) * unit;
+                }
+            }
+        }
+    }
+    for (int64_t i = (int64_t)blockIdx.x * XD_THREADS + threadIdx.x; i < h.n_err; i += (int64_t)gridDim.x * XD_THREADS)
+        D.err[D.rb[r] + i] = h.trace_base + __ldcv(reinterpret_cast<const long long*>(data + h.o_err) + i);
+}
+
+__global__ void xchg_tail_kernel(int64_t* occ_off, int64_t n_tr, int64_t n_occ, int64_t* ev_off, int64_t n_ev) {
+    occ_off[n_tr] = n_occ;
+    ev_off[n_occ] = n_ev;
+}
+
+// all-reduce of int64 arrays that sit at the start of every rank's data area: out[i] = op over the ranks, in rank order
+__global__ void xchg_reduce_kernel(const __grid_constant__ XPeers peers, int world, int64_t n, int op, int64_t* out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        long long acc = __ldcv(reinterpret_cast<const long long*>(peers.region[0] + XCHG_CTRL_BYTES) + i);
+        for (int p = 1; p < world; ++p) {
+            const long long v = __ldcv(reinterpret_cast<const long long*>(peers.region[p] + XCHG_CTRL_BYTES) + i);
+            acc = op == SIESTA_REDUCE_SUM ? acc + v : (op == SIESTA_REDUCE_MIN ? (v < acc ? v : acc) : (v > acc ? v : acc));
+        }
+        out[i] = acc;
+    }
+}
+
+struct DevMatchesImplX {   // layout-compatible with detect.cu's DevMatchesImpl (siesta_dev_matches_free releases it)
+    void* bufs[8];
+    cudaStream_t free_stream;
+    int device;
+};
+
+static int check_ready(Exchange* x, const char* who) {
+    if (!x) {
+        set_error(std::string(who) + ": null exchange");
+        return SIESTA_E_INVALID;
+    }
+    for (int p = 0; p < x->world; ++p)
+        if (!x->connected[p]) {
+            set_error(std::string(who) + ": rank " + std::to_string(p) + " is not connected (siesta_exchange_import / _connect_local)");
+            return SIESTA_E_INVALID;
+        }
+    return SIESTA_OK;
+}
+
+}  // namespace siesta
+
+using namespace siesta;
+
+extern "C" int siesta_exchange_create(siesta_ctx* ctx, int32_t world, int32_t rank, int64_t capacity_bytes, siesta_exchange** out) {
+    if (!ctx || !out || world < 1 || world > XCHG_MAX_RANKS || rank < 0 || rank >= world || capacity_bytes < 0) {
+        set_error("siesta_exchange_create: bad argument (1 <= world <= 16, 0 <= rank < world)");
+        return SIESTA_E_INVALID;
+    }
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    SIESTA_CUDA_OK(cudaSetDevice(c->device));
+    Exchange* x = new Exchange();
+    x->ctx = c;
+    x->world = world;
+    x->rank = rank;
+    x->cap_bytes = ((size_t)capacity_bytes + 255) & ~(size_t)255;
+    std::memset(&x->peers, 0, sizeof(x->peers));
+    std::memset(x->ipc, 0, sizeof(x->ipc));
+    std::memset(x->connected, 0, sizeof(x->connected));
+    // plain cudaMalloc: IPC handles cannot be taken of stream-ordered pool memory
+    cudaError_t e = cudaMalloc((void**)&x->region, XCHG_CTRL_BYTES + x->cap_bytes);
+    if (e != cudaSuccess) {
+        set_error(std::string("siesta_exchange_create: cudaMalloc(") + std::to_string(XCHG_CTRL_BYTES + x->cap_bytes) + "): " + cudaGetErrorString(e));
+        delete x;
+        return SIESTA_E_NOMEM;
+    }
+    e = cudaMemset(x->region, 0, XCHG_CTRL_BYTES);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        // Load every kernel and driver-internal copy path a collective uses NOW: with lazy module loading the first
+        // launch of a function may wait for the device to drain, and inside a collective another rank of this process
+        // may already be spinning on this one (ranks that share a device in the tests; one JVM driving all GPUs).
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, xchg_wait_acks_kernel);
+        cudaFuncGetAttributes(&fa, xchg_signal_kernel);
+        cudaFuncGetAttributes(&fa, xchg_ack_kernel);
+        cudaFuncGetAttributes(&fa, xchg_decode_uniform_kernel);
+        cudaFuncGetAttributes(&fa, xchg_decode_general_kernel);
+        cudaFuncGetAttributes(&fa, xchg_tail_kernel);
+        cudaFuncGetAttributes(&fa, xchg_reduce_kernel);
+        XHeader warm;
+        std::memset(&warm, 0, sizeof(warm));
+        cudaMemcpyAsync(x->region, &warm, sizeof(warm), cudaMemcpyHostToDevice, x->stream);
+        cudaMemcpyAsync(x->region + XCHG_CTRL_BYTES, x->region, std::min<size_t>(256, x->cap_bytes), cudaMemcpyDeviceToDevice, x->stream);
+        cudaMemsetAsync(x->region + XCHG_CTRL_BYTES, 0, std::min<size_t>(256, x->cap_bytes), x->stream);
+        xchg_reduce_kernel<<<1, 32, 0, x->stream>>>(x->peers, 0, 0, SIESTA_REDUCE_SUM, nullptr);
+        xchg_tail_kernel<<<1, 1, 0, x->stream>>>(reinterpret_cast<int64_t*>(x->region + XCHG_CTRL_BYTES), 0, 0,
+                                                 reinterpret_cast<int64_t*>(x->region + XCHG_CTRL_BYTES), 0);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMalloc((void**)&x->d_hdrs, sizeof(XHeader) * XCHG_MAX_RANKS + 256);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&x->h_hdrs, sizeof(XHeader) * XCHG_MAX_RANKS + 256, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        set_error(std::string("siesta_exchange_create: ") + cudaGetErrorString(e));
+        siesta_exchange_free(reinterpret_cast<siesta_exchange*>(x));
+        return SIESTA_E_CUDA;
+    }
+    x->peers.region[rank] = x->region;
+    x->connected[rank] = true;
+    *out = reinterpret_cast<siesta_exchange*>(x);
+    return SIESTA_OK;
+}
+
+extern "C" int siesta_exchange_export(siesta_exchange* xh, void* handle_out) {
+    Exchange* x = reinterpret_cast<Exchange*>(xh);
+    if (!x || !handle_out) {
+        set_error("siesta_exchange_export: null argument");
+        return SIESTA_E_INVALID;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == SIESTA_EXCHANGE_HANDLE_BYTES, "IPC handle size");
+    SIESTA_CUDA_OK(cudaSetDevice(x->ctx->device));
+    cudaIpcMemHandle_t h;
+    SIESTA_CUDA_OK(cudaIpcGetMemHandle(&h, x->region));
+    std::memcpy(handle_out, &h, sizeof(h));
+    return SIESTA_OK;
+}
+
+extern "C" int siesta_exchange_import(siesta_exchange* xh, int32_t peer_rank, const void* handle) {
+    Exchange* x = reinterpret_cast<Exchange*>(xh);
+    if (!x || !handle || peer_rank < 0 || peer_rank >= x->world || peer_rank == x->rank) {
+        set_error("siesta_exchange_import: bad argument");
+        return SIESTA_E_INVALID;
+    }
+    SIESTA_CUDA_OK(cudaSetDevice(x->ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    SIESTA_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    x->peers.region[peer_rank] = reinterpret_cast<char*>(p);
+    x->ipc[peer_rank] = true;
+    x->connected[peer_rank] = true;
+    return SIESTA_OK;
+}
+
+extern "C" int siesta_exchange_connect_local(siesta_exchange* xh, int32_t peer_rank, siesta_exchange* peer) {
+    Exchange* x = reinterpret_cast<Exchange*>(xh);
+    Exchange* y = reinterpret_cast<Exchange*>(peer);
+    if (!x || !y || peer_rank < 0 || peer_rank >= x->world || peer_rank == x->rank || y->rank != peer_rank || y->world != x->world) {
+        set_error("siesta_exchange_connect_local: bad argument");
+        return SIESTA_E_INVALID;
+    }
+    if (y->ctx->device != x->ctx->device) {
+        SIESTA_CUDA_OK(cudaSetDevice(x->ctx->device));
+        int can = 0;
+        SIESTA_CUDA_OK(cudaDeviceCanAccessPeer(&can, x->ctx->device, y->ctx->device));
+        if (!can) {
+            set_error("siesta_exchange_connect_local: no peer access between the two devices");
+            return SIESTA_E_CUDA;
+        }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(y->ctx->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+            set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            return SIESTA_E_CUDA;
+        }
+        cudaGetLastError();
+    }
+    x->peers.region[peer_rank] = y->region;
+    x->connected[peer_rank] = true;
+    return SIESTA_OK;
+}
+
+extern "C" void siesta_exchange_free(siesta_exchange* xh) {
+    Exchange* x = reinterpret_cast<Exchange*>(xh);
+    if (!x) return;
+    cudaSetDevice(x->ctx->device);
+    if (x->stream) cudaStreamSynchronize(x->stream);
+    for (int p = 0; p < x->world; ++p)
+        if (x->ipc[p] && x->peers.region[p]) cudaIpcCloseMemHandle(x->peers.region[p]);
+    if (x->region) cudaFree(x->region);
+    if (x->d_hdrs) cudaFree(x->d_hdrs);
+    if (x->h_hdrs) cudaFreeHost(x->h_hdrs);
+    if (x->stream) cudaStreamDestroy(x->stream);
+    delete x;
+}
+
+extern "C" int64_t siesta_exchange_required_bytes(siesta_log* log, const siesta_nfa* nfa, uint32_t flags) {
+    Log* L = reinterpret_cast<Log*>(log);
+    if (!L || !nfa) return -1;
+    return detect_pack_required_bytes(L->n_traces, L->n_events, detect_uniform_k(nfa, flags), !(flags & SIESTA_F_NO_EVENT_COLUMNS),
+                                      (flags & SIESTA_F_RETURN_ALL) != 0);
+}
+
+extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, uint32_t flags, siesta_exchange* xh,
+                                       siesta_dev_matches* out, siesta_exchange_stats* stats) {
+    Exchange* x = reinterpret_cast<Exchange*>(xh);
+    Log* L = reinterpret_cast<Log*>(log);
+    if (!L || !nfa || !out) {
+        set_error("siesta_detect_allgather: null argument");
+        return SIESTA_E_INVALID;
+    }
+    int rc = check_ready(x, "siesta_detect_allgather");
+    if (rc) return rc;
+    if (L->ctx != x->ctx) {
+        set_error("siesta_detect_allgather: the log and the exchange belong to different contexts");
+        return SIESTA_E_INVALID;
+    }
+    std::memset(out, 0, sizeof(*out));
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    std::lock_guard<std::mutex> lock(x->mu);
+    SIESTA_CUDA_OK(cudaSetDevice(x->ctx->device));
+    cudaStream_t stream = x->stream;
+    const int world = x->world, rank = x->rank;
+    XCtrl* me = reinterpret_cast<XCtrl*>(x->region);
+    const unsigned long long seq = ++x->seq;
+
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    struct EvGuard {
+        cudaEvent_t* e;
+        ~EvGuard() { for (int i = 0; i < 4; ++i) if (e[i]) cudaEventDestroy(e[i]); }
+    } ev_guard{ev};
+    for (int i = 0; i < 4; ++i) SIESTA_CUDA_OK(cudaEventCreate(&ev[i]));
+    int* d_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(x->d_hdrs) + sizeof(XHeader) * XCHG_MAX_RANKS);
+    int* h_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(x->h_hdrs) + sizeof(XHeader) * XCHG_MAX_RANKS);
+    SIESTA_CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), stream));
+
+    // ---- the scan of my shard (kernels K1 / K1-P), enqueued without waiting
+    SIESTA_CUDA_OK(cudaEventRecord(ev[0], stream));
+    DetectPending* q = nullptr;
+    rc = detect_device_begin_impl(L, nfa, nullptr, 0, flags, stream, RebaseOffsets{0, 0, 0}, &q);
+    if (rc) {
+        // keep the collective in step: peers wait for my block of this operation - announce a failed one
+        XHeader fail;
+        std::memset(&fail, 0, sizeof(fail));
+        fail.seq = seq;
+        fail.status = XST_LIMITS;
+        cudaMemcpyAsync(&me->hdr, &fail, sizeof(fail), cudaMemcpyHostToDevice, stream);
+    } else {
+        // ---- my block into my region: wait for the peers' acks of the previous operation first
+        xchg_wait_acks_kernel<<<1, 32, 0, stream>>>(me, world, rank, seq - 1, d_flag);
+        SIESTA_LAUNCHED();
+        PackTarget tgt{x->region + XCHG_CTRL_BYTES, (int64_t)x->cap_bytes, &me->hdr, seq};
+        const int rc2 = detect_device_pack_impl(q, tgt);
+        if (rc2) {
+            rc = rc2;
+            XHeader fail;
+            std::memset(&fail, 0, sizeof(fail));
+            fail.seq = seq;
+            fail.status = XST_STAGING;
+            cudaMemcpyAsync(&me->hdr, &fail, sizeof(fail), cudaMemcpyHostToDevice, stream);
+        }
+    }
+    const std::string first_error = rc ? std::string(siesta_last_error()) : std::string();
+    SIESTA_CUDA_OK(cudaEventRecord(ev[1], stream));
+    // ---- announce, wait for every rank, fetch the headers
+    xchg_signal_kernel<<<1, 32, 0, stream>>>(x->peers, world, rank, seq, x->d_hdrs, d_flag);
+    SIESTA_LAUNCHED();
+    SIESTA_CUDA_OK(cudaMemcpyAsync(x->h_hdrs, x->d_hdrs, sizeof(XHeader) * XCHG_MAX_RANKS + 256, cudaMemcpyDeviceToHost, stream));
+    SIESTA_CUDA_OK(cudaEventRecord(ev[2], stream));
+    SIESTA_CUDA_OK(cudaStreamSynchronize(stream));   // host wait 1 of 2: the sizes of all blocks
+    const float k1_ms = detect_pending_k1_ms(q);
+    if (q) detect_pending_discard(q);
+
+    int bad = *h_flag ? XST_TIMEOUT : 0;
+    int64_t tb[XCHG_MAX_RANKS + 1] = {0}, ob[XCHG_MAX_RANKS + 1] = {0}, eb[XCHG_MAX_RANKS + 1] = {0}, rb[XCHG_MAX_RANKS + 1] = {0};
+    bool uniform = true, all_cols = !(flags & SIESTA_F_NO_EVENT_COLUMNS);
+    int64_t emitted = 0;
+    for (int p = 0; p < world; ++p) {
+        const XHeader& h = x->h_hdrs[p];
+        bad |= h.status;
+        if (!h.status && h.seq != seq) bad |= XST_TIMEOUT;   // a peer is out of step
+        tb[p + 1] = tb[p] + h.n_tr;
+        ob[p + 1] = ob[p] + h.n_occ;
+        eb[p + 1] = eb[p] + h.n_ev;
+        rb[p + 1] = rb[p] + h.n_err;
+        uniform = uniform && h.uniform_k > 0;
+        emitted += h.n_emitted;
+    }
+    if (bad || rc) {
+        // every rank saw the same headers: all of them fail this operation, and all acknowledge it so that the next one
+        // can overwrite the regions
+        xchg_ack_kernel<<<1, 32, 0, stream>>>(x->peers, world, rank, seq);
+        SIESTA_LAUNCHED();
+        cudaStreamSynchronize(stream);
+        if (rc) {
+            set_error(first_error);
+            return rc;
+        }
+        if (bad & XST_TIMEOUT) {
+            set_error("exchange: a peer did not arrive within the time limit (or is out of step)");
+            return SIESTA_E_CUDA;
+        }
+        if (bad & XST_LIMITS) {
+            set_error("exchange: a trace exceeds the engine limits on some rank (see siesta_detect)");
+            return SIESTA_E_UNSUPPORTED;
+        }
+        if (bad & XST_RANGE) {
+            set_error("exchange: a value does not fit the compact block (trace longer than 65 535 events, activity id >= 65 536, "
+                      "a timestamp more than 2^31 units from the trace's first reported event)");
+            return SIESTA_E_UNSUPPORTED;
+        }
+        set_error("exchange: staging overflow or too many reference errors on some rank");
+        return SIESTA_E_NOMEM;
+    }
+    const int64_t n_tr = tb[world], n_occ = ob[world], n_ev = eb[world], n_err = rb[world];
+
+    // ---- the joined result: one allocation, the library's standard block layout
+    void* fin = nullptr;
+    size_t f_off = 0;
+    auto fcarve = [&f_off](size_t bytes) {
+        const size_t at = f_off;
+        f_off += (bytes + 255) & ~(size_t)255;
+        return at;
+    };
+    const size_t q_trace = fcarve((size_t)n_tr * 8), q_occ = fcarve((size_t)(n_tr + 1) * 8), q_evoff = fcarve((size_t)(n_occ + 1) * 8),
+                 q_pos = fcarve((size_t)n_ev * 4), q_err = fcarve((size_t)n_err * 8);
+    size_t q_rank = 0, q_act = 0, q_ts = 0;
+    if (all_cols) {
+        q_rank = fcarve((size_t)n_ev * 4);
+        q_act = fcarve((size_t)n_ev * 4);
+        q_ts = fcarve((size_t)n_ev * 8);
+    }
+    {
+        const cudaError_t e = cudaMallocAsync(&fin, f_off ? f_off : 16, stream);
+        if (e != cudaSuccess) {
+            set_error(std::string("exchange: cudaMalloc(joined result, ") + std::to_string(f_off) + "): " + cudaGetErrorString(e));
+            xchg_ack_kernel<<<1, 32, 0, stream>>>(x->peers, world, rank, seq);
+            cudaStreamSynchronize(stream);
+            return SIESTA_E_NOMEM;
+        }
+    }
+    char* fb = reinterpret_cast<char*>(fin);
+    XDecode D;
+    std::memset(&D, 0, sizeof(D));
+    D.world = world;
+    for (int p = 0; p < world; ++p) D.data[p] = x->peers.region[p] + XCHG_CTRL_BYTES;
+    D.hdrs = x->d_hdrs;
+    std::memcpy(D.tb, tb, sizeof(tb));
+    std::memcpy(D.ob, ob, sizeof(ob));
+    std::memcpy(D.eb, eb, sizeof(eb));
+    std::memcpy(D.rb, rb, sizeof(rb));
+    D.trace_idx = reinterpret_cast<int64_t*>(fb + q_trace);
+    D.occ_off = reinterpret_cast<int64_t*>(fb + q_occ);
+    D.ev_off = reinterpret_cast<int64_t*>(fb + q_evoff);
+    D.pos = reinterpret_cast<int32_t*>(fb + q_pos);
+    D.err = reinterpret_cast<int64_t*>(fb + q_err);
+    D.rank = all_cols ? reinterpret_cast<int32_t*>(fb + q_rank) : nullptr;
+    D.act = all_cols ? reinterpret_cast<int32_t*>(fb + q_act) : nullptr;
+    D.ts = all_cols ? reinterpret_cast<int64_t*>(fb + q_ts) : nullptr;
+    {
+        int64_t biggest = 1;
+        for (int p = 0; p < world; ++p) biggest = std::max(biggest, uniform ? x->h_hdrs[p].n_ev / XD_TE + 1 : x->h_hdrs[p].n_tr / XD_THREADS + 1);
+        int gx = (int)std::min<int64_t>(biggest, (int64_t)x->ctx->sm_count * 8 / world + 1);
+        if (const char* env = std::getenv("SIESTA_XCHG_DECODE_CTAS")) {
+            const int v = std::atoi(env);
+            if (v >= 1) gx = v;
+        }
+        const dim3 grid((unsigned)gx, (unsigned)world);
+        if (uniform) xchg_decode_uniform_kernel<<<grid, XD_THREADS, 0, stream>>>(D);
+        else xchg_decode_general_kernel<<<grid, XD_THREADS, 0, stream>>>(D);
+        SIESTA_LAUNCHED();
+    }
+    xchg_tail_kernel<<<1, 1, 0, stream>>>(D.occ_off, n_tr, n_occ, D.ev_off, n_ev);
+    SIESTA_LAUNCHED();
+    xchg_ack_kernel<<<1, 32, 0, stream>>>(x->peers, world, rank, seq);
+    SIESTA_LAUNCHED();
+    SIESTA_CUDA_OK(cudaEventRecord(ev[3], stream));
+    if (n_err > 0) {   // the (rare) error list in ascending order
+        std::vector<int64_t> herr((size_t)n_err);
+        SIESTA_CUDA_OK(cudaMemcpyAsync(herr.data(), D.err, (size_t)n_err * 8, cudaMemcpyDeviceToHost, stream));
+        SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+        std::sort(herr.begin(), herr.end());
+        SIESTA_CUDA_OK(cudaMemcpyAsync(D.err, herr.data(), (size_t)n_err * 8, cudaMemcpyHostToDevice, stream));
+    }
+    SIESTA_CUDA_OK(cudaStreamSynchronize(stream));   // host wait 2 of 2: the joined list is complete on this rank
+    float ms_scan = 0.f, ms_wait = 0.f, ms_pull = 0.f;
+    cudaEventElapsedTime(&ms_scan, ev[0], ev[1]);
+    cudaEventElapsedTime(&ms_wait, ev[1], ev[2]);
+    cudaEventElapsedTime(&ms_pull, ev[2], ev[3]);
+
+    DevMatchesImplX* impl = new DevMatchesImplX();
+    std::memset(impl, 0, sizeof(*impl));
+    impl->bufs[0] = fin;
+    impl->free_stream = x->ctx->stream;
+    impl->device = x->ctx->device;
+    out->n_traces = n_tr;
+    out->n_occurrences = n_occ;
+    out->n_events = n_ev;
+    const bool counted = (flags & (SIESTA_F_COUNT_MATCHES | SIESTA_F_RETURN_ALL | SIESTA_F_LITERAL_RUNS)) != 0;
+    out->n_matches_emitted = counted ? emitted : -1;
+    out->n_ref_errors = n_err;
+    out->kernel_ms = ms_scan + ms_wait + ms_pull;
+    out->detect_ms = k1_ms;
+    out->d_trace_idx = D.trace_idx;
+    out->d_occ_off = D.occ_off;
+    out->d_ev_off = D.ev_off;
+    out->d_ev_pos = D.pos;
+    out->d_ev_rank = D.rank;
+    out->d_ev_act = D.act;
+    out->d_ev_ts_ms = D.ts;
+    out->d_err_trace_idx = D.err;
+    out->d_block = fin;
+    out->block_bytes = (int64_t)f_off;
+    out->impl = impl;
+    if (stats) {
+        const XHeader& mine = x->h_hdrs[rank];
+        stats->local_traces = mine.n_tr;
+        stats->local_occurrences = mine.n_occ;
+        stats->local_events = mine.n_ev;
+        stats->k1_ms = k1_ms;
+        stats->scan_ms = ms_scan;
+        stats->wait_ms = ms_wait;
+        stats->pull_ms = ms_pull;
+        int64_t wire = 0;
+        for (int p = 0; p < world; ++p) {
+            if (p == rank) continue;
+            const XHeader& h = x->h_hdrs[p];
+            wire += h.n_tr * (4 + (all_cols ? 8 : 0)) + (h.uniform_k ? 0 : 4 * (h.n_tr + h.n_occ + 2)) + h.n_ev * (all_cols ? 9 : 2) + 8 * h.n_err;
+        }
+        stats->pulled_bytes = wire;
+    }
+    return SIESTA_OK;
+}
+
+extern "C" int siesta_exchange_allreduce_i64(siesta_exchange* xh, int64_t* d_buf, int64_t n, int32_t op, void* stream_) {
+    Exchange* x = reinterpret_cast<Exchange*>(xh);
+    int rc = check_ready(x, "siesta_exchange_allreduce_i64");
+    if (rc) return rc;
+    if (!d_buf || n < 0 || (op != SIESTA_REDUCE_SUM && op != SIESTA_REDUCE_MIN && op != SIESTA_REDUCE_MAX)) {
+        set_error("siesta_exchange_allreduce_i64: bad argument");
+        return SIESTA_E_INVALID;
+    }
+    if ((size_t)n * 8 > x->cap_bytes) {
+        set_error("siesta_exchange_allreduce_i64: the array does not fit the exchange region");
+        return SIESTA_E_NOMEM;
+    }
+    std::lock_guard<std::mutex> lock(x->mu);
+    SIESTA_CUDA_OK(cudaSetDevice(x->ctx->device));
+    cudaStream_t stream = x->stream;
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream_);
+    const unsigned long long seq = ++x->seq;
+    XCtrl* me = reinterpret_cast<XCtrl*>(x->region);
+    int* d_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(x->d_hdrs) + sizeof(XHeader) * XCHG_MAX_RANKS);
+    int* h_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(x->h_hdrs) + sizeof(XHeader) * XCHG_MAX_RANKS);
+    // order after the producer of d_buf on the caller's stream
+    cudaEvent_t evu;
+    SIESTA_CUDA_OK(cudaEventCreateWithFlags(&evu, cudaEventDisableTiming));
+    cudaEventRecord(evu, user ? user : x->ctx->stream);
+    cudaStreamWaitEvent(stream, evu, 0);
+    cudaEventDestroy(evu);
+    SIESTA_CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), stream));
+    xchg_wait_acks_kernel<<<1, 32, 0, stream>>>(me, x->world, x->rank, seq - 1, d_flag);
+    SIESTA_LAUNCHED();
+    XHeader hd;
+    std::memset(&hd, 0, sizeof(hd));
+    hd.seq = seq;
+    SIESTA_CUDA_OK(cudaMemcpyAsync(&me->hdr, &hd, sizeof(hd), cudaMemcpyHostToDevice, stream));
+    if (n) SIESTA_CUDA_OK(cudaMemcpyAsync(x->region + XCHG_CTRL_BYTES, d_buf, (size_t)n * 8, cudaMemcpyDeviceToDevice, stream));
+    xchg_signal_kernel<<<1, 32, 0, stream>>>(x->peers, x->world, x->rank, seq, x->d_hdrs, d_flag);
+    SIESTA_LAUNCHED();
+    if (n) {
+        const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)x->ctx->sm_count * 4);
+        xchg_reduce_kernel<<<grid, 256, 0, stream>>>(x->peers, x->world, n, op, d_buf);
+        SIESTA_LAUNCHED();
+    }
+    xchg_ack_kernel<<<1, 32, 0, stream>>>(x->peers, x->world, x->rank, seq);
+    SIESTA_LAUNCHED();
+    SIESTA_CUDA_OK(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+    if (*h_flag) {
+        set_error("exchange: a peer did not arrive within the time limit");
+        return SIESTA_E_CUDA;
+    }
+    return SIESTA_OK;
+}

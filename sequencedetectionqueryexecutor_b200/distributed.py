@@ -363,6 +363,107 @@ def allreduce_explore(completions, sum_duration_ms, group=None):
     return completions, sum_duration_ms
 
 
+# ------------------------------------------------------------------------------------- exchange inside the library
+class MatchExchange:
+    """One process per GPU (torchrun): the library's own exchange (siesta_exchange_*, csrc/multi.cu) wired up over
+    torch.distributed.  torch only carries the 64-byte IPC handles and the capacity agreement at set-up; every request
+    afterwards runs inside libsiesta_gpu: the scan places its compact block in the rank's region, sizes travel in the
+    block's header, one kernel pulls all peers' blocks over NVLink and decodes them to the joined columns."""
+
+    def __init__(self, ctx, device, group=None):
+        self.ctx, self.device, self.group = ctx, device, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.x = None
+        self.capacity = 0
+
+    def _ensure(self, need):
+        """Collective: (re)create the exchanges when any rank needs a larger region."""
+        t = torch.tensor([need], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        need = int(t.item())
+        if self.x is not None and need <= self.capacity:
+            return
+        from . import api
+        if self.x is not None:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            self.x.close()
+        self.capacity = int(need * 1.25) + (1 << 20)
+        self.x = api.Exchange(self.ctx, self.world, self.rank, self.capacity)
+        mine = torch.frombuffer(bytearray(self.x.export()), dtype=torch.uint8).to(self.device)
+        handles = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(handles, mine, group=self.group)
+        handles = handles.cpu().view(self.world, -1)
+        for p in range(self.world):
+            if p != self.rank:
+                self.x.import_peer(p, bytes(handles[p].numpy().tobytes()))
+        dist.barrier(group=self.group)
+
+    def detect_allgather(self, log, nfa, flags=0):
+        """-> (api.DeviceMatches holding the match list of ALL ranks, ExchangeStats).  Collective."""
+        from . import api
+        key = (log.n_traces, log.n_events, bytes(nfa), flags)
+        if getattr(self, "_sized_for", None) != key:
+            self._ensure(api.exchange_required_bytes(log, nfa, flags))
+            self._sized_for = key
+        return self.x.detect_allgather(log, nfa, flags)
+
+    def allreduce_counts(self, packed, op=_abi.REDUCE_SUM):
+        if self.x is None or packed.numel() * 8 > self.capacity:
+            self._ensure(packed.numel() * 8)
+            self._sized_for = None
+        return self.x.allreduce_i64(packed, op, torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if self.x is not None:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            self.x.close()
+            self.x = None
+
+
+def joined_prefix(tensors, n_first_traces):
+    """The part of a joined match list (dict of device tensors, DeviceMatches.tensors()) that belongs to global traces
+    [0, n_first_traces): prefix slices, because the list is in trace order."""
+    tr = tensors["trace_idx"]
+    n = int(torch.searchsorted(tr, torch.tensor([n_first_traces], dtype=tr.dtype, device=tr.device)).item())
+    n_occ = int(tensors["occ_off"][n].item()) if tensors["occ_off"].numel() else 0
+    n_ev = int(tensors["ev_off"][n_occ].item()) if tensors["ev_off"].numel() else 0
+    out = {"trace_idx": tr[:n], "occ_off": tensors["occ_off"][:n + 1], "ev_off": tensors["ev_off"][:n_occ + 1],
+           "err_trace_idx": tensors["err_trace_idx"][tensors["err_trace_idx"] < n_first_traces]}
+    for k in ("ev_pos", "ev_rank", "ev_act", "ev_ts_ms"):
+        if k in tensors:
+            out[k] = tensors[k][:n_ev]
+    return out
+
+
+_COLS = ("trace_idx", "occ_off", "ev_off", "err_trace_idx", "ev_pos", "ev_rank", "ev_act", "ev_ts_ms")
+
+
+def send_columns(cols, dst, group=None):
+    """Point-to-point transfer of a dict of 1-D tensors (sizes first); the receiver calls recv_columns."""
+    dev = cols["trace_idx"].device
+    sizes = torch.tensor([cols[k].numel() if k in cols else -1 for k in _COLS], dtype=torch.int64, device=dev)
+    dist.send(sizes, dst, group=group)
+    for k in _COLS:
+        if k in cols and cols[k].numel():
+            dist.send(cols[k].contiguous(), dst, group=group)
+
+
+def recv_columns(src, device, group=None):
+    sizes = torch.zeros(len(_COLS), dtype=torch.int64, device=device)
+    dist.recv(sizes, src, group=group)
+    out = {}
+    for k, n in zip(_COLS, sizes.tolist()):
+        if n < 0:
+            continue
+        t = torch.zeros(n, dtype=_DT[k], device=device)
+        if n:
+            dist.recv(t, src, group=group)
+        out[k] = t
+    return out
+
+
 def to_match_result(g, n_matches_emitted=-1):
     """dict of tensors -> host MatchResult (for comparison with the oracle)."""
     r = _abi.MatchResult()

@@ -1,0 +1,192 @@
+"""The library's own multi-GPU exchange (csrc/multi.cu, siesta_exchange_*) on ONE device: a log is cut into shard logs,
+every shard gets its own exchange object (connected in-process), the shards run siesta_detect_allgather concurrently
+from host threads - scan, packed placement, signal, pull + decode - and EVERY rank's joined list must equal the oracle's
+result on the unsharded log.  The same code runs across processes / GPUs with IPC handles (tests/exchange_worker.py)."""
+import threading
+
+import numpy as np
+import pytest
+
+import oracle
+from sequencedetectionqueryexecutor_b200 import _abi as abi
+from tests import gen
+
+pytestmark = pytest.mark.gpu
+
+N_, P_, S_, X_, O_ = abi.STATE_NORMAL, abi.STATE_KLEENE_PLUS, abi.STATE_KLEENE_STAR, abi.STATE_NEGATIVE, abi.STATE_OR
+
+GAP6 = [dict(kind=N_, types=[0]), dict(kind=O_, types=[1, 2], preds=[(abi.ATTR_POSITION, abi.OP_LE, 0, 10)]),
+        dict(kind=X_, types=[3]), dict(kind=N_, types=[4]), dict(kind=N_, types=[5], preds=[(abi.ATTR_POSITION, abi.OP_GE, 3, 2)])]
+KLEENE = [dict(kind=P_, types=[0]), dict(kind=S_, types=[1], preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 600)])]
+ABC = [dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[2])]
+AB = [dict(kind=N_, types=[0]), dict(kind=N_, types=[1])]
+
+
+def _to_result(dm, device=0):
+    from sequencedetectionqueryexecutor_b200 import distributed as D
+    r = D.to_match_result(dm.tensors(device), dm.n_matches_emitted)
+    return r
+
+
+def _run_sharded(ctx, off, act, ts, n_act, nfa, flags, bounds):
+    """bounds: trace indices [b0=0, b1, ..., T]; returns the joined result as every rank sees it."""
+    from sequencedetectionqueryexecutor_b200 import api
+    world = len(bounds) - 1
+    logs = []
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        e0, e1 = int(off[lo]), int(off[hi])
+        lg = ctx.load_log(off[lo:hi + 1] - e0, act[e0:e1], ts[e0:e1], n_act)
+        lg.set_first_trace(lo)
+        logs.append(lg)
+    need = max(api.exchange_required_bytes(lg, nfa, flags) for lg in logs)
+    xs = [api.Exchange(ctx, world, r, need) for r in range(world)]
+    for a in xs:
+        for b in xs:
+            if a is not b:
+                a.connect_local(b)
+    out, err = [None] * world, [None] * world
+
+    def work(r, rounds):
+        try:
+            for _ in range(rounds):    # twice: the second request waits for the acks of the first
+                if out[r] is not None:
+                    out[r][0].close()
+                out[r] = xs[r].detect_allgather(logs[r], nfa, flags)
+        except Exception as e:  # noqa: BLE001
+            err[r] = e
+
+    th = [threading.Thread(target=work, args=(r, 2)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not any(err), err
+    res = [(_to_result(dm), st) for dm, st in out]
+    for dm, _ in out:
+        dm.close()
+    for x in xs:
+        x.close()
+    for lg in logs:
+        lg.close()
+    return res
+
+
+CASES = [
+    ("gap6 uniform block (K1-P)", GAP6, 0, dict(min_len=50, max_len=50, n_act=20)),
+    ("gap6, positions only", GAP6, abi.F_NO_EVENT_COLUMNS, dict(min_len=30, max_len=60, n_act=20)),
+    ("gap6 EventPos route", GAP6, abi.F_EVT_POS, dict(min_len=0, max_len=70, n_act=12)),
+    ("a+ b* within 10 min (general block)", KLEENE, 0, dict(min_len=100, max_len=100, n_act=20, max_gap_s=120)),
+    ("a b+ c (run-list engine)", ABC, 0, dict(min_len=5, max_len=40, n_act=6)),
+    ("A B returnAll (several occurrences per trace)", AB, abi.F_RETURN_ALL, dict(min_len=5, max_len=60, n_act=5)),
+    ("A B returnAll EventPos", AB, abi.F_RETURN_ALL | abi.F_EVT_POS, dict(min_len=5, max_len=60, n_act=5)),
+    ("no match at all", [dict(kind=N_, types=[0]), dict(kind=N_, types=[19])], 0, dict(min_len=10, max_len=20, n_act=3)),
+]
+
+
+@pytest.mark.parametrize("name,states,flags,shape", CASES, ids=[c[0] for c in CASES])
+def test_sharded_allgather_equals_unsharded_oracle(name, states, flags, shape):
+    from sequencedetectionqueryexecutor_b200 import api
+    n_act = shape["n_act"]
+    off, act, ts = gen.make_log(3000, shape["min_len"], shape["max_len"], n_act, seed=0xE8C4 + len(name),
+                                max_gap_s=shape.get("max_gap_s", 300), jitter_ms=True)
+    nfa = abi.make_nfa(states)
+    want = oracle.detect(off, act, ts, nfa, flags=flags)
+    T = len(off) - 1
+    with api.Context(0) as ctx:
+        for bounds in ([0, 1000, 1900, T], [0, 0, 1500, 1500, T]):   # three shards; four with two EMPTY shards
+            res = _run_sharded(ctx, off, act, ts, n_act, nfa, flags, bounds)
+            local = 0
+            for r, (got, st) in enumerate(res):
+                ok, why = got.same_as(want)
+                assert ok, (name, bounds, r, why)
+                local += st.local_traces
+            assert local == want.n_traces
+
+
+def test_long_and_unaligned_traces_cross_shards():
+    """Traces that leave K1-P for the staged kernels (more than 64 slots / 32 relevant events) inside a shard."""
+    from sequencedetectionqueryexecutor_b200 import api
+    off, act, ts = gen.make_log(1200, 0, 130, 9, seed=77, max_gap_s=50)
+    nfa = abi.make_nfa([dict(kind=N_, types=[0]), dict(kind=X_, types=[1]), dict(kind=N_, types=[2], preds=[(abi.ATTR_POSITION, abi.OP_GE, 0, 3)])])
+    want = oracle.detect(off, act, ts, nfa, flags=0)
+    with api.Context(0) as ctx:
+        for got, _ in _run_sharded(ctx, off, act, ts, 9, nfa, 0, [0, 333, 800, 1200]):
+            ok, why = got.same_as(want)
+            assert ok, why
+
+
+def test_allreduce_of_counts_over_peer_regions():
+    """siesta_exchange_allreduce_i64: declare counts of three shards summed on the device == counts of the whole log."""
+    import torch
+
+    from sequencedetectionqueryexecutor_b200 import api
+    off, act, ts = gen.make_log(2500, 0, 60, 9, seed=5)
+    want = oracle.declare_counts(off, act, 9, 30).packed
+    bounds = [0, 700, 1800, 2500]
+    with api.Context(0) as ctx:
+        logs = []
+        for r in range(3):
+            lo, hi = bounds[r], bounds[r + 1]
+            e0, e1 = int(off[lo]), int(off[hi])
+            logs.append(ctx.load_log(off[lo:hi + 1] - e0, act[e0:e1], ts[e0:e1], 9))
+        xs = [api.Exchange(ctx, 3, r, 1 << 20) for r in range(3)]
+        for a in xs:
+            for b in xs:
+                if a is not b:
+                    a.connect_local(b)
+        bufs = [torch.zeros(len(want), dtype=torch.int64, device="cuda:0") for _ in range(3)]
+        mins = [torch.tensor([5 - r, 100 + r, -7 * r], dtype=torch.int64, device="cuda:0") for r in range(3)]
+        err = [None] * 3
+
+        # (a device-wide synchronize inside a rank's thread would wait for another rank's spinning kernel: here the
+        # ranks share ONE device, so the counts are produced before the collective starts)
+        for r in range(3):
+            logs[r].declare_counts_device(bufs[r], 30)
+        torch.cuda.synchronize()
+
+        def work(r):
+            try:
+                xs[r].allreduce_i64(bufs[r], abi.REDUCE_SUM)
+                xs[r].allreduce_i64(mins[r], abi.REDUCE_MIN)
+            except Exception as e:  # noqa: BLE001
+                err[r] = e
+
+        th = [threading.Thread(target=work, args=(r,)) for r in range(3)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not any(err), err
+        for r in range(3):
+            assert np.array_equal(bufs[r].cpu().numpy(), want), r
+            assert mins[r].cpu().tolist() == [3, 100, -14]
+        for x in xs:
+            x.close()
+        for lg in logs:
+            lg.close()
+
+
+def test_exchange_rejects_an_unconnected_peer_and_a_small_region():
+    from sequencedetectionqueryexecutor_b200 import api
+    from sequencedetectionqueryexecutor_b200._lib import SiestaError
+    off, act, ts = gen.make_log(500, 20, 20, 6, seed=3)
+    nfa = abi.make_nfa(AB)
+    with api.Context(0) as ctx:
+        log = ctx.load_log(off, act, ts, 6)
+        x = api.Exchange(ctx, 2, 0, 1 << 20)
+        with pytest.raises(SiestaError):     # rank 1 never connected
+            x.detect_allgather(log, nfa, 0)
+        x.close()
+        x = api.Exchange(ctx, 1, 0, 256)     # world of one: the call works alone, but this region is too small
+        with pytest.raises(SiestaError) as ei:
+            x.detect_allgather(log, nfa, 0)
+        assert ei.value.code == abi.E_NOMEM
+        x.close()
+        x = api.Exchange(ctx, 1, 0, api.exchange_required_bytes(log, nfa, 0))
+        dm, st = x.detect_allgather(log, nfa, 0)
+        ok, why = _to_result(dm).same_as(oracle.detect(off, act, ts, nfa, flags=0))
+        assert ok, why
+        dm.close()
+        x.close()
+        log.close()
