@@ -322,6 +322,26 @@ int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, uint32_t fla
  * order (deterministic).  `stream` = the cudaStream_t that produced d_buf (NULL = the ctx stream); returns when done. */
 int siesta_exchange_allreduce_i64(siesta_exchange* x, int64_t* d_buf, int64_t n, int32_t op, void* stream);
 
+/* One process driving all GPUs (the reference is ONE JVM): a context and an exchange per device, connected through
+ * peer access; a host CSR log sharded by contiguous trace range balanced by event count; every request entry point
+ * runs all shards at once, one host thread per device.  /detection results are joined on the HOST (each device copies
+ * its columns into its slice of one pinned block: all host links in parallel), counts are all-reduced on the devices.
+ * device_ids may name a device more than once (several shards on one GPU: tests). */
+typedef struct siesta_multi siesta_multi;
+typedef struct siesta_multi_log siesta_multi_log;
+int siesta_multi_init(const int32_t* device_ids, int32_t n_dev, siesta_multi** out);
+void siesta_multi_shutdown(siesta_multi* m);
+int32_t siesta_multi_n_devices(const siesta_multi* m);
+int siesta_multi_log_load(siesta_multi* m, const int64_t* trace_off, const int32_t* act, const int64_t* ts_ms,
+                          int64_t n_traces, int64_t n_events, int32_t n_activities, siesta_multi_log** out);
+void siesta_multi_log_free(siesta_multi_log* log);
+siesta_log* siesta_multi_log_shard(siesta_multi_log* log, int32_t shard); /* borrowed: any single-GPU call on one shard */
+/* = siesta_detect(whole log, nfa, NULL, 0, flags): SaseConnector.evaluate + clearOccurrences
+ * (SaseConnection/SaseConnector.java:48-76), global trace indices, trace order. */
+int siesta_multi_detect(siesta_multi_log* log, const siesta_nfa* nfa, uint32_t flags, siesta_matches** out);
+/* = siesta_declare_counts(whole log): kernel K3 per shard + one sum all-reduce over the exchange. */
+int siesta_multi_declare_counts(siesta_multi_log* log, int32_t k_cap, int64_t* out, double* kernel_ms);
+
 /* ------------------------------------------------- pair index + intersection */
 /* Kernel K2.  Replaces SparkDatabaseRepository.getCommonIds (storage/repositories/
  * SparkDatabaseRepository.java:160-178): the traces that contain ALL true pairs = the intersection of the

@@ -22,6 +22,8 @@ EXPORTS = [
     "siesta_packed_block_bytes", "siesta_dev_matches_pack",
     "siesta_exchange_create", "siesta_exchange_export", "siesta_exchange_import", "siesta_exchange_connect_local",
     "siesta_exchange_free", "siesta_exchange_required_bytes", "siesta_detect_allgather", "siesta_exchange_allreduce_i64",
+    "siesta_multi_init", "siesta_multi_shutdown", "siesta_multi_n_devices", "siesta_multi_log_load", "siesta_multi_log_free",
+    "siesta_multi_log_shard", "siesta_multi_detect", "siesta_multi_declare_counts",
 ]
 
 
@@ -100,6 +102,17 @@ def lib():
     L.siesta_exchange_required_bytes.restype = i64
     L.siesta_detect_allgather.argtypes = [vp, P(_abi.Nfa), u32, vp, P(_abi.DevMatches), P(_abi.ExchangeStats)]
     L.siesta_exchange_allreduce_i64.argtypes = [vp, vp, i64, i32, vp]
+    L.siesta_multi_init.argtypes = [vp, i32, P(vp)]
+    L.siesta_multi_shutdown.argtypes = [vp]
+    L.siesta_multi_shutdown.restype = None
+    L.siesta_multi_n_devices.argtypes = [vp]
+    L.siesta_multi_log_load.argtypes = [vp, vp, vp, vp, i64, i64, i32, P(vp)]
+    L.siesta_multi_log_free.argtypes = [vp]
+    L.siesta_multi_log_free.restype = None
+    L.siesta_multi_log_shard.argtypes = [vp, i32]
+    L.siesta_multi_log_shard.restype = vp
+    L.siesta_multi_detect.argtypes = [vp, P(_abi.Nfa), u32, P(P(_abi.Matches))]
+    L.siesta_multi_declare_counts.argtypes = [vp, i32, vp, P(C.c_double)]
     L.siesta_device_free.argtypes = [vp, vp]
     L.siesta_device_free.restype = None
     _lib = L

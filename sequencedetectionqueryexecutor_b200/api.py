@@ -271,6 +271,62 @@ class Exchange:
             self._h = C.c_void_p()
 
 
+class Multi:
+    """siesta_multi: ONE process driving several GPUs (what a single JVM does).  device_ids may repeat a device."""
+
+    def __init__(self, device_ids):
+        ids = np.asarray(device_ids, dtype=np.int32)
+        self._h = C.c_void_p()
+        check(lib().siesta_multi_init(_ptr(ids), len(ids), C.byref(self._h)))
+        self.n_devices = len(ids)
+
+    def load_log(self, trace_off, act, ts_ms, n_activities):
+        return MultiLog(self, trace_off, act, ts_ms, n_activities)
+
+    def close(self):
+        if self._h:
+            lib().siesta_multi_shutdown(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class MultiLog:
+    """siesta_multi_log: a host CSR log sharded over the devices of a Multi by contiguous trace range."""
+
+    def __init__(self, multi, trace_off, act, ts_ms, n_activities):
+        trace_off = np.ascontiguousarray(trace_off, dtype=np.int64)
+        act = np.ascontiguousarray(act, dtype=np.int32)
+        ts_ms = np.ascontiguousarray(ts_ms, dtype=np.int64)
+        self.multi, self.n_activities = multi, int(n_activities)
+        self._h = C.c_void_p()
+        check(lib().siesta_multi_log_load(multi._h, _ptr(trace_off), _ptr(act), _ptr(ts_ms), len(trace_off) - 1, len(act),
+                                          self.n_activities, C.byref(self._h)))
+
+    def detect(self, nfa, flags=0):
+        out = C.POINTER(_abi.Matches)()
+        check(lib().siesta_multi_detect(self._h, C.byref(nfa), flags, C.byref(out)))
+        res = _abi.MatchResult.from_struct(out.contents)
+        lib().siesta_matches_free(out)
+        return res
+
+    def declare_counts(self, k_cap=64):
+        n = lib().siesta_declare_counts_size(self.n_activities, int(k_cap))
+        out = np.zeros(n, dtype=np.int64)
+        ms = C.c_double(0.0)
+        check(lib().siesta_multi_declare_counts(self._h, int(k_cap), _ptr(out), C.byref(ms)))
+        return _abi.DeclareCounts(out, self.n_activities, int(k_cap), ms.value)
+
+    def close(self):
+        if self._h:
+            lib().siesta_multi_log_free(self._h)
+            self._h = C.c_void_p()
+
+
 def exchange_required_bytes(log, nfa, flags=0):
     return int(lib().siesta_exchange_required_bytes(log._h, C.byref(nfa), flags))
 

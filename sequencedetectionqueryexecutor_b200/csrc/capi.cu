@@ -271,8 +271,12 @@ void arena_free(Ctx* c, void* p) {
 
 inline size_t align64(size_t x) { return (x + 63) & ~(size_t)63; }
 
-// Device results of one or more consecutive chunks (already rebased: see RebaseOffsets) -> one host siesta_matches.
-int assemble_matches(Ctx* c, std::vector<siesta_dev_matches>& parts, uint32_t flags, cudaStream_t stream, siesta_matches** out) {
+}  // namespace
+namespace siesta {
+// Device results of one or more consecutive chunks / shards (already rebased: see RebaseOffsets) -> one host
+// siesta_matches.  part_ctx (optional): the context (device, stream) each part lives on - shards of a multi-GPU log.
+int assemble_matches(Ctx* c, std::vector<siesta_dev_matches>& parts, uint32_t flags, cudaStream_t stream, siesta_matches** out,
+                     const std::vector<Ctx*>* part_ctx) {
     int64_t n_tr = 0, n_occ = 0, n_ev = 0, n_err = 0, n_emit = 0;
     double k_ms = 0, d_ms = 0;
     bool counted = true;
@@ -334,10 +338,16 @@ int assemble_matches(Ctx* c, std::vector<siesta_dev_matches>& parts, uint32_t fl
     m->ev_off[0] = 0;
     int64_t a_tr = 0, a_occ = 0, a_ev = 0, a_err = 0;
     cudaError_t e = cudaSuccess;
+    cudaStream_t cur = stream;
     auto d2h = [&](void* dst, const void* src, size_t bytes) {
-        if (bytes && src && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream);
+        if (bytes && src && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, cur);
     };
-    for (const siesta_dev_matches& p : parts) {
+    for (size_t pi = 0; pi < parts.size(); ++pi) {
+        const siesta_dev_matches& p = parts[pi];
+        if (part_ctx) {
+            if (e == cudaSuccess) e = cudaSetDevice((*part_ctx)[pi]->device);
+            cur = (*part_ctx)[pi]->stream;
+        }
         d2h(m->trace_idx + a_tr, p.d_trace_idx, (size_t)p.n_traces * 8);
         // each part carries its own tail entry; the next part overwrites it with the same value
         d2h(m->occ_off + a_tr, p.d_occ_off, (size_t)(p.n_traces + 1) * 8);
@@ -354,7 +364,14 @@ int assemble_matches(Ctx* c, std::vector<siesta_dev_matches>& parts, uint32_t fl
         a_ev += p.n_events;
         a_err += p.n_ref_errors;
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (part_ctx) {
+        for (size_t pi = 0; pi < parts.size() && e == cudaSuccess; ++pi) {
+            e = cudaSetDevice((*part_ctx)[pi]->device);
+            if (e == cudaSuccess) e = cudaStreamSynchronize((*part_ctx)[pi]->stream);
+        }
+    } else if (e == cudaSuccess) {
+        e = cudaStreamSynchronize(stream);
+    }
     if (e != cudaSuccess) {
         set_error(std::string("device -> host copy of the occurrences: ") + cudaGetErrorString(e));
         siesta_matches_free(m);
@@ -363,7 +380,7 @@ int assemble_matches(Ctx* c, std::vector<siesta_dev_matches>& parts, uint32_t fl
     *out = m;
     return SIESTA_OK;
 }
-}  // namespace
+}  // namespace siesta
 
 extern "C" void siesta_matches_free(siesta_matches* m) {
     if (!m) return;
@@ -411,7 +428,7 @@ extern "C" int siesta_detect(siesta_log* log, const siesta_nfa* nfa, const int64
         }
         rc = siesta_detect_device(log, nfa, d_cand, n_cand, flags, stream, &parts[0]);
         if (rc) break;
-        rc = assemble_matches(L->ctx, parts, flags, stream, out);
+        rc = assemble_matches(L->ctx, parts, flags, stream, out, nullptr);
     } while (0);
     siesta_dev_matches_free(&parts[0]);
     if (d_cand) cudaFreeAsync(d_cand, stream);
@@ -515,7 +532,7 @@ extern "C" int siesta_evaluate_events(siesta_ctx* ctx, const int64_t* trace_off,
         set_error(std::string("siesta_evaluate_events: ") + cudaGetErrorString(e));
         rc = SIESTA_E_CUDA;
     }
-    if (rc == SIESTA_OK) rc = assemble_matches(c, parts, flags, s_run, out);
+    if (rc == SIESTA_OK) rc = assemble_matches(c, parts, flags, s_run, out, nullptr);
     for (siesta_dev_matches& p : parts) siesta_dev_matches_free(&p);
     cudaStreamSynchronize(s_copy);
     cudaStreamSynchronize(s_run);

@@ -96,6 +96,7 @@ struct NkwProgram {
 
 int nkw_build(const DevNfa& dn, uint32_t flags, NkwProgram* out);
 
+struct DetectPending;
 // Chunked evaluation (siesta_evaluate_events): where a chunk's results sit in the whole result.
 struct RebaseOffsets {
     int64_t trace, occ, ev;
@@ -103,6 +104,10 @@ struct RebaseOffsets {
 int detect_device_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand, uint32_t flags, cudaStream_t stream,
                        RebaseOffsets base, siesta_dev_matches* out);
 int validate_act_range(Log* L, int64_t first_event, int64_t n_events, cudaStream_t stream);
+int assemble_matches(Ctx* c, std::vector<siesta_dev_matches>& parts, uint32_t flags, cudaStream_t stream, siesta_matches** out,
+                     const std::vector<Ctx*>* part_ctx);
+int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out);
+void detect_pending_set_base(DetectPending* q, RebaseOffsets base);
 
 int validate_nfa(const siesta_nfa* nfa, uint32_t flags, DevNfa* out);
 
@@ -131,7 +136,6 @@ struct PackTarget {
     XHeader* hdr;          // header slot of the local region
     unsigned long long seq;
 };
-struct DetectPending;
 int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand, uint32_t flags,
                              cudaStream_t stream, RebaseOffsets base, DetectPending** pending);
 int detect_device_pack_impl(DetectPending* q, const PackTarget& tgt);   // enqueues only, no host wait

@@ -1264,6 +1264,12 @@ int64_t detect_pack_required_bytes(int64_t n, int64_t n_events_log, int uniform_
 }
 
 void detect_pending_discard(DetectPending* q) { pending_discard(q); }
+// Where the request's result sits in a larger one (shards of a multi-GPU log): may be set between the two halves, once
+// the sizes of the shards before this one are known.  base.trace is added to the shard's first trace.
+void detect_pending_set_base(DetectPending* q, RebaseOffsets base) {
+    base.trace += q->log->first_trace;
+    q->base = base;
+}
 // device time of the verification kernels alone (K1-P + staged re-run); valid once the request's stream has been waited for
 float detect_pending_k1_ms(DetectPending* q) {
     float ms = 0.f;

@@ -690,3 +690,247 @@ extern "C" int siesta_exchange_allreduce_i64(siesta_exchange* xh, int64_t* d_buf
     }
     return SIESTA_OK;
 }
+
+// ------------------------------------------------------------------------------------------ one process, all GPUs
+// The reference is ONE JVM; its drop-in drives every GPU of the box from that process.  siesta_multi owns one context
+// and one exchange per device (connected through peer access), siesta_multi_log shards a host CSR log by contiguous
+// trace range balanced by event count, and the request entry points run every shard on its own device from its own
+// host thread.  /detection results go to the HOST (that is where the JVM needs them), so the shards' match lists are
+// joined there: each device copies its columns straight into its slice of one pinned block - eight PCIe links in
+// parallel, no device-side all-gather in front of them.  The count arrays are all-reduced on the devices over the
+// exchange and read back once.
+#include <thread>
+
+namespace siesta {
+struct Multi {
+    std::vector<Ctx*> ctx;
+    std::vector<Exchange*> xchg;
+};
+struct MultiLog {
+    Multi* m = nullptr;
+    std::vector<Log*> shard;
+    std::vector<int64_t> first;   // first trace of each shard (+ the total at the end)
+    int32_t n_activities = 0;
+};
+}  // namespace siesta
+
+extern "C" int siesta_multi_init(const int32_t* device_ids, int32_t n_dev, siesta_multi** out) {
+    if (!device_ids || !out || n_dev < 1 || n_dev > XCHG_MAX_RANKS) {
+        set_error("siesta_multi_init: 1..16 device ids");
+        return SIESTA_E_INVALID;
+    }
+    Multi* m = new Multi();
+    int rc = SIESTA_OK;
+    for (int r = 0; r < n_dev && rc == SIESTA_OK; ++r) {
+        siesta_ctx* c = nullptr;
+        rc = siesta_init(device_ids[r], &c);
+        if (rc == SIESTA_OK) m->ctx.push_back(reinterpret_cast<Ctx*>(c));
+    }
+    for (int r = 0; r < n_dev && rc == SIESTA_OK; ++r) {
+        siesta_exchange* x = nullptr;
+        rc = siesta_exchange_create(reinterpret_cast<siesta_ctx*>(m->ctx[r]), n_dev, r, 8 << 20, &x);
+        if (rc == SIESTA_OK) m->xchg.push_back(reinterpret_cast<Exchange*>(x));
+    }
+    for (int a = 0; a < n_dev && rc == SIESTA_OK; ++a)
+        for (int b = 0; b < n_dev && rc == SIESTA_OK; ++b)
+            if (a != b) rc = siesta_exchange_connect_local(reinterpret_cast<siesta_exchange*>(m->xchg[a]), b, reinterpret_cast<siesta_exchange*>(m->xchg[b]));
+    if (rc != SIESTA_OK) {
+        const std::string why = siesta_last_error();
+        siesta_multi_shutdown(reinterpret_cast<siesta_multi*>(m));
+        set_error(why);
+        return rc;
+    }
+    *out = reinterpret_cast<siesta_multi*>(m);
+    return SIESTA_OK;
+}
+
+extern "C" void siesta_multi_shutdown(siesta_multi* mh) {
+    Multi* m = reinterpret_cast<Multi*>(mh);
+    if (!m) return;
+    for (Exchange* x : m->xchg) siesta_exchange_free(reinterpret_cast<siesta_exchange*>(x));
+    for (Ctx* c : m->ctx) siesta_shutdown(reinterpret_cast<siesta_ctx*>(c));
+    delete m;
+}
+
+extern "C" int32_t siesta_multi_n_devices(const siesta_multi* mh) { return mh ? (int32_t)reinterpret_cast<const Multi*>(mh)->ctx.size() : 0; }
+
+extern "C" int siesta_multi_log_load(siesta_multi* mh, const int64_t* trace_off, const int32_t* act, const int64_t* ts_ms,
+                                     int64_t n_traces, int64_t n_events, int32_t n_activities, siesta_multi_log** out) {
+    Multi* m = reinterpret_cast<Multi*>(mh);
+    if (!m || !trace_off || !out || n_traces < 0 || n_events < 0 || trace_off[0] != 0 || trace_off[n_traces] != n_events) {
+        set_error("siesta_multi_log_load: bad argument (trace_off must start at 0 and end at n_events)");
+        return SIESTA_E_INVALID;
+    }
+    const int n = (int)m->ctx.size();
+    MultiLog* ml = new MultiLog();
+    ml->m = m;
+    ml->n_activities = n_activities;
+    // contiguous trace ranges balanced by event count (as distributed.shard_bounds)
+    ml->first.assign((size_t)n + 1, n_traces);
+    ml->first[0] = 0;
+    for (int r = 1; r < n; ++r) {
+        const int64_t target = (int64_t)((__int128)n_events * r / n);
+        const int64_t cut = (int64_t)(std::lower_bound(trace_off, trace_off + n_traces + 1, target) - trace_off);
+        ml->first[r] = std::max(ml->first[r - 1], std::min<int64_t>(cut, n_traces));
+    }
+    int rc = SIESTA_OK;
+    std::vector<int64_t> rebased;
+    for (int r = 0; r < n && rc == SIESTA_OK; ++r) {
+        const int64_t lo = ml->first[r], hi = ml->first[r + 1], e0 = trace_off[lo], e1 = trace_off[hi];
+        rebased.assign(trace_off + lo, trace_off + hi + 1);
+        for (int64_t& v : rebased) v -= e0;
+        siesta_log* lg = nullptr;
+        rc = siesta_log_load(reinterpret_cast<siesta_ctx*>(m->ctx[r]), rebased.data(), act ? act + e0 : nullptr, ts_ms ? ts_ms + e0 : nullptr,
+                             hi - lo, e1 - e0, n_activities, &lg);
+        if (rc == SIESTA_OK) {
+            siesta_log_set_first_trace(lg, lo);
+            ml->shard.push_back(reinterpret_cast<Log*>(lg));
+        }
+    }
+    if (rc != SIESTA_OK) {
+        const std::string why = siesta_last_error();
+        siesta_multi_log_free(reinterpret_cast<siesta_multi_log*>(ml));
+        set_error(why);
+        return rc;
+    }
+    *out = reinterpret_cast<siesta_multi_log*>(ml);
+    return SIESTA_OK;
+}
+
+extern "C" void siesta_multi_log_free(siesta_multi_log* lh) {
+    MultiLog* ml = reinterpret_cast<MultiLog*>(lh);
+    if (!ml) return;
+    for (Log* l : ml->shard) siesta_log_free(reinterpret_cast<siesta_log*>(l));
+    delete ml;
+}
+
+extern "C" siesta_log* siesta_multi_log_shard(siesta_multi_log* lh, int32_t r) {
+    MultiLog* ml = reinterpret_cast<MultiLog*>(lh);
+    return (ml && r >= 0 && r < (int)ml->shard.size()) ? reinterpret_cast<siesta_log*>(ml->shard[(size_t)r]) : nullptr;
+}
+
+// SaseConnector.evaluate + clearOccurrences over the whole (sharded) log: every device verifies its shard at the same
+// time; the placements then run in shard order (each needs the sizes of the shards before it to write global offsets)
+// and the columns travel to one host block over all host links at once.  Equals siesta_detect on the unsharded log.
+extern "C" int siesta_multi_detect(siesta_multi_log* lh, const siesta_nfa* nfa, uint32_t flags, siesta_matches** out) {
+    MultiLog* ml = reinterpret_cast<MultiLog*>(lh);
+    if (!ml || !nfa || !out) {
+        set_error("siesta_multi_detect: null argument");
+        return SIESTA_E_INVALID;
+    }
+    const int n = (int)ml->shard.size();
+    std::vector<DetectPending*> pend((size_t)n, nullptr);
+    std::vector<int> rcs((size_t)n, SIESTA_OK);
+    std::vector<std::string> errs((size_t)n);
+    {   // first halves: all scans in flight
+        std::vector<std::thread> th;
+        for (int r = 0; r < n; ++r)
+            th.emplace_back([&, r] {
+                rcs[r] = detect_device_begin_impl(ml->shard[r], nfa, nullptr, 0, flags, ml->shard[r]->ctx->stream, RebaseOffsets{0, 0, 0}, &pend[r]);
+                if (rcs[r]) errs[r] = siesta_last_error();
+            });
+        for (std::thread& t : th) t.join();
+    }
+    int rc = SIESTA_OK;
+    std::vector<siesta_dev_matches> parts((size_t)n);
+    for (siesta_dev_matches& p : parts) std::memset(&p, 0, sizeof(p));
+    RebaseOffsets base{0, 0, 0};
+    for (int r = 0; r < n; ++r) {
+        if (rcs[r] != SIESTA_OK) {
+            if (rc == SIESTA_OK) {
+                rc = rcs[r];
+                set_error(errs[r]);
+            }
+            if (pend[r]) detect_pending_discard(pend[r]);
+            continue;
+        }
+        if (rc != SIESTA_OK) {   // an earlier shard failed: release this one
+            siesta_dev_matches tmp;
+            detect_device_finish_impl(pend[r], &tmp);
+            siesta_dev_matches_free(&tmp);
+            continue;
+        }
+        detect_pending_set_base(pend[r], base);
+        rc = detect_device_finish_impl(pend[r], &parts[r]);
+        if (rc == SIESTA_OK) {
+            base.occ += parts[r].n_occurrences;
+            base.ev += parts[r].n_events;
+        }
+    }
+    if (rc == SIESTA_OK) {
+        std::vector<Ctx*> pc;
+        for (int r = 0; r < n; ++r) pc.push_back(ml->shard[r]->ctx);
+        rc = assemble_matches(ml->shard[0]->ctx, parts, flags, nullptr, out, &pc);
+        if (rc == SIESTA_OK) {   // device time of a request = the slowest shard, not the sum
+            double k = 0, d = 0;
+            for (const siesta_dev_matches& p : parts) {
+                k = std::max(k, p.kernel_ms);
+                d = std::max(d, p.detect_ms);
+            }
+            (*out)->kernel_ms = k;
+            (*out)->detect_ms = d;
+        }
+    }
+    for (siesta_dev_matches& p : parts) siesta_dev_matches_free(&p);
+    return rc;
+}
+
+// The integer matrices behind /declare over the whole (sharded) log: kernel K3 on every shard, one sum all-reduce over
+// the exchange, one read-back.  Equals siesta_declare_counts on the unsharded log.
+extern "C" int siesta_multi_declare_counts(siesta_multi_log* lh, int32_t k_cap, int64_t* out, double* kernel_ms) {
+    MultiLog* ml = reinterpret_cast<MultiLog*>(lh);
+    if (!ml || !out) {
+        set_error("siesta_multi_declare_counts: null argument");
+        return SIESTA_E_INVALID;
+    }
+    const int n = (int)ml->shard.size();
+    const int64_t len = siesta_declare_counts_size(ml->n_activities, k_cap);
+    if ((size_t)len * 8 > ml->m->xchg[0]->cap_bytes) {
+        set_error("siesta_multi_declare_counts: count array larger than the exchange region");
+        return SIESTA_E_NOMEM;
+    }
+    std::vector<int> rcs((size_t)n, SIESTA_OK);
+    std::vector<std::string> errs((size_t)n);
+    std::vector<double> ms((size_t)n, 0.0);
+    std::vector<std::thread> th;
+    for (int r = 0; r < n; ++r)
+        th.emplace_back([&, r] {
+            Ctx* c = ml->shard[r]->ctx;
+            int64_t* d = nullptr;
+            if (cudaSetDevice(c->device) != cudaSuccess || cudaMallocAsync((void**)&d, (size_t)len * 8, c->stream) != cudaSuccess) {
+                rcs[r] = SIESTA_E_NOMEM;
+                errs[r] = "siesta_multi_declare_counts: cudaMalloc";
+                d = nullptr;
+            }
+            int rc = rcs[r];
+            if (rc == SIESTA_OK) rc = siesta_declare_counts_device(reinterpret_cast<siesta_log*>(ml->shard[r]), k_cap, d, c->stream, &ms[r]);
+            // the collective runs even after a local failure (with zeros), so that the other ranks are not left waiting
+            if (rc != SIESTA_OK && d) cudaMemsetAsync(d, 0, (size_t)len * 8, c->stream);
+            if (rc != SIESTA_OK && errs[r].empty()) errs[r] = siesta_last_error();
+            int rc2 = d ? siesta_exchange_allreduce_i64(reinterpret_cast<siesta_exchange*>(ml->m->xchg[r]), d, len, SIESTA_REDUCE_SUM, c->stream) : SIESTA_E_NOMEM;
+            if (rc == SIESTA_OK && rc2 != SIESTA_OK) {
+                rc = rc2;
+                errs[r] = siesta_last_error();
+            }
+            if (rc == SIESTA_OK && r == 0) {
+                if (cudaMemcpyAsync(out, d, (size_t)len * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                    cudaStreamSynchronize(c->stream) != cudaSuccess) {
+                    rc = SIESTA_E_CUDA;
+                    errs[r] = "siesta_multi_declare_counts: D2H";
+                }
+            }
+            if (d) cudaFreeAsync(d, c->stream);
+            rcs[r] = rc;
+        });
+    for (std::thread& t : th) t.join();
+    double worst = 0;
+    for (int r = 0; r < n; ++r) {
+        worst = std::max(worst, ms[r]);
+        if (rcs[r] != SIESTA_OK) {
+            set_error(errs[r]);
+            return rcs[r];
+        }
+    }
+    if (kernel_ms) *kernel_ms = worst;
+    return SIESTA_OK;
+}

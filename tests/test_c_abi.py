@@ -48,3 +48,19 @@ def test_no_cpu_fallback_without_a_device():
     rc = _lib.lib().siesta_init(0, C.byref(h))
     assert rc == _abi.E_CUDA and not h.value
     assert b"" != _lib.lib().siesta_last_error()
+
+
+def test_jni_shim_implements_every_native_method_of_the_java_class():
+    """jni/siesta_gpu_jni.c (compiled against jni/stub/jni.h: no JDK in this image) defines one
+    Java_..._GpuNative_<name> per `static native` method of jni/java/.../GpuNative.java, and links against the library."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "jni"), "-s"])
+    java = open(os.path.join(ROOT, "jni", "java", "com", "datalab", "siesta", "queryprocessor", "SaseConnection", "GpuNative.java")).read()
+    natives = sorted(set(re.findall(r"static native [\w\[\]]+ (\w+)\(", java)))
+    assert len(natives) >= 10
+    so = os.path.join(ROOT, "jni", "_build", "libsiesta_gpu_jni.so")
+    out = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+    prefix = "Java_com_datalab_siesta_queryprocessor_SaseConnection_GpuNative_"
+    defined = sorted(ln.split()[-1][len(prefix):] for ln in out.splitlines() if prefix in ln)
+    assert defined == natives
+    needed = subprocess.run(["readelf", "-d", so], capture_output=True, text=True).stdout
+    assert "libsiesta_gpu.so" in needed

@@ -190,3 +190,24 @@ def test_exchange_rejects_an_unconnected_peer_and_a_small_region():
         dm.close()
         x.close()
         log.close()
+
+
+def test_one_process_all_gpus_entry_points():
+    """siesta_multi_*: what a single JVM calls - the log sharded over the devices (here: three shards on device 0, or one
+    per visible GPU), /detection joined on the host, /declare counts all-reduced on the devices."""
+    import torch
+
+    from sequencedetectionqueryexecutor_b200 import api
+    n_gpu = torch.cuda.device_count()
+    for ids in ([0, 0, 0], list(range(n_gpu)) if n_gpu > 1 else [0]):
+        with api.Multi(ids) as m:
+            for states, flags, n_act in ((GAP6, 0, 20), (KLEENE, 0, 20), (AB, abi.F_RETURN_ALL | abi.F_EVT_POS, 5), (ABC, abi.F_COUNT_MATCHES, 6)):
+                off, act, ts = gen.make_log(4000, 0, 70, n_act, seed=31 + n_act, max_gap_s=200, jitter_ms=True)
+                nfa = abi.make_nfa(states)
+                log = m.load_log(off, act, ts, n_act)
+                for _ in range(2):
+                    got = log.detect(nfa, flags)
+                ok, why = got.same_as(oracle.detect(off, act, ts, nfa, flags=flags))
+                assert ok, (ids, why)
+                assert np.array_equal(log.declare_counts(25).packed, oracle.declare_counts(off, act, n_act, 25).packed)
+                log.close()
