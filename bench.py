@@ -227,7 +227,7 @@ def sample_log(wl):
     return (off[:ns + 1], act[:e], ts[:e]), "host generator (same bits as the GPU arm)"
 
 
-def run_reference(args, wl, world, rank):
+def run_reference(args, wl, world, rank, emit):
     """--impl reference: the reference's own CPU implementation of the path (the oracle port; the Java original
     cannot run here: no JVM) on all host threads; each step = the first SAMPLE_TRACES traces of the workload's log,
     the same sample the GPU arm's cpu_baseline and parity check use."""
@@ -246,7 +246,7 @@ def run_reference(args, wl, world, rank):
     dt = (time.perf_counter() - t0) / args.steps
     v = len(act) / dt
     sample = f"first {len(off) - 1} traces ({len(act)} events) of the log per step; {how}"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "events scanned/sec (/detection verification)", "value": v, "unit": "events/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
@@ -254,10 +254,18 @@ def run_reference(args, wl, world, rank):
         "cpu_baseline": {"value": v, "unit": "events/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def main():
+    # stdout carries exactly ONE JSON line: anything a library prints there while the bench runs (NCCL's version banner,
+    # for one) is sent to stderr instead
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -283,7 +291,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, wl, world, rank)
+        run_reference(args, wl, world, rank, emit)
         return
 
     import torch
@@ -345,7 +353,7 @@ def main():
             # scan of the shard + device-side all-gather: returns when this rank holds every rank's decoded columns
             dm, st = join.detect_allgather(log, nfa, flags)
             out = (st.local_traces, st.local_occurrences, st.local_events, dm.n_matches_emitted, dm.kernel_ms, st.k1_ms,
-                   dm.n_traces, st.wait_ms + st.pull_ms, st.scan_ms, st.wait_ms, st.pull_ms, st.pulled_bytes)
+                   dm.n_traces, st.wait_ms + st.host_gap_ms + st.pull_ms, st.scan_ms, st.wait_ms, st.pull_ms, st.pulled_bytes, st.host_gap_ms)
         else:
             dm = log.detect_device(nfa, flags=flags)
             out = (dm.n_traces, dm.n_occurrences, dm.n_events, dm.n_matches_emitted, dm.kernel_ms, dm.detect_ms, dm.n_traces, 0.0)
@@ -475,7 +483,7 @@ def main():
                            "min": float(lat.min()), "max": float(lat.max())},
             "p50_latency_ms": float(np.percentile(lat, 50)),
             "exchange": ({"ms": float(np.mean(x_ms)), "scan_and_place_ms": r[8], "wait_for_slowest_rank_ms": r[9],
-                          "pull_and_decode_ms": r[10], "pulled_bytes_per_rank": r[11],
+                          "host_sizes_and_alloc_ms": r[12], "pull_and_decode_ms": r[10], "pulled_bytes_per_rank": r[11],
                           "nvlink_GBps_in": r[11] / max(r[10], 1e-9) / 1e6,
                           "what": "siesta_detect_allgather: compact blocks placed in peer-mapped regions, sizes in-band, one "
                                   "fused pull + decode kernel, two host waits per request"} if join is not None else None),
@@ -495,7 +503,7 @@ def main():
             line["cpu_baseline"] = {"value": len(s_act) / dt, "unit": "events/s", "cores": 1, "kind": "port",
                                     "sample": f"first {ns} traces ({len(s_act)} events) of the same log, {dt:.1f} s",
                                     "parity_on_sample": parity}
-        print(json.dumps(line))
+        emit(line)
     log.close()
     if join is not None:
         join.close()

@@ -169,6 +169,27 @@ void siesta_log_free(siesta_log* log);
 int64_t siesta_log_n_traces(const siesta_log* log);
 int64_t siesta_log_n_events(const siesta_log* log);
 
+/* ---------------------------------------------------- derived logs (device) */
+/* Trace.filter(from, till) (model/DBModel/Trace.java:25-29; the same test in SparkDatabaseRepository.addFilterIds
+ * :204-218 and Utils.evaluateEvent, model/Utils/Utils.java:67-79) over a resident log, on the device: a new resident
+ * log that holds, per trace, the events with from_ms <= timestamp <= till_ms (a bound counts only if its has_* flag is
+ * set).  The reference filters the event list BEFORE numbering it, so positions in the derived log are ranks among
+ * the surviving events; siesta_log_source_events gives each event's index in the source log.  Traces keep their
+ * indices (a trace may become empty).  Free with siesta_log_free. */
+int siesta_log_filter_time(siesta_log* log, int64_t from_ms, int32_t has_from, int64_t till_ms, int32_t has_till,
+                           siesta_log** out);
+/* The streams of /detection over groups of traces (SparkDatabaseRepository.querySingleTableGroups :307-336, evaluated
+ * by SaseConnector.evaluateGroups, SaseConnector.java:85-110 = siesta_detect on the log returned here): group g lists
+ * the traces group_traces[group_off[g] .. group_off[g+1]); a trace belongs to the FIRST group that lists it; a group's
+ * stream is the events of its traces merged by timestamp (ties: order of the trace in the group's list, then position
+ * - the reference's order of ties is undefined); a group whose events do not cover all n_types event types of the
+ * query (<= 64) is dropped.  Trace i of the new log is the i-th kept group, group_ids[i] its 1-based number as the
+ * reference reports it (:317); group_ids must hold n_groups entries.  Traces must be sorted by timestamp. */
+int siesta_log_group(siesta_log* log, const int64_t* group_off, const int64_t* group_traces, int32_t n_groups,
+                     const int32_t* types, int32_t n_types, siesta_log** out, int32_t* group_ids, int32_t* n_kept);
+/* Derived logs only: out[e] = index in the SOURCE log of event e (host array of siesta_log_n_events entries). */
+int siesta_log_source_events(siesta_log* log, int64_t* out);
+
 /* -------------------------------------------------------------- detection */
 /* flags */
 #define SIESTA_F_RETURN_ALL 1u       /* Occurrences.clearOccurrences(true) (model/Occurrences.java:58-89) */
@@ -304,6 +325,7 @@ typedef struct siesta_exchange_stats {
     double scan_ms;  /* verification + placement of this rank's block (device time)                               */
     double wait_ms;  /* announce + wait for the slowest rank + fetch of the headers                               */
     double pull_ms;  /* pull + decode of all blocks into the joined columns                                       */
+    double host_gap_ms; /* between the two: the host reads the sizes and allocates the joined result              */
 } siesta_exchange_stats;
 
 /* siesta_detect_device over this rank's shard FOLLOWED BY the all-gather: `out` holds the match list of ALL ranks in

@@ -24,6 +24,7 @@ EXPORTS = [
     "siesta_exchange_free", "siesta_exchange_required_bytes", "siesta_detect_allgather", "siesta_exchange_allreduce_i64",
     "siesta_multi_init", "siesta_multi_shutdown", "siesta_multi_n_devices", "siesta_multi_log_load", "siesta_multi_log_free",
     "siesta_multi_log_shard", "siesta_multi_detect", "siesta_multi_declare_counts",
+    "siesta_log_filter_time", "siesta_log_group", "siesta_log_source_events",
 ]
 
 
@@ -113,6 +114,9 @@ def lib():
     L.siesta_multi_log_shard.restype = vp
     L.siesta_multi_detect.argtypes = [vp, P(_abi.Nfa), u32, P(P(_abi.Matches))]
     L.siesta_multi_declare_counts.argtypes = [vp, i32, vp, P(C.c_double)]
+    L.siesta_log_filter_time.argtypes = [vp, i64, i32, i64, i32, P(vp)]
+    L.siesta_log_group.argtypes = [vp, vp, vp, i32, vp, i32, P(vp), vp, P(i32)]
+    L.siesta_log_source_events.argtypes = [vp, vp]
     L.siesta_device_free.argtypes = [vp, vp]
     L.siesta_device_free.restype = None
     _lib = L

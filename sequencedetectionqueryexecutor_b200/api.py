@@ -79,6 +79,41 @@ class EventLog:
         self.n_traces = lib().siesta_log_n_traces(self._h)
         self.n_events = lib().siesta_log_n_events(self._h)
 
+    @classmethod
+    def _adopt(cls, ctx, handle, n_activities):
+        """An EventLog over a siesta_log the library created (derived logs)."""
+        self = cls.__new__(cls)
+        self.ctx, self._h, self.n_activities, self._keep = ctx, handle, int(n_activities), None
+        self.n_traces = lib().siesta_log_n_traces(handle)
+        self.n_events = lib().siesta_log_n_events(handle)
+        return self
+
+    def filter_time(self, from_ms=None, till_ms=None):
+        """siesta_log_filter_time: Trace.filter(from, till) on the device -> a new resident EventLog."""
+        h = C.c_void_p()
+        check(lib().siesta_log_filter_time(self._h, int(from_ms or 0), 0 if from_ms is None else 1, int(till_ms or 0),
+                                           0 if till_ms is None else 1, C.byref(h)))
+        return EventLog._adopt(self.ctx, h, self.n_activities)
+
+    def group(self, groups, types):
+        """siesta_log_group: groups = list of lists of trace indices, types = the query's activity ids ->
+        (EventLog whose traces are the kept groups' merged streams, 1-based group ids of those traces)."""
+        off = np.zeros(len(groups) + 1, dtype=np.int64)
+        np.cumsum([len(g) for g in groups], out=off[1:])
+        flat = np.array([t for g in groups for t in g], dtype=np.int64)
+        ty = np.asarray(sorted(set(types)), dtype=np.int32)
+        gids = np.zeros(max(len(groups), 1), dtype=np.int32)
+        h, k = C.c_void_p(), C.c_int32(0)
+        check(lib().siesta_log_group(self._h, _ptr(off), _ptr(flat) if len(flat) else None, len(groups), _ptr(ty), len(ty), C.byref(h),
+                                     _ptr(gids), C.byref(k)))
+        return EventLog._adopt(self.ctx, h, self.n_activities), gids[:k.value].copy()
+
+    def source_events(self):
+        """Derived logs: index in the source log of every event."""
+        out = np.zeros(max(self.n_events, 1), dtype=np.int64)
+        check(lib().siesta_log_source_events(self._h, _ptr(out)))
+        return out[:self.n_events]
+
     def set_first_trace(self, first_trace):
         """This log is the shard starting at global trace `first_trace`: returned trace indices become global."""
         lib().siesta_log_set_first_trace(self._h, int(first_trace))

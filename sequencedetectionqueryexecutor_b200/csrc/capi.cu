@@ -209,6 +209,7 @@ extern "C" void siesta_log_free(siesta_log* log) {
         cudaFree((void*)L->d_trace_off);
         cudaFree((void*)L->d_act);
         cudaFree((void*)L->d_ts_ms);
+        if (L->d_src_event) cudaFree((void*)L->d_src_event);
     }
     delete L;
 }

@@ -51,6 +51,7 @@ struct Log {
     const int64_t* d_trace_off = nullptr;  // [T+1]
     const int32_t* d_act = nullptr;        // [E]
     const int64_t* d_ts_ms = nullptr;      // [E]
+    const int64_t* d_src_event = nullptr;  // [E] derived logs (logview.cu): index of the event in the source log
     int64_t n_traces = 0, n_events = 0;
     int32_t n_activities = 0;
     int32_t max_trace_len = 0;             // caller's hint (wrapped logs) or exact (loaded logs)
@@ -92,6 +93,12 @@ struct NkwProgram {
     uint8_t le[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];     // 1: e below bit idx(ref) + cc, 0: e at or above it
     uint8_t sh[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];     // 8 * referenced state (byte of the packed indices)
     uint8_t cc[SIESTA_MAX_STATES][SIESTA_MAX_PREDS];     // min(c, 64) (+ 1 for <=)
+    // Markov form (every predicate of a positive state references the positive state before it; a negative state in
+    // between carries no predicate and neither does the state after it): all starts are evaluated at once, backwards
+    // (nkw_markov, detect_fast.cuh).  For positive state k >= 1: prev[k] = the positive state before it, m_ge[k] / m_le[k] =
+    // the event taken for k lies between ge and le index steps after the one taken for prev[k] (le = 255: unbounded).
+    uint8_t markov;
+    uint8_t prev[SIESTA_MAX_STATES], m_ge[SIESTA_MAX_STATES], m_le[SIESTA_MAX_STATES];
 };
 
 int nkw_build(const DevNfa& dn, uint32_t flags, NkwProgram* out);

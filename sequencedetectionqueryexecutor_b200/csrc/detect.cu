@@ -770,8 +770,8 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
         const uint16_t sg = lut[a] & 0xFFu;
         if (sg && std::find(sigs.begin(), sigs.end(), sg) == sigs.end()) sigs.push_back(sg);
     }
-    const bool use_nkp = nkw_space != NKW_NONE && !needs_ts && log->act_valid && log->n_activities <= 1023 && !sigs.empty() && sigs.size() <= 7 &&
-                         (reinterpret_cast<uintptr_t>(log->d_act) & 15u) == 0 && std::getenv("SIESTA_K1_NO_NKP") == nullptr;
+    const bool use_nkp = nkw_space != NKW_NONE && !needs_ts && log->act_valid && log->n_activities <= 255 && !sigs.empty() && sigs.size() <= 7 &&
+                         (reinterpret_cast<uintptr_t>(log->d_act) & 31u) == 0 && std::getenv("SIESTA_K1_NO_NKP") == nullptr;
     const size_t n_reg = use_nkp ? 2 : 1;  // staging regions: [0, cap) by atomics (staged kernels), [cap, 2 cap) fixed tile slots (K1-P)
     const size_t n_blk = (nn + GT - 1) / GT;
     const size_t o_ovf2 = use_nkp ? carve(nn * 8) : 0;
@@ -895,6 +895,20 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
             SIESTA_CUDA_OK(cudaMemcpyAsync(wb + o_nlut, nlut.data(), nlut.size() * 4, cudaMemcpyHostToDevice, stream));
             N.nkp_lut = reinterpret_cast<const uint4*>(wb + o_nlut);
             N.n_planes = sigs.size() <= 1 ? 1 : (sigs.size() <= 3 ? 2 : 3);
+            std::memset(N.st_inv, 0, sizeof(N.st_inv));
+            std::memset(N.st_single, 0, sizeof(N.st_single));
+            for (int k = 0; k < nfa->n_states; ++k) {
+                int n_own = 0, c_own = 0;
+                for (int c = 1; c <= (int)sigs.size(); ++c)
+                    if (sigs[(size_t)c - 1] & (1u << k)) {
+                        ++n_own;
+                        c_own = c;
+                    }
+                if (n_own == 1) {
+                    N.st_single[k] = 1;
+                    for (int p = 0; p < 3; ++p) N.st_inv[k][p] = ((c_own >> p) & 1) ? 0u : 0xFFFFFFFFu;
+                }
+            }
             if ((rc = launch_nkp(ctx, stream, N, prog, nkw_space))) return rc;
             // the staged kernel below re-runs the traces that did not fit 64 slots (count read from the device)
             P.work = N.ovf_list;

@@ -51,6 +51,10 @@ struct DetectParams {
     // [fix_ev + 32 i fix_np, + 32 fix_np) of a second staging region behind the first one
     int64_t fix_ev;
     int32_t fix_np;
+    // K1-P: a state that owns exactly ONE class is the minterm of the class planes with these polarities
+    // (st_inv[k][p] = 0 or ~0: plane p enters state k's mask as it is / complemented); st_single[k] = 0: OR of several classes
+    uint32_t st_inv[SIESTA_MAX_STATES][3];
+    uint8_t st_single[SIESTA_MAX_STATES];
     const uint4* nkp_lut;     // K1-P: [n_act + 1] {m, b0, b1, b2} per activity (detect_nkp.cu), entry n_act = no event
     int32_t tile_batch;       // K1-P: consecutive tiles a warp takes per atomic (one atomic per tile would bound a 10^8-trace scan)
     // counters: 0 occ reserved, 1 ev reserved, 2 emitted, 3 errors, 4 overflow, 5 staging overflow, 6 matched traces,
@@ -90,7 +94,7 @@ __device__ __forceinline__ void load_sectors(const DetectParams& P, long long e,
         }
     }
 }
-// The same for kernel K1-P, which only runs on 16-byte aligned logs with validated activity ids and sends a trace whose
+// The same for kernel K1-P, which only runs on 32-byte aligned logs with validated activity ids and sends a trace whose
 // last sector crosses the end of the log to the staged kernel: no scalar path, a sixth of the code.  Slots outside the
 // trace read as activity n_act, the "no event" entry of K1-P's table.
 __device__ __forceinline__ void load_sectors_vec(const DetectParams& P, long long e, long long o1, int4 (&v)[8]) {
@@ -101,8 +105,12 @@ __device__ __forceinline__ void load_sectors_vec(const DetectParams& P, long lon
         if (c >= o1) {
             v[2 * q] = v[2 * q + 1] = make_int4(none, none, none, none);
         } else {
-            v[2 * q] = __ldg(reinterpret_cast<const int4*>(P.act + c));
-            v[2 * q + 1] = __ldg(reinterpret_cast<const int4*>(P.act + c + 4));
+            // one 256-bit load = the lane's whole 32-byte sector (sm_100: LDG.E.256); two 128-bit loads would present
+            // every sector to the L1 twice
+            asm volatile("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(v[2 * q].x), "=r"(v[2 * q].y), "=r"(v[2 * q].z), "=r"(v[2 * q].w), "=r"(v[2 * q + 1].x),
+                           "=r"(v[2 * q + 1].y), "=r"(v[2 * q + 1].z), "=r"(v[2 * q + 1].w)
+                         : "l"(P.act + c));
         }
     }
 }

@@ -472,7 +472,85 @@ struct NkwWalk {
     }
 };
 
+// Markov form (NkwProgram::markov): every predicate of a positive state k references prev[k], the positive state before
+// it, so whether a run completes from an event taken for prev[k] depends on that event alone, and ALL starts are
+// evaluated together, backwards, on whole masks:
+//   good[S-1] = T[S-1];  good[prev[k]] = { p in T[prev[k]] : the first event of k's types at least ge[k] steps after p
+//                                          lies at most le[k] steps after p and is in good[k] }
+// "the first marker above q is in X" for all q at once is a downward fill from X through non-marker positions
+// (five doubling steps on 32 bits), the upper bound a smear of the markers by le - ge + 1, the lower bound a shift by
+// ge - 1.  With a (predicate-free) negative state before k the markers are the negative type's events as well: the
+// first of {negative, k} after p must be an event of k that is not of the negative type (Engine.java:679-682,
+// 1165-1180).  good[0] is the set of starts whose run completes: its popcount is the engine's match count, its lowest
+// bit the start of the first-largest occurrence, whose events ONE forward walk then collects.  No per-start loop.
+template <class MT>
+struct NkwMarkov {
+    typedef NkwBits<MT> B;
+    // g(q) = "the first bit of `markers` strictly above q is in X" (X subset of markers)
+    static SIESTA_HD __forceinline__ MT fill_down(MT X, MT markers) {
+        MT g = X >> 1;
+        MT P = ~markers >> 1;   // P(q): position q + 1 is not a marker; after the step with shift s: q+1 .. q+2s are none
+#pragma unroll
+        for (int s = 1; s < (int)(8 * sizeof(MT)); s <<= 1) {
+            g |= (g >> s) & P;
+            P &= P >> s;
+        }
+        return g;
+    }
+    // n(q) = "a bit of `markers` lies in (q, q + L]", 1 <= L
+    static SIESTA_HD __forceinline__ MT near_above(MT markers, int L) {
+        MT n = markers >> 1;
+        int covered = 1;
+        while (covered < L) {
+            const int step = covered < L - covered ? covered : L - covered;
+            n |= n >> step;
+            covered += step;
+        }
+        return n;
+    }
+    static SIESTA_HD __forceinline__ MT shr(MT x, int n) { return n >= (int)(8 * sizeof(MT)) ? (MT)0 : (MT)(x >> n); }
+    // the starts whose run completes
+    static SIESTA_HD __forceinline__ MT good_starts(const NkwProgram& P, const MT* T) {
+        const int S = P.n_states;
+        MT G = 0;
+        int k_next = S - 1;
+#pragma unroll
+        for (int k = SIESTA_MAX_STATES - 1; k >= 1; --k) {
+            if (k >= S) continue;
+            if (k == S - 1) G = T[k];
+            if (k != k_next) continue;
+            const int j = P.prev[k];
+            MT markers = T[k], X = G;
+            if (j != k - 1) {          // a negative state sits between j and k
+                markers |= T[k - 1];
+                X &= ~T[k - 1];
+            }
+            const int ge = P.m_ge[k], le = P.m_le[k];
+            MT g = 0;
+            if (le >= ge) {
+                g = fill_down(X, markers);
+                if (le != 255) g &= near_above(markers, le - ge + 1);
+                g = shr(g, ge - 1);
+            }
+            G = T[j] & g;
+            k_next = j;
+        }
+        return S == 1 ? T[0] : G;
+    }
+};
+
 // first-largest occurrence = smallest (completion, start); first_only as in nk_eval
+template <class MT>
+SIESTA_HD __forceinline__ bool nkw_eval_markov(const NkwProgram& P, const MT* T, MT& best, unsigned& n_emitted) {
+    const MT G = NkwMarkov<MT>::good_starts(P, T);
+    n_emitted = (unsigned)NkwBits<MT>::popc(G);
+    best = 0;
+    if (!G) return false;
+    bool exhausted = false;
+    best = NkwWalk<MT>::walk(P, T, G & ((MT)0 - G), exhausted);
+    return best != 0;
+}
+
 template <class MT>
 SIESTA_HD __forceinline__ bool nkw_eval(const NkwProgram& P, const MT* T, MT& best, unsigned& n_emitted, bool first_only) {
     typedef NkwBits<MT> B;

@@ -43,6 +43,10 @@ namespace siesta {
 // b_p = 0 otherwise - a slot pushes its bits only if it holds a relevant event, so the planes come out compacted to
 // the filtered list; the raw relevance mask is advanced as r = 2 r + m (after 32 pushes r + 1 is the mask: each push
 // adds m - 1 = the relevance bit plus a constant that sums to 2^32 - 1).  Raw space: m = 2 for every entry.
+// The table is kept eight times, entry a of copy c at [a * 8 + c]: lane l reads copy l & 7, so the eight lanes a
+// shared-memory wavefront serves (LDS.128: a quarter warp) always sit on eight different bank quads - no bank conflict
+// whatever the activity ids are (measured before: 58 M wavefronts for 30 M ideal, the L1 data pipe at 85 % of its peak).
+constexpr int LUT_SKEW = 8;
 template <int NPL, bool RAW>
 __device__ __forceinline__ void scan32(const uint4* __restrict__ lut, const int4 (&v)[8], uint32_t (&pl)[3], uint32_t& racc) {
 #pragma unroll
@@ -50,7 +54,7 @@ __device__ __forceinline__ void scan32(const uint4* __restrict__ lut, const int4
         const int a[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
 #pragma unroll
         for (int i = 3; i >= 0; --i) {
-            const uint4 w = lut[a[i]];
+            const uint4 w = lut[a[i] * LUT_SKEW];
             pl[0] = pl[0] * w.x + w.y;
             if (NPL > 1) pl[1] = pl[1] * w.x + w.z;
             if (NPL > 2) pl[2] = pl[2] * w.x + w.w;
@@ -78,15 +82,16 @@ __device__ __forceinline__ int select64(unsigned long long x, int r) {
     return r >= c ? 32 + select32(hi, r - c) : select32(lo, r);
 }
 
-template <int NPL, bool RAW>
+template <int NPL, bool RAW, bool MARKOV>
 __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ NkwProgram prog) {
     typedef typename std::conditional<RAW, unsigned long long, uint32_t>::type mask_t;
     typedef unsigned long long u64;
     typedef NkwBits<mask_t> B;
     const int lane = threadIdx.x & 31;
-    extern __shared__ uint4 s_lut[];   // the table [n_act + 1]
-    for (int i = threadIdx.x; i <= P.n_act; i += blockDim.x) s_lut[i] = P.nkp_lut[i];
+    extern __shared__ uint4 s_lut_all[];   // the table [n_act + 1][LUT_SKEW]
+    for (int i = threadIdx.x; i < (P.n_act + 1) * LUT_SKEW; i += blockDim.x) s_lut_all[i] = P.nkp_lut[i / LUT_SKEW];
     __syncthreads();
+    const uint4* s_lut = s_lut_all + (lane & (LUT_SKEW - 1));
     const bool evt_pos = (P.flags & SIESTA_F_EVT_POS) != 0;
     const bool all_cols = (P.flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
     const bool first_only = (P.flags & SIESTA_F_COUNT_MATCHES) == 0;  // monotone walks: the first completed start wins
@@ -170,26 +175,29 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
 #pragma unroll
             for (int p = 0; p < 3; ++p) pl[p] = p < NPL ? ((q[p] >> n_lead) & keep) : 0u;
         }
-        // state masks: class c (1..7) = minterm of the planes; cls_word[c] bit k <=> class c belongs to state k
-        mask_t M[8];
-#pragma unroll
-        for (int c = 1; c < 8; ++c) {
-            M[c] = 0;
-            if (c < (1 << NPL)) {
-                mask_t m = ~(mask_t)0;
-#pragma unroll
-                for (int p = 0; p < NPL; ++p) m &= ((c >> p) & 1) ? pl[p] : ~pl[p];
-                M[c] = m;
-            }
-        }
+        // state masks.  A state that owns one class (the usual case: classes are state-membership signatures) is the
+        // minterm of the planes with host-chosen polarities - three logic ops; otherwise the OR of its classes' minterms
+        // (cls_word[c] bit k <=> class c belongs to state k).
         mask_t T[SIESTA_MAX_STATES + 1];
 #pragma unroll
         for (int k = 0; k <= SIESTA_MAX_STATES; ++k) {
             T[k] = 0;
-            if (k < prog.n_states) {  // uniform
+            if (k < SIESTA_MAX_STATES && k < prog.n_states) {  // uniform
+                if (P.st_single[k]) {
+                    mask_t m = ~(mask_t)0;
 #pragma unroll
-                for (int c = 1; c < (1 << NPL); ++c)
-                    if (P.cls_word[c] & (1u << k)) T[k] |= M[c];
+                    for (int p = 0; p < NPL; ++p) m &= pl[p] ^ (mask_t)(long long)(int)P.st_inv[k][p];   // sign-extends to 64 bits
+                    T[k] = m;
+                } else {
+#pragma unroll
+                    for (int c = 1; c < (1 << NPL); ++c)
+                        if (P.cls_word[c] & (1u << k)) {
+                            mask_t m = ~(mask_t)0;
+#pragma unroll
+                            for (int p = 0; p < NPL; ++p) m &= ((c >> p) & 1) ? pl[p] : ~pl[p];
+                            T[k] |= m;
+                        }
+                }
             }
         }
 
@@ -198,7 +206,12 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
         mask_t best = 0;
         if (ci >= 0 && o1 > o0) {
             if (!fits) status = ST_OVF;
-            else if (Rv && nkw_eval<mask_t>(prog, T, best, n_emitted, first_only)) status = ST_MATCH;
+            else if (Rv) {
+                bool hit;
+                if constexpr (MARKOV) hit = nkw_eval_markov<mask_t>(prog, T, best, n_emitted);   // all starts at once
+                else hit = nkw_eval<mask_t>(prog, T, best, n_emitted, first_only);
+                if (hit) status = ST_MATCH;
+            }
         }
 
         // ------------------------------------------------------------------ output: fixed staging slots of the tile
@@ -303,10 +316,10 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
 }
 
 namespace {
-template <int NPL, bool RAW>
+template <int NPL, bool RAW, bool MARKOV>
 int launch_one(const Ctx* ctx, cudaStream_t stream, DetectParams P, const NkwProgram& prog) {
-    auto kern = detect_nkp_kernel<NPL, RAW>;
-    const size_t smem = (size_t)(P.n_act + 1) * sizeof(uint4);
+    auto kern = detect_nkp_kernel<NPL, RAW, MARKOV>;
+    const size_t smem = (size_t)(P.n_act + 1) * LUT_SKEW * sizeof(uint4);
     int per_sm = 0;
     SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
     if (per_sm < 1) per_sm = 1;
@@ -338,9 +351,14 @@ int launch_one(const Ctx* ctx, cudaStream_t stream, DetectParams P, const NkwPro
 
 int launch_nkp(const Ctx* ctx, cudaStream_t stream, const DetectParams& P, const NkwProgram& prog, int space) {
     const bool raw = space == NKW_RAW;
-    if (P.n_planes == 1) return raw ? launch_one<1, true>(ctx, stream, P, prog) : launch_one<1, false>(ctx, stream, P, prog);
-    if (P.n_planes == 2) return raw ? launch_one<2, true>(ctx, stream, P, prog) : launch_one<2, false>(ctx, stream, P, prog);
-    return raw ? launch_one<3, true>(ctx, stream, P, prog) : launch_one<3, false>(ctx, stream, P, prog);
+    const bool markov = prog.markov && std::getenv("SIESTA_NKP_NO_MARKOV") == nullptr;
+#define SIESTA_NKP_GO(NPL)                                                                                              \
+    (raw ? (markov ? launch_one<NPL, true, true>(ctx, stream, P, prog) : launch_one<NPL, true, false>(ctx, stream, P, prog))   \
+         : (markov ? launch_one<NPL, false, true>(ctx, stream, P, prog) : launch_one<NPL, false, false>(ctx, stream, P, prog)))
+    if (P.n_planes == 1) return SIESTA_NKP_GO(1);
+    if (P.n_planes == 2) return SIESTA_NKP_GO(2);
+    return SIESTA_NKP_GO(3);
+#undef SIESTA_NKP_GO
 }
 
 }  // namespace siesta

@@ -170,14 +170,23 @@ __global__ void __launch_bounds__(XD_THREADS) xchg_decode_uniform_kernel(const _
             }
         }
         __syncthreads();
-        const int64_t t0 = e0 / K;
-        for (int i = tid; i < cnt; i += XD_THREADS) {
-            const int64_t e = e0 + i;
-            D.pos[eb + e] = (int32_t)s_pos[i];
-            if (h.all_cols) {
-                D.rank[eb + e] = (int32_t)s_rank[i];
-                D.act[eb + e] = (int32_t)s_act[i];
-                D.ts[eb + e] = s_base[e / K - t0] + (long long)s_delta[i] * unit;
+        {
+            // event i of the tile belongs to trace (r0 + i) / K of the tile (r0 = events of the tile's first trace that sit
+            // in the previous tile): small numbers, so the division is one multiply-high by ceil(2^32 / K)
+            const uint32_t r0 = (uint32_t)(e0 - (e0 / K) * K);
+            const uint32_t magic = (uint32_t)((0x100000000ull + (unsigned)K - 1) / (unsigned)K);
+            int32_t* o_pos = D.pos + eb + e0;
+            int32_t* o_rank = h.all_cols ? D.rank + eb + e0 : nullptr;
+            int32_t* o_act = h.all_cols ? D.act + eb + e0 : nullptr;
+            long long* o_ts = h.all_cols ? reinterpret_cast<long long*>(D.ts) + eb + e0 : nullptr;
+#pragma unroll 4
+            for (int i = tid; i < cnt; i += XD_THREADS) {
+                o_pos[i] = (int32_t)s_pos[i];
+                if (h.all_cols) {
+                    o_rank[i] = (int32_t)s_rank[i];
+                    o_act[i] = (int32_t)s_act[i];
+                    o_ts[i] = s_base[K == 1 ? (r0 + i) : __umulhi(r0 + (uint32_t)i, magic)] + (long long)s_delta[i] * unit;
+                }
             }
         }
         __syncthreads();
@@ -431,12 +440,12 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
     XCtrl* me = reinterpret_cast<XCtrl*>(x->region);
     const unsigned long long seq = ++x->seq;
 
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     struct EvGuard {
         cudaEvent_t* e;
-        ~EvGuard() { for (int i = 0; i < 4; ++i) if (e[i]) cudaEventDestroy(e[i]); }
+        ~EvGuard() { for (int i = 0; i < 5; ++i) if (e[i]) cudaEventDestroy(e[i]); }
     } ev_guard{ev};
-    for (int i = 0; i < 4; ++i) SIESTA_CUDA_OK(cudaEventCreate(&ev[i]));
+    for (int i = 0; i < 5; ++i) SIESTA_CUDA_OK(cudaEventCreate(&ev[i]));
     int* d_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(x->d_hdrs) + sizeof(XHeader) * XCHG_MAX_RANKS);
     int* h_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(x->h_hdrs) + sizeof(XHeader) * XCHG_MAX_RANKS);
     SIESTA_CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), stream));
@@ -573,6 +582,7 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
             if (v >= 1) gx = v;
         }
         const dim3 grid((unsigned)gx, (unsigned)world);
+        SIESTA_CUDA_OK(cudaEventRecord(ev[4], stream));
         if (uniform) xchg_decode_uniform_kernel<<<grid, XD_THREADS, 0, stream>>>(D);
         else xchg_decode_general_kernel<<<grid, XD_THREADS, 0, stream>>>(D);
         SIESTA_LAUNCHED();
@@ -593,12 +603,14 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
     float ms_scan = 0.f, ms_wait = 0.f, ms_pull = 0.f;
     cudaEventElapsedTime(&ms_scan, ev[0], ev[1]);
     cudaEventElapsedTime(&ms_wait, ev[1], ev[2]);
-    cudaEventElapsedTime(&ms_pull, ev[2], ev[3]);
+    cudaEventElapsedTime(&ms_pull, ev[4], ev[3]);
+    float ms_gap = 0.f;   // the device idles while the host reads the sizes and allocates the joined result
+    cudaEventElapsedTime(&ms_gap, ev[2], ev[4]);
 
     DevMatchesImplX* impl = new DevMatchesImplX();
     std::memset(impl, 0, sizeof(*impl));
     impl->bufs[0] = fin;
-    impl->free_stream = x->ctx->stream;
+    impl->free_stream = x->stream;   // freed on the stream it was allocated on: the pool hands the block to the next request at once
     impl->device = x->ctx->device;
     out->n_traces = n_tr;
     out->n_occurrences = n_occ;
@@ -606,7 +618,7 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
     const bool counted = (flags & (SIESTA_F_COUNT_MATCHES | SIESTA_F_RETURN_ALL | SIESTA_F_LITERAL_RUNS)) != 0;
     out->n_matches_emitted = counted ? emitted : -1;
     out->n_ref_errors = n_err;
-    out->kernel_ms = ms_scan + ms_wait + ms_pull;
+    out->kernel_ms = ms_scan + ms_wait + ms_gap + ms_pull;
     out->detect_ms = k1_ms;
     out->d_trace_idx = D.trace_idx;
     out->d_occ_off = D.occ_off;
@@ -628,6 +640,7 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
         stats->scan_ms = ms_scan;
         stats->wait_ms = ms_wait;
         stats->pull_ms = ms_pull;
+        stats->host_gap_ms = ms_gap;
         int64_t wire = 0;
         for (int p = 0; p < world; ++p) {
             if (p == rank) continue;

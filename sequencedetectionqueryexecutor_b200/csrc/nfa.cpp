@@ -163,6 +163,25 @@ int nkw_build(const DevNfa& dn, uint32_t flags, NkwProgram* out) {
             out->cc[s][k] = (uint8_t)(c + (le ? 1 : 0));
         }
     }
+    // Markov form?
+    out->markov = 1;
+    for (int k = 1; k < dn.n_states; ++k) {
+        if (out->neg[k]) {
+            if (dn.n_preds[k] || dn.n_preds[k + 1]) out->markov = 0;   // (class NK: a negative state is never the last one)
+            continue;
+        }
+        const int j = out->neg[k - 1] ? k - 2 : k - 1;
+        out->prev[k] = (uint8_t)j;
+        int64_t ge = 1, le = 255;
+        for (int q = 0; q < dn.n_preds[k]; ++q) {
+            if (dn.p_ref[k][q] != j) out->markov = 0;
+            const int64_t c = std::min<int64_t>(dn.p_c[k][q], 200);
+            if (dn.p_op[k][q] == SIESTA_OP_LE) le = std::min(le, c);
+            else ge = std::max(ge, c);
+        }
+        out->m_ge[k] = (uint8_t)std::min<int64_t>(ge, 200);
+        out->m_le[k] = (uint8_t)le;
+    }
     if (!evt_pos) return any_ts ? NKW_NONE : NKW_RANK;
     if (any_pos && any_ts) return NKW_NONE;
     return any_pos ? NKW_RAW : NKW_RANK;

@@ -127,6 +127,15 @@ extern "C" int engine_host_detect(const int64_t* trace_off, const int32_t* act, 
                     for (int k = 0; k < SIESTA_MAX_STATES; ++k)
                         if (meta[j] & (1u << k)) T[k] |= 1u << j;
                 hit = nkw_eval<uint32_t>(prog, T, best, emitted, first_only);
+                if (prog.markov) {   // the backward all-starts evaluation must agree with the per-start walks
+                    uint32_t best_m = 0;
+                    unsigned emitted_m = 0;
+                    const bool hit_m = nkw_eval_markov<uint32_t>(prog, T, best_m, emitted_m);
+                    if (hit_m != hit || (hit && best_m != best) || (!first_only && emitted_m != emitted)) {
+                        siesta::set_error("nkw_eval_markov<rank> disagrees with nkw_eval");
+                        return -98;
+                    }
+                }
                 // cross-check against the generic greedy walk on the filtered list (the staged kernel's evaluator)
                 TraceEvents ev{meta.data(), nullptr, 1, (int)meta.size(), evt_pos, 1};
                 int nsel = 0;
@@ -146,6 +155,15 @@ extern "C" int engine_host_detect(const int64_t* trace_off, const int32_t* act, 
                         if (m & (1u << k)) T[k] |= 1ull << slot;
                 }
                 hit = nkw_eval<unsigned long long>(prog, T, best, emitted, first_only);
+                if (prog.markov) {
+                    unsigned long long best_m = 0;
+                    unsigned emitted_m = 0;
+                    const bool hit_m = nkw_eval_markov<unsigned long long>(prog, T, best_m, emitted_m);
+                    if (hit_m != hit || (hit && best_m != best) || (!first_only && emitted_m != emitted)) {
+                        siesta::set_error("nkw_eval_markov<raw> disagrees with nkw_eval");
+                        return -98;
+                    }
+                }
                 PosEvents pe{R, lead, evt_pos};
                 int nsel = 0;
                 unsigned emitted_g = 0;

@@ -37,6 +37,14 @@ def nk_nfa(rng, n_act):
         types = [int(x) for x in rng.choice(n_act, size=min(k, n_act), replace=False)]
         states.append({"kind": kind, "types": types, "preds": []})
     positive = [s for s in range(n) if states[s]["kind"] != X_]
+    if rng.random() < 0.4:   # Markov shape: position predicates on the positive state before (kernel K1-P's backward evaluation)
+        for b in range(1, n):
+            if states[b]["kind"] == X_ or states[b - 1]["kind"] == X_:
+                continue
+            for _ in range(int(rng.integers(0, 3))):
+                op = abi.OP_LE if rng.random() < 0.5 else abi.OP_GE
+                states[b]["preds"].append((abi.ATTR_POSITION, op, b - 1, int(rng.integers(0, 12))))
+        return states
     for _ in range(3):
         if n >= 2 and rng.random() < 0.6:
             b = int(rng.integers(1, n))
