@@ -115,6 +115,23 @@ __device__ __forceinline__ void load_sectors_vec(const DetectParams& P, long lon
     }
 }
 
+// 16 slots (two sectors) of this lane's trace starting at element e: two 256-bit loads, or "no event" past the trace
+__device__ __forceinline__ void load_quarter(const DetectParams& P, long long e, long long o1, int4 (&v)[4]) {
+    const int none = P.n_act;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const long long c = e + 8 * q;
+        if (c >= o1) {
+            v[2 * q] = v[2 * q + 1] = make_int4(none, none, none, none);
+        } else {
+            asm volatile("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(v[2 * q].x), "=r"(v[2 * q].y), "=r"(v[2 * q].z), "=r"(v[2 * q].w), "=r"(v[2 * q + 1].x),
+                           "=r"(v[2 * q + 1].y), "=r"(v[2 * q + 1].z), "=r"(v[2 * q + 1].w)
+                         : "l"(P.act + c));
+        }
+    }
+}
+
 // Relevance test of the filter: relrev holds the pattern's activity set bit-reversed (bit 31 - a <=> activity a), so
 // `relrev << a` moves activity a's bit to the top and one funnel shift pushes it into the survivor mask: two
 // instructions per event.  shl.b32 clamps shift amounts above 31, so a masked-out slot (a = -1) pushes 0.

@@ -29,7 +29,7 @@
 namespace siesta {
 
 #ifndef SIESTA_NKP_MIN_CTAS
-#define SIESTA_NKP_MIN_CTAS 6
+#define SIESTA_NKP_MIN_CTAS 8
 #endif
 #ifndef SIESTA_NKP_PREFETCH   // 1: request the next tile's offsets a tile early (six more live registers)
 #define SIESTA_NKP_PREFETCH 0
@@ -48,9 +48,9 @@ namespace siesta {
 // whatever the activity ids are (measured before: 58 M wavefronts for 30 M ideal, the L1 data pipe at 85 % of its peak).
 constexpr int LUT_SKEW = 8;
 template <int NPL, bool RAW>
-__device__ __forceinline__ void scan32(const uint4* __restrict__ lut, const int4 (&v)[8], uint32_t (&pl)[3], uint32_t& racc) {
+__device__ __forceinline__ void scan16(const uint4* __restrict__ lut, const int4 (&v)[4], uint32_t (&pl)[3], uint32_t& racc) {
 #pragma unroll
-    for (int q = 7; q >= 0; --q) {   // last slot first: bit 0 = first slot / first relevant event
+    for (int q = 3; q >= 0; --q) {   // last slot first: bit 0 = first slot / first relevant event
         const int a[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
 #pragma unroll
         for (int i = 3; i >= 0; --i) {
@@ -142,30 +142,39 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
         const long long span = (o1 - o0) + lead;  // slots the trace needs
         bool fits = span <= 64 && ((o1 + 7) & ~7LL) <= P.n_events;
         const long long o1s = fits ? o1 : o0;     // a trace that does not fit is not read here
-        int4 v0[8], v1[8];
-        load_sectors_vec(P, e0 + 32, o1s, v1);   // scanned first (last slot first)
-        load_sectors_vec(P, e0, o1s, v0);
         u64 valid = 0;
         if (fits && o1 > o0) valid = (span == 64 ? ~0ull : ((1ull << (int)span) - 1ull)) & ~((1ull << lead) - 1ull);
         const bool second = __any_sync(0xffffffffu, fits && span > 32);
 
+        // The 64 slots come in quarters of 16 (two 256-bit loads each), last quarter first, double-buffered: the loads of
+        // the next quarter are in flight while this one is scanned, and only two quarters (32 registers) are ever live -
+        // the kernel fits more warps on an SM than with all 64 slots in registers.
+        uint32_t q[3] = {0u, 0u, 0u}, qb[3] = {0u, 0u, 0u}, ra = 0u, rb = 0u;   // RAW: q = slots 0..31, qb = slots 32..63
+        {
+            int4 A[4], B[4];
+            if (second) {
+                load_quarter(P, e0 + 48, o1s, A);
+                load_quarter(P, e0 + 32, o1s, B);
+                scan16<NPL, RAW>(s_lut, A, RAW ? qb : q, rb);
+                load_quarter(P, e0 + 16, o1s, A);
+                scan16<NPL, RAW>(s_lut, B, RAW ? qb : q, rb);
+                load_quarter(P, e0, o1s, B);
+                rb += 1u;
+            } else {
+                load_quarter(P, e0 + 16, o1s, A);
+                load_quarter(P, e0, o1s, B);
+            }
+            scan16<NPL, RAW>(s_lut, A, q, ra);
+            scan16<NPL, RAW>(s_lut, B, q, ra);
+            ra += 1u;
+        }
         mask_t pl[3];
         u64 Rv;   // slots of the trace that hold an event of the pattern
         if constexpr (RAW) {
-            uint32_t pa[3] = {0u, 0u, 0u}, pb[3] = {0u, 0u, 0u}, unused = 0u;
-            scan32<NPL, true>(s_lut, v0, pa, unused);
-            if (second) scan32<NPL, true>(s_lut, v1, pb, unused);
 #pragma unroll
-            for (int p = 0; p < 3; ++p) pl[p] = p < NPL ? (((u64)pa[p] | ((u64)pb[p] << 32)) & valid) : 0ull;
+            for (int p = 0; p < 3; ++p) pl[p] = p < NPL ? (((u64)q[p] | ((u64)qb[p] << 32)) & valid) : 0ull;
             Rv = pl[0] | pl[1] | pl[2];
         } else {
-            uint32_t q[3] = {0u, 0u, 0u}, ra = 0u, rb = 0u;
-            if (second) {   // last slot first
-                scan32<NPL, false>(s_lut, v1, q, rb);
-                rb += 1u;
-            }
-            scan32<NPL, false>(s_lut, v0, q, ra);
-            ra += 1u;
             const u64 Rraw = (u64)ra | ((u64)rb << 32);             // includes the neighbours' events in the end sectors
             Rv = Rraw & valid;
             const int n_lead = __popc(ra & ((1u << lead) - 1u));    // relevant events of the previous trace: ranks 0 ..
