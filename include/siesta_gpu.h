@@ -35,7 +35,7 @@ extern "C" {
 #define SIESTA_OK 0
 #define SIESTA_E_INVALID (-1)     /* bad argument / malformed NFA                */
 #define SIESTA_E_CUDA (-2)        /* CUDA runtime failure, or no device          */
-#define SIESTA_E_UNSUPPORTED (-3) /* NFA shape the GPU engine does not accept    */
+#define SIESTA_E_UNSUPPORTED (-3) /* NFA shape / flag combination the GPU engine does not accept */
 #define SIESTA_E_NOMEM (-4)
 #define SIESTA_E_REFERENCE_THROWS (-5) /* the Java engine would throw (see n_ref_errors) */
 
@@ -225,7 +225,15 @@ typedef struct siesta_matches {
     int64_t* err_trace_idx;    /* [n_ref_errors] ascending                           */
     double kernel_ms;          /* device time of all kernels of the call (CUDA events) */
     double detect_ms;          /* device time of the verification kernel K1 alone      */
+    /* Traces beyond the GPU engine's per-trace limits (more than 64 pattern-relevant events, 1024 live runs or 65 536
+     * events).  The reference has no such limit (S/engine/Engine.java:207-224), so the request does NOT fail for them:
+     * every other trace is answered and these are listed (ascending) for the caller to evaluate elsewhere - the JNI
+     * shim hands them to the reference's own engine.  More than SIESTA_MAX_UNSUPPORTED of them fail
+     * the call with SIESTA_E_UNSUPPORTED. */
+    int64_t n_unsupported;
+    int64_t* unsupported_trace_idx; /* [n_unsupported] */
 } siesta_matches;
+#define SIESTA_MAX_UNSUPPORTED 65536
 
 /* Replaces SaseConnector.evaluate(pattern, events, onlyAppearances) followed by
  * occurrences.forEach(clearOccurrences(returnAll))
@@ -265,6 +273,8 @@ typedef struct siesta_dev_matches {
     void* d_block;
     int64_t block_bytes;
     void* impl;
+    int64_t n_unsupported;            /* as in siesta_matches; the ninth array of the block */
+    int64_t* d_unsupported_trace_idx;
 } siesta_dev_matches;
 
 int siesta_detect_device(siesta_log* log, const siesta_nfa* nfa, const int64_t* d_cand,

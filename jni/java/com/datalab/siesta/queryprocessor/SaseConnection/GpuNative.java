@@ -23,7 +23,7 @@ final class GpuNative {
     static native long detect(long log, int[] nfa, int flags);
     static native long evaluateEvents(long multi, long[] traceOff, int[] act, long[] tsMs, int nActivities, int[] nfa, int flags);
     static native long[] matchesSizes(long matches);
-    static native long[] matchesLongs(long matches, int which);   // 0 trace_idx, 1 occ_off, 2 ev_off, 3 ev_ts_ms, 4 err_trace_idx
+    static native long[] matchesLongs(long matches, int which);   // 0 trace_idx, 1 occ_off, 2 ev_off, 3 ev_ts_ms, 4 err_trace_idx, 5 unsupported_trace_idx
     static native int[] matchesInts(long matches, int which);     // 0 ev_pos, 1 ev_rank, 2 ev_act
     static native void matchesFree(long matches);
     static native long[] declareCounts(long log, int nActivities, int kCap);

@@ -44,6 +44,8 @@ import java.util.Map;
  *    only reads the trace ids (retrieveTimeInformation :235-236).
  *  - the events travel as a CSR log: trace offsets, dense activity ids (names folded with toLowerCase, because the
  *    engine compares types with equalsIgnoreCase, State.java:135-137), epoch milliseconds.
+ *  - a trace beyond the GPU engine's per-trace limits does not fail the request: the library answers all others and
+ *    lists it; this class hands the listed traces to super.evaluate (the reference's engine).
  *  - EventPos lists (positions-mode logs) carry their own `position`; the CSR has no position column - the position
  *    of an event is its index in the trace - so such a list is laid out sparsely: slot = position, empty slots hold an
  *    activity id no pattern uses.  The library's EventPos route (SIESTA_F_EVT_POS) then sees exactly the
@@ -140,6 +142,14 @@ public class GpuSaseConnector extends SaseConnector {
                     ocs.addOccurrence(new Occurrence(evs));
                 }
                 out.add(ocs);
+            }
+            // traces beyond the GPU engine's per-trace limits (more than 64 pattern-relevant events ...): the reference's own
+            // engine answers them - it has no such limit (Engine.java:207-224).  Its result carries EVERY match, which the
+            // caller's clearOccurrences reduces exactly as on the CPU path.
+            if (sizes[5] > 0) {
+                Map<String, List<Event>> rest = new HashMap<>();
+                for (long u : GpuNative.matchesLongs(m, 5)) rest.put(traceIds.get((int) u), events.get(traceIds.get((int) u)));
+                out.addAll(super.evaluate(pattern, rest, onlyAppearances));
             }
             return out;
         } finally {

@@ -153,17 +153,18 @@ NATIVE(jlong, evaluateEvents)(JNIEnv* env, jclass cls, jlong multi, jlongArray t
     return m;
 }
 
-/* long[] matchesSizes(long m) -> { n_traces, n_occurrences, n_events, n_matches_emitted, n_ref_errors } */
+/* long[] matchesSizes(long m) -> { n_traces, n_occurrences, n_events, n_matches_emitted, n_ref_errors, n_unsupported } */
 NATIVE(jlongArray, matchesSizes)(JNIEnv* env, jclass cls, jlong mh) {
     (void)cls;
     const siesta_matches* m = (const siesta_matches*)(intptr_t)mh;
-    const jlong v[5] = {m->n_traces, m->n_occurrences, m->n_events, m->n_matches_emitted, m->n_ref_errors};
-    jlongArray out = (*env)->NewLongArray(env, 5);
-    if (out) (*env)->SetLongArrayRegion(env, out, 0, 5, v);
+    const jlong v[6] = {m->n_traces, m->n_occurrences, m->n_events, m->n_matches_emitted, m->n_ref_errors, m->n_unsupported};
+    jlongArray out = (*env)->NewLongArray(env, 6);
+    if (out) (*env)->SetLongArrayRegion(env, out, 0, 6, v);
     return out;
 }
 
-/* long[] matchesLongs(long m, int which): 0 trace_idx, 1 occ_off, 2 ev_off, 3 ev_ts_ms, 4 err_trace_idx */
+/* long[] matchesLongs(long m, int which): 0 trace_idx, 1 occ_off, 2 ev_off, 3 ev_ts_ms, 4 err_trace_idx,
+ * 5 unsupported_trace_idx (traces beyond the GPU engine's limits: evaluate them with the reference's engine) */
 NATIVE(jlongArray, matchesLongs)(JNIEnv* env, jclass cls, jlong mh, jint which) {
     (void)cls;
     const siesta_matches* m = (const siesta_matches*)(intptr_t)mh;
@@ -175,6 +176,7 @@ NATIVE(jlongArray, matchesLongs)(JNIEnv* env, jclass cls, jlong mh, jint which) 
         case 2: src = m->ev_off; n = m->n_occurrences + 1; break;
         case 3: src = m->ev_ts_ms; n = src ? m->n_events : 0; break;
         case 4: src = m->err_trace_idx; n = m->n_ref_errors; break;
+        case 5: src = m->unsupported_trace_idx; n = m->n_unsupported; break;
         default: break;
     }
     if (n > 0x7fffffff) {   /* a Java array holds < 2^31 elements: ask for a narrower candidate list */

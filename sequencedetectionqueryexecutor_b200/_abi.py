@@ -55,7 +55,8 @@ class Matches(C.Structure):
                 ("ev_off", C.POINTER(C.c_int64)), ("ev_pos", C.POINTER(C.c_int32)),
                 ("ev_rank", C.POINTER(C.c_int32)), ("ev_act", C.POINTER(C.c_int32)),
                 ("ev_ts_ms", C.POINTER(C.c_int64)), ("err_trace_idx", C.POINTER(C.c_int64)),
-                ("kernel_ms", C.c_double), ("detect_ms", C.c_double)]
+                ("kernel_ms", C.c_double), ("detect_ms", C.c_double),
+                ("n_unsupported", C.c_int64), ("unsupported_trace_idx", C.POINTER(C.c_int64))]
 
 
 class PairCount(C.Structure):
@@ -70,7 +71,7 @@ class DevMatches(C.Structure):
                 ("d_ev_pos", C.c_void_p), ("d_ev_rank", C.c_void_p), ("d_ev_act", C.c_void_p),
                 ("d_ev_ts_ms", C.c_void_p), ("d_err_trace_idx", C.c_void_p),
                 ("kernel_ms", C.c_double), ("detect_ms", C.c_double), ("d_block", C.c_void_p), ("block_bytes", C.c_int64),
-                ("impl", C.c_void_p)]
+                ("impl", C.c_void_p), ("n_unsupported", C.c_int64), ("d_unsupported_trace_idx", C.c_void_p)]
 
 
 class ExchangeStats(C.Structure):
@@ -119,7 +120,7 @@ class MatchResult:
 
     __slots__ = ("n_traces", "n_occurrences", "n_events", "n_matches_emitted", "n_ref_errors", "trace_idx",
                  "occ_off", "ev_off", "ev_pos", "ev_rank", "ev_act", "ev_ts_ms", "err_trace_idx", "kernel_ms", "detect_ms",
-                 "_free")
+                 "n_unsupported", "unsupported_trace_idx", "_free")
 
     def close(self):
         """Release the library-owned block behind zero-copy views (from_struct(copy=False)); the arrays die with it."""
@@ -153,6 +154,8 @@ class MatchResult:
         r.ev_act = _arr(m.ev_act, m.n_events, np.int32, copy) if m.ev_act else None
         r.ev_ts_ms = _arr(m.ev_ts_ms, m.n_events, np.int64, copy) if m.ev_ts_ms else None
         r.err_trace_idx = _arr(m.err_trace_idx, m.n_ref_errors, np.int64, copy)
+        r.n_unsupported = getattr(m, "n_unsupported", 0)
+        r.unsupported_trace_idx = _arr(m.unsupported_trace_idx, r.n_unsupported, np.int64, True) if r.n_unsupported else np.zeros(0, dtype=np.int64)
         return r
 
     def occurrences_of(self, i):

@@ -385,7 +385,7 @@ class PendingDetect:
 class DeviceMatches:
     def __init__(self, dm):
         self.dm = dm
-        for k in ("n_traces", "n_occurrences", "n_events", "n_matches_emitted", "n_ref_errors", "kernel_ms", "detect_ms"):
+        for k in ("n_traces", "n_occurrences", "n_events", "n_matches_emitted", "n_ref_errors", "kernel_ms", "detect_ms", "n_unsupported"):
             setattr(self, k, getattr(dm, k))
 
     def close(self):
@@ -442,7 +442,8 @@ class DeviceMatches:
                "occ_off": view(d.d_occ_off, d.n_traces + 1, "<i8", torch.int64),
                "ev_off": view(d.d_ev_off, d.n_occurrences + 1, "<i8", torch.int64),
                "ev_pos": view(d.d_ev_pos, d.n_events, "<i4", torch.int32),
-               "err_trace_idx": view(d.d_err_trace_idx, d.n_ref_errors, "<i8", torch.int64)}
+               "err_trace_idx": view(d.d_err_trace_idx, d.n_ref_errors, "<i8", torch.int64),
+               "unsupported_trace_idx": view(d.d_unsupported_trace_idx, d.n_unsupported, "<i8", torch.int64)}
         if d.d_ev_rank:
             out["ev_rank"] = view(d.d_ev_rank, d.n_events, "<i4", torch.int32)
             out["ev_act"] = view(d.d_ev_act, d.n_events, "<i4", torch.int32)

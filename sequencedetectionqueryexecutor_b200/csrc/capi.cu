@@ -278,7 +278,7 @@ namespace siesta {
 // siesta_matches.  part_ctx (optional): the context (device, stream) each part lives on - shards of a multi-GPU log.
 int assemble_matches(Ctx* c, std::vector<siesta_dev_matches>& parts, uint32_t flags, cudaStream_t stream, siesta_matches** out,
                      const std::vector<Ctx*>* part_ctx) {
-    int64_t n_tr = 0, n_occ = 0, n_ev = 0, n_err = 0, n_emit = 0;
+    int64_t n_tr = 0, n_occ = 0, n_ev = 0, n_err = 0, n_emit = 0, n_unsup = 0;
     double k_ms = 0, d_ms = 0;
     bool counted = true;
     for (const siesta_dev_matches& p : parts) {
@@ -286,6 +286,7 @@ int assemble_matches(Ctx* c, std::vector<siesta_dev_matches>& parts, uint32_t fl
         n_occ += p.n_occurrences;
         n_ev += p.n_events;
         n_err += p.n_ref_errors;
+        n_unsup += p.n_unsupported;
         if (p.n_matches_emitted < 0) counted = false;
         else n_emit += p.n_matches_emitted;
         k_ms += p.kernel_ms;
@@ -298,6 +299,7 @@ int assemble_matches(Ctx* c, std::vector<siesta_dev_matches>& parts, uint32_t fl
     const size_t o_evoff = off; off += align64((size_t)(n_occ + 1) * 8);
     const size_t o_pos = off;   off += align64((size_t)(n_ev ? n_ev : 1) * 4);
     const size_t o_err = off;   off += align64((size_t)(n_err ? n_err : 1) * 8);
+    const size_t o_unsup = off; off += align64((size_t)(n_unsup ? n_unsup : 1) * 8);
     size_t o_rank = 0, o_act = 0, o_ts = 0;
     if (all_cols) {
         o_rank = off; off += align64((size_t)(n_ev ? n_ev : 1) * 4);
@@ -323,6 +325,8 @@ int assemble_matches(Ctx* c, std::vector<siesta_dev_matches>& parts, uint32_t fl
     m->n_events = n_ev;
     m->n_matches_emitted = counted ? n_emit : -1;
     m->n_ref_errors = n_err;
+    m->n_unsupported = n_unsup;
+    m->unsupported_trace_idx = reinterpret_cast<int64_t*>(base + o_unsup);
     m->kernel_ms = k_ms;
     m->detect_ms = d_ms;
     m->trace_idx = reinterpret_cast<int64_t*>(base + o_trace);
@@ -337,7 +341,7 @@ int assemble_matches(Ctx* c, std::vector<siesta_dev_matches>& parts, uint32_t fl
     }
     m->occ_off[0] = 0;
     m->ev_off[0] = 0;
-    int64_t a_tr = 0, a_occ = 0, a_ev = 0, a_err = 0;
+    int64_t a_tr = 0, a_occ = 0, a_ev = 0, a_err = 0, a_unsup = 0;
     cudaError_t e = cudaSuccess;
     cudaStream_t cur = stream;
     auto d2h = [&](void* dst, const void* src, size_t bytes) {
@@ -355,6 +359,7 @@ int assemble_matches(Ctx* c, std::vector<siesta_dev_matches>& parts, uint32_t fl
         d2h(m->ev_off + a_occ, p.d_ev_off, (size_t)(p.n_occurrences + 1) * 8);
         d2h(m->ev_pos + a_ev, p.d_ev_pos, (size_t)p.n_events * 4);
         d2h(m->err_trace_idx + a_err, p.d_err_trace_idx, (size_t)p.n_ref_errors * 8);
+        d2h(m->unsupported_trace_idx + a_unsup, p.d_unsupported_trace_idx, (size_t)p.n_unsupported * 8);
         if (all_cols) {
             d2h(m->ev_rank + a_ev, p.d_ev_rank, (size_t)p.n_events * 4);
             d2h(m->ev_act + a_ev, p.d_ev_act, (size_t)p.n_events * 4);
@@ -364,6 +369,7 @@ int assemble_matches(Ctx* c, std::vector<siesta_dev_matches>& parts, uint32_t fl
         a_occ += p.n_occurrences;
         a_ev += p.n_events;
         a_err += p.n_ref_errors;
+        a_unsup += p.n_unsupported;
     }
     if (part_ctx) {
         for (size_t pi = 0; pi < parts.size() && e == cudaSuccess; ++pi) {

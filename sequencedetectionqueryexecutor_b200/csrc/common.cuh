@@ -127,13 +127,13 @@ constexpr size_t XCHG_CTRL_BYTES = 4096;   // control page at the start of a reg
 enum { XST_LIMITS = 1, XST_STAGING = 2, XST_RANGE = 4, XST_ERRCAP = 8, XST_TIMEOUT = 16 };
 struct XHeader {
     unsigned long long seq;
-    int64_t n_tr, n_occ, n_ev, n_err, n_emitted;
+    int64_t n_tr, n_occ, n_ev, n_err, n_emitted, n_unsup;
     int64_t trace_base;        // global index of the shard's first trace
     int32_t all_cols, seconds; // event columns present; ts_delta in seconds (EventTs route) or milliseconds
     int32_t uniform_k;         // > 0: one occurrence per trace and uniform_k events per occurrence (no offset sections)
     int32_t status;            // XST_* bits: the request failed on this rank
-    int64_t o_trace, o_base, o_occ_off, o_ev_off, o_pos, o_rank, o_act, o_delta, o_err;   // byte offsets into the data area
-    int64_t pad[14];
+    int64_t o_trace, o_base, o_occ_off, o_ev_off, o_pos, o_rank, o_act, o_delta, o_err, o_unsup;   // byte offsets into the data area
+    int64_t pad[12];
 };
 static_assert(sizeof(XHeader) == 256, "XHeader is 256 bytes");
 // Where the placement writes the compact block (detect.cu: detect_device_pack_impl)

@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4)
                 if (status == ST_ERR) P.err_list[atomicAdd(P.counters + 3, 1ull)] = t;
                 else if (status == ST_OVF) {
                     const unsigned long long at = atomicAdd(P.counters + P.ovf_slot, 1ull);
-                    if (P.ovf_list) P.ovf_list[at] = ci;
+                    if (P.ovf_list && (P.ovf_cap == 0 || (long long)at < P.ovf_cap)) P.ovf_list[at] = ci;
                 }
             }
         }
@@ -691,6 +691,7 @@ struct DetectPending {
     size_t n_blk = 0;
     unsigned long long *d_blk = nullptr, *d_top = nullptr, *d_counters = nullptr;
     int64_t* d_err = nullptr;
+    int64_t* d_unsup = nullptr;           // candidate indices of the traces beyond the engine limits
     void* work = nullptr;                 // scratch of the call (freed by the second half)
     int uniform_k = 0;                    // > 0: one occurrence per trace, uniform_k events each (class NK, first-largest)
     cudaEvent_t ev0 = nullptr, evd = nullptr;
@@ -775,6 +776,7 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
     const size_t n_reg = use_nkp ? 2 : 1;  // staging regions: [0, cap) by atomics (staged kernels), [cap, 2 cap) fixed tile slots (K1-P)
     const size_t n_blk = (nn + GT - 1) / GT;
     const size_t o_ovf2 = use_nkp ? carve(nn * 8) : 0;
+    const size_t o_unsup = carve((size_t)SIESTA_MAX_UNSUPPORTED * 8);   // traces beyond the engine limits (wide launch)
     const size_t o_nlut = use_nkp ? carve((size_t)(log->n_activities + 1) * 16) : 0;
     const size_t o_lut = carve(lut.size() * sizeof(uint16_t)), o_nocc = carve(nn * 4), o_stage = carve(nn * 8),
                  o_stage_occ = carve(return_all ? nn * 8 : 0), o_counters = carve(32 * 8), o_err = carve(nn * 8), o_ovf = carve(nn * 8),
@@ -925,7 +927,8 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
         DetectParams Q = P;
         Q.work = b_ovf.as<int64_t>();
         Q.n_work_dev = b_counters.as<unsigned long long>() + 4;
-        Q.ovf_list = nullptr;
+        Q.ovf_list = reinterpret_cast<int64_t*>(wb + o_unsup);
+        Q.ovf_cap = SIESTA_MAX_UNSUPPORTED;
         Q.ovf_slot = 7;
         Q.tile_slot = 17;
         if (dn.fast_class == FAST_FK2) rc = launch_detect<2, 0, 0, false, FAST_FK2>(ctx, stream, Q, dn);
@@ -948,6 +951,7 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
     q->d_top = reinterpret_cast<unsigned long long*>(wb + o_top);
     q->d_counters = b_counters.as<unsigned long long>();
     q->d_err = b_err.as<int64_t>();
+    q->d_unsup = reinterpret_cast<int64_t*>(wb + o_unsup);
     q->work = work.release();
     q->uniform_k = (!return_all && !dn.any_kleene) ? std::max(1, n_positive) : 0;
     q->ev0 = ev0;
@@ -983,9 +987,9 @@ int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out) {
     int rc = SIESTA_OK;
     SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
     if (n > 0) {
-        if (h_cnt[7] > 0) {
-            set_error(std::to_string(h_cnt[7]) + " trace(s) exceed the engine limits (64 pattern-relevant events, "
-                      "1024 live runs or 65536 events per trace)");
+        if (h_cnt[7] > SIESTA_MAX_UNSUPPORTED) {
+            set_error(std::to_string(h_cnt[7]) + " traces exceed the engine limits (64 pattern-relevant events, 1024 live runs or "
+                      "65536 events per trace); at most " + std::to_string(SIESTA_MAX_UNSUPPORTED) + " are listed per request");
             return SIESTA_E_UNSUPPORTED;
         }
         if (h_cnt[5] > 0) {
@@ -1002,6 +1006,7 @@ int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out) {
     fprintf(stderr, "[siesta phase timing] warp-cycles: filter %llu engine %llu output %llu\n", h_cnt[8], h_cnt[9], h_cnt[10]);
 #endif
     const int64_t n_occ = (int64_t)h_cnt[0], n_ev = (int64_t)h_cnt[1], n_tr = (int64_t)h_cnt[6], n_err = (int64_t)h_cnt[3];
+    const int64_t n_unsup = n > 0 ? (int64_t)h_cnt[7] : 0;
 
     // the result columns: one allocation, owned by the returned object
     DevBuf fin(stream);
@@ -1019,8 +1024,10 @@ int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out) {
         q_act = fcarve((size_t)n_ev * 4);
         q_ts = fcarve((size_t)n_ev * 8);
     }
+    const size_t q_unsup = fcarve((size_t)n_unsup * 8);
     if ((rc = fin.alloc(f_off))) return rc;
     char* fb = fin.as<char>();
+    const View f_unsup{fb + q_unsup};
     const View f_trace{fb + q_trace}, f_occ_off{fb + q_occ}, f_ev_off{fb + q_evoff}, f_pos{fb + q_pos}, f_err{fb + q_err},
         f_rank{all_cols ? fb + q_rank : nullptr}, f_act{all_cols ? fb + q_act : nullptr}, f_ts{all_cols ? fb + q_ts : nullptr};
 
@@ -1071,6 +1078,21 @@ int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out) {
         for (int64_t& x : h) x += base.trace;
         SIESTA_CUDA_OK(cudaMemcpyAsync(f_err.p, h.data(), (size_t)n_err * 8, cudaMemcpyHostToDevice, stream));
     }
+    if (n_unsup > 0) {  // the traces beyond the engine limits, ascending global indices
+        std::vector<int64_t> h((size_t)n_unsup);
+        SIESTA_CUDA_OK(cudaMemcpyAsync(h.data(), q->d_unsup, (size_t)n_unsup * 8, cudaMemcpyDeviceToHost, stream));
+        SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+        if (d_cand) {       // list entries index the candidate list
+            std::vector<int64_t> hc((size_t)n_unsup);
+            for (int64_t i = 0; i < n_unsup; ++i)
+                SIESTA_CUDA_OK(cudaMemcpyAsync(&hc[(size_t)i], d_cand + h[(size_t)i], 8, cudaMemcpyDeviceToHost, stream));
+            SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+            h.swap(hc);
+        }
+        std::sort(h.begin(), h.end());
+        for (int64_t& x : h) x += base.trace;
+        SIESTA_CUDA_OK(cudaMemcpyAsync(f_unsup.p, h.data(), (size_t)n_unsup * 8, cudaMemcpyHostToDevice, stream));
+    }
     SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
     float ms = 0.f, dms = 0.f;
     SIESTA_CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -1096,6 +1118,8 @@ int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out) {
     out->d_ev_act = f_act.as<int32_t>();
     out->d_ev_ts_ms = f_ts.as<int64_t>();
     out->d_err_trace_idx = f_err.as<int64_t>();
+    out->n_unsupported = n_unsup;
+    out->d_unsupported_trace_idx = f_unsup.as<int64_t>();
     out->block_bytes = (int64_t)f_off;
     impl->bufs[0] = out->d_block = fin.release();
     out->impl = impl;
@@ -1122,6 +1146,7 @@ struct PackSections {
     uint16_t* act;
     int32_t* delta;
     int64_t* err;
+    int64_t* unsup;
     int32_t seconds;
     int* status;
 };
@@ -1139,6 +1164,7 @@ static size_t pack_layout(int64_t n, int64_t cap_occ, int64_t cap_ev, int unifor
     h->o_act = all_cols ? take((size_t)cap_ev * 2) : 0;
     h->o_delta = all_cols ? take((size_t)cap_ev * 4) : 0;
     h->o_err = take((size_t)XCHG_ERR_CAP * 8);
+    h->o_unsup = take((size_t)XCHG_ERR_CAP * 8);
     return o;
 }
 
@@ -1238,15 +1264,16 @@ __global__ void __launch_bounds__(GT) gather_packed_kernel(const __grid_constant
 }
 
 // Header of the block: sizes from the request's counters, status, the tails of the offset sections, the error list.
-__global__ void pack_header_kernel(const unsigned long long* counters, const int64_t* err_list, XHeader proto, XHeader* hdr,
-                                   const __grid_constant__ PackSections O) {
+__global__ void pack_header_kernel(const unsigned long long* counters, const int64_t* err_list, const int64_t* unsup_list, XHeader proto,
+                                   XHeader* hdr, const __grid_constant__ PackSections O) {
     const int64_t n_occ = (int64_t)counters[0], n_ev = (int64_t)counters[1], n_tr = (int64_t)counters[6], n_err = (int64_t)counters[3];
+    const int64_t n_unsup = (int64_t)counters[7];
     if (threadIdx.x == 0) {
         int status = *O.status;
-        if (counters[7] > 0) status |= XST_LIMITS;
+        if (n_unsup > XCHG_ERR_CAP) status |= XST_LIMITS;
         if (counters[5] > 0) status |= XST_STAGING;
         if (n_err > XCHG_ERR_CAP) status |= XST_ERRCAP;
-        if (!proto.uniform_k && !(status & (XST_LIMITS | XST_STAGING))) {
+        if (!proto.uniform_k && !(status & XST_STAGING)) {
             O.occ_off[n_tr] = (uint32_t)n_occ;
             O.ev_off[n_occ] = (uint32_t)n_ev;
         }
@@ -1254,11 +1281,13 @@ __global__ void pack_header_kernel(const unsigned long long* counters, const int
         proto.n_occ = n_occ;
         proto.n_ev = n_ev;
         proto.n_err = n_err;
+        proto.n_unsup = n_unsup;
         proto.n_emitted = (int64_t)counters[2];
         proto.status = status;
         *hdr = proto;
     }
     for (int64_t i = threadIdx.x; i < n_err && i < XCHG_ERR_CAP; i += blockDim.x) O.err[i] = err_list[i];
+    for (int64_t i = threadIdx.x; i < n_unsup && i < XCHG_ERR_CAP; i += blockDim.x) O.unsup[i] = unsup_list[i];
 }
 
 int detect_uniform_k(const siesta_nfa* nfa, uint32_t flags) {
@@ -1332,6 +1361,7 @@ int detect_device_pack_impl(DetectPending* q, const PackTarget& tgt) {
     O.act = reinterpret_cast<uint16_t*>(tgt.data + proto.o_act);
     O.delta = reinterpret_cast<int32_t*>(tgt.data + proto.o_delta);
     O.err = reinterpret_cast<int64_t*>(tgt.data + proto.o_err);
+    O.unsup = reinterpret_cast<int64_t*>(tgt.data + proto.o_unsup);
     O.seconds = proto.seconds;
     O.status = reinterpret_cast<int*>(q->d_counters + 24);   // a zeroed word of the request's counter block
     if (n > 0) {
@@ -1360,7 +1390,7 @@ int detect_device_pack_impl(DetectPending* q, const PackTarget& tgt) {
         gather_packed_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G, O, q->uniform_k ? 1 : 0);
         SIESTA_LAUNCHED();
     }
-    pack_header_kernel<<<1, 256, 0, stream>>>(q->d_counters, q->d_err, proto, tgt.hdr, O);
+    pack_header_kernel<<<1, 256, 0, stream>>>(q->d_counters, q->d_err, q->d_unsup, proto, tgt.hdr, O);
     SIESTA_LAUNCHED();
     SIESTA_CUDA_OK(cudaGetLastError());
     return SIESTA_OK;

@@ -63,6 +63,7 @@ struct DetectParams {
     unsigned long long* counters;
     int64_t* err_list;
     int64_t* ovf_list;
+    int64_t ovf_cap;          // entries ovf_list holds (0 = one per candidate); the counter keeps counting past it
 };
 
 __device__ __forceinline__ long long shfl_i64(long long v, int src) {

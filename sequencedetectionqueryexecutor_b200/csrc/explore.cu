@@ -313,6 +313,9 @@ extern "C" int siesta_explore_accurate(siesta_log* log, const int32_t* pattern_a
             if (dm.n_ref_errors) {
                 set_error("siesta_explore_accurate: the reference engine throws on this pattern");
                 rc = SIESTA_E_REFERENCE_THROWS;
+            } else if (dm.n_unsupported) {   // an aggregate over all traces cannot leave some out
+                set_error("siesta_explore_accurate: " + std::to_string(dm.n_unsupported) + " trace(s) exceed the engine limits (siesta_detect lists them)");
+                rc = SIESTA_E_UNSUPPORTED;
             } else if (dm.n_occurrences > 0) {
                 completions[c] += dm.n_occurrences;
                 SIESTA_CUDA_OK(cudaMemsetAsync(d_one, 0, 8, stream));

@@ -121,11 +121,12 @@ struct XDecode {
     int world;
     const char* data[XCHG_MAX_RANKS];   // data areas of all ranks (mine included)
     const XHeader* hdrs;                // [world], device copy
-    int64_t tb[XCHG_MAX_RANKS + 1], ob[XCHG_MAX_RANKS + 1], eb[XCHG_MAX_RANKS + 1], rb[XCHG_MAX_RANKS + 1];  // exclusive prefixes
+    int64_t tb[XCHG_MAX_RANKS + 1], ob[XCHG_MAX_RANKS + 1], eb[XCHG_MAX_RANKS + 1], rb[XCHG_MAX_RANKS + 1], ub[XCHG_MAX_RANKS + 1];  // exclusive prefixes
     int64_t *trace_idx, *occ_off, *ev_off;
     int32_t *pos, *rank, *act;
     int64_t* ts;
     int64_t* err;
+    int64_t* unsup;
 };
 
 // Uniform blocks (one occurrence per trace, K events per occurrence): a CTA takes tiles of TE events of one rank.  The
@@ -198,6 +199,8 @@ __global__ void __launch_bounds__(XD_THREADS) xchg_decode_uniform_kernel(const _
     }
     for (int64_t i = (int64_t)blockIdx.x * XD_THREADS + tid; i < h.n_err; i += (int64_t)gridDim.x * XD_THREADS)
         D.err[D.rb[r] + i] = h.trace_base + __ldcv(reinterpret_cast<const long long*>(data + h.o_err) + i);
+    for (int64_t i = (int64_t)blockIdx.x * XD_THREADS + tid; i < h.n_unsup; i += (int64_t)gridDim.x * XD_THREADS)
+        D.unsup[D.ub[r] + i] = h.trace_base + __ldcv(reinterpret_cast<const long long*>(data + h.o_unsup) + i);
 }
 
 // General blocks (any number of occurrences per trace and of events per occurrence): one thread per trace.
@@ -236,6 +239,8 @@ __global__ void __launch_bounds__(XD_THREADS) xchg_decode_general_kernel(const _
     }
     for (int64_t i = (int64_t)blockIdx.x * XD_THREADS + threadIdx.x; i < h.n_err; i += (int64_t)gridDim.x * XD_THREADS)
         D.err[D.rb[r] + i] = h.trace_base + __ldcv(reinterpret_cast<const long long*>(data + h.o_err) + i);
+    for (int64_t i = (int64_t)blockIdx.x * XD_THREADS + threadIdx.x; i < h.n_unsup; i += (int64_t)gridDim.x * XD_THREADS)
+        D.unsup[D.ub[r] + i] = h.trace_base + __ldcv(reinterpret_cast<const long long*>(data + h.o_unsup) + i);
 }
 
 __global__ void xchg_tail_kernel(int64_t* occ_off, int64_t n_tr, int64_t n_occ, int64_t* ev_off, int64_t n_ev) {
@@ -488,7 +493,8 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
     if (q) detect_pending_discard(q);
 
     int bad = *h_flag ? XST_TIMEOUT : 0;
-    int64_t tb[XCHG_MAX_RANKS + 1] = {0}, ob[XCHG_MAX_RANKS + 1] = {0}, eb[XCHG_MAX_RANKS + 1] = {0}, rb[XCHG_MAX_RANKS + 1] = {0};
+    int64_t tb[XCHG_MAX_RANKS + 1] = {0}, ob[XCHG_MAX_RANKS + 1] = {0}, eb[XCHG_MAX_RANKS + 1] = {0}, rb[XCHG_MAX_RANKS + 1] = {0},
+            ub[XCHG_MAX_RANKS + 1] = {0};
     bool uniform = true, all_cols = !(flags & SIESTA_F_NO_EVENT_COLUMNS);
     int64_t emitted = 0;
     for (int p = 0; p < world; ++p) {
@@ -499,6 +505,7 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
         ob[p + 1] = ob[p] + h.n_occ;
         eb[p + 1] = eb[p] + h.n_ev;
         rb[p + 1] = rb[p] + h.n_err;
+        ub[p + 1] = ub[p] + h.n_unsup;
         uniform = uniform && h.uniform_k > 0;
         emitted += h.n_emitted;
     }
@@ -517,7 +524,7 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
             return SIESTA_E_CUDA;
         }
         if (bad & XST_LIMITS) {
-            set_error("exchange: a trace exceeds the engine limits on some rank (see siesta_detect)");
+            set_error("exchange: too many traces beyond the engine limits on some rank, or its verification failed (see siesta_detect)");
             return SIESTA_E_UNSUPPORTED;
         }
         if (bad & XST_RANGE) {
@@ -528,7 +535,7 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
         set_error("exchange: staging overflow or too many reference errors on some rank");
         return SIESTA_E_NOMEM;
     }
-    const int64_t n_tr = tb[world], n_occ = ob[world], n_ev = eb[world], n_err = rb[world];
+    const int64_t n_tr = tb[world], n_occ = ob[world], n_ev = eb[world], n_err = rb[world], n_unsup = ub[world];
 
     // ---- the joined result: one allocation, the library's standard block layout
     void* fin = nullptr;
@@ -546,6 +553,7 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
         q_act = fcarve((size_t)n_ev * 4);
         q_ts = fcarve((size_t)n_ev * 8);
     }
+    const size_t q_unsup = fcarve((size_t)n_unsup * 8);
     {
         const cudaError_t e = cudaMallocAsync(&fin, f_off ? f_off : 16, stream);
         if (e != cudaSuccess) {
@@ -565,11 +573,13 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
     std::memcpy(D.ob, ob, sizeof(ob));
     std::memcpy(D.eb, eb, sizeof(eb));
     std::memcpy(D.rb, rb, sizeof(rb));
+    std::memcpy(D.ub, ub, sizeof(ub));
     D.trace_idx = reinterpret_cast<int64_t*>(fb + q_trace);
     D.occ_off = reinterpret_cast<int64_t*>(fb + q_occ);
     D.ev_off = reinterpret_cast<int64_t*>(fb + q_evoff);
     D.pos = reinterpret_cast<int32_t*>(fb + q_pos);
     D.err = reinterpret_cast<int64_t*>(fb + q_err);
+    D.unsup = reinterpret_cast<int64_t*>(fb + q_unsup);
     D.rank = all_cols ? reinterpret_cast<int32_t*>(fb + q_rank) : nullptr;
     D.act = all_cols ? reinterpret_cast<int32_t*>(fb + q_act) : nullptr;
     D.ts = all_cols ? reinterpret_cast<int64_t*>(fb + q_ts) : nullptr;
@@ -598,6 +608,13 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
         SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
         std::sort(herr.begin(), herr.end());
         SIESTA_CUDA_OK(cudaMemcpyAsync(D.err, herr.data(), (size_t)n_err * 8, cudaMemcpyHostToDevice, stream));
+    }
+    if (n_unsup > 0) {   // per-rank lists arrive in completion order
+        std::vector<int64_t> hu((size_t)n_unsup);
+        SIESTA_CUDA_OK(cudaMemcpyAsync(hu.data(), D.unsup, (size_t)n_unsup * 8, cudaMemcpyDeviceToHost, stream));
+        SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+        std::sort(hu.begin(), hu.end());
+        SIESTA_CUDA_OK(cudaMemcpyAsync(D.unsup, hu.data(), (size_t)n_unsup * 8, cudaMemcpyHostToDevice, stream));
     }
     SIESTA_CUDA_OK(cudaStreamSynchronize(stream));   // host wait 2 of 2: the joined list is complete on this rank
     float ms_scan = 0.f, ms_wait = 0.f, ms_pull = 0.f;
@@ -628,6 +645,8 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
     out->d_ev_act = D.act;
     out->d_ev_ts_ms = D.ts;
     out->d_err_trace_idx = D.err;
+    out->n_unsupported = n_unsup;
+    out->d_unsupported_trace_idx = D.unsup;
     out->d_block = fin;
     out->block_bytes = (int64_t)f_off;
     out->impl = impl;

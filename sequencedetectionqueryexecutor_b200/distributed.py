@@ -473,6 +473,8 @@ def to_match_result(g, n_matches_emitted=-1):
     r.ev_rank, r.ev_act, r.ev_ts_ms = h.get("ev_rank"), h.get("ev_act"), h.get("ev_ts_ms")
     r.n_traces, r.n_occurrences, r.n_events = len(r.trace_idx), len(r.ev_off) - 1, int(r.ev_off[-1])
     r.n_ref_errors, r.n_matches_emitted, r.kernel_ms, r.detect_ms = len(r.err_trace_idx), n_matches_emitted, 0.0, 0.0
+    r.unsupported_trace_idx = h.get("unsupported_trace_idx", np.zeros(0, dtype=np.int64))
+    r.n_unsupported = len(r.unsupported_trace_idx)
     return r
 
 

@@ -31,6 +31,11 @@ def _check(ctx, off, act, ts, n_act, states, flags, cand=None):
     finally:
         log.close()
     want = oracle.detect(off, act, ts, nfa, cand=cand, flags=flags)
+    if got.n_unsupported:   # traces beyond the engine's per-trace limits are listed, every other trace is exact
+        out = set(got.unsupported_trace_idx.tolist())
+        assert got.as_dict() == {t: o for t, o in want.as_dict().items() if t not in out}, f"states={states} flags={flags}"
+        assert [t for t in got.err_trace_idx.tolist()] == [t for t in want.err_trace_idx.tolist() if t not in out]
+        return got
     ok, why = got.same_as(want)
     assert ok, f"mismatch in {why}: states={states} flags={flags}"
     return got
@@ -132,13 +137,32 @@ def test_wide_engine_path(ctx):
 
 
 def test_limits_are_reported_not_silently_wrong(ctx):
+    """A trace beyond the engine's per-trace limits does not fail the request (the reference has no limit,
+    Engine.java:207-224): every other trace is answered exactly and the outliers are listed."""
     from sequencedetectionqueryexecutor_b200._lib import SiestaError
-    off, act, ts = gen.make_log(4, 200, 200, 2, seed=5)  # ~100 relevant events per trace > 64
-    log = ctx.load_log(off, act, ts, 2)
-    with pytest.raises(SiestaError) as e:
-        log.detect(abi.make_nfa([dict(kind=N_, types=[0]), dict(kind=N_, types=[1])]))
-    log.close()
-    assert e.value.code == abi.E_UNSUPPORTED
+    off, act, ts = gen.make_log(300, 0, 40, 2, seed=5)
+    long_off, long_act, long_ts = gen.make_log(3, 200, 200, 2, seed=6)          # ~200 relevant events per trace > 64
+    # the three long traces go to positions 17, 18 and the very end
+    cut = int(off[17])
+    act2 = np.concatenate([act[:cut], long_act[:400], act[cut:], long_act[400:]])
+    ts2 = np.concatenate([ts[:cut], long_ts[:400], ts[cut:], long_ts[400:]])
+    lens = np.concatenate([np.diff(off)[:17], [200, 200], np.diff(off)[17:], [200]])
+    off2 = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    outliers = [17, 18, len(lens) - 1]
+    for states, flags in (([dict(kind=N_, types=[0]), dict(kind=N_, types=[1])], 0),
+                          ([dict(kind=P_, types=[0]), dict(kind=S_, types=[1])], 0),
+                          ([dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[0])], abi.F_RETURN_ALL)):
+        nfa = abi.make_nfa(states)
+        log = ctx.load_log(off2, act2, ts2, 2)
+        got = log.detect(nfa, flags=flags)
+        log.close()
+        assert got.unsupported_trace_idx.tolist() == outliers and got.n_unsupported == 3
+        want = oracle.detect(off2, act2, ts2, nfa, flags=flags)
+        keep = ~np.isin(want.trace_idx, outliers)
+        assert np.array_equal(got.trace_idx, want.trace_idx[keep])
+        # the occurrences of the supported traces, one by one
+        wd = want.as_dict()
+        assert got.as_dict() == {t: o for t, o in wd.items() if t not in outliers}
     log = ctx.load_log(*gen.make_log(4, 5, 5, 2, seed=5), 2)
     with pytest.raises(SiestaError) as e:  # HEAD mode has no defined output when state 1 is kleeneClosure*
         log.detect(abi.make_nfa([dict(kind=N_, types=[0]), dict(kind=S_, types=[1])]), flags=abi.F_MODE_HEAD)
@@ -388,7 +412,8 @@ def test_compact_wire_format_round_trip(ctx):
             got = D.unpack_block(block, header)
             torch.cuda.synchronize()
             for k, v in want.items():
-                assert torch.equal(got[k], v), (k, states, flags)
+                if k != "unsupported_trace_idx":   # (not part of this older wire format; siesta_detect_allgather ships it)
+                    assert torch.equal(got[k], v), (k, states, flags)
             dm.close()
     finally:
         log.close()

@@ -105,15 +105,22 @@ def test_sharded_allgather_equals_unsharded_oracle(name, states, flags, shape):
 
 
 def test_long_and_unaligned_traces_cross_shards():
-    """Traces that leave K1-P for the staged kernels (more than 64 slots / 32 relevant events) inside a shard."""
+    """Traces that leave K1-P for the staged kernels (more than 64 slots / 32 relevant events) inside a shard, and traces
+    beyond the engine limits (more than 64 relevant events): listed on every rank, all others exact."""
     from sequencedetectionqueryexecutor_b200 import api
-    off, act, ts = gen.make_log(1200, 0, 130, 9, seed=77, max_gap_s=50)
     nfa = abi.make_nfa([dict(kind=N_, types=[0]), dict(kind=X_, types=[1]), dict(kind=N_, types=[2], preds=[(abi.ATTR_POSITION, abi.OP_GE, 0, 3)])])
-    want = oracle.detect(off, act, ts, nfa, flags=0)
-    with api.Context(0) as ctx:
-        for got, _ in _run_sharded(ctx, off, act, ts, 9, nfa, 0, [0, 333, 800, 1200]):
-            ok, why = got.same_as(want)
-            assert ok, why
+    for n_act in (9, 4):
+        off, act, ts = gen.make_log(1200, 0, 130, n_act, seed=77, max_gap_s=50)
+        want = oracle.detect(off, act, ts, nfa, flags=0)
+        rel = np.add.reduceat(np.concatenate([(act < 3).astype(np.int64), [0]]), off[:-1]) * (np.diff(off) > 0)
+        outliers = np.flatnonzero(rel > 64)
+        assert (len(outliers) > 0) == (n_act == 4)
+        keep = ~np.isin(want.trace_idx, outliers)
+        with api.Context(0) as ctx:
+            for got, _ in _run_sharded(ctx, off, act, ts, n_act, nfa, 0, [0, 333, 800, 1200]):
+                assert got.unsupported_trace_idx.tolist() == outliers.tolist()
+                assert np.array_equal(got.trace_idx, want.trace_idx[keep])
+                assert got.as_dict() == {t: o for t, o in want.as_dict().items() if t not in set(outliers.tolist())}
 
 
 def test_allreduce_of_counts_over_peer_regions():
