@@ -287,6 +287,19 @@ __global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4)
             acc_match += n_match;
         }
         const unsigned tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
+        if (P.work == nullptr) {          // a tile of 32 consecutive candidates: one reduction per tile
+            if (lane == 31 && n_match) {
+                unsigned long long* b = P.blk_sums + (tile >> 3);
+                atomicAdd(b, (unsigned long long)n_match);
+                atomicAdd(b + P.n_blk, (unsigned long long)i0);
+                atomicAdd(b + 2 * P.n_blk, (unsigned long long)i1);
+            }
+        } else if (status == ST_MATCH) {  // a re-run list: the candidates come from anywhere
+            unsigned long long* b = P.blk_sums + (ci >> 8);
+            atomicAdd(b, 1ull);
+            atomicAdd(b + P.n_blk, (unsigned long long)my_occ);
+            atomicAdd(b + 2 * P.n_blk, (unsigned long long)my_ev);
+        }
         base0 = __shfl_sync(0xffffffffu, base0, 31);
         base1 = __shfl_sync(0xffffffffu, base1, 31);
         const long long occ_at = return_all ? (long long)(base0 + i0 - my_occ) : (long long)ci;
@@ -666,6 +679,9 @@ int launch_detect(const Ctx* ctx, cudaStream_t stream, DetectParams P, const Dev
         if (v >= 1 && v < per_sm) per_sm = v;
     }
     int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)ctx->sm_count * per_sm);
+    // a re-run launch (work count on the device: the traces the previous kernel could not hold) usually finds nothing to do;
+    // two CTAs per SM start and end in a few microseconds and still take any list through the tile counter
+    if (P.n_work_dev) grid = std::min(grid, ctx->sm_count * 2);
     if (grid < 1) grid = 1;
     kern<<<grid, nt, smem, stream>>>(P, nfa);
     SIESTA_LAUNCHED();
@@ -812,6 +828,7 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
     } begin_guard{ev0, evd, h_cnt, log->ctx, true};
     SIESTA_CUDA_OK(cudaMemcpyAsync(b_lut.p, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
     SIESTA_CUDA_OK(cudaMemsetAsync(b_counters.p, 0, 256, stream));
+    SIESTA_CUDA_OK(cudaMemsetAsync(b_blk.p, 0, n_blk * 3 * 8, stream));
     SIESTA_CUDA_OK(cudaEventRecord(ev0, stream));
 
     DetectParams P;
@@ -864,6 +881,8 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
     P.counters = b_counters.as<unsigned long long>();
     P.err_list = b_err.as<int64_t>();
     P.ovf_list = b_ovf.as<int64_t>();
+    P.blk_sums = b_blk.as<unsigned long long>();
+    P.n_blk = (int64_t)n_blk;
 
     P.ovf_slot = 4;
     P.tile_slot = 16;   // the tile counters live on their own 128-byte line (slots 16..)
@@ -1057,8 +1076,7 @@ int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out) {
         G.ev_act = f_act.as<int32_t>();
         G.ev_ts = f_ts.as<int64_t>();
         G.all_cols = all_cols ? 1 : 0;
-        count_blocks_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G);
-        SIESTA_LAUNCHED();
+        // (the block sums were accumulated by the verification kernels: no counting pass)
         scan_chunks_kernel<<<(unsigned)G.n_chunks, SC, 0, stream>>>(G.blk, G.n_blk, G.top, G.n_chunks);
         SIESTA_LAUNCHED();
         scan_top_kernel<<<1, SC, 0, stream>>>(G.top, G.n_chunks);
@@ -1381,8 +1399,6 @@ int detect_device_pack_impl(DetectPending* q, const PackTarget& tgt) {
         G.s_ev_act = P.s_ev_act;
         G.s_ev_ts = P.s_ev_ts;
         G.all_cols = all_cols ? 1 : 0;
-        count_blocks_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G);
-        SIESTA_LAUNCHED();
         scan_chunks_kernel<<<(unsigned)G.n_chunks, SC, 0, stream>>>(G.blk, G.n_blk, G.top, G.n_chunks);
         SIESTA_LAUNCHED();
         scan_top_kernel<<<1, SC, 0, stream>>>(G.top, G.n_chunks);

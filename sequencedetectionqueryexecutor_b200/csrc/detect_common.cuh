@@ -61,6 +61,10 @@ struct DetectParams {
     // 7 wide overflow, 8-10 phase timing, 13 K1-P overflow; second 128-byte line: 16 / 17 / 18 next tile of the narrow /
     // wide / K1-P launch
     unsigned long long* counters;
+    // [3][n_blk] matching traces / occurrences / events per block of 256 candidates, accumulated by the verification
+    // kernels themselves (one reduction per tile), so the placement needs no counting pass over the candidates
+    unsigned long long* blk_sums;
+    int64_t n_blk;
     int64_t* err_list;
     int64_t* ovf_list;
     int64_t ovf_cap;          // entries ovf_list holds (0 = one per candidate); the counter keeps counting past it

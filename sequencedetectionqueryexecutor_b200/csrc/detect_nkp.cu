@@ -240,10 +240,17 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
                 if (lane >= d) i2 += y2;
             }
         }
-        acc_occ += __popc(__ballot_sync(0xffffffffu, status == ST_MATCH));
+        const unsigned n_match = __popc(__ballot_sync(0xffffffffu, status == ST_MATCH));
+        acc_occ += n_match;
         acc_ev += i1;     // lane 31 holds the tile totals
         acc_emit += i2;
         const unsigned tot1 = __shfl_sync(0xffffffffu, i1, 31);
+        if (lane == 31 && n_match) {   // the tile's share of its block of 256 candidates (8 tiles); one occurrence per match
+            unsigned long long* b = P.blk_sums + (tile >> 3);
+            atomicAdd(b, (unsigned long long)n_match);
+            atomicAdd(b + P.n_blk, (unsigned long long)n_match);
+            atomicAdd(b + 2 * P.n_blk, (unsigned long long)i1);
+        }
         const long long base1 = P.fix_ev + tile * 32 * P.fix_np;
         if (ci >= 0) {
             P.d_cnt[ci] = my_occ | (my_ev << 16);

@@ -118,7 +118,7 @@ __global__ void xchg_ack_kernel(const __grid_constant__ XPeers peers, int world,
 
 // ------------------------------------------------------------------------------------------------ pull + decode
 struct XDecode {
-    int world;
+    int world, me;   // grid row y handles source rank (me + y) % world: at any moment the ranks read from different peers
     const char* data[XCHG_MAX_RANKS];   // data areas of all ranks (mine included)
     const XHeader* hdrs;                // [world], device copy
     int64_t tb[XCHG_MAX_RANKS + 1], ob[XCHG_MAX_RANKS + 1], eb[XCHG_MAX_RANKS + 1], rb[XCHG_MAX_RANKS + 1], ub[XCHG_MAX_RANKS + 1];  // exclusive prefixes
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(XD_THREADS) xchg_decode_uniform_kernel(const _
     __shared__ __align__(16) uint16_t s_act[XD_TE];
     __shared__ __align__(16) int32_t s_delta[XD_TE];
     __shared__ long long s_base[XD_TE + 1];
-    const int r = blockIdx.y;
+    const int r = (int)((blockIdx.y + D.me) % D.world);
     const XHeader h = D.hdrs[r];
     if (h.status) return;
     const int K = h.uniform_k;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(XD_THREADS) xchg_decode_uniform_kernel(const _
 
 // General blocks (any number of occurrences per trace and of events per occurrence): one thread per trace.
 __global__ void __launch_bounds__(XD_THREADS) xchg_decode_general_kernel(const __grid_constant__ XDecode D) {
-    const int r = blockIdx.y;
+    const int r = (int)((blockIdx.y + D.me) % D.world);
     const XHeader h = D.hdrs[r];
     if (h.status) return;
     const char* data = D.data[r];
@@ -567,6 +567,7 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
     XDecode D;
     std::memset(&D, 0, sizeof(D));
     D.world = world;
+    D.me = rank;
     for (int p = 0; p < world; ++p) D.data[p] = x->peers.region[p] + XCHG_CTRL_BYTES;
     D.hdrs = x->d_hdrs;
     std::memcpy(D.tb, tb, sizeof(tb));
