@@ -139,6 +139,8 @@ class ClockSampler:
         self.marks = [0, None]
 
     def start(self):
+        if os.environ.get("SIESTA_BENCH_NO_SAMPLER"):   # diagnosis only: is a hiccup the sampler's?
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -164,12 +166,15 @@ class ClockSampler:
         nv = self.nv
         R = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
              "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        pw, k = 0.0, 0
         while not self.stop_flag.is_set():
             try:
                 sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
                 bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.samples.append((sm, self.max_sm, pw, {k for k, v in R.items() if bits & v}))
+                if k % 8 == 0 and not os.environ.get("SIESTA_BENCH_NO_POWER"):   # the power read goes to the board's controller: slower, rarer
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                k += 1
+                self.samples.append((sm, self.max_sm, pw, {k2 for k2, v in R.items() if bits & v}))
             except Exception:
                 pass
             self.stop_flag.wait(0.02)
@@ -407,6 +412,8 @@ def main():
         x_ms.append(r[7])
     barrier()
     wall = time.perf_counter() - t0
+    if os.environ.get("SIESTA_BENCH_DEBUG"):
+        print(f"[rank {rank}] step ms: {[round(x, 2) for x in lat_ms]} exchange ms: {[round(x, 2) for x in x_ms]}", file=sys.stderr, flush=True)
     launches = api.kernel_launches() - launches0
     clocks = sampler.stop()
     assert r[:4] == r0[:4], "result changed between steps"
@@ -509,7 +516,7 @@ def main():
             "e2e": e2e,
             # one /detection request on the resident shard(s): wall time of the call on rank 0, result sizes back on the host
             "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
-                           "min": float(lat.min()), "max": float(lat.max())},
+                           "min": float(lat.min()), "max": float(lat.max()), "steps": [round(float(x), 3) for x in lat]},
             "p50_latency_ms": float(np.percentile(lat, 50)),
             "exchange": ({"ms": float(np.mean(x_ms)), "scan_and_place_ms": r[8], "wait_for_slowest_rank_ms": r[9],
                           "host_sizes_and_alloc_ms": r[12], "pull_and_decode_ms": r[10], "pulled_bytes_per_rank": r[11],

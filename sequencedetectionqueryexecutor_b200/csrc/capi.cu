@@ -60,10 +60,65 @@ extern "C" int siesta_init(int32_t device_id, siesta_ctx** out) {
     return SIESTA_OK;
 }
 
+namespace siesta {
+void* dev_arena_alloc(Ctx* c, size_t bytes) {
+    if (bytes < 256) bytes = 256;
+    {
+        std::lock_guard<std::mutex> g(c->arena_mu);
+        DevBlock* best = nullptr;
+        for (DevBlock& b : c->dev_arena)
+            if (!b.used && b.size >= bytes && b.size <= 2 * bytes + (64u << 20) && (!best || b.size < best->size)) best = &b;
+        if (best) {
+            best->used = true;
+            return best->p;
+        }
+    }
+    const size_t want = ((bytes + bytes / 8) + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);   // slack: the next request may be a little larger
+    void* p = nullptr;
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {   // give the unused blocks back to the driver and try once more
+        cudaGetLastError();
+        std::vector<void*> drop;
+        {
+            std::lock_guard<std::mutex> g(c->arena_mu);
+            for (size_t i = 0; i < c->dev_arena.size();) {
+                if (!c->dev_arena[i].used) {
+                    drop.push_back(c->dev_arena[i].p);
+                    c->dev_arena.erase(c->dev_arena.begin() + (long)i);
+                } else ++i;
+            }
+        }
+        for (void* q : drop) cudaFree(q);
+        e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error(std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> g(c->arena_mu);
+    c->dev_arena.push_back(DevBlock{p, want, true});
+    return p;
+}
+
+void dev_arena_free(Ctx* c, void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(c->arena_mu);
+    for (DevBlock& b : c->dev_arena)
+        if (b.p == p) {
+            b.used = false;
+            return;
+        }
+}
+}  // namespace siesta
+
 extern "C" void siesta_shutdown(siesta_ctx* ctx) {
     if (!ctx) return;
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (DevBlock& b : c->dev_arena) cudaFree(b.p);   // results must have been freed before the ctx
     if (c->stream) cudaStreamDestroy(c->stream);
     for (HostBlock& b : c->arena) cudaFreeHost(b.p);  // result objects must have been freed before the ctx
     for (void* p : c->pinned_slabs) cudaFreeHost(p);

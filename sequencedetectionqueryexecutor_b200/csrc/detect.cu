@@ -619,23 +619,17 @@ __global__ void set_tail_kernel(int64_t* occ_off, int64_t n_tr, int64_t n_occ, i
 // ---------------------------------------------------------------------------------- host side
 namespace {
 
-// Stream-ordered allocations from the device's default pool (kept warm: siesta_init raises the release
-// threshold), so a request costs no cudaMalloc/cudaFree round trips after the first one.
+// A block of the context's device arena (common.cuh): scratch and results of a request, returned when the request is done.
 struct DevBuf {
     void* p = nullptr;
-    cudaStream_t s = nullptr;
-    explicit DevBuf(cudaStream_t stream) : s(stream) {}
+    Ctx* c = nullptr;
+    explicit DevBuf(Ctx* ctx) : c(ctx) {}
     DevBuf(const DevBuf&) = delete;
-    ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+    ~DevBuf() { if (p) dev_arena_free(c, p); }
     int alloc(size_t bytes) {
-        if (p) { cudaFreeAsync(p, s); p = nullptr; }
-        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, s);
-        if (e != cudaSuccess) {
-            set_error(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
-            p = nullptr;
-            return SIESTA_E_NOMEM;
-        }
-        return SIESTA_OK;
+        if (p) { dev_arena_free(c, p); p = nullptr; }
+        p = dev_arena_alloc(c, bytes);
+        return p ? SIESTA_OK : SIESTA_E_NOMEM;
     }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
     void* release() { void* q = p; p = nullptr; return q; }
@@ -645,12 +639,6 @@ struct DevBuf {
 struct View {
     void* p;
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-struct DevMatchesImpl {
-    void* bufs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaStream_t free_stream = nullptr;
-    int device = 0;
 };
 
 template <int W, int R, int NF, bool SMEM_RUNS, int MODE>
@@ -734,7 +722,7 @@ static void pinned_counters_put(Ctx* c, unsigned long long* p) {
 
 static void pending_discard(DetectPending* q) {
     if (!q) return;
-    if (q->work) cudaFreeAsync(q->work, q->stream);
+    if (q->work) dev_arena_free(q->log->ctx, q->work);   // (every caller has waited for the request's stream)
     if (q->ev0) cudaEventDestroy(q->ev0);
     if (q->evd) cudaEventDestroy(q->evd);
     pinned_counters_put(q->log->ctx, q->h_cnt);
@@ -768,7 +756,7 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
     const int64_t cap_ev = (!return_all && !dn.any_kleene) ? n * std::max(1, n_positive) : wide;
 
     // one stream-ordered allocation for all scratch of the call, carved by a bump pointer
-    DevBuf work(stream);
+    DevBuf work(log->ctx);
     const size_t nn = (size_t)std::max<int64_t>(n, 1);
     size_t w_off = 0;
     auto carve = [&w_off](size_t bytes) {
@@ -1028,7 +1016,7 @@ int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out) {
     const int64_t n_unsup = n > 0 ? (int64_t)h_cnt[7] : 0;
 
     // the result columns: one allocation, owned by the returned object
-    DevBuf fin(stream);
+    DevBuf fin(log->ctx);
     size_t f_off = 0;
     auto fcarve = [&f_off](size_t bytes) {
         const size_t at = f_off;
@@ -1126,8 +1114,7 @@ int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out) {
     out->n_ref_errors = n_err;
     out->kernel_ms = ms;
     out->detect_ms = dms;
-    impl->free_stream = ctx->stream;
-    impl->device = ctx->device;
+    impl->owner = log->ctx;
     out->d_trace_idx = f_trace.as<int64_t>();
     out->d_occ_off = f_occ_off.as<int64_t>();
     out->d_ev_off = f_ev_off.as<int64_t>();
@@ -1139,7 +1126,7 @@ int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out) {
     out->n_unsupported = n_unsup;
     out->d_unsupported_trace_idx = f_unsup.as<int64_t>();
     out->block_bytes = (int64_t)f_off;
-    impl->bufs[0] = out->d_block = fin.release();
+    impl->block = out->d_block = fin.release();
     out->impl = impl;
     return SIESTA_OK;
 }
@@ -1457,9 +1444,7 @@ extern "C" int siesta_detect_device(siesta_log* log, const siesta_nfa* nfa, cons
 extern "C" void siesta_dev_matches_free(siesta_dev_matches* m) {
     if (!m || !m->impl) return;
     siesta::DevMatchesImpl* impl = reinterpret_cast<siesta::DevMatchesImpl*>(m->impl);
-    cudaSetDevice(impl->device);
-    for (void* p : impl->bufs)
-        if (p) cudaFreeAsync(p, impl->free_stream);
+    siesta::dev_arena_free(impl->owner, impl->block);   // the caller is done with the result: its block serves the next request
     delete impl;
     m->impl = nullptr;
 }

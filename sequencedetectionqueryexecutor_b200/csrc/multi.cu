@@ -260,12 +260,6 @@ __global__ void xchg_reduce_kernel(const __grid_constant__ XPeers peers, int wor
     }
 }
 
-struct DevMatchesImplX {   // layout-compatible with detect.cu's DevMatchesImpl (siesta_dev_matches_free releases it)
-    void* bufs[8];
-    cudaStream_t free_stream;
-    int device;
-};
-
 static int check_ready(Exchange* x, const char* who) {
     if (!x) {
         set_error(std::string(who) + ": null exchange");
@@ -554,15 +548,19 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
         q_ts = fcarve((size_t)n_ev * 8);
     }
     const size_t q_unsup = fcarve((size_t)n_unsup * 8);
-    {
-        const cudaError_t e = cudaMallocAsync(&fin, f_off ? f_off : 16, stream);
-        if (e != cudaSuccess) {
-            set_error(std::string("exchange: cudaMalloc(joined result, ") + std::to_string(f_off) + "): " + cudaGetErrorString(e));
-            xchg_ack_kernel<<<1, 32, 0, stream>>>(x->peers, world, rank, seq);
-            cudaStreamSynchronize(stream);
-            return SIESTA_E_NOMEM;
-        }
+    fin = dev_arena_alloc(x->ctx, f_off);
+    if (!fin) {
+        xchg_ack_kernel<<<1, 32, 0, stream>>>(x->peers, world, rank, seq);
+        cudaStreamSynchronize(stream);
+        return SIESTA_E_NOMEM;
     }
+    struct FinGuard {   // an error return below gives the block back
+        Ctx* c;
+        void*& p;
+        ~FinGuard() { if (p) dev_arena_free(c, p); }
+    };
+    void* fin_owned = fin;
+    FinGuard fin_guard{x->ctx, fin_owned};
     char* fb = reinterpret_cast<char*>(fin);
     XDecode D;
     std::memset(&D, 0, sizeof(D));
@@ -625,11 +623,10 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
     float ms_gap = 0.f;   // the device idles while the host reads the sizes and allocates the joined result
     cudaEventElapsedTime(&ms_gap, ev[2], ev[4]);
 
-    DevMatchesImplX* impl = new DevMatchesImplX();
-    std::memset(impl, 0, sizeof(*impl));
-    impl->bufs[0] = fin;
-    impl->free_stream = x->stream;   // freed on the stream it was allocated on: the pool hands the block to the next request at once
-    impl->device = x->ctx->device;
+    DevMatchesImpl* impl = new DevMatchesImpl();
+    impl->block = fin;
+    impl->owner = x->ctx;
+    fin_owned = nullptr;   // the result owns the block now
     out->n_traces = n_tr;
     out->n_occurrences = n_occ;
     out->n_events = n_ev;
