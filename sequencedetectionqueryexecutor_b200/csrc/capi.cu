@@ -155,6 +155,44 @@ int validate_act_range(Log* L, int64_t first_event, int64_t n_events, cudaStream
 }
 }  // namespace siesta
 
+// A wrapped CSR lives in memory the caller filled: offsets must start at 0, never decrease and end at n_events, or every
+// kernel would read out of bounds.  One pass over trace_off on the device.
+__global__ void csr_check_kernel(const int64_t* off, int64_t n_traces, int64_t n_events, int* bad) {
+    int any = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_traces; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = off[i];
+        if (v < 0 || v > n_events) any = 1;
+        if (i == 0 && v != 0) any = 1;
+        if (i == n_traces && v != n_events) any = 1;
+        if (i < n_traces && off[i + 1] < v) any = 1;
+    }
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(bad, 1);
+}
+
+static int validate_device_csr(Log* L) {
+    Ctx* c = L->ctx;
+    int* d_bad = nullptr;
+    SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_bad, sizeof(int), c->stream));
+    struct Free {
+        int* p;
+        cudaStream_t s;
+        ~Free() { cudaFreeAsync(p, s); }
+    } guard{d_bad, c->stream};
+    SIESTA_CUDA_OK(cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream));
+    const int64_t want = (L->n_traces + 1 + 255) / 256;
+    const int grid = (int)(want < (int64_t)c->sm_count * 16 ? want : (int64_t)c->sm_count * 16);
+    csr_check_kernel<<<grid, 256, 0, c->stream>>>(L->d_trace_off, L->n_traces, L->n_events, d_bad);
+    SIESTA_LAUNCHED();
+    int bad = 1;
+    SIESTA_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SIESTA_CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (bad) {
+        set_error("siesta_log_wrap_device: trace_off must start at 0, be non-decreasing and end at n_events");
+        return SIESTA_E_INVALID;
+    }
+    return SIESTA_OK;
+}
+
 static int validate_act(Log* L) {
     L->act_valid = true;
     return validate_act_range(L, 0, L->n_events, L->ctx->stream);
@@ -211,12 +249,15 @@ extern "C" int siesta_log_load(siesta_ctx* ctx, const int64_t* trace_off, const 
     L->d_trace_off = (const int64_t*)d_off;
     L->d_act = (const int32_t*)d_act;
     L->d_ts_ms = (const int64_t*)d_ts;
-    SIESTA_CUDA_OK(cudaMemcpyAsync(d_off, trace_off, (size_t)(n_traces + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    if (n_events) {
-        SIESTA_CUDA_OK(cudaMemcpyAsync(d_act, act, (size_t)n_events * 4, cudaMemcpyHostToDevice, c->stream));
-        SIESTA_CUDA_OK(cudaMemcpyAsync(d_ts, ts_ms, (size_t)n_events * 8, cudaMemcpyHostToDevice, c->stream));
+    e = cudaMemcpyAsync(d_off, trace_off, (size_t)(n_traces + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && n_events) e = cudaMemcpyAsync(d_act, act, (size_t)n_events * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && n_events) e = cudaMemcpyAsync(d_ts, ts_ms, (size_t)n_events * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        set_error(std::string("siesta_log_load: host -> device copy: ") + cudaGetErrorString(e));
+        siesta_log_free(reinterpret_cast<siesta_log*>(L));   // owns its three allocations
+        return SIESTA_E_CUDA;
     }
-    SIESTA_CUDA_OK(cudaStreamSynchronize(c->stream));
     if ((rc = validate_act(L))) {
         siesta_log_free(reinterpret_cast<siesta_log*>(L));
         return rc;
@@ -228,8 +269,8 @@ extern "C" int siesta_log_load(siesta_ctx* ctx, const int64_t* trace_off, const 
 extern "C" int siesta_log_wrap_device(siesta_ctx* ctx, const int64_t* d_trace_off, const int32_t* d_act,
                                       const int64_t* d_ts_ms, int64_t n_traces, int64_t n_events, int32_t n_activities,
                                       int32_t max_trace_len, siesta_log** out) {
-    if (!ctx || !d_trace_off || !out || n_traces < 0 || n_events < 0) {
-        set_error("siesta_log_wrap_device: bad argument");
+    if (!ctx || !d_trace_off || !out || n_traces < 0 || n_events < 0 || n_activities < 0 || (n_events > 0 && (!d_act || !d_ts_ms))) {
+        set_error("siesta_log_wrap_device: bad argument (null column with n_events > 0?)");
         return SIESTA_E_INVALID;
     }
     Log* L = new Log();
@@ -242,8 +283,9 @@ extern "C" int siesta_log_wrap_device(siesta_ctx* ctx, const int64_t* d_trace_of
     L->n_activities = n_activities;
     L->max_trace_len = max_trace_len;
     L->owns = false;
-    SIESTA_CUDA_OK(cudaSetDevice(L->ctx->device));
-    int rc = validate_act(L);
+    int rc = cudaSetDevice(L->ctx->device) == cudaSuccess ? SIESTA_OK : SIESTA_E_CUDA;
+    if (rc == SIESTA_OK) rc = validate_device_csr(L);
+    if (rc == SIESTA_OK) rc = validate_act(L);
     if (rc) {
         delete L;
         return rc;
@@ -538,7 +580,11 @@ extern "C" int siesta_evaluate_events(siesta_ctx* ctx, const int64_t* trace_off,
 
     cudaStream_t s_copy = nullptr, s_run = nullptr;
     SIESTA_CUDA_OK(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-    SIESTA_CUDA_OK(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking));
+    if (cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamDestroy(s_copy);
+        set_error("siesta_evaluate_events: cudaStreamCreate");
+        return SIESTA_E_CUDA;
+    }
     int64_t* d_off = nullptr;
     int32_t* d_act = nullptr;
     int64_t* d_ts = nullptr;

@@ -366,6 +366,26 @@ extern "C" int siesta_index_get_list(const siesta_index* index, int32_t pair, in
 }
 
 // result stays on the device (ascending trace indices); free with siesta_device_free
+namespace {
+// events and stream-ordered scratch of one call, released on every return path
+struct CallScratch {
+    cudaStream_t s;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::vector<void*> bufs;
+    explicit CallScratch(cudaStream_t stream) : s(stream) {}
+    ~CallScratch() {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        for (void* p : bufs) cudaFreeAsync(p, s);
+    }
+    cudaError_t alloc(void** p, size_t bytes) {
+        const cudaError_t e = cudaMallocAsync(p, bytes, s);
+        if (e == cudaSuccess) bufs.push_back(*p);
+        return e;
+    }
+};
+}  // namespace
+
 extern "C" int siesta_intersect_device(siesta_index* index, const int32_t* pair_ids, int32_t n, int64_t** d_out, int64_t* out_n,
                                        double* kernel_ms) {
     Index* ix = reinterpret_cast<Index*>(index);
@@ -387,12 +407,14 @@ extern "C" int siesta_intersect_device(siesta_index* index, const int32_t* pair_
     const int nd = (int)ids.size();
     const int64_t T = ix->log->n_traces;
     const size_t hit_bytes = (size_t)((std::max<int64_t>(T, 1) + 3) / 4) * 4;
-    cudaEvent_t e0, e1;
+    CallScratch cs(stream);
+    cudaEvent_t& e0 = cs.e0;
+    cudaEvent_t& e1 = cs.e1;
     SIESTA_CUDA_OK(cudaEventCreate(&e0));
     SIESTA_CUDA_OK(cudaEventCreate(&e1));
     SIESTA_CUDA_OK(cudaEventRecord(e0, stream));
     uint32_t* d_hit = nullptr;
-    SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_hit, hit_bytes, stream));
+    SIESTA_CUDA_OK(cs.alloc((void**)&d_hit, hit_bytes));
     SIESTA_CUDA_OK(cudaMemsetAsync(d_hit, 0, hit_bytes, stream));
     int rc = count_list_hits(ix, ids.data(), nd, d_hit, stream);
     std::vector<int64_t> counts, row_off;
@@ -401,9 +423,6 @@ extern "C" int siesta_intersect_device(siesta_index* index, const int32_t* pair_
     SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFreeAsync(d_hit, stream);
     if (rc) return rc;
     *out_n = counts[0];
     if (kernel_ms) *kernel_ms = ms;
@@ -433,16 +452,18 @@ extern "C" int siesta_candidates_device(siesta_index* index, const int32_t* exp_
     SIESTA_CUDA_OK(cudaSetDevice(ix->log->ctx->device));
     cudaStream_t stream = ix->log->ctx->stream;
     const int64_t T = ix->log->n_traces;
-    cudaEvent_t e0, e1;
+    CallScratch cs(stream);
+    cudaEvent_t& e0 = cs.e0;
+    cudaEvent_t& e1 = cs.e1;
     SIESTA_CUDA_OK(cudaEventCreate(&e0));
     SIESTA_CUDA_OK(cudaEventCreate(&e1));
     SIESTA_CUDA_OK(cudaEventRecord(e0, stream));
     uint8_t* d_mark = nullptr;
     uint32_t* d_hit = nullptr;
     const size_t hit_bytes = (size_t)((std::max<int64_t>(T, 1) + 3) / 4) * 4;
-    SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_mark, (size_t)std::max<int64_t>(T, 1), stream));
+    SIESTA_CUDA_OK(cs.alloc((void**)&d_mark, (size_t)std::max<int64_t>(T, 1)));
     SIESTA_CUDA_OK(cudaMemsetAsync(d_mark, 0, (size_t)std::max<int64_t>(T, 1), stream));
-    SIESTA_CUDA_OK(cudaMallocAsync((void**)&d_hit, hit_bytes, stream));
+    SIESTA_CUDA_OK(cs.alloc((void**)&d_hit, hit_bytes));
     SIESTA_CUDA_OK(cudaMemsetAsync(d_hit, 0, hit_bytes, stream));
     for (int x = 0; x < n_exp; ++x) {
         std::vector<int32_t> ids(pair_ids + exp_off[x], pair_ids + exp_off[x + 1]);
@@ -462,10 +483,6 @@ extern "C" int siesta_candidates_device(siesta_index* index, const int32_t* exp_
     SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFreeAsync(d_mark, stream);
-    cudaFreeAsync(d_hit, stream);
     if (rc) return rc;
     *out_n = counts[0];
     if (kernel_ms) *kernel_ms = ms;

@@ -524,3 +524,23 @@ def test_begin_finish_requests_in_flight(ctx):
         b.close()
     finally:
         log.close()
+
+
+def test_wrapped_device_logs_are_validated(ctx):
+    """siesta_log_wrap_device checks the caller's CSR on the device: offsets that decrease, do not start at 0 or do not end at
+    n_events, and null columns, are refused instead of becoming out-of-bounds reads in every kernel."""
+    import torch
+
+    from sequencedetectionqueryexecutor_b200._lib import SiestaError
+    off, act, ts = gen.make_log(50, 1, 9, 4, seed=1)
+    d_act, d_ts = torch.from_numpy(act).cuda(), torch.from_numpy(ts).cuda()
+    good = ctx.wrap_log(torch.from_numpy(off).cuda(), d_act, d_ts, 4)
+    assert good.n_traces == 50
+    good.close()
+    for mutate in (lambda o: o.__setitem__(0, 1), lambda o: o.__setitem__(-1, o[-1] - 1), lambda o: o.__setitem__(10, o[12] + 1),
+                   lambda o: o.__setitem__(5, -3)):
+        bad = off.copy()
+        mutate(bad)
+        with pytest.raises(SiestaError) as e:
+            ctx.wrap_log(torch.from_numpy(bad).cuda(), d_act, d_ts, 4)
+        assert e.value.code == abi.E_INVALID
