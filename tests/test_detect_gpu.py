@@ -544,3 +544,22 @@ def test_wrapped_device_logs_are_validated(ctx):
         with pytest.raises(SiestaError) as e:
             ctx.wrap_log(torch.from_numpy(bad).cuda(), d_act, d_ts, 4)
         assert e.value.code == abi.E_INVALID
+
+
+def test_evaluate_events_reads_pinned_timestamps_in_place(ctx):
+    """Without a time constraint siesta_evaluate_events leaves a page-locked timestamp column on the host and the kernels
+    read the reported events' timestamps through the mapping; results equal the oracle's either way."""
+    import torch
+    off, act, ts = gen.make_log(20000, 0, 60, 12, seed=404, max_gap_s=500, jitter_ms=True)
+    p_off, p_act, p_ts = (torch.from_numpy(x).pin_memory() for x in (off, act, ts))
+    cases = [([dict(kind=N_, types=[0]), dict(kind=O_, types=[1, 2], preds=[(abi.ATTR_POSITION, abi.OP_LE, 0, 10)]),
+               dict(kind=X_, types=[3]), dict(kind=N_, types=[4])], 0),                         # K1-P
+             ([dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[2])], 0),  # staged kernel, run-list engine
+             ([dict(kind=N_, types=[0]), dict(kind=N_, types=[1])], abi.F_EVT_POS),
+             ([dict(kind=P_, types=[0]), dict(kind=S_, types=[1], preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 600)])], 0)]  # matches on time: copied
+    for states, flags in cases:
+        nfa = abi.make_nfa(states)
+        want = oracle.detect(off, act, ts, nfa, flags=flags)
+        got = ctx.evaluate_events(p_off.numpy(), p_act.numpy(), p_ts.numpy(), 12, nfa, flags=flags)
+        ok, why = got.same_as(want)
+        assert ok, (why, states, flags)
