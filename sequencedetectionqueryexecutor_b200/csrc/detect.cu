@@ -417,6 +417,209 @@ __global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4)
     }
 }
 
+// ---------------------------------------------------------------------------------- K1-L: class NK on traces of any length
+// The traces the wide launch could not hold (more than 64 pattern-relevant events, more than 65 536 events) re-run here when
+// the NFA has no Kleene state: one warp per trace, no masks.  Phase A compacts the trace's relevant events into plain arrays
+// (state word, position, relative seconds) carved from a bump-allocated pool; phase B walks every start forward through
+// that list, lanes = starts (nk_long_walk, detect_fast.cuh); phase C selects as Occurrences.clearOccurrences does - the
+// smallest (completion, start), then, for returnAll, the later runs in emission order that overlap nothing chosen - and
+// stages the events in a region of its own.  A trace that does not fit the pool, the staging region or the 16-bit
+// per-trace counts of the placement goes to the final list of unsupported traces.
+struct LongParams {
+    const int64_t* work;                     // candidate indices (the wide launch's overflow list)
+    const unsigned long long* n_work_dev;
+    int64_t work_cap;
+    char* pool;
+    unsigned long long pool_bytes;
+    int64_t ev_base, ev_cap;                 // staging region of this kernel inside the s_ev_* arrays
+    int64_t occ_base, occ_cap;               // ... inside s_occ_nev (returnAll)
+    int64_t* unsup;                          // final list of unsupported traces (candidate indices)
+    int64_t unsup_cap;
+    int32_t n_positive;
+    // counters: 14 final unsupported, 19 next work item, 20 pool cursor, 21 staged events, 22 staged occurrences
+};
+
+__global__ void __launch_bounds__(128) detect_long_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ LongParams Q,
+                                                          const __grid_constant__ DevNfa nfa) {
+    const int lane = threadIdx.x & 31;
+    const bool evt_pos = (P.flags & SIESTA_F_EVT_POS) != 0;
+    const bool return_all = (P.flags & SIESTA_F_RETURN_ALL) != 0;
+    const bool all_cols = (P.flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
+    const int np = Q.n_positive;
+    long long n_work = (long long)__ldg(Q.n_work_dev);
+    if (n_work > Q.work_cap) n_work = Q.work_cap;   // (the host fails the request beyond the cap)
+    for (;;) {
+        long long w = 0;
+        if (lane == 0) w = (long long)atomicAdd(P.counters + 19, 1ull);
+        w = shfl_i64(w, 0);
+        if (w >= n_work) break;
+        const int64_t ci = Q.work[w];
+        const int64_t t = P.cand ? P.cand[ci] : ci;
+        const long long o0 = P.trace_off[t], o1 = P.trace_off[t + 1];
+        const long long len = o1 - o0;
+        bool ok = len <= 0x7fffffffll;
+        // ---- pool: word u16[len] | pos i32[len] | sec i32[len] | rec_c i32[len] | rec_e i32[len * np] | sel i32[len]
+        const unsigned long long need = ((unsigned long long)len * (2 + 4 + 4 + 4 + 4 * (unsigned)np + 4) + 255) & ~255ull;
+        unsigned long long at = 0;
+        if (lane == 0 && ok) at = atomicAdd(P.counters + 20, need);
+        at = (unsigned long long)shfl_i64((long long)at, 0);
+        ok = ok && at + need <= Q.pool_bytes;
+        int n_rel = 0, nsel = 0;
+        unsigned n_emitted = 0;
+        long long t0ms = 0;
+        int32_t *pos = nullptr, *sec = nullptr, *rec_c = nullptr, *rec_e = nullptr, *sel = nullptr;
+        uint16_t* word = nullptr;
+        if (ok) {
+            char* base = Q.pool + at;
+            pos = reinterpret_cast<int32_t*>(base);
+            sec = pos + len;
+            rec_c = sec + len;
+            rec_e = rec_c + len;
+            sel = rec_e + len * np;
+            word = reinterpret_cast<uint16_t*>(sel + len);
+            // ---- phase A: compact the relevant events (lanes = events, coalesced)
+            bool have_t0 = false;
+            for (long long e0 = 0; e0 < len; e0 += 32) {
+                const long long e = e0 + lane;
+                uint32_t wd = 0;
+                long long raw = 0;
+                if (e < len) {
+                    const int a = __ldg(P.act + o0 + e);
+                    if ((unsigned)a < (unsigned)P.n_act) wd = (uint32_t)__ldg(P.lut + a) & 0xFFu;
+                    if (wd && (P.needs_ts || (all_cols && !evt_pos))) raw = __ldg(reinterpret_cast<const long long*>(P.ts_ms) + o0 + e);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, wd != 0);
+                if (!have_t0 && m) {   // first event of the filtered list (Utils.java:51-53)
+                    t0ms = shfl_i64(raw, __ffs((int)m) - 1);
+                    have_t0 = true;
+                }
+                if (wd) {
+                    const int r = n_rel + __popc(m & ((1u << lane) - 1u));
+                    word[r] = (uint16_t)wd;
+                    pos[r] = (int32_t)e;
+                    sec[r] = P.needs_ts ? rel_seconds(raw - t0ms) : 0;
+                    rec_c[r] = -1;
+                }
+                n_rel += __popc(m);
+            }
+            __syncwarp();
+            // ---- phase B: every start's run, lanes = starts
+            LongEvents ev{n_rel, word, pos, P.needs_ts ? sec : nullptr, evt_pos};
+            int best_c = 0x7fffffff, best_s = 0x7fffffff;
+            for (int j0 = 0; j0 < n_rel; j0 += 32) {
+                const int j = j0 + lane;
+                if (j < n_rel && (word[j] & 1u)) {
+                    int o[SIESTA_MAX_STATES];
+                    const int k = nk_long_walk(nfa, ev, j, o);
+                    if (k) {
+                        for (int i = 0; i < k; ++i) rec_e[(long long)j * np + i] = o[i];
+                        rec_c[j] = o[k - 1];
+                        ++n_emitted;
+                        if (o[k - 1] < best_c || (o[k - 1] == best_c && j < best_s)) { best_c = o[k - 1]; best_s = j; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d; d >>= 1) {
+                n_emitted += __shfl_xor_sync(0xffffffffu, n_emitted, d);
+                const int oc = __shfl_xor_sync(0xffffffffu, best_c, d), os = __shfl_xor_sync(0xffffffffu, best_s, d);
+                if (oc < best_c || (oc == best_c && os < best_s)) { best_c = oc; best_s = os; }
+            }
+            __syncwarp();
+            // ---- phase C: selection (Occurrences.java:58-89)
+            if (n_emitted) {
+                if (lane == 0) { sel[0] = best_s; rec_c[best_s] = -2 - best_c; }   // taken: completion kept as -2 - c
+                nsel = 1;
+                __syncwarp();
+                if (return_all && n_emitted > 1) {
+                    const bool by_pos = evt_pos;
+                    for (unsigned round = 1; round < n_emitted; ++round) {
+                        // the next run in emission order: smallest (completion, start) among those not looked at yet
+                        int mc = 0x7fffffff, ms = 0x7fffffff;
+                        for (int j = lane; j < n_rel; j += 32) {
+                            const int c = rec_c[j];
+                            if (c >= 0 && (c < mc || (c == mc && j < ms))) { mc = c; ms = j; }
+                        }
+#pragma unroll
+                        for (int d = 16; d; d >>= 1) {
+                            const int oc = __shfl_xor_sync(0xffffffffu, mc, d), os = __shfl_xor_sync(0xffffffffu, ms, d);
+                            if (oc < mc || (oc == mc && os < ms)) { mc = oc; ms = os; }
+                        }
+                        bool ov = false;   // against every chosen run, lanes = chosen runs
+                        for (int q = lane; q < nsel; q += 32) {
+                            const int bs = sel[q];
+                            const int bl = -2 - rec_c[bs];
+                            ov = ov || nk_long_overlaps(ev, by_pos, ms, mc, bs, bl);
+                        }
+                        ov = __any_sync(0xffffffffu, ov);
+                        if (lane == 0) {
+                            if (!ov) { sel[nsel] = ms; rec_c[ms] = -2 - mc; }
+                            else rec_c[ms] = -1;                                   // looked at, not chosen
+                        }
+                        if (!ov) ++nsel;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        // ---- output
+        const long long n_ev = (long long)nsel * np;
+        long long ev_at = 0, occ_at = 0;
+        if (ok && nsel) {
+            ok = nsel <= 0xFFFF && n_ev <= 0xFFFF;   // the placement packs both counts into 16 bits
+            if (ok && lane == 0) {
+                ev_at = (long long)atomicAdd(P.counters + 21, (unsigned long long)n_ev);
+                if (return_all) occ_at = (long long)atomicAdd(P.counters + 22, (unsigned long long)nsel);
+            }
+            ev_at = shfl_i64(ev_at, 0);
+            occ_at = shfl_i64(occ_at, 0);
+            ok = ok && ev_at + n_ev <= Q.ev_cap && (!return_all || occ_at + nsel <= Q.occ_cap);
+        }
+        if (!ok) {
+            if (lane == 0) {
+                P.d_cnt[ci] = 0;
+                const unsigned long long u = atomicAdd(P.counters + 14, 1ull);
+                if ((long long)u < Q.unsup_cap) Q.unsup[u] = ci;
+            }
+            continue;
+        }
+        if (lane == 0) {
+            P.d_cnt[ci] = (uint32_t)nsel | ((uint32_t)n_ev << 16);
+            if (nsel) {
+                P.d_stage[ci] = Q.ev_base + ev_at;
+                if (return_all) P.d_stage_occ[ci] = Q.occ_base + occ_at;
+                unsigned long long* b = P.blk_sums + (ci >> 8);
+                atomicAdd(b, 1ull);
+                atomicAdd(b + P.n_blk, (unsigned long long)nsel);
+                atomicAdd(b + 2 * P.n_blk, (unsigned long long)n_ev);
+                atomicAdd(P.counters + 0, (unsigned long long)nsel);
+                atomicAdd(P.counters + 1, (unsigned long long)n_ev);
+                atomicAdd(P.counters + 6, 1ull);
+            }
+            if (n_emitted) atomicAdd(P.counters + 2, (unsigned long long)n_emitted);
+        }
+        for (long long f = lane; f < n_ev; f += 32) {
+            const int o = (int)(f / np), i = (int)(f % np);
+            const int j = rec_e[(long long)sel[o] * np + i];
+            const int src = pos[j];
+            const long long dst = Q.ev_base + ev_at + f;
+            P.s_ev_pos[dst] = src;
+            if (all_cols) {
+                P.s_ev_rank[dst] = j;
+                P.s_ev_act[dst] = __ldg(P.act + o0 + src);
+                long long out_ts;
+                if (P.needs_ts) out_ts = (long long)sec[j] * 1000 + t0ms;   // SaseEvent.getEventBoth (SaseEvent.java:94-106)
+                else {
+                    const long long raw = __ldg(reinterpret_cast<const long long*>(P.ts_ms) + o0 + src);
+                    out_ts = evt_pos ? raw : (long long)rel_seconds(raw - t0ms) * 1000 + t0ms;
+                }
+                P.s_ev_ts[dst] = out_ts;
+            }
+            if (return_all && i == 0) P.s_occ_nev[Q.occ_base + occ_at + o] = np;
+        }
+    }
+}
+
 // Final placement.  The dense per-candidate counts (d_nocc, d_nev) are scanned in three levels
 // (per-block sums -> chunks of 1024 block sums -> chunk sums, + the in-block scan inside the gather), and the
 // gather copies each matching trace's staged occurrences to its final, trace-ordered position.
@@ -696,6 +899,7 @@ struct DetectPending {
     unsigned long long *d_blk = nullptr, *d_top = nullptr, *d_counters = nullptr;
     int64_t* d_err = nullptr;
     int64_t* d_unsup = nullptr;           // candidate indices of the traces beyond the engine limits
+    int unsup_slot = 7;                   // counter that counts them (7: wide launch, 14: K1-L)
     void* work = nullptr;                 // scratch of the call (freed by the second half)
     int uniform_k = 0;                    // > 0: one occurrence per trace, uniform_k events each (class NK, first-largest)
     cudaEvent_t ev0 = nullptr, evd = nullptr;
@@ -778,18 +982,25 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
     const bool use_nkp = nkw_space != NKW_NONE && !needs_ts && log->act_valid && log->n_activities <= 255 && !sigs.empty() && sigs.size() <= 7 &&
                          (reinterpret_cast<uintptr_t>(log->d_act) & 31u) == 0 && std::getenv("SIESTA_K1_NO_NKP") == nullptr;
     const size_t n_reg = use_nkp ? 2 : 1;  // staging regions: [0, cap) by atomics (staged kernels), [cap, 2 cap) fixed tile slots (K1-P)
+    // class NK: the traces beyond the mask kernels' limits re-run on K1-L, which stages in a region of its own behind
+    // the others and takes its per-trace arrays from a pool
+    const bool use_long = dn.fast_class == FAST_NK && std::getenv("SIESTA_K1_NO_LONG") == nullptr;
+    const int64_t cap_long = use_long ? std::min<int64_t>(log->n_events, (int64_t)1 << 21) : 0;
+    const size_t long_pool = use_long ? (size_t)std::min<int64_t>(std::max<int64_t>(log->n_events * 64, (int64_t)1 << 20), (int64_t)256 << 20) : 0;
     const size_t n_blk = (nn + GT - 1) / GT;
     const size_t o_ovf2 = use_nkp ? carve(nn * 8) : 0;
     const size_t o_unsup = carve((size_t)SIESTA_MAX_UNSUPPORTED * 8);   // traces beyond the engine limits (wide launch)
+    const size_t o_unsup2 = use_long ? carve((size_t)SIESTA_MAX_UNSUPPORTED * 8) : 0;   // ... and beyond K1-L's pool / staging
+    const size_t o_pool = carve(long_pool);
     const size_t o_nlut = use_nkp ? carve((size_t)(log->n_activities + 1) * 16) : 0;
     const size_t o_lut = carve(lut.size() * sizeof(uint16_t)), o_nocc = carve(nn * 4), o_stage = carve(nn * 8),
                  o_stage_occ = carve(return_all ? nn * 8 : 0), o_counters = carve(32 * 8), o_err = carve(nn * 8), o_ovf = carve(nn * 8),
-                 o_blk = carve(n_blk * 3 * 8), o_top = carve(((n_blk + 1023) / 1024) * 3 * 8), o_occ_nev = carve(return_all ? (size_t)cap_occ * 4 : 0), o_pos = carve((size_t)cap_ev * 4 * n_reg);
+                 o_blk = carve(n_blk * 3 * 8), o_top = carve(((n_blk + 1023) / 1024) * 3 * 8), o_occ_nev = carve(return_all ? (size_t)(cap_occ + cap_long) * 4 : 0), o_pos = carve(((size_t)cap_ev * n_reg + (size_t)cap_long) * 4);
     size_t o_rank = 0, o_act = 0, o_ts = 0;
     if (all_cols) {
-        o_rank = carve((size_t)cap_ev * 4 * n_reg);
-        o_act = carve((size_t)cap_ev * 4 * n_reg);
-        o_ts = carve((size_t)cap_ev * 8 * n_reg);
+        o_rank = carve(((size_t)cap_ev * n_reg + (size_t)cap_long) * 4);
+        o_act = carve(((size_t)cap_ev * n_reg + (size_t)cap_long) * 4);
+        o_ts = carve(((size_t)cap_ev * n_reg + (size_t)cap_long) * 8);
     }
     if ((rc = work.alloc(w_off))) return rc;
     char* wb = work.as<char>();
@@ -942,6 +1153,25 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
         else if (dn.fast_class == FAST_NK) rc = launch_detect<2, 0, 0, false, FAST_NK>(ctx, stream, Q, dn);
         else rc = launch_detect<2, 1024, 128, false, FAST_NONE>(ctx, stream, Q, dn);
         if (rc) return rc;
+        if (use_long) {
+            LongParams LQ;
+            std::memset(&LQ, 0, sizeof(LQ));
+            LQ.work = reinterpret_cast<const int64_t*>(wb + o_unsup);
+            LQ.n_work_dev = b_counters.as<unsigned long long>() + 7;
+            LQ.work_cap = SIESTA_MAX_UNSUPPORTED;
+            LQ.pool = wb + o_pool;
+            LQ.pool_bytes = long_pool;
+            LQ.ev_base = (int64_t)cap_ev * (int64_t)n_reg;
+            LQ.ev_cap = cap_long;
+            LQ.occ_base = cap_occ;
+            LQ.occ_cap = cap_long;
+            LQ.unsup = reinterpret_cast<int64_t*>(wb + o_unsup2);
+            LQ.unsup_cap = SIESTA_MAX_UNSUPPORTED;
+            LQ.n_positive = std::max(1, n_positive);
+            detect_long_kernel<<<ctx->sm_count * 2, 128, 0, stream>>>(P, LQ, dn);
+            SIESTA_LAUNCHED();
+            SIESTA_CUDA_OK(cudaGetLastError());
+        }
         SIESTA_CUDA_OK(cudaMemcpyAsync(h_cnt, b_counters.p, 128, cudaMemcpyDeviceToHost, stream));
     }
     // ---- end of the first half: nothing above waits for the device
@@ -958,7 +1188,8 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
     q->d_top = reinterpret_cast<unsigned long long*>(wb + o_top);
     q->d_counters = b_counters.as<unsigned long long>();
     q->d_err = b_err.as<int64_t>();
-    q->d_unsup = reinterpret_cast<int64_t*>(wb + o_unsup);
+    q->d_unsup = reinterpret_cast<int64_t*>(wb + (use_long ? o_unsup2 : o_unsup));
+    q->unsup_slot = use_long ? 14 : 7;
     q->work = work.release();
     q->uniform_k = (!return_all && !dn.any_kleene) ? std::max(1, n_positive) : 0;
     q->ev0 = ev0;
@@ -994,7 +1225,7 @@ int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out) {
     int rc = SIESTA_OK;
     SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
     if (n > 0) {
-        if (h_cnt[7] > SIESTA_MAX_UNSUPPORTED) {
+        if (h_cnt[7] > SIESTA_MAX_UNSUPPORTED || h_cnt[q->unsup_slot] > SIESTA_MAX_UNSUPPORTED) {
             set_error(std::to_string(h_cnt[7]) + " traces exceed the engine limits (64 pattern-relevant events, 1024 live runs or "
                       "65536 events per trace); at most " + std::to_string(SIESTA_MAX_UNSUPPORTED) + " are listed per request");
             return SIESTA_E_UNSUPPORTED;
@@ -1013,7 +1244,7 @@ int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out) {
     fprintf(stderr, "[siesta phase timing] warp-cycles: filter %llu engine %llu output %llu\n", h_cnt[8], h_cnt[9], h_cnt[10]);
 #endif
     const int64_t n_occ = (int64_t)h_cnt[0], n_ev = (int64_t)h_cnt[1], n_tr = (int64_t)h_cnt[6], n_err = (int64_t)h_cnt[3];
-    const int64_t n_unsup = n > 0 ? (int64_t)h_cnt[7] : 0;
+    const int64_t n_unsup = n > 0 ? (int64_t)h_cnt[q->unsup_slot] : 0;
 
     // the result columns: one allocation, owned by the returned object
     DevBuf fin(log->ctx);
@@ -1269,13 +1500,13 @@ __global__ void __launch_bounds__(GT) gather_packed_kernel(const __grid_constant
 }
 
 // Header of the block: sizes from the request's counters, status, the tails of the offset sections, the error list.
-__global__ void pack_header_kernel(const unsigned long long* counters, const int64_t* err_list, const int64_t* unsup_list, XHeader proto,
-                                   XHeader* hdr, const __grid_constant__ PackSections O) {
+__global__ void pack_header_kernel(const unsigned long long* counters, const int64_t* err_list, const int64_t* unsup_list, int unsup_slot,
+                                   XHeader proto, XHeader* hdr, const __grid_constant__ PackSections O) {
     const int64_t n_occ = (int64_t)counters[0], n_ev = (int64_t)counters[1], n_tr = (int64_t)counters[6], n_err = (int64_t)counters[3];
-    const int64_t n_unsup = (int64_t)counters[7];
+    const int64_t n_unsup = (int64_t)counters[unsup_slot];
     if (threadIdx.x == 0) {
         int status = *O.status;
-        if (n_unsup > XCHG_ERR_CAP) status |= XST_LIMITS;
+        if (n_unsup > XCHG_ERR_CAP || (long long)counters[7] > SIESTA_MAX_UNSUPPORTED) status |= XST_LIMITS;
         if (counters[5] > 0) status |= XST_STAGING;
         if (n_err > XCHG_ERR_CAP) status |= XST_ERRCAP;
         if (!proto.uniform_k && !(status & XST_STAGING)) {
@@ -1393,7 +1624,7 @@ int detect_device_pack_impl(DetectPending* q, const PackTarget& tgt) {
         gather_packed_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G, O, q->uniform_k ? 1 : 0);
         SIESTA_LAUNCHED();
     }
-    pack_header_kernel<<<1, 256, 0, stream>>>(q->d_counters, q->d_err, q->d_unsup, proto, tgt.hdr, O);
+    pack_header_kernel<<<1, 256, 0, stream>>>(q->d_counters, q->d_err, q->d_unsup, q->unsup_slot, proto, tgt.hdr, O);
     SIESTA_LAUNCHED();
     SIESTA_CUDA_OK(cudaGetLastError());
     return SIESTA_OK;

@@ -365,6 +365,69 @@ SIESTA_HD __forceinline__ bool nk_eval(const DevNfa& nfa, const EV& ev, const ty
     return true;
 }
 
+// --------------------------------------------------------------------------------- class NK on traces of any length
+// The mask evaluators above hold a trace's pattern-relevant events in 32 / 64 / 64-bit masks.  For class NK the greedy walk
+// needs no mask at all: it moves forward through the filtered event list once per start.  LongEvents is that list in
+// plain arrays (global memory on the device); nk_long_walk is nk_walk over it.  Kernel K1-L (detect.cu) runs one warp per
+// trace beyond the mask kernels' limits, lanes = starts, so NO trace length is out of reach for a pattern without a
+// Kleene state (the reference has no limit either: S/engine/Engine.java:207-224).
+struct LongEvents {
+    int n;                  // pattern-relevant events of the trace
+    const uint16_t* word;   // [n] bit k <=> the event's type belongs to state k
+    const int32_t* pos;     // [n] in-trace position
+    const int32_t* sec;     // [n] relative seconds (EventTs route with a time predicate / returnAll), or nullptr
+    bool evt_pos;
+    // SaseEvent attributes after Utils.transformToSaseEvents (J/model/Utils/Utils.java:48-65)
+    SIESTA_HD __forceinline__ int position(int j) const { return evt_pos ? pos[j] : j; }
+    SIESTA_HD __forceinline__ int timestamp(int j) const { return evt_pos ? j : (sec ? sec[j] : 0); }
+    SIESTA_HD __forceinline__ int attr(int j, int a) const { return a == SIESTA_ATTR_POSITION ? position(j) : timestamp(j); }
+};
+
+// Greedy walk of the run started at filtered event s: out[0..n_positive) = the events it takes (indices into the filtered
+// list); returns the number of events taken, 0 = the run never completes or is deleted at a negative state.
+SIESTA_HD inline int nk_long_walk(const DevNfa& nfa, const LongEvents& ev, int s, int* out) {
+    const int S = nfa.n_states;
+    int vvi[SIESTA_MAX_STATES];
+    vvi[0] = s;
+    auto vv = [&vvi](int ref) { return vvi[ref]; };
+    int n_out = 0;
+    out[n_out++] = s;
+    int p = s, k = 1;
+    while (k < S) {
+        const bool neg = nfa.kind[k] == SIESTA_STATE_NEGATIVE;
+        int got = -1;
+        for (int e = p + 1; e < ev.n; ++e) {
+            const uint32_t w = ev.word[e];
+            if (neg) {
+                if ((w >> k) & 1u) {
+                    if (fast_preds(nfa, ev, k, e, k, vv)) return 0;   // containsNegative: deleted (Engine.java:679-682)
+                } else if (((w >> (k + 1)) & 1u) && fast_preds(nfa, ev, k + 1, e, k, vv)) {   // Engine.checkPredicatesForNextState :1165-1180
+                    got = e;
+                    break;
+                }
+            } else if (((w >> k) & 1u) && fast_preds(nfa, ev, k, e, k, vv)) {
+                got = e;
+                break;
+            }
+        }
+        if (got < 0) return 0;
+        const int ks = neg ? k + 1 : k;
+        vvi[ks] = got;
+        out[n_out++] = got;
+        p = got;
+        k = ks + 1;
+    }
+    return n_out;
+}
+
+// Occurrence.overlaps (J/model/Occurrence.java:36-49) between two runs given by their first / last filtered events
+SIESTA_HD __forceinline__ bool nk_long_overlaps(const LongEvents& ev, bool by_pos, int af, int al, int bf, int bl) {
+    bool not_ov;
+    if (by_pos) not_ov = ev.position(al) < ev.position(bf) || ev.position(af) > ev.position(bl);
+    else not_ov = ev.timestamp(al) < ev.timestamp(bf) || ev.timestamp(af) > ev.timestamp(bl);
+    return !not_ov;
+}
+
 // ------------------------------------------------------------------------- class NK as window walks (kernel K1-P)
 // Kernel K1-P addresses a trace's events by ONE index space in which every attribute the NFA's predicates read IS the
 // bit index of the event:

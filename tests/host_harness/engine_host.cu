@@ -1,6 +1,7 @@
 // engine_host.cu — TEST HARNESS (not the product): runs the device engine (detect_engine.cuh), compiled for the
 // host, over a CSR log on the CPU so tests can compare it with the oracle without a GPU.  The filter and the
 // output assembly here are simple serial restatements of kernel K1's phases A and C.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -186,6 +187,53 @@ extern "C" int engine_host_detect(const int64_t* trace_off, const int32_t* act, 
                 o.ev_ts.push_back(evt_pos ? raw : (long long)((int)((raw - t0) / 1000)) * 1000 + t0);
             }
             o.ev_off.push_back((int64_t)o.ev_pos.size());
+            o.occ_off.push_back((int64_t)o.ev_off.size() - 1);
+            continue;
+        }
+        // kernel K1-L: class NK on a trace beyond the mask kernels' limits - the forward walk over the filtered list.  The
+        // harness takes it from 25 relevant events on, so that the usual soak traces exercise it too.
+        if (dn.fast_class == FAST_NK && meta.size() > 24 && std::getenv("SIESTA_HARNESS_NO_LONG") == nullptr) {
+            std::vector<uint16_t> word(meta.size());
+            std::vector<int32_t> posv(meta.size());
+            for (size_t j = 0; j < meta.size(); ++j) {
+                word[j] = (uint16_t)(meta[j] & 0xFFFFu);
+                posv[j] = (int32_t)(meta[j] >> 16);
+            }
+            LongEvents le{(int)meta.size(), word.data(), posv.data(), needs_ts ? ts.data() : nullptr, evt_pos};
+            const bool return_all = (flags & SIESTA_F_RETURN_ALL) != 0;
+            const int np = n_pos > 0 ? n_pos : 1;
+            // every start's run; emission order = (completion, start)
+            struct Run { int c, s; std::vector<int> e; };
+            std::vector<Run> runs;
+            for (int s0 = 0; s0 < le.n; ++s0) {
+                if (!(word[s0] & 1u)) continue;
+                int o[SIESTA_MAX_STATES];
+                const int k = nk_long_walk(dn, le, s0, o);
+                if (k) runs.push_back(Run{o[k - 1], s0, std::vector<int>(o, o + k)});
+            }
+            if (runs.empty()) continue;
+            (void)np;
+            std::stable_sort(runs.begin(), runs.end(), [](const Run& a, const Run& b) { return a.c != b.c ? a.c < b.c : a.s < b.s; });
+            std::vector<const Run*> sel{&runs[0]};   // all runs have the same size: the first emitted one is the first-largest
+            if (return_all)
+                for (size_t r = 1; r < runs.size(); ++r) {
+                    bool ov = false;
+                    for (const Run* q : sel) ov = ov || nk_long_overlaps(le, evt_pos, runs[r].e.front(), runs[r].e.back(), q->e.front(), q->e.back());
+                    if (!ov) sel.push_back(&runs[r]);
+                }
+            o.emitted += (int64_t)runs.size();
+            o.trace_idx.push_back(t);
+            for (const Run* q : sel) {
+                for (int j : q->e) {
+                    const int src = posv[j];
+                    o.ev_pos.push_back(src);
+                    o.ev_rank.push_back(j);
+                    o.ev_act.push_back(act[b0 + src]);
+                    const long long raw = ts_ms[b0 + src];
+                    o.ev_ts.push_back(evt_pos ? raw : (long long)((int)((raw - t0) / 1000)) * 1000 + t0);
+                }
+                o.ev_off.push_back((int64_t)o.ev_pos.size());
+            }
             o.occ_off.push_back((int64_t)o.ev_off.size() - 1);
             continue;
         }

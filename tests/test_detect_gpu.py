@@ -149,15 +149,20 @@ def test_limits_are_reported_not_silently_wrong(ctx):
     lens = np.concatenate([np.diff(off)[:17], [200, 200], np.diff(off)[17:], [200]])
     off2 = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
     outliers = [17, 18, len(lens) - 1]
-    for states, flags in (([dict(kind=N_, types=[0]), dict(kind=N_, types=[1])], 0),
-                          ([dict(kind=P_, types=[0]), dict(kind=S_, types=[1])], 0),
-                          ([dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[0])], abi.F_RETURN_ALL)):
+    for states, flags, limited in (([dict(kind=N_, types=[0]), dict(kind=N_, types=[1])], 0, False),          # class NK: kernel K1-L answers them
+                                   ([dict(kind=P_, types=[0]), dict(kind=S_, types=[1])], 0, True),
+                                   ([dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[0])], abi.F_RETURN_ALL, True)):
         nfa = abi.make_nfa(states)
         log = ctx.load_log(off2, act2, ts2, 2)
         got = log.detect(nfa, flags=flags)
         log.close()
-        assert got.unsupported_trace_idx.tolist() == outliers and got.n_unsupported == 3
         want = oracle.detect(off2, act2, ts2, nfa, flags=flags)
+        if not limited:
+            assert got.n_unsupported == 0
+            ok, why = got.same_as(want)
+            assert ok, why
+            continue
+        assert got.unsupported_trace_idx.tolist() == outliers and got.n_unsupported == 3
         keep = ~np.isin(want.trace_idx, outliers)
         assert np.array_equal(got.trace_idx, want.trace_idx[keep])
         # the occurrences of the supported traces, one by one
@@ -563,3 +568,23 @@ def test_evaluate_events_reads_pinned_timestamps_in_place(ctx):
         got = ctx.evaluate_events(p_off.numpy(), p_act.numpy(), p_ts.numpy(), 12, nfa, flags=flags)
         ok, why = got.same_as(want)
         assert ok, (why, states, flags)
+
+
+@pytest.mark.parametrize("flags", [0, abi.F_RETURN_ALL, abi.F_EVT_POS, abi.F_EVT_POS | abi.F_RETURN_ALL, abi.F_COUNT_MATCHES, abi.F_NO_EVENT_COLUMNS])
+def test_patterns_without_kleene_states_on_traces_of_any_length(ctx, flags):
+    """Kernel K1-L: 3-activity logs with 200 - 2 000 events per trace (every event is pattern-relevant, far beyond the 64 the
+    mask kernels hold) against the oracle; the reference's engine has no per-trace limit (Engine.java:207-224)."""
+    off, act, ts = gen.make_log(60, 200, 2000, 3, seed=9, max_gap_s=30, jitter_ms=True)
+    short = gen.make_log(500, 0, 40, 3, seed=10, max_gap_s=30)           # the usual traces around them
+    off = np.concatenate([off, off[-1] + short[0][1:]])
+    act = np.concatenate([act, short[1]])
+    ts = np.concatenate([ts, short[2]])
+    patterns = [
+        [dict(kind=N_, types=[0]), dict(kind=N_, types=[1]), dict(kind=N_, types=[2])],
+        [dict(kind=N_, types=[0]), dict(kind=X_, types=[1]), dict(kind=N_, types=[2], preds=[(abi.ATTR_POSITION, abi.OP_GE, 0, 4)])],
+        [dict(kind=O_, types=[0, 1]), dict(kind=N_, types=[2], preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 40)]),
+         dict(kind=N_, types=[0], preds=[(abi.ATTR_POSITION, abi.OP_LE, 0, 9), (abi.ATTR_TIMESTAMP, abi.OP_GE, 1, 5)])],
+    ]
+    for states in patterns:
+        got = _check(ctx, off, act, ts, 3, states, flags)
+        assert got.n_unsupported == 0 and got.n_traces > 0

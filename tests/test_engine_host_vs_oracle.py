@@ -80,8 +80,9 @@ def test_baseline_config_shapes(flags):
     assert _compare(off, act, ts, 20, st, flags)[0] == "ok"
 
 
-def test_wide_engine_path_is_exercised():
+def test_wide_engine_path_is_exercised(monkeypatch):
     """Few activity types -> many relevant events and O(n^2) Kleene runs: must fall over to the wide configuration."""
+    monkeypatch.setenv("SIESTA_HARNESS_NO_LONG", "1")   # (the harness otherwise takes class NK to the long-trace evaluator from 25 events on)
     N_, P_, S_ = abi.STATE_NORMAL, abi.STATE_KLEENE_PLUS, abi.STATE_KLEENE_STAR
     off, act, ts = gen.make_log(60, 20, 45, 3, seed=77)
     r, n_wide = _compare(off, act, ts, 3, [dict(kind=P_, types=[0]), dict(kind=S_, types=[1])], 0)

@@ -105,18 +105,26 @@ def test_sharded_allgather_equals_unsharded_oracle(name, states, flags, shape):
 
 
 def test_long_and_unaligned_traces_cross_shards():
-    """Traces that leave K1-P for the staged kernels (more than 64 slots / 32 relevant events) inside a shard, and traces
-    beyond the engine limits (more than 64 relevant events): listed on every rank, all others exact."""
+    """Traces that leave K1-P for the staged kernels (more than 64 slots / 32 relevant events) and for K1-L (more than 64
+    relevant events) inside a shard: exact on every rank; with a Kleene state the traces beyond the engine limits are
+    listed on every rank and all others are exact."""
     from sequencedetectionqueryexecutor_b200 import api
-    nfa = abi.make_nfa([dict(kind=N_, types=[0]), dict(kind=X_, types=[1]), dict(kind=N_, types=[2], preds=[(abi.ATTR_POSITION, abi.OP_GE, 0, 3)])])
+    nk = [dict(kind=N_, types=[0]), dict(kind=X_, types=[1]), dict(kind=N_, types=[2], preds=[(abi.ATTR_POSITION, abi.OP_GE, 0, 3)])]
+    kl = [dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[2])]
     for n_act in (9, 4):
         off, act, ts = gen.make_log(1200, 0, 130, n_act, seed=77, max_gap_s=50)
-        want = oracle.detect(off, act, ts, nfa, flags=0)
         rel = np.add.reduceat(np.concatenate([(act < 3).astype(np.int64), [0]]), off[:-1]) * (np.diff(off) > 0)
         outliers = np.flatnonzero(rel > 64)
         assert (len(outliers) > 0) == (n_act == 4)
-        keep = ~np.isin(want.trace_idx, outliers)
         with api.Context(0) as ctx:
+            nfa = abi.make_nfa(nk)
+            want = oracle.detect(off, act, ts, nfa, flags=0)
+            for got, _ in _run_sharded(ctx, off, act, ts, n_act, nfa, 0, [0, 333, 800, 1200]):
+                ok, why = got.same_as(want)
+                assert ok and got.n_unsupported == 0, why
+            nfa = abi.make_nfa(kl)
+            want = oracle.detect(off, act, ts, nfa, flags=0)
+            keep = ~np.isin(want.trace_idx, outliers)
             for got, _ in _run_sharded(ctx, off, act, ts, n_act, nfa, 0, [0, 333, 800, 1200]):
                 assert got.unsupported_trace_idx.tolist() == outliers.tolist()
                 assert np.array_equal(got.trace_idx, want.trace_idx[keep])
