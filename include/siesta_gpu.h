@@ -225,8 +225,9 @@ typedef struct siesta_matches {
     int64_t* err_trace_idx;    /* [n_ref_errors] ascending                           */
     double kernel_ms;          /* device time of all kernels of the call (CUDA events) */
     double detect_ms;          /* device time of the verification kernel K1 alone      */
-    /* Traces beyond the GPU engine's per-trace limits (more than 64 pattern-relevant events, 1024 live runs or 65 536
-     * events).  The reference has no such limit (S/engine/Engine.java:207-224), so the request does NOT fail for them:
+    /* Traces beyond the GPU engine's per-trace limits: for a pattern WITH a Kleene state, more than 64 pattern-relevant
+     * events, 1024 live runs or 65 536 events (patterns without one are evaluated on traces of any length, kernel K1-L,
+     * and never list a trace).  The reference has no such limit (S/engine/Engine.java:207-224), so the request does NOT fail for them:
      * every other trace is answered and these are listed (ascending) for the caller to evaluate elsewhere - the JNI
      * shim hands them to the reference's own engine.  More than SIESTA_MAX_UNSUPPORTED of them fail
      * the call with SIESTA_E_UNSUPPORTED. */
@@ -246,7 +247,12 @@ int siesta_detect(siesta_log* log, const siesta_nfa* nfa, const int64_t* cand, i
 void siesta_matches_free(siesta_matches* m);
 
 /* Literal SaseConnector.evaluate signature: the caller hands the events of
- * this request (host CSR); equals log_load + detect + log_free. */
+ * this request (host CSR); equals log_load + detect + log_free, in chunks that
+ * overlap the host link with the kernels.  When no predicate of the pattern
+ * reads relative seconds and ts_ms lies in page-locked host memory
+ * (cudaHostAlloc / cudaHostRegister), the timestamp column is not copied: the
+ * kernels read the reported events' timestamps in place (4 B/event on the
+ * link instead of 12).  Pageable columns are copied; same results either way. */
 int siesta_evaluate_events(siesta_ctx* ctx, const int64_t* trace_off, const int32_t* act,
                            const int64_t* ts_ms, int64_t n_traces, int64_t n_events,
                            int32_t n_activities, const siesta_nfa* nfa, uint32_t flags,
