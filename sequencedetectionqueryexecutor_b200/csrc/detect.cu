@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4)
         int status = ST_NONE;
         unsigned n_emitted = 0;
         int nsel = 0;
-        mask_t sel_local[(MODE == FAST_FK2) ? 1 : NE];
+        mask_t sel_local[(MODE == FAST_FK2 || MODE == FAST_NP1) ? 1 : NE];
         if (ci >= 0 && my_cnt > 0) {
             if (my_cnt > NE) {
                 status = ST_OVF;
@@ -210,6 +210,15 @@ __global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4)
                     if (fk2_eval<W>(nfa, ev, m)) {
                         status = ST_MATCH;
                         sel_local[0] = m;
+                        nsel = 1;
+                    }
+                } else if constexpr (MODE == FAST_NP1) {
+                    NkMasks<W> nkm;
+                    nkm.init();
+                    for (int j = 0; j < ev.n; ++j) nkm.on_event(j, ev.word(j));
+                    const bool count = (P.flags & (SIESTA_F_RETURN_ALL | SIESTA_F_COUNT_MATCHES)) != 0;
+                    if (np1_eval<W>(nfa, nkm.T, count, sel_local[0], n_emitted)) {
+                        status = ST_MATCH;
                         nsel = 1;
                     }
                 } else if constexpr (MODE == FAST_NK) {
@@ -1136,6 +1145,7 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
         }
         if (dn.fast_class == FAST_FK2) rc = launch_detect<1, 0, 0, false, FAST_FK2>(ctx, stream, P, dn);
         else if (dn.fast_class == FAST_NK) rc = launch_detect<1, 0, 0, false, FAST_NK>(ctx, stream, P, dn);
+        else if (dn.fast_class == FAST_NP1) rc = launch_detect<1, 0, 0, false, FAST_NP1>(ctx, stream, P, dn);
         else rc = launch_detect<1, 16, 16, true, FAST_NONE>(ctx, stream, P, dn);
         if (rc) return rc;
         SIESTA_CUDA_OK(cudaEventRecord(evd, stream));
@@ -1151,6 +1161,7 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
         Q.tile_slot = 17;
         if (dn.fast_class == FAST_FK2) rc = launch_detect<2, 0, 0, false, FAST_FK2>(ctx, stream, Q, dn);
         else if (dn.fast_class == FAST_NK) rc = launch_detect<2, 0, 0, false, FAST_NK>(ctx, stream, Q, dn);
+        else if (dn.fast_class == FAST_NP1) rc = launch_detect<2, 0, 0, false, FAST_NP1>(ctx, stream, Q, dn);
         else rc = launch_detect<2, 1024, 128, false, FAST_NONE>(ctx, stream, Q, dn);
         if (rc) return rc;
         if (use_long) {

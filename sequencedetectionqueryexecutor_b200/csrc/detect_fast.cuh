@@ -45,12 +45,38 @@
 //   took), X precedes Y at event k iff the highest event below k in pl(X) xor pl(Y) belongs to pl(Y).  Q(0,m) is
 //   created in Z(0)'s slot, which was placed at a_{m-1}; at a_q, q >= 1, Z(0) is re-appended before P(q) is created,
 //   at a_0 P(0) is appended first.
+//
+// Class NP1 — normal / or states and exactly ONE kleeneClosure+ state (index k; k = 0 needs a second state), no predicate
+//             on any state (SIESTA's pattern without constraints, or any pattern under onlyAppearances:
+//             ComplexPattern.getNfaWithoutConstraints :253-283), e.g. `a b+ c`.  returnAll only on the EventPos route.
+//   Without predicates there is no value vector, so runs do not interact; only their list order matters, for ties.
+//   k >= 1: the run started at an event of state 0's types walks the prefix greedily (first later event of each state's
+//   types) and reaches the Kleene state after its prefix end p.  There it takes EVERY later event b_1 < b_2 < ... of the
+//   Kleene type; each time the run that took b_m moves on (Run.proceed) and a clone stays behind at the tail of the
+//   list and takes b_{m+1} (Engine.java:702-713).  The run that moved on after b_m walks the suffix greedily from b_m.
+//   The engine's matches are therefore (start i, m) = prefix_i + {b_1..b_m} + suffix(b_m) for every m whose suffix
+//   completes, with n_states - 1 + m events.  Whether the suffix completes from a position is monotone: it does iff the
+//   position lies below l = the state-(k+1) event of the LATEST embedding of the suffix (backward greedy); F = the
+//   positions below l (everything when the Kleene state is the last one: the run is full when it moves on).
+//   Largest: prefix ends never decrease with the start, so the first start has the most Kleene events after its prefix,
+//   m* = |T[k] & above(p_0) & F| (no start completes a prefix if the first one does not).  Another start ties only if no
+//   Kleene event lies between the two prefix ends; both then take the same b's and complete at the same event, and the
+//   first start's run sits earlier in the list: (i, 1) is the start run itself, placed at its start event; (i, m) is
+//   the clone placed while b_{m-1} was processed, in the list order of the runs it was cloned from.  By induction the
+//   first start precedes.  Engine matches: the sum over the starts of |T[k] & above(p_i) & F|.
+//   k = 0: Engine.createNewRun :933-982 creates two runs per event a_j of the Kleene type, [a_j] moved on to state 1 and
+//   [a_j] staying, which takes every later a_l and leaves [a_j..a_l] at state 1 each time: matches (j, l >= j) =
+//   {a_j..a_l} + suffix(a_l); the largest, {all a up to the last one in F} + suffix, is unique.
+//   returnAll (Occurrences.java:74-87): every match starts at or after the largest one's first event and completes at
+//   or before its last (suffix completion is monotone in the position it starts from), so on the EventPos route, where
+//   Occurrence.overlaps compares positions, every other match overlaps it: the selection is the largest alone.  On the
+//   EventTs route overlaps compares timestamps, which the caller may hand over unsorted: not taken.
 #pragma once
 #include "detect_engine.cuh"
 
 namespace siesta {
 
-enum { FAST_NONE = 0, FAST_NK = 1, FAST_FK2 = 2 };
+enum { FAST_NONE = 0, FAST_NK = 1, FAST_FK2 = 2, FAST_NP1 = 3 };
 
 template <int W>
 struct MaskX : MaskOps<W> {
@@ -282,6 +308,81 @@ SIESTA_HD __forceinline__ typename MaskOps<W>::T nk_walk(const DevNfa& nfa, cons
         k_next = ks + 1;
     }
     return taken;
+}
+
+// ------------------------------------------------------------------------------------------------ class NP1
+// T[s] = events whose type belongs to state s.  out = the events of the first-largest occurrence (state order = index
+// order); n_emitted = the engine's match count when `count`.
+template <int W>
+SIESTA_HD __forceinline__ bool np1_eval(const DevNfa& nfa, const typename MaskOps<W>::T* T, bool count, typename MaskOps<W>::T& out,
+                                        unsigned& n_emitted) {
+    typedef MaskX<W> MO;
+    typedef typename MO::T mask_t;
+    const int S = nfa.n_states;
+    n_emitted = 0;
+    int k = 0;
+#pragma unroll
+    for (int s = 0; s < SIESTA_MAX_STATES; ++s) {
+        if (s >= S) break;
+        if (T[s] == 0) return false;
+        if (nfa.kind[s] == SIESTA_STATE_KLEENE_PLUS) k = s;
+    }
+    // F: positions from which the suffix completes (backward greedy: the latest embedding of states S-1 .. k+1)
+    mask_t F = ~(mask_t)0;
+#pragma unroll
+    for (int s = SIESTA_MAX_STATES - 1; s >= 1; --s) {
+        if (s >= S || s <= k) continue;
+        const mask_t c = T[s] & F;
+        if (!c) return false;
+        F = MO::below(MO::hi(c));
+    }
+    // prefix walk of the run started at event p; returns the mask of its events (0: does not complete) and its end in p
+    auto prefix = [&](int& p) -> mask_t {
+        mask_t m = MO::bit(p);
+#pragma unroll
+        for (int s = 1; s < SIESTA_MAX_STATES; ++s) {
+            if (s >= k) break;
+            const mask_t c = T[s] & MO::above(p);
+            if (!c) return 0;
+            p = MO::lo(c);
+            m |= MO::bit(p);
+        }
+        return m;
+    };
+    mask_t B, taken;
+    if (k == 0) {
+        B = T[0] & F;
+        taken = 0;
+        if (count)
+            for (mask_t r = B; r; r &= r - 1) n_emitted += (unsigned)MO::popc(T[0] & MO::below(MO::lo(r))) + 1u;   // starts at or before a_l
+    } else {
+        int p = MO::lo(T[0]);
+        taken = prefix(p);
+        if (!taken) return false;
+        B = T[k] & MO::above(p) & F;
+        if (count) {
+            n_emitted = (unsigned)MO::popc(B);
+            for (mask_t r = T[0] & (T[0] - 1); r; r &= r - 1) {
+                int q = MO::lo(r);
+                if (!prefix(q)) break;                       // later starts do not complete their prefix either
+                const unsigned n = (unsigned)MO::popc(T[k] & MO::above(q) & F);
+                if (!n) break;
+                n_emitted += n;
+            }
+        }
+    }
+    if (!B) return false;
+    taken |= B;
+    int q = MO::hi(B);
+#pragma unroll
+    for (int s = 1; s < SIESTA_MAX_STATES; ++s) {
+        if (s >= S) break;
+        if (s <= k) continue;
+        q = MO::lo(T[s] & MO::above(q));   // exists: q lies in F
+        taken |= MO::bit(q);
+    }
+    out = taken;
+    return true;
 }
 
 // aux: scratch of NE masks (one per possible start), element i at aux[i * aux_stride]; only used when return_all.

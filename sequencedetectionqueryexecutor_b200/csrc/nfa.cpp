@@ -8,7 +8,7 @@
 namespace siesta {
 
 // Which closed-form evaluator (detect_fast.cuh) may replace the run-list engine for this NFA and these flags?
-// 0 = none, 1 = NK (no Kleene state), 2 = FK2 (`a+ b*`).  The conditions are exactly the ones the derivations in
+// 0 = none, 1 = NK (no Kleene state), 2 = FK2 (`a+ b*`), 3 = NP1 (one `+` state, no predicates).  The conditions are exactly the ones the derivations in
 // detect_fast.cuh rely on; anything else keeps the general engine.
 static int classify_fast(const siesta_nfa* nfa, const DevNfa& d, uint32_t flags) {
     if (flags & SIESTA_F_LITERAL_RUNS) return 0;
@@ -32,7 +32,17 @@ static int classify_fast(const siesta_nfa* nfa, const DevNfa& d, uint32_t flags)
             if (d.p_ref[1][k] != 0) return 0;
         return 2;
     }
-    return 0;
+    {   // NP1: positive states and exactly one kleeneClosure+ state, no predicate (after onlyAppearances)
+        int n_plus = 0;
+        for (int s = 0; s < S; ++s) {
+            if (nfa->states[s].kind == SIESTA_STATE_KLEENE_PLUS) ++n_plus;
+            else if (!positive(s)) return 0;
+            if (d.n_preds[s] != 0) return 0;
+        }
+        if (n_plus != 1 || S < 2) return 0;
+        if ((flags & SIESTA_F_RETURN_ALL) && !(flags & SIESTA_F_EVT_POS)) return 0;
+        return 3;
+    }
 }
 
 int validate_nfa(const siesta_nfa* nfa, uint32_t flags, DevNfa* out) {

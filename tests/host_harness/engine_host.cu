@@ -44,6 +44,15 @@ static int run_one(const DevNfa& dn, const std::vector<uint32_t>& meta, const st
         sel.assign(1, m);
         return 1;
     }
+    if (dn.fast_class == FAST_NP1) {
+        typename MaskOps<W>::T m = 0;
+        NkMasks<W> nm;
+        nm.init();
+        for (int j = 0; j < ev.n; ++j) nm.on_event(j, ev.word(j));
+        if (!np1_eval<W>(dn, nm.T, (flags & (SIESTA_F_RETURN_ALL | SIESTA_F_COUNT_MATCHES)) != 0, m, *n_emitted)) return 0;
+        sel.assign(1, m);
+        return 1;
+    }
     if (dn.fast_class == FAST_NK) {
         std::vector<typename MaskOps<W>::T> aux(NE), s(NE);
         int nsel = 0;

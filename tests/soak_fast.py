@@ -1,5 +1,5 @@
 """Randomized soak of the closed-form evaluators (detect_fast.cuh, host build) against the oracle.  Not collected by
-pytest; run `python tests/soak_fast.py <seed0> <n_seeds>`.  Draws only NFAs of the NK and FK2 classes (few activity
+pytest; run `python tests/soak_fast.py <seed0> <n_seeds>`.  Draws only NFAs of the NK, FK2 and NP1 classes (few activity
 types so that traces are dense in pattern events, ties and negatives are frequent)."""
 import sys
 
@@ -61,6 +61,22 @@ def fk2_nfa(rng, n_act):
     return [{"kind": P_, "types": [a], "preds": []}, {"kind": S_, "types": [b], "preds": preds}]
 
 
+def np1_nfa(rng, n_act):
+    """normal / or states and exactly one kleeneClosure+ state anywhere, no predicates; types may repeat."""
+    n = int(rng.integers(2, 7))
+    k = int(rng.integers(0, n))
+    states = []
+    for s in range(n):
+        if s == k:
+            kind = P_
+        else:
+            kind = O_ if rng.random() < 0.3 else N_
+        m = int(rng.integers(2, 4)) if kind == O_ else 1
+        types = [int(x) for x in rng.choice(n_act, size=min(m, n_act), replace=False)]
+        states.append({"kind": kind, "types": types, "preds": []})
+    return states
+
+
 def main(seed0, n_seeds):
     bad = 0
     stats = {"ok": 0, "err": 0, "unsupported": 0, "wide": 0, "matches": 0}
@@ -73,14 +89,18 @@ def main(seed0, n_seeds):
         if not sorted_ts:
             ts = ts.copy()
             rng.shuffle(ts)
-        fk2 = rng.random() < 0.4
-        states = fk2_nfa(rng, n_act) if fk2 else nk_nfa(rng, n_act)
+        which = rng.random()
+        fk2 = which < 0.25
+        np1 = 0.25 <= which < 0.6
+        states = fk2_nfa(rng, n_act) if fk2 else (np1_nfa(rng, n_act) if np1 else nk_nfa(rng, n_act))
+        if np1 and rng.random() < 0.15:    # any pattern under onlyAppearances is in the class as well
+            states[int(rng.integers(1, len(states)))]["preds"].append(rand_pred(rng, 0))
         flags = 0
         if rng.random() < 0.4:
             flags |= abi.F_EVT_POS
         if not fk2 and rng.random() < 0.4:
             flags |= abi.F_RETURN_ALL
-        if rng.random() < 0.1:
+        if rng.random() < 0.1 or (np1 and any(st["preds"] for st in states)):
             flags |= abi.F_ONLY_APPEARANCES
         if not fk2 and rng.random() < 0.2:
             flags |= abi.F_COUNT_MATCHES

@@ -57,3 +57,34 @@ def test_class_boundaries_fall_back_to_the_engine():
             want = oracle.detect(off, act, ts, nfa, flags=flags)
             ok, why = got.same_as(want)
             assert ok, (why, states, flags)
+
+
+def test_np1_is_the_first_start_with_every_kleene_event_the_suffix_allows():
+    """Class NP1 (one `+` state, no predicates): the first-largest occurrence and the engine's match count against the
+    oracle's FULL emission list on dense two- and three-letter streams (ties between starts, Kleene type repeated in
+    the prefix / suffix, Kleene state first / in the middle / last)."""
+    shapes = [
+        [dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[2])],            # a b+ c
+        [dict(kind=N_, types=[0]), dict(kind=P_, types=[1])],                                      # a b+
+        [dict(kind=P_, types=[0]), dict(kind=N_, types=[1])],                                      # a+ b
+        [dict(kind=P_, types=[0]), dict(kind=N_, types=[0]), dict(kind=N_, types=[1])],            # a+ a b
+        [dict(kind=N_, types=[1]), dict(kind=P_, types=[1]), dict(kind=N_, types=[1])],            # b b+ b
+        [dict(kind=N_, types=[0]), dict(kind=N_, types=[1]), dict(kind=P_, types=[0]), dict(kind=O_, types=[1, 2]), dict(kind=N_, types=[0])],
+    ]
+    rng = np.random.default_rng(23)
+    for states in shapes:
+        nfa = abi.make_nfa(states)
+        for _ in range(150):
+            n = int(rng.integers(2, 14))
+            types = rng.integers(0, 3, size=n).astype(np.int32)
+            ts_s = np.cumsum(rng.integers(0, 3, size=n))
+            _, matches = oracle.run_stream(nfa, types, np.arange(n), ts_s)
+            want = _first_largest(matches)
+            off = np.array([0, n], dtype=np.int64)
+            rc, got, _ = host_engine.detect(off, types, ts_s.astype(np.int64) * 1000, 3, nfa, flags=abi.F_COUNT_MATCHES)
+            assert rc == 0
+            if want is None:
+                assert got.n_traces == 0 and got.n_matches_emitted == 0
+            else:
+                assert got.as_dict() == {0: [want]}, (states, types.tolist())
+                assert got.n_matches_emitted == len(matches), (states, types.tolist())
