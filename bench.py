@@ -53,7 +53,7 @@ WORKLOADS = {
                                             dict(kind=abi.STATE_KLEENE_STAR, types=[1],
                                                  preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 600)])], e2e_traces=1_000_000),
     # Kleene patterns outside the a+ b* closed form: a b+ c has its own closed form since round 2
-    # (class NP1); with a constraint it stays on the run-list engine
+    # (class NP1), also with constraints that reference states before the `+` state
     "detection_abc_kleene_1Mx100": dict(n_traces=1_000_000, min_len=100, max_len=100, n_act=20, max_gap_s=120, seed=0x51E57A02,
                                         bytes_per_event=4, pattern="a b+ c (EventTs route, returnAll=false)",
                                         kernel="detect_kernel<W=1, FAST_NP1> (K1: filter + one-`+`-state closed form + staged output)",
@@ -61,7 +61,7 @@ WORKLOADS = {
                                                 dict(kind=abi.STATE_NORMAL, types=[2])], e2e_traces=1_000_000),
     "detection_abc_kleene_gap_1Mx100": dict(n_traces=1_000_000, min_len=100, max_len=100, n_act=20, max_gap_s=120, seed=0x51E57A02,
                                             bytes_per_event=4, pattern="a b+ c, gap within 20 (0,2) (EventTs route, returnAll=false)",
-                                            kernel="detect_kernel<FAST_NONE> (K1: filter + run-list engine)",
+                                            kernel="detect_kernel<W=1, FAST_NP1> (K1: filter + one-`+`-state closed form, every start on its filtered masks)",
                                             states=[dict(kind=abi.STATE_NORMAL, types=[0]), dict(kind=abi.STATE_KLEENE_PLUS, types=[1]),
                                                     dict(kind=abi.STATE_NORMAL, types=[2], preds=[(abi.ATTR_POSITION, abi.OP_LE, 0, 20)])],
                                             e2e_traces=1_000_000),

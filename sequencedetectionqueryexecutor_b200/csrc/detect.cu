@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(NT_MAX, (W == 1 && MODE != FAST_NONE) ? 5 : 4)
                     nkm.init();
                     for (int j = 0; j < ev.n; ++j) nkm.on_event(j, ev.word(j));
                     const bool count = (P.flags & (SIESTA_F_RETURN_ALL | SIESTA_F_COUNT_MATCHES)) != 0;
-                    if (np1_eval<W>(nfa, nkm.T, count, sel_local[0], n_emitted)) {
+                    if (nfa.need_vv ? np1p_eval<W>(nfa, ev, nkm.T, sel_local[0], n_emitted) : np1_eval<W>(nfa, nkm.T, count, sel_local[0], n_emitted)) {
                         status = ST_MATCH;
                         nsel = 1;
                     }

@@ -67,7 +67,18 @@
 //   k = 0: Engine.createNewRun :933-982 creates two runs per event a_j of the Kleene type, [a_j] moved on to state 1 and
 //   [a_j] staying, which takes every later a_l and leaves [a_j..a_l] at state 1 each time: matches (j, l >= j) =
 //   {a_j..a_l} + suffix(a_l); the largest, {all a up to the last one in F} + suffix, is unique.
-//   returnAll (Occurrences.java:74-87): every match starts at or after the largest one's first event and completes at
+//   Constraints that reference PREFIX states (k >= 1, every predicate's referenced state < k, none on state 0; first-largest
+//   only): the value vector is shared by a start run and all its clones (Run.clone is shallow), but the prefix slots
+//   never change once the prefix is complete and nobody writes the others (a slot is written only for referenced
+//   states), so the family of start i behaves as above on its own filtered masks: prefix walk with predicates as in
+//   class NK, B_i = the later Kleene events that pass state k's predicates against prefix_i, suffix states take the first
+//   later event that passes theirs.  The B_i are no longer nested, so all starts are evaluated: the largest m wins, then
+//   the earlier completion event, then the earlier place in the run list.  (i, m) sits where its lineage was last placed:
+//   pl(i, m) = {a_i, b_1 .. b_{m-1}}; a later placement is later in the list, clones placed at the same event keep their
+//   parents' order, and a start run is appended after the clones of its event (Engine.java:207-224: createNewRun follows
+//   the loop): with h = the highest event in pl(X) xor pl(Y), say in pl(X): Y precedes unless pl(Y) has nothing below h.
+//   (A predicate that references the Kleene state or a suffix state reads a slot that siblings overwrite: not taken.)
+//   returnAll (Occurrences.java:74-87), without constraints: every match starts at or after the largest one's first event and completes at
 //   or before its last (suffix completion is monotone in the position it starts from), so on the EventPos route, where
 //   Occurrence.overlaps compares positions, every other match overlaps it: the selection is the largest alone.  On the
 //   EventTs route overlaps compares timestamps, which the caller may hand over unsorted: not taken.
@@ -382,6 +393,93 @@ SIESTA_HD __forceinline__ bool np1_eval(const DevNfa& nfa, const typename MaskOp
         taken |= MO::bit(q);
     }
     out = taken;
+    return true;
+}
+
+// With constraints on prefix states (see the header): every start on its own filtered masks.
+template <int W, class EV>
+SIESTA_HD __forceinline__ bool np1p_eval(const DevNfa& nfa, const EV& ev, const typename MaskOps<W>::T* T, typename MaskOps<W>::T& out,
+                                         unsigned& n_emitted) {
+    typedef MaskX<W> MO;
+    typedef typename MO::T mask_t;
+    const int S = nfa.n_states;
+    n_emitted = 0;
+    int k = 0;
+    for (int s = 0; s < S; ++s) {
+        if (T[s] == 0) return false;
+        if (nfa.kind[s] == SIESTA_STATE_KLEENE_PLUS) k = s;
+    }
+    mask_t best = 0, best_pl = 0;
+    int best_m = 0, best_c = 0;
+    for (mask_t r = T[0]; r; r &= r - 1) {
+        const int s0 = MO::lo(r);
+        unsigned long long vvw = (unsigned long long)s0;  // byte j = event taken for prefix state j
+        auto vv = [&vvw](int ref) { return (int)((vvw >> (8 * ref)) & 0xFF); };
+        mask_t taken = MO::bit(s0);
+        int p = s0;
+        bool ok = true;
+        for (int j = 1; j < k && ok; ++j) {
+            mask_t c = T[j] & MO::above(p);
+            int got = -1;
+            while (c) {
+                const int e = MO::lo(c);
+                c &= c - 1;
+                if (fast_preds(nfa, ev, j, e, j, vv)) { got = e; break; }
+            }
+            if (got < 0) { ok = false; break; }
+            taken |= MO::bit(got);
+            vvw |= (unsigned long long)got << (8 * j);
+            p = got;
+        }
+        if (!ok) continue;
+        mask_t B = 0;
+        for (mask_t c = T[k] & MO::above(p); c; c &= c - 1) {
+            const int e = MO::lo(c);
+            if (fast_preds(nfa, ev, k, e, k, vv)) B |= MO::bit(e);
+        }
+        if (!B) continue;
+        // latest embedding of the suffix: the Kleene events below its first event can complete
+        mask_t F = ~(mask_t)0;
+        for (int j = S - 1; j > k && ok; --j) {
+            mask_t c = T[j] & F;
+            int got = -1;
+            while (c) {
+                const int e = MO::hi(c);
+                c &= ~MO::bit(e);
+                if (fast_preds(nfa, ev, j, e, j, vv)) { got = e; break; }
+            }
+            if (got < 0) { ok = false; break; }
+            F = MO::below(got);
+        }
+        if (!ok) continue;
+        B &= F;
+        const int m = MO::popc(B);
+        if (!m) continue;
+        n_emitted += (unsigned)m;
+        if (m < best_m) continue;
+        int q = MO::hi(B);
+        const mask_t pl = MO::bit(s0) | (B & ~MO::bit(q));
+        taken |= B;
+        for (int j = k + 1; j < S; ++j) {
+            mask_t c = T[j] & MO::above(q);
+            while (c) {   // exists: q lies in F
+                const int e = MO::lo(c);
+                c &= c - 1;
+                if (fast_preds(nfa, ev, j, e, j, vv)) { q = e; break; }
+            }
+            taken |= MO::bit(q);
+        }
+        bool better = m > best_m || q < best_c;
+        if (!better && q == best_c) {   // same size, same completion event: the run list's order
+            const mask_t d = pl ^ best_pl;
+            const int h = MO::hi(d);
+            if ((pl >> h) & 1) better = (best_pl & MO::below(h)) == 0;
+            else better = (pl & MO::below(h)) != 0;
+        }
+        if (better) { best = taken; best_pl = pl; best_m = m; best_c = q; }
+    }
+    if (!best) return false;
+    out = best;
     return true;
 }
 

@@ -32,14 +32,18 @@ static int classify_fast(const siesta_nfa* nfa, const DevNfa& d, uint32_t flags)
             if (d.p_ref[1][k] != 0) return 0;
         return 2;
     }
-    {   // NP1: positive states and exactly one kleeneClosure+ state, no predicate (after onlyAppearances)
-        int n_plus = 0;
+    {   // NP1: positive states and exactly one kleeneClosure+ state; predicates (after onlyAppearances) only reference
+        // states before the Kleene state
+        int n_plus = 0, k = 0;
         for (int s = 0; s < S; ++s) {
-            if (nfa->states[s].kind == SIESTA_STATE_KLEENE_PLUS) ++n_plus;
+            if (nfa->states[s].kind == SIESTA_STATE_KLEENE_PLUS) { ++n_plus; k = s; }
             else if (!positive(s)) return 0;
-            if (d.n_preds[s] != 0) return 0;
         }
-        if (n_plus != 1 || S < 2) return 0;
+        if (n_plus != 1 || S < 2 || d.n_preds[0] != 0) return 0;
+        for (int s = 0; s < S; ++s)
+            for (int q = 0; q < d.n_preds[s]; ++q)
+                if (d.p_ref[s][q] >= k) return 0;
+        if (d.need_vv) return (flags & SIESTA_F_RETURN_ALL) ? 0 : 3;
         if ((flags & SIESTA_F_RETURN_ALL) && !(flags & SIESTA_F_EVT_POS)) return 0;
         return 3;
     }

@@ -49,7 +49,8 @@ static int run_one(const DevNfa& dn, const std::vector<uint32_t>& meta, const st
         NkMasks<W> nm;
         nm.init();
         for (int j = 0; j < ev.n; ++j) nm.on_event(j, ev.word(j));
-        if (!np1_eval<W>(dn, nm.T, (flags & (SIESTA_F_RETURN_ALL | SIESTA_F_COUNT_MATCHES)) != 0, m, *n_emitted)) return 0;
+        if (!(dn.need_vv ? np1p_eval<W>(dn, ev, nm.T, m, *n_emitted)
+                         : np1_eval<W>(dn, nm.T, (flags & (SIESTA_F_RETURN_ALL | SIESTA_F_COUNT_MATCHES)) != 0, m, *n_emitted))) return 0;
         sel.assign(1, m);
         return 1;
     }

@@ -74,6 +74,11 @@ def np1_nfa(rng, n_act):
         m = int(rng.integers(2, 4)) if kind == O_ else 1
         types = [int(x) for x in rng.choice(n_act, size=min(m, n_act), replace=False)]
         states.append({"kind": kind, "types": types, "preds": []})
+    if k >= 1 and rng.random() < 0.6:   # constraints that reference states before the Kleene state
+        for _ in range(int(rng.integers(1, 4))):
+            b = int(rng.integers(1, n))
+            if len(states[b]["preds"]) < abi.MAX_PREDS:
+                states[b]["preds"].append(rand_pred(rng, int(rng.integers(0, min(b, k)))))
     return states
 
 
@@ -93,14 +98,17 @@ def main(seed0, n_seeds):
         fk2 = which < 0.25
         np1 = 0.25 <= which < 0.6
         states = fk2_nfa(rng, n_act) if fk2 else (np1_nfa(rng, n_act) if np1 else nk_nfa(rng, n_act))
-        if np1 and rng.random() < 0.15:    # any pattern under onlyAppearances is in the class as well
-            states[int(rng.integers(1, len(states)))]["preds"].append(rand_pred(rng, 0))
+        only = False
+        if np1 and rng.random() < 0.1:    # any pattern under onlyAppearances is in the class as well
+            b = int(rng.integers(1, len(states)))
+            states[b]["preds"].append(rand_pred(rng, int(rng.integers(0, b + 1))))
+            only = True
         flags = 0
         if rng.random() < 0.4:
             flags |= abi.F_EVT_POS
-        if not fk2 and rng.random() < 0.4:
+        if not fk2 and rng.random() < (0.15 if np1 else 0.4):
             flags |= abi.F_RETURN_ALL
-        if rng.random() < 0.1 or (np1 and any(st["preds"] for st in states)):
+        if rng.random() < 0.1 or only:
             flags |= abi.F_ONLY_APPEARANCES
         if not fk2 and rng.random() < 0.2:
             flags |= abi.F_COUNT_MATCHES

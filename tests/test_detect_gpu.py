@@ -596,6 +596,10 @@ NP1_SHAPES = [
     ("a+ b", [dict(kind=P_, types=[0]), dict(kind=N_, types=[1])]),
     ("a (b|c) d+ (a|e) b", [dict(kind=N_, types=[0]), dict(kind=O_, types=[1, 2]), dict(kind=P_, types=[3]), dict(kind=O_, types=[0, 4]), dict(kind=N_, types=[1])]),
     ("b b+ b", [dict(kind=N_, types=[1]), dict(kind=P_, types=[1]), dict(kind=N_, types=[1])]),
+    ("a b+ c, gap within 6 (0,2)", [dict(kind=N_, types=[0]), dict(kind=P_, types=[1]),
+                                    dict(kind=N_, types=[2], preds=[(abi.ATTR_POSITION, abi.OP_LE, 0, 6)])]),
+    ("a c b+ a, b within 200 s of a, last a at least 3 after c", [dict(kind=N_, types=[0]), dict(kind=N_, types=[2]),
+        dict(kind=P_, types=[1], preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 200)]), dict(kind=N_, types=[0], preds=[(abi.ATTR_POSITION, abi.OP_GE, 1, 3)])]),
     ("a b+ c, constraints dropped by onlyAppearances", [dict(kind=N_, types=[0]), dict(kind=P_, types=[1]),
                                                          dict(kind=N_, types=[2], preds=[(abi.ATTR_POSITION, abi.OP_LE, 0, 3)])]),
 ]
@@ -605,7 +609,7 @@ NP1_SHAPES = [
 def test_one_kleene_plus_state_without_constraints_closed_form(ctx, name, states):
     """Class NP1 (detect_fast.cuh): the closed form replaces the run-list engine; occurrences, the engine's match count
     and the listed outliers (more than 64 relevant events) against the oracle, narrow and wide configuration."""
-    only = abi.F_ONLY_APPEARANCES if any(s.get("preds") for s in states) else 0
+    only = abi.F_ONLY_APPEARANCES if "onlyAppearances" in name else 0
     for n_act, max_len in ((5, 30), (7, 120), (3, 90)):
         off, act, ts = gen.make_log(3000, 0, max_len, n_act, seed=77 + n_act, max_gap_s=100, jitter_ms=True)
         for flags in (0, abi.F_COUNT_MATCHES, abi.F_EVT_POS, abi.F_EVT_POS | abi.F_RETURN_ALL, abi.F_NO_EVENT_COLUMNS):

@@ -88,3 +88,30 @@ def test_np1_is_the_first_start_with_every_kleene_event_the_suffix_allows():
             else:
                 assert got.as_dict() == {0: [want]}, (states, types.tolist())
                 assert got.n_matches_emitted == len(matches), (states, types.tolist())
+
+
+@pytest.mark.parametrize("seed0", [900, 1420])
+def test_np1_constraints_on_prefix_states_and_the_run_list_order(seed0):
+    """Class NP1 with time constraints that reference prefix states on UNSORTED timestamps: the starts' Kleene-event sets
+    are not nested, equal sizes completing at the same event are decided by the run list's order (seeds 919 and 1431 are
+    decided by it: a later start's run sits earlier in the list)."""
+    for seed in range(seed0, seed0 + 40):
+        rng = np.random.default_rng(seed)
+        n_act = int(rng.integers(2, 4))
+        off, act, ts = gen.make_log(60, 3, int(rng.integers(6, 30)), n_act, seed=int(rng.integers(1 << 30)), max_gap_s=20)
+        ts = ts.copy()
+        rng.shuffle(ts)
+        k = int(rng.integers(1, 3))
+        n = k + 1 + int(rng.integers(0, 2))
+        states = [dict(kind=P_ if s == k else N_, types=[int(rng.integers(0, n_act))], preds=[]) for s in range(n)]
+        for _ in range(int(rng.integers(1, 4))):
+            b = int(rng.integers(k, n))
+            if len(states[b]["preds"]) < 4:
+                states[b]["preds"].append((abi.ATTR_TIMESTAMP, abi.OP_LE if rng.random() < 0.5 else abi.OP_GE,
+                                           int(rng.integers(0, k)), int(rng.integers(0, 400))))
+        flags = abi.F_COUNT_MATCHES if rng.random() < 0.5 else 0
+        nfa = abi.make_nfa(states)
+        rc, got, _ = host_engine.detect(off, act, ts, n_act, nfa, flags=flags)
+        assert rc == 0
+        ok, why = got.same_as(oracle.detect(off, act, ts, nfa, flags=flags))
+        assert ok, (seed, why, states)
