@@ -428,7 +428,8 @@ void siesta_device_free(siesta_log* log, void* d_ptr);
  * countResponseChain :83-89, countPrecedenceChain :96-102).
  * (meaning of each block: oracle/counting_oracle.cpp).  Supports and thresholds (one double division each:
  * QueryPlanExistences templates :188-438, QueryPlanOrderedRelations.filterBasedOnSupport :161-233) stay with
- * the caller.  n_activities <= 104 (the A x A matrices live in shared memory). */
+ * the caller.  n_activities <= 4096 (the result itself: eight A x A int64 matrices = 1 GB); alphabets above 104
+ * activities use a kernel that works on the distinct activities of each trace, any trace length. */
 int64_t siesta_declare_counts_size(int32_t n_activities, int32_t k_cap);
 int siesta_declare_counts(siesta_log* log, int32_t k_cap, int64_t* out /* host, _size() values */, double* kernel_ms);
 int siesta_declare_counts_device(siesta_log* log, int32_t k_cap, int64_t* d_out /* device */, void* stream,

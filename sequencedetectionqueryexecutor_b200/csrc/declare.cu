@@ -25,7 +25,8 @@ namespace siesta {
 
 constexpr int DT = 256;      // threads per CTA
 constexpr int HS = 16;       // histogram buckets kept in shared memory (k < HS)
-constexpr int MAX_A_SMEM = 104;
+constexpr int MAX_A_SMEM = 104;   // the serial kernels keep four A x A matrices in shared memory
+constexpr int MAX_A_ANY = 4096;   // declare_any_kernel: bounded by the result itself (8 A^2 int64 = 1 GB)
 
 struct DeclareParams {
     const int64_t* trace_off;
@@ -515,6 +516,145 @@ __global__ void __launch_bounds__(256, 3) declare_pairs_kernel(const __grid_cons
     }
 }
 
+// ---------------------------------------------------------------------------------- K3 for ANY alphabet and trace length
+// More than MAX_A_SMEM activities: the A x A matrices no longer fit in shared memory, and a trace only ever holds a small
+// part of the alphabet.  One warp per trace; the warp keeps its per-activity state (count, first, last, slot) and the list
+// of the trace's DISTINCT activities (with running count and last position per slot) in a private slice of a global scratch
+// (plain loads / stores: the slice is only touched by this warp), and every loop that was "lanes = activities" in the
+// kernels above becomes "lanes = distinct activities of this trace".  Counts go to the output with 64-bit atomics.  Same
+// definitions, same order of the serial pass: pass 1 counts, pass 2 existence + presence, pass 3 response / precedence at
+// the first / last occurrences, alternate at every event, chain on adjacent events.
+struct DeclareAnyParams {
+    DeclareParams d;
+    uint32_t* scratch;   // [warps][7][A]
+};
+
+__global__ void __launch_bounds__(DT) declare_any_kernel(const __grid_constant__ DeclareAnyParams Q) {
+    const DeclareParams& P = Q.d;
+    const int A = P.A;
+    const long long AA = (long long)A * A;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * (DT / 32) + warp, warps_total = (long long)gridDim.x * (DT / 32);
+    uint32_t* w_cnt = Q.scratch + gw * 7 * A;   // zero outside a trace
+    uint32_t* w_first = w_cnt + A;
+    uint32_t* w_last = w_first + A;
+    uint32_t* w_slot = w_last + A;              // activity -> slot in the distinct list
+    uint32_t* w_act = w_slot + A;               // slot -> activity
+    uint32_t* w_run = w_act + A;                // slot -> occurrences so far (pass 3)
+    int* w_lastpos = reinterpret_cast<int*>(w_run + A);   // slot -> last position so far (pass 3)
+
+    unsigned long long* o_tot = P.out;
+    unsigned long long* o_uniq = o_tot + A;
+    unsigned long long* o_first = o_uniq + A;
+    unsigned long long* o_last = o_first + A;
+    unsigned long long* o_hist = o_last + A;
+    unsigned long long* o_co = o_hist + (long long)A * (P.k_cap + 1);
+    unsigned long long* o_ord = o_co + AA;
+    unsigned long long* o_resp = o_ord + AA;
+    unsigned long long* o_prec = o_resp + AA;
+    unsigned long long* o_alt = o_prec + AA;          // alternate response; the precedence copy is made by the host call
+    unsigned long long* o_chain = o_alt + 2 * AA;     // chain response; likewise
+
+    unsigned long long n_nonempty = 0, n_hist_ovf = 0;
+    for (long long t = gw; t < P.n_traces; t += warps_total) {
+        long long lo = 0, hi = 0;
+        if (lane == 0) { lo = P.trace_off[t]; hi = P.trace_off[t + 1]; }
+        lo = shfl64(lo, 0);
+        hi = shfl64(hi, 0);
+        if (hi <= lo) continue;
+        const long long len = hi - lo;
+        ++n_nonempty;
+        // pass 1: count / first / last per activity, list of distinct activities (in order of first occurrence)
+        int d = 0;
+        for (long long base = 0; base < len; base += 32) {
+            const int x = base + lane < len ? __ldg(P.act + lo + base + lane) : -1;
+            const bool valid = x >= 0 && x < A;
+            const unsigned grp = __match_any_sync(0xffffffffu, valid ? x : A + lane);
+            const bool leader = valid && lane == __ffs(grp) - 1;
+            uint32_t c = 0;
+            if (leader) c = w_cnt[x];
+            const bool is_new = leader && c == 0;
+            const unsigned nb = __ballot_sync(0xffffffffu, is_new);
+            if (leader) {
+                if (is_new) {
+                    const int sl = d + __popc(nb & ((1u << lane) - 1u));
+                    w_first[x] = (uint32_t)(base + lane);
+                    w_slot[x] = (uint32_t)sl;
+                    w_act[sl] = (uint32_t)x;
+                    w_run[sl] = 0;
+                    w_lastpos[sl] = -1;
+                }
+                w_cnt[x] = c + (uint32_t)__popc(grp);
+                w_last[x] = (uint32_t)(base + 31 - __clz(grp));
+            }
+            d += __popc(nb);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            const int xf = __ldg(P.act + lo), xl = __ldg(P.act + hi - 1);
+            if (xf >= 0 && xf < A) atomicAdd(o_first + xf, 1ull);
+            if (xl >= 0 && xl < A) atomicAdd(o_last + xl, 1ull);
+        }
+        // pass 2: existence counts and the presence matrices
+        for (int j = lane; j < d; j += 32) {
+            const int b = (int)w_act[j];
+            const uint32_t c = w_cnt[b];
+            atomicAdd(o_tot + b, (unsigned long long)c);
+            atomicAdd(o_uniq + b, 1ull);
+            if (c > (uint32_t)P.k_cap) ++n_hist_ovf;
+            else atomicAdd(o_hist + (long long)b * (P.k_cap + 1) + c, 1ull);
+            if (c >= 2) { atomicAdd(o_ord + (long long)b * A + b, 1ull); atomicAdd(o_co + (long long)b * A + b, 1ull); }
+        }
+        for (int ai = 0; ai < d; ++ai) {
+            const int a = (int)w_act[ai];
+            const uint32_t fa = w_first[a];
+            for (int j = lane; j < d; j += 32) {
+                if (j == ai) continue;
+                const int b = (int)w_act[j];
+                atomicAdd(o_co + (long long)a * A + b, 1ull);
+                if (fa < w_last[b]) atomicAdd(o_ord + (long long)a * A + b, 1ull);
+            }
+        }
+        // pass 3: serial over the events
+        int px = -1;
+        for (long long base = 0; base < len; base += 32) {
+            const int mine = base + lane < len ? __ldg(P.act + lo + base + lane) : -1;
+            const int n_here = len - base < 32 ? (int)(len - base) : 32;
+            for (int k = 0; k < n_here; ++k) {
+                const int x = __shfl_sync(0xffffffffu, mine, k);
+                const long long i = base + k;
+                if (x < 0 || x >= A) { px = -1; continue; }
+                const int sx = (int)w_slot[x];
+                const bool is_last = w_last[x] == (uint32_t)i, is_first = w_first[x] == (uint32_t)i;
+                const int prev = w_lastpos[sx];
+                for (int j = lane; j < d; j += 32) {
+                    if (j == sx) continue;
+                    const int o = (int)w_act[j];
+                    const uint32_t r = w_run[j];
+                    if (is_last && r) atomicAdd(o_resp + (long long)o * A + x, (unsigned long long)r);                       // response[o][x]
+                    if (is_first) {
+                        const uint32_t co = w_cnt[o];
+                        if (co > r) atomicAdd(o_prec + (long long)x * A + o, (unsigned long long)(co - r));                  // precedence[x][o]
+                    }
+                    if (w_lastpos[j] > prev) atomicAdd(o_alt + (long long)o * A + x, 1ull);                                  // alternate[o][x]
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    w_run[sx] += 1;
+                    w_lastpos[sx] = (int)i;
+                    if (px >= 0 && px != x) atomicAdd(o_chain + (long long)px * A + x, 1ull);
+                }
+                px = x;
+                __syncwarp();
+            }
+        }
+        for (int j = lane; j < d; j += 32) w_cnt[w_act[j]] = 0;
+        __syncwarp();
+    }
+    if (lane == 0 && n_nonempty) atomicAdd(o_prec + 5 * AA + 1, n_nonempty);
+    if (n_hist_ovf) atomicAdd(o_prec + 5 * AA, n_hist_ovf);
+}
+
 __global__ void max_trace_len_kernel(const int64_t* trace_off, int64_t n_traces, unsigned long long* out) {
     unsigned long long m = 0;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_traces; t += (int64_t)gridDim.x * blockDim.x) {
@@ -595,8 +735,8 @@ extern "C" int siesta_declare_counts_device(siesta_log* log, int32_t k_cap, int6
     }
     Log* L = reinterpret_cast<Log*>(log);
     const int A = L->n_activities;
-    if (A < 1 || A > MAX_A_SMEM) {
-        set_error("declare counting keeps the A x A matrices in shared memory: 1 <= n_activities <= " + std::to_string(MAX_A_SMEM));
+    if (A < 1 || A > MAX_A_ANY) {
+        set_error("declare counting: 1 <= n_activities <= " + std::to_string(MAX_A_ANY) + " (the eight A x A count matrices of the result)");
         return SIESTA_E_UNSUPPORTED;
     }
     SIESTA_CUDA_OK(cudaSetDevice(L->ctx->device));
@@ -630,7 +770,31 @@ extern "C" int siesta_declare_counts_device(siesta_log* log, int32_t k_cap, int6
     }
     SIESTA_CUDA_OK(cudaEventRecord(e0, stream));
     const bool pairs_path = A <= 32 && L->true_max_len <= 128 && std::getenv("SIESTA_K3_SERIAL") == nullptr;
-    if (pairs_path) {
+    if (A > MAX_A_SMEM || std::getenv("SIESTA_K3_ANY") != nullptr) {
+        // any alphabet, any trace length: lanes = the distinct activities of a trace, counts by 64-bit atomics
+        const int64_t ctas_needed = (L->n_traces + DT / 32 - 1) / (DT / 32);
+        const int grid = (int)std::min<int64_t>(std::max<int64_t>(ctas_needed, 1), (int64_t)L->ctx->sm_count * 2);
+        const size_t sbytes = sizeof(uint32_t) * (size_t)grid * (DT / 32) * 7 * A;
+        void* scratch = dev_arena_alloc(L->ctx, sbytes);
+        if (!scratch) return SIESTA_E_NOMEM;
+        SIESTA_CUDA_OK(cudaMemsetAsync(scratch, 0, sbytes, stream));
+        DeclareAnyParams Q;
+        Q.d = P;
+        Q.scratch = reinterpret_cast<uint32_t*>(scratch);
+        declare_any_kernel<<<grid, DT, 0, stream>>>(Q);
+        SIESTA_LAUNCHED();
+        cudaError_t e = cudaGetLastError();
+        const size_t aa = sizeof(int64_t) * (size_t)A * A;
+        int64_t* o_alt = d_out + 4ll * A + (int64_t)A * (k_cap + 1) + 4ll * A * A;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(o_alt + (size_t)A * A, o_alt, aa, cudaMemcpyDeviceToDevice, stream);                      // alternate precedence = response
+        if (e == cudaSuccess) e = cudaMemcpyAsync(o_alt + 3 * (size_t)A * A, o_alt + 2 * (size_t)A * A, aa, cudaMemcpyDeviceToDevice, stream);  // chain likewise
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        dev_arena_free(L->ctx, scratch);
+        if (e != cudaSuccess) {
+            set_error(std::string("declare_any_kernel: ") + cudaGetErrorString(e));
+            return SIESTA_E_CUDA;
+        }
+    } else if (pairs_path) {
         // one kernel: position masks + pair-owned counters
         const int n_pairs = A * (A - 1) / 2;
         const int ppt = n_pairs > 256 ? 2 : 1;

@@ -23,7 +23,10 @@ def ctx():
                                                       # <= 64 / <= 128 events per trace; one event more falls back
                                                       (32, 2500, (0, 64), None), (24, 2000, (60, 64), 1.1), (23, 1500, (0, 128), None),
                                                       (32, 900, (100, 128), 1.1), (2, 3000, (0, 40), None), (1, 500, (0, 9), None),
-                                                      (20, 800, (0, 129), None), (7, 4099, (33, 33), None)])
+                                                      (20, 800, (0, 129), None), (7, 4099, (33, 33), None),
+                                                      # more than 104 activities: declare_any_kernel (lanes = the distinct
+                                                      # activities of a trace, counts by global atomics), any trace length
+                                                      (105, 1200, (0, 80), None), (600, 800, (20, 400), 1.1), (1500, 300, (0, 2500), 1.05)])
 def test_declare_counts_match_oracle(ctx, n_act, n_traces, lens, zipf):
     off, act, ts = gen.make_log(n_traces, lens[0], lens[1], n_act, seed=100 + n_act, zipf=zipf)
     log = ctx.load_log(off, act, ts, n_act)
@@ -44,10 +47,24 @@ def test_declare_counts_histogram_cap_and_limits(ctx):
     want = oracle.declare_counts(off, act, 4, 5)
     log.close()
     assert np.array_equal(got.packed, want.packed) and got.hist_overflow > 0
-    log = ctx.load_log(*gen.make_log(10, 5, 5, 200, seed=8), 200)
+    log = ctx.load_log(*gen.make_log(10, 5, 5, 5000, seed=8), 5000)   # the eight A x A matrices of the result bound the alphabet (4096)
     with pytest.raises(SiestaError):
         log.declare_counts()
     log.close()
+
+
+@pytest.mark.parametrize("n_act,lens", [(5, (0, 30)), (40, (0, 150)), (100, (10, 60))])
+def test_declare_counts_any_alphabet_kernel_equals_the_others(ctx, n_act, lens, monkeypatch):
+    """SIESTA_K3_ANY forces declare_any_kernel on alphabets the shared-memory kernels also take: all three agree with the oracle."""
+    off, act, ts = gen.make_log(1500, lens[0], lens[1], n_act, seed=200 + n_act, zipf=1.1)
+    want = oracle.declare_counts(off, act, n_act, 30)
+    log = ctx.load_log(off, act, ts, n_act)
+    a = log.declare_counts(k_cap=30)
+    monkeypatch.setenv("SIESTA_K3_ANY", "1")
+    b = log.declare_counts(k_cap=30)
+    log.close()
+    assert np.array_equal(a.packed, want.packed)
+    assert np.array_equal(b.packed, want.packed)
 
 
 @pytest.mark.parametrize("n_act,n_traces,lens", [(5, 2000, (0, 12)), (20, 20000, (30, 50)), (3, 777, (0, 4))])
