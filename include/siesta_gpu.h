@@ -165,6 +165,16 @@ int siesta_log_wrap_device(siesta_ctx* ctx, const int64_t* d_trace_off, const in
 /* Multi-GPU: this log is the shard [first_trace, first_trace + n_traces) of a larger log.  Every trace index the
  * library RETURNS for it (trace_idx, err_trace_idx) is then global; candidate lists stay local to the shard. */
 void siesta_log_set_first_trace(siesta_log* log, int64_t first_trace);
+/* Multi-GPU, block-cyclic shard: the log is cut into n_blocks * world blocks of consecutive traces and rank r holds
+ * blocks r, world + r, 2 world + r, ... back to back.  Block b of THIS shard = its local traces
+ * [local_first[b], local_first[b + 1]) = the global traces starting at global_first[b] (local_first[0] = 0,
+ * local_first[n_blocks] = the shard's trace count, 1 <= n_blocks <= SIESTA_MAX_BLOCKS, the same on every rank).
+ * siesta_detect_allgather then runs block by block: while block b + 1 is verified, block b of every rank is already
+ * pulled over NVLink and decoded at its place in the joined list, which stays in global trace order (block 0 of rank
+ * 0, 1, ..., block 1 of rank 0, ...).  Other entry points keep reporting first_trace + local index for such a log.
+ * n_blocks = 0 clears the declaration. */
+#define SIESTA_MAX_BLOCKS 16
+int siesta_log_set_blocks(siesta_log* log, int32_t n_blocks, const int64_t* local_first, const int64_t* global_first);
 void siesta_log_free(siesta_log* log);
 int64_t siesta_log_n_traces(const siesta_log* log);
 int64_t siesta_log_n_events(const siesta_log* log);
@@ -342,13 +352,26 @@ typedef struct siesta_exchange_stats {
     double wait_ms;  /* announce + wait for the slowest rank + fetch of the headers                               */
     double pull_ms;  /* pull + decode of all blocks into the joined columns                                       */
     double host_gap_ms; /* between the two: the host reads the sizes and allocates the joined result              */
+    /* block-pipelined requests (siesta_log_set_blocks): scan_ms spans all blocks, pull_ms is what the join adds behind
+     * the last block's announcement (wait_ms and host_gap_ms are 0), join_ms the span of the join stream */
+    double join_ms;
+    int32_t n_blocks; /* blocks the shard was processed in (1 = contiguous shard)                                 */
+    int32_t eager;    /* 1: joined columns allocated for the worst case up front and filled block by block         */
 } siesta_exchange_stats;
 
 /* siesta_detect_device over this rank's shard FOLLOWED BY the all-gather: `out` holds the match list of ALL ranks in
  * trace order (global trace indices), in the library's standard columns, on this rank's device.  The verification
  * kernels place their result directly into the exchange region as a compact block whose header carries the sizes;
  * one kernel then pulls every peer's block over NVLink and decodes it at its place in the joined list.  The host
- * waits twice (sizes of all blocks; end of the request).  An error on any rank fails the call on every rank. */
+ * waits twice (sizes of the first blocks; end of the request).  An error on any rank fails the call on every rank.
+ * Block-cyclic shards (siesta_log_set_blocks): the scan, the placement and the announcement of block b + 1 run on one
+ * stream while a second stream waits for block b of every rank, pulls and decodes it - the join overlaps the scan.
+ * When every match has the same shape (no Kleene state, first-largest occurrence) the joined columns are allocated
+ * for the worst case up front (every trace of every shard matches; the shard sizes travel in the headers) and filled
+ * block by block at running offsets computed on the device: `out`'s arrays are then compact, but they sit at
+ * capacity-based offsets inside d_block.  Other requests on a blocked log decode after the last block (exact
+ * allocation), so only their pulls' latency is hidden.  SIESTA_XCHG_EAGER_MAX_BYTES (default 24 GiB) bounds the
+ * worst-case allocation; above it the request decodes after the last block. */
 int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, uint32_t flags, siesta_exchange* x,
                             siesta_dev_matches* out, siesta_exchange_stats* stats /* may be NULL */);
 

@@ -76,7 +76,8 @@ class DevMatches(C.Structure):
 
 class ExchangeStats(C.Structure):
     _fields_ = [("local_traces", C.c_int64), ("local_occurrences", C.c_int64), ("local_events", C.c_int64),
-                ("pulled_bytes", C.c_int64), ("k1_ms", C.c_double), ("scan_ms", C.c_double), ("wait_ms", C.c_double), ("pull_ms", C.c_double), ("host_gap_ms", C.c_double)]
+                ("pulled_bytes", C.c_int64), ("k1_ms", C.c_double), ("scan_ms", C.c_double), ("wait_ms", C.c_double), ("pull_ms", C.c_double), ("host_gap_ms", C.c_double),
+                ("join_ms", C.c_double), ("n_blocks", C.c_int32), ("eager", C.c_int32)]
 
 
 EXCHANGE_HANDLE_BYTES = 64

@@ -18,7 +18,7 @@ EXPORTS = [
     "siesta_index_load", "siesta_index_build", "siesta_index_free", "siesta_index_list_len", "siesta_index_get_list",
     "siesta_intersect", "siesta_intersect_device", "siesta_device_free", "siesta_pattern_extract_pairs",
     "siesta_candidates", "siesta_candidates_device", "siesta_pair_stats", "siesta_pair_stats_device",
-    "siesta_explore_accurate", "siesta_log_set_first_trace",
+    "siesta_explore_accurate", "siesta_log_set_first_trace", "siesta_log_set_blocks",
     "siesta_packed_block_bytes", "siesta_dev_matches_pack",
     "siesta_exchange_create", "siesta_exchange_export", "siesta_exchange_import", "siesta_exchange_connect_local",
     "siesta_exchange_free", "siesta_exchange_required_bytes", "siesta_detect_allgather", "siesta_exchange_allreduce_i64",
@@ -56,6 +56,7 @@ def lib():
     L.siesta_dev_matches_pack.argtypes = [vp, P(_abi.DevMatches), u32, i64, vp, i64, vp]
     L.siesta_log_set_first_trace.argtypes = [vp, i64]
     L.siesta_log_set_first_trace.restype = None
+    L.siesta_log_set_blocks.argtypes = [vp, i32, P(i64), P(i64)]
     L.siesta_log_free.argtypes = [vp]
     L.siesta_log_free.restype = None
     L.siesta_log_n_traces.argtypes = [vp]

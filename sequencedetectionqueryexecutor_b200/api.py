@@ -118,6 +118,15 @@ class EventLog:
         """This log is the shard starting at global trace `first_trace`: returned trace indices become global."""
         lib().siesta_log_set_first_trace(self._h, int(first_trace))
 
+    def set_blocks(self, local_first, global_first):
+        """siesta_log_set_blocks: this log is a block-cyclic shard; block b = local traces [local_first[b], local_first[b + 1])
+        = the global traces starting at global_first[b].  Exchange.detect_allgather then overlaps the join with the scan."""
+        n = len(global_first)
+        assert len(local_first) == n + 1
+        lf = (C.c_int64 * (n + 1))(*[int(v) for v in local_first])
+        gf = (C.c_int64 * max(n, 1))(*[int(v) for v in global_first])
+        check(lib().siesta_log_set_blocks(self._h, n, lf, gf))
+
     def close(self):
         if self._h:
             lib().siesta_log_free(self._h)

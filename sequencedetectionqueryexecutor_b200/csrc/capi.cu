@@ -298,6 +298,26 @@ extern "C" void siesta_log_set_first_trace(siesta_log* log, int64_t first_trace)
     if (log) reinterpret_cast<Log*>(log)->first_trace = first_trace;
 }
 
+extern "C" int siesta_log_set_blocks(siesta_log* log, int32_t n_blocks, const int64_t* local_first, const int64_t* global_first) {
+    Log* L = reinterpret_cast<Log*>(log);
+    if (!L || n_blocks < 0 || n_blocks > SIESTA_MAX_BLOCKS || (n_blocks > 0 && (!local_first || !global_first))) {
+        set_error("siesta_log_set_blocks: bad argument (0 <= n_blocks <= SIESTA_MAX_BLOCKS)");
+        return SIESTA_E_INVALID;
+    }
+    if (n_blocks > 0) {
+        bool ok = local_first[0] == 0 && local_first[n_blocks] == L->n_traces;
+        for (int b = 0; b < n_blocks && ok; ++b) ok = local_first[b] <= local_first[b + 1] && global_first[b] >= 0;
+        if (!ok) {
+            set_error("siesta_log_set_blocks: local_first must ascend from 0 to the shard's trace count, global_first >= 0");
+            return SIESTA_E_INVALID;
+        }
+        for (int b = 0; b <= n_blocks; ++b) L->blk_local[b] = local_first[b];
+        for (int b = 0; b < n_blocks; ++b) L->blk_global[b] = global_first[b];
+    }
+    L->n_blocks = n_blocks;
+    return SIESTA_OK;
+}
+
 extern "C" void siesta_log_free(siesta_log* log) {
     if (!log) return;
     Log* L = reinterpret_cast<Log*>(log);

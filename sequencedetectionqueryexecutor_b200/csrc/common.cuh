@@ -79,6 +79,11 @@ struct Log {
     int64_t true_max_len = -1;             // exact, measured on the device on first use (declare counting); -1 = not yet
     bool owns = false;
     int64_t first_trace = 0;  // global index of trace 0 (multi-GPU shards)
+    // Block-cyclic shard (siesta_log_set_blocks): local traces [blk_local[b], blk_local[b + 1]) are the global traces
+    // starting at blk_global[b].  n_blocks == 0: one contiguous range starting at first_trace.
+    int32_t n_blocks = 0;
+    int64_t blk_local[SIESTA_MAX_BLOCKS + 1] = {0};
+    int64_t blk_global[SIESTA_MAX_BLOCKS] = {0};
     bool act_valid = false;  // every activity id lies in [0, n_activities): kernels may skip the per-event range check
 };
 
@@ -144,7 +149,8 @@ int validate_nfa(const siesta_nfa* nfa, uint32_t flags, DevNfa* out);
 // the block is complete; every rank reads every header (sizes travel in-band: no size collective, no host round trip
 // before the payload moves).
 constexpr int XCHG_MAX_RANKS = 16;
-constexpr size_t XCHG_CTRL_BYTES = 4096;   // control page at the start of a region; the data area follows
+constexpr size_t XCHG_CTRL_BYTES = 8192;   // control pages at the start of a region; the data area follows
+constexpr int64_t XCHG_ERR_CAP = 4096;     // error / outlier list entries a block carries
 enum { XST_LIMITS = 1, XST_STAGING = 2, XST_RANGE = 4, XST_ERRCAP = 8, XST_TIMEOUT = 16 };
 struct XHeader {
     unsigned long long seq;
@@ -153,8 +159,10 @@ struct XHeader {
     int32_t all_cols, seconds; // event columns present; ts_delta in seconds (EventTs route) or milliseconds
     int32_t uniform_k;         // > 0: one occurrence per trace and uniform_k events per occurrence (no offset sections)
     int32_t status;            // XST_* bits: the request failed on this rank
-    int64_t o_trace, o_base, o_occ_off, o_ev_off, o_pos, o_rank, o_act, o_delta, o_err, o_unsup;   // byte offsets into the data area
-    int64_t pad[12];
+    int64_t o_trace, o_base, o_occ_off, o_ev_off, o_pos, o_rank, o_act, o_delta, o_err, o_unsup;   // byte offsets into the block
+    int64_t slot_off;          // byte offset of the block inside the rank's data area (one slot per block of a blocked log)
+    int64_t shard_traces;      // traces of the rank's whole shard (all blocks): the capacity the receivers plan with
+    int64_t pad[10];
 };
 static_assert(sizeof(XHeader) == 256, "XHeader is 256 bytes");
 // Where the placement writes the compact block (detect.cu: detect_device_pack_impl)
@@ -163,6 +171,8 @@ struct PackTarget {
     int64_t cap_bytes;
     XHeader* hdr;          // header slot of the local region
     unsigned long long seq;
+    int64_t slot_off = 0;      // -> XHeader::slot_off
+    int64_t shard_traces = 0;  // -> XHeader::shard_traces
 };
 int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand, uint32_t flags,
                              cudaStream_t stream, RebaseOffsets base, DetectPending** pending);

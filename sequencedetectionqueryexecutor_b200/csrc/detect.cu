@@ -1383,7 +1383,6 @@ int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out) {
 //   pos u16[n_ev]  rank u8[n_ev]  act u16[n_ev]  delta i32[n_ev]  (ev_ts_ms - base) in seconds (EventTs route: exact,
 //                                                           both are rel_s * 1000 + t0) or milliseconds (EventPos route)
 //   err      i64[n_err] shard-local indices of the traces on which the Java engine would throw (<= XCHG_ERR_CAP)
-constexpr int64_t XCHG_ERR_CAP = 4096;
 struct PackSections {
     uint32_t* trace;
     int64_t* base;
@@ -1598,6 +1597,8 @@ int detect_device_pack_impl(DetectPending* q, const PackTarget& tgt) {
     proto.all_cols = all_cols ? 1 : 0;
     proto.seconds = (q->flags & SIESTA_F_EVT_POS) ? 0 : 1;
     proto.uniform_k = q->uniform_k;
+    proto.slot_off = tgt.slot_off;
+    proto.shard_traces = tgt.shard_traces;
     PackSections O;
     O.trace = reinterpret_cast<uint32_t*>(tgt.data + proto.o_trace);
     O.base = all_cols ? reinterpret_cast<int64_t*>(tgt.data + proto.o_base) : nullptr;

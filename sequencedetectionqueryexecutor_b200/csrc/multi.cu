@@ -30,15 +30,35 @@ namespace siesta {
 
 constexpr unsigned long long XCHG_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
 
+constexpr int XCHG_MAX_BLOCKS = SIESTA_MAX_BLOCKS;
 struct XCtrl {
-    XHeader hdr;                                 // header of the block in this region's data area
+    XHeader hdr[XCHG_MAX_BLOCKS];                // hdr[b]: header of block b of the request in flight (slot 0: every other operation)
     unsigned long long ready[XCHG_MAX_RANKS];    // ready[p]: written by rank p - its block of operation `value` is complete
-    unsigned long long ack[XCHG_MAX_RANKS];      // ack[p]:   written by rank p - it has pulled my block of operation `value`
+    unsigned long long ack[XCHG_MAX_RANKS];      // ack[p]:   written by rank p - it has pulled my blocks up to operation `value`
 };
-static_assert(sizeof(XCtrl) <= XCHG_CTRL_BYTES, "control page");
+static_assert(sizeof(XCtrl) <= XCHG_CTRL_BYTES, "control pages");
 
 struct XPeers {
     char* region[XCHG_MAX_RANKS];
+};
+
+// Places of one block's ranks in the joined list (absolute exclusive prefixes) and the running totals of a request; both
+// live in device memory and are advanced by xchg_prefix_kernel block by block, so a block is decoded as soon as every
+// rank has announced it - no host round trip per block.
+struct XBases {
+    int64_t tb[XCHG_MAX_RANKS + 1], ob[XCHG_MAX_RANKS + 1], eb[XCHG_MAX_RANKS + 1], rb[XCHG_MAX_RANKS + 1], ub[XCHG_MAX_RANKS + 1];
+};
+struct XRun {
+    int64_t n_tr, n_occ, n_ev, n_err, n_unsup, n_emitted;
+    int32_t status;       // OR of the headers' status bits (and XST_TIMEOUT for a block that is out of step)
+    int32_t pad;
+};
+struct XDev {
+    XHeader hdrs[XCHG_MAX_BLOCKS * XCHG_MAX_RANKS];   // [block][rank], as fetched by the wait kernels
+    XBases bases[XCHG_MAX_BLOCKS];
+    XRun run;
+    int flag;                                         // a device-side wait timed out
+    int pad[15];
 };
 
 struct Exchange {
@@ -50,10 +70,11 @@ struct Exchange {
     bool ipc[XCHG_MAX_RANKS];
     bool connected[XCHG_MAX_RANKS];
     unsigned long long seq = 0;
-    cudaStream_t stream = nullptr;
-    XHeader* d_hdrs = nullptr;   // [world] headers as fetched by the signal kernel
-    XHeader* h_hdrs = nullptr;   // pinned copy
-    std::mutex mu;               // one collective at a time per exchange
+    cudaStream_t stream = nullptr;    // scan, placement, announcements
+    cudaStream_t jstream = nullptr;   // waits for the peers, pulls + decodes (higher priority: its CTAs go first when SMs free up)
+    XDev* d_x = nullptr;
+    XDev* h_x = nullptr;              // pinned copy
+    std::mutex mu;                    // one collective at a time per exchange
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -84,6 +105,43 @@ __global__ void xchg_wait_acks_kernel(XCtrl* me, int world, int rank, unsigned l
     if (p < world && p != rank && !spin_until(&me->ack[p], seq_prev)) atomicOr(timed_out, 1);
 }
 
+// announce: my block of operation `seq` is complete (everything the kernels before this one wrote is visible first)
+__global__ void xchg_post_kernel(const __grid_constant__ XPeers peers, int world, int rank, unsigned long long seq) {
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    __threadfence_system();
+    st_release_sys(&reinterpret_cast<XCtrl*>(peers.region[p])->ready[rank], seq);
+}
+
+// wait until every rank has announced operation `seq`, then fetch header slot `slot` of every rank into d_hdrs[0..world)
+__global__ void xchg_wait_kernel(const __grid_constant__ XPeers peers, int world, int rank, unsigned long long seq, int slot, XHeader* d_hdrs,
+                                 int* timed_out) {
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    const bool ok = spin_until(&reinterpret_cast<XCtrl*>(peers.region[rank])->ready[p], seq);
+    XHeader h;
+    if (ok) {
+        const volatile uint4* src = reinterpret_cast<const volatile uint4*>(&reinterpret_cast<XCtrl*>(peers.region[p])->hdr[slot]);
+        uint4* dst = reinterpret_cast<uint4*>(&h);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(XHeader) / 16); ++i) {
+            uint4 v;
+            v.x = src[i].x; v.y = src[i].y; v.z = src[i].z; v.w = src[i].w;
+            dst[i] = v;
+        }
+        if (!h.status && h.seq != seq) {   // the peer is out of step (another request, another number of blocks)
+            memset(&h, 0, sizeof(h));
+            h.status = XST_TIMEOUT;
+        }
+    } else {
+        memset(&h, 0, sizeof(h));
+        h.status = XST_TIMEOUT;
+        atomicOr(timed_out, 1);
+    }
+    d_hdrs[p] = h;
+}
+
+// announce + wait + fetch in one launch (the count all-reduce: one block, nothing to overlap)
 __global__ void xchg_signal_kernel(const __grid_constant__ XPeers peers, int world, int rank, unsigned long long seq, XHeader* d_hdrs,
                                    int* timed_out) {
     const int p = threadIdx.x;
@@ -93,7 +151,7 @@ __global__ void xchg_signal_kernel(const __grid_constant__ XPeers peers, int wor
     const bool ok = spin_until(&reinterpret_cast<XCtrl*>(peers.region[rank])->ready[p], seq);
     XHeader h;
     if (ok) {
-        const volatile uint4* src = reinterpret_cast<const volatile uint4*>(&reinterpret_cast<XCtrl*>(peers.region[p])->hdr);
+        const volatile uint4* src = reinterpret_cast<const volatile uint4*>(&reinterpret_cast<XCtrl*>(peers.region[p])->hdr[0]);
         uint4* dst = reinterpret_cast<uint4*>(&h);
 #pragma unroll
         for (int i = 0; i < (int)(sizeof(XHeader) / 16); ++i) {
@@ -116,12 +174,33 @@ __global__ void xchg_ack_kernel(const __grid_constant__ XPeers peers, int world,
     st_release_sys(&reinterpret_cast<XCtrl*>(peers.region[p])->ack[rank], seq);
 }
 
+// places of block `blk`'s ranks in the joined list: the running totals so far + the sizes in the block's headers
+__global__ void xchg_prefix_kernel(XDev* d, int blk, int world) {
+    if (threadIdx.x || blockIdx.x) return;
+    XRun run = d->run;
+    XBases& B = d->bases[blk];
+    const XHeader* h = d->hdrs + blk * XCHG_MAX_RANKS;
+    B.tb[0] = run.n_tr; B.ob[0] = run.n_occ; B.eb[0] = run.n_ev; B.rb[0] = run.n_err; B.ub[0] = run.n_unsup;
+    for (int p = 0; p < world; ++p) {
+        const bool good = h[p].status == 0;
+        run.status |= h[p].status;
+        B.tb[p + 1] = B.tb[p] + (good ? h[p].n_tr : 0);
+        B.ob[p + 1] = B.ob[p] + (good ? h[p].n_occ : 0);
+        B.eb[p + 1] = B.eb[p] + (good ? h[p].n_ev : 0);
+        B.rb[p + 1] = B.rb[p] + (good ? h[p].n_err : 0);
+        B.ub[p + 1] = B.ub[p] + (good ? h[p].n_unsup : 0);
+        run.n_emitted += good ? h[p].n_emitted : 0;
+    }
+    run.n_tr = B.tb[world]; run.n_occ = B.ob[world]; run.n_ev = B.eb[world]; run.n_err = B.rb[world]; run.n_unsup = B.ub[world];
+    d->run = run;
+}
+
 // ------------------------------------------------------------------------------------------------ pull + decode
 struct XDecode {
     int world, me;   // grid row y handles source rank (me + y) % world: at any moment the ranks read from different peers
     const char* data[XCHG_MAX_RANKS];   // data areas of all ranks (mine included)
-    const XHeader* hdrs;                // [world], device copy
-    int64_t tb[XCHG_MAX_RANKS + 1], ob[XCHG_MAX_RANKS + 1], eb[XCHG_MAX_RANKS + 1], rb[XCHG_MAX_RANKS + 1], ub[XCHG_MAX_RANKS + 1];  // exclusive prefixes
+    const XHeader* hdrs;                // [world] headers of the block, device copy
+    const XBases* bases;                // the ranks' places in the joined list (device memory: xchg_prefix_kernel)
     int64_t *trace_idx, *occ_off, *ev_off;
     int32_t *pos, *rank, *act;
     int64_t* ts;
@@ -144,10 +223,10 @@ __global__ void __launch_bounds__(XD_THREADS) xchg_decode_uniform_kernel(const _
     const XHeader h = D.hdrs[r];
     if (h.status) return;
     const int K = h.uniform_k;
-    const char* data = D.data[r];
+    const char* data = D.data[r] + h.slot_off;
     const int tid = threadIdx.x;
     const int64_t n_ev = h.n_ev, n_tr = h.n_tr;
-    const int64_t eb = D.eb[r], tb = D.tb[r];
+    const int64_t eb = D.bases->eb[r], tb = D.bases->tb[r];
     const long long unit = h.seconds ? 1000 : 1;
     const uint32_t* g_trace = reinterpret_cast<const uint32_t*>(data + h.o_trace);
     const long long* g_base = reinterpret_cast<const long long*>(data + h.o_base);
@@ -198,9 +277,9 @@ __global__ void __launch_bounds__(XD_THREADS) xchg_decode_uniform_kernel(const _
         D.ev_off[tb + t] = eb + t * K;
     }
     for (int64_t i = (int64_t)blockIdx.x * XD_THREADS + tid; i < h.n_err; i += (int64_t)gridDim.x * XD_THREADS)
-        D.err[D.rb[r] + i] = h.trace_base + __ldcv(reinterpret_cast<const long long*>(data + h.o_err) + i);
+        D.err[D.bases->rb[r] + i] = h.trace_base + __ldcv(reinterpret_cast<const long long*>(data + h.o_err) + i);
     for (int64_t i = (int64_t)blockIdx.x * XD_THREADS + tid; i < h.n_unsup; i += (int64_t)gridDim.x * XD_THREADS)
-        D.unsup[D.ub[r] + i] = h.trace_base + __ldcv(reinterpret_cast<const long long*>(data + h.o_unsup) + i);
+        D.unsup[D.bases->ub[r] + i] = h.trace_base + __ldcv(reinterpret_cast<const long long*>(data + h.o_unsup) + i);
 }
 
 // General blocks (any number of occurrences per trace and of events per occurrence): one thread per trace.
@@ -208,7 +287,7 @@ __global__ void __launch_bounds__(XD_THREADS) xchg_decode_general_kernel(const _
     const int r = (int)((blockIdx.y + D.me) % D.world);
     const XHeader h = D.hdrs[r];
     if (h.status) return;
-    const char* data = D.data[r];
+    const char* data = D.data[r] + h.slot_off;
     const uint32_t* g_trace = reinterpret_cast<const uint32_t*>(data + h.o_trace);
     const long long* g_base = reinterpret_cast<const long long*>(data + h.o_base);
     const uint32_t* g_occ = reinterpret_cast<const uint32_t*>(data + h.o_occ_off);
@@ -217,7 +296,7 @@ __global__ void __launch_bounds__(XD_THREADS) xchg_decode_general_kernel(const _
     const uint8_t* g_rank = reinterpret_cast<const uint8_t*>(data + h.o_rank);
     const uint16_t* g_act = reinterpret_cast<const uint16_t*>(data + h.o_act);
     const int32_t* g_delta = reinterpret_cast<const int32_t*>(data + h.o_delta);
-    const int64_t tb = D.tb[r], ob = D.ob[r], eb = D.eb[r];
+    const int64_t tb = D.bases->tb[r], ob = D.bases->ob[r], eb = D.bases->eb[r];
     const long long unit = h.seconds ? 1000 : 1;
     for (int64_t t = (int64_t)blockIdx.x * XD_THREADS + threadIdx.x; t < h.n_tr; t += (int64_t)gridDim.x * XD_THREADS) {
         D.trace_idx[tb + t] = h.trace_base + (int64_t)__ldcv(g_trace + t);
@@ -238,14 +317,14 @@ __global__ void __launch_bounds__(XD_THREADS) xchg_decode_general_kernel(const _
         }
     }
     for (int64_t i = (int64_t)blockIdx.x * XD_THREADS + threadIdx.x; i < h.n_err; i += (int64_t)gridDim.x * XD_THREADS)
-        D.err[D.rb[r] + i] = h.trace_base + __ldcv(reinterpret_cast<const long long*>(data + h.o_err) + i);
+        D.err[D.bases->rb[r] + i] = h.trace_base + __ldcv(reinterpret_cast<const long long*>(data + h.o_err) + i);
     for (int64_t i = (int64_t)blockIdx.x * XD_THREADS + threadIdx.x; i < h.n_unsup; i += (int64_t)gridDim.x * XD_THREADS)
-        D.unsup[D.ub[r] + i] = h.trace_base + __ldcv(reinterpret_cast<const long long*>(data + h.o_unsup) + i);
+        D.unsup[D.bases->ub[r] + i] = h.trace_base + __ldcv(reinterpret_cast<const long long*>(data + h.o_unsup) + i);
 }
 
-__global__ void xchg_tail_kernel(int64_t* occ_off, int64_t n_tr, int64_t n_occ, int64_t* ev_off, int64_t n_ev) {
-    occ_off[n_tr] = n_occ;
-    ev_off[n_occ] = n_ev;
+__global__ void xchg_tail_kernel(int64_t* occ_off, int64_t* ev_off, const XRun* run) {
+    occ_off[run->n_tr] = run->n_occ;
+    ev_off[run->n_occ] = run->n_ev;
 }
 
 // all-reduce of int64 arrays that sit at the start of every rank's data area: out[i] = op over the ranks, in rank order
@@ -302,12 +381,20 @@ extern "C" int siesta_exchange_create(siesta_ctx* ctx, int32_t world, int32_t ra
     e = cudaMemset(x->region, 0, XCHG_CTRL_BYTES);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) {
+        int lo = 0, hi = 0;   // (lowest, greatest) priority; greatest is numerically smallest
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = cudaStreamCreateWithPriority(&x->jstream, cudaStreamNonBlocking, hi);
+    }
+    if (e == cudaSuccess) {
         // Load every kernel and driver-internal copy path a collective uses NOW: with lazy module loading the first
         // launch of a function may wait for the device to drain, and inside a collective another rank of this process
         // may already be spinning on this one (ranks that share a device in the tests; one JVM driving all GPUs).
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, xchg_wait_acks_kernel);
         cudaFuncGetAttributes(&fa, xchg_signal_kernel);
+        cudaFuncGetAttributes(&fa, xchg_post_kernel);
+        cudaFuncGetAttributes(&fa, xchg_wait_kernel);
+        cudaFuncGetAttributes(&fa, xchg_prefix_kernel);
         cudaFuncGetAttributes(&fa, xchg_ack_kernel);
         cudaFuncGetAttributes(&fa, xchg_decode_uniform_kernel);
         cudaFuncGetAttributes(&fa, xchg_decode_general_kernel);
@@ -319,12 +406,19 @@ extern "C" int siesta_exchange_create(siesta_ctx* ctx, int32_t world, int32_t ra
         cudaMemcpyAsync(x->region + XCHG_CTRL_BYTES, x->region, std::min<size_t>(256, x->cap_bytes), cudaMemcpyDeviceToDevice, x->stream);
         cudaMemsetAsync(x->region + XCHG_CTRL_BYTES, 0, std::min<size_t>(256, x->cap_bytes), x->stream);
         xchg_reduce_kernel<<<1, 32, 0, x->stream>>>(x->peers, 0, 0, SIESTA_REDUCE_SUM, nullptr);
-        xchg_tail_kernel<<<1, 1, 0, x->stream>>>(reinterpret_cast<int64_t*>(x->region + XCHG_CTRL_BYTES), 0, 0,
-                                                 reinterpret_cast<int64_t*>(x->region + XCHG_CTRL_BYTES), 0);
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMalloc((void**)&x->d_hdrs, sizeof(XHeader) * XCHG_MAX_RANKS + 256);
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&x->h_hdrs, sizeof(XHeader) * XCHG_MAX_RANKS + 256, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&x->d_x, sizeof(XDev));
+    if (e == cudaSuccess) e = cudaMemset(x->d_x, 0, sizeof(XDev));
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&x->h_x, sizeof(XDev), cudaHostAllocDefault);
+    if (e == cudaSuccess) {
+        std::memset(x->h_x, 0, sizeof(XDev));
+        xchg_prefix_kernel<<<1, 32, 0, x->jstream>>>(x->d_x, 0, 0);
+        xchg_tail_kernel<<<1, 1, 0, x->jstream>>>(reinterpret_cast<int64_t*>(x->region + XCHG_CTRL_BYTES),
+                                                  reinterpret_cast<int64_t*>(x->region + XCHG_CTRL_BYTES), &x->d_x->run);
+        e = cudaMemcpyAsync(x->h_x, x->d_x, sizeof(XDev), cudaMemcpyDeviceToHost, x->jstream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         set_error(std::string("siesta_exchange_create: ") + cudaGetErrorString(e));
@@ -400,20 +494,43 @@ extern "C" void siesta_exchange_free(siesta_exchange* xh) {
     if (!x) return;
     cudaSetDevice(x->ctx->device);
     if (x->stream) cudaStreamSynchronize(x->stream);
+    if (x->jstream) cudaStreamSynchronize(x->jstream);
     for (int p = 0; p < x->world; ++p)
         if (x->ipc[p] && x->peers.region[p]) cudaIpcCloseMemHandle(x->peers.region[p]);
     if (x->region) cudaFree(x->region);
-    if (x->d_hdrs) cudaFree(x->d_hdrs);
-    if (x->h_hdrs) cudaFreeHost(x->h_hdrs);
+    if (x->d_x) cudaFree(x->d_x);
+    if (x->h_x) cudaFreeHost(x->h_x);
     if (x->stream) cudaStreamDestroy(x->stream);
+    if (x->jstream) cudaStreamDestroy(x->jstream);
     delete x;
+}
+
+// the blocks of a shard log: [first local trace, one past the last), global index of the first trace
+static int log_blocks(const Log* L, int64_t (&lo)[XCHG_MAX_BLOCKS], int64_t (&hi)[XCHG_MAX_BLOCKS], int64_t (&glob)[XCHG_MAX_BLOCKS]) {
+    if (L->n_blocks <= 0) {
+        lo[0] = 0;
+        hi[0] = L->n_traces;
+        glob[0] = L->first_trace;
+        return 1;
+    }
+    for (int b = 0; b < L->n_blocks; ++b) {
+        lo[b] = L->blk_local[b];
+        hi[b] = L->blk_local[b + 1];
+        glob[b] = L->blk_global[b];
+    }
+    return L->n_blocks;
 }
 
 extern "C" int64_t siesta_exchange_required_bytes(siesta_log* log, const siesta_nfa* nfa, uint32_t flags) {
     Log* L = reinterpret_cast<Log*>(log);
     if (!L || !nfa) return -1;
-    return detect_pack_required_bytes(L->n_traces, L->n_events, detect_uniform_k(nfa, flags), !(flags & SIESTA_F_NO_EVENT_COLUMNS),
-                                      (flags & SIESTA_F_RETURN_ALL) != 0);
+    int64_t lo[XCHG_MAX_BLOCKS], hi[XCHG_MAX_BLOCKS], glob[XCHG_MAX_BLOCKS];
+    const int C = log_blocks(L, lo, hi, glob);
+    int64_t need = 0;   // one slot per block: a block stays in the region until every peer has pulled it
+    for (int b = 0; b < C; ++b)
+        need += detect_pack_required_bytes(hi[b] - lo[b], L->n_events, detect_uniform_k(nfa, flags), !(flags & SIESTA_F_NO_EVENT_COLUMNS),
+                                           (flags & SIESTA_F_RETURN_ALL) != 0);
+    return need;
 }
 
 extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, uint32_t flags, siesta_exchange* xh,
@@ -434,81 +551,121 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
     if (stats) std::memset(stats, 0, sizeof(*stats));
     std::lock_guard<std::mutex> lock(x->mu);
     SIESTA_CUDA_OK(cudaSetDevice(x->ctx->device));
-    cudaStream_t stream = x->stream;
+    cudaStream_t S = x->stream, J = x->jstream;
     const int world = x->world, rank = x->rank;
     XCtrl* me = reinterpret_cast<XCtrl*>(x->region);
-    const unsigned long long seq = ++x->seq;
+    XDev* dx = x->d_x;
+    XDev* hx = x->h_x;
+    const bool all_cols = !(flags & SIESTA_F_NO_EVENT_COLUMNS);
 
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    struct EvGuard {
-        cudaEvent_t* e;
-        ~EvGuard() { for (int i = 0; i < 5; ++i) if (e[i]) cudaEventDestroy(e[i]); }
-    } ev_guard{ev};
-    for (int i = 0; i < 5; ++i) SIESTA_CUDA_OK(cudaEventCreate(&ev[i]));
-    int* d_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(x->d_hdrs) + sizeof(XHeader) * XCHG_MAX_RANKS);
-    int* h_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(x->h_hdrs) + sizeof(XHeader) * XCHG_MAX_RANKS);
-    SIESTA_CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), stream));
-
-    // ---- the scan of my shard (kernels K1 / K1-P), enqueued without waiting
-    SIESTA_CUDA_OK(cudaEventRecord(ev[0], stream));
-    DetectPending* q = nullptr;
-    rc = detect_device_begin_impl(L, nfa, nullptr, 0, flags, stream, RebaseOffsets{0, 0, 0}, &q);
-    if (rc) {
-        // keep the collective in step: peers wait for my block of this operation - announce a failed one
-        XHeader fail;
-        std::memset(&fail, 0, sizeof(fail));
-        fail.seq = seq;
-        fail.status = XST_LIMITS;
-        cudaMemcpyAsync(&me->hdr, &fail, sizeof(fail), cudaMemcpyHostToDevice, stream);
-    } else {
-        // ---- my block into my region: wait for the peers' acks of the previous operation first
-        xchg_wait_acks_kernel<<<1, 32, 0, stream>>>(me, world, rank, seq - 1, d_flag);
-        SIESTA_LAUNCHED();
-        PackTarget tgt{x->region + XCHG_CTRL_BYTES, (int64_t)x->cap_bytes, &me->hdr, seq};
-        const int rc2 = detect_device_pack_impl(q, tgt);
-        if (rc2) {
-            rc = rc2;
-            XHeader fail;
-            std::memset(&fail, 0, sizeof(fail));
-            fail.seq = seq;
-            fail.status = XST_STAGING;
-            cudaMemcpyAsync(&me->hdr, &fail, sizeof(fail), cudaMemcpyHostToDevice, stream);
+    // ---- the blocks of my shard (one for a contiguous shard): each is verified, placed and announced on its own, in
+    // order, on stream S; operation numbers are consecutive, block b of this request is operation seq0 + 1 + b
+    int64_t b_lo[XCHG_MAX_BLOCKS], b_hi[XCHG_MAX_BLOCKS], b_glob[XCHG_MAX_BLOCKS];
+    const int C = log_blocks(L, b_lo, b_hi, b_glob);
+    const unsigned long long seq0 = x->seq;
+    x->seq += (unsigned long long)C;
+    const unsigned long long seq_last = seq0 + (unsigned long long)C;
+    std::vector<Log> view((size_t)C, *L);
+    int64_t slot_off[XCHG_MAX_BLOCKS], slot_bytes[XCHG_MAX_BLOCKS];
+    {
+        const int uk = detect_uniform_k(nfa, flags);
+        int64_t at = 0;
+        for (int b = 0; b < C; ++b) {
+            Log& V = view[(size_t)b];
+            V.d_trace_off = L->d_trace_off + b_lo[b];   // offsets stay absolute: the event columns are shared
+            V.n_traces = b_hi[b] - b_lo[b];
+            V.first_trace = b_glob[b];
+            V.n_blocks = 0;
+            V.owns = false;
+            slot_off[b] = at;
+            slot_bytes[b] = detect_pack_required_bytes(V.n_traces, L->n_events, uk, all_cols, (flags & SIESTA_F_RETURN_ALL) != 0);
+            at += slot_bytes[b];
         }
     }
-    const std::string first_error = rc ? std::string(siesta_last_error()) : std::string();
-    SIESTA_CUDA_OK(cudaEventRecord(ev[1], stream));
-    // ---- announce, wait for every rank, fetch the headers
-    xchg_signal_kernel<<<1, 32, 0, stream>>>(x->peers, world, rank, seq, x->d_hdrs, d_flag);
-    SIESTA_LAUNCHED();
-    SIESTA_CUDA_OK(cudaMemcpyAsync(x->h_hdrs, x->d_hdrs, sizeof(XHeader) * XCHG_MAX_RANKS + 256, cudaMemcpyDeviceToHost, stream));
-    SIESTA_CUDA_OK(cudaEventRecord(ev[2], stream));
-    SIESTA_CUDA_OK(cudaStreamSynchronize(stream));   // host wait 1 of 2: the sizes of all blocks
-    const float k1_ms = detect_pending_k1_ms(q);
-    if (q) detect_pending_discard(q);
 
-    int bad = *h_flag ? XST_TIMEOUT : 0;
-    int64_t tb[XCHG_MAX_RANKS + 1] = {0}, ob[XCHG_MAX_RANKS + 1] = {0}, eb[XCHG_MAX_RANKS + 1] = {0}, rb[XCHG_MAX_RANKS + 1] = {0},
-            ub[XCHG_MAX_RANKS + 1] = {0};
-    bool uniform = true, all_cols = !(flags & SIESTA_F_NO_EVENT_COLUMNS);
-    int64_t emitted = 0;
-    for (int p = 0; p < world; ++p) {
-        const XHeader& h = x->h_hdrs[p];
-        bad |= h.status;
-        if (!h.status && h.seq != seq) bad |= XST_TIMEOUT;   // a peer is out of step
-        tb[p + 1] = tb[p] + h.n_tr;
-        ob[p + 1] = ob[p] + h.n_occ;
-        eb[p + 1] = eb[p] + h.n_ev;
-        rb[p + 1] = rb[p] + h.n_err;
-        ub[p + 1] = ub[p] + h.n_unsup;
-        uniform = uniform && h.uniform_k > 0;
-        emitted += h.n_emitted;
-    }
-    if (bad || rc) {
-        // every rank saw the same headers: all of them fail this operation, and all acknowledge it so that the next one
-        // can overwrite the regions
-        xchg_ack_kernel<<<1, 32, 0, stream>>>(x->peers, world, rank, seq);
+    enum { EV_S0 = 0, EV_S1, EV_J0, EV_J1, EV_RESET, EV_H0, N_EV };
+    cudaEvent_t ev[N_EV] = {nullptr};
+    struct EvGuard {
+        cudaEvent_t* e;
+        ~EvGuard() { for (int i = 0; i < N_EV; ++i) if (e[i]) cudaEventDestroy(e[i]); }
+    } ev_guard{ev};
+    for (int i = 0; i < N_EV; ++i) SIESTA_CUDA_OK(cudaEventCreate(&ev[i]));
+    std::vector<DetectPending*> pend((size_t)C, nullptr);
+    struct PendGuard {   // the scans' scratch goes back to the arena once both streams are idle
+        std::vector<DetectPending*>& q;
+        cudaStream_t a, b;
+        ~PendGuard() {
+            cudaStreamSynchronize(a);
+            cudaStreamSynchronize(b);
+            for (DetectPending* p : q) if (p) detect_pending_discard(p);
+        }
+    } pend_guard{pend, S, J};
+
+    SIESTA_CUDA_OK(cudaMemsetAsync(&dx->run, 0, sizeof(XRun) + sizeof(int), S));   // running totals and the time-out flag
+    SIESTA_CUDA_OK(cudaEventRecord(ev[EV_RESET], S));
+    SIESTA_CUDA_OK(cudaStreamWaitEvent(J, ev[EV_RESET], 0));
+    SIESTA_CUDA_OK(cudaEventRecord(ev[EV_S0], S));
+    std::string first_error;
+    for (int b = 0; b < C; ++b) {
+        if (!rc) {
+            const int rcb = detect_device_begin_impl(&view[(size_t)b], nfa, nullptr, 0, flags, S, RebaseOffsets{0, 0, 0}, &pend[(size_t)b]);
+            if (rcb) {
+                rc = rcb;
+                first_error = siesta_last_error();
+            }
+        }
+        // my region is rewritten from here on: every peer must have pulled the previous operation's blocks out of it
+        if (b == 0) {
+            xchg_wait_acks_kernel<<<1, 32, 0, S>>>(me, world, rank, seq0, &dx->flag);
+            SIESTA_LAUNCHED();
+        }
+        int fail = rc ? XST_LIMITS : 0;
+        if (!rc) {
+            PackTarget tgt{x->region + XCHG_CTRL_BYTES + slot_off[b], std::min<int64_t>(slot_bytes[b], (int64_t)x->cap_bytes - slot_off[b]),
+                           &me->hdr[b], seq0 + 1 + (unsigned long long)b};
+            tgt.slot_off = slot_off[b];
+            tgt.shard_traces = L->n_traces;
+            const int rc2 = detect_device_pack_impl(pend[(size_t)b], tgt);
+            if (rc2) {
+                rc = rc2;
+                first_error = siesta_last_error();
+                fail = XST_STAGING;
+            }
+        }
+        if (fail) {   // keep the collective in step: the peers wait for this block - announce a failed one
+            XHeader fh;
+            std::memset(&fh, 0, sizeof(fh));
+            fh.seq = seq0 + 1 + (unsigned long long)b;
+            fh.status = fail;
+            cudaMemcpyAsync(&me->hdr[b], &fh, sizeof(fh), cudaMemcpyHostToDevice, S);
+        }
+        xchg_post_kernel<<<1, 32, 0, S>>>(x->peers, world, rank, seq0 + 1 + (unsigned long long)b);
         SIESTA_LAUNCHED();
-        cudaStreamSynchronize(stream);
+    }
+    SIESTA_CUDA_OK(cudaEventRecord(ev[EV_S1], S));
+
+    // ---- stream J: block 0 of every rank -> its headers tell how the request continues
+    SIESTA_CUDA_OK(cudaEventRecord(ev[EV_J0], J));
+    xchg_wait_kernel<<<1, 32, 0, J>>>(x->peers, world, rank, seq0 + 1, 0, dx->hdrs, &dx->flag);
+    SIESTA_LAUNCHED();
+    SIESTA_CUDA_OK(cudaMemcpyAsync(hx->hdrs, dx->hdrs, sizeof(XHeader) * XCHG_MAX_RANKS, cudaMemcpyDeviceToHost, J));
+    SIESTA_CUDA_OK(cudaMemcpyAsync(&hx->flag, &dx->flag, sizeof(int), cudaMemcpyDeviceToHost, J));
+    SIESTA_CUDA_OK(cudaEventRecord(ev[EV_H0], J));
+    SIESTA_CUDA_OK(cudaEventSynchronize(ev[EV_H0]));   // host wait 1 of 2 (my later blocks keep running on S)
+
+    // every rank sees the same headers, so every rank takes the same path from here
+    auto finish_failed = [&](int bad, bool skip_waits = false) -> int {
+        // all ranks fail this request, and all acknowledge it so that the next one can overwrite the regions; the
+        // later blocks are waited for first (bounded) unless a peer is missing already
+        if (!(bad & XST_TIMEOUT) && !skip_waits)
+            for (int b = 1; b < C; ++b) {
+                xchg_wait_kernel<<<1, 32, 0, J>>>(x->peers, world, rank, seq0 + 1 + (unsigned long long)b, b, dx->hdrs + b * XCHG_MAX_RANKS, &dx->flag);
+                SIESTA_LAUNCHED();
+            }
+        xchg_ack_kernel<<<1, 32, 0, J>>>(x->peers, world, rank, seq_last);
+        SIESTA_LAUNCHED();
+        cudaStreamSynchronize(J);
+        cudaStreamSynchronize(S);
         if (rc) {
             set_error(first_error);
             return rc;
@@ -528,112 +685,211 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
         }
         set_error("exchange: staging overflow or too many reference errors on some rank");
         return SIESTA_E_NOMEM;
+    };
+    int bad = hx->flag ? XST_TIMEOUT : 0;
+    bool uniform = true;
+    int64_t cap_tr = 0;
+    for (int p = 0; p < world; ++p) {
+        const XHeader& h = hx->hdrs[p];
+        bad |= h.status;
+        uniform = uniform && h.uniform_k > 0;
+        cap_tr += h.shard_traces;
     }
-    const int64_t n_tr = tb[world], n_occ = ob[world], n_ev = eb[world], n_err = rb[world], n_unsup = ub[world];
+    if (bad || rc) return finish_failed(bad);
+    const int K = uniform ? hx->hdrs[0].uniform_k : 0;
 
-    // ---- the joined result: one allocation, the library's standard block layout
-    void* fin = nullptr;
-    size_t f_off = 0;
-    auto fcarve = [&f_off](size_t bytes) {
-        const size_t at = f_off;
-        f_off += (bytes + 255) & ~(size_t)255;
-        return at;
+    // ---- the joined result: one allocation, the library's standard columns.  Eager: sized for the worst case now and
+    // filled block by block; otherwise sized exactly once the last block's headers are in.
+    auto layout = [&](int64_t n_tr, int64_t n_occ, int64_t n_ev, int64_t n_err, int64_t n_unsup, size_t (&q)[9]) {
+        size_t f_off = 0;
+        auto fcarve = [&f_off](size_t bytes) {
+            const size_t at = f_off;
+            f_off += (bytes + 255) & ~(size_t)255;
+            return at;
+        };
+        q[0] = fcarve((size_t)n_tr * 8);
+        q[1] = fcarve((size_t)(n_tr + 1) * 8);
+        q[2] = fcarve((size_t)(n_occ + 1) * 8);
+        q[3] = fcarve((size_t)n_ev * 4);
+        q[4] = fcarve((size_t)n_err * 8);
+        q[5] = q[6] = q[7] = 0;
+        if (all_cols) {
+            q[5] = fcarve((size_t)n_ev * 4);
+            q[6] = fcarve((size_t)n_ev * 4);
+            q[7] = fcarve((size_t)n_ev * 8);
+        }
+        q[8] = fcarve((size_t)n_unsup * 8);
+        return f_off;
     };
-    const size_t q_trace = fcarve((size_t)n_tr * 8), q_occ = fcarve((size_t)(n_tr + 1) * 8), q_evoff = fcarve((size_t)(n_occ + 1) * 8),
-                 q_pos = fcarve((size_t)n_ev * 4), q_err = fcarve((size_t)n_err * 8);
-    size_t q_rank = 0, q_act = 0, q_ts = 0;
-    if (all_cols) {
-        q_rank = fcarve((size_t)n_ev * 4);
-        q_act = fcarve((size_t)n_ev * 4);
-        q_ts = fcarve((size_t)n_ev * 8);
+    size_t qo[9];
+    size_t f_bytes = 0;
+    bool eager = false;
+    if (C > 1 && uniform) {
+        const int64_t lists = (int64_t)XCHG_ERR_CAP * world * C;
+        f_bytes = layout(cap_tr, cap_tr, cap_tr * K, lists, lists, qo);
+        size_t limit = (size_t)24 << 30;
+        if (const char* env = std::getenv("SIESTA_XCHG_EAGER_MAX_BYTES")) limit = (size_t)std::strtoull(env, nullptr, 10);
+        eager = f_bytes <= limit;
     }
-    const size_t q_unsup = fcarve((size_t)n_unsup * 8);
-    fin = dev_arena_alloc(x->ctx, f_off);
-    if (!fin) {
-        xchg_ack_kernel<<<1, 32, 0, stream>>>(x->peers, world, rank, seq);
-        cudaStreamSynchronize(stream);
-        return SIESTA_E_NOMEM;
-    }
-    struct FinGuard {   // an error return below gives the block back
-        Ctx* c;
-        void*& p;
-        ~FinGuard() { if (p) dev_arena_free(c, p); }
-    };
-    void* fin_owned = fin;
-    FinGuard fin_guard{x->ctx, fin_owned};
-    char* fb = reinterpret_cast<char*>(fin);
     XDecode D;
     std::memset(&D, 0, sizeof(D));
     D.world = world;
     D.me = rank;
     for (int p = 0; p < world; ++p) D.data[p] = x->peers.region[p] + XCHG_CTRL_BYTES;
-    D.hdrs = x->d_hdrs;
-    std::memcpy(D.tb, tb, sizeof(tb));
-    std::memcpy(D.ob, ob, sizeof(ob));
-    std::memcpy(D.eb, eb, sizeof(eb));
-    std::memcpy(D.rb, rb, sizeof(rb));
-    std::memcpy(D.ub, ub, sizeof(ub));
-    D.trace_idx = reinterpret_cast<int64_t*>(fb + q_trace);
-    D.occ_off = reinterpret_cast<int64_t*>(fb + q_occ);
-    D.ev_off = reinterpret_cast<int64_t*>(fb + q_evoff);
-    D.pos = reinterpret_cast<int32_t*>(fb + q_pos);
-    D.err = reinterpret_cast<int64_t*>(fb + q_err);
-    D.unsup = reinterpret_cast<int64_t*>(fb + q_unsup);
-    D.rank = all_cols ? reinterpret_cast<int32_t*>(fb + q_rank) : nullptr;
-    D.act = all_cols ? reinterpret_cast<int32_t*>(fb + q_act) : nullptr;
-    D.ts = all_cols ? reinterpret_cast<int64_t*>(fb + q_ts) : nullptr;
-    {
-        int64_t biggest = 1;
-        for (int p = 0; p < world; ++p) biggest = std::max(biggest, uniform ? x->h_hdrs[p].n_ev / XD_TE + 1 : x->h_hdrs[p].n_tr / XD_THREADS + 1);
-        int gx = (int)std::min<int64_t>(biggest, (int64_t)x->ctx->sm_count * 8 / world + 1);
+    void* fin_owned = nullptr;
+    struct FinGuard {   // an error return below gives the block back
+        Ctx* c;
+        void*& p;
+        ~FinGuard() { if (p) dev_arena_free(c, p); }
+    } fin_guard{x->ctx, fin_owned};
+    auto bind = [&](void* fin) {
+        char* fb = reinterpret_cast<char*>(fin);
+        D.trace_idx = reinterpret_cast<int64_t*>(fb + qo[0]);
+        D.occ_off = reinterpret_cast<int64_t*>(fb + qo[1]);
+        D.ev_off = reinterpret_cast<int64_t*>(fb + qo[2]);
+        D.pos = reinterpret_cast<int32_t*>(fb + qo[3]);
+        D.err = reinterpret_cast<int64_t*>(fb + qo[4]);
+        D.rank = all_cols ? reinterpret_cast<int32_t*>(fb + qo[5]) : nullptr;
+        D.act = all_cols ? reinterpret_cast<int32_t*>(fb + qo[6]) : nullptr;
+        D.ts = all_cols ? reinterpret_cast<int64_t*>(fb + qo[7]) : nullptr;
+        D.unsup = reinterpret_cast<int64_t*>(fb + qo[8]);
+    };
+    // grid of one block's decode: row y = source rank (me + y) % world; columns sized from the largest block
+    auto decode_block = [&](int b, int64_t biggest_units) {
+        int gx = (int)std::min<int64_t>(std::max<int64_t>(biggest_units, 1), (int64_t)x->ctx->sm_count * 8 / world + 1);
         if (const char* env = std::getenv("SIESTA_XCHG_DECODE_CTAS")) {
             const int v = std::atoi(env);
             if (v >= 1) gx = v;
         }
-        const dim3 grid((unsigned)gx, (unsigned)world);
-        SIESTA_CUDA_OK(cudaEventRecord(ev[4], stream));
-        if (uniform) xchg_decode_uniform_kernel<<<grid, XD_THREADS, 0, stream>>>(D);
-        else xchg_decode_general_kernel<<<grid, XD_THREADS, 0, stream>>>(D);
+        XDecode Db = D;
+        Db.hdrs = dx->hdrs + b * XCHG_MAX_RANKS;
+        Db.bases = dx->bases + b;
+        xchg_prefix_kernel<<<1, 32, 0, J>>>(dx, b, world);
         SIESTA_LAUNCHED();
+        const dim3 grid((unsigned)gx, (unsigned)world);
+        if (uniform) xchg_decode_uniform_kernel<<<grid, XD_THREADS, 0, J>>>(Db);
+        else xchg_decode_general_kernel<<<grid, XD_THREADS, 0, J>>>(Db);
+        SIESTA_LAUNCHED();
+    };
+    if (eager) {
+        fin_owned = dev_arena_alloc(x->ctx, f_bytes);
+        if (!fin_owned) {
+            first_error = siesta_last_error();
+            rc = SIESTA_E_NOMEM;   // (this rank only; it still waits for the blocks and acknowledges them)
+            return finish_failed(0);
+        }
+        bind(fin_owned);
+        int64_t big = 1;
+        for (int p = 0; p < world; ++p) big = std::max(big, (hx->hdrs[p].shard_traces / C + 1) * K / XD_TE + 1);
+        decode_block(0, big);
+        for (int b = 1; b < C; ++b) {
+            xchg_wait_kernel<<<1, 32, 0, J>>>(x->peers, world, rank, seq0 + 1 + (unsigned long long)b, b, dx->hdrs + b * XCHG_MAX_RANKS, &dx->flag);
+            SIESTA_LAUNCHED();
+            decode_block(b, big);
+        }
+    } else {
+        for (int b = 1; b < C; ++b) {
+            xchg_wait_kernel<<<1, 32, 0, J>>>(x->peers, world, rank, seq0 + 1 + (unsigned long long)b, b, dx->hdrs + b * XCHG_MAX_RANKS, &dx->flag);
+            SIESTA_LAUNCHED();
+        }
+        if (C > 1) {
+            SIESTA_CUDA_OK(cudaMemcpyAsync(hx->hdrs, dx->hdrs, sizeof(XHeader) * XCHG_MAX_RANKS * (size_t)C, cudaMemcpyDeviceToHost, J));
+            SIESTA_CUDA_OK(cudaMemcpyAsync(&hx->flag, &dx->flag, sizeof(int), cudaMemcpyDeviceToHost, J));
+            SIESTA_CUDA_OK(cudaStreamSynchronize(J));
+            bad = hx->flag ? XST_TIMEOUT : 0;
+            for (int b = 0; b < C; ++b)
+                for (int p = 0; p < world; ++p) bad |= hx->hdrs[b * XCHG_MAX_RANKS + p].status;
+            if (bad) return finish_failed(bad, true);
+        }
+        int64_t t_tr = 0, t_occ = 0, t_ev = 0, t_err = 0, t_unsup = 0;
+        for (int b = 0; b < C; ++b)
+            for (int p = 0; p < world; ++p) {
+                const XHeader& h = hx->hdrs[b * XCHG_MAX_RANKS + p];
+                t_tr += h.n_tr; t_occ += h.n_occ; t_ev += h.n_ev; t_err += h.n_err; t_unsup += h.n_unsup;
+            }
+        f_bytes = layout(t_tr, t_occ, t_ev, t_err, t_unsup, qo);
+        fin_owned = dev_arena_alloc(x->ctx, f_bytes);
+        if (!fin_owned) {
+            first_error = siesta_last_error();
+            rc = SIESTA_E_NOMEM;
+            return finish_failed(0, true);
+        }
+        bind(fin_owned);
+        for (int b = 0; b < C; ++b) {
+            int64_t big = 1;
+            for (int p = 0; p < world; ++p) {
+                const XHeader& h = hx->hdrs[b * XCHG_MAX_RANKS + p];
+                big = std::max(big, uniform ? h.n_ev / XD_TE + 1 : h.n_tr / XD_THREADS + 1);
+            }
+            decode_block(b, big);
+        }
     }
-    xchg_tail_kernel<<<1, 1, 0, stream>>>(D.occ_off, n_tr, n_occ, D.ev_off, n_ev);
+    xchg_tail_kernel<<<1, 1, 0, J>>>(D.occ_off, D.ev_off, &dx->run);
     SIESTA_LAUNCHED();
-    xchg_ack_kernel<<<1, 32, 0, stream>>>(x->peers, world, rank, seq);
+    xchg_ack_kernel<<<1, 32, 0, J>>>(x->peers, world, rank, seq_last);
     SIESTA_LAUNCHED();
-    SIESTA_CUDA_OK(cudaEventRecord(ev[3], stream));
+    SIESTA_CUDA_OK(cudaEventRecord(ev[EV_J1], J));
+    SIESTA_CUDA_OK(cudaMemcpyAsync(hx->hdrs, dx->hdrs, sizeof(XHeader) * XCHG_MAX_RANKS * (size_t)C, cudaMemcpyDeviceToHost, J));
+    SIESTA_CUDA_OK(cudaMemcpyAsync(&hx->run, &dx->run, sizeof(XRun) + sizeof(int), cudaMemcpyDeviceToHost, J));
+    SIESTA_CUDA_OK(cudaStreamSynchronize(J));   // host wait 2 of 2: the joined list is complete on this rank
+    SIESTA_CUDA_OK(cudaStreamSynchronize(S));
+    const XRun run = hx->run;
+    bad = (hx->flag ? XST_TIMEOUT : 0) | run.status;
+    if (bad) {   // (already acknowledged)
+        rc = SIESTA_OK;
+        if (bad & XST_TIMEOUT) {
+            set_error("exchange: a peer did not arrive within the time limit (or is out of step)");
+            return SIESTA_E_CUDA;
+        }
+        if (bad & XST_LIMITS) {
+            set_error("exchange: too many traces beyond the engine limits on some rank, or its verification failed (see siesta_detect)");
+            return SIESTA_E_UNSUPPORTED;
+        }
+        if (bad & XST_RANGE) {
+            set_error("exchange: a value does not fit the compact block (trace longer than 65 535 events, activity id >= 65 536, "
+                      "a timestamp more than 2^31 units from the trace's first reported event)");
+            return SIESTA_E_UNSUPPORTED;
+        }
+        set_error("exchange: staging overflow or too many reference errors on some rank");
+        return SIESTA_E_NOMEM;
+    }
+    const int64_t n_tr = run.n_tr, n_occ = run.n_occ, n_ev = run.n_ev, n_err = run.n_err, n_unsup = run.n_unsup;
     if (n_err > 0) {   // the (rare) error list in ascending order
         std::vector<int64_t> herr((size_t)n_err);
-        SIESTA_CUDA_OK(cudaMemcpyAsync(herr.data(), D.err, (size_t)n_err * 8, cudaMemcpyDeviceToHost, stream));
-        SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+        SIESTA_CUDA_OK(cudaMemcpyAsync(herr.data(), D.err, (size_t)n_err * 8, cudaMemcpyDeviceToHost, J));
+        SIESTA_CUDA_OK(cudaStreamSynchronize(J));
         std::sort(herr.begin(), herr.end());
-        SIESTA_CUDA_OK(cudaMemcpyAsync(D.err, herr.data(), (size_t)n_err * 8, cudaMemcpyHostToDevice, stream));
+        SIESTA_CUDA_OK(cudaMemcpyAsync(D.err, herr.data(), (size_t)n_err * 8, cudaMemcpyHostToDevice, J));
+        SIESTA_CUDA_OK(cudaStreamSynchronize(J));
     }
     if (n_unsup > 0) {   // per-rank lists arrive in completion order
         std::vector<int64_t> hu((size_t)n_unsup);
-        SIESTA_CUDA_OK(cudaMemcpyAsync(hu.data(), D.unsup, (size_t)n_unsup * 8, cudaMemcpyDeviceToHost, stream));
-        SIESTA_CUDA_OK(cudaStreamSynchronize(stream));
+        SIESTA_CUDA_OK(cudaMemcpyAsync(hu.data(), D.unsup, (size_t)n_unsup * 8, cudaMemcpyDeviceToHost, J));
+        SIESTA_CUDA_OK(cudaStreamSynchronize(J));
         std::sort(hu.begin(), hu.end());
-        SIESTA_CUDA_OK(cudaMemcpyAsync(D.unsup, hu.data(), (size_t)n_unsup * 8, cudaMemcpyHostToDevice, stream));
+        SIESTA_CUDA_OK(cudaMemcpyAsync(D.unsup, hu.data(), (size_t)n_unsup * 8, cudaMemcpyHostToDevice, J));
+        SIESTA_CUDA_OK(cudaStreamSynchronize(J));
     }
-    SIESTA_CUDA_OK(cudaStreamSynchronize(stream));   // host wait 2 of 2: the joined list is complete on this rank
-    float ms_scan = 0.f, ms_wait = 0.f, ms_pull = 0.f;
-    cudaEventElapsedTime(&ms_scan, ev[0], ev[1]);
-    cudaEventElapsedTime(&ms_wait, ev[1], ev[2]);
-    cudaEventElapsedTime(&ms_pull, ev[4], ev[3]);
-    float ms_gap = 0.f;   // the device idles while the host reads the sizes and allocates the joined result
-    cudaEventElapsedTime(&ms_gap, ev[2], ev[4]);
+    float ms_scan = 0.f, ms_tail = 0.f, ms_all = 0.f, ms_join = 0.f;
+    cudaEventElapsedTime(&ms_scan, ev[EV_S0], ev[EV_S1]);
+    cudaEventElapsedTime(&ms_all, ev[EV_S0], ev[EV_J1]);
+    cudaEventElapsedTime(&ms_join, ev[EV_J0], ev[EV_J1]);
+    ms_tail = ms_all - ms_scan;   // what the join adds behind the last block's announcement
+    float k1_ms = 0.f;
+    for (DetectPending* q : pend) k1_ms += detect_pending_k1_ms(q);
 
     DevMatchesImpl* impl = new DevMatchesImpl();
-    impl->block = fin;
+    impl->block = fin_owned;
     impl->owner = x->ctx;
+    void* fin = fin_owned;
     fin_owned = nullptr;   // the result owns the block now
     out->n_traces = n_tr;
     out->n_occurrences = n_occ;
     out->n_events = n_ev;
     const bool counted = (flags & (SIESTA_F_COUNT_MATCHES | SIESTA_F_RETURN_ALL | SIESTA_F_LITERAL_RUNS)) != 0;
-    out->n_matches_emitted = counted ? emitted : -1;
+    out->n_matches_emitted = counted ? run.n_emitted : -1;
     out->n_ref_errors = n_err;
-    out->kernel_ms = ms_scan + ms_wait + ms_gap + ms_pull;
+    out->kernel_ms = ms_all;
     out->detect_ms = k1_ms;
     out->d_trace_idx = D.trace_idx;
     out->d_occ_off = D.occ_off;
@@ -646,25 +902,30 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
     out->n_unsupported = n_unsup;
     out->d_unsupported_trace_idx = D.unsup;
     out->d_block = fin;
-    out->block_bytes = (int64_t)f_off;
+    out->block_bytes = (int64_t)f_bytes;
     out->impl = impl;
     if (stats) {
-        const XHeader& mine = x->h_hdrs[rank];
-        stats->local_traces = mine.n_tr;
-        stats->local_occurrences = mine.n_occ;
-        stats->local_events = mine.n_ev;
+        int64_t wire = 0;
+        for (int b = 0; b < C; ++b)
+            for (int p = 0; p < world; ++p) {
+                const XHeader& h = hx->hdrs[b * XCHG_MAX_RANKS + p];
+                if (p == rank) {
+                    stats->local_traces += h.n_tr;
+                    stats->local_occurrences += h.n_occ;
+                    stats->local_events += h.n_ev;
+                    continue;
+                }
+                wire += h.n_tr * (4 + (all_cols ? 8 : 0)) + (h.uniform_k ? 0 : 4 * (h.n_tr + h.n_occ + 2)) + h.n_ev * (all_cols ? 9 : 2) + 8 * h.n_err;
+            }
         stats->k1_ms = k1_ms;
         stats->scan_ms = ms_scan;
-        stats->wait_ms = ms_wait;
-        stats->pull_ms = ms_pull;
-        stats->host_gap_ms = ms_gap;
-        int64_t wire = 0;
-        for (int p = 0; p < world; ++p) {
-            if (p == rank) continue;
-            const XHeader& h = x->h_hdrs[p];
-            wire += h.n_tr * (4 + (all_cols ? 8 : 0)) + (h.uniform_k ? 0 : 4 * (h.n_tr + h.n_occ + 2)) + h.n_ev * (all_cols ? 9 : 2) + 8 * h.n_err;
-        }
+        stats->wait_ms = 0.0;
+        stats->pull_ms = ms_tail > 0.f ? ms_tail : 0.f;
+        stats->host_gap_ms = 0.0;
         stats->pulled_bytes = wire;
+        stats->n_blocks = C;
+        stats->eager = eager ? 1 : 0;
+        stats->join_ms = ms_join;
     }
     return SIESTA_OK;
 }
@@ -687,8 +948,8 @@ extern "C" int siesta_exchange_allreduce_i64(siesta_exchange* xh, int64_t* d_buf
     cudaStream_t user = reinterpret_cast<cudaStream_t>(stream_);
     const unsigned long long seq = ++x->seq;
     XCtrl* me = reinterpret_cast<XCtrl*>(x->region);
-    int* d_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(x->d_hdrs) + sizeof(XHeader) * XCHG_MAX_RANKS);
-    int* h_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(x->h_hdrs) + sizeof(XHeader) * XCHG_MAX_RANKS);
+    int* d_flag = &x->d_x->flag;
+    int* h_flag = &x->h_x->flag;
     // order after the producer of d_buf on the caller's stream
     cudaEvent_t evu;
     SIESTA_CUDA_OK(cudaEventCreateWithFlags(&evu, cudaEventDisableTiming));
@@ -701,9 +962,9 @@ extern "C" int siesta_exchange_allreduce_i64(siesta_exchange* xh, int64_t* d_buf
     XHeader hd;
     std::memset(&hd, 0, sizeof(hd));
     hd.seq = seq;
-    SIESTA_CUDA_OK(cudaMemcpyAsync(&me->hdr, &hd, sizeof(hd), cudaMemcpyHostToDevice, stream));
+    SIESTA_CUDA_OK(cudaMemcpyAsync(&me->hdr[0], &hd, sizeof(hd), cudaMemcpyHostToDevice, stream));
     if (n) SIESTA_CUDA_OK(cudaMemcpyAsync(x->region + XCHG_CTRL_BYTES, d_buf, (size_t)n * 8, cudaMemcpyDeviceToDevice, stream));
-    xchg_signal_kernel<<<1, 32, 0, stream>>>(x->peers, x->world, x->rank, seq, x->d_hdrs, d_flag);
+    xchg_signal_kernel<<<1, 32, 0, stream>>>(x->peers, x->world, x->rank, seq, x->d_x->hdrs, d_flag);
     SIESTA_LAUNCHED();
     if (n) {
         const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)x->ctx->sm_count * 4);

@@ -72,6 +72,65 @@ def _run_sharded(ctx, off, act, ts, n_act, nfa, flags, bounds):
     return res
 
 
+def _run_blocked(ctx, off, act, ts, n_act, nfa, flags, world, bounds, rounds=2):
+    """Block-cyclic shards: bounds = global trace boundaries of C * world blocks; rank r holds blocks r, world + r, ...
+    (siesta_log_set_blocks).  Returns every rank's joined result (+ stats)."""
+    from sequencedetectionqueryexecutor_b200 import api
+    nb = len(bounds) - 1
+    assert nb % world == 0
+    C_ = nb // world
+    logs = []
+    for r in range(world):
+        offs, acts, tss, local_first, global_first, n_ev = [np.zeros(1, np.int64)], [], [], [0], [], 0
+        for c in range(C_):
+            lo, hi = bounds[c * world + r], bounds[c * world + r + 1]
+            e0, e1 = int(off[lo]), int(off[hi])
+            offs.append(off[lo + 1:hi + 1] - e0 + n_ev)
+            n_ev += e1 - e0
+            acts.append(act[e0:e1])
+            tss.append(ts[e0:e1])
+            local_first.append(local_first[-1] + hi - lo)
+            global_first.append(lo)
+        lg = ctx.load_log(np.concatenate(offs), np.concatenate(acts) if acts else np.zeros(0, np.int32),
+                          np.concatenate(tss) if tss else np.zeros(0, np.int64), n_act)
+        lg.set_blocks(local_first, global_first)
+        logs.append(lg)
+    need = max(api.exchange_required_bytes(lg, nfa, flags) for lg in logs)
+    xs = [api.Exchange(ctx, world, r, need) for r in range(world)]
+    for a in xs:
+        for b in xs:
+            if a is not b:
+                a.connect_local(b)
+    out, err = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            for _ in range(rounds):
+                if out[r] is not None:
+                    out[r][0].close()
+                out[r] = xs[r].detect_allgather(logs[r], nfa, flags)
+        except Exception as e:  # noqa: BLE001
+            err[r] = e
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    res = None
+    if not any(err):
+        res = [(_to_result(dm), st) for dm, st in out]
+    for o in out:
+        if o is not None:
+            o[0].close()
+    for x in xs:
+        x.close()
+    for lg in logs:
+        lg.close()
+    assert not any(err), err
+    return res
+
+
 CASES = [
     ("gap6 uniform block (K1-P)", GAP6, 0, dict(min_len=50, max_len=50, n_act=20)),
     ("gap6, positions only", GAP6, abi.F_NO_EVENT_COLUMNS, dict(min_len=30, max_len=60, n_act=20)),
@@ -102,6 +161,49 @@ def test_sharded_allgather_equals_unsharded_oracle(name, states, flags, shape):
                 assert ok, (name, bounds, r, why)
                 local += st.local_traces
             assert local == want.n_traces
+
+
+@pytest.mark.parametrize("name,states,flags,shape", CASES, ids=[c[0] for c in CASES])
+def test_block_cyclic_shards_join_while_scanning(name, states, flags, shape):
+    """siesta_log_set_blocks: the shards are block-cyclic, every block is verified, placed and announced on its own while
+    the blocks before it are pulled and decoded; the joined list of EVERY rank equals the oracle's result on the unsharded
+    log, in global trace order.  Uniform results take the eager path (worst-case allocation, device-side running offsets),
+    the others decode after the last block."""
+    from sequencedetectionqueryexecutor_b200 import api
+    n_act = shape["n_act"]
+    off, act, ts = gen.make_log(3000, shape["min_len"], shape["max_len"], n_act, seed=0xB10C + len(name),
+                                max_gap_s=shape.get("max_gap_s", 300), jitter_ms=True)
+    nfa = abi.make_nfa(states)
+    want = oracle.detect(off, act, ts, nfa, flags=flags)
+    T = len(off) - 1
+    uniform = not (flags & abi.F_RETURN_ALL) and all(st["kind"] not in (P_, S_) for st in states)
+    with api.Context(0) as ctx:
+        for world, bounds in ((3, [0, 400, 700, 1000, 1300, 1500, 1900, 2000, 2600, T]),          # 3 ranks x 3 blocks
+                              (2, [0, 0, 500, 500, 1200, 1200, 1200, 2100, T]),                       # 2 ranks x 4 blocks, empty ones
+                              (4, list(range(0, T, T // 16))[:16] + [T])):                         # 4 ranks x 4 blocks
+            res = _run_blocked(ctx, off, act, ts, n_act, nfa, flags, world, bounds)
+            local = 0
+            for r, (got, st) in enumerate(res):
+                ok, why = got.same_as(want)
+                assert ok, (name, world, r, why)
+                assert st.n_blocks == (len(bounds) - 1) // world and st.eager == (1 if uniform else 0), (st.n_blocks, st.eager)
+                local += st.local_traces
+            assert local == want.n_traces
+
+
+def test_blocked_eager_limit_falls_back_to_exact_allocation(monkeypatch):
+    """SIESTA_XCHG_EAGER_MAX_BYTES below the worst case: the same request decodes after the last block, same result."""
+    from sequencedetectionqueryexecutor_b200 import api
+    off, act, ts = gen.make_log(2000, 50, 50, 20, seed=0xEA6E)
+    nfa = abi.make_nfa(GAP6)
+    want = oracle.detect(off, act, ts, nfa, flags=0)
+    monkeypatch.setenv("SIESTA_XCHG_EAGER_MAX_BYTES", "1000")
+    with api.Context(0) as ctx:
+        res = _run_blocked(ctx, off, act, ts, 20, nfa, 0, 2, [0, 300, 800, 1000, 1700, 1800, 2000])
+        for got, st in res:
+            ok, why = got.same_as(want)
+            assert ok, why
+            assert st.eager == 0 and st.n_blocks == 3
 
 
 def test_long_and_unaligned_traces_cross_shards():
