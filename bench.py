@@ -104,30 +104,37 @@ def make_log_fast(n_traces, min_len, max_len, n_act, seed, max_gap_s, rank=0):
     return off, act, ts
 
 
-def make_log_device(torch, dev, t_begin, t_end, n_total, length, n_act, seed, max_gap_s):
-    """Traces [t_begin, t_end) of the fixed-length synthetic log, generated on the GPU (the 100 M-trace log is 60.8 GB:
-    it never exists on the host).  The generator is keyed by (seed, chunk of CHUNK traces), so a shard holds exactly
-    the traces the one-GPU run holds at the same global indices, whatever N is."""
-    n = t_end - t_begin
+def make_log_device(torch, dev, t_begin, t_end, n_total, length, n_act, seed, max_gap_s, ranges=None):
+    """Traces [t_begin, t_end) - or the trace ranges `ranges` back to back (a block-cyclic shard) - of the fixed-length
+    synthetic log, generated on the GPU (the 100 M-trace log is 60.8 GB: it never exists on the host).  The generator is
+    keyed by (seed, chunk of CHUNK traces), so a shard holds exactly the traces the one-GPU run holds at the same global
+    indices, whatever N and the block layout are."""
+    if ranges is None:
+        ranges = [(t_begin, t_end)]
+    n = sum(hi - lo for lo, hi in ranges)
     E = n * length
     off = torch.arange(0, E + 1, length, dtype=torch.int64, device=dev)
     act = torch.empty(E, dtype=torch.int32, device=dev)
     ts = torch.empty(E, dtype=torch.int64, device=dev)
     g = torch.Generator(device=dev)
-    for c in range(t_begin // CHUNK, (t_end + CHUNK - 1) // CHUNK):
-        c0, c1 = c * CHUNK, min(n_total, (c + 1) * CHUNK)
-        m = c1 - c0
-        g.manual_seed(int(seed) * 1000003 + c)
-        a = torch.randint(0, n_act, (m * length,), dtype=torch.int32, device=dev, generator=g)
-        gaps = torch.randint(1, max_gap_s + 1, (m, length), dtype=torch.int64, device=dev, generator=g)
-        gaps *= 1000
-        torch.cumsum(gaps, dim=1, out=gaps)
-        start = 1577836800000 + torch.randint(0, 30 * 86400, (m, 1), dtype=torch.int64, device=dev, generator=g) * 1000
-        gaps += start
-        lo, hi = max(c0, t_begin), min(c1, t_end)     # the part of the chunk this shard owns
-        act[(lo - t_begin) * length:(hi - t_begin) * length] = a[(lo - c0) * length:(hi - c0) * length]
-        ts[(lo - t_begin) * length:(hi - t_begin) * length] = gaps.view(-1)[(lo - c0) * length:(hi - c0) * length]
-        del a, gaps, start
+    at = 0   # local index of the range's first trace
+    for r_lo, r_hi in ranges:
+        for c in range(r_lo // CHUNK, (r_hi + CHUNK - 1) // CHUNK):
+            c0, c1 = c * CHUNK, min(n_total, (c + 1) * CHUNK)
+            m = c1 - c0
+            g.manual_seed(int(seed) * 1000003 + c)
+            a = torch.randint(0, n_act, (m * length,), dtype=torch.int32, device=dev, generator=g)
+            gaps = torch.randint(1, max_gap_s + 1, (m, length), dtype=torch.int64, device=dev, generator=g)
+            gaps *= 1000
+            torch.cumsum(gaps, dim=1, out=gaps)
+            start = 1577836800000 + torch.randint(0, 30 * 86400, (m, 1), dtype=torch.int64, device=dev, generator=g) * 1000
+            gaps += start
+            lo, hi = max(c0, r_lo), min(c1, r_hi)     # the part of the chunk this range owns
+            d0 = at + (lo - r_lo)
+            act[d0 * length:(d0 + hi - lo) * length] = a[(lo - c0) * length:(hi - c0) * length]
+            ts[d0 * length:(d0 + hi - lo) * length] = gaps.view(-1)[(lo - c0) * length:(hi - c0) * length]
+            del a, gaps, start
+        at += r_hi - r_lo
     return off, act, ts
 
 
@@ -316,6 +323,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--blocks", type=int, default=10,
+                    help="N > 1: blocks per shard of the block-cyclic layout (1 = contiguous shards, no overlap of join and scan)")
     ap.add_argument("--join", default="allgather", choices=["allgather", "none"],
                     help="N > 1: allgather = every rank ends the step with the decoded match list of all ranks")
     args = ap.parse_args()
@@ -352,7 +361,18 @@ def main():
     flags = wl.get("flags", 0)
     fixed = wl["min_len"] == wl["max_len"]
     NT = wl["n_traces"]
-    if fixed:
+    blocks = None     # block-cyclic shard: [(global first, global end)] of this rank's blocks
+    if fixed and world > 1 and args.join == "allgather" and args.blocks > 1:
+        # Block-cyclic shards (siesta_log_set_blocks): the log is cut into blocks * world blocks of consecutive traces, rank
+        # r holds blocks r, world + r, ...: block b + 1 is scanned while block b of every rank is pulled and decoded.
+        nb = args.blocks * world
+        bounds = [(NT * i) // nb for i in range(nb + 1)]
+        if NT >= nb * CHUNK:
+            bounds = [min(NT, -(-b // CHUNK) * CHUNK) for b in bounds]     # block boundaries on generator chunks
+        blocks = [(bounds[c * world + rank], bounds[c * world + rank + 1]) for c in range(args.blocks)]
+        t_lo, t_hi = blocks[0]
+        d_off, d_act, d_ts = make_log_device(torch, dev, 0, 0, NT, wl["min_len"], wl["n_act"], wl["seed"], wl["max_gap_s"], ranges=blocks)
+    elif fixed:
         per = -(-NT // world)
         per = -(-per // CHUNK) * CHUNK if NT >= world * CHUNK else per     # shard boundaries on generator chunks
         t_lo, t_hi = min(NT, rank * per), min(NT, (rank + 1) * per)
@@ -374,6 +394,11 @@ def main():
     ctx = api.Context(local_rank)
     log = ctx.wrap_log(d_off, d_act, d_ts, wl["n_act"], max_trace_len=wl["max_len"])
     log.set_first_trace(t_lo)
+    if blocks is not None:
+        local_first = [0]
+        for lo, hi in blocks:
+            local_first.append(local_first[-1] + hi - lo)
+        log.set_blocks(local_first, [lo for lo, _ in blocks])
 
     def barrier():
         if world > 1:
@@ -393,7 +418,8 @@ def main():
             # scan of the shard + device-side all-gather: returns when this rank holds every rank's decoded columns
             dm, st = join.detect_allgather(log, nfa, flags)
             out = (st.local_traces, st.local_occurrences, st.local_events, dm.n_matches_emitted, dm.kernel_ms, st.k1_ms,
-                   dm.n_traces, st.wait_ms + st.host_gap_ms + st.pull_ms, st.scan_ms, st.wait_ms, st.pull_ms, st.pulled_bytes, st.host_gap_ms)
+                   dm.n_traces, st.wait_ms + st.host_gap_ms + st.pull_ms, st.scan_ms, st.wait_ms, st.pull_ms, st.pulled_bytes, st.host_gap_ms,
+                   st.n_blocks, st.eager, st.join_ms)
         else:
             dm = log.detect_device(nfa, flags=flags)
             out = (dm.n_traces, dm.n_occurrences, dm.n_events, dm.n_matches_emitted, dm.kernel_ms, dm.detect_ms, dm.n_traces, 0.0)
@@ -433,7 +459,7 @@ def main():
 
     # ---- parity on the sample: the first SAMPLE_TRACES traces of the log live on rank 0; at N > 1 rank LAST decodes
     # them out of the joined list it received (the exchanged bytes are what is checked), at N = 1 rank 0 re-runs them
-    ns = min(SAMPLE_TRACES, T) if rank == 0 else 0
+    ns = min(SAMPLE_TRACES, T if blocks is None else blocks[0][1] - blocks[0][0]) if rank == 0 else 0
     s_off = s_act = s_ts = None
     if rank == 0:
         e = int(d_off[ns].item())
@@ -513,9 +539,13 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": config_of(args, wl),
             "layout": {"traces_per_gpu": T, "events_per_gpu": E,
-                       "parallelism": f"traces sharded over {world} GPU(s) by contiguous range" +
-                                      ("; every rank ends the step with the decoded match list of all ranks (one fused "
-                                       "pull + decode kernel over NVLink peer memory, sizes in-band)" if join is not None else ""),
+                       "parallelism": (f"traces sharded over {world} GPU(s) " +
+                                       (f"block-cyclically ({args.blocks} blocks per rank of {blocks[0][1] - blocks[0][0]} traces)"
+                                        if blocks is not None else "by contiguous range")) +
+                                      ("; every rank ends the step with the decoded match list of all ranks in global trace order "
+                                       "(pull + decode kernels over NVLink peer memory, sizes in-band" +
+                                       (", block b pulled and decoded while block b + 1 is scanned)" if blocks is not None else ")")
+                                       if join is not None else ""),
                        "l2": (f"inputs ({12 * E / 1e9:.2f} GB/GPU resident, {wl['bytes_per_event']} B/event read) "
                               + ("larger than L2; no flush needed" if flush is None else
                                  "SMALLER than L2: a 512 MB buffer is rewritten between steps"))},
@@ -531,9 +561,12 @@ def main():
             "p50_latency_ms": float(np.percentile(lat, 50)),
             "exchange": ({"ms": float(np.mean(x_ms)), "scan_and_place_ms": r[8], "wait_for_slowest_rank_ms": r[9],
                           "host_sizes_and_alloc_ms": r[12], "pull_and_decode_ms": r[10], "pulled_bytes_per_rank": r[11],
-                          "nvlink_GBps_in": r[11] / max(r[10], 1e-9) / 1e6,
-                          "what": "siesta_detect_allgather: compact blocks placed in peer-mapped regions, sizes in-band, one "
-                                  "fused pull + decode kernel, two host waits per request"} if join is not None else None),
+                          "nvlink_GBps_in": r[11] / max(r[15] if r[13] > 1 else r[10], 1e-9) / 1e6,
+                          "blocks_per_rank": r[13], "eager_allocation": bool(r[14]), "join_stream_ms": r[15],
+                          "what": "siesta_detect_allgather: compact blocks placed in peer-mapped regions, sizes in-band, pull + decode "
+                                  "kernels on a second stream (block-cyclic shards: overlapped with the scan of the next block; "
+                                  "pull_and_decode_ms is then what the join adds behind the last block), two host waits per request"}
+                         if join is not None else None),
             "gpu_launches": launches,
             "clocks": clocks,
             "result": {"matching_traces_rank0": r[0], "occurrences_rank0": r[1], "events_rank0": r[2],

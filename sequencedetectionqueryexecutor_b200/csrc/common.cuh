@@ -175,7 +175,7 @@ struct PackTarget {
     int64_t shard_traces = 0;  // -> XHeader::shard_traces
 };
 int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand, uint32_t flags,
-                             cudaStream_t stream, RebaseOffsets base, DetectPending** pending);
+                             cudaStream_t stream, RebaseOffsets base, DetectPending** pending, const DetectPending* sibling = nullptr);
 int detect_device_pack_impl(DetectPending* q, const PackTarget& tgt);   // enqueues only, no host wait
 void detect_pending_discard(DetectPending* q);
 float detect_pending_k1_ms(DetectPending* q);                            // releases the request (stream-ordered)

@@ -913,6 +913,8 @@ struct DetectPending {
     int uniform_k = 0;                    // > 0: one occurrence per trace, uniform_k events each (class NK, first-largest)
     cudaEvent_t ev0 = nullptr, evd = nullptr;
     unsigned long long* h_cnt = nullptr;  // pinned, 16 words
+    const uint16_t* d_lut = nullptr;      // the request's tables on the device (a later block of the same request reuses them)
+    const uint4* d_nkp_lut = nullptr;
 };
 
 static unsigned long long* pinned_counters_get(Ctx* c) {
@@ -945,7 +947,10 @@ static void pending_discard(DetectPending* q) {
 int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out);
 
 int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_cand, int64_t n_cand, uint32_t flags,
-                             cudaStream_t stream, RebaseOffsets base, DetectPending** pending) {
+                             cudaStream_t stream, RebaseOffsets base, DetectPending** pending, const DetectPending* sibling) {
+    // sibling: an earlier block of the SAME request (same NFA, flags, alphabet) on the exchange path - its device tables
+    // are reused and the counters are not copied to the host (the placement reads them on the device), so the block adds
+    // no copy to the stream and the host runs ahead of the device.
     *pending = nullptr;
     base.trace += log->first_trace;
     DevNfa dn;
@@ -1022,6 +1027,7 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
     SIESTA_CUDA_OK(cudaEventCreate(&ev0));
     SIESTA_CUDA_OK(cudaEventCreate(&evd));
     unsigned long long* h_cnt = nullptr;
+    const uint4* d_nkp_lut = nullptr;
     struct BeginGuard {   // an error return of the first half releases what it holds so far
         cudaEvent_t &a, &b;
         unsigned long long*& h;
@@ -1034,7 +1040,7 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
             pinned_counters_put(c, h);
         }
     } begin_guard{ev0, evd, h_cnt, log->ctx, true};
-    SIESTA_CUDA_OK(cudaMemcpyAsync(b_lut.p, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
+    if (!sibling) SIESTA_CUDA_OK(cudaMemcpyAsync(b_lut.p, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
     SIESTA_CUDA_OK(cudaMemsetAsync(b_counters.p, 0, 256, stream));
     SIESTA_CUDA_OK(cudaMemsetAsync(b_blk.p, 0, n_blk * 3 * 8, stream));
     SIESTA_CUDA_OK(cudaEventRecord(ev0, stream));
@@ -1047,7 +1053,7 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
     P.cand = d_cand;
     P.work = nullptr;
     P.n_work = n;
-    P.lut = b_lut.as<uint16_t>();
+    P.lut = sibling ? sibling->d_lut : b_lut.as<uint16_t>();
     P.n_act = log->n_activities;
     P.n_events = log->n_events;
     // classes: the pattern's activities numbered 1..K
@@ -1121,8 +1127,12 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
                 nlut[4 * a + 0] = (nkw_space == NKW_RAW || c) ? 2u : 1u;
                 for (int p = 0; p < 3; ++p) nlut[4 * a + 1 + p] = (c >> p) & 1;
             }
-            SIESTA_CUDA_OK(cudaMemcpyAsync(wb + o_nlut, nlut.data(), nlut.size() * 4, cudaMemcpyHostToDevice, stream));
-            N.nkp_lut = reinterpret_cast<const uint4*>(wb + o_nlut);
+            if (sibling && sibling->d_nkp_lut) N.nkp_lut = sibling->d_nkp_lut;
+            else {
+                SIESTA_CUDA_OK(cudaMemcpyAsync(wb + o_nlut, nlut.data(), nlut.size() * 4, cudaMemcpyHostToDevice, stream));
+                N.nkp_lut = reinterpret_cast<const uint4*>(wb + o_nlut);
+            }
+            d_nkp_lut = N.nkp_lut;
             N.n_planes = sigs.size() <= 1 ? 1 : (sigs.size() <= 3 ? 2 : 3);
             std::memset(N.st_inv, 0, sizeof(N.st_inv));
             std::memset(N.st_single, 0, sizeof(N.st_single));
@@ -1183,7 +1193,7 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
             SIESTA_LAUNCHED();
             SIESTA_CUDA_OK(cudaGetLastError());
         }
-        SIESTA_CUDA_OK(cudaMemcpyAsync(h_cnt, b_counters.p, 128, cudaMemcpyDeviceToHost, stream));
+        if (!sibling) SIESTA_CUDA_OK(cudaMemcpyAsync(h_cnt, b_counters.p, 128, cudaMemcpyDeviceToHost, stream));
     }
     // ---- end of the first half: nothing above waits for the device
     DetectPending* q = new DetectPending();
@@ -1206,6 +1216,8 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
     q->ev0 = ev0;
     q->evd = evd;
     q->h_cnt = h_cnt;
+    q->d_lut = P.lut;
+    q->d_nkp_lut = d_nkp_lut;
     begin_guard.armed = false;
     *pending = q;
     return SIESTA_OK;

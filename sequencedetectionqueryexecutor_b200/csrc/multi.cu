@@ -383,7 +383,8 @@ extern "C" int siesta_exchange_create(siesta_ctx* ctx, int32_t world, int32_t ra
     if (e == cudaSuccess) {
         int lo = 0, hi = 0;   // (lowest, greatest) priority; greatest is numerically smallest
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        e = cudaStreamCreateWithPriority(&x->jstream, cudaStreamNonBlocking, hi);
+        const char* env = std::getenv("SIESTA_XCHG_JOIN_PRIORITY");   // tuning aid: "low" = the join's CTAs yield to the scan's
+        e = cudaStreamCreateWithPriority(&x->jstream, cudaStreamNonBlocking, env && env[0] == 'l' ? lo : hi);
     }
     if (e == cudaSuccess) {
         // Load every kernel and driver-internal copy path a collective uses NOW: with lazy module loading the first
@@ -551,7 +552,6 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
     if (stats) std::memset(stats, 0, sizeof(*stats));
     std::lock_guard<std::mutex> lock(x->mu);
     SIESTA_CUDA_OK(cudaSetDevice(x->ctx->device));
-    cudaStream_t S = x->stream, J = x->jstream;
     const int world = x->world, rank = x->rank;
     XCtrl* me = reinterpret_cast<XCtrl*>(x->region);
     XDev* dx = x->d_x;
@@ -562,6 +562,8 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
     // order, on stream S; operation numbers are consecutive, block b of this request is operation seq0 + 1 + b
     int64_t b_lo[XCHG_MAX_BLOCKS], b_hi[XCHG_MAX_BLOCKS], b_glob[XCHG_MAX_BLOCKS];
     const int C = log_blocks(L, b_lo, b_hi, b_glob);
+    // one block: nothing to overlap, the join follows the scan on the same stream
+    cudaStream_t S = x->stream, J = (C == 1 && std::getenv("SIESTA_XCHG_TWO_STREAMS") == nullptr) ? x->stream : x->jstream;
     const unsigned long long seq0 = x->seq;
     x->seq += (unsigned long long)C;
     const unsigned long long seq_last = seq0 + (unsigned long long)C;
@@ -583,7 +585,7 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
         }
     }
 
-    enum { EV_S0 = 0, EV_S1, EV_J0, EV_J1, EV_RESET, EV_H0, N_EV };
+    enum { EV_S0 = 0, EV_S1, EV_J0, EV_J1, EV_RESET, EV_H0, EV_D0, N_EV };
     cudaEvent_t ev[N_EV] = {nullptr};
     struct EvGuard {
         cudaEvent_t* e;
@@ -608,7 +610,8 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
     std::string first_error;
     for (int b = 0; b < C; ++b) {
         if (!rc) {
-            const int rcb = detect_device_begin_impl(&view[(size_t)b], nfa, nullptr, 0, flags, S, RebaseOffsets{0, 0, 0}, &pend[(size_t)b]);
+            const int rcb = detect_device_begin_impl(&view[(size_t)b], nfa, nullptr, 0, flags, S, RebaseOffsets{0, 0, 0}, &pend[(size_t)b],
+                                                     b > 0 ? pend[0] : nullptr);
             if (rcb) {
                 rc = rcb;
                 first_error = siesta_last_error();
@@ -756,7 +759,9 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
     };
     // grid of one block's decode: row y = source rank (me + y) % world; columns sized from the largest block
     auto decode_block = [&](int b, int64_t biggest_units) {
-        int gx = (int)std::min<int64_t>(std::max<int64_t>(biggest_units, 1), (int64_t)x->ctx->sm_count * 8 / world + 1);
+        // all rows together stay within ONE wave of resident CTAs (34 KB of shared memory each: six per SM): measured at
+        // N = 2, 148 / 296 / 593 / 1184 CTAs per row: 1.79 / 1.06 / 1.49 / 1.16 ms
+        int gx = (int)std::min<int64_t>(std::max<int64_t>(biggest_units, 1), std::max(1, x->ctx->sm_count * 4 / world));
         if (const char* env = std::getenv("SIESTA_XCHG_DECODE_CTAS")) {
             const int v = std::atoi(env);
             if (v >= 1) gx = v;
@@ -779,6 +784,7 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
             return finish_failed(0);
         }
         bind(fin_owned);
+        SIESTA_CUDA_OK(cudaEventRecord(ev[EV_D0], J));
         int64_t big = 1;
         for (int p = 0; p < world; ++p) big = std::max(big, (hx->hdrs[p].shard_traces / C + 1) * K / XD_TE + 1);
         decode_block(0, big);
@@ -815,6 +821,7 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
             return finish_failed(0, true);
         }
         bind(fin_owned);
+        SIESTA_CUDA_OK(cudaEventRecord(ev[EV_D0], J));
         for (int b = 0; b < C; ++b) {
             int64_t big = 1;
             for (int p = 0; p < world; ++p) {
@@ -919,9 +926,19 @@ extern "C" int siesta_detect_allgather(siesta_log* log, const siesta_nfa* nfa, u
             }
         stats->k1_ms = k1_ms;
         stats->scan_ms = ms_scan;
-        stats->wait_ms = 0.0;
-        stats->pull_ms = ms_tail > 0.f ? ms_tail : 0.f;
-        stats->host_gap_ms = 0.0;
+        if (C == 1) {   // one block: the phases follow one another
+            float ms_wait = 0.f, ms_gap = 0.f, ms_pull = 0.f;
+            cudaEventElapsedTime(&ms_wait, ev[EV_S1], ev[EV_H0]);
+            cudaEventElapsedTime(&ms_gap, ev[EV_H0], ev[EV_D0]);
+            cudaEventElapsedTime(&ms_pull, ev[EV_D0], ev[EV_J1]);
+            stats->wait_ms = ms_wait > 0.f ? ms_wait : 0.f;
+            stats->host_gap_ms = ms_gap;
+            stats->pull_ms = ms_pull;
+        } else {
+            stats->wait_ms = 0.0;
+            stats->pull_ms = ms_tail > 0.f ? ms_tail : 0.f;
+            stats->host_gap_ms = 0.0;
+        }
         stats->pulled_bytes = wire;
         stats->n_blocks = C;
         stats->eager = eager ? 1 : 0;
