@@ -323,8 +323,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--blocks", type=int, default=10,
-                    help="N > 1: blocks per shard of the block-cyclic layout (1 = contiguous shards, no overlap of join and scan)")
+    ap.add_argument("--blocks", type=int, default=1,
+                    help="N > 1: blocks per shard of the block-cyclic layout (siesta_log_set_blocks: block b is pulled and decoded "
+                         "while block b + 1 is scanned).  Default 1 = contiguous shards: measured faster on 2 and 8 B200 "
+                         "(profiles/r02b_exchange_blocks.md)")
     ap.add_argument("--join", default="allgather", choices=["allgather", "none"],
                     help="N > 1: allgather = every rank ends the step with the decoded match list of all ranks")
     args = ap.parse_args()
