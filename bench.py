@@ -323,6 +323,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-extra-flags", type=int, default=0,
+                    help="experiment: OR these SIESTA_F_* bits into the e2e leg's request (16 = no event columns: ev_pos only)")
+    ap.add_argument("--e2e-int32", action="store_true", help="e2e leg through the int32 activity column only (siesta_evaluate_events)")
     ap.add_argument("--blocks", type=int, default=1,
                     help="N > 1: blocks per shard of the block-cyclic layout (siesta_log_set_blocks: block b is pulled and decoded "
                          "while block b + 1 is scanned).  Default 1 = contiguous shards: measured faster on 2 and 8 B200 "
@@ -498,30 +501,48 @@ def main():
         h_ts.copy_(d_ts[:e_e])
         torch.cuda.synchronize()
         np_off, np_act, np_ts = h_off.numpy(), h_act.numpy(), h_ts.numpy()
-        for _ in range(2):  # warm: stream-ordered pool, pinned result arena
-            ctx.evaluate_events(np_off, np_act, np_ts, wl["n_act"], nfa, flags=flags, copy=False).close()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(max(1, args.e2e_steps)):
-            res = ctx.evaluate_events(np_off, np_act, np_ts, wl["n_act"], nfa, flags=flags, copy=False)
-            n_res = (res.n_traces, res.n_occurrences, res.n_events, int(res.trace_idx[-1]) if res.n_traces else -1)
-            res.close()
-        barrier()
-        e2e_sec = (time.perf_counter() - t0) / max(1, args.e2e_steps)
-        t_e2e = torch.tensor([e2e_sec], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        e2e_sec = float(t_e2e.item())
         # a query without a time constraint reads timestamps only for the events it reports, in place from the pinned host
         # column (siesta_evaluate_events): 4 B/event + 8 B per reported event / matching trace cross the link instead of 12 B/event
         ts_in_place = wl["bytes_per_event"] == 4 and not (flags & abi.F_RETURN_ALL) and not os.environ.get("SIESTA_NO_TS_ZERO_COPY")
-        h2d = 8 * (n_e + 1) + 4 * e_e + (8 * (n_res[2] + n_res[0]) if ts_in_place else 8 * e_e)
-        d2h = 8 * n_res[0] + 8 * (n_res[0] + 1) + 8 * (n_res[1] + 1) + (4 + 4 + 4 + 8) * n_res[2]
-        e2e = {"value": e_e * world / e2e_sec, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": e2e_sec * 1e3, "bound": "pcie (host link: %.1f GB/s achieved)" % ((h2d + d2h) / e2e_sec / 1e9),
-               "slice": f"first {n_e} traces ({e_e} events) of each rank's shard, pinned host memory",
-               "timestamps": "read in place from the pinned host column, reported events only" if ts_in_place else "copied to the device",
-               "call": "siesta_evaluate_events (pinned host CSR in, chunked H2D overlapped with K1, host occurrences out)"}
+        flags0 = flags
+
+        def e2e_leg(col, act_bytes, call):
+            flags = flags0 | args.e2e_extra_flags
+            for _ in range(2):  # warm: stream-ordered pool, pinned result arena
+                ctx.evaluate_events(np_off, col, np_ts, wl["n_act"], nfa, flags=flags, copy=False).close()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(max(1, args.e2e_steps)):
+                res = ctx.evaluate_events(np_off, col, np_ts, wl["n_act"], nfa, flags=flags, copy=False)
+                n_res = (res.n_traces, res.n_occurrences, res.n_events, int(res.trace_idx[-1]) if res.n_traces else -1)
+                res.close()
+            barrier()
+            sec = (time.perf_counter() - t0) / max(1, args.e2e_steps)
+            t_e2e = torch.tensor([sec], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+            sec = float(t_e2e.item())
+            no_cols = bool(flags & abi.F_NO_EVENT_COLUMNS)
+            h2d = 8 * (n_e + 1) + act_bytes * e_e + ((0 if no_cols else 8 * (n_res[2] + n_res[0])) if ts_in_place else 8 * e_e)
+            d2h = 8 * n_res[0] + 8 * (n_res[0] + 1) + 8 * (n_res[1] + 1) + (4 if no_cols else 4 + 4 + 4 + 8) * n_res[2]
+            return {"value": e_e * world / sec, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": sec * 1e3, "bound": "pcie (host link: %.1f GB/s achieved)" % ((h2d + d2h) / sec / 1e9),
+                    "slice": f"first {n_e} traces ({e_e} events) of each rank's shard, pinned host memory",
+                    "timestamps": "read in place from the pinned host column, reported events only" if ts_in_place else "copied to the device",
+                    "call": call}
+
+        e2e = e2e_leg(np_act, 4, "siesta_evaluate_events (pinned host CSR in, int32 activity column, chunked H2D overlapped with K1, host occurrences out)")
+        if wl["n_act"] <= 256 and not args.e2e_int32:
+            # the call runs at the speed of the host link, so the C-ABI also takes the activity column as one byte per event
+            # (what the JNI serialiser writes for alphabets of at most 256 activities); the int32 call stays beside it
+            h_act8 = torch.empty(e_e, dtype=torch.uint8).pin_memory()
+            h_act8.copy_(d_act[:e_e].to(torch.uint8))
+            torch.cuda.synchronize()
+            wide = e2e
+            e2e = e2e_leg(h_act8.numpy(), 1, "siesta_evaluate_events_act8 (pinned host CSR in, one byte per event for the activity column, "
+                          "widened on the device, chunked H2D overlapped with K1, host occurrences out)")
+            e2e["int32_column"] = {k: wide[k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "bound", "call")}
+            del h_act8
         del h_off, h_act, h_ts
 
     if rank == 0:

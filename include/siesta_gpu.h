@@ -268,6 +268,18 @@ int siesta_evaluate_events(siesta_ctx* ctx, const int64_t* trace_off, const int3
                            int32_t n_activities, const siesta_nfa* nfa, uint32_t flags,
                            siesta_matches** out);
 
+/* The same request with the activity column as ONE BYTE per event (n_activities
+ * <= 256).  siesta_evaluate_events runs at the speed of the host link and the
+ * activity column is what crosses it, so the caller's serialiser - the JNI shim
+ * that flattens Map<String, List<Event>> (SaseConnector.java:48) into direct
+ * buffers - writes the dictionary id into a byte: 1 B/event on the link instead
+ * of 4.  The device widens each chunk to the int32 column the kernels read.
+ * Same results as siesta_evaluate_events on the widened column. */
+int siesta_evaluate_events_act8(siesta_ctx* ctx, const int64_t* trace_off, const uint8_t* act8,
+                                const int64_t* ts_ms, int64_t n_traces, int64_t n_events,
+                                int32_t n_activities, const siesta_nfa* nfa, uint32_t flags,
+                                siesta_matches** out);
+
 /* Device-level variant used by the torch/NCCL layer: results stay in HBM.
  * All pointers are device pointers owned by the library until
  * siesta_dev_matches_free; `stream` is a cudaStream_t (NULL = the ctx stream). */

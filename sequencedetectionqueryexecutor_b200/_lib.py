@@ -13,7 +13,7 @@ _lib = None
 EXPORTS = [
     "siesta_last_error", "siesta_pattern_compile", "siesta_init", "siesta_shutdown", "siesta_log_load",
     "siesta_log_wrap_device", "siesta_log_free", "siesta_log_n_traces", "siesta_log_n_events", "siesta_detect",
-    "siesta_matches_free", "siesta_evaluate_events", "siesta_detect_device", "siesta_detect_device_begin", "siesta_detect_device_finish", "siesta_dev_matches_free",
+    "siesta_matches_free", "siesta_evaluate_events", "siesta_evaluate_events_act8", "siesta_detect_device", "siesta_detect_device_begin", "siesta_detect_device_finish", "siesta_dev_matches_free",
     "siesta_kernel_launches", "siesta_declare_counts_size", "siesta_declare_counts", "siesta_declare_counts_device",
     "siesta_index_load", "siesta_index_build", "siesta_index_free", "siesta_index_list_len", "siesta_index_get_list",
     "siesta_intersect", "siesta_intersect_device", "siesta_device_free", "siesta_pattern_extract_pairs",
@@ -67,6 +67,7 @@ def lib():
     L.siesta_matches_free.argtypes = [P(_abi.Matches)]
     L.siesta_matches_free.restype = None
     L.siesta_evaluate_events.argtypes = [vp, vp, vp, vp, i64, i64, i32, P(_abi.Nfa), u32, P(P(_abi.Matches))]
+    L.siesta_evaluate_events_act8.argtypes = [vp, vp, vp, vp, i64, i64, i32, P(_abi.Nfa), u32, P(P(_abi.Matches))]
     L.siesta_detect_device.argtypes = [vp, P(_abi.Nfa), vp, i64, u32, vp, P(_abi.DevMatches)]
     L.siesta_detect_device_begin.argtypes = [vp, P(_abi.Nfa), vp, i64, u32, vp, P(vp)]
     L.siesta_detect_device_finish.argtypes = [vp, P(_abi.DevMatches)]

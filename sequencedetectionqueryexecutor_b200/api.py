@@ -40,13 +40,19 @@ class Context:
 
     def evaluate_events(self, trace_off, act, ts_ms, n_activities, nfa, flags=0, copy=True):
         """Literal SaseConnector.evaluate: events travel host -> device inside the call (streamed in chunks).
+        An activity column of dtype uint8 (alphabets of at most 256 activities) crosses the link as it is.
         copy=False returns zero-copy views of the library's pinned result block; call .close() on the result."""
         trace_off = np.ascontiguousarray(trace_off, dtype=np.int64)
-        act = np.ascontiguousarray(act, dtype=np.int32)
         ts_ms = np.ascontiguousarray(ts_ms, dtype=np.int64)
         out = C.POINTER(_abi.Matches)()
-        check(lib().siesta_evaluate_events(self._h, _ptr(trace_off), _ptr(act), _ptr(ts_ms), len(trace_off) - 1, len(act),
-                                           n_activities, C.byref(nfa), flags, C.byref(out)))
+        if np.asarray(act).dtype == np.uint8:   # byte activity column: siesta_evaluate_events_act8 (1 B/event on the host link)
+            act = np.ascontiguousarray(act)
+            fn = lib().siesta_evaluate_events_act8
+        else:
+            act = np.ascontiguousarray(act, dtype=np.int32)
+            fn = lib().siesta_evaluate_events
+        check(fn(self._h, _ptr(trace_off), _ptr(act), _ptr(ts_ms), len(trace_off) - 1, len(act),
+                 n_activities, C.byref(nfa), flags, C.byref(out)))
         if not copy:
             return _abi.MatchResult.from_struct(out.contents, copy=False, free=lambda: lib().siesta_matches_free(out))
         res = _abi.MatchResult.from_struct(out.contents)

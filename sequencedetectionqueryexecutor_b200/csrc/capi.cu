@@ -565,17 +565,56 @@ extern "C" int siesta_detect(siesta_log* log, const siesta_nfa* nfa, const int64
 // of whole traces; chunk c + 1 (and c + 2) travel host -> device on a copy stream while chunk c is verified, so the
 // call runs at the speed of the host link.  Chunk results are rebased on the device (RebaseOffsets) and land in one
 // host block.
-extern "C" int siesta_evaluate_events(siesta_ctx* ctx, const int64_t* trace_off, const int32_t* act, const int64_t* ts_ms,
-                                      int64_t n_traces, int64_t n_events, int32_t n_activities, const siesta_nfa* nfa,
-                                      uint32_t flags, siesta_matches** out) {
-    if (!ctx || !trace_off || (!act && n_events) || (!ts_ms && n_events) || !nfa || !out || n_activities < 0) {
-        set_error("siesta_evaluate_events: null argument");
+//
+// The offsets of a chunk are validated on the host right before the chunk is enqueued (the check of chunk c + 1 runs while
+// chunk c is on the link) instead of in one serial host pass over all of trace_off in front of the first copy.
+// act8 != nullptr: the activity column arrives as one byte per event (siesta_evaluate_events_act8); it crosses the link
+// narrow and widen_act8_kernel rebuilds the int32 column the kernels read, chunk by chunk, on the run stream.
+__global__ void widen_act8_kernel(const uint8_t* __restrict__ src, int32_t* __restrict__ dst, int64_t e0, int64_t e1) {
+    // groups of four events at absolute indices [4 g, 4 g + 4): both columns come from cudaMalloc, so a whole group is one
+    // aligned 4-byte load and one aligned 16-byte store; the ragged groups at the two ends of the chunk go event by event
+    const int64_t g0 = e0 >> 2, g1 = (e1 + 3) >> 2;
+    for (int64_t g = g0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < g1; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = g << 2;
+        if (i >= e0 && i + 4 <= e1) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(src + i);
+            *reinterpret_cast<int4*>(dst + i) = make_int4((int)(w & 255u), (int)((w >> 8) & 255u), (int)((w >> 16) & 255u), (int)(w >> 24));
+        } else {
+            for (int64_t j = (i > e0 ? i : e0); j < e1 && j < i + 4; ++j) dst[j] = (int32_t)src[j];
+        }
+    }
+}
+
+static int check_csr_range(const int64_t* trace_off, int64_t t0, int64_t t1, int64_t n_events, int32_t* max_len) {
+    int64_t mx = *max_len, bad = 0;
+    for (int64_t t = t0; t < t1; ++t) {
+        const int64_t len = trace_off[t + 1] - trace_off[t];
+        bad |= len | trace_off[t + 1];   // no offset below 0, so no difference overflows
+        mx = len > mx ? len : mx;
+    }
+    if (bad < 0 || trace_off[t0] < 0 || trace_off[t1] > n_events) {
+        set_error("CSR log: trace_off must be non-decreasing and lie in [0, n_events]");
+        return SIESTA_E_INVALID;
+    }
+    *max_len = (int32_t)(mx > 0x7fffffff ? 0x7fffffff : mx);
+    return SIESTA_OK;
+}
+
+static int evaluate_events_impl(siesta_ctx* ctx, const int64_t* trace_off, const int32_t* act, const uint8_t* act8,
+                                const int64_t* ts_ms, int64_t n_traces, int64_t n_events, int32_t n_activities,
+                                const siesta_nfa* nfa, uint32_t flags, siesta_matches** out) {
+    if (!ctx || !trace_off || (!act && !act8 && n_events) || (!ts_ms && n_events) || !nfa || !out || n_activities < 0 ||
+        (act8 && n_activities > 256)) {
+        set_error(act8 && n_activities > 256 ? "siesta_evaluate_events_act8: more than 256 activities do not fit a byte column"
+                                             : "siesta_evaluate_events: null argument");
         return SIESTA_E_INVALID;
     }
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    int32_t max_len = 0;
-    int rc = check_csr(trace_off, n_traces, n_events, &max_len);
-    if (rc) return rc;
+    if (n_traces < 0 || n_events < 0 || trace_off[0] != 0 || trace_off[n_traces] != n_events) {
+        set_error("CSR log: trace_off must start at 0 and end at n_events");
+        return SIESTA_E_INVALID;
+    }
+    int rc = SIESTA_OK;
     int needs_ts = 1;
     {
         DevNfa dn;  // fail on a malformed NFA before anything is copied
@@ -607,6 +646,7 @@ extern "C" int siesta_evaluate_events(siesta_ctx* ctx, const int64_t* trace_off,
     std::vector<int64_t> cut{0};
     while (cut.back() < n_traces) {
         const int64_t t0 = cut.back();
+        // (offsets are validated chunk by chunk below; on a malformed array the search still ends inside it)
         const int64_t* lim = std::upper_bound(trace_off + t0 + 1, trace_off + n_traces + 1, trace_off[t0] + CHUNK_EVENTS);
         int64_t t1 = (int64_t)(lim - trace_off) - 1;   // last trace end <= budget
         if (t1 <= t0) t1 = t0 + 1;                      // a single trace longer than the budget
@@ -623,8 +663,10 @@ extern "C" int siesta_evaluate_events(siesta_ctx* ctx, const int64_t* trace_off,
     }
     int64_t* d_off = nullptr;
     int32_t* d_act = nullptr;
+    uint8_t* d_act8 = nullptr;
     int64_t* d_ts = nullptr;
     std::vector<cudaEvent_t> ready((size_t)n_chunks, nullptr);
+    std::vector<int32_t> chunk_max_len((size_t)n_chunks, 0);
     std::vector<siesta_dev_matches> parts;
     parts.reserve((size_t)n_chunks);
     cudaError_t e = cudaSuccess;
@@ -635,35 +677,56 @@ extern "C" int siesta_evaluate_events(siesta_ctx* ctx, const int64_t* trace_off,
     const size_t ne = (size_t)(n_events ? n_events : 1);
     ok(cudaMallocAsync((void**)&d_off, (size_t)(n_traces + 1) * 8, s_copy));
     ok(cudaMallocAsync((void**)&d_act, ne * 4 + 32, s_copy));
+    if (act8) ok(cudaMallocAsync((void**)&d_act8, ne + 32, s_copy));
     if (!ts_mapped) ok(cudaMallocAsync((void**)&d_ts, ne * 8 + 32, s_copy));
     int enq = 0;
+    int32_t max_len = 0;
     auto enqueue_copy = [&](int k) {
-        const int64_t t0 = cut[k], t1 = cut[k + 1], e0 = trace_off[t0], e1 = trace_off[t1];
+        const int64_t t0 = cut[k], t1 = cut[k + 1];
+        if (rc == SIESTA_OK) rc = check_csr_range(trace_off, t0, t1, n_events, &max_len);
+        if (rc) return;
+        chunk_max_len[(size_t)k] = max_len;   // longest trace of chunks 0 .. k: an upper bound for chunk k is all a view needs
+        const int64_t e0 = trace_off[t0], e1 = trace_off[t1];
         ok(cudaMemcpyAsync(d_off + t0, trace_off + t0, (size_t)(t1 - t0 + 1) * 8, cudaMemcpyHostToDevice, s_copy));
         if (e1 > e0) {
-            ok(cudaMemcpyAsync(d_act + e0, act + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, s_copy));
+            if (act8) ok(cudaMemcpyAsync(d_act8 + e0, act8 + e0, (size_t)(e1 - e0), cudaMemcpyHostToDevice, s_copy));
+            else ok(cudaMemcpyAsync(d_act + e0, act + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, s_copy));
             if (!ts_mapped) ok(cudaMemcpyAsync(d_ts + e0, ts_ms + e0, (size_t)(e1 - e0) * 8, cudaMemcpyHostToDevice, s_copy));
         }
         ok(cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming));
         ok(cudaEventRecord(ready[k], s_copy));
     };
     RebaseOffsets base{0, 0, 0};
+    bool ids_valid = true;
     for (int k = 0; k < n_chunks && e == cudaSuccess && rc == SIESTA_OK; ++k) {
-        while (enq < n_chunks && enq <= k + 2) enqueue_copy(enq++);
-        if (e != cudaSuccess) break;
+        while (enq < n_chunks && enq <= k + 2 && rc == SIESTA_OK) enqueue_copy(enq++);
+        if (e != cudaSuccess || rc != SIESTA_OK) break;
         ok(cudaStreamWaitEvent(s_run, ready[k], 0));
+        if (act8) {
+            const int64_t e0 = trace_off[cut[k]], n = trace_off[cut[k + 1]] - e0;
+            if (n > 0) {
+                const int64_t want = (n / 4 + 256) / 256;
+                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sm_count * 8));
+                widen_act8_kernel<<<grid, 256, 0, s_run>>>(d_act8, d_act, e0, e0 + n);
+                SIESTA_LAUNCHED();
+            }
+        }
         Log view;
         view.ctx = c;
         view.d_trace_off = d_off + cut[k];  // offsets are global event indices: act / ts_ms stay whole
         view.d_act = d_act;
         view.d_ts_ms = ts_mapped ? ts_mapped : d_ts;
         view.n_traces = cut[k + 1] - cut[k];
-        view.n_events = n_events;
+        // the view ends where the chunk ends: the 32-byte sector that holds the chunk's last event also holds the first
+        // events of chunk k + 1, which may not have arrived yet - K1-P indexes its table with whatever a sector holds, so a
+        // trace whose last sector crosses the end of the view must take the staged kernel (it does: detect_nkp.cu `fits`)
+        view.n_events = trace_off[cut[k + 1]];
         view.n_activities = n_activities;
-        view.max_trace_len = max_len;
+        view.max_trace_len = chunk_max_len[(size_t)k];
         view.owns = false;
-        view.act_valid = true;
-        if ((rc = validate_act_range(&view, trace_off[cut[k]], trace_off[cut[k + 1]] - trace_off[cut[k]], s_run))) break;
+        view.act_valid = ids_valid;
+        if (ids_valid && (rc = validate_act_range(&view, trace_off[cut[k]], trace_off[cut[k + 1]] - trace_off[cut[k]], s_run))) break;
+        ids_valid = view.act_valid;   // sticky: the first sector of chunk k + 1 holds the last events of chunk k
         siesta_dev_matches dm;
         base.trace = cut[k];
         rc = detect_device_impl(&view, nfa, nullptr, 0, flags, s_run, base, &dm);
@@ -682,6 +745,7 @@ extern "C" int siesta_evaluate_events(siesta_ctx* ctx, const int64_t* trace_off,
     cudaStreamSynchronize(s_run);
     if (d_off) cudaFreeAsync(d_off, s_run);
     if (d_act) cudaFreeAsync(d_act, s_run);
+    if (d_act8) cudaFreeAsync(d_act8, s_run);
     if (d_ts) cudaFreeAsync(d_ts, s_run);
     for (cudaEvent_t ev : ready)
         if (ev) cudaEventDestroy(ev);
@@ -689,4 +753,24 @@ extern "C" int siesta_evaluate_events(siesta_ctx* ctx, const int64_t* trace_off,
     cudaStreamDestroy(s_copy);
     cudaStreamDestroy(s_run);
     return rc;
+}
+
+extern "C" int siesta_evaluate_events(siesta_ctx* ctx, const int64_t* trace_off, const int32_t* act, const int64_t* ts_ms,
+                                      int64_t n_traces, int64_t n_events, int32_t n_activities, const siesta_nfa* nfa,
+                                      uint32_t flags, siesta_matches** out) {
+    return evaluate_events_impl(ctx, trace_off, act, nullptr, ts_ms, n_traces, n_events, n_activities, nfa, flags, out);
+}
+
+// The same request with the activity column as ONE BYTE per event (alphabets of at most 256 activities - every log the
+// reference's papers use): the call runs at the speed of the host link, and the activity column is what crosses it, so the
+// caller's serialiser (the JNI shim filling a direct buffer from List<Event>) writes the dictionary id into a byte.
+extern "C" int siesta_evaluate_events_act8(siesta_ctx* ctx, const int64_t* trace_off, const uint8_t* act8, const int64_t* ts_ms,
+                                           int64_t n_traces, int64_t n_events, int32_t n_activities, const siesta_nfa* nfa,
+                                           uint32_t flags, siesta_matches** out) {
+    if (!act8 && n_events) {
+        set_error("siesta_evaluate_events_act8: null argument");
+        return SIESTA_E_INVALID;
+    }
+    return evaluate_events_impl(ctx, trace_off, nullptr, act8 ? act8 : reinterpret_cast<const uint8_t*>(""), ts_ms, n_traces,
+                                n_events, n_activities, nfa, flags, out);
 }

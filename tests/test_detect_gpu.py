@@ -258,6 +258,44 @@ def test_evaluate_events_streams_in_chunks(ctx, monkeypatch):
     assert ctx.evaluate_events(off2, act2, ts2, 1000, nfa).same_as(oracle.detect(off2, act2, ts2, nfa))[0]
     z = ctx.evaluate_events(np.zeros(4, dtype=np.int64), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int64), 4, nfa)
     assert z.n_traces == 0 and z.occ_off.tolist() == [0]
+    # offsets are validated chunk by chunk: a decreasing offset deep inside the request fails the call, nothing is read out of bounds
+    bad = off.copy()
+    bad[2000] = bad[1999] - 1
+    with pytest.raises(SiestaError) as e:
+        ctx.evaluate_events(bad, act, ts, 6, nfa)
+    assert e.value.code == abi.E_INVALID
+
+
+def test_evaluate_events_byte_activity_column(ctx, monkeypatch):
+    """siesta_evaluate_events_act8: the activity column crosses the host link as one byte per event and is widened on the
+    device chunk by chunk (chunks start at any event index, so the ragged ends of the 4-event groups are exercised);
+    results equal the oracle's on the int32 column, with pinned (timestamps read in place) and pageable inputs."""
+    import torch
+    off, act, ts = gen.make_log(4000, 0, 70, 200, seed=77, max_gap_s=300, jitter_ms=True)
+    act = (act % 7 + (act % 3 == 0) * 190).astype(np.int32)        # ids 0 .. 6 and 190 .. 196: both ends of the byte range
+    act8 = act.astype(np.uint8)
+    cases = [([dict(kind=N_, types=[0]), dict(kind=O_, types=[1, 2], preds=[(abi.ATTR_POSITION, abi.OP_LE, 0, 10)]),
+               dict(kind=X_, types=[3]), dict(kind=N_, types=[190])], 0),
+             ([dict(kind=P_, types=[0]), dict(kind=S_, types=[191], preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 600)])], 0),
+             ([dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[2])], abi.F_RETURN_ALL)]
+    p_off, p_act8, p_ts = (torch.from_numpy(x).pin_memory() for x in (off, act8, ts))
+    for chunk in ("1000", "4099", None):
+        if chunk:
+            monkeypatch.setenv("SIESTA_CHUNK_EVENTS", chunk)
+        else:
+            monkeypatch.delenv("SIESTA_CHUNK_EVENTS")
+        for states, flags in cases:
+            nfa = abi.make_nfa(states)
+            want = oracle.detect(off, act, ts, nfa, flags=flags)
+            for a, b, c in ((off, act8, ts), (p_off.numpy(), p_act8.numpy(), p_ts.numpy())):
+                got = ctx.evaluate_events(a, b, c, 200, nfa, flags=flags)
+                ok, why = got.same_as(want)
+                assert ok, (why, states, flags, chunk)
+    with pytest.raises(SiestaError) as e:
+        ctx.evaluate_events(off, act8, ts, 300, abi.make_nfa(cases[0][0]))     # 300 activities do not fit a byte
+    assert e.value.code == abi.E_INVALID
+    z = ctx.evaluate_events(np.zeros(4, dtype=np.int64), np.zeros(0, dtype=np.uint8), np.zeros(0, dtype=np.int64), 4, abi.make_nfa(cases[0][0]))
+    assert z.n_traces == 0
 
 
 def test_filter_variants_long_traces_large_alphabets_bad_ids(ctx):
