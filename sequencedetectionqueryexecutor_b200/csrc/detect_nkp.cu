@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
         const int lead = (int)(o0 - e0);
         const long long span = (o1 - o0) + lead;  // slots the trace needs
         bool fits = span <= 64 && ((o1 + 7) & ~7LL) <= P.n_events;
-        const long long o1s = fits ? o1 : o0;     // a trace that does not fit is not read here
+        const long long o1s = fits ? o1 : e0;     // a trace that does not fit is not read here - not even the sector of its first event,
+                                                  // which may cross the end of the log (or of a chunk that is still on the host link)
         u64 valid = 0;
         if (fits && o1 > o0) valid = (span == 64 ? ~0ull : ((1ull << (int)span) - 1ull)) & ~((1ull << lead) - 1ull);
         const bool second = __any_sync(0xffffffffu, fits && span > 32);
