@@ -637,8 +637,8 @@ static int evaluate_events_impl(siesta_ctx* ctx, const int64_t* trace_off, const
     }
 
     // chunk boundaries: whole traces, about CHUNK_EVENTS events each (about 50 - 64 MB on the link: each chunk costs two
-    // host waits, so fewer, larger chunks when only the activity column travels)
-    int64_t CHUNK_EVENTS = ts_mapped ? (16 << 20) : (4 << 20);
+    // host waits, so fewer, larger chunks when only the activity column travels, and fewer again when it travels as bytes)
+    int64_t CHUNK_EVENTS = ts_mapped ? (act8 ? (48 << 20) : (16 << 20)) : (4 << 20);
     if (const char* env = std::getenv("SIESTA_CHUNK_EVENTS")) {  // test aid: force many small chunks
         const long long v = std::atoll(env);
         if (v > 0) CHUNK_EVENTS = v;
@@ -654,18 +654,32 @@ static int evaluate_events_impl(siesta_ctx* ctx, const int64_t* trace_off, const
     }
     const int n_chunks = (int)cut.size() - 1;
 
-    cudaStream_t s_copy = nullptr, s_run = nullptr;
+    // three streams: s_copy carries the chunks over the host link back to back; s_prep widens a byte column and checks the
+    // activity ids of chunk c as soon as it has landed (its verdict goes to a pinned flag the host reads when it gets to the
+    // chunk: no dedicated wait, no allocation per chunk); s_run verifies
+    cudaStream_t s_copy = nullptr, s_run = nullptr, s_prep = nullptr;
     SIESTA_CUDA_OK(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-    if (cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s_prep, cudaStreamNonBlocking) != cudaSuccess) {
         cudaStreamDestroy(s_copy);
+        if (s_run) cudaStreamDestroy(s_run);
         set_error("siesta_evaluate_events: cudaStreamCreate");
         return SIESTA_E_CUDA;
+    }
+    int* h_bad = reinterpret_cast<int*>(arena_alloc(c, (size_t)(n_chunks > 0 ? n_chunks : 1) * sizeof(int)));   // pinned, reused across requests
+    if (!h_bad) {
+        cudaStreamDestroy(s_copy);
+        cudaStreamDestroy(s_run);
+        cudaStreamDestroy(s_prep);
+        set_error("siesta_evaluate_events: cudaHostAlloc");
+        return SIESTA_E_NOMEM;
     }
     int64_t* d_off = nullptr;
     int32_t* d_act = nullptr;
     uint8_t* d_act8 = nullptr;
     int64_t* d_ts = nullptr;
-    std::vector<cudaEvent_t> ready((size_t)n_chunks, nullptr);
+    int* d_bad = nullptr;
+    std::vector<cudaEvent_t> ready((size_t)n_chunks, nullptr), copied((size_t)n_chunks, nullptr);
     std::vector<int32_t> chunk_max_len((size_t)n_chunks, 0);
     std::vector<siesta_dev_matches> parts;
     parts.reserve((size_t)n_chunks);
@@ -679,12 +693,14 @@ static int evaluate_events_impl(siesta_ctx* ctx, const int64_t* trace_off, const
     ok(cudaMallocAsync((void**)&d_act, ne * 4 + 32, s_copy));
     if (act8) ok(cudaMallocAsync((void**)&d_act8, ne + 32, s_copy));
     if (!ts_mapped) ok(cudaMallocAsync((void**)&d_ts, ne * 8 + 32, s_copy));
+    ok(cudaMallocAsync((void**)&d_bad, (size_t)(n_chunks > 0 ? n_chunks : 1) * sizeof(int), s_copy));
+    if (e == cudaSuccess) ok(cudaMemsetAsync(d_bad, 0, (size_t)(n_chunks > 0 ? n_chunks : 1) * sizeof(int), s_copy));
     int enq = 0;
     int32_t max_len = 0;
     auto enqueue_copy = [&](int k) {
         const int64_t t0 = cut[k], t1 = cut[k + 1];
         if (rc == SIESTA_OK) rc = check_csr_range(trace_off, t0, t1, n_events, &max_len);
-        if (rc) return;
+        if (rc || e != cudaSuccess) return;
         chunk_max_len[(size_t)k] = max_len;   // longest trace of chunks 0 .. k: an upper bound for chunk k is all a view needs
         const int64_t e0 = trace_off[t0], e1 = trace_off[t1];
         ok(cudaMemcpyAsync(d_off + t0, trace_off + t0, (size_t)(t1 - t0 + 1) * 8, cudaMemcpyHostToDevice, s_copy));
@@ -693,8 +709,25 @@ static int evaluate_events_impl(siesta_ctx* ctx, const int64_t* trace_off, const
             else ok(cudaMemcpyAsync(d_act + e0, act + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, s_copy));
             if (!ts_mapped) ok(cudaMemcpyAsync(d_ts + e0, ts_ms + e0, (size_t)(e1 - e0) * 8, cudaMemcpyHostToDevice, s_copy));
         }
+        ok(cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming));
+        ok(cudaEventRecord(copied[k], s_copy));
+        ok(cudaStreamWaitEvent(s_prep, copied[k], 0));
+        if (e1 > e0 && e == cudaSuccess) {
+            const int64_t n = e1 - e0;
+            if (act8) {   // chunks are widened in order on one stream: the ragged 4-event groups at a border are written by their own chunk
+                const int64_t want = (n / 4 + 256) / 256;
+                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sm_count * 8));
+                widen_act8_kernel<<<grid, 256, 0, s_prep>>>(d_act8, d_act, e0, e1);
+                SIESTA_LAUNCHED();
+            }
+            const int64_t want = (n + 255) / 256;
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sm_count * 16));
+            act_range_kernel<<<grid, 256, 0, s_prep>>>(d_act + e0, n, n_activities, d_bad + k);
+            SIESTA_LAUNCHED();
+        }
+        ok(cudaMemcpyAsync(h_bad + k, d_bad + k, sizeof(int), cudaMemcpyDeviceToHost, s_prep));
         ok(cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming));
-        ok(cudaEventRecord(ready[k], s_copy));
+        ok(cudaEventRecord(ready[k], s_prep));
     };
     RebaseOffsets base{0, 0, 0};
     bool ids_valid = true;
@@ -702,15 +735,8 @@ static int evaluate_events_impl(siesta_ctx* ctx, const int64_t* trace_off, const
         while (enq < n_chunks && enq <= k + 2 && rc == SIESTA_OK) enqueue_copy(enq++);
         if (e != cudaSuccess || rc != SIESTA_OK) break;
         ok(cudaStreamWaitEvent(s_run, ready[k], 0));
-        if (act8) {
-            const int64_t e0 = trace_off[cut[k]], n = trace_off[cut[k + 1]] - e0;
-            if (n > 0) {
-                const int64_t want = (n / 4 + 256) / 256;
-                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sm_count * 8));
-                widen_act8_kernel<<<grid, 256, 0, s_run>>>(d_act8, d_act, e0, e0 + n);
-                SIESTA_LAUNCHED();
-            }
-        }
+        ok(cudaEventSynchronize(ready[k]));   // the chunk has landed (usually long ago: the copies run two chunks ahead) and h_bad[k] is final
+        if (e != cudaSuccess) break;
         Log view;
         view.ctx = c;
         view.d_trace_off = d_off + cut[k];  // offsets are global event indices: act / ts_ms stay whole
@@ -724,9 +750,8 @@ static int evaluate_events_impl(siesta_ctx* ctx, const int64_t* trace_off, const
         view.n_activities = n_activities;
         view.max_trace_len = chunk_max_len[(size_t)k];
         view.owns = false;
+        if (h_bad[k]) ids_valid = false;   // sticky: the first sector of chunk k + 1 holds the last events of chunk k
         view.act_valid = ids_valid;
-        if (ids_valid && (rc = validate_act_range(&view, trace_off[cut[k]], trace_off[cut[k + 1]] - trace_off[cut[k]], s_run))) break;
-        ids_valid = view.act_valid;   // sticky: the first sector of chunk k + 1 holds the last events of chunk k
         siesta_dev_matches dm;
         base.trace = cut[k];
         rc = detect_device_impl(&view, nfa, nullptr, 0, flags, s_run, base, &dm);
@@ -742,15 +767,21 @@ static int evaluate_events_impl(siesta_ctx* ctx, const int64_t* trace_off, const
     if (rc == SIESTA_OK) rc = assemble_matches(c, parts, flags, s_run, out, nullptr);
     for (siesta_dev_matches& p : parts) siesta_dev_matches_free(&p);
     cudaStreamSynchronize(s_copy);
+    cudaStreamSynchronize(s_prep);
     cudaStreamSynchronize(s_run);
     if (d_off) cudaFreeAsync(d_off, s_run);
     if (d_act) cudaFreeAsync(d_act, s_run);
     if (d_act8) cudaFreeAsync(d_act8, s_run);
     if (d_ts) cudaFreeAsync(d_ts, s_run);
+    if (d_bad) cudaFreeAsync(d_bad, s_run);
     for (cudaEvent_t ev : ready)
         if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : copied)
+        if (ev) cudaEventDestroy(ev);
     cudaStreamSynchronize(s_run);
+    arena_free(c, h_bad);
     cudaStreamDestroy(s_copy);
+    cudaStreamDestroy(s_prep);
     cudaStreamDestroy(s_run);
     return rc;
 }
