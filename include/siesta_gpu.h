@@ -507,6 +507,59 @@ int siesta_explore_accurate(siesta_log* log, const int32_t* pattern_activities, 
                             const int32_t* candidates, int32_t n_candidates, uint32_t flags,
                             int64_t* completions, int64_t* sum_duration_ms, double* kernel_ms);
 
+/* ------------------------------------------------------------ why-not-match */
+/* Replaces WhyNotMatchSASE.evaluate(SimplePattern, restEvents, uncertaintyPerEvent, step, k)
+ * (model/WhyNotMatch/UsingSase/WhyNotMatchSASE.java:37-55; caller QueryPlanWhyNotMatch.execute :54-100, which
+ * hands in the traces WITHOUT a true occurrence): for every candidate trace the events of the pattern's activities
+ * are expanded into the uncertain stream (getUnCertainStream :63-83: every event at primary - u .. primary + u in
+ * steps of `step`, clamped at 0, change = |shift|, stable sort by the shifted value; primary = epoch seconds, or the
+ * position under SIESTA_F_EVT_POS: Event.getPrimaryMetric), the pattern's "normal" states run on it under
+ * skip-till-any-match (S/engine/Engine.java:159-178, 341-350, 593-645) with the predicates of getNFA :91-152, and
+ * the match of least total change is reported, the LAST such match in the engine's emission order (createResponse
+ * :160-173: reduce keeps the later of two equal sums).  A trace without any match is not listed.
+ *
+ * The engine's behaviour is reproduced as it is, not as its comments describe it (oracle/wnm_oracle.cpp restates it
+ * literally; DESIGN.md section 3, kernel W):
+ *  - `change <= k - $2.change - ...` is only effective on the FIRST state: on every later state the predicate names
+ *    its own state and PredicateOptimized.evaluate returns true for it (PredicateOptimized.java:348-350);
+ *  - a constraint (posA, posB) with posA >= 1 is compared with the event that the runs of the same START took LAST at
+ *    state posA, not with the run's own (Run.clone is shallow: the value vectors are shared by all runs that descend
+ *    from one start, S/engine/Run.java:319-327, 332-355);
+ *  - gap constraints count positions of the uncertain stream; `timestamp > $previous.timestamp` is only asked at a
+ *    state a time constraint ends at.
+ * Not supported (SIESTA_E_UNSUPPORTED): a constraint with posA >= 1 between two states of the same activity (the
+ * result then depends on the order of the run list inside one event).  Traces whose uncertain stream exceeds
+ * SIESTA_WNM_MAX_STREAM events are listed in unsupported_trace_idx, every other trace is answered. */
+#define SIESTA_WNM_GAP 0
+#define SIESTA_WNM_TIME 1
+#define SIESTA_WNM_WITHIN 0
+#define SIESTA_WNM_ATLEAST 1
+#define SIESTA_WNM_MAX_STREAM 1024
+typedef struct siesta_wnm_constraint {
+    int32_t pos_a, pos_b; /* Constraint.getPosA / getPosB, 0-based, pos_a < pos_b */
+    int32_t kind;         /* SIESTA_WNM_GAP | SIESTA_WNM_TIME */
+    int32_t method;       /* SIESTA_WNM_WITHIN | SIESTA_WNM_ATLEAST */
+    int64_t value;        /* GapConstraint.getConstraint() / TimeConstraint.getConstraintInSeconds(), >= 0 */
+} siesta_wnm_constraint;
+typedef struct siesta_almost_matches {
+    int64_t n_traces;        /* traces with an almost-match (AlmostMatch objects of the response) */
+    int32_t n_states;        /* events per almost-match = length of the pattern */
+    int64_t* trace_idx;      /* [n_traces] ascending (candidate order) */
+    int32_t* total_change;   /* [n_traces] AlmostMatch.totalChange */
+    int32_t* ev_pos;         /* [n_traces * n_states] index of the ORIGINAL event inside its trace */
+    int32_t* ev_value;       /* [n_traces * n_states] UncertainTimeEvent.getTimestamp(): shifted primary metric */
+    int32_t* ev_change;      /* [n_traces * n_states] UncertainTimeEvent.getChange() */
+    int32_t* ev_stream_pos;  /* [n_traces * n_states] UncertainTimeEvent.getPosition(): index in the uncertain stream */
+    int64_t n_unsupported;
+    int64_t* unsupported_trace_idx;
+    double kernel_ms;
+} siesta_almost_matches;
+int siesta_why_not_match(siesta_log* log, const int32_t* pattern_activities, int32_t n_pattern,
+                         const siesta_wnm_constraint* constraints, int32_t n_constraints, int32_t uncertainty,
+                         int32_t step, int32_t k, const int64_t* cand, int64_t n_cand, uint32_t flags,
+                         siesta_almost_matches** out);
+void siesta_almost_matches_free(siesta_almost_matches* m);
+
 /* Number of kernels this library has launched in this process (bench.py's
  * gpu_launches). */
 int64_t siesta_kernel_launches(void);

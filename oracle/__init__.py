@@ -20,7 +20,7 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("sase_oracle.cpp", "counting_oracle.cpp", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("sase_oracle.cpp", "counting_oracle.cpp", "wnm_oracle.cpp", "Makefile")]
     srcs.append(os.path.join(_HERE, "..", "include", "siesta_gpu.h"))
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
@@ -145,3 +145,39 @@ def intersect(lists):
     L.oracle_intersect.restype = C.c_int64
     n = L.oracle_intersect(ptrs, _p(lens, C.c_int64), C.c_int32(len(lists)), _p(out, C.c_int64))
     return out[:n].copy()
+
+
+def wnm_stream_size(primary, uncertainty, step):
+    """WhyNotMatchSASE.getUnCertainStream(...).getSize() for a list of primary metrics (oracle/wnm_oracle.cpp)."""
+    L = lib()
+    L.oracle_wnm_stream_size.restype = C.c_int64
+    primary = np.ascontiguousarray(primary, dtype=np.int64)
+    return int(L.oracle_wnm_stream_size(_p(primary, C.c_int64), C.c_int32(len(primary)), C.c_int32(uncertainty), C.c_int32(step)))
+
+
+def why_not_match(trace_off, act, ts_ms, pattern, constraints, uncertainty, step, k, cand=None, flags=0, run_limit=2_000_000):
+    """WhyNotMatchSASE.evaluate + createResponse, literally (exponential: small cases) -> _abi.AlmostMatchResult,
+    or None when a trace needs more than run_limit runs."""
+    L = lib()
+    trace_off = np.ascontiguousarray(trace_off, dtype=np.int64)
+    act = np.ascontiguousarray(act, dtype=np.int32)
+    ts_ms = np.ascontiguousarray(ts_ms, dtype=np.int64)
+    pattern = np.ascontiguousarray(pattern, dtype=np.int32)
+    cons, n_cons = _abi.make_wnm_constraints(constraints)
+    if cand is not None:
+        cand = np.ascontiguousarray(cand, dtype=np.int64)
+        cp, nc = _p(cand, C.c_int64), len(cand)
+    else:
+        cp, nc = None, 0
+    out = C.POINTER(_abi.AlmostMatches)()
+    L.oracle_why_not_match.restype = C.c_int
+    L.oracle_almost_matches_free.argtypes = [C.POINTER(_abi.AlmostMatches)]
+    rc = L.oracle_why_not_match(_p(trace_off, C.c_int64), _p(act, C.c_int32), _p(ts_ms, C.c_int64), C.c_int64(len(trace_off) - 1),
+                                _p(pattern, C.c_int32), C.c_int32(len(pattern)), cons, C.c_int32(n_cons), C.c_int32(uncertainty),
+                                C.c_int32(step), C.c_int32(k), cp, C.c_int64(nc), C.c_uint32(flags), C.c_int64(run_limit), C.byref(out))
+    if rc == 1:
+        return None
+    assert rc == 0, rc
+    res = _abi.AlmostMatchResult(out.contents)
+    L.oracle_almost_matches_free(out)
+    return res

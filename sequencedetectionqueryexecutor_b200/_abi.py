@@ -59,6 +59,57 @@ class Matches(C.Structure):
                 ("n_unsupported", C.c_int64), ("unsupported_trace_idx", C.POINTER(C.c_int64))]
 
 
+class WnmConstraint(C.Structure):
+    """siesta_wnm_constraint"""
+    _fields_ = [("pos_a", C.c_int32), ("pos_b", C.c_int32), ("kind", C.c_int32), ("method", C.c_int32), ("value", C.c_int64)]
+
+
+class AlmostMatches(C.Structure):
+    """siesta_almost_matches"""
+    _fields_ = [("n_traces", C.c_int64), ("n_states", C.c_int32), ("trace_idx", C.POINTER(C.c_int64)),
+                ("total_change", C.POINTER(C.c_int32)), ("ev_pos", C.POINTER(C.c_int32)), ("ev_value", C.POINTER(C.c_int32)),
+                ("ev_change", C.POINTER(C.c_int32)), ("ev_stream_pos", C.POINTER(C.c_int32)), ("n_unsupported", C.c_int64),
+                ("unsupported_trace_idx", C.POINTER(C.c_int64)), ("kernel_ms", C.c_double)]
+
+
+WNM_GAP, WNM_TIME, WNM_WITHIN, WNM_ATLEAST = 0, 1, 0, 1
+
+
+def make_wnm_constraints(constraints):
+    """[(pos_a, pos_b, kind, method, value)] -> (ctypes array, n)"""
+    arr = (WnmConstraint * max(len(constraints), 1))()
+    for i, (a, b, kind, method, value) in enumerate(constraints):
+        arr[i] = WnmConstraint(int(a), int(b), int(kind), int(method), int(value))
+    return arr, len(constraints)
+
+
+class AlmostMatchResult:
+    """Host copy of siesta_almost_matches: per trace with an almost-match its m uncertain events."""
+
+    def __init__(self, st):
+        import numpy as np
+        n, m = int(st.n_traces), int(st.n_states)
+        self.n_traces, self.n_states = n, m
+        self.kernel_ms = float(st.kernel_ms)
+
+        def col(ptr, k, dt):
+            return np.ctypeslib.as_array(ptr, shape=(max(k, 1),))[:k].astype(dt, copy=True) if k else np.zeros(0, dtype=dt)
+        self.trace_idx = col(st.trace_idx, n, np.int64)
+        self.total_change = col(st.total_change, n, np.int32)
+        self.ev_pos = col(st.ev_pos, n * m, np.int32).reshape(n, m)
+        self.ev_value = col(st.ev_value, n * m, np.int32).reshape(n, m)
+        self.ev_change = col(st.ev_change, n * m, np.int32).reshape(n, m)
+        self.ev_stream_pos = col(st.ev_stream_pos, n * m, np.int32).reshape(n, m)
+        self.unsupported_trace_idx = col(st.unsupported_trace_idx, int(st.n_unsupported), np.int64)
+
+    def same_as(self, other):
+        import numpy as np
+        for k in ("trace_idx", "total_change", "ev_pos", "ev_value", "ev_change", "ev_stream_pos"):
+            if not np.array_equal(getattr(self, k), getattr(other, k)):
+                return False, k
+        return True, ""
+
+
 class PairCount(C.Structure):
     _fields_ = [("count", C.c_int64), ("sum_duration_ms", C.c_int64), ("min_duration_ms", C.c_int64),
                 ("max_duration_ms", C.c_int64), ("sum_squares_lo", C.c_uint64), ("sum_squares_hi", C.c_uint64)]

@@ -18,7 +18,7 @@ EXPORTS = [
     "siesta_index_load", "siesta_index_build", "siesta_index_free", "siesta_index_list_len", "siesta_index_get_list",
     "siesta_intersect", "siesta_intersect_device", "siesta_device_free", "siesta_pattern_extract_pairs",
     "siesta_candidates", "siesta_candidates_device", "siesta_pair_stats", "siesta_pair_stats_device",
-    "siesta_explore_accurate", "siesta_log_set_first_trace", "siesta_log_set_blocks",
+    "siesta_explore_accurate", "siesta_why_not_match", "siesta_almost_matches_free", "siesta_log_set_first_trace", "siesta_log_set_blocks",
     "siesta_packed_block_bytes", "siesta_dev_matches_pack",
     "siesta_exchange_create", "siesta_exchange_export", "siesta_exchange_import", "siesta_exchange_connect_local",
     "siesta_exchange_free", "siesta_exchange_required_bytes", "siesta_detect_allgather", "siesta_exchange_allreduce_i64",
@@ -95,6 +95,9 @@ def lib():
     L.siesta_pair_stats.argtypes = [vp, vp, vp, i32, P(_abi.PairCount), P(C.c_double)]
     L.siesta_pair_stats_device.argtypes = [vp, vp, vp, i32, vp, vp, P(C.c_double)]
     L.siesta_explore_accurate.argtypes = [vp, vp, i32, vp, i32, u32, vp, vp, P(C.c_double)]
+    L.siesta_why_not_match.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, vp, i64, u32, P(P(_abi.AlmostMatches))]
+    L.siesta_almost_matches_free.argtypes = [P(_abi.AlmostMatches)]
+    L.siesta_almost_matches_free.restype = None
     L.siesta_exchange_create.argtypes = [vp, i32, i32, i64, P(vp)]
     L.siesta_exchange_export.argtypes = [vp, vp]
     L.siesta_exchange_import.argtypes = [vp, i32, vp]

@@ -215,6 +215,22 @@ class EventLog:
                                             C.byref(ms)))
         return comp[:len(ca)], dur[:len(ca)], ms.value
 
+    def why_not_match(self, pattern_activities, constraints, uncertainty, step, k, cand=None, flags=0):
+        """siesta_why_not_match (WhyNotMatchSASE.evaluate): constraints = [(pos_a, pos_b, kind, method, value)],
+        cand = the traces without a true occurrence (None: every trace) -> _abi.AlmostMatchResult."""
+        pa = np.asarray(pattern_activities, dtype=np.int32)
+        cons, n_cons = _abi.make_wnm_constraints(constraints)
+        out = C.POINTER(_abi.AlmostMatches)()
+        n_cand = 0
+        if cand is not None:   # an empty list means "no trace", a null pointer "every trace"
+            n_cand = len(cand)
+            cand = np.ascontiguousarray(cand if n_cand else [0], dtype=np.int64)
+        check(lib().siesta_why_not_match(self._h, _ptr(pa), len(pa), C.cast(cons, C.c_void_p), n_cons, int(uncertainty), int(step),
+                                         int(k), _ptr(cand), n_cand, flags, C.byref(out)))
+        res = _abi.AlmostMatchResult(out.contents)
+        lib().siesta_almost_matches_free(out)
+        return res
+
     def build_index(self, pairs):
         """siesta_index_build: posting lists of the (A,B) pairs from the resident log (SeqTable view)."""
         return PairIndex(self, pairs)

@@ -260,3 +260,77 @@ def explore_accurate(pattern_names, log, activities: ActivityDictionary, candida
     # reversed once more by reverseOrder -> ascending event name
     props.sort(key=lambda p: (-p.score(), p.event))
     return props
+
+
+# ------------------------------------------------------------------------------------------------ why-not-match
+@dataclass
+class UncertainTimeEvent:
+    """J/model/WhyNotMatch/UsingSase/UncertainTimeEvent.java: an event of the uncertain stream as the response carries it."""
+    event_type: str
+    timestamp: int      # shifted primary metric: epoch seconds (or the position in positions mode)
+    change: int
+    position: int       # index in the uncertain stream
+    source_position: int = -1   # index of the original event inside its trace (not a field of the Java class)
+
+
+@dataclass
+class AlmostMatch:
+    """J/model/WhyNotMatch/AlmostMatch.java"""
+    trace_id: object
+    match: List[UncertainTimeEvent]
+    totalChange: int
+
+
+def _wnm_constraints(constraints):
+    """WhyNotMatchSASE.generatePredicatesFromConstraints (:136-158): gap constraints in positions, time constraints in seconds"""
+    mult = {"seconds": 1, "minutes": 60, "hours": 3600}
+    out = []
+    for c in constraints:
+        if isinstance(c, TimeConstraint):
+            out.append((c.posA, c.posB, _abi.WNM_TIME, _abi.WNM_WITHIN if c.method == "within" else _abi.WNM_ATLEAST,
+                        c.constraint * mult.get(c.granularity, 1)))   # TimeConstraint.getConstraintInSeconds :45-49
+        else:
+            out.append((c.posA, c.posB, _abi.WNM_GAP, _abi.WNM_WITHIN if c.method == "within" else _abi.WNM_ATLEAST, c.constraint))
+    return out
+
+
+class WhyNotMatchSASE:
+    """evaluate(simple pattern, rest traces, uncertaintyPerEvent, step, k) -> List[AlmostMatch]
+    (WhyNotMatchSASE.java:37-55) on the GPU (siesta_why_not_match)."""
+
+    def __init__(self, activities: ActivityDictionary, trace_ids=None, positions_mode=False):
+        self.activities = activities
+        self.trace_ids = trace_ids
+        self.positions_mode = positions_mode
+
+    def evaluate_raw(self, event_names, constraints, log, rest, uncertaintyPerEvent, step, k):
+        pattern = [self.activities.id(n) for n in event_names]
+        return log.why_not_match(pattern, _wnm_constraints(constraints), uncertaintyPerEvent, step, k, cand=rest,
+                                 flags=_abi.F_EVT_POS if self.positions_mode else 0)
+
+    def evaluate(self, event_names, constraints, log, rest, uncertaintyPerEvent, step, k):
+        res = self.evaluate_raw(event_names, constraints, log, rest, uncertaintyPerEvent, step, k)
+        out = []
+        for i, t in enumerate(res.trace_idx):
+            evs = [UncertainTimeEvent(event_names[j], int(res.ev_value[i, j]), int(res.ev_change[i, j]), int(res.ev_stream_pos[i, j]),
+                                      int(res.ev_pos[i, j])) for j in range(res.n_states)]
+            out.append(AlmostMatch(self.trace_ids[t] if self.trace_ids is not None else int(t), evs, int(res.total_change[i])))
+        return out
+
+
+def why_not_match_plan(pattern: "ComplexPattern", log, activities: ActivityDictionary, uncertainty, step, k, returnAll=False,
+                       cand=None, trace_ids=None, positions_mode=False):
+    """QueryPlanWhyNotMatch.execute (:54-100) after the pruning: the true occurrences of the candidates, then the
+    why-not-match search over the candidates WITHOUT an occurrence (:78-89).  Only simple patterns (every symbol "_", :66-70).
+    -> (List[Occurrences], List[AlmostMatch])"""
+    if any(e.symbol != "_" for e in pattern.eventsWithSymbols):
+        raise ValueError("why-not-match takes a simple pattern (QueryResponseBadRequestWhyNotMatch.setSimple(false))")
+    conn = SaseConnector(activities, trace_ids, positions_mode)
+    raw = conn.evaluate_raw(pattern, log, False, returnAll, cand)
+    occurrences = conn.evaluate(pattern, log, False, returnAll, cand)
+    import numpy as np
+    universe = np.arange(log.n_traces, dtype=np.int64) if cand is None else np.asarray(cand, dtype=np.int64)
+    rest = np.setdiff1d(universe, raw.trace_idx, assume_unique=False)
+    names = [e.name for e in sorted(pattern.eventsWithSymbols, key=lambda e: e.position)]
+    almost = WhyNotMatchSASE(activities, trace_ids, positions_mode).evaluate(names, pattern.constraints, log, rest, uncertainty, step, k)
+    return occurrences, almost

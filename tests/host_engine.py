@@ -47,3 +47,31 @@ def detect(trace_off, act, ts_ms, n_act, nfa, cand=None, flags=0):
     res = _abi.MatchResult.from_struct(out.contents)
     oracle.lib().oracle_matches_free(out)
     return 0, res, n_wide.value
+
+
+def wnm_eval(trace_off, act, ts_ms, pattern, constraints, uncertainty, step, k, flags=0):
+    """Kernel W's per-trace evaluation (csrc/wnm.cuh) on the host -> _abi.AlmostMatchResult-like object."""
+    L = lib()
+    trace_off = np.ascontiguousarray(trace_off, dtype=np.int64)
+    act = np.ascontiguousarray(act, dtype=np.int32)
+    ts_ms = np.ascontiguousarray(ts_ms, dtype=np.int64)
+    pattern = np.ascontiguousarray(pattern, dtype=np.int32)
+    cons, n_cons = _abi.make_wnm_constraints(constraints)
+    T, m = len(trace_off) - 1, len(pattern)
+    status = np.zeros(max(T, 1), dtype=np.int32)
+    total = np.zeros(max(T, 1), dtype=np.int32)
+    cols = [np.zeros(max(T * m, 1), dtype=np.int32) for _ in range(4)]
+    L.wnm_host_eval.restype = C.c_int
+    rc = L.wnm_host_eval(_p(trace_off, C.c_int64), _p(act, C.c_int32), _p(ts_ms, C.c_int64), C.c_int64(T), _p(pattern, C.c_int32),
+                         C.c_int32(m), cons, C.c_int32(n_cons), C.c_int32(uncertainty), C.c_int32(step), C.c_int32(k), C.c_uint32(flags),
+                         _p(status, C.c_int32), _p(total, C.c_int32), *[_p(c, C.c_int32) for c in cols])
+    assert rc == 0, "wnm_rank did not produce a permutation"
+
+    class R:
+        pass
+    r = R()
+    hit = np.nonzero(status[:T] == 1)[0]
+    r.trace_idx = hit.astype(np.int64)
+    r.total_change = total[hit]
+    r.ev_pos, r.ev_value, r.ev_change, r.ev_stream_pos = (c[:T * m].reshape(T, m)[hit] for c in cols)
+    return r
