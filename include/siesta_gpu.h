@@ -414,6 +414,14 @@ siesta_log* siesta_multi_log_shard(siesta_multi_log* log, int32_t shard); /* bor
 int siesta_multi_detect(siesta_multi_log* log, const siesta_nfa* nfa, uint32_t flags, siesta_matches** out);
 /* = siesta_declare_counts(whole log): kernel K3 per shard + one sum all-reduce over the exchange. */
 int siesta_multi_declare_counts(siesta_multi_log* log, int32_t k_cap, int64_t* out, double* kernel_ms);
+/* siesta_why_not_match (below) over all shards: cand = ascending GLOBAL trace indices (NULL: every trace); every
+ * device answers its own candidates, the answers are concatenated in trace order. */
+struct siesta_wnm_constraint;
+struct siesta_almost_matches;
+int siesta_multi_why_not_match(siesta_multi_log* log, const int32_t* pattern_activities, int32_t n_pattern,
+                               const struct siesta_wnm_constraint* constraints, int32_t n_constraints,
+                               int32_t uncertainty, int32_t step, int32_t k, const int64_t* cand, int64_t n_cand,
+                               uint32_t flags, struct siesta_almost_matches** out);
 
 /* ------------------------------------------------- pair index + intersection */
 /* Kernel K2.  Replaces SparkDatabaseRepository.getCommonIds (storage/repositories/

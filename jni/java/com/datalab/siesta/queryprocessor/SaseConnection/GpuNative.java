@@ -27,6 +27,11 @@ final class GpuNative {
     static native int[] matchesInts(long matches, int which);     // 0 ev_pos, 1 ev_rank, 2 ev_act
     static native void matchesFree(long matches);
     static native long[] declareCounts(long log, int nActivities, int kCap);
+    // why-not-match (WhyNotMatchSASE.evaluate): constraints = 5 longs each (posA, posB, kind 0 gap | 1 time, method 0 within | 1 atleast, value)
+    static native long whyNotMatch(long log, int[] pattern, long[] constraints, int uncertainty, int step, int k, long[] cand, int flags);
+    static native long[] almostLongs(long almost, int which);    // 0 trace_idx, 1 unsupported_trace_idx
+    static native int[] almostInts(long almost, int which);      // 0 total_change, 1 ev_pos, 2 ev_value, 3 ev_change, 4 ev_stream_pos
+    static native void almostFree(long almost);
 
     private GpuNative() { }
 }

@@ -226,3 +226,74 @@ NATIVE(jlongArray, declareCounts)(JNIEnv* env, jclass cls, jlong log, jint nActi
     free(buf);
     return out;
 }
+
+/* long whyNotMatch(long log, int[] pattern, long[] constraints, int uncertainty, int step, int k, long[] cand, int flags):
+ * WhyNotMatchSASE.evaluate (model/WhyNotMatch/UsingSase/WhyNotMatchSASE.java:37-55) over the candidate traces of a
+ * resident log.  constraints: 5 longs per Constraint (posA, posB, kind SIESTA_WNM_GAP|TIME, method SIESTA_WNM_WITHIN|ATLEAST,
+ * value: positions, or TimeConstraint.getConstraintInSeconds()); cand: ascending trace indices, null = every trace. */
+NATIVE(jlong, whyNotMatch)(JNIEnv* env, jclass cls, jlong log, jintArray pattern, jlongArray constraints, jint uncertainty, jint step,
+                           jint k, jlongArray cand, jint flags) {
+    (void)cls;
+    const jsize m = (*env)->GetArrayLength(env, pattern), nc = (*env)->GetArrayLength(env, constraints) / 5;
+    const jsize ncand = cand ? (*env)->GetArrayLength(env, cand) : 0;
+    jint* p = (*env)->GetIntArrayElements(env, pattern, NULL);
+    jlong* c = (*env)->GetLongArrayElements(env, constraints, NULL);
+    jlong* cd = cand ? (*env)->GetLongArrayElements(env, cand, NULL) : NULL;
+    siesta_wnm_constraint* cons = (siesta_wnm_constraint*)malloc(sizeof(siesta_wnm_constraint) * (size_t)(nc > 0 ? nc : 1));
+    siesta_almost_matches* out = NULL;
+    int rc = SIESTA_E_NOMEM;
+    if (cons) {
+        for (jsize i = 0; i < nc; ++i) {
+            cons[i].pos_a = (int32_t)c[5 * i];
+            cons[i].pos_b = (int32_t)c[5 * i + 1];
+            cons[i].kind = (int32_t)c[5 * i + 2];
+            cons[i].method = (int32_t)c[5 * i + 3];
+            cons[i].value = (int64_t)c[5 * i + 4];
+        }
+        static const int64_t none = 0;   /* an empty candidate list is "no trace", not "every trace" */
+        rc = siesta_multi_why_not_match((siesta_multi_log*)(intptr_t)log, (const int32_t*)p, (int32_t)m, cons, (int32_t)nc, (int32_t)uncertainty,
+                                        (int32_t)step, (int32_t)k, cand ? (ncand ? (const int64_t*)cd : &none) : NULL, (int64_t)ncand,
+                                        (uint32_t)flags, &out);
+    }
+    free(cons);
+    (*env)->ReleaseIntArrayElements(env, pattern, p, JNI_ABORT);
+    (*env)->ReleaseLongArrayElements(env, constraints, c, JNI_ABORT);
+    if (cd) (*env)->ReleaseLongArrayElements(env, cand, cd, JNI_ABORT);
+    if (rc != SIESTA_OK) {
+        throw_last(env, "siesta_multi_why_not_match");
+        return 0;
+    }
+    return (jlong)(intptr_t)out;
+}
+
+/* long[] almostLongs(long a, int which): 0 trace_idx, 1 unsupported_trace_idx */
+NATIVE(jlongArray, almostLongs)(JNIEnv* env, jclass cls, jlong ah, jint which) {
+    (void)cls;
+    const siesta_almost_matches* a = (const siesta_almost_matches*)(intptr_t)ah;
+    const int64_t* src = which == 0 ? a->trace_idx : a->unsupported_trace_idx;
+    const int64_t n = which == 0 ? a->n_traces : a->n_unsupported;
+    jlongArray out = (*env)->NewLongArray(env, (jsize)n);
+    if (out && n) (*env)->SetLongArrayRegion(env, out, 0, (jsize)n, (const jlong*)src);
+    return out;
+}
+
+/* int[] almostInts(long a, int which): 0 total_change [n], then n * n_states each: 1 ev_pos, 2 ev_value, 3 ev_change, 4 ev_stream_pos */
+NATIVE(jintArray, almostInts)(JNIEnv* env, jclass cls, jlong ah, jint which) {
+    (void)cls;
+    const siesta_almost_matches* a = (const siesta_almost_matches*)(intptr_t)ah;
+    const int32_t* src = which == 0 ? a->total_change : which == 1 ? a->ev_pos : which == 2 ? a->ev_value : which == 3 ? a->ev_change : a->ev_stream_pos;
+    const int64_t n = which == 0 ? a->n_traces : a->n_traces * a->n_states;
+    if (n > 0x7fffffff) {
+        jclass rte = (*env)->FindClass(env, "java/lang/RuntimeException");
+        if (rte) (*env)->ThrowNew(env, rte, "result column longer than a Java array");
+        return NULL;
+    }
+    jintArray out = (*env)->NewIntArray(env, (jsize)n);
+    if (out && n) (*env)->SetIntArrayRegion(env, out, 0, (jsize)n, (const jint*)src);
+    return out;
+}
+
+NATIVE(void, almostFree)(JNIEnv* env, jclass cls, jlong ah) {
+    (void)env; (void)cls;
+    siesta_almost_matches_free((siesta_almost_matches*)(intptr_t)ah);
+}

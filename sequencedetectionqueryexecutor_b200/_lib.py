@@ -23,7 +23,7 @@ EXPORTS = [
     "siesta_exchange_create", "siesta_exchange_export", "siesta_exchange_import", "siesta_exchange_connect_local",
     "siesta_exchange_free", "siesta_exchange_required_bytes", "siesta_detect_allgather", "siesta_exchange_allreduce_i64",
     "siesta_multi_init", "siesta_multi_shutdown", "siesta_multi_n_devices", "siesta_multi_log_load", "siesta_multi_log_free",
-    "siesta_multi_log_shard", "siesta_multi_detect", "siesta_multi_declare_counts",
+    "siesta_multi_log_shard", "siesta_multi_detect", "siesta_multi_declare_counts", "siesta_multi_why_not_match",
     "siesta_log_filter_time", "siesta_log_group", "siesta_log_source_events",
 ]
 
@@ -96,6 +96,7 @@ def lib():
     L.siesta_pair_stats_device.argtypes = [vp, vp, vp, i32, vp, vp, P(C.c_double)]
     L.siesta_explore_accurate.argtypes = [vp, vp, i32, vp, i32, u32, vp, vp, P(C.c_double)]
     L.siesta_why_not_match.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, vp, i64, u32, P(P(_abi.AlmostMatches))]
+    L.siesta_multi_why_not_match.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, vp, i64, u32, P(P(_abi.AlmostMatches))]
     L.siesta_almost_matches_free.argtypes = [P(_abi.AlmostMatches)]
     L.siesta_almost_matches_free.restype = None
     L.siesta_exchange_create.argtypes = [vp, i32, i32, i64, P(vp)]

@@ -380,6 +380,21 @@ class MultiLog:
         lib().siesta_matches_free(out)
         return res
 
+    def why_not_match(self, pattern_activities, constraints, uncertainty, step, k, cand=None, flags=0):
+        """siesta_multi_why_not_match: cand = ascending GLOBAL trace indices (None: every trace)."""
+        pa = np.asarray(pattern_activities, dtype=np.int32)
+        cons, n_cons = _abi.make_wnm_constraints(constraints)
+        out = C.POINTER(_abi.AlmostMatches)()
+        n_cand = 0
+        if cand is not None:
+            n_cand = len(cand)
+            cand = np.ascontiguousarray(cand if n_cand else [0], dtype=np.int64)
+        check(lib().siesta_multi_why_not_match(self._h, _ptr(pa), len(pa), C.cast(cons, C.c_void_p), n_cons, int(uncertainty), int(step),
+                                               int(k), _ptr(cand), n_cand, flags, C.byref(out)))
+        res = _abi.AlmostMatchResult(out.contents)
+        lib().siesta_almost_matches_free(out)
+        return res
+
     def declare_counts(self, k_cap=64):
         n = lib().siesta_declare_counts_size(self.n_activities, int(k_cap))
         out = np.zeros(n, dtype=np.int64)

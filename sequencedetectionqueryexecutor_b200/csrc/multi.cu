@@ -1242,3 +1242,96 @@ extern "C" int siesta_multi_declare_counts(siesta_multi_log* lh, int32_t k_cap, 
     if (kernel_ms) *kernel_ms = worst;
     return SIESTA_OK;
 }
+
+
+// Why-not-match over a sharded log: the candidates (global trace indices, ascending) are cut at the shard borders, every
+// device evaluates its own (siesta_why_not_match on the shard, wnm.cu), the answers are concatenated in shard order -
+// traces are independent, nothing crosses a device.
+extern "C" int siesta_multi_why_not_match(siesta_multi_log* lh, const int32_t* pattern, int32_t m, const siesta_wnm_constraint* cons,
+                                          int32_t n_cons, int32_t uncertainty, int32_t step, int32_t k, const int64_t* cand,
+                                          int64_t n_cand, uint32_t flags, siesta_almost_matches** out) {
+    MultiLog* ml = reinterpret_cast<MultiLog*>(lh);
+    if (!ml || !out || (cand == nullptr && n_cand != 0) || n_cand < 0) {
+        set_error("siesta_multi_why_not_match: null argument");
+        return SIESTA_E_INVALID;
+    }
+    const int n = (int)ml->shard.size();
+    for (int64_t i = 0; i < n_cand; ++i)
+        if (cand[i] < 0 || cand[i] >= ml->first[(size_t)n] || (i && cand[i] < cand[i - 1])) {
+            set_error("siesta_multi_why_not_match: candidates must be ascending trace indices of the log");
+            return SIESTA_E_INVALID;
+        }
+    std::vector<siesta_almost_matches*> part((size_t)n, nullptr);
+    std::vector<int> rcs((size_t)n, SIESTA_OK);
+    std::vector<std::string> errs((size_t)n);
+    std::vector<std::thread> th;
+    for (int r = 0; r < n; ++r)
+        th.emplace_back([&, r] {
+            std::vector<int64_t> local;
+            const int64_t* lp = nullptr;
+            int64_t ln = 0;
+            if (cand) {
+                const int64_t* a = std::lower_bound(cand, cand + n_cand, ml->first[(size_t)r]);
+                const int64_t* b = std::lower_bound(cand, cand + n_cand, ml->first[(size_t)r + 1]);
+                local.assign(a, b);
+                for (int64_t& t : local) t -= ml->first[(size_t)r];
+                local.push_back(0);   // never a null pointer: null means "every trace"
+                lp = local.data();
+                ln = (int64_t)local.size() - 1;
+            }
+            rcs[r] = siesta_why_not_match(reinterpret_cast<siesta_log*>(ml->shard[r]), pattern, m, cons, n_cons, uncertainty, step, k, lp, ln,
+                                          flags, &part[r]);
+            if (rcs[r]) errs[r] = siesta_last_error();
+        });
+    for (std::thread& t : th) t.join();
+    int rc = SIESTA_OK;
+    int64_t n_hit = 0, n_unsup = 0;
+    double ms = 0;
+    for (int r = 0; r < n; ++r) {
+        if (rcs[r] != SIESTA_OK && rc == SIESTA_OK) {
+            rc = rcs[r];
+            set_error(errs[r]);
+        }
+        if (part[r]) {
+            n_hit += part[r]->n_traces;
+            n_unsup += part[r]->n_unsupported;
+            ms = std::max(ms, part[r]->kernel_ms);
+        }
+    }
+    siesta_almost_matches* res = nullptr;
+    if (rc == SIESTA_OK) {
+        const size_t h = (size_t)std::max<int64_t>(n_hit, 1), ev = h * (size_t)m, us = (size_t)std::max<int64_t>(n_unsup, 1);
+        char* base = (char*)std::malloc(((sizeof(siesta_almost_matches) + 63) & ~(size_t)63) + h * 12 + us * 8 + ev * 16 + 64);
+        if (!base) rc = SIESTA_E_NOMEM;
+        else {
+            res = reinterpret_cast<siesta_almost_matches*>(base);
+            std::memset(res, 0, sizeof(*res));
+            char* p = base + ((sizeof(siesta_almost_matches) + 63) & ~(size_t)63);
+            res->trace_idx = reinterpret_cast<int64_t*>(p); p += h * 8;
+            res->unsupported_trace_idx = reinterpret_cast<int64_t*>(p); p += us * 8;
+            res->total_change = reinterpret_cast<int32_t*>(p); p += h * 4;
+            res->ev_pos = reinterpret_cast<int32_t*>(p); p += ev * 4;
+            res->ev_value = reinterpret_cast<int32_t*>(p); p += ev * 4;
+            res->ev_change = reinterpret_cast<int32_t*>(p); p += ev * 4;
+            res->ev_stream_pos = reinterpret_cast<int32_t*>(p);
+            res->n_states = m;
+            res->kernel_ms = ms;
+            for (int r = 0; r < n; ++r) {
+                const siesta_almost_matches* q = part[r];
+                std::memcpy(res->trace_idx + res->n_traces, q->trace_idx, (size_t)q->n_traces * 8);
+                std::memcpy(res->total_change + res->n_traces, q->total_change, (size_t)q->n_traces * 4);
+                std::memcpy(res->ev_pos + res->n_traces * m, q->ev_pos, (size_t)q->n_traces * m * 4);
+                std::memcpy(res->ev_value + res->n_traces * m, q->ev_value, (size_t)q->n_traces * m * 4);
+                std::memcpy(res->ev_change + res->n_traces * m, q->ev_change, (size_t)q->n_traces * m * 4);
+                std::memcpy(res->ev_stream_pos + res->n_traces * m, q->ev_stream_pos, (size_t)q->n_traces * m * 4);
+                std::memcpy(res->unsupported_trace_idx + res->n_unsupported, q->unsupported_trace_idx, (size_t)q->n_unsupported * 8);
+                res->n_traces += q->n_traces;
+                res->n_unsupported += q->n_unsupported;
+            }
+        }
+    }
+    for (siesta_almost_matches* q : part) siesta_almost_matches_free(q);
+    if (rc != SIESTA_OK) return rc;
+    *out = res;
+    return SIESTA_OK;
+}

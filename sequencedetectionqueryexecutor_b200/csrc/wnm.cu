@@ -321,7 +321,10 @@ extern "C" int siesta_why_not_match(siesta_log* log, const int32_t* pattern, int
         SIESTA_CUDA_OK(cudaFuncSetAttribute(wnm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wnm_kernel, WNM_WARPS * 32, smem));
-        per_sm = std::max(1, std::min(per_sm, 4));
+        // resident CTAs: as many as fit, as long as the back-pointer scratch of all warps stays below 1 GB
+        const size_t prev_per_warp = (size_t)std::max(1, m - 1) * P.n_cap * 32 * sizeof(unsigned short);
+        const int by_scratch = (int)std::max<size_t>(1, ((size_t)1 << 30) / (prev_per_warp * WNM_WARPS * (size_t)c->sm_count));
+        per_sm = std::max(1, std::min(per_sm, std::min(12, by_scratch)));
         const int grid = (int)std::min<int64_t>((n + WNM_WARPS - 1) / WNM_WARPS, (int64_t)c->sm_count * per_sm);
         const size_t warps = (size_t)grid * WNM_WARPS;
         P.r_lo = (long long*)dalloc(warps * P.r_cap * 8);

@@ -77,8 +77,8 @@ WNM_HD int wnm_rank(const WnmProgram& W, const long long* lo, const int* nv, int
         if (p == q) continue;
         const long long d = x - lo[p] - (p < q ? 0 : 1);   // variants of p at or below x (p earlier: ties go first), below x otherwise
         if (d < 0) continue;
-        const long long c = d / W.step + 1;
-        idx += c < nv[p] ? c : nv[p];
+        if (d >= (long long)(nv[p] - 1) * W.step) idx += nv[p];   // all of them: the usual case, events lie further apart than 2 u
+        else idx += (int)d / W.step + 1;                           // (d < 2 u: 32-bit division)
     }
     return (int)idx;
 }

@@ -164,3 +164,26 @@ def test_limits_and_rejected_shapes(ctx):
             log.why_not_match(bad["p"], bad["c"], 3, bad["step"], 3)
         assert e.value.code == bad["code"]
     log.close()
+
+
+@pytest.mark.gpu
+def test_sharded_log_one_process_all_gpus():
+    """siesta_multi_why_not_match: candidates are cut at the shard borders, every shard answers its own, trace indices stay global."""
+    import torch
+
+    from sequencedetectionqueryexecutor_b200 import api
+    rng = np.random.default_rng(5)
+    n_gpu = torch.cuda.device_count()
+    for ids in ([0, 0, 0], list(range(n_gpu)) if n_gpu > 1 else [0]):
+        with api.Multi(ids) as m:
+            for _ in range(6):
+                off, act, ts, pattern, cons, u, step, k, flags = random_case(rng, n_traces=60)
+                want = oracle.why_not_match(off, act, ts, pattern, cons, u, step, k, flags=flags, run_limit=300_000)
+                if want is None or off[-1] == 0:
+                    continue
+                log = m.load_log(off, act, ts, 4)
+                assert log.why_not_match(pattern, cons, u, step, k, flags=flags).same_as(want)[0]
+                cand = np.sort(rng.choice(60, size=25, replace=False)).astype(np.int64)
+                sub = oracle.why_not_match(off, act, ts, pattern, cons, u, step, k, cand=cand, flags=flags, run_limit=300_000)
+                assert log.why_not_match(pattern, cons, u, step, k, cand=cand, flags=flags).same_as(sub)[0]
+                log.close()
