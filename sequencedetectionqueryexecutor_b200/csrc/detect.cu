@@ -823,6 +823,67 @@ __global__ void __launch_bounds__(GT) gather_kernel(const __grid_constant__ Gath
     }
 }
 
+// The same placement when every matching trace holds ONE occurrence of k events (class NK asked for the first-largest
+// occurrence: the metric's configuration).  The three running sums collapse into one count of matching traces - a ballot and
+// a popcount per warp instead of three 64-bit shuffle scans - and the owner of an output slot is found through a
+// 32-entry table in shared memory instead of a five-step shuffle search: the general kernel spends ~470 instructions per
+// candidate (profiles/r02c_gather_ncu_summary.md), this one a third of that.
+__global__ void __launch_bounds__(GT) gather_uniform_kernel(const __grid_constant__ GatherParams G, const int k) {
+    __shared__ unsigned s_wsum[GT / 32];
+    __shared__ long long s_se[GT / 32][32];
+    const int64_t i = (int64_t)blockIdx.x * GT + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t chunk = blockIdx.x / SC;
+    const unsigned long long b0 = G.top[chunk] + G.blk[blockIdx.x];   // matching traces before this block (sum 0 of 3)
+    uint32_t w = 0;
+    long long se = 0;
+    int64_t cand_i = i;
+    if (i < G.n) {
+        w = G.d_cnt[i];
+        se = G.d_stage[i];
+        if (G.cand) cand_i = G.cand[i];
+    }
+    const bool hit = (w & 0xFFFFu) != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    const unsigned wex = __popc(bal & ((1u << lane) - 1u));
+    const unsigned wn = __popc(bal);
+    if (lane == 0) s_wsum[warp] = wn;
+    if (hit) s_se[warp][wex] = se;   // the r-th matching trace of the warp: where its k events are staged
+    __syncthreads();
+    unsigned before = 0;
+#pragma unroll
+    for (int q = 0; q < GT / 32; ++q) before += q < warp ? s_wsum[q] : 0u;
+    const int64_t wtp = (int64_t)b0 + before;   // matching traces before this warp
+    if (hit) {
+        const int64_t tp = wtp + wex;
+        G.trace_idx[tp] = cand_i + G.base.trace;
+        G.occ_off[tp] = tp + G.base.occ;
+        G.ev_off[tp] = tp * k + G.base.ev;
+    }
+    const unsigned wtot = wn * (unsigned)k;
+    const long long wbase = wtp * k;
+    const unsigned inv = 65536u / (unsigned)k + 1u;   // (f * inv) >> 16 == f / k for every f < 2048 and k <= 8
+    for (unsigned f = lane; f < wtot; f += 32) {
+        const unsigned r = (f * inv) >> 16, e = f - r * (unsigned)k;
+        const long long from = s_se[warp][r] + e;
+        const long long to = wbase + f;
+        const int32_t c_pos = __ldg(G.s_ev_pos + from);
+        int32_t c_rank = 0, c_act = 0;
+        long long c_ts = 0;
+        if (G.all_cols) {
+            c_rank = __ldg(G.s_ev_rank + from);
+            c_act = __ldg(G.s_ev_act + from);
+            c_ts = __ldg(reinterpret_cast<const long long*>(G.s_ev_ts) + from);
+        }
+        G.ev_posv[to] = c_pos;
+        if (G.all_cols) {
+            G.ev_rank[to] = c_rank;
+            G.ev_act[to] = c_act;
+            G.ev_ts[to] = c_ts;
+        }
+    }
+}
+
 __global__ void set_tail_kernel(int64_t* occ_off, int64_t n_tr, int64_t n_occ, int64_t* ev_off, int64_t n_ev, RebaseOffsets base) {
     occ_off[n_tr] = n_occ + base.occ;
     ev_off[n_occ] = n_ev + base.ev;
@@ -1323,7 +1384,10 @@ int detect_device_finish_impl(DetectPending* q, siesta_dev_matches* out) {
         SIESTA_LAUNCHED();
         scan_top_kernel<<<1, SC, 0, stream>>>(G.top, G.n_chunks);
         SIESTA_LAUNCHED();
-        gather_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G);
+        if (q->uniform_k > 0 && q->uniform_k <= 8 && std::getenv("SIESTA_NO_UNIFORM_GATHER") == nullptr)
+            gather_uniform_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G, q->uniform_k);
+        else
+            gather_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G);
         SIESTA_LAUNCHED();
         SIESTA_CUDA_OK(cudaGetLastError());
     }
