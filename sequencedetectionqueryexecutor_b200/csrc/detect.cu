@@ -1585,6 +1585,74 @@ __global__ void __launch_bounds__(GT) gather_packed_kernel(const __grid_constant
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(O.status, XST_RANGE);
 }
 
+// The compact block when every matching trace holds one occurrence of k events (gather_uniform_kernel's counting, the
+// wire format of gather_packed_kernel with uniform = 1: no offset sections).
+__global__ void __launch_bounds__(GT) gather_packed_uniform_kernel(const __grid_constant__ GatherParams G, const __grid_constant__ PackSections O,
+                                                                   const int k) {
+    __shared__ unsigned s_wsum[GT / 32];
+    __shared__ long long s_se[GT / 32][32];
+    const int64_t i = (int64_t)blockIdx.x * GT + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t chunk = blockIdx.x / SC;
+    const unsigned long long b0 = G.top[chunk] + G.blk[blockIdx.x];
+    uint32_t w = 0;
+    long long se = 0;
+    if (i < G.n) {
+        w = G.d_cnt[i];
+        se = G.d_stage[i];
+    }
+    const bool hit = (w & 0xFFFFu) != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    const unsigned wex = __popc(bal & ((1u << lane) - 1u));
+    const unsigned wn = __popc(bal);
+    if (lane == 0) s_wsum[warp] = wn;
+    if (hit) s_se[warp][wex] = se;
+    __syncthreads();
+    unsigned before = 0;
+#pragma unroll
+    for (int q = 0; q < GT / 32; ++q) before += q < warp ? s_wsum[q] : 0u;
+    const int64_t wtp = (int64_t)b0 + before;
+    int bad = 0;
+    if (hit) {
+        const int64_t tp = wtp + wex;
+        bad |= (unsigned long long)i > 0xFFFFFFFFull;
+        O.trace[tp] = (uint32_t)i;
+        if (O.base) O.base[tp] = G.s_ev_ts[se];
+    }
+    const unsigned wtot = wn * (unsigned)k;
+    const long long wbase = wtp * k;
+    const unsigned inv = 65536u / (unsigned)k + 1u;   // (f * inv) >> 16 == f / k for every f < 2048 and k <= 8
+    for (unsigned f = lane; f < wtot; f += 32) {
+        const unsigned r = (f * inv) >> 16, e = f - r * (unsigned)k;
+        const long long o_se = s_se[warp][r];
+        const long long from = o_se + e;
+        const long long to = wbase + f;
+        const int32_t c_pos = __ldg(G.s_ev_pos + from);
+        int32_t c_rank = 0, c_act = 0;
+        long long c_ts = 0, c_base = 0;
+        if (G.all_cols) {
+            c_rank = __ldg(G.s_ev_rank + from);
+            c_act = __ldg(G.s_ev_act + from);
+            c_ts = __ldg(reinterpret_cast<const long long*>(G.s_ev_ts) + from);
+            c_base = __ldg(reinterpret_cast<const long long*>(G.s_ev_ts) + o_se);
+        }
+        bad |= (unsigned)c_pos > 0xFFFFu;
+        O.pos[to] = (uint16_t)c_pos;
+        if (G.all_cols) {
+            long long d = c_ts - c_base;
+            if (O.seconds) {
+                bad |= d % 1000 != 0;
+                d /= 1000;
+            }
+            bad |= (unsigned)c_rank > 0xFFu || (unsigned)c_act > 0xFFFFu || d < -0x7fffffffll - 1 || d > 0x7fffffffll;
+            O.rank[to] = (uint8_t)c_rank;
+            O.act[to] = (uint16_t)c_act;
+            O.delta[to] = (int32_t)d;
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(O.status, XST_RANGE);
+}
+
 // Header of the block: sizes from the request's counters, status, the tails of the offset sections, the error list.
 __global__ void pack_header_kernel(const unsigned long long* counters, const int64_t* err_list, const int64_t* unsup_list, int unsup_slot,
                                    XHeader proto, XHeader* hdr, const __grid_constant__ PackSections O) {
@@ -1709,7 +1777,10 @@ int detect_device_pack_impl(DetectPending* q, const PackTarget& tgt) {
         SIESTA_LAUNCHED();
         scan_top_kernel<<<1, SC, 0, stream>>>(G.top, G.n_chunks);
         SIESTA_LAUNCHED();
-        gather_packed_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G, O, q->uniform_k ? 1 : 0);
+        if (q->uniform_k > 0 && q->uniform_k <= 8 && std::getenv("SIESTA_NO_UNIFORM_GATHER") == nullptr)
+            gather_packed_uniform_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G, O, q->uniform_k);
+        else
+            gather_packed_kernel<<<(unsigned)G.n_blk, GT, 0, stream>>>(G, O, q->uniform_k ? 1 : 0);
         SIESTA_LAUNCHED();
     }
     pack_header_kernel<<<1, 256, 0, stream>>>(q->d_counters, q->d_err, q->d_unsup, q->unsup_slot, proto, tgt.hdr, O);

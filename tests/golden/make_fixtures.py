@@ -5,7 +5,7 @@
   serialised from tests/kat.py.  These are the vectors that pin the oracle.
 * fixtures.npz - outputs of the pinned CPU oracle on small seeded logs for every entry point of the hot path
   (detection in the shapes of BASELINE configs[0], [1], [4] and a run-list-engine pattern, declare counts, pair
-  statistics, posting lists + intersection, /explore).  tests/test_golden.py checks that the oracle still reproduces
+  statistics, posting lists + intersection, /explore, why-not-match).  tests/test_golden.py checks that the oracle still reproduces
   them (CPU) and that the CUDA path reproduces them through the C-ABI (-m gpu).  The reference itself cannot run here
   (no JVM), so these are oracle outputs, not outputs of the Java code.
 """
@@ -43,6 +43,12 @@ DETECT_CASES = {
 COUNT_LOG = dict(n_traces=500, min_len=30, max_len=70, n_act=20, seed=0x51E57A03)
 PAIRS = [(0, 1), (1, 2), (2, 2), (5, 0)]
 EXPLORE = dict(log=dict(n_traces=600, min_len=10, max_len=50, n_act=12, seed=81, jitter_ms=True), pattern=[0, 1])
+# why-not-match: (pattern, constraints (pos_a, pos_b, kind, method, value), uncertainty, step, k, flags)
+WNM = dict(log=dict(n_traces=400, min_len=5, max_len=25, n_act=8, seed=83, max_gap_s=6, jitter_ms=True),
+           cases={"time3": ([0, 1, 2], [(0, 1, abi.WNM_TIME, abi.WNM_WITHIN, 4), (1, 2, abi.WNM_TIME, abi.WNM_ATLEAST, 6)], 3, 1, 3, 0),
+                  "gap_far": ([0, 1, 0, 3], [(0, 2, abi.WNM_GAP, abi.WNM_WITHIN, 30), (1, 3, abi.WNM_TIME, abi.WNM_ATLEAST, 9)], 4, 2, 2, 0),
+                  "positions": ([2, 1], [(0, 1, abi.WNM_TIME, abi.WNM_ATLEAST, 4)], 2, 1, 1, abi.F_EVT_POS)})
+WNM_KEYS = ("trace_idx", "total_change", "ev_pos", "ev_value", "ev_change", "ev_stream_pos")
 
 MATCH_KEYS = ("trace_idx", "occ_off", "ev_off", "ev_pos", "ev_rank", "ev_act", "ev_ts_ms", "err_trace_idx")
 
@@ -77,6 +83,12 @@ def compute():
     off, act, ts = gen.make_log(**EXPLORE["log"])
     comp, dur = explore_by_detection(off, act, ts, EXPLORE["pattern"], EXPLORE["log"]["n_act"])
     out["explore/completions"], out["explore/sum_duration_ms"] = comp, dur
+    off, act, ts = gen.make_log(**WNM["log"])
+    for name, (pattern, cons, u, step, k, flags) in WNM["cases"].items():
+        r = oracle.why_not_match(off, act, ts, pattern, cons, u, step, k, flags=flags, run_limit=3_000_000)
+        assert r is not None and r.n_traces > 0, name
+        for key in WNM_KEYS:
+            out[f"wnm/{name}/{key}"] = np.asarray(getattr(r, key))
     return out
 
 

@@ -95,3 +95,15 @@ def test_gpu_counting_paths_reproduce_the_fixtures(ctx, fx):
     finally:
         log.close()
     assert np.array_equal(comp, fx["explore/completions"]) and np.array_equal(dur, fx["explore/sum_duration_ms"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(mf.WNM["cases"]))
+def test_gpu_why_not_match_reproduces_the_fixtures(ctx, fx, name):
+    off, act, ts = gen.make_log(**mf.WNM["log"])
+    pattern, cons, u, step, k, flags = mf.WNM["cases"][name]
+    log = ctx.load_log(off, act, ts, mf.WNM["log"]["n_act"])
+    got = log.why_not_match(pattern, cons, u, step, k, flags=flags)
+    log.close()
+    for key in mf.WNM_KEYS:
+        assert np.array_equal(np.asarray(getattr(got, key)), fx[f"wnm/{name}/{key}"]), (name, key)
