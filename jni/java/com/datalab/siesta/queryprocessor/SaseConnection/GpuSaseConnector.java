@@ -75,6 +75,17 @@ public class GpuSaseConnector extends SaseConnector {
 
     @Override
     public List<Occurrences> evaluate(SIESTAPattern pattern, Map<String, List<Event>> events, boolean onlyAppearances) {
+        return evaluate(pattern, events, onlyAppearances, true);
+    }
+
+    /**
+     * The same request with the caller's returnAll known.  The seam's signature does not carry it, so the override above asks
+     * for every non-overlapping occurrence; a plan that is adapted to call this overload (one line in
+     * QueryPlanPatternDetection.execute :121, which reads qpdw.isReturnAll() on the next line anyway) gets
+     * clearOccurrences(returnAll)'s selection directly, and with returnAll = false the library only computes the first-largest
+     * occurrence of every trace (no relative seconds, no overlap test: the fastest kernels).
+     */
+    public List<Occurrences> evaluate(SIESTAPattern pattern, Map<String, List<Event>> events, boolean onlyAppearances, boolean returnAll) {
         // ---- dictionaries: trace ids in map order, activity names folded case-insensitively
         List<String> traceIds = new ArrayList<>();
         Map<String, Integer> actIds = new HashMap<>();
@@ -116,7 +127,7 @@ public class GpuSaseConnector extends SaseConnector {
         }
         // ---- the pattern: ComplexPattern.getNfa / SimplePattern.getNfa, compiled by the library
         int[] nfa = GpuNative.patternCompile(symbolsOf(pattern, actIds, actNames), constraintsOf(pattern), onlyAppearances);
-        int flags = GpuNative.F_RETURN_ALL | (evtPos ? GpuNative.F_EVT_POS : 0);
+        int flags = (returnAll ? GpuNative.F_RETURN_ALL : 0) | (evtPos ? GpuNative.F_EVT_POS : 0);
         long m = GpuNative.evaluateEvents(MULTI, traceOff, act, tsMs, actNames.size() + 1, nfa, flags);
         try {
             long[] sizes = GpuNative.matchesSizes(m);
