@@ -46,8 +46,8 @@ WORKLOADS = {
                                  bytes_per_event=4, pattern=GAP6_TEXT, kernel=NKP, states=GAP6, e2e_traces=4_000_000),
     # the same query with returnAll=true: what the JNI drop-in asks for (the seam does not carry returnAll: INTEGRATION.md 1)
     "detection_gap6_all_4Mx50": dict(n_traces=4_000_000, min_len=50, max_len=50, n_act=20, max_gap_s=600, seed=0x51E57A05,
-                                     bytes_per_event=12, pattern=GAP6_TEXT.replace("returnAll=false", "returnAll=true"),
-                                     kernel="detect_kernel<W=1, FAST_NK> (K1: filter + class NK closed form, greedy non-overlap selection)",
+                                     bytes_per_event=4, pattern=GAP6_TEXT.replace("returnAll=false", "returnAll=true"),
+                                     kernel=NKP + "; traces with more than one engine match (1.2 %) re-run on the staged kernel, which reads their timestamps for the overlap test",
                                      flags=abi.F_RETURN_ALL, states=GAP6, e2e_traces=4_000_000),
     # BASELINE.json configs[1]: /detection Kleene pattern a+ b* with a within-10-minutes time constraint,
     # 1M traces x 100 events (20 activity types, gaps U{1..120} s).  SURVEY.md §8(d) cfg 2.
@@ -508,7 +508,7 @@ def main():
         np_off, np_act, np_ts = h_off.numpy(), h_act.numpy(), h_ts.numpy()
         # a query without a time constraint reads timestamps only for the events it reports, in place from the pinned host
         # column (siesta_evaluate_events): 4 B/event + 8 B per reported event / matching trace cross the link instead of 12 B/event
-        ts_in_place = wl["bytes_per_event"] == 4 and not (flags & abi.F_RETURN_ALL) and not os.environ.get("SIESTA_NO_TS_ZERO_COPY")
+        ts_in_place = wl["bytes_per_event"] == 4 and not os.environ.get("SIESTA_NO_TS_ZERO_COPY")
         flags0 = flags
 
         def e2e_leg(col, act_bytes, call):

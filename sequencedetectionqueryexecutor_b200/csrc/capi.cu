@@ -629,7 +629,10 @@ static int evaluate_events_impl(siesta_ctx* ctx, const int64_t* trace_off, const
     // cudaHostRegister, torch pin_memory), the kernels read those few values straight from it over the host link
     // instead of the whole column travelling to the device first: 4 B/event cross the link instead of 12.
     const int64_t* ts_mapped = nullptr;
-    if (!needs_ts && n_events > 0 && std::getenv("SIESTA_NO_TS_ZERO_COPY") == nullptr) {
+    // (returnAll asks for relative seconds only in Occurrence.overlaps: when kernel K1-P takes the request, the traces with more
+    //  than one engine match - the only ones that test overlaps - are a small minority and read theirs through the mapping too)
+    const bool few_ts = !needs_ts || ((flags & SIESTA_F_RETURN_ALL) && detect_nkp_eligible(nfa, flags, n_activities));
+    if (few_ts && n_events > 0 && std::getenv("SIESTA_NO_TS_ZERO_COPY") == nullptr) {
         cudaPointerAttributes pa;
         if (cudaPointerGetAttributes(&pa, ts_ms) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
             ts_mapped = reinterpret_cast<const int64_t*>(pa.devicePointer);

@@ -181,6 +181,7 @@ void detect_pending_discard(DetectPending* q);
 float detect_pending_k1_ms(DetectPending* q);                            // releases the request (stream-ordered)
 int64_t detect_pack_required_bytes(int64_t n_cand_or_traces, int64_t n_events_log, int uniform_k, bool all_cols, bool return_all);
 int detect_uniform_k(const siesta_nfa* nfa, uint32_t flags);
+bool detect_nkp_eligible(const siesta_nfa* nfa, uint32_t flags, int32_t n_activities);
 void build_lut(const siesta_nfa* nfa, const DevNfa& dn, int32_t n_activities, uint32_t flags, std::vector<uint16_t>& lut,
                int* needs_ts, int* n_positive);
 

@@ -1054,9 +1054,15 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
         const uint16_t sg = lut[a] & 0xFFu;
         if (sg && std::find(sigs.begin(), sigs.end(), sg) == sigs.end()) sigs.push_back(sg);
     }
-    const bool use_nkp = nkw_space != NKW_NONE && !needs_ts && log->act_valid && log->n_activities <= 255 && !sigs.empty() && sigs.size() <= 7 &&
-                         (reinterpret_cast<uintptr_t>(log->d_act) & 31u) == 0 && std::getenv("SIESTA_K1_NO_NKP") == nullptr;
-    const size_t n_reg = use_nkp ? 2 : 1;  // staging regions: [0, cap) by atomics (staged kernels), [cap, 2 cap) fixed tile slots (K1-P)
+    // (nkw_build only admits predicates that read no relative seconds; with returnAll the seconds are needed by the overlap
+    //  test alone, and the traces that need it - more than one engine match - are re-run on the staged kernel)
+    const bool use_nkp = nkw_space != NKW_NONE && (!needs_ts || return_all) && log->act_valid && log->n_activities <= 255 && !sigs.empty() && sigs.size() <= 7 &&
+                         (reinterpret_cast<uintptr_t>(log->d_act) & 31u) == 0 && std::getenv("SIESTA_K1_NO_NKP") == nullptr;   // (keep in step with detect_nkp_eligible)
+    // staging regions: [0, cap_ev) by atomics (staged kernels), then K1-P's fixed tile slots (n_positive per candidate: with
+    // returnAll cap_ev is bounded by the log's events, which may be fewer), then K1-L's
+    const size_t reg2 = use_nkp ? (size_t)std::max<int64_t>(cap_ev, n * (int64_t)std::max(1, n_positive)) : 0;
+    // returnAll: K1-P answers the traces with ONE engine match (its occurrence is the selection) and stages that occurrence's
+    // event count in a slot of its own per candidate, behind the staged kernels' and K1-L's
     // class NK: the traces beyond the mask kernels' limits re-run on K1-L, which stages in a region of its own behind
     // the others and takes its per-trace arrays from a pool
     const bool use_long = dn.fast_class == FAST_NK && std::getenv("SIESTA_K1_NO_LONG") == nullptr;
@@ -1070,12 +1076,12 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
     const size_t o_nlut = use_nkp ? carve((size_t)(log->n_activities + 1) * 16) : 0;
     const size_t o_lut = carve(lut.size() * sizeof(uint16_t)), o_nocc = carve(nn * 4), o_stage = carve(nn * 8),
                  o_stage_occ = carve(return_all ? nn * 8 : 0), o_counters = carve(32 * 8), o_err = carve(nn * 8), o_ovf = carve(nn * 8),
-                 o_blk = carve(n_blk * 3 * 8), o_top = carve(((n_blk + 1023) / 1024) * 3 * 8), o_occ_nev = carve(return_all ? (size_t)(cap_occ + cap_long) * 4 : 0), o_pos = carve(((size_t)cap_ev * n_reg + (size_t)cap_long) * 4);
+                 o_blk = carve(n_blk * 3 * 8), o_top = carve(((n_blk + 1023) / 1024) * 3 * 8), o_occ_nev = carve(return_all ? ((size_t)(cap_occ + cap_long) + (use_nkp ? nn : 0)) * 4 : 0), o_pos = carve(((size_t)cap_ev + reg2 + (size_t)cap_long) * 4);
     size_t o_rank = 0, o_act = 0, o_ts = 0;
     if (all_cols) {
-        o_rank = carve(((size_t)cap_ev * n_reg + (size_t)cap_long) * 4);
-        o_act = carve(((size_t)cap_ev * n_reg + (size_t)cap_long) * 4);
-        o_ts = carve(((size_t)cap_ev * n_reg + (size_t)cap_long) * 8);
+        o_rank = carve(((size_t)cap_ev + reg2 + (size_t)cap_long) * 4);
+        o_act = carve(((size_t)cap_ev + reg2 + (size_t)cap_long) * 4);
+        o_ts = carve(((size_t)cap_ev + reg2 + (size_t)cap_long) * 8);
     }
     if ((rc = work.alloc(w_off))) return rc;
     char* wb = work.as<char>();
@@ -1175,6 +1181,7 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
             N.tile_slot = 18;
             N.fix_ev = cap_ev;
             N.fix_np = std::max(1, n_positive);
+            N.fix_occ = return_all ? cap_occ + cap_long : -1;
             // the scan's table: {m, b0, b1, b2} per activity (detect_nkp.cu); class c = index of the signature + 1
             std::vector<uint32_t> nlut((size_t)(log->n_activities + 1) * 4, 0u);
             std::memset(N.cls_word, 0, sizeof(N.cls_word));
@@ -1243,7 +1250,7 @@ int detect_device_begin_impl(Log* log, const siesta_nfa* nfa, const int64_t* d_c
             LQ.work_cap = SIESTA_MAX_UNSUPPORTED;
             LQ.pool = wb + o_pool;
             LQ.pool_bytes = long_pool;
-            LQ.ev_base = (int64_t)cap_ev * (int64_t)n_reg;
+            LQ.ev_base = (int64_t)cap_ev + (int64_t)reg2;
             LQ.ev_cap = cap_long;
             LQ.occ_base = cap_occ;
             LQ.occ_cap = cap_long;
@@ -1678,6 +1685,25 @@ __global__ void pack_header_kernel(const unsigned long long* counters, const int
     }
     for (int64_t i = threadIdx.x; i < n_err && i < XCHG_ERR_CAP; i += blockDim.x) O.err[i] = err_list[i];
     for (int64_t i = threadIdx.x; i < n_unsup && i < XCHG_ERR_CAP; i += blockDim.x) O.unsup[i] = unsup_list[i];
+}
+
+// Would kernel K1-P take this request on a log with validated ids and an aligned activity column?  (siesta_evaluate_events
+// decides with it whether a returnAll request can leave the timestamp column on the host: K1-P reads no timestamps to match,
+// and only the few traces with more than one engine match are re-run on the staged kernel, which does.)
+bool detect_nkp_eligible(const siesta_nfa* nfa, uint32_t flags, int32_t n_activities) {
+    DevNfa dn;
+    if (validate_nfa(nfa, flags, &dn) != SIESTA_OK || n_activities > 255 || std::getenv("SIESTA_K1_NO_NKP") != nullptr) return false;
+    NkwProgram prog;
+    if (nkw_build(dn, flags, &prog) == NKW_NONE) return false;
+    std::vector<uint16_t> lut;
+    int needs_ts = 0, n_positive = 0;
+    build_lut(nfa, dn, n_activities, flags, lut, &needs_ts, &n_positive);
+    std::vector<uint16_t> sigs;
+    for (size_t a = 0; a < lut.size(); ++a) {
+        const uint16_t sg = lut[a] & 0xFFu;
+        if (sg && std::find(sigs.begin(), sigs.end(), sg) == sigs.end()) sigs.push_back(sg);
+    }
+    return !sigs.empty() && sigs.size() <= 7;
 }
 
 int detect_uniform_k(const siesta_nfa* nfa, uint32_t flags) {

@@ -51,6 +51,7 @@ struct DetectParams {
     // [fix_ev + 32 i fix_np, + 32 fix_np) of a second staging region behind the first one
     int64_t fix_ev;
     int32_t fix_np;
+    int64_t fix_occ;          // returnAll: candidate i stages its occurrence's event count at s_occ_nev[fix_occ + i] (-1: not asked for)
     // K1-P: a state that owns exactly ONE class is the minterm of the class planes with these polarities
     // (st_inv[k][p] = 0 or ~0: plane p enters state k's mask as it is / complemented); st_single[k] = 0: OR of several classes
     uint32_t st_inv[SIESTA_MAX_STATES][3];

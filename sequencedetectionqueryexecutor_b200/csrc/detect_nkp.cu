@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
     const uint4* s_lut = s_lut_all + (lane & (LUT_SKEW - 1));
     const bool evt_pos = (P.flags & SIESTA_F_EVT_POS) != 0;
     const bool all_cols = (P.flags & SIESTA_F_NO_EVENT_COLUMNS) == 0;
-    const bool first_only = (P.flags & SIESTA_F_COUNT_MATCHES) == 0;  // monotone walks: the first completed start wins
+    const bool return_all = (P.flags & SIESTA_F_RETURN_ALL) != 0;
+    // monotone walks: the first completed start wins; the number of engine matches is only needed for COUNT_MATCHES and for
+    // returnAll (one match: it is the selection; more: Occurrence.overlaps decides, on the staged kernel)
+    const bool first_only = (P.flags & (SIESTA_F_COUNT_MATCHES | SIESTA_F_RETURN_ALL)) == 0;
 
     const long long n_work = P.n_work_dev ? (long long)__ldg(P.n_work_dev) : (long long)P.n_work;
     const long long n_tiles = (n_work + 31) / 32;
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
                 bool hit;
                 if constexpr (MARKOV) hit = nkw_eval_markov<mask_t>(prog, T, best, n_emitted);   // all starts at once
                 else hit = nkw_eval<mask_t>(prog, T, best, n_emitted, first_only);
-                if (hit) status = ST_MATCH;
+                if (hit) status = (return_all && n_emitted > 1) ? ST_OVF : ST_MATCH;
             }
         }
 
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
             const unsigned y1 = __shfl_up_sync(0xffffffffu, i1, d);
             if (lane >= d) i1 += y1;
         }
-        if (!first_only) {
+        if (!first_only) {   // COUNT_MATCHES / returnAll: the engine's match count is part of the result
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const unsigned long long y2 = __shfl_up_sync(0xffffffffu, i2, d);
@@ -257,6 +260,10 @@ __global__ void __launch_bounds__(NT_MAX, SIESTA_NKP_MIN_CTAS) detect_nkp_kernel
             P.d_cnt[ci] = my_occ | (my_ev << 16);
             if (status == ST_MATCH) {
                 P.d_stage[ci] = base1 + (long long)(i1 - my_ev);
+                if (P.fix_occ >= 0) {   // returnAll: the placement reads the event count of every staged occurrence
+                    P.d_stage_occ[ci] = P.fix_occ + ci;
+                    P.s_occ_nev[P.fix_occ + ci] = (int32_t)my_ev;
+                }
             } else if (status == ST_OVF) {
                 const unsigned long long at = atomicAdd(P.counters + P.ovf_slot, 1ull);
                 P.ovf_list[at] = ci;

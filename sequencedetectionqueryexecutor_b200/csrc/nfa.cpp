@@ -161,7 +161,9 @@ int validate_nfa(const siesta_nfa* nfa, uint32_t flags, DevNfa* out) {
 //                  position -> raw slots; an NFA that mixes the two stays on the staged kernel.
 int nkw_build(const DevNfa& dn, uint32_t flags, NkwProgram* out) {
     std::memset(out, 0, sizeof(*out));
-    if (dn.fast_class != 1 /* FAST_NK */ || (flags & SIESTA_F_RETURN_ALL)) return NKW_NONE;
+    // (returnAll: kernel K1-P answers the traces with a single engine match - its occurrence IS clearOccurrences(true)'s
+    //  selection - and hands the others to the staged kernel, which knows the overlap test)
+    if (dn.fast_class != 1 /* FAST_NK */) return NKW_NONE;
     const bool evt_pos = (flags & SIESTA_F_EVT_POS) != 0;
     bool any_pos = false, any_ts = false;
     out->n_states = dn.n_states;

@@ -128,8 +128,11 @@ extern "C" int engine_host_detect(const int64_t* trace_off, const int32_t* act, 
         const int lead = (int)(b0 & 7);
         NkwProgram prog;
         const int space = nkw_build(dn, flags, &prog);
-        const bool first_only = !(flags & SIESTA_F_COUNT_MATCHES);
-        if (space != NKW_NONE && !needs_ts && (b1 - b0) + lead <= 64 && (space == NKW_RAW || meta.size() <= 32)) {
+        // returnAll: K1-P answers a trace with ONE engine match (that occurrence is the selection); with more, the overlap test
+        // decides and the trace goes to the staged kernel (below), as a trace that does not fit
+        const bool return_all_h = (flags & SIESTA_F_RETURN_ALL) != 0;
+        const bool first_only = !(flags & (SIESTA_F_COUNT_MATCHES | SIESTA_F_RETURN_ALL));
+        if (space != NKW_NONE && (!needs_ts || return_all_h) && (b1 - b0) + lead <= 64 && (space == NKW_RAW || meta.size() <= 32)) {
             std::vector<int> sel_idx;   // the selected occurrence as indices into the filtered list
             bool hit;
             if (space == NKW_RANK) {
@@ -186,19 +189,22 @@ extern "C" int engine_host_detect(const int64_t* trace_off, const int32_t* act, 
                 for (unsigned long long m = best; m; m &= m - 1) sel_idx.push_back(pe.rank(__builtin_ffsll((long long)m) - 1));
             }
             if (!hit) continue;
-            o.emitted += emitted;
-            o.trace_idx.push_back(t);
-            for (int j : sel_idx) {
-                const int src = (int)(meta[j] >> 16);
-                o.ev_pos.push_back(src);
-                o.ev_rank.push_back(j);
-                o.ev_act.push_back(act[b0 + src]);
-                const long long raw = ts_ms[b0 + src];
-                o.ev_ts.push_back(evt_pos ? raw : (long long)((int)((raw - t0) / 1000)) * 1000 + t0);
+            if (!(return_all_h && emitted > 1)) {
+                o.emitted += emitted;
+                o.trace_idx.push_back(t);
+                for (int j : sel_idx) {
+                    const int src = (int)(meta[j] >> 16);
+                    o.ev_pos.push_back(src);
+                    o.ev_rank.push_back(j);
+                    o.ev_act.push_back(act[b0 + src]);
+                    const long long raw = ts_ms[b0 + src];
+                    o.ev_ts.push_back(evt_pos ? raw : (long long)((int)((raw - t0) / 1000)) * 1000 + t0);
+                }
+                o.ev_off.push_back((int64_t)o.ev_pos.size());
+                o.occ_off.push_back((int64_t)o.ev_off.size() - 1);
+                continue;
             }
-            o.ev_off.push_back((int64_t)o.ev_pos.size());
-            o.occ_off.push_back((int64_t)o.ev_off.size() - 1);
-            continue;
+            emitted = 0;   // more than one engine match: evaluated again below, with the overlap test
         }
         // kernel K1-L: class NK on a trace beyond the mask kernels' limits - the forward walk over the filtered list.  The
         // harness takes it from 25 relevant events on, so that the usual soak traces exercise it too.
