@@ -47,7 +47,7 @@ WORKLOADS = {
     # the same query with returnAll=true: what the JNI drop-in asks for (the seam does not carry returnAll: INTEGRATION.md 1)
     "detection_gap6_all_4Mx50": dict(n_traces=4_000_000, min_len=50, max_len=50, n_act=20, max_gap_s=600, seed=0x51E57A05,
                                      bytes_per_event=4, pattern=GAP6_TEXT.replace("returnAll=false", "returnAll=true"),
-                                     kernel=NKP + "; traces with more than one engine match (1.2 %) re-run on the staged kernel, which reads their timestamps for the overlap test",
+                                     kernel=NKP + "; traces with more than one engine match re-run on the staged kernel, which reads their timestamps for the overlap test",
                                      flags=abi.F_RETURN_ALL, states=GAP6, e2e_traces=4_000_000),
     # BASELINE.json configs[1]: /detection Kleene pattern a+ b* with a within-10-minutes time constraint,
     # 1M traces x 100 events (20 activity types, gaps U{1..120} s).  SURVEY.md §8(d) cfg 2.
