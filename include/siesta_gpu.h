@@ -492,7 +492,7 @@ typedef struct siesta_pair_count {
     int64_t max_duration_ms;
     uint64_t sum_squares_lo, sum_squares_hi; /* sum of duration_ms^2 as a 128-bit integer */
 } siesta_pair_count;
-int siesta_pair_stats(siesta_log* log, const int32_t* pair_a, const int32_t* pair_b, int32_t n_pairs /* <= 32 */,
+int siesta_pair_stats(siesta_log* log, const int32_t* pair_a, const int32_t* pair_b, int32_t n_pairs /* any number: passes of 32 */,
                       siesta_pair_count* out, double* kernel_ms);
 /* Device form for the multi-GPU combine: d_out[8 * n_pairs] int64 = count, sum, min, max, and the sum of squares as
  * four 32-bit limbs (one per int64).  count / sum / limbs combine with a SUM all-reduce (carry-normalise afterwards),

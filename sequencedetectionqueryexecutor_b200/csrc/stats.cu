@@ -140,13 +140,31 @@ __global__ void __launch_bounds__(32) pair_stats_fold_kernel(const unsigned long
 
 using namespace siesta;
 
+static int pair_stats_chunk(siesta_log* log, const int32_t* pair_a, const int32_t* pair_b, int32_t n_pairs, int64_t* d_out, void* stream_,
+                            double* kernel_ms);
+
+// Any number of pairs: the kernel keeps one pair per lane, so a request is served in passes of MAX_STAT_PAIRS pairs.
 extern "C" int siesta_pair_stats_device(siesta_log* log, const int32_t* pair_a, const int32_t* pair_b, int32_t n_pairs,
                                         int64_t* d_out, void* stream_, double* kernel_ms) {
-    Log* L = reinterpret_cast<Log*>(log);
-    if (!L || !pair_a || !pair_b || n_pairs < 1 || n_pairs > MAX_STAT_PAIRS || !d_out) {
-        set_error("siesta_pair_stats: 1.." + std::to_string(MAX_STAT_PAIRS) + " pairs per call");
+    if (!log || !pair_a || !pair_b || n_pairs < 1 || !d_out) {
+        set_error("siesta_pair_stats: null argument or no pair");
         return SIESTA_E_INVALID;
     }
+    double total = 0;
+    for (int32_t at = 0; at < n_pairs; at += MAX_STAT_PAIRS) {
+        double ms = 0;
+        const int rc = pair_stats_chunk(log, pair_a + at, pair_b + at, std::min<int32_t>(MAX_STAT_PAIRS, n_pairs - at), d_out + 8 * (int64_t)at,
+                                        stream_, &ms);
+        if (rc) return rc;
+        total += ms;
+    }
+    if (kernel_ms) *kernel_ms = total;
+    return SIESTA_OK;
+}
+
+static int pair_stats_chunk(siesta_log* log, const int32_t* pair_a, const int32_t* pair_b, int32_t n_pairs, int64_t* d_out, void* stream_,
+                            double* kernel_ms) {
+    Log* L = reinterpret_cast<Log*>(log);
     SIESTA_CUDA_OK(cudaSetDevice(L->ctx->device));
     cudaStream_t stream = stream_ ? reinterpret_cast<cudaStream_t>(stream_) : L->ctx->stream;
     StatParams P;

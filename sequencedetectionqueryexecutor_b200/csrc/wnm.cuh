@@ -67,7 +67,10 @@ WNM_HD unsigned wnm_state_mask(const WnmProgram& W, int a) {
 // Event.getPrimaryMetric: EventTs.java:87-89 (epoch ms / 1000, Java's truncating division), EventPos.java:84-86
 WNM_HD long long wnm_primary(const WnmProgram& W, long long ts_ms, long long pos) { return W.evt_pos ? pos : ts_ms / 1000; }
 WNM_HD long long wnm_lo(const WnmProgram& W, long long primary) { return primary - W.u > 0 ? primary - W.u : 0; }
-WNM_HD int wnm_variants(const WnmProgram& W, long long primary) { return (int)((primary + W.u - wnm_lo(W, primary)) / W.step) + 1; }
+WNM_HD int wnm_variants(const WnmProgram& W, long long primary) {   // (clamped far above SIESTA_WNM_MAX_STREAM: such a trace is listed)
+    const long long v = (primary + W.u - wnm_lo(W, primary)) / W.step + 1;
+    return v > (1 << 20) ? (1 << 20) : (int)v;
+}
 
 // index of variant v of relevant event q in the stable sort by shifted value (getUnCertainStream :76-80)
 WNM_HD int wnm_rank(const WnmProgram& W, const long long* lo, const int* nv, int n_rel, int q, int v) {

@@ -118,6 +118,9 @@ def test_pair_stats_match_oracle(ctx):
     log = ctx.load_log(off, act, ts, 9)
     got, ms = log.pair_stats(pairs)
     assert got == oracle.pair_stats(off, act, ts, pairs)
+    every = [(a, b) for a in range(9) for b in range(9)]     # 81 pairs: served in passes of 32
+    got_all, _ = log.pair_stats(every)
+    assert got_all == oracle.pair_stats(off, act, ts, every)
     # a pair nobody holds, an activity outside the alphabet, durations of years (128-bit sum of squares)
     off2 = np.array([0, 4], dtype=np.int64)
     act2 = np.array([0, 1, 0, 1], dtype=np.int32)

@@ -599,6 +599,10 @@ def test_evaluate_events_reads_pinned_timestamps_in_place(ctx):
                dict(kind=X_, types=[3]), dict(kind=N_, types=[4])], 0),                         # K1-P
              ([dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[2])], 0),  # staged kernel, run-list engine
              ([dict(kind=N_, types=[0]), dict(kind=N_, types=[1])], abi.F_EVT_POS),
+             # returnAll on K1-P: the overlap test of the few traces with more than one engine match reads through the mapping as well
+             ([dict(kind=N_, types=[0]), dict(kind=O_, types=[1, 2], preds=[(abi.ATTR_POSITION, abi.OP_LE, 0, 10)]),
+               dict(kind=X_, types=[3]), dict(kind=N_, types=[4])], abi.F_RETURN_ALL),
+             ([dict(kind=N_, types=[0]), dict(kind=N_, types=[1])], abi.F_RETURN_ALL | abi.F_COUNT_MATCHES),
              ([dict(kind=P_, types=[0]), dict(kind=S_, types=[1], preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 600)])], 0)]  # matches on time: copied
     for states, flags in cases:
         nfa = abi.make_nfa(states)
