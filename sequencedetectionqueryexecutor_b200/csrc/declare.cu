@@ -24,6 +24,8 @@
 namespace siesta {
 
 constexpr int DT = 256;      // threads per CTA
+constexpr int DTS_MAX = 1024;   // the serial kernels: CTA size chosen per launch (shared-memory matrices are per CTA: large alphabets
+                                // fit one CTA per SM, which then has to hold all the SM's warps)
 constexpr int HS = 16;       // histogram buckets kept in shared memory (k < HS)
 constexpr int MAX_A_SMEM = 104;   // the serial kernels keep four A x A matrices in shared memory
 constexpr int MAX_A_ANY = 4096;   // declare_any_kernel: bounded by the result itself (8 A^2 int64 = 1 GB)
@@ -44,7 +46,7 @@ __device__ __forceinline__ long long shfl64(long long v, int src) {
 }
 
 template <int NB>  // NB = ceil(A / 32) activity blocks held in registers per lane
-__global__ void __launch_bounds__(DT) declare_kernel(const __grid_constant__ DeclareParams P) {
+__global__ void __launch_bounds__(DTS_MAX) declare_kernel(const __grid_constant__ DeclareParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int A = P.A;
     const int AA = A * A;
@@ -65,12 +67,12 @@ __global__ void __launch_bounds__(DT) declare_kernel(const __grid_constant__ Dec
     uint32_t* w_first = w_cnt + A;
     uint32_t* w_last = w_first + A;
 
-    for (int i = threadIdx.x; i < 4 * AA + 4 * A + A * HS; i += DT) s_co[i] = 0;
+    for (int i = threadIdx.x; i < 4 * AA + 4 * A + A * HS; i += blockDim.x) s_co[i] = 0;
     if (threadIdx.x < 2) s_misc[threadIdx.x] = 0;
     __syncthreads();
 
-    const long long warps_total = (long long)gridDim.x * (DT / 32);
-    for (long long t = (long long)blockIdx.x * (DT / 32) + warp; t < P.n_traces; t += warps_total) {
+    const long long warps_total = (long long)gridDim.x * (blockDim.x / 32);
+    for (long long t = (long long)blockIdx.x * (blockDim.x / 32) + warp; t < P.n_traces; t += warps_total) {
         long long lo = 0, hi = 0;
         if (lane == 0) { lo = P.trace_off[t]; hi = P.trace_off[t + 1]; }
         lo = shfl64(lo, 0);
@@ -157,17 +159,17 @@ __global__ void __launch_bounds__(DT) declare_kernel(const __grid_constant__ Dec
     unsigned long long* o_ord = o_co + AA;
     unsigned long long* o_resp = o_ord + AA;
     unsigned long long* o_prec = o_resp + AA;
-    for (int i = threadIdx.x; i < A; i += DT) {
+    for (int i = threadIdx.x; i < A; i += blockDim.x) {
         if (s_tot[i]) atomicAdd(o_tot + i, (unsigned long long)s_tot[i]);
         if (s_uniq[i]) atomicAdd(o_uniq + i, (unsigned long long)s_uniq[i]);
         if (s_first[i]) atomicAdd(o_first + i, (unsigned long long)s_first[i]);
         if (s_last[i]) atomicAdd(o_last + i, (unsigned long long)s_last[i]);
     }
-    for (int i = threadIdx.x; i < A * HS; i += DT) {
+    for (int i = threadIdx.x; i < A * HS; i += blockDim.x) {
         const int a = i / HS, k = i % HS;
         if (s_hist[i] && k <= P.k_cap) atomicAdd(o_hist + (long long)a * (P.k_cap + 1) + k, (unsigned long long)s_hist[i]);
     }
-    for (int i = threadIdx.x; i < AA; i += DT) {
+    for (int i = threadIdx.x; i < AA; i += blockDim.x) {
         if (s_co[i]) atomicAdd(o_co + i, (unsigned long long)s_co[i]);
         if (s_ord[i]) atomicAdd(o_ord + i, (unsigned long long)s_ord[i]);
         if (s_prec[i]) atomicAdd(o_prec + i, (unsigned long long)s_prec[i]);
@@ -192,17 +194,17 @@ __global__ void __launch_bounds__(DT) declare_kernel(const __grid_constant__ Dec
 // One warp per trace, serial over the events, lanes = activities: lane o keeps the last position of activity o; at an
 // event of activity x every lane whose last position is later than x's previous one adds 1 to alternate[o][x].
 template <int NB>
-__global__ void __launch_bounds__(DT) declare_alt_chain_kernel(const __grid_constant__ DeclareParams P) {
+__global__ void __launch_bounds__(DTS_MAX) declare_alt_chain_kernel(const __grid_constant__ DeclareParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int A = P.A;
     const int AA = A * A;
     uint32_t* s_altT = reinterpret_cast<uint32_t*>(smem_raw);  // transposed: [x][o] = alternate[o][x]
     uint32_t* s_chain = s_altT + AA;                           // [a][b]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 2 * AA; i += DT) s_altT[i] = 0;
+    for (int i = threadIdx.x; i < 2 * AA; i += blockDim.x) s_altT[i] = 0;
     __syncthreads();
-    const long long warps_total = (long long)gridDim.x * (DT / 32);
-    for (long long t = (long long)blockIdx.x * (DT / 32) + warp; t < P.n_traces; t += warps_total) {
+    const long long warps_total = (long long)gridDim.x * (blockDim.x / 32);
+    for (long long t = (long long)blockIdx.x * (blockDim.x / 32) + warp; t < P.n_traces; t += warps_total) {
         long long lo = 0, hi = 0;
         if (lane == 0) { lo = P.trace_off[t]; hi = P.trace_off[t + 1]; }
         lo = shfl64(lo, 0);
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(DT) declare_alt_chain_kernel(const __grid_cons
     unsigned long long* o_alt_p = o_alt_r + AA;
     unsigned long long* o_chain_r = o_alt_p + AA;
     unsigned long long* o_chain_p = o_chain_r + AA;
-    for (int i = threadIdx.x; i < AA; i += DT) {
+    for (int i = threadIdx.x; i < AA; i += blockDim.x) {
         if (s_altT[i]) {
             const int x = i / A, o = i % A;
             atomicAdd(o_alt_r + (long long)o * A + x, (unsigned long long)s_altT[i]);
@@ -686,35 +688,68 @@ static int launch_pairs(const Ctx* ctx, cudaStream_t stream, const DeclareParams
     return SIESTA_OK;
 }
 
+// CTA size of a serial kernel: the one that keeps the most warps resident.  The count matrices live in shared memory per
+// CTA, so a large alphabet fits one CTA per SM, and that CTA has to bring all of the SM's warps (256 threads left 8 warps on
+// an SM at 100 activities).
+template <class K, class SmemOf>
+static int pick_cta(K kern, SmemOf smem_of, int* threads, size_t* smem, int* per_sm) {
+    int best_warps = 0;
+    for (int dt : {256, 512, DTS_MAX}) {
+        const size_t sm = smem_of(dt);
+        if (sm > (size_t)227 * 1024) continue;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, dt, sm) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        if (n * (dt / 32) > best_warps) {
+            best_warps = n * (dt / 32);
+            *threads = dt;
+            *smem = sm;
+            *per_sm = n;
+        }
+    }
+    if (!best_warps) {
+        set_error("declare counting: no CTA size fits the shared memory of this alphabet");
+        return SIESTA_E_UNSUPPORTED;
+    }
+    SIESTA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+    return SIESTA_OK;
+}
+
 template <int NB>
 static int launch_alt_chain(const Ctx* ctx, cudaStream_t stream, const DeclareParams& P) {
-    const size_t smem = sizeof(uint32_t) * (size_t)2 * P.A * P.A;
     auto kern = declare_alt_chain_kernel<NB>;
-    SIESTA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DT, smem));
-    if (per_sm < 1) per_sm = 1;
-    const int64_t ctas_needed = (P.n_traces + DT / 32 - 1) / (DT / 32);
+    int dt = 0, per_sm = 0;
+    size_t smem = 0;
+    const int A = P.A;
+    int rc = pick_cta(kern, [A](int) { return sizeof(uint32_t) * (size_t)2 * A * A; }, &dt, &smem, &per_sm);
+    if (rc) return rc;
+    const int64_t ctas_needed = (P.n_traces + dt / 32 - 1) / (dt / 32);
     int grid = (int)std::min<int64_t>(std::max<int64_t>(ctas_needed, 1), (int64_t)ctx->sm_count * per_sm);
-    kern<<<grid, DT, smem, stream>>>(P);
+    kern<<<grid, dt, smem, stream>>>(P);
     SIESTA_LAUNCHED();
     SIESTA_CUDA_OK(cudaGetLastError());
     return SIESTA_OK;
 }
 
-static size_t declare_smem(int A) { return sizeof(uint32_t) * ((size_t)4 * A * A + 4 * A + (size_t)A * HS + (size_t)(DT / 32) * 3 * A); }
+static size_t declare_smem(int A, int dt) { return sizeof(uint32_t) * ((size_t)4 * A * A + 4 * A + (size_t)A * HS + (size_t)(dt / 32) * 3 * A); }
 
 template <int NB>
 static int launch_declare(const Ctx* ctx, cudaStream_t stream, const DeclareParams& P) {
-    const size_t smem = declare_smem(P.A);
     auto kern = declare_kernel<NB>;
-    SIESTA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    SIESTA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DT, smem));
-    if (per_sm < 1) per_sm = 1;
-    const int64_t ctas_needed = (P.n_traces + DT / 32 - 1) / (DT / 32);
+    int dt = 0, per_sm = 0;
+    size_t smem = 0;
+    const int A = P.A;
+    int rc = pick_cta(kern, [A](int t) { return declare_smem(A, t); }, &dt, &smem, &per_sm);
+    if (rc) return rc;
+    const int64_t ctas_needed = (P.n_traces + dt / 32 - 1) / (dt / 32);
     int grid = (int)std::min<int64_t>(std::max<int64_t>(ctas_needed, 1), (int64_t)ctx->sm_count * per_sm);
-    kern<<<grid, DT, smem, stream>>>(P);
+    kern<<<grid, dt, smem, stream>>>(P);
     SIESTA_LAUNCHED();
     SIESTA_CUDA_OK(cudaGetLastError());
     return SIESTA_OK;
