@@ -89,18 +89,16 @@ WNM_HD int wnm_rank(const WnmProgram& W, const long long* lo, const int* nv, int
 // The sweep of one start event s over the stream [0, n): value / change / state mask per stream index.
 // prev: back pointers, entry (j, e) at prev[((j - 1) * n_cap + e) * prev_stride] for states j = 1 .. m - 1.
 // Returns the least total change of a match that starts at s (WNM_INF: none) and its stream indices in tup[0 .. m).
-template <typename PrevT>
-WNM_HD int wnm_sweep(const WnmProgram& W, const int* __restrict__ val, const int* __restrict__ chg, const unsigned char* __restrict__ smask,
-                     int n, int s, PrevT* prev, int n_cap, int prev_stride, int* tup) {
-    const int m = W.m;
-    if (m == 1) {
-        tup[0] = s;
-        return chg[s];
-    }
-    int latest[SIESTA_MAX_STATES];                       // latest event the family took at state j (-1: none yet)
-    int all_f[SIESTA_MAX_STATES], all_i[SIESTA_MAX_STATES];   // least cost of a run at state j over every taken event so far (ties: later)
-    int old_f[SIESTA_MAX_STATES], old_i[SIESTA_MAX_STATES];   // ... over the events strictly earlier in time than the current one
-    for (int j = 0; j < SIESTA_MAX_STATES; ++j) {
+// M = number of states, a template parameter: every per-state array is indexed by unrolled loops only, so the sweep's
+// state lives in registers (with a run-time state count the arrays sat in local memory).
+template <int M, typename PrevT>
+WNM_HD int wnm_sweep_m(const WnmProgram& W, const int* __restrict__ val, const int* __restrict__ chg, const unsigned char* __restrict__ smask,
+                       int n, int s, PrevT* prev, int n_cap, int prev_stride, int* tup) {
+    int latest[M];                // latest event the family took at state j (-1: none yet)
+    int all_f[M], all_i[M];       // least cost of a run at state j over every taken event so far (ties: later)
+    int old_f[M], old_i[M];       // ... over the events strictly earlier in time than the current one
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
         latest[j] = -1;
         all_f[j] = old_f[j] = WNM_INF;
         all_i[j] = old_i[j] = -1;
@@ -111,16 +109,19 @@ WNM_HD int wnm_sweep(const WnmProgram& W, const int* __restrict__ val, const int
     int best_f = WNM_INF, best_e = -1;
     int cur_val = val[s];
     for (int e = s + 1; e < n; ++e) {
-        if (val[e] != cur_val) {   // time moved on: everything taken so far is strictly earlier
-            cur_val = val[e];
-            for (int j = 0; j < m - 1; ++j) {
+        const int ve = val[e];
+        if (ve != cur_val) {   // time moved on: everything taken so far is strictly earlier
+            cur_val = ve;
+#pragma unroll
+            for (int j = 0; j < M - 1; ++j) {
                 old_f[j] = all_f[j];
                 old_i[j] = all_i[j];
             }
         }
         const unsigned sm = smask[e] >> 1;
         if (!sm) continue;
-        for (int j = m - 1; j >= 1; --j) {   // high to low: a run that took e at state j - 1 is not offered e again
+#pragma unroll
+        for (int j = M - 1; j >= 1; --j) {   // high to low: a run that took e at state j - 1 is not offered e again
             if (!((sm >> (j - 1)) & 1u)) continue;
             const int pf = W.time_at[j] ? old_f[j - 1] : all_f[j - 1];
             const int pi = W.time_at[j] ? old_i[j - 1] : all_i[j - 1];
@@ -128,12 +129,15 @@ WNM_HD int wnm_sweep(const WnmProgram& W, const int* __restrict__ val, const int
             bool ok = true;
             for (int q = 0; q < W.n_cons; ++q) {
                 if (W.c_b[q] != j) continue;
-                const int r = latest[W.c_a[q]];
+                const int a = W.c_a[q];
+                int r = -1;
+#pragma unroll
+                for (int x = 0; x < M - 1; ++x) r = x == a ? latest[x] : r;
                 if (r < 0) {   // (cannot happen with c_a < c_b: a run at state j went through c_a)
                     ok = false;
                     break;
                 }
-                const long long lhs = W.c_kind[q] == SIESTA_WNM_GAP ? e : val[e];
+                const long long lhs = W.c_kind[q] == SIESTA_WNM_GAP ? e : ve;
                 const long long rhs = (W.c_kind[q] == SIESTA_WNM_GAP ? r : val[r]) + W.c_value[q];
                 if (W.c_method[q] == SIESTA_WNM_WITHIN ? !(lhs <= rhs) : !(lhs >= rhs)) {
                     ok = false;
@@ -143,7 +147,7 @@ WNM_HD int wnm_sweep(const WnmProgram& W, const int* __restrict__ val, const int
             if (!ok) continue;
             const int f = pf + chg[e];
             prev[((size_t)(j - 1) * n_cap + e) * prev_stride] = (PrevT)pi;
-            if (j == m - 1) {
+            if (j == M - 1) {
                 if (f <= best_f) {
                     best_f = f;
                     best_e = e;
@@ -159,12 +163,28 @@ WNM_HD int wnm_sweep(const WnmProgram& W, const int* __restrict__ val, const int
     }
     if (best_f == WNM_INF) return WNM_INF;
     int e = best_e;
-    for (int j = m - 1; j >= 1; --j) {
+#pragma unroll
+    for (int j = M - 1; j >= 1; --j) {
         tup[j] = e;
         e = (int)prev[((size_t)(j - 1) * n_cap + e) * prev_stride];
     }
     tup[0] = e;
     return best_f;
+}
+
+template <typename PrevT>
+WNM_HD int wnm_sweep(const WnmProgram& W, const int* __restrict__ val, const int* __restrict__ chg, const unsigned char* __restrict__ smask,
+                     int n, int s, PrevT* prev, int n_cap, int prev_stride, int* tup) {
+    switch (W.m) {
+        case 1: tup[0] = s; return chg[s];
+        case 2: return wnm_sweep_m<2>(W, val, chg, smask, n, s, prev, n_cap, prev_stride, tup);
+        case 3: return wnm_sweep_m<3>(W, val, chg, smask, n, s, prev, n_cap, prev_stride, tup);
+        case 4: return wnm_sweep_m<4>(W, val, chg, smask, n, s, prev, n_cap, prev_stride, tup);
+        case 5: return wnm_sweep_m<5>(W, val, chg, smask, n, s, prev, n_cap, prev_stride, tup);
+        case 6: return wnm_sweep_m<6>(W, val, chg, smask, n, s, prev, n_cap, prev_stride, tup);
+        case 7: return wnm_sweep_m<7>(W, val, chg, smask, n, s, prev, n_cap, prev_stride, tup);
+        default: return wnm_sweep_m<8>(W, val, chg, smask, n, s, prev, n_cap, prev_stride, tup);
+    }
 }
 
 // (cost, tuple) a better than b: less total change, then the later match = the greater reversed tuple

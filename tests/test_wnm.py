@@ -41,9 +41,9 @@ def test_reference_evaluation_known_answer():
 
 
 def random_case(rng, n_traces=12):
-    """Small traces over 4 activities with close, sometimes equal, sometimes unsorted timestamps; a pattern of 1 - 4 events
+    """Small traces over 4 activities with close, sometimes equal, sometimes unsorted timestamps; a pattern of 1 - 6 events
     (activities may repeat); constraints between any earlier and later event, except the shape the kernel rejects."""
-    m = int(rng.integers(1, 5))
+    m = int(rng.integers(1, 7))
     pattern = rng.integers(0, 3, size=m).astype(np.int32)
     cons = []
     for _ in range(int(rng.integers(0, 4))):
