@@ -531,7 +531,7 @@ def main():
             h2d = 8 * (n_e + 1) + act_bytes * e_e + ((0 if no_cols else 8 * (n_res[2] + n_res[0])) if ts_in_place else 8 * e_e)
             d2h = 8 * n_res[0] + 8 * (n_res[0] + 1) + 8 * (n_res[1] + 1) + (4 if no_cols else 4 + 4 + 4 + 8) * n_res[2]
             return {"value": e_e * world / sec, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": sec * 1e3, "bound": "pcie (host link: %.1f GB/s achieved)" % ((h2d + d2h) / sec / 1e9),
+                    "ms_per_step": sec * 1e3, "bound": "pcie (host link: %.1f GB/s of payload%s)" % ((h2d + d2h) / sec / 1e9, "; the in-place timestamp reads are 8-byte transactions over the same link" if ts_in_place and not no_cols else ""),
                     "slice": f"first {n_e} traces ({e_e} events) of each rank's shard, pinned host memory",
                     "timestamps": "read in place from the pinned host column, reported events only" if ts_in_place else "copied to the device",
                     "call": call}

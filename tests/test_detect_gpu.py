@@ -277,7 +277,8 @@ def test_evaluate_events_byte_activity_column(ctx, monkeypatch):
     cases = [([dict(kind=N_, types=[0]), dict(kind=O_, types=[1, 2], preds=[(abi.ATTR_POSITION, abi.OP_LE, 0, 10)]),
                dict(kind=X_, types=[3]), dict(kind=N_, types=[190])], 0),
              ([dict(kind=P_, types=[0]), dict(kind=S_, types=[191], preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 600)])], 0),
-             ([dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[2])], abi.F_RETURN_ALL)]
+             ([dict(kind=N_, types=[0]), dict(kind=P_, types=[1]), dict(kind=N_, types=[2])], abi.F_RETURN_ALL),
+             ([dict(kind=N_, types=[0]), dict(kind=N_, types=[1]), dict(kind=N_, types=[190])], abi.F_RETURN_ALL)]   # returnAll on K1-P
     p_off, p_act8, p_ts = (torch.from_numpy(x).pin_memory() for x in (off, act8, ts))
     for chunk in ("1000", "4099", None):
         if chunk:
