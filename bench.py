@@ -88,6 +88,64 @@ CHUNK = 1_250_000      # traces per generator chunk: 100 M / 8 GPUs = 10 chunks,
 SAMPLE_TRACES = 1_000_000   # the CPU arms (cpu_baseline, --impl reference) run the first SAMPLE_TRACES traces of the log
 
 
+def full_size_properties(log, nfa, flags, states, d_off, d_act, d_ts, device_index):
+    """Checks on EVERY occurrence of the full-size result, on the device with torch (the CPU oracle sees a sample only):
+    trace ids strictly ascending, CSR offsets consistent, positions strictly increasing inside an occurrence, every
+    reported event is the log's event at (trace, position) - activity and, on the EventTs route, a timestamp at most a
+    second below the log's (SaseEvent.getEventBoth rebuilds it from whole seconds) - and, for patterns without a Kleene state asked for the
+    first-largest occurrence, one occurrence per trace with one event per positive state, of that state's types, that
+    satisfies the state's position predicates.  Returns {name: bool}."""
+    import torch
+    dm = log.detect_device(nfa, flags=flags)
+    t = dm.tensors(device_index)
+    out = {}
+    n_tr, n_occ, n_ev = dm.n_traces, dm.n_occurrences, dm.n_events
+    tr, occ_off, ev_off, pos = t["trace_idx"], t["occ_off"], t["ev_off"], t["ev_pos"].long()
+    out["trace_ids_ascending"] = bool(n_tr < 2 or torch.all(tr[1:] > tr[:-1]).item())
+    out["offsets_consistent"] = bool(occ_off[0].item() == 0 and occ_off[-1].item() == n_occ and ev_off[0].item() == 0 and
+                                     ev_off[-1].item() == n_ev and torch.all(occ_off[1:] > occ_off[:-1]).item() and
+                                     torch.all(ev_off[1:] > ev_off[:-1]).item())
+    first = torch.zeros(n_ev, dtype=torch.bool, device=pos.device)
+    first[ev_off[:-1]] = True
+    out["positions_increase_inside_occurrences"] = bool(torch.all((pos[1:] > pos[:-1]) | first[1:]).item())
+    # the trace of every event: occurrence of the event -> trace of the occurrence
+    occ_of_ev = torch.repeat_interleave(torch.arange(n_occ, device=pos.device), ev_off[1:] - ev_off[:-1])
+    tr_of_occ = torch.repeat_interleave(tr, occ_off[1:] - occ_off[:-1])
+    at = d_off[tr_of_occ[occ_of_ev]] + pos
+    out["events_are_the_logs_events"] = bool(torch.all(pos < (d_off[tr_of_occ[occ_of_ev] + 1] - d_off[tr_of_occ[occ_of_ev]])).item() and
+                                             torch.all(t["ev_act"] == d_act[at]).item())
+    if not (flags & abi.F_EVT_POS):
+        dts = d_ts[at] - t["ev_ts_ms"]           # SaseEvent.getEventBoth: whole seconds after the first filtered event
+        out["timestamps_within_a_second_of_the_logs"] = bool(torch.all((dts >= 0) & (dts < 1000)).item())
+    positive = [s for s in states if s["kind"] != abi.STATE_NEGATIVE]
+    if not (flags & abi.F_RETURN_ALL) and all(s["kind"] in (abi.STATE_NORMAL, abi.STATE_OR, abi.STATE_NEGATIVE) for s in states):
+        k = len(positive)
+        uniform = n_occ == n_tr and n_ev == k * n_occ and bool(torch.all(ev_off == k * torch.arange(n_occ + 1, device=pos.device)).item())
+        out["one_occurrence_of_k_events_per_trace"] = uniform
+        if uniform:
+            act_m, rank_m = t["ev_act"].view(n_occ, k), t["ev_rank"].view(n_occ, k)
+            ord_of = {}
+            for i, s_ in enumerate(states):
+                if s_["kind"] != abi.STATE_NEGATIVE:
+                    ord_of[i] = len(ord_of)
+            types_ok, preds_ok = True, True
+            for i, s_ in enumerate(states):
+                if i not in ord_of:
+                    continue
+                col = act_m[:, ord_of[i]]
+                types_ok &= bool(torch.isin(col, torch.tensor(s_["types"], device=col.device, dtype=col.dtype)).all().item())
+                for (attr, op, ref, c) in s_.get("preds", []):
+                    if attr != abi.ATTR_POSITION or (flags & abi.F_EVT_POS):
+                        continue             # EventTs route: `position` is the index in the filtered list = ev_rank
+                    lhs, rhs = rank_m[:, ord_of[i]], rank_m[:, ord_of[ref]] + c
+                    preds_ok &= bool(((lhs <= rhs) if op == abi.OP_LE else (lhs >= rhs)).all().item())
+            out["events_have_their_states_types"] = types_ok
+            out["position_predicates_hold"] = preds_ok
+    out["occurrences_checked"] = int(n_occ)
+    dm.close()
+    return out
+
+
 def make_log_fast(n_traces, min_len, max_len, n_act, seed, max_gap_s, rank=0):
     """Host generator (variable-length workloads); same distribution as tests/gen.make_log, vectorised."""
     rng = np.random.default_rng([seed, rank])
@@ -328,6 +386,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-properties", action="store_true", help="skip the size-independent checks of the full result")
     ap.add_argument("--e2e-extra-flags", type=int, default=0,
                     help="experiment: OR these SIESTA_F_* bits into the e2e leg's request (16 = no event columns: ev_pos only)")
     ap.add_argument("--e2e-int32", action="store_true", help="e2e leg through the int32 activity column only (siesta_evaluate_events)")
@@ -467,6 +526,11 @@ def main():
     sec_per_step = float(t_step.item())
     value = E_total / sec_per_step
 
+    # ---- size-independent properties of the FULL result (outside the timed region; the oracle only sees the sample below)
+    properties = None
+    if world == 1 and not args.no_properties:
+        properties = full_size_properties(log, nfa, flags, wl["states"], d_off, d_act, d_ts, local_rank)
+
     # ---- parity on the sample: the first SAMPLE_TRACES traces of the log live on rank 0; at N > 1 rank LAST decodes
     # them out of the joined list it received (the exchanged bytes are what is checked), at N = 1 rank 0 re-runs them
     ns = min(SAMPLE_TRACES, T if blocks is None else blocks[0][1] - blocks[0][0]) if rank == 0 else 0
@@ -600,6 +664,8 @@ def main():
             "result": {"matching_traces_rank0": r[0], "occurrences_rank0": r[1], "events_rank0": r[2],
                        "matching_traces_all_ranks": r[6]},
         }
+        if properties is not None:
+            line["properties_full_size"] = properties
         if not args.no_cpu_baseline:
             import oracle
             t0 = time.perf_counter()
