@@ -732,6 +732,110 @@ static int evaluate_events_impl(siesta_ctx* ctx, const int64_t* trace_off, const
         ok(cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming));
         ok(cudaEventRecord(ready[k], s_prep));
     };
+    // ---- streamed result.  When every matching trace holds ONE occurrence of k events (detect_uniform_k), the request's
+    // trace count bounds every column, so the host block is laid out for the worst case before the first chunk and the
+    // columns of a chunk travel device -> host as soon as the chunk is verified - under the later chunks' host -> device
+    // copies (the link is full duplex) instead of after the last one.  Error / outlier lists get a fixed capacity; a request
+    // that outgrows it, or a block above 1 GB, is assembled at the end as before.
+    struct Streamed {
+        bool on = false;
+        char* base = nullptr;
+        siesta_matches* m = nullptr;
+        cudaStream_t s = nullptr;
+        std::vector<cudaEvent_t> done;
+        int64_t a_tr = 0, a_occ = 0, a_ev = 0, a_err = 0, a_unsup = 0, n_emit = 0;
+        bool counted = true;
+        double k_ms = 0, d_ms = 0;
+    } S;
+    constexpr int64_t LIST_CAP = 65536;
+    const bool all_cols = !(flags & SIESTA_F_NO_EVENT_COLUMNS);
+    {
+        const int uk = detect_uniform_k(nfa, flags);
+        if (uk > 0 && n_chunks > 1 && std::getenv("SIESTA_NO_STREAMED_RESULT") == nullptr) {
+            const size_t cap_tr = (size_t)n_traces, cap_ev = (size_t)n_traces * (size_t)uk;
+            size_t off = sizeof(ResultHeader) + align64(sizeof(siesta_matches));
+            const size_t o_trace = off; off += align64(cap_tr * 8);
+            const size_t o_occ = off;   off += align64((cap_tr + 1) * 8);
+            const size_t o_evoff = off; off += align64((cap_tr + 1) * 8);
+            const size_t o_pos = off;   off += align64(cap_ev * 4);
+            const size_t o_err = off;   off += align64((size_t)LIST_CAP * 8);
+            const size_t o_unsup = off; off += align64((size_t)LIST_CAP * 8);
+            size_t o_rank = 0, o_act = 0, o_ts = 0;
+            if (all_cols) {
+                o_rank = off; off += align64(cap_ev * 4);
+                o_act = off;  off += align64(cap_ev * 4);
+                o_ts = off;   off += align64(cap_ev * 8);
+            }
+            if (off <= ((size_t)1 << 30) && cudaStreamCreateWithFlags(&S.s, cudaStreamNonBlocking) == cudaSuccess) {
+                S.base = (char*)arena_alloc(c, off);
+                if (S.base) {
+                    ResultHeader* h = reinterpret_cast<ResultHeader*>(S.base);
+                    h->magic = RESULT_MAGIC;
+                    h->ctx = c;
+                    h->base = S.base;
+                    siesta_matches* m = reinterpret_cast<siesta_matches*>(S.base + sizeof(ResultHeader));
+                    std::memset(m, 0, sizeof(*m));
+                    m->trace_idx = reinterpret_cast<int64_t*>(S.base + o_trace);
+                    m->occ_off = reinterpret_cast<int64_t*>(S.base + o_occ);
+                    m->ev_off = reinterpret_cast<int64_t*>(S.base + o_evoff);
+                    m->ev_pos = reinterpret_cast<int32_t*>(S.base + o_pos);
+                    m->err_trace_idx = reinterpret_cast<int64_t*>(S.base + o_err);
+                    m->unsupported_trace_idx = reinterpret_cast<int64_t*>(S.base + o_unsup);
+                    if (all_cols) {
+                        m->ev_rank = reinterpret_cast<int32_t*>(S.base + o_rank);
+                        m->ev_act = reinterpret_cast<int32_t*>(S.base + o_act);
+                        m->ev_ts_ms = reinterpret_cast<int64_t*>(S.base + o_ts);
+                    }
+                    m->occ_off[0] = 0;
+                    m->ev_off[0] = 0;
+                    S.m = m;
+                    S.on = true;
+                }
+            }
+            cudaGetLastError();
+        }
+    }
+    auto stream_part = [&](const siesta_dev_matches& p) {   // the chunk's columns -> their final place in the host block
+        if (!S.on) return;
+        if (S.a_err + p.n_ref_errors > LIST_CAP || S.a_unsup + p.n_unsupported > LIST_CAP || S.a_tr + p.n_traces > n_traces) {
+            S.on = false;   // (outgrew the fixed lists: assembled at the end)
+            return;
+        }
+        cudaEvent_t ev = nullptr;
+        cudaError_t x = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (x == cudaSuccess) x = cudaEventRecord(ev, s_run);          // the placement of this chunk is the last thing on s_run
+        if (x == cudaSuccess) x = cudaStreamWaitEvent(S.s, ev, 0);
+        if (ev) S.done.push_back(ev);
+        siesta_matches* m = S.m;
+        auto d2h = [&](void* dst, const void* src, size_t bytes) {
+            if (bytes && src && x == cudaSuccess) x = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, S.s);
+        };
+        d2h(m->trace_idx + S.a_tr, p.d_trace_idx, (size_t)p.n_traces * 8);
+        d2h(m->occ_off + S.a_tr, p.d_occ_off, (size_t)(p.n_traces + 1) * 8);     // the tail entry is overwritten by the next part
+        d2h(m->ev_off + S.a_occ, p.d_ev_off, (size_t)(p.n_occurrences + 1) * 8);
+        d2h(m->ev_pos + S.a_ev, p.d_ev_pos, (size_t)p.n_events * 4);
+        d2h(m->err_trace_idx + S.a_err, p.d_err_trace_idx, (size_t)p.n_ref_errors * 8);
+        d2h(m->unsupported_trace_idx + S.a_unsup, p.d_unsupported_trace_idx, (size_t)p.n_unsupported * 8);
+        if (all_cols) {
+            d2h(m->ev_rank + S.a_ev, p.d_ev_rank, (size_t)p.n_events * 4);
+            d2h(m->ev_act + S.a_ev, p.d_ev_act, (size_t)p.n_events * 4);
+            d2h(m->ev_ts_ms + S.a_ev, p.d_ev_ts_ms, (size_t)p.n_events * 8);
+        }
+        if (x != cudaSuccess) {
+            cudaGetLastError();
+            S.on = false;
+            return;
+        }
+        S.a_tr += p.n_traces;
+        S.a_occ += p.n_occurrences;
+        S.a_ev += p.n_events;
+        S.a_err += p.n_ref_errors;
+        S.a_unsup += p.n_unsupported;
+        if (p.n_matches_emitted < 0) S.counted = false;
+        else S.n_emit += p.n_matches_emitted;
+        S.k_ms += p.kernel_ms;
+        S.d_ms += p.detect_ms;
+    };
     RebaseOffsets base{0, 0, 0};
     bool ids_valid = true;
     for (int k = 0; k < n_chunks && e == cudaSuccess && rc == SIESTA_OK; ++k) {
@@ -760,6 +864,7 @@ static int evaluate_events_impl(siesta_ctx* ctx, const int64_t* trace_off, const
         rc = detect_device_impl(&view, nfa, nullptr, 0, flags, s_run, base, &dm);
         if (rc) break;
         parts.push_back(dm);
+        stream_part(dm);
         base.occ += dm.n_occurrences;
         base.ev += dm.n_events;
     }
@@ -767,7 +872,34 @@ static int evaluate_events_impl(siesta_ctx* ctx, const int64_t* trace_off, const
         set_error(std::string("siesta_evaluate_events: ") + cudaGetErrorString(e));
         rc = SIESTA_E_CUDA;
     }
-    if (rc == SIESTA_OK) rc = assemble_matches(c, parts, flags, s_run, out, nullptr);
+    if (S.s) {
+        if (cudaStreamSynchronize(S.s) != cudaSuccess) {
+            cudaGetLastError();
+            S.on = false;
+        }
+        for (cudaEvent_t ev : S.done) cudaEventDestroy(ev);
+        cudaStreamDestroy(S.s);
+    }
+    if (rc == SIESTA_OK && S.on && S.a_tr == base.occ) {   // (one occurrence per matching trace: the two counts agree)
+        siesta_matches* m = S.m;
+        m->n_traces = S.a_tr;
+        m->n_occurrences = S.a_occ;
+        m->n_events = S.a_ev;
+        m->n_ref_errors = S.a_err;
+        m->n_unsupported = S.a_unsup;
+        m->n_matches_emitted = S.counted ? S.n_emit : -1;
+        m->kernel_ms = S.k_ms;
+        m->detect_ms = S.d_ms;
+        m->occ_off[S.a_tr] = S.a_occ;
+        m->ev_off[S.a_occ] = S.a_ev;
+        *out = m;
+    } else {
+        if (S.base) {   // not streamed after all: the block goes back, the parts are assembled as a whole
+            reinterpret_cast<ResultHeader*>(S.base)->magic = 0;
+            arena_free(c, S.base);
+        }
+        if (rc == SIESTA_OK) rc = assemble_matches(c, parts, flags, s_run, out, nullptr);
+    }
     for (siesta_dev_matches& p : parts) siesta_dev_matches_free(&p);
     cudaStreamSynchronize(s_copy);
     cudaStreamSynchronize(s_prep);
