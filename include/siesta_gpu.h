@@ -535,9 +535,8 @@ int siesta_explore_accurate(siesta_log* log, const int32_t* pattern_activities, 
  *    from one start, S/engine/Run.java:319-327, 332-355);
  *  - gap constraints count positions of the uncertain stream; `timestamp > $previous.timestamp` is only asked at a
  *    state a time constraint ends at.
- * Not supported (SIESTA_E_UNSUPPORTED): a constraint with posA >= 1 between two states of the same activity (the
- * result then depends on the order of the run list inside one event).  Traces whose uncertain stream exceeds
- * SIESTA_WNM_MAX_STREAM events are listed in unsupported_trace_idx, every other trace is answered. */
+ * Traces whose uncertain stream exceeds SIESTA_WNM_MAX_STREAM events are listed in unsupported_trace_idx, every
+ * other trace is answered. */
 #define SIESTA_WNM_GAP 0
 #define SIESTA_WNM_TIME 1
 #define SIESTA_WNM_WITHIN 0

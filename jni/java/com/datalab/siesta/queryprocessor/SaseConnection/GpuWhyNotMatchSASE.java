@@ -31,7 +31,7 @@ import java.util.Map;
  *
  * The reference's engine turns every combination of uncertain events into a run object; the library computes the match it
  * would report (least total change, the last such match in emission order) with one sweep per start event (csrc/wnm.cuh).
- * Traces whose uncertain stream exceeds the library's bound and constraint shapes it does not cover go to super.evaluate.
+ * Traces whose uncertain stream exceeds the library's bound go to super.evaluate.
  *
  * NOT compiled in the repository this file ships in (no JDK in its image); the native half is compiled there.
  */
@@ -44,10 +44,9 @@ public class GpuWhyNotMatchSASE extends WhyNotMatchSASE {
 
     @Override
     public List<AlmostMatch> evaluate(SimplePattern sp, Map<String, List<Event>> restEvents, int uncertaintyPerEvent, int step, int k) {
-        // a constraint between two later events of the same activity depends on the engine's run-list order: reference engine
+        // constraints the library does not take (they do not name an earlier and a later event of the pattern): reference engine
         for (Constraint c : sp.getConstraints())
-            if (c.getPosA() >= 1 && c.getPosA() < c.getPosB() && c.getPosB() < sp.getEvents().size()
-                    && sp.getEvents().get(c.getPosA()).getName().equalsIgnoreCase(sp.getEvents().get(c.getPosB()).getName()))
+            if (c.getPosA() < 0 || c.getPosA() >= c.getPosB() || c.getPosB() >= sp.getEvents().size())
                 return super.evaluate(sp, restEvents, uncertaintyPerEvent, step, k);
         Map<String, Integer> actIds = new HashMap<>();
         List<String> names = new ArrayList<>();

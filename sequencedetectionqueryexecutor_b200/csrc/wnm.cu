@@ -213,11 +213,6 @@ int wnm_build(const int32_t* pattern, int32_t m, const siesta_wnm_constraint* co
             set_error("siesta_why_not_match: a constraint must name an earlier and a later event of the pattern and a value >= 0");
             return SIESTA_E_INVALID;
         }
-        if (c.pos_a >= 1 && pattern[c.pos_a] == pattern[c.pos_b]) {
-            set_error("siesta_why_not_match: a constraint between two events of the same activity (other than the first) depends on "
-                      "the engine's run-list order inside one event; not covered");
-            return SIESTA_E_UNSUPPORTED;
-        }
         W->c_a[q] = c.pos_a;
         W->c_b[q] = c.pos_b;
         W->c_kind[q] = c.kind;

@@ -29,8 +29,10 @@
 //    the run only through "some run at state j - 1 whose last event lies before e (and strictly earlier in time, if a time
 //    constraint ends at j)".  One forward sweep per start keeps, per state, the latest taken event and the least cost of a
 //    partial run ending before e (ties to the later event: the greater reversed tuple), plus a back pointer per taken event.
-//  * not covered: a constraint (A >= 1, B) between two states of the same activity - the family's value vector may then be
-//    overwritten by the very event that is being evaluated, depending on run-list order (the host rejects the request).
+//  * a constraint (A >= 1, B) between two states of the SAME activity: the event e that a run at state B is offered may be
+//    taken at state A in the same step, and the family's slot then holds e itself when the run at B is evaluated - always,
+//    because the earliest run at state A takes whatever any run at A takes and was created before every run at a later
+//    state, so it sits earlier in the run list.  The sweep decides the states of an event in ascending order for that.
 #pragma once
 #include <cstdint>
 
@@ -120,8 +122,16 @@ WNM_HD int wnm_sweep_m(const WnmProgram& W, const int* __restrict__ val, const i
         }
         const unsigned sm = smask[e] >> 1;
         if (!sm) continue;
+        // Pass 1, states ascending: which states take e.  A run is offered e once, at its own state, and the partial runs it
+        // extends are those that existed before e (all_* / old_* are only updated in pass 2).  A constraint (A, j) reads the
+        // family's slot of state A as it is when the run at state j is evaluated: if e itself is taken at state A (same
+        // activity at both states), the run that takes it - the earliest run at state A takes whatever any run at A takes, and
+        // it was created before every run at state j > A - sits earlier in the run list, so the slot already holds e.
+        unsigned acc = 0;
+        int fj[M];
 #pragma unroll
-        for (int j = M - 1; j >= 1; --j) {   // high to low: a run that took e at state j - 1 is not offered e again
+        for (int j = 1; j < M; ++j) {
+            fj[j] = WNM_INF;
             if (!((sm >> (j - 1)) & 1u)) continue;
             const int pf = W.time_at[j] ? old_f[j - 1] : all_f[j - 1];
             const int pi = W.time_at[j] ? old_i[j - 1] : all_i[j - 1];
@@ -133,6 +143,7 @@ WNM_HD int wnm_sweep_m(const WnmProgram& W, const int* __restrict__ val, const i
                 int r = -1;
 #pragma unroll
                 for (int x = 0; x < M - 1; ++x) r = x == a ? latest[x] : r;
+                if ((acc >> a) & 1u) r = e;
                 if (r < 0) {   // (cannot happen with c_a < c_b: a run at state j went through c_a)
                     ok = false;
                     break;
@@ -145,8 +156,15 @@ WNM_HD int wnm_sweep_m(const WnmProgram& W, const int* __restrict__ val, const i
                 }
             }
             if (!ok) continue;
-            const int f = pf + chg[e];
+            acc |= 1u << j;
+            fj[j] = pf + chg[e];
             prev[((size_t)(j - 1) * n_cap + e) * prev_stride] = (PrevT)pi;
+        }
+        // Pass 2: the taken states' bookkeeping
+#pragma unroll
+        for (int j = 1; j < M; ++j) {
+            if (!((acc >> j) & 1u)) continue;
+            const int f = fj[j];
             if (j == M - 1) {
                 if (f <= best_f) {
                     best_f = f;
