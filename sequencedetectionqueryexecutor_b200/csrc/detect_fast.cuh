@@ -46,8 +46,8 @@
 //   created in Z(0)'s slot, which was placed at a_{m-1}; at a_q, q >= 1, Z(0) is re-appended before P(q) is created,
 //   at a_0 P(0) is appended first.
 //
-// Class NP1 — normal / or states and exactly ONE kleeneClosure+ state (index k; k = 0 needs a second state), no predicate
-//             on any state (SIESTA's pattern without constraints, or any pattern under onlyAppearances:
+// Class NP1 — normal / or states and exactly ONE kleeneClosure+ state (index k; k = 0 needs a second state; kleeneClosure*:
+//             see the end of this block), no predicate on any state (SIESTA's pattern without constraints, or any pattern under onlyAppearances:
 //             ComplexPattern.getNfaWithoutConstraints :253-283), e.g. `a b+ c`.  returnAll only on the EventPos route.
 //   Without predicates there is no value vector, so runs do not interact; only their list order matters, for ties.
 //   k >= 1: the run started at an event of state 0's types walks the prefix greedily (first later event of each state's
@@ -82,6 +82,25 @@
 //   or before its last (suffix completion is monotone in the position it starts from), so on the EventPos route, where
 //   Occurrence.overlaps compares positions, every other match overlaps it: the selection is the largest alone.  On the
 //   EventTs route overlaps compares timestamps, which the caller may hand over unsorted: not taken.
+//   kleeneClosure* instead of kleeneClosure+ (one type, NO predicate anywhere; the shapes of the reference's own tests: `a b* e`,
+//   `a* b`, `a* b e`, `a b*`, `a b a*`, `(a|b) b* e`, EvaluateComplexQueries.java:101-103, 126-127, 150-152, 175-176, 199-201,
+//   298-301).  A run at the state takes events exactly as above (Engine.checkPredicate :1102-1163 rejects every event of another
+//   type for both kinds); what differs is how a run gets PAST the state without a Kleene event:
+//   k = 1: the start run is created at state 1 by Engine.createNewRun (no proceed block there).  When it is offered its first
+//     event b_1 of the Kleene type, the block at Engine.java:658-670 (kleeneClosure*, not initialised) appends a clone that
+//     skipped the state; the clone walks the suffix from behind b_1: one more match per start, (i, 0) = prefix_i +
+//     suffix(b_1), iff b_1 lies in F, i.e. iff (i, 1) exists.  It is smaller than (i, 1): the selection is the `+` one.  A trace
+//     without any event of the Kleene type after the prefix has NO match (`a e` does not match `a b* e`).
+//   k >= 2: the run enters the state inside evaluateEventForSkipTillNext, and the proceed block behind addEvent (:691-713) fires
+//     at once (Engine.checkProceed :1205-1224 only holds back an untouched kleeneClosure+ state): the run itself moves on from
+//     its prefix end p_i (k last: it is a match at once), the clone stays, initialised, and takes the b's as above.  One more
+//     match per start, (i, 0) = prefix_i + suffix(p_i), iff p_i lies in F - with or without Kleene events.  If the first
+//     start has none the suffix allows, every match has S - 1 events and the first emitted wins: completion is monotone in the
+//     start and the first start's run sits first in the list: (0, 0).
+//   k = 0: createNewRun :960-982 starts a run at state 1 for an event that is of state 1's types and not of the Kleene type (state 0
+//     counts as passed); those runs never fork and emit S - 1 events, fewer than any match that holds an a.  They are
+//     selected only when no a lies in F; the first of them (the earliest embedding of states 1 .. S-1) is then the first emitted.
+//   returnAll: (i, 0) of k >= 2 and the runs started at state 1 may lie outside the largest match: only k = 1 is taken.
 #pragma once
 #include "detect_engine.cuh"
 
@@ -332,20 +351,31 @@ SIESTA_HD __forceinline__ bool np1_eval(const DevNfa& nfa, const typename MaskOp
     const int S = nfa.n_states;
     n_emitted = 0;
     int k = 0;
+    bool star = false;
 #pragma unroll
     for (int s = 0; s < SIESTA_MAX_STATES; ++s) {
         if (s >= S) break;
-        if (T[s] == 0) return false;
-        if (nfa.kind[s] == SIESTA_STATE_KLEENE_PLUS) k = s;
+        if (nfa.kind[s] == SIESTA_STATE_KLEENE_PLUS || nfa.kind[s] == SIESTA_STATE_KLEENE_STAR) {
+            k = s;
+            star = nfa.kind[s] == SIESTA_STATE_KLEENE_STAR;
+        }
+    }
+    const bool star0 = star && k == 0;   // `a* b ..`: an event of state 1's types starts a run without any a
+    const bool star2 = star && k >= 2;   // the run is cloned past the state the moment it enters it: matches without any b
+#pragma unroll
+    for (int s = 0; s < SIESTA_MAX_STATES; ++s) {
+        if (s >= S) break;
+        if (T[s] == 0 && !(star0 && s == 0) && !(star2 && s == k)) return false;
     }
     // F: positions from which the suffix completes (backward greedy: the latest embedding of states S-1 .. k+1)
-    mask_t F = ~(mask_t)0;
+    mask_t F = ~(mask_t)0, F2 = ~(mask_t)0;   // F2: the same for states S-1 .. 2
 #pragma unroll
     for (int s = SIESTA_MAX_STATES - 1; s >= 1; --s) {
         if (s >= S || s <= k) continue;
         const mask_t c = T[s] & F;
         if (!c) return false;
         F = MO::below(MO::hi(c));
+        if (s == 2) F2 = F;
     }
     // prefix walk of the run started at event p; returns the mask of its events (0: does not complete) and its end in p
     auto prefix = [&](int& p) -> mask_t {
@@ -366,20 +396,60 @@ SIESTA_HD __forceinline__ bool np1_eval(const DevNfa& nfa, const typename MaskOp
         taken = 0;
         if (count)
             for (mask_t r = B; r; r &= r - 1) n_emitted += (unsigned)MO::popc(T[0] & MO::below(MO::lo(r))) + 1u;   // starts at or before a_l
+        if (star0) {
+            // Engine.createNewRun :960-982: an event that cannot start state 0 but is of state 1's types starts a run at
+            // state 1 (state 0 counts as passed).  Those runs never fork; each emits S - 1 events, fewer than any match
+            // that holds an a, so they matter for the selection only when no a lies in F: the first of them then completes
+            // first (walks are monotone) and is the first emitted.
+            const mask_t bs = T[1] & ~T[0] & F2;
+            if (count) n_emitted += (unsigned)MO::popc(bs);
+            if (!B) {
+                if (!bs) return false;
+                int q = MO::lo(bs);
+                taken = MO::bit(q);
+#pragma unroll
+                for (int s = 2; s < SIESTA_MAX_STATES; ++s) {
+                    if (s >= S) break;
+                    q = MO::lo(T[s] & MO::above(q));   // exists: q lies in F2
+                    taken |= MO::bit(q);
+                }
+                out = taken;
+                return true;
+            }
+        }
     } else {
         int p = MO::lo(T[0]);
         taken = prefix(p);
         if (!taken) return false;
         B = T[k] & MO::above(p) & F;
+        // kleeneClosure*, one more match per start, the prefix and the suffix alone.  k = 1: the start run (created by
+        // Engine.createNewRun at state 1) is cloned past the state when it is offered its first event of the Kleene type
+        // (Engine.java:658-670): the suffix starts behind that event.  k >= 2: the run enters the state inside
+        // evaluateEventForSkipTillNext, whose proceed block (:691-713) fires at once (a kleeneClosure* state counts as
+        // initialised): the run itself moves on from its prefix end, the clone stays and takes the b's.
+        const bool skip0 = star2 && ((F >> p) & 1);
         if (count) {
-            n_emitted = (unsigned)MO::popc(B);
+            n_emitted = (unsigned)MO::popc(B) + ((star && k == 1 && B) || skip0 ? 1u : 0u);
             for (mask_t r = T[0] & (T[0] - 1); r; r &= r - 1) {
                 int q = MO::lo(r);
                 if (!prefix(q)) break;                       // later starts do not complete their prefix either
                 const unsigned n = (unsigned)MO::popc(T[k] & MO::above(q) & F);
-                if (!n) break;
-                n_emitted += n;
+                const unsigned extra = (star && k == 1 && n) || (star2 && ((F >> q) & 1)) ? 1u : 0u;
+                if (!n && !extra) break;
+                n_emitted += n + extra;
             }
+        }
+        if (!B && skip0) {   // no b the suffix allows: the first start's own run is the first match of the least size
+            int q = p;
+#pragma unroll
+            for (int s = 1; s < SIESTA_MAX_STATES; ++s) {
+                if (s >= S) break;
+                if (s <= k) continue;
+                q = MO::lo(T[s] & MO::above(q));   // exists: p lies in F
+                taken |= MO::bit(q);
+            }
+            out = taken;
+            return true;
         }
     }
     if (!B) return false;

@@ -8,7 +8,7 @@
 namespace siesta {
 
 // Which closed-form evaluator (detect_fast.cuh) may replace the run-list engine for this NFA and these flags?
-// 0 = none, 1 = NK (no Kleene state), 2 = FK2 (`a+ b*`), 3 = NP1 (one `+` state, no predicates).  The conditions are exactly the ones the derivations in
+// 0 = none, 1 = NK (no Kleene state), 2 = FK2 (`a+ b*`), 3 = NP1 (one `+` or `*` state).  The conditions are exactly the ones the derivations in
 // detect_fast.cuh rely on; anything else keeps the general engine.
 static int classify_fast(const siesta_nfa* nfa, const DevNfa& d, uint32_t flags) {
     if (flags & SIESTA_F_LITERAL_RUNS) return 0;
@@ -32,14 +32,20 @@ static int classify_fast(const siesta_nfa* nfa, const DevNfa& d, uint32_t flags)
             if (d.p_ref[1][k] != 0) return 0;
         return 2;
     }
-    {   // NP1: positive states and exactly one kleeneClosure+ state; predicates (after onlyAppearances) only reference
-        // states before the Kleene state
-        int n_plus = 0, k = 0;
+    {   // NP1: positive states and exactly one Kleene state.  kleeneClosure+: predicates (after onlyAppearances) only
+        // reference states before the Kleene state.  kleeneClosure* (one type): no predicate at all; `a* b ..` has
+        // matches that start at a b, `a b c* d` matches without any c: they may lie outside the largest one, so returnAll
+        // keeps the engine unless the state is the second one.
+        int n_kleene = 0, k = 0;
         for (int s = 0; s < S; ++s) {
-            if (nfa->states[s].kind == SIESTA_STATE_KLEENE_PLUS) { ++n_plus; k = s; }
+            if (nfa->states[s].kind == SIESTA_STATE_KLEENE_PLUS || nfa->states[s].kind == SIESTA_STATE_KLEENE_STAR) { ++n_kleene; k = s; }
             else if (!positive(s)) return 0;
         }
-        if (n_plus != 1 || S < 2 || d.n_preds[0] != 0) return 0;
+        if (n_kleene != 1 || S < 2 || d.n_preds[0] != 0) return 0;
+        if (nfa->states[k].kind == SIESTA_STATE_KLEENE_STAR) {
+            if (d.need_vv || nfa->states[k].n_types != 1 || (flags & SIESTA_F_MODE_HEAD)) return 0;
+            if (k != 1 && (flags & SIESTA_F_RETURN_ALL)) return 0;
+        }
         for (int s = 0; s < S; ++s)
             for (int q = 0; q < d.n_preds[s]; ++q)
                 if (d.p_ref[s][q] >= k) return 0;

@@ -62,19 +62,20 @@ def fk2_nfa(rng, n_act):
 
 
 def np1_nfa(rng, n_act):
-    """normal / or states and exactly one kleeneClosure+ state anywhere, no predicates; types may repeat."""
+    """normal / or states and exactly one kleeneClosure+ (or kleeneClosure*) state anywhere; types may repeat."""
     n = int(rng.integers(2, 7))
     k = int(rng.integers(0, n))
+    star = rng.random() < 0.4   # kleeneClosure* instead: in the class without any predicate
     states = []
     for s in range(n):
         if s == k:
-            kind = P_
+            kind = S_ if star else P_
         else:
             kind = O_ if rng.random() < 0.3 else N_
         m = int(rng.integers(2, 4)) if kind == O_ else 1
         types = [int(x) for x in rng.choice(n_act, size=min(m, n_act), replace=False)]
         states.append({"kind": kind, "types": types, "preds": []})
-    if k >= 1 and rng.random() < 0.6:   # constraints that reference states before the Kleene state
+    if k >= 1 and not star and rng.random() < 0.6:   # constraints that reference states before the Kleene state
         for _ in range(int(rng.integers(1, 4))):
             b = int(rng.integers(1, n))
             if len(states[b]["preds"]) < abi.MAX_PREDS:

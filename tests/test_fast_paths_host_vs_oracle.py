@@ -60,7 +60,7 @@ def test_class_boundaries_fall_back_to_the_engine():
 
 
 def test_np1_is_the_first_start_with_every_kleene_event_the_suffix_allows():
-    """Class NP1 (one `+` state, no predicates): the first-largest occurrence and the engine's match count against the
+    """Class NP1 (one `+` or `*` state, no predicates): the first-largest occurrence and the engine's match count against the
     oracle's FULL emission list on dense two- and three-letter streams (ties between starts, Kleene type repeated in
     the prefix / suffix, Kleene state first / in the middle / last)."""
     shapes = [
@@ -70,6 +70,16 @@ def test_np1_is_the_first_start_with_every_kleene_event_the_suffix_allows():
         [dict(kind=P_, types=[0]), dict(kind=N_, types=[0]), dict(kind=N_, types=[1])],            # a+ a b
         [dict(kind=N_, types=[1]), dict(kind=P_, types=[1]), dict(kind=N_, types=[1])],            # b b+ b
         [dict(kind=N_, types=[0]), dict(kind=N_, types=[1]), dict(kind=P_, types=[0]), dict(kind=O_, types=[1, 2]), dict(kind=N_, types=[0])],
+        # kleeneClosure*: the extra matches (a run cloned past the state, a run started at state 1) count and may be the result
+        [dict(kind=N_, types=[0]), dict(kind=S_, types=[1]), dict(kind=N_, types=[2])],            # a b* c
+        [dict(kind=N_, types=[0]), dict(kind=S_, types=[1])],                                      # a b*
+        [dict(kind=S_, types=[0]), dict(kind=N_, types=[1])],                                      # a* b
+        [dict(kind=S_, types=[0]), dict(kind=N_, types=[1]), dict(kind=N_, types=[2])],            # a* b c
+        [dict(kind=N_, types=[0]), dict(kind=N_, types=[1]), dict(kind=S_, types=[0])],            # a b a*
+        [dict(kind=N_, types=[0]), dict(kind=N_, types=[1]), dict(kind=S_, types=[2]), dict(kind=N_, types=[0])],   # a b c* a
+        [dict(kind=O_, types=[0, 1]), dict(kind=S_, types=[1]), dict(kind=N_, types=[2])],         # (a|b) b* c
+        [dict(kind=S_, types=[0]), dict(kind=N_, types=[0]), dict(kind=N_, types=[1])],            # a* a b
+        [dict(kind=N_, types=[1]), dict(kind=S_, types=[1]), dict(kind=N_, types=[1])],            # b b* b
     ]
     rng = np.random.default_rng(23)
     for states in shapes:
