@@ -70,6 +70,12 @@ WORKLOADS = {
                                             states=[dict(kind=abi.STATE_NORMAL, types=[0]), dict(kind=abi.STATE_KLEENE_PLUS, types=[1]),
                                                     dict(kind=abi.STATE_NORMAL, types=[2], preds=[(abi.ATTR_POSITION, abi.OP_LE, 0, 20)])],
                                             e2e_traces=1_000_000),
+    # the reference's own Kleene test shape (EvaluateComplexQueries.java:101-103): one `*` state, no constraints
+    "detection_abstar_c_1Mx100": dict(n_traces=1_000_000, min_len=100, max_len=100, n_act=20, max_gap_s=120, seed=0x51E57A02,
+                                      bytes_per_event=4, pattern="a b* c (EventTs route, returnAll=false)",
+                                      kernel="detect_kernel<W=1, FAST_NP1> (K1: filter + one-Kleene-state closed form + staged output)",
+                                      states=[dict(kind=abi.STATE_NORMAL, types=[0]), dict(kind=abi.STATE_KLEENE_STAR, types=[1]),
+                                              dict(kind=abi.STATE_NORMAL, types=[2])], e2e_traces=1_000_000),
     "detection_kleene_all_1Mx100": dict(n_traces=1_000_000, min_len=100, max_len=100, n_act=20, max_gap_s=120, seed=0x51E57A02,
                                         bytes_per_event=12, pattern="a+ b* within 10 minutes, returnAll=true",
                                         kernel="detect_kernel<FAST_NONE> (K1: filter + run-list engine)", flags=abi.F_RETURN_ALL,
