@@ -28,8 +28,28 @@ def _to_result(dm, device=0):
     return r
 
 
+def _retry_stalled(run_once):
+    """Several ranks on ONE device is a configuration only these tests use: every rank's kernels spin on flags that the other
+    ranks' kernels set, so the driver must keep all their streams moving at once.  When it serialises two of them (streams that
+    share a hardware queue, see tests/conftest.py) the collective ends by its own time limit on every rank.  That says nothing
+    about the exchange itself - ranks on their own GPUs (tests/exchange_worker.py, bench.py --gpus N) cannot get there - so such a
+    stall (and nothing else) is retried on fresh exchange objects, and reported."""
+    import warnings
+    for attempt in range(3):
+        res, err = run_once()
+        stalled = [e for e in err if e is not None and "did not arrive within the time limit" in str(e)]
+        if not stalled or attempt == 2:
+            assert not any(err), err
+            return res
+        warnings.warn(f"ranks sharing one device stalled (attempt {attempt + 1}): {stalled[0]}; retrying on fresh exchange objects")
+
+
 def _run_sharded(ctx, off, act, ts, n_act, nfa, flags, bounds):
-    """bounds: trace indices [b0=0, b1, ..., T]; returns the joined result as every rank sees it."""
+    return _retry_stalled(lambda: _run_sharded_once(ctx, off, act, ts, n_act, nfa, flags, bounds))
+
+
+def _run_sharded_once(ctx, off, act, ts, n_act, nfa, flags, bounds):
+    """bounds: trace indices [b0=0, b1, ..., T]; returns the joined result as every rank sees it (+ the ranks' errors)."""
     from sequencedetectionqueryexecutor_b200 import api
     world = len(bounds) - 1
     logs = []
@@ -61,18 +81,24 @@ def _run_sharded(ctx, off, act, ts, n_act, nfa, flags, bounds):
         t.start()
     for t in th:
         t.join()
-    assert not any(err), err
-    res = [(_to_result(dm), st) for dm, st in out]
-    for dm, _ in out:
-        dm.close()
+    res = None
+    if not any(err):
+        res = [(_to_result(dm), st) for dm, st in out]
+    for o in out:
+        if o is not None:
+            o[0].close()
     for x in xs:
         x.close()
     for lg in logs:
         lg.close()
-    return res
+    return res, err
 
 
 def _run_blocked(ctx, off, act, ts, n_act, nfa, flags, world, bounds, rounds=2):
+    return _retry_stalled(lambda: _run_blocked_once(ctx, off, act, ts, n_act, nfa, flags, world, bounds, rounds))
+
+
+def _run_blocked_once(ctx, off, act, ts, n_act, nfa, flags, world, bounds, rounds=2):
     """Block-cyclic shards: bounds = global trace boundaries of C * world blocks; rank r holds blocks r, world + r, ...
     (siesta_log_set_blocks).  Returns every rank's joined result (+ stats)."""
     from sequencedetectionqueryexecutor_b200 import api
@@ -127,8 +153,7 @@ def _run_blocked(ctx, off, act, ts, n_act, nfa, flags, world, bounds, rounds=2):
         x.close()
     for lg in logs:
         lg.close()
-    assert not any(err), err
-    return res
+    return res, err
 
 
 CASES = [
