@@ -22,6 +22,16 @@ def lib():
     return _lib
 
 
+FAST_NONE, FAST_NK, FAST_FK2, FAST_NP1 = 0, 1, 2, 3   # detect_fast.cuh
+
+
+def fast_class(nfa, flags=0):
+    """The evaluator the product's validate_nfa picks for this NFA and these flags (FAST_*), or the negative error code."""
+    L = lib()
+    L.engine_host_fast_class.restype = C.c_int
+    return int(L.engine_host_fast_class(C.byref(nfa), C.c_uint32(flags)))
+
+
 def _p(a, ct):
     return a.ctypes.data_as(C.POINTER(ct))
 

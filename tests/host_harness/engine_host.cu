@@ -93,6 +93,13 @@ static int run_one(const DevNfa& dn, const std::vector<uint32_t>& meta, const st
 
 extern "C" const char* engine_host_last_error() { return siesta::t_err.c_str(); }
 
+// which evaluator validate_nfa (csrc/nfa.cpp, the product's own host code) picks: FAST_* of detect_fast.cuh, or < 0 = the error
+extern "C" int engine_host_fast_class(const siesta_nfa* nfa, uint32_t flags) {
+    DevNfa dn;
+    const int rc = validate_nfa(nfa, flags, &dn);
+    return rc ? (rc < 0 ? rc : -rc) : (int)dn.fast_class;
+}
+
 extern "C" int engine_host_detect(const int64_t* trace_off, const int32_t* act, const int64_t* ts_ms, int64_t n_traces,
                                   int32_t n_act, const siesta_nfa* nfa, const int64_t* cand, int64_t n_cand, uint32_t flags,
                                   int64_t* n_wide, siesta_matches** out) {

@@ -125,3 +125,39 @@ def test_np1_constraints_on_prefix_states_and_the_run_list_order(seed0):
         assert rc == 0
         ok, why = got.same_as(oracle.detect(off, act, ts, nfa, flags=flags))
         assert ok, (seed, why, states)
+
+
+def test_which_shapes_take_a_closed_form():
+    """validate_nfa's class decision (csrc/nfa.cpp, the product's host code, through the harness): the reference's own test
+    shapes (tests/kat.py: EvaluateNewQueries.java / EvaluateComplexQueries.java) and BASELINE.json's two /detection queries
+    all take a closed form; shapes the derivations do not cover keep the run-list engine."""
+    from tests.kat import KATS
+    NONE, NK, FK2, NP1 = host_engine.FAST_NONE, host_engine.FAST_NK, host_engine.FAST_FK2, host_engine.FAST_NP1
+    want = {"A,(C|D),B": NK, "A,!C,B": NK, "A,B*,E": NP1, "A*,B": NP1, "A*,B,E": NP1, "A,B*": NP1, "A,B,A*": NP1,
+            "!A,B,C": NONE, "B,C,!A": NONE,   # leading / trailing negative state
+            "A,B,C": NK, "A,E,C": NK, "A,B": NK, "(A|B),C": NK, "D,(A|B),E": NK, "A+,B,E": NP1, "A,B+,E": NP1, "A,B,A+": NP1,
+            "(A|B),B*,E": NP1, "A,(C|D),B gap within 2 (0,1)": NK, "A,!D,E gap within 2 (0,1)": NK,
+            "A,B*,E gap within 1 (0,1),(1,2)": NONE}   # constraints on and behind a `*` state
+    assert set(want) == {k["name"] for k in KATS}
+    for k in KATS:
+        assert host_engine.fast_class(abi.make_nfa(k["states"]), abi.F_EVT_POS) == want[k["name"]], k["name"]
+    gap6 = [dict(kind=N_, types=[0]), dict(kind=O_, types=[1, 2], preds=[(abi.ATTR_POSITION, abi.OP_LE, 0, 10)]),
+            dict(kind=X_, types=[3]), dict(kind=N_, types=[4]), dict(kind=N_, types=[5], preds=[(abi.ATTR_POSITION, abi.OP_GE, 3, 2)])]
+    kleene = [dict(kind=P_, types=[0]), dict(kind=S_, types=[1], preds=[(abi.ATTR_TIMESTAMP, abi.OP_LE, 0, 600)])]
+    assert host_engine.fast_class(abi.make_nfa(gap6), 0) == NK                       # BASELINE configs[4]
+    assert host_engine.fast_class(abi.make_nfa(gap6), abi.F_RETURN_ALL) == NK
+    assert host_engine.fast_class(abi.make_nfa(kleene), 0) == FK2                    # BASELINE configs[1]
+    assert host_engine.fast_class(abi.make_nfa(kleene), abi.F_RETURN_ALL) == NONE
+    star = lambda k, n: [dict(kind=S_ if s == k else N_, types=[s]) for s in range(n)]   # noqa: E731
+    for k, n in ((0, 2), (0, 3), (1, 2), (1, 3), (2, 3), (2, 4)):
+        assert host_engine.fast_class(abi.make_nfa(star(k, n)), 0) == NP1
+        assert host_engine.fast_class(abi.make_nfa(star(k, n)), abi.F_COUNT_MATCHES) == NP1
+        # returnAll: only on the EventPos route, and for `*` only as the second state (other extra matches may lie outside the largest)
+        assert host_engine.fast_class(abi.make_nfa(star(k, n)), abi.F_RETURN_ALL) == NONE
+        assert host_engine.fast_class(abi.make_nfa(star(k, n)), abi.F_RETURN_ALL | abi.F_EVT_POS) == (NP1 if k == 1 else NONE)
+    two = [dict(kind=N_, types=[0]), dict(kind=S_, types=[1]), dict(kind=P_, types=[2])]
+    assert host_engine.fast_class(abi.make_nfa(two), 0) == NONE                      # two Kleene states
+    c = [dict(kind=N_, types=[0]), dict(kind=S_, types=[1]), dict(kind=N_, types=[2], preds=[(abi.ATTR_POSITION, abi.OP_LE, 0, 5)])]
+    assert host_engine.fast_class(abi.make_nfa(c), 0) == NONE                        # a constraint next to a `*` state
+    assert host_engine.fast_class(abi.make_nfa(c), abi.F_ONLY_APPEARANCES) == NP1    # ... dropped by onlyAppearances
+    assert host_engine.fast_class(abi.make_nfa(star(1, 3)), abi.F_LITERAL_RUNS) == NONE
