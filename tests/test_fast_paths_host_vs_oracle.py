@@ -161,3 +161,16 @@ def test_which_shapes_take_a_closed_form():
     assert host_engine.fast_class(abi.make_nfa(c), 0) == NONE                        # a constraint next to a `*` state
     assert host_engine.fast_class(abi.make_nfa(c), abi.F_ONLY_APPEARANCES) == NP1    # ... dropped by onlyAppearances
     assert host_engine.fast_class(abi.make_nfa(star(1, 3)), abi.F_LITERAL_RUNS) == NONE
+
+
+def test_bench_workloads_run_on_the_kernels_their_labels_name():
+    """bench.py labels every workload with the kernel it measures (`roofline.kernel`); the label must be the evaluator the
+    library's own class decision picks for that NFA and those flags."""
+    import bench
+    label = {host_engine.FAST_NK: ("detect_nkp_kernel",), host_engine.FAST_FK2: ("FAST_FK2",), host_engine.FAST_NP1: ("FAST_NP1",),
+             host_engine.FAST_NONE: ("FAST_NONE",)}
+    assert bench.DEFAULT_WORKLOAD == "detection_gap6_100Mx50"   # BASELINE.json configs[4], the metric's configuration
+    for name, wl in bench.WORKLOADS.items():
+        c = host_engine.fast_class(abi.make_nfa(wl["states"]), wl.get("flags", 0))
+        assert c >= 0, name
+        assert any(t in wl["kernel"] for t in label[c]), (name, c, wl["kernel"])
